@@ -1,0 +1,319 @@
+#!/usr/bin/env python
+"""bench.py — Mpoints/s encode+decode of 1M-point XYZI clouds (BASELINE.json configs[1] / C5 frame-sharded batch).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--frames F] [--impl ours|reference]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+One "step" = one pass of the hot path over a batch of F distinct synthetic 1M-point XYZI clouds per GPU (1 mm
+resolution, stage 1 only): one fused encode launch for the batch, then one fused decode of the blobs just produced.
+The pool of F clouds (F x 16 MB >> 126 MB L2) is device resident; `value` is whole-job points/s with inputs in HBM,
+`e2e` is the same metric through the host-pointer C ABI (pinned host buffers, H2D + D2H inside the timed region).
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+POINTS = 1_000_000
+WORKLOAD = "C2/C5: 1M-point synthetic XYZI float32x4 clouds, 1 mm, stage 1 only (compression NONE), frame-sharded batch"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--frames", type=int, default=32, help="distinct 1M-point clouds per GPU per step")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """Samples SM clocks / throttle reasons with nvidia-smi while the timed region runs (B200_PROFILING.md)."""
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for k, nme in enumerate(names):
+                    if r[4 + k].lower().startswith("active"):
+                        reasons.add(nme)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+        except Exception:
+            pass
+    return 6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
+
+
+def cpu_reference_numbers(oracle, info, cloud, blob, seconds, threads):
+    """Times the CPU path on a bounded sample: `reps` encode + decode passes of one 1M-point cloud per thread."""
+    t1, _ = oracle.time_encode(info, cloud, 1, 1)
+    t2 = oracle.time_decode(blob, 1, 1)
+    reps = max(2, int(seconds / max(t1 + t2, 1e-3)))
+    te, _ = oracle.time_encode(info, cloud, reps, threads)
+    td = oracle.time_decode(blob, reps, threads)
+    pts = reps * threads * POINTS
+    return {"enc_mpts": pts / te / 1e6, "dec_mpts": pts / td / 1e6, "rt_mpts": pts / (te + td) / 1e6,
+            "sample": f"{reps} x {threads} encode+decode passes of one 1M-point XYZI cloud ({(te + td):.1f} s)", "seconds": te + td}
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU implementation on all host threads (rank 0 only)."""
+    if rank != 0:
+        return
+    import cloudini_b200 as cb  # host helpers only (YAML text for the oracle); no kernels involved
+    from cloudini_b200 import synth
+    from oracle.client import best_oracle
+    oracle = best_oracle()
+    info, cloud = synth.cloud_c2(POINTS, seed=2)
+    blob = oracle.encode(info, cloud)
+    threads = os.cpu_count() or 1
+    steps = []
+    per_step_seconds = max(2.0, min(20.0, 120.0 / max(args.steps + args.warmup, 1)))
+    for s in range(args.warmup + args.steps):
+        r = cpu_reference_numbers(oracle, info, cloud, blob, per_step_seconds / max(threads, 1) * 1.0, threads)
+        if s >= args.warmup:
+            steps.append(r)
+    rt = float(np.mean([r["rt_mpts"] for r in steps]))
+    ms = float(np.mean([r["seconds"] for r in steps])) * 1e3
+    line = {
+        "impl": "reference", "metric": "Mpoints/s encode+decode (1M-pt XYZI, 1mm res)", "value": rt, "unit": "Mpoints/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32->i32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "impl_detail": f"{oracle.kind} CPU path, {threads} host threads, one encoder instance per thread"},
+        "cpu_baseline": {"value": rt, "unit": "Mpoints/s", "cores": threads, "kind": oracle.kind, "sample": steps[-1]["sample"],
+                         "encode_mpts": float(np.mean([r["enc_mpts"] for r in steps])), "decode_mpts": float(np.mean([r["dec_mpts"] for r in steps]))},
+        "e2e": {"value": rt, "unit": "Mpoints/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import cloudini_b200 as cb
+    from cloudini_b200 import synth
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — cloudini_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    distributed = world > 1
+    if distributed:
+        dist.init_process_group("nccl", device_id=dev)
+
+    F = args.frames
+    info = synth.info_xyzi(POINTS)
+    stream = torch.cuda.current_stream()
+    enc = cb.PointcloudEncoder(info, device=local_rank, stream=stream.cuda_stream)
+    dec = cb.PointcloudDecoder(device=local_rank, stream=stream.cuda_stream)
+
+    # ---- pool of F distinct clouds per rank (seeds 1000 + rank*64 + k), device resident ----
+    host_clouds = [synth.cloud_c2(POINTS, seed=1000 + rank * 64 + k)[1] for k in range(F)]
+    d_in = [torch.from_numpy(c).to(dev) for c in host_clouds]
+    cap = cb.MaxCompressedSize(info, POINTS, True)
+    d_blob = [torch.empty(cap, dtype=torch.uint8, device=dev) for _ in range(F)]
+    d_out = [torch.zeros(POINTS * 16, dtype=torch.uint8, device=dev) for _ in range(F)]
+    ebatch = enc.make_device_batch([t.data_ptr() for t in d_in], [POINTS * 16] * F, [t.data_ptr() for t in d_blob], [cap] * F)
+    sizes = enc.encode_batch_device(ebatch, write_header=True, want_sizes=True)
+    hdr = len(enc.getHeader())
+    dbatch = dec.make_device_batch([t.data_ptr() + hdr for t in d_blob], [s - hdr for s in sizes], [t.data_ptr() for t in d_out], [POINTS * 16] * F)
+    dec.decode_batch_device(info, dbatch, sync=True)
+
+    # ---- parity spot check inside the bench (checker only): frame 0 against the oracle ----
+    parity = "unchecked"
+    if rank == 0:
+        try:
+            from oracle.client import best_oracle
+            oracle = best_oracle()
+            expect = oracle.encode(info, host_clouds[0])
+            got = bytes(d_blob[0][:sizes[0]].cpu().numpy())
+            want = np.zeros(POINTS * 16, dtype=np.uint8)
+            oracle.decode(expect, want)
+            parity = "bit-exact" if (got == expect and np.array_equal(d_out[0].cpu().numpy(), want)) else "MISMATCH"
+        except Exception as e:  # the oracle is a checker; its absence must not turn into a fake number
+            parity = f"oracle unavailable: {e}"
+        if parity == "MISMATCH":
+            raise SystemExit("bench.py: GPU output differs from the oracle — refusing to report a number")
+
+    def barrier():
+        torch.cuda.synchronize()
+        if distributed:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def device_step(ev=None):
+        if ev:
+            ev[0].record()
+        enc.encode_batch_device(ebatch, write_header=True)
+        if ev:
+            ev[1].record()
+        dec.decode_batch_device(info, dbatch, sync=False)
+        if ev:
+            ev[2].record()
+
+    for _ in range(args.warmup):
+        device_step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = cb.kernel_launch_count()
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    t_start = torch.cuda.Event(enable_timing=True)
+    t_end = torch.cuda.Event(enable_timing=True)
+    t_start.record()
+    for s in range(args.steps):
+        device_step(evs[s])
+    t_end.record()
+    barrier()
+    launches = cb.kernel_launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    enc.sync()
+    dec.sync()
+    elapsed_ms = t_start.elapsed_time(t_end)
+    enc_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in evs]))
+    dec_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in evs]))
+
+    # ---- end-to-end through the host-pointer C ABI (pinned host memory, copies inside the timed region) ----
+    e2e = None
+    if not args.no_e2e:
+        Fe = min(F, 8)
+        h_in = [torch.from_numpy(host_clouds[k]).pin_memory() for k in range(Fe)]
+        h_blob = [torch.empty(cap, dtype=torch.uint8).pin_memory() for _ in range(Fe)]
+        h_out = [torch.zeros(POINTS * 16, dtype=torch.uint8).pin_memory() for _ in range(Fe)]
+        henc = cb.PointcloudEncoder(info, device=local_rank)
+        hdec = cb.PointcloudDecoder(device=local_rank)
+
+        def host_step():
+            w = henc.encode_batch_host(h_in, h_blob, write_header=True)
+            hdec.decode_batch_host(info, [b[hdr:n] for b, n in zip(h_blob, w)], h_out)
+            return w
+
+        w = None
+        for _ in range(max(args.warmup, 3)):
+            w = host_step()
+        barrier()
+        t0 = time.perf_counter()
+        e2e_steps = max(3, min(args.steps, 10))
+        for _ in range(e2e_steps):
+            host_step()
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+        if rank == 0 and parity == "bit-exact":
+            assert np.array_equal(h_out[0].numpy(), d_out[0].cpu().numpy()), "host path differs from device path"
+        blob_bytes = int(sum(w))
+        e2e = {"seconds": e2e_s, "steps": e2e_steps, "frames": Fe, "h2d": Fe * POINTS * 16 + blob_bytes - Fe * hdr, "d2h": blob_bytes + Fe * POINTS * 16}
+
+    # ---- reduce over ranks: time = max, points = sum ----
+    stats = torch.tensor([elapsed_ms, enc_ms, dec_ms, e2e["seconds"] if e2e else 0.0], dtype=torch.float64, device=dev)
+    if distributed:
+        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
+    elapsed_ms, enc_ms_max, dec_ms_max, e2e_s_max = [float(x) for x in stats.tolist()]
+    total_points = world * F * POINTS * args.steps
+    value = total_points / (elapsed_ms * 1e-3) / 1e6
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        stage1_bytes = float(np.mean(sizes)) - hdr                      # S: stage-1 bytes incl. the u32 chunk prefixes
+        algo_bytes = F * (POINTS * 16 + stage1_bytes)                    # encode: read N*point_step once + write S once
+        achieved = algo_bytes / (enc_ms * 1e-3) / 1e9
+        dec_achieved = algo_bytes / (dec_ms * 1e-3) / 1e9
+        line = {
+            "metric": "Mpoints/s encode+decode (1M-pt XYZI, 1mm res)", "value": value, "unit": "Mpoints/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32->i32 (quantise) / u8 (varint stream)", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "frames_per_gpu_per_step": F, "points_per_frame": POINTS, "point_step": 16,
+                       "stage1_bytes_per_point": stage1_bytes / POINTS, "cache": "inputs larger than L2 (pool of %d x 16 MB per GPU)" % F,
+                       "parallelism": f"frame-sharded x{world}, no data-path collective", "parity": parity,
+                       "encode_mpts": world * F * POINTS / (enc_ms_max * 1e-3) / 1e6, "decode_mpts": world * F * POINTS / (dec_ms_max * 1e-3) / 1e6,
+                       "encode_ms_per_step": enc_ms, "decode_ms_per_step": dec_ms},
+            "roofline": {"bound": "hbm", "kernel": "encode_floatn_kernel<4,8,vec4> (quantise+delta+varint+pack)", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": algo_bytes, "launch_ms": enc_ms,
+                         "decode": {"achieved": dec_achieved, "frac": dec_achieved / peak, "launch_ms": dec_ms}},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+        }
+        if e2e:
+            e2e_pts = world * e2e["frames"] * POINTS * e2e["steps"]
+            line["e2e"] = {"value": e2e_pts / e2e_s_max / 1e6, "unit": "Mpoints/s", "h2d_bytes_per_step": int(e2e["h2d"]),
+                           "d2h_bytes_per_step": int(e2e["d2h"]), "frames_per_step": e2e["frames"],
+                           "api": "cldn_b200_encode_batch + cldn_b200_decode_batch, CLDN_MEM_HOST, pinned host buffers"}
+        # ---- CPU baseline on this box's host cores (rank 0, N=1 only): bounded sample ----
+        if world == 1:
+            try:
+                from oracle.client import best_oracle
+                oracle = best_oracle()
+                blob0 = oracle.encode(info, host_clouds[0])
+                r = cpu_reference_numbers(oracle, info, host_clouds[0], blob0, args.cpu_seconds, 1)
+                line["cpu_baseline"] = {"value": r["rt_mpts"], "unit": "Mpoints/s", "cores": 1, "kind": oracle.kind, "sample": r["sample"],
+                                        "encode_mpts": r["enc_mpts"], "decode_mpts": r["dec_mpts"], "host_cores_available": os.cpu_count()}
+            except Exception as e:
+                line["cpu_baseline"] = {"value": None, "unit": "Mpoints/s", "cores": 0, "kind": "unavailable", "sample": str(e)}
+        print(json.dumps(line), flush=True)
+    if distributed:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,696 @@
+// C-ABI layer: handles, device memory, stream plumbing and kernel launches. See include/cloudini_b200.h.
+// There is deliberately no CPU implementation of the codec here: if CUDA is unavailable every compute entry point
+// fails with CLDN_ERR_CUDA.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "cldn_device.cuh"
+#include "cldn_kernels.h"
+#include "cldn_plan.h"
+
+namespace cldn {
+std::string info_to_yaml(const cldn_info_t& info);
+int info_from_yaml(const char* yaml, size_t len, cldn_info_t* info);
+size_t max_compressed_size(const cldn_info_t& info, size_t points, bool include_header, bool* ok);
+std::vector<uint8_t> make_header(const cldn_info_t& info);
+}  // namespace cldn
+
+using namespace cldn;
+
+#define CUDA_TRY(expr)                                                                          \
+  do {                                                                                          \
+    cudaError_t e__ = (expr);                                                                   \
+    if (e__ != cudaSuccess) {                                                                   \
+      set_error("CUDA error %s at %s:%d: %s", cudaGetErrorName(e__), __FILE__, __LINE__, cudaGetErrorString(e__)); \
+      return CLDN_ERR_CUDA;                                                                     \
+    }                                                                                           \
+  } while (0)
+
+namespace {
+
+// Grow-only device / pinned-host buffers.
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t cap = 0;
+  int reserve(size_t n, bool zero = false) {
+    if (n <= cap) return CLDN_OK;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = std::max<size_t>(n, 16);
+    CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&p), want * sizeof(T)));
+    cap = want;
+    if (zero) CUDA_TRY(cudaMemset(p, 0, want * sizeof(T)));
+    return CLDN_OK;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+template <typename T>
+struct PinBuf {
+  T* p = nullptr;
+  size_t cap = 0;
+  int reserve(size_t n) {
+    if (n <= cap) return CLDN_OK;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = std::max<size_t>(n, 16);
+    CUDA_TRY(cudaMallocHost(reinterpret_cast<void**>(&p), want * sizeof(T)));
+    cap = want;
+    return CLDN_OK;
+  }
+  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+// Ring of pinned upload slots: a slot is only rewritten by the host after the async copy that read it has completed
+// (back-to-back asynchronous batch calls would otherwise race on a single pinned table).
+template <typename T, int SLOTS = 8>
+struct PinRing {
+  PinBuf<T> slot[SLOTS];
+  cudaEvent_t ev[SLOTS] = {};
+  bool used[SLOTS] = {};
+  int next = 0;
+  // returns a host pointer with room for n elements
+  int acquire(size_t n, T** out, int* idx) {
+    const int i = next;
+    next = (next + 1) % SLOTS;
+    if (used[i]) CUDA_TRY(cudaEventSynchronize(ev[i]));
+    if (!ev[i]) CUDA_TRY(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
+    if (int rc = slot[i].reserve(n)) return rc;
+    *out = slot[i].p;
+    *idx = i;
+    return CLDN_OK;
+  }
+  int commit(int idx, cudaStream_t stream) {
+    CUDA_TRY(cudaEventRecord(ev[idx], stream));
+    used[idx] = true;
+    return CLDN_OK;
+  }
+  void release() {
+    for (int i = 0; i < SLOTS; ++i) {
+      slot[i].release();
+      if (ev[i]) cudaEventDestroy(ev[i]);
+      ev[i] = nullptr;
+      used[i] = false;
+    }
+  }
+};
+
+int select_device(int device) {
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    set_error("no CUDA device available (%s): cloudini_b200 has no CPU fallback", e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    return CLDN_ERR_CUDA;
+  }
+  if (device >= 0) CUDA_TRY(cudaSetDevice(device));
+  return CLDN_OK;
+}
+
+const char* dev_error_text(uint32_t code) {
+  switch (code) {
+    case DEV_ERR_TRUNCATED: return "Truncated encoded data: not enough bytes for a complete point";
+    case DEV_ERR_VARINT_OVERFLOW: return "decodeVarint: value overflow";
+    case DEV_ERR_NAN_MARKER: return "decodeVarint: unexpected NaN marker";
+    case DEV_ERR_TRAILING: return "V5 chunk has trailing bytes after decode";
+    case DEV_ERR_BAD_MODE: return "V5 adaptive int: missing or unknown mode byte";
+    case DEV_ERR_PALETTE: return "V5 adaptive int: bad palette section";
+    case DEV_ERR_RLE: return "V5 adaptive int: bad run-length section";
+    case DEV_ERR_CHUNK_SIZE: return "Invalid chunk size found while decoding";
+    case DEV_ERR_CHUNK_COUNT: return "Encoded data does not match the declared number of points (chunk count)";
+    case DEV_ERR_OUTPUT_SMALL: return "Output buffer is too small to hold the decoded data";
+    default: return "unknown device error";
+  }
+}
+
+}  // namespace
+
+// =====================================================================================================================
+struct cldn_encoder {
+  cldn_info_t info;
+  Plan plan;
+  std::vector<uint8_t> header;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  uint32_t tile_points = 0;
+  uint32_t epoch = 0;
+
+  DevBuf<Plan> d_plan;
+  DevBuf<uint8_t> d_header;
+  DevBuf<uint64_t> d_status;
+  DevBuf<EncFrame> d_frames;
+  PinRing<EncFrame> h_frames;
+  DevBuf<uint64_t> d_sizes;
+  PinBuf<uint64_t> h_sizes;
+  DevBuf<uint32_t> d_err;
+  PinBuf<uint32_t> h_err;
+  // host-memory path staging
+  DevBuf<uint8_t> d_in, d_out;
+  // V5 section scratch
+  DevBuf<uint8_t> d_modes;
+  DevBuf<uint8_t> d_sec_scratch;
+  DevBuf<uint32_t> d_sec_sizes;
+  DevBuf<uint32_t> d_sec_excl;
+  DevBuf<uint32_t> d_chunk_frame;
+  PinRing<uint32_t> h_chunk_frame;
+  DevBuf<uint64_t> d_hash;
+  size_t last_frames = 0;
+};
+
+extern "C" {
+
+uint64_t cldn_b200_kernel_launch_count(void) { return kernel_launch_count(); }
+
+int cldn_b200_encoder_create(const cldn_info_t* info, int device, void* stream, cldn_encoder_t** out) {
+  if (!info || !out) { set_error("null argument"); return CLDN_ERR_INVALID_ARGUMENT; }
+  *out = nullptr;
+  Plan plan;
+  if (int rc = build_encode_plan(*info, &plan)) return rc;
+  if (!plan.supported) {
+    set_error("EncodingInfo needs a lossless float encoder (XOR / Gorilla) that this build does not accelerate");
+    return CLDN_ERR_UNSUPPORTED;
+  }
+  if (info->compression_opt != CLDN_COMP_NONE) {
+    set_error("compression_opt %d: stage 2 (LZ4/ZSTD) is delegated and not executed by this library; use NONE",
+              static_cast<int>(info->compression_opt));
+    return CLDN_ERR_UNSUPPORTED;
+  }
+  if (plan.n_sections > 0 && !(plan.floatn_only || plan.n_ops == 0)) {
+    set_error("V5 clouds whose regular stream holds more than the leading XYZ(I) group are not accelerated in this build");
+    return CLDN_ERR_UNSUPPORTED;
+  }
+  if (int rc = select_device(device)) return rc;
+  cldn_encoder* e = new cldn_encoder();
+  e->info = *info;
+  e->plan = plan;
+  e->header = make_header(*info);
+  cudaGetDevice(&e->device);
+  e->tile_points = choose_tile_points(plan);
+  if (stream) {
+    e->stream = static_cast<cudaStream_t>(stream);
+  } else {
+    if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) {
+      set_error("cudaStreamCreate failed");
+      delete e;
+      return CLDN_ERR_CUDA;
+    }
+    e->own_stream = true;
+  }
+  int rc = e->d_plan.reserve(1);
+  if (!rc) rc = e->d_header.reserve(e->header.size());
+  if (!rc) rc = e->d_err.reserve(1, true);
+  if (!rc) rc = e->h_err.reserve(1);
+  if (!rc) {
+    cudaError_t ce = cudaMemcpy(e->d_plan.p, &e->plan, sizeof(Plan), cudaMemcpyHostToDevice);
+    if (ce == cudaSuccess) ce = cudaMemcpy(e->d_header.p, e->header.data(), e->header.size(), cudaMemcpyHostToDevice);
+    if (ce != cudaSuccess) { set_error("cudaMemcpy failed: %s", cudaGetErrorString(ce)); rc = CLDN_ERR_CUDA; }
+  }
+  if (rc) { cldn_b200_encoder_destroy(e); return rc; }
+  *out = e;
+  return CLDN_OK;
+}
+
+void cldn_b200_encoder_destroy(cldn_encoder_t* e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  if (e->stream) cudaStreamSynchronize(e->stream);
+  e->d_plan.release(); e->d_header.release(); e->d_status.release(); e->d_frames.release(); e->h_frames.release();
+  e->d_sizes.release(); e->h_sizes.release(); e->d_err.release(); e->h_err.release(); e->d_in.release(); e->d_out.release();
+  e->d_modes.release(); e->d_sec_scratch.release(); e->d_sec_sizes.release(); e->d_sec_excl.release();
+  e->d_chunk_frame.release(); e->h_chunk_frame.release(); e->d_hash.release();
+  if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
+  delete e;
+}
+
+int cldn_b200_encoder_header(const cldn_encoder_t* enc, const uint8_t** header, size_t* header_bytes) {
+  if (!enc) { set_error("null encoder"); return CLDN_ERR_INVALID_ARGUMENT; }
+  if (header) *header = enc->header.data();
+  if (header_bytes) *header_bytes = enc->header.size();
+  return CLDN_OK;
+}
+
+const uint64_t* cldn_b200_encoder_sizes_device(const cldn_encoder_t* enc) { return enc ? enc->d_sizes.p : nullptr; }
+
+static int check_device_error(cudaStream_t stream, uint32_t* d_err, uint32_t* h_err) {
+  CUDA_TRY(cudaMemcpyAsync(h_err, d_err, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+  CUDA_TRY(cudaStreamSynchronize(stream));
+  if (*h_err != DEV_OK) {
+    const uint32_t code = *h_err;
+    cudaMemsetAsync(d_err, 0, sizeof(uint32_t), stream);
+    set_error("%s", dev_error_text(code));
+    return CLDN_ERR_CORRUPT_DATA;
+  }
+  return CLDN_OK;
+}
+
+int cldn_b200_encoder_sync(cldn_encoder_t* e) {
+  if (!e) { set_error("null encoder"); return CLDN_ERR_INVALID_ARGUMENT; }
+  CUDA_TRY(cudaSetDevice(e->device));
+  return check_device_error(e->stream, e->d_err.p, e->h_err.p);
+}
+
+// Enqueues the kernels for a batch whose inputs/outputs are device pointers.
+static int encode_batch_device(cldn_encoder* e, size_t n_frames, const void* const* clouds, const size_t* cloud_bytes,
+                               void* const* outs, const size_t* out_capacities, int write_header) {
+  const cldn_info_t& info = e->info;
+  if (info.point_step == 0) { set_error("point_step cannot be 0"); return CLDN_ERR_INVALID_ARGUMENT; }  // cloudini.cpp:523-525
+  EncFrame* hf = nullptr;
+  int hf_slot = 0;
+  if (int rc = e->h_frames.acquire(n_frames, &hf, &hf_slot)) return rc;
+  if (int rc = e->d_frames.reserve(n_frames)) return rc;
+  if (int rc = e->d_sizes.reserve(n_frames)) return rc;
+  const uint32_t T = e->tile_points;
+  const size_t hdr = write_header ? e->header.size() : 0;
+  uint64_t tiles = 0, chunks = 0;
+  bool aligned16 = true;
+  for (size_t f = 0; f < n_frames; ++f) {
+    if (cloud_bytes[f] % info.point_step != 0) {
+      set_error("Input cloud_data size is not a multiple of point_step");  // cloudini.cpp:526-528
+      return CLDN_ERR_INVALID_ARGUMENT;
+    }
+    const size_t n = cloud_bytes[f] / info.point_step;
+    if (n > 0xFFFFFFFFull) { set_error("too many points in one frame"); return CLDN_ERR_UNSUPPORTED; }
+    bool ok;
+    const size_t need = max_compressed_size(info, n, false, &ok) + hdr;  // cloudini.cpp:530-534
+    if (!ok) return CLDN_ERR_INVALID_ARGUMENT;
+    if (out_capacities[f] < need) {
+      set_error("Output buffer too small for worst-case compressed size");
+      return CLDN_ERR_BUFFER_TOO_SMALL;
+    }
+    if (n > 0 && (!clouds[f] || !outs[f])) { set_error("null frame pointer"); return CLDN_ERR_INVALID_ARGUMENT; }
+    EncFrame& F = hf[f];
+    F.in = static_cast<const uint8_t*>(clouds[f]);
+    F.out = static_cast<uint8_t*>(outs[f]);
+    F.n_points = static_cast<uint32_t>(n);
+    F.tile_begin = static_cast<uint32_t>(tiles);
+    F.n_tiles = static_cast<uint32_t>((n + T - 1) / T);
+    F.n_chunks = static_cast<uint32_t>((n + kChunkPoints - 1) / kChunkPoints);
+    F.sec_excl = nullptr;
+    tiles += F.n_tiles;
+    chunks += F.n_chunks;
+    if (reinterpret_cast<uintptr_t>(clouds[f]) & 15u) aligned16 = false;
+  }
+  if (tiles > 0x7FFFFFFFull) { set_error("batch too large"); return CLDN_ERR_UNSUPPORTED; }
+  if (int rc = e->d_status.reserve(static_cast<size_t>(tiles) + 1, true)) return rc;
+  e->epoch = (e->epoch + 1) & 0x3FFFFFu;
+  if (e->epoch == 0) {  // epoch wrapped: stale words could alias
+    CUDA_TRY(cudaMemsetAsync(e->d_status.p, 0, e->d_status.cap * sizeof(uint64_t), e->stream));
+    e->epoch = 1;
+  }
+  EncLaunch L;
+  L.frames = e->d_frames.p;
+  L.n_frames = static_cast<uint32_t>(n_frames);
+  L.n_tiles_total = static_cast<uint32_t>(tiles);
+  L.plan = e->d_plan.p;
+  L.header = e->d_header.p;
+  L.header_bytes = static_cast<uint32_t>(hdr);
+  L.status = e->d_status.p;
+  L.epoch = e->epoch;
+  L.sizes = e->d_sizes.p;
+  L.err = e->d_err.p;
+  L.tile_points = T;
+  L.flags = aligned16 ? kEncInputsAligned16 : 0u;
+
+  if (e->plan.n_sections > 0) {
+    // V5: adaptive integer sections are produced first (they determine where every later chunk starts).
+    const uint32_t ns = e->plan.n_sections;
+    const uint32_t stride = 16 + kChunkPoints * 11u;  // worst case of any mode: <= 1+4 + n*(10+1) bytes
+    if (int rc = e->d_modes.reserve(n_frames * ns)) return rc;
+    if (int rc = e->d_sec_scratch.reserve(static_cast<size_t>(chunks) * ns * stride)) return rc;
+    if (int rc = e->d_sec_sizes.reserve(static_cast<size_t>(chunks) * ns + 1)) return rc;
+    if (int rc = e->d_sec_excl.reserve(static_cast<size_t>(chunks) + n_frames + 1)) return rc;
+    uint32_t* hcf = nullptr;
+    int hcf_slot = 0;
+    if (int rc = e->h_chunk_frame.acquire(static_cast<size_t>(chunks) + n_frames + 1, &hcf, &hcf_slot)) return rc;
+    if (int rc = e->d_chunk_frame.reserve(static_cast<size_t>(chunks) + n_frames + 1)) return rc;
+    if (int rc = e->d_hash.reserve(static_cast<size_t>(chunks) * 65536u * 2u)) return rc;
+    uint32_t cb = 0;
+    for (size_t f = 0; f < n_frames; ++f) {
+      EncFrame& F = hf[f];
+      F.sec_excl = e->d_sec_excl.p + cb + f;  // (n_chunks + 1) entries per frame
+      for (uint32_t c = 0; c < F.n_chunks; ++c) hcf[cb + c] = static_cast<uint32_t>(f);
+      hcf[chunks + f] = cb;  // chunk_first[f]
+      cb += F.n_chunks;
+    }
+    CUDA_TRY(cudaMemcpyAsync(e->d_chunk_frame.p, hcf, (chunks + n_frames) * sizeof(uint32_t), cudaMemcpyHostToDevice, e->stream));
+    if (int rc = e->h_chunk_frame.commit(hcf_slot, e->stream)) return rc;
+    CUDA_TRY(cudaMemcpyAsync(e->d_frames.p, hf, n_frames * sizeof(EncFrame), cudaMemcpyHostToDevice, e->stream));
+    if (int rc = e->h_frames.commit(hf_slot, e->stream)) return rc;
+    SecLaunch S;
+    S.frames = e->d_frames.p;
+    S.n_frames = static_cast<uint32_t>(n_frames);
+    S.n_chunks_total = static_cast<uint32_t>(chunks);
+    S.chunk_frame = e->d_chunk_frame.p;
+    S.chunk_first = e->d_chunk_frame.p + chunks;
+    S.plan = e->d_plan.p;
+    S.modes = e->d_modes.p;
+    S.scratch = e->d_sec_scratch.p;
+    S.sec_stride = stride;
+    S.sec_sizes = e->d_sec_sizes.p;
+    S.sec_excl = e->d_sec_excl.p;
+    S.hash_scratch = e->d_hash.p;
+    S.err = e->d_err.p;
+    S.header_bytes = static_cast<uint32_t>(hdr);
+    if (launch_encode_sections(e->plan, S, e->stream) < 0) { set_error("section kernel launch failed"); return CLDN_ERR_CUDA; }
+    if (launch_encode_regular(e->plan, L, e->stream) < 0) { set_error("encode kernel launch failed"); return CLDN_ERR_CUDA; }
+    if (launch_place_sections(e->plan, S, e->d_status.p, e->epoch, T, e->stream) < 0) { set_error("section placement launch failed"); return CLDN_ERR_CUDA; }
+  } else {
+    CUDA_TRY(cudaMemcpyAsync(e->d_frames.p, hf, n_frames * sizeof(EncFrame), cudaMemcpyHostToDevice, e->stream));
+    if (int rc = e->h_frames.commit(hf_slot, e->stream)) return rc;
+    if (launch_encode_regular(e->plan, L, e->stream) < 0) { set_error("encode kernel launch failed"); return CLDN_ERR_CUDA; }
+  }
+  CUDA_TRY(cudaGetLastError());
+  e->last_frames = n_frames;
+  return CLDN_OK;
+}
+
+int cldn_b200_encode_batch(cldn_encoder_t* e, size_t n_frames, const void* const* clouds, const size_t* cloud_bytes,
+                           void* const* outs, const size_t* out_capacities, int write_header, size_t* written_host,
+                           int mem) {
+  if (!e || (n_frames && (!clouds || !cloud_bytes || !outs || !out_capacities))) {
+    set_error("null argument");
+    return CLDN_ERR_INVALID_ARGUMENT;
+  }
+  if (n_frames == 0) return CLDN_OK;
+  CUDA_TRY(cudaSetDevice(e->device));
+  if (mem == CLDN_MEM_DEVICE) {
+    if (int rc = encode_batch_device(e, n_frames, clouds, cloud_bytes, outs, out_capacities, write_header)) return rc;
+    if (written_host) {
+      if (int rc = e->h_sizes.reserve(n_frames)) return rc;
+      CUDA_TRY(cudaMemcpyAsync(e->h_sizes.p, e->d_sizes.p, n_frames * sizeof(uint64_t), cudaMemcpyDeviceToHost, e->stream));
+      if (int rc = check_device_error(e->stream, e->d_err.p, e->h_err.p)) return rc;
+      for (size_t f = 0; f < n_frames; ++f) written_host[f] = static_cast<size_t>(e->h_sizes.p[f]);
+    }
+    return CLDN_OK;
+  }
+  if (mem != CLDN_MEM_HOST) { set_error("bad mem kind"); return CLDN_ERR_INVALID_ARGUMENT; }
+  // ---- host path: H2D -> kernels -> D2H (sizes first, then exactly the encoded bytes) ----
+  size_t in_total = 0, out_total = 0;
+  std::vector<size_t> in_off(n_frames), out_off(n_frames), caps(n_frames);
+  const size_t hdr = write_header ? e->header.size() : 0;
+  for (size_t f = 0; f < n_frames; ++f) {
+    if (e->info.point_step == 0) { set_error("point_step cannot be 0"); return CLDN_ERR_INVALID_ARGUMENT; }
+    if (cloud_bytes[f] % e->info.point_step != 0) { set_error("Input cloud_data size is not a multiple of point_step"); return CLDN_ERR_INVALID_ARGUMENT; }
+    bool ok;
+    const size_t need = max_compressed_size(e->info, cloud_bytes[f] / e->info.point_step, false, &ok) + hdr;
+    if (!ok) return CLDN_ERR_INVALID_ARGUMENT;
+    if (out_capacities[f] < need) { set_error("Output buffer too small for worst-case compressed size"); return CLDN_ERR_BUFFER_TOO_SMALL; }
+    in_off[f] = in_total;
+    in_total += (cloud_bytes[f] + 255) & ~size_t(255);
+    out_off[f] = out_total;
+    caps[f] = need;
+    out_total += (need + 255) & ~size_t(255);
+  }
+  if (int rc = e->d_in.reserve(in_total + 256)) return rc;
+  if (int rc = e->d_out.reserve(out_total + 256)) return rc;
+  std::vector<const void*> din(n_frames);
+  std::vector<void*> dout(n_frames);
+  for (size_t f = 0; f < n_frames; ++f) {
+    din[f] = e->d_in.p + in_off[f];
+    dout[f] = e->d_out.p + out_off[f];
+    if (cloud_bytes[f]) CUDA_TRY(cudaMemcpyAsync(e->d_in.p + in_off[f], clouds[f], cloud_bytes[f], cudaMemcpyHostToDevice, e->stream));
+  }
+  if (int rc = encode_batch_device(e, n_frames, din.data(), cloud_bytes, dout.data(), caps.data(), write_header)) return rc;
+  if (int rc = e->h_sizes.reserve(n_frames)) return rc;
+  CUDA_TRY(cudaMemcpyAsync(e->h_sizes.p, e->d_sizes.p, n_frames * sizeof(uint64_t), cudaMemcpyDeviceToHost, e->stream));
+  if (int rc = check_device_error(e->stream, e->d_err.p, e->h_err.p)) return rc;
+  for (size_t f = 0; f < n_frames; ++f) {
+    const size_t sz = static_cast<size_t>(e->h_sizes.p[f]);
+    if (sz > out_capacities[f]) { set_error("internal: encoded size exceeds capacity"); return CLDN_ERR_INTERNAL; }
+    if (sz) CUDA_TRY(cudaMemcpyAsync(outs[f], e->d_out.p + out_off[f], sz, cudaMemcpyDeviceToHost, e->stream));
+    if (written_host) written_host[f] = sz;
+  }
+  CUDA_TRY(cudaStreamSynchronize(e->stream));
+  return CLDN_OK;
+}
+
+int cldn_b200_encode(cldn_encoder_t* enc, const void* cloud, size_t cloud_bytes, void* out, size_t out_capacity,
+                     int write_header, size_t* written, int mem) {
+  const void* clouds[1] = {cloud};
+  void* outs[1] = {out};
+  return cldn_b200_encode_batch(enc, 1, clouds, &cloud_bytes, outs, &out_capacity, write_header, written, mem);
+}
+
+}  // extern "C"
+
+// =====================================================================================================================
+struct cldn_decoder {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  cldn_info_t info;  // info of the cached plan
+  bool have_plan = false;
+  Plan plan;
+  bool has_padding = false;
+  DevBuf<Plan> d_plan;
+  DevBuf<DecFrame> d_frames;
+  PinRing<DecFrame> h_frames;
+  DevBuf<uint64_t> d_chunk_offsets;
+  DevBuf<uint32_t> d_chunk_sizes;
+  DevBuf<uint32_t> d_err;
+  PinBuf<uint32_t> h_err;
+  DevBuf<uint8_t> d_in, d_out;
+};
+
+static bool same_info(const cldn_info_t& a, const cldn_info_t& b) {
+  if (a.width != b.width || a.height != b.height || a.point_step != b.point_step || a.encoding_opt != b.encoding_opt ||
+      a.compression_opt != b.compression_opt || a.version != b.version || a.n_fields != b.n_fields) return false;
+  for (uint32_t i = 0; i < a.n_fields; ++i) {
+    const cldn_field_t &x = a.fields[i], &y = b.fields[i];
+    if (x.offset != y.offset || x.type != y.type || x.has_resolution != y.has_resolution ||
+        (x.has_resolution && memcmp(&x.resolution, &y.resolution, 4) != 0)) return false;
+  }
+  return true;
+}
+
+// PointcloudDecoder::updateDecoders (cloudini.cpp:627-633)
+static int decoder_update_plan(cldn_decoder* d, const cldn_info_t& info) {
+  if (d->have_plan && same_info(d->info, info)) return CLDN_OK;
+  Plan plan;
+  if (int rc = build_decode_plan(info, &plan)) return rc;
+  if (!plan.supported) {
+    set_error("EncodingInfo needs a lossless float decoder (XOR / Gorilla) that this build does not accelerate");
+    return CLDN_ERR_UNSUPPORTED;
+  }
+  if (info.compression_opt != CLDN_COMP_NONE) {
+    set_error("compression_opt %d: stage 2 (LZ4/ZSTD) is delegated; decompress the chunks first", static_cast<int>(info.compression_opt));
+    return CLDN_ERR_UNSUPPORTED;
+  }
+  if (info.version < 3) { set_error("wire version %d (single unframed chunk) is not supported", info.version); return CLDN_ERR_UNSUPPORTED; }
+  if (plan.n_sections > 0 && !(plan.all_varint || plan.n_ops == 0)) {
+    set_error("V5 clouds whose regular stream mixes raw and varint fields are not accelerated in this build");
+    return CLDN_ERR_UNSUPPORTED;
+  }
+  if (int rc = d->d_plan.reserve(1)) return rc;
+  CUDA_TRY(cudaMemcpyAsync(d->d_plan.p, &plan, sizeof(Plan), cudaMemcpyHostToDevice, d->stream));
+  CUDA_TRY(cudaStreamSynchronize(d->stream));  // `plan` is a stack object
+  d->plan = plan;
+  d->info = info;
+  d->have_plan = true;
+  // do the declared fields cover every byte of a point? (otherwise host outputs must round-trip their padding)
+  std::vector<uint8_t> cover(info.point_step, 0);
+  for (uint32_t i = 0; i < info.n_fields; ++i) {
+    const int sz = size_of_type(info.fields[i].type);
+    for (int b = 0; b < sz; ++b) {
+      const uint64_t o = static_cast<uint64_t>(info.fields[i].offset) + b;
+      if (o < info.point_step) cover[o] = 1;
+    }
+  }
+  d->has_padding = std::find(cover.begin(), cover.end(), 0) != cover.end();
+  return CLDN_OK;
+}
+
+static int decode_batch_device(cldn_decoder* d, const cldn_info_t& info, size_t n_frames, const void* const* payloads,
+                               const size_t* payload_bytes, void* const* outs, const size_t* out_capacities) {
+  if (int rc = decoder_update_plan(d, info)) return rc;
+  const uint64_t n_points = static_cast<uint64_t>(info.width) * info.height;
+  if (n_points > 0xFFFFFFFFull) { set_error("too many points"); return CLDN_ERR_UNSUPPORTED; }
+  const uint64_t out_need = n_points * info.point_step;
+  DecFrame* hf = nullptr;
+  int hf_slot = 0;
+  if (int rc = d->h_frames.acquire(n_frames, &hf, &hf_slot)) return rc;
+  if (int rc = d->d_frames.reserve(n_frames)) return rc;
+  uint64_t chunks = 0;
+  for (size_t f = 0; f < n_frames; ++f) {
+    if (out_capacities[f] < out_need) {
+      set_error("Output buffer is too small to hold the decoded data");  // v4_codec.cpp:93-95 / v5_codec.cpp:991-993
+      return CLDN_ERR_BUFFER_TOO_SMALL;
+    }
+    DecFrame& F = hf[f];
+    F.payload = static_cast<const uint8_t*>(payloads[f]);
+    F.payload_bytes = payload_bytes[f];
+    F.out = static_cast<uint8_t*>(outs[f]);
+    F.n_points = static_cast<uint32_t>(n_points);
+    F.n_chunks = static_cast<uint32_t>((n_points + kChunkPoints - 1) / kChunkPoints);
+    F.chunk_begin = static_cast<uint32_t>(chunks);
+    F.pad_ = 0;
+    chunks += F.n_chunks;
+  }
+  if (chunks > 0x7FFFFFFFull) { set_error("batch too large"); return CLDN_ERR_UNSUPPORTED; }
+  if (int rc = d->d_chunk_offsets.reserve(static_cast<size_t>(chunks) + 1)) return rc;
+  if (int rc = d->d_chunk_sizes.reserve(static_cast<size_t>(chunks) + 1)) return rc;
+  CUDA_TRY(cudaMemcpyAsync(d->d_frames.p, hf, n_frames * sizeof(DecFrame), cudaMemcpyHostToDevice, d->stream));
+  if (int rc = d->h_frames.commit(hf_slot, d->stream)) return rc;
+  DecLaunch L;
+  L.frames = d->d_frames.p;
+  L.n_frames = static_cast<uint32_t>(n_frames);
+  L.n_chunks_total = static_cast<uint32_t>(chunks);
+  L.plan = d->d_plan.p;
+  L.chunk_offsets = d->d_chunk_offsets.p;
+  L.chunk_sizes = d->d_chunk_sizes.p;
+  L.err = d->d_err.p;
+  if (launch_decode(d->plan, L, d->stream) < 0) { set_error("decode kernel launch failed"); return CLDN_ERR_CUDA; }
+  CUDA_TRY(cudaGetLastError());
+  return CLDN_OK;
+}
+
+extern "C" {
+
+int cldn_b200_decoder_create(int device, void* stream, cldn_decoder_t** out) {
+  if (!out) { set_error("null argument"); return CLDN_ERR_INVALID_ARGUMENT; }
+  *out = nullptr;
+  if (int rc = select_device(device)) return rc;
+  cldn_decoder* d = new cldn_decoder();
+  cudaGetDevice(&d->device);
+  if (stream) {
+    d->stream = static_cast<cudaStream_t>(stream);
+  } else {
+    if (cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking) != cudaSuccess) {
+      set_error("cudaStreamCreate failed");
+      delete d;
+      return CLDN_ERR_CUDA;
+    }
+    d->own_stream = true;
+  }
+  int rc = d->d_err.reserve(1, true);
+  if (!rc) rc = d->h_err.reserve(1);
+  if (rc) { cldn_b200_decoder_destroy(d); return rc; }
+  *out = d;
+  return CLDN_OK;
+}
+
+void cldn_b200_decoder_destroy(cldn_decoder_t* d) {
+  if (!d) return;
+  cudaSetDevice(d->device);
+  if (d->stream) cudaStreamSynchronize(d->stream);
+  d->d_plan.release(); d->d_frames.release(); d->h_frames.release(); d->d_chunk_offsets.release(); d->d_chunk_sizes.release();
+  d->d_err.release(); d->h_err.release(); d->d_in.release(); d->d_out.release();
+  if (d->own_stream && d->stream) cudaStreamDestroy(d->stream);
+  delete d;
+}
+
+int cldn_b200_decoder_sync(cldn_decoder_t* d) {
+  if (!d) { set_error("null decoder"); return CLDN_ERR_INVALID_ARGUMENT; }
+  CUDA_TRY(cudaSetDevice(d->device));
+  return check_device_error(d->stream, d->d_err.p, d->h_err.p);
+}
+
+int cldn_b200_decode_batch(cldn_decoder_t* d, const cldn_info_t* info, size_t n_frames, const void* const* payloads,
+                           const size_t* payload_bytes, void* const* outs, const size_t* out_capacities, int mem, int sync) {
+  if (!d || !info || (n_frames && (!payloads || !payload_bytes || !outs || !out_capacities))) {
+    set_error("null argument");
+    return CLDN_ERR_INVALID_ARGUMENT;
+  }
+  if (n_frames == 0) return CLDN_OK;
+  CUDA_TRY(cudaSetDevice(d->device));
+  if (mem == CLDN_MEM_DEVICE) {
+    if (int rc = decode_batch_device(d, *info, n_frames, payloads, payload_bytes, outs, out_capacities)) return rc;
+    if (sync) return check_device_error(d->stream, d->d_err.p, d->h_err.p);
+    return CLDN_OK;
+  }
+  if (mem != CLDN_MEM_HOST) { set_error("bad mem kind"); return CLDN_ERR_INVALID_ARGUMENT; }
+  // the reference rejects a payload that still carries the header (cloudini.cpp:640-643)
+  for (size_t f = 0; f < n_frames; ++f) {
+    if (payload_bytes[f] >= 10 && memcmp(payloads[f], "CLOUDINI_V", 10) == 0) {
+      set_error("compressed_data contains the header. You should use DecodeHeader first");
+      return CLDN_ERR_INVALID_ARGUMENT;
+    }
+  }
+  if (int rc = decoder_update_plan(d, *info)) return rc;
+  const size_t out_need = static_cast<size_t>(info->width) * info->height * info->point_step;
+  size_t in_total = 0;
+  std::vector<size_t> in_off(n_frames);
+  for (size_t f = 0; f < n_frames; ++f) {
+    if (out_capacities[f] < out_need) { set_error("Output buffer is too small to hold the decoded data"); return CLDN_ERR_BUFFER_TOO_SMALL; }
+    in_off[f] = in_total;
+    in_total += (payload_bytes[f] + 255) & ~size_t(255);
+  }
+  const size_t out_stride = (out_need + 255) & ~size_t(255);
+  if (int rc = d->d_in.reserve(in_total + 256)) return rc;
+  if (int rc = d->d_out.reserve(out_stride * n_frames + 256)) return rc;
+  std::vector<const void*> din(n_frames);
+  std::vector<void*> dout(n_frames);
+  std::vector<size_t> caps(n_frames, out_need);
+  for (size_t f = 0; f < n_frames; ++f) {
+    din[f] = d->d_in.p + in_off[f];
+    dout[f] = d->d_out.p + out_stride * f;
+    if (payload_bytes[f]) CUDA_TRY(cudaMemcpyAsync(d->d_in.p + in_off[f], payloads[f], payload_bytes[f], cudaMemcpyHostToDevice, d->stream));
+    // only declared field bytes are written by the decoder: keep the caller's padding bytes intact
+    if (d->has_padding && out_need) CUDA_TRY(cudaMemcpyAsync(dout[f], outs[f], out_need, cudaMemcpyHostToDevice, d->stream));
+  }
+  if (int rc = decode_batch_device(d, *info, n_frames, din.data(), payload_bytes, dout.data(), caps.data())) return rc;
+  if (int rc = check_device_error(d->stream, d->d_err.p, d->h_err.p)) return rc;
+  for (size_t f = 0; f < n_frames; ++f) {
+    if (out_need) CUDA_TRY(cudaMemcpyAsync(outs[f], dout[f], out_need, cudaMemcpyDeviceToHost, d->stream));
+  }
+  CUDA_TRY(cudaStreamSynchronize(d->stream));
+  return CLDN_OK;
+}
+
+int cldn_b200_decode(cldn_decoder_t* dec, const cldn_info_t* info, const void* payload, size_t payload_bytes, void* out,
+                     size_t out_capacity, int mem) {
+  const void* payloads[1] = {payload};
+  void* outs[1] = {out};
+  return cldn_b200_decode_batch(dec, info, 1, payloads, &payload_bytes, outs, &out_capacity, mem, 1);
+}
+
+// ---- one-shot helpers shaped like the reference's WASM C ABI ------------------------------------------------------
+uint32_t cldn_b200_EncodePointcloudData(const char* header_as_yaml, const void* pc_data, uint32_t pc_data_size,
+                                        void* output_data, uint32_t output_capacity) {
+  if (!header_as_yaml || !output_data) { set_error("null argument"); return 0; }
+  cldn_info_t info;
+  if (info_from_yaml(header_as_yaml, strlen(header_as_yaml), &info) != CLDN_OK) return 0;
+  const uint64_t expected = static_cast<uint64_t>(info.width) * info.height * info.point_step;
+  if (pc_data_size != expected) {  // wasm_functions.cpp:222-228
+    set_error("Data size mismatch: expected %llu but got %u", static_cast<unsigned long long>(expected), pc_data_size);
+    return 0;
+  }
+  cldn_encoder_t* enc = nullptr;
+  if (cldn_b200_encoder_create(&info, -1, nullptr, &enc) != CLDN_OK) return 0;
+  bool ok;
+  const size_t cap = max_compressed_size(info, pc_data_size / info.point_step, true, &ok);
+  std::vector<uint8_t> tmp(ok ? cap : 0);
+  size_t written = 0;
+  int rc = ok ? cldn_b200_encode(enc, pc_data, pc_data_size, tmp.data(), tmp.size(), 1, &written, CLDN_MEM_HOST) : CLDN_ERR_INVALID_ARGUMENT;
+  cldn_b200_encoder_destroy(enc);
+  if (rc != CLDN_OK) return 0;
+  if (written > output_capacity) { set_error("Output buffer too small for encoded data. Need %zu bytes, got %u", written, output_capacity); return 0; }
+  memcpy(output_data, tmp.data(), written);
+  return static_cast<uint32_t>(written);
+}
+
+uint32_t cldn_b200_DecodeCompressedData(const void* encoded_data, uint32_t encoded_data_size, void* output_data,
+                                        uint32_t output_capacity) {
+  if (!encoded_data || !output_data) { set_error("null argument"); return 0; }
+  cldn_info_t info;
+  size_t hdr = 0;
+  if (cldn_b200_decode_header(static_cast<const uint8_t*>(encoded_data), encoded_data_size, &info, &hdr) != CLDN_OK) return 0;
+  const uint64_t decoded = static_cast<uint64_t>(info.width) * info.height * info.point_step;
+  if (decoded > output_capacity) { set_error("output buffer too small"); return 0; }
+  cldn_decoder_t* dec = nullptr;
+  if (cldn_b200_decoder_create(-1, nullptr, &dec) != CLDN_OK) return 0;
+  const int rc = cldn_b200_decode(dec, &info, static_cast<const uint8_t*>(encoded_data) + hdr, encoded_data_size - hdr,
+                                  output_data, output_capacity, CLDN_MEM_HOST);
+  cldn_b200_decoder_destroy(dec);
+  return rc == CLDN_OK ? static_cast<uint32_t>(decoded) : 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,815 @@
+// Stage-1 DECODE kernels.
+//
+// Replaces PointcloudDecoder::decode's chunk walk (cloudini_lib/src/cloudini.cpp:645-664), DecodeV4Stage1Chunk
+// (v4_codec.cpp:85-117), DecodeV5Stage1Chunk (v5_codec.cpp:984-1012) and decodeV5AdaptiveIntSection (:764-879).
+//
+// Work decomposition: one CTA per 32768-point chunk (chunks are independently decodable: every decoder resets at a
+// chunk start). Inside a chunk the byte stream is processed in tiles of kDecTileBytes bytes:
+//   pass A  (byte-parallel)  a byte with a clear MSB terminates a value (the 0x00 NaN marker too), so the number of
+//           terminators before a byte is the index of the value it belongs to; each thread scans 16-byte vectors,
+//           a CTA scan ranks the terminators, and the thread owning a terminator reassembles the varint behind it;
+//   pass B  (point-parallel) values are regrouped per point / per field ("slot"), a segmented CTA scan (reset at NaN)
+//           turns deltas into absolute quantised values, which are scaled and scattered into the strided output.
+// Plans whose regular stream holds raw (Copy) fields cannot be ranked by terminators: all-Copy plans have a fixed
+// point size and are trivially parallel; mixed plans fall back to a sequential per-chunk parser (one thread per chunk).
+#include <stdio.h>
+
+#include "cldn_device.cuh"
+#include "cldn_kernels.h"
+
+namespace cldn {
+
+constexpr int kDecVecPerThread = 2;
+constexpr int kDecTileBytes = kThreads * 16 * kDecVecPerThread;  // 8192
+constexpr int kLookBehind = 16;
+
+// One varint-coded value per point ("slot") of the regular stream, or the single slot of a DeltaVarint section.
+enum SlotKind : uint8_t { SLOT_FLOATN = 0, SLOT_F32 = 1, SLOT_F64 = 2, SLOT_INT = 3 };
+struct DecSlot {
+  uint32_t offset;
+  uint8_t kind;
+  uint8_t size;  // bytes stored for SLOT_INT
+  uint8_t pad_[2];
+  float mul_f;
+  double mul_d;
+};
+
+// ------------------------------------------------------------------------------------------------------------------
+// Chunk table: cloudini.cpp:645-664. One thread per frame walks the u32 prefixes (a dependent chain by construction).
+__global__ void walk_chunks_kernel(const DecLaunch L) {
+  const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= L.n_frames) return;
+  const DecFrame F = L.frames[f];
+  uint64_t pos = 0;
+  for (uint32_t c = 0; c < F.n_chunks; ++c) {
+    uint64_t body = 0;
+    uint32_t size = 0;
+    if (pos >= F.payload_bytes) {
+      report_error(L.err, DEV_ERR_CHUNK_COUNT);  // "Encoded data ended before all declared points were decoded"
+    } else if (F.payload_bytes - pos < 4) {
+      report_error(L.err, DEV_ERR_TRUNCATED);    // decode<uint32_t>: not enough input data
+      pos = F.payload_bytes;
+    } else {
+      size = load_u32(F.payload + pos);
+      pos += 4;
+      if (size > F.payload_bytes - pos) {
+        report_error(L.err, DEV_ERR_CHUNK_SIZE);  // "Invalid chunk size found while decoding"
+        size = 0;
+        pos = F.payload_bytes;
+      }
+      body = pos;
+      pos += size;
+    }
+    L.chunk_offsets[F.chunk_begin + c] = body;
+    L.chunk_sizes[F.chunk_begin + c] = size;
+  }
+  if (pos < F.payload_bytes) report_error(L.err, DEV_ERR_CHUNK_COUNT);  // "more chunks than declared points"
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Shared-memory working set of the chunk decoder.
+struct DecShared {
+  uint32_t scan[kThreads / 32 + 1];
+  uint32_t values_done;      // values of the current stream decoded so far
+  uint32_t stream_end;       // byte offset (inside the chunk body) one past the stream's last value
+  uint32_t stop;             // stream finished (or failed)
+  uint32_t pad_;
+  long long carry[kMaxOps];  // per slot: absolute quantised value of the last decoded point
+  long long seg_sum[kThreads / 32][4];
+  uint32_t seg_rst[kThreads / 32];
+};
+
+// Segmented-sum element for NS slots processed together: sum[j] is the sum of deltas since the last reset (NaN) of
+// slot j, bit j of rst tells whether a reset happened inside the range.
+// Wrapping add (FieldDecoderFloatN_Lossy adds in int32 with wrap-around, field_decoder.cpp:68).
+__device__ __forceinline__ int32_t wadd(int32_t a, int32_t b) { return static_cast<int32_t>(static_cast<uint32_t>(a) + static_cast<uint32_t>(b)); }
+__device__ __forceinline__ long long wadd(long long a, long long b) {
+  return static_cast<long long>(static_cast<unsigned long long>(a) + static_cast<unsigned long long>(b));
+}
+
+template <typename AccT, int NS>
+struct Seg {
+  AccT sum[NS];
+  uint32_t rst;
+};
+template <typename AccT, int NS>
+__device__ __forceinline__ Seg<AccT, NS> seg_combine(const Seg<AccT, NS>& a, const Seg<AccT, NS>& b) {  // a then b
+  Seg<AccT, NS> r;
+#pragma unroll
+  for (int j = 0; j < NS; ++j) r.sum[j] = ((b.rst >> j) & 1u) ? b.sum[j] : wadd(a.sum[j], b.sum[j]);
+  r.rst = a.rst | b.rst;
+  return r;
+}
+template <typename AccT, int NS>
+__device__ __forceinline__ Seg<AccT, NS> seg_shfl_up(const Seg<AccT, NS>& a, int d) {
+  Seg<AccT, NS> r;
+#pragma unroll
+  for (int j = 0; j < NS; ++j) r.sum[j] = __shfl_up_sync(0xffffffffu, a.sum[j], d);
+  r.rst = __shfl_up_sync(0xffffffffu, a.rst, d);
+  return r;
+}
+
+// CTA-wide EXCLUSIVE segmented scan. smem: per-warp aggregates. Also returns the CTA total in *total.
+template <typename AccT, int NS>
+__device__ __forceinline__ Seg<AccT, NS> block_seg_exclusive(const Seg<AccT, NS>& mine, long long (*w_sum)[4],
+                                                             uint32_t* w_rst, Seg<AccT, NS>* total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  Seg<AccT, NS> inc = mine;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const Seg<AccT, NS> up = seg_shfl_up<AccT, NS>(inc, d);
+    if (lane >= d) inc = seg_combine<AccT, NS>(up, inc);
+  }
+  if (lane == 31) {
+#pragma unroll
+    for (int j = 0; j < NS; ++j) w_sum[warp][j] = static_cast<long long>(inc.sum[j]);
+    w_rst[warp] = inc.rst;
+  }
+  __syncthreads();
+  Seg<AccT, NS> prefix;  // combination of all earlier warps
+#pragma unroll
+  for (int j = 0; j < NS; ++j) prefix.sum[j] = 0;
+  prefix.rst = 0;
+  Seg<AccT, NS> tot = prefix;
+#pragma unroll
+  for (int w = 0; w < kThreads / 32; ++w) {
+    Seg<AccT, NS> x;
+#pragma unroll
+    for (int j = 0; j < NS; ++j) x.sum[j] = static_cast<AccT>(w_sum[w][j]);
+    x.rst = w_rst[w];
+    if (w < warp) prefix = seg_combine<AccT, NS>(prefix, x);
+    tot = seg_combine<AccT, NS>(tot, x);
+  }
+  *total = tot;
+  // exclusive = prefix (+) inclusive-of-previous-lane
+  Seg<AccT, NS> prev_lane = seg_shfl_up<AccT, NS>(inc, 1);
+  Seg<AccT, NS> res = prefix;
+  if (lane > 0) res = seg_combine<AccT, NS>(prefix, prev_lane);
+  __syncthreads();  // w_sum / w_rst may be reused by the caller
+  return res;
+}
+
+// Stores one decoded value of a slot.
+template <typename AccT>
+__device__ __forceinline__ void store_slot_value(uint8_t* point, const DecSlot& s, AccT value, bool nan) {
+  if (s.offset == CLDN_SKIP_STORE_OFFSET) return;  // kDecodeButSkipStore (basic_types.hpp:71)
+  uint8_t* dst = point + s.offset;
+  switch (s.kind) {
+    case SLOT_FLOATN:  // field_decoder.cpp:62-70
+    case SLOT_F32: {   // field_decoder.hpp:331-353
+      float f;
+      if (nan) f = __uint_as_float(0x7FC00000u);  // std::numeric_limits<float>::quiet_NaN()
+      else if (s.kind == SLOT_FLOATN) f = __fmul_rn(__int2float_rn(static_cast<int32_t>(value)), s.mul_f);
+      else f = __fmul_rn(__ll2float_rn(static_cast<long long>(value)), s.mul_f);
+      store_u32(dst, __float_as_uint(f));
+    } break;
+    case SLOT_F64: {
+      double d;
+      if (nan) d = __longlong_as_double(0x7FF8000000000000ll);
+      else d = __dmul_rn(__ll2double_rn(static_cast<long long>(value)), s.mul_d);
+      store_u64(dst, static_cast<uint64_t>(__double_as_longlong(d)));
+    } break;
+    default:  // SLOT_INT: memcpy(&value, sizeof(IntType)) (field_decoder.hpp:93-95)
+      store_low_bytes(dst, static_cast<uint64_t>(static_cast<long long>(value)), s.size);
+      break;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Decodes a stream of `n_points * K` varint-coded values (K slots per point, interleaved) that starts at `src`
+// (at most `avail` readable bytes) and scatters them to out + point * step + slot.offset.
+// KT > 0: compile-time K with 32-bit accumulators (FloatN: wrapping int32 adds, field_decoder.cpp:68);
+// KT == 0: run-time K, 64-bit accumulators, one slot at a time.
+// Returns (to all threads) the number of bytes consumed, or 0xFFFFFFFF after reporting an error.
+template <int KT>
+__device__ uint32_t decode_varint_stream(const uint8_t* __restrict__ src, uint32_t avail, uint32_t n_points, int K_rt,
+                                         const DecSlot* __restrict__ slots, uint8_t* __restrict__ out, uint32_t step,
+                                         DecShared& sh, uint8_t* tile_bytes, uint8_t* vals_raw, uint32_t* nanbits,
+                                         uint32_t* err) {
+  using AccT = typename std::conditional<(KT > 0), int32_t, long long>::type;
+  const int K = KT > 0 ? KT : K_rt;
+  AccT* vals = reinterpret_cast<AccT*>(vals_raw);
+  const uint32_t V = n_points * static_cast<uint32_t>(K);
+  if (threadIdx.x == 0) {
+    sh.values_done = 0;
+    sh.stream_end = 0;
+    sh.stop = (V == 0) ? 1u : 0u;
+  }
+  for (int j = threadIdx.x; j < K; j += blockDim.x) sh.carry[j] = 0;
+  __syncthreads();
+  if (V == 0) return 0;
+
+  // tiles are aligned to 16 bytes in global memory so that every thread issues aligned 16-byte loads
+  const uintptr_t src_addr = reinterpret_cast<uintptr_t>(src);
+  const uint32_t mis = static_cast<uint32_t>(src_addr & 15u);
+  const uint8_t* aligned = src - mis;  // tile k covers stream bytes [k*TB - mis, (k+1)*TB - mis)
+
+  for (uint32_t tile = 0;; ++tile) {
+    const int64_t tile_b0 = static_cast<int64_t>(tile) * kDecTileBytes - mis;  // stream offset of the tile's first byte
+    if (tile_b0 >= static_cast<int64_t>(avail)) {
+      // ran out of bytes before all values were seen: "Truncated encoded data" (v4_codec.cpp:102-104)
+      if (threadIdx.x == 0) report_error(err, DEV_ERR_TRUNCATED);
+      return 0xFFFFFFFFu;
+    }
+    // ---- load: tile_bytes[kLookBehind + i] = stream byte (tile_b0 + i); bytes outside [0, avail) read as 0x80 ----
+#pragma unroll
+    for (int vv = 0; vv < kDecVecPerThread; ++vv) {
+      const uint32_t i = (vv * kThreads + threadIdx.x) * 16u;
+      const int64_t b = tile_b0 + i;
+      uint4 q = make_uint4(0x80808080u, 0x80808080u, 0x80808080u, 0x80808080u);
+      if (b >= 0 && b + 16 <= static_cast<int64_t>(avail)) {
+        q = *reinterpret_cast<const uint4*>(aligned + static_cast<size_t>(tile) * kDecTileBytes + i);
+      } else if (b + 16 > 0 && b < static_cast<int64_t>(avail)) {  // stream edge: only touch bytes inside the stream
+        uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          const int64_t bb = b + k;
+          if (bb >= 0 && bb < static_cast<int64_t>(avail)) {
+            w[k >> 2] = (w[k >> 2] & ~(0xFFu << (8 * (k & 3)))) | (static_cast<uint32_t>(src[bb]) << (8 * (k & 3)));
+          }
+        }
+        q = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+      *reinterpret_cast<uint4*>(tile_bytes + kLookBehind + i) = q;
+    }
+    if (threadIdx.x < 4) {  // look-behind: the 16 stream bytes before the tile (0x80 before the stream start)
+      uint32_t w = 0x80808080u;
+      const int64_t b = tile_b0 - 16 + 4 * static_cast<int64_t>(threadIdx.x);
+      if (tile > 0) {
+        w = *reinterpret_cast<const uint32_t*>(aligned + static_cast<size_t>(tile) * kDecTileBytes - 16 + 4 * threadIdx.x);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (b + k < 0) w = (w & ~(0xFFu << (8 * k))) | (0x80u << (8 * k));
+        }
+      }
+      // a terminator must separate the look-behind from the stream start: byte (-1) is treated as a terminator
+      reinterpret_cast<uint32_t*>(tile_bytes)[threadIdx.x] = w;
+    }
+    __syncthreads();
+
+    // ---- pass A: rank terminators ----
+    uint32_t tmask[kDecVecPerThread];
+    uint32_t cnt = 0;
+#pragma unroll
+    for (int vv = 0; vv < kDecVecPerThread; ++vv) {
+      const uint32_t i = (vv * kThreads + threadIdx.x) * 16u;
+      const uint4 q = *reinterpret_cast<const uint4*>(tile_bytes + kLookBehind + i);
+      const uint32_t w[4] = {~q.x & 0x80808080u, ~q.y & 0x80808080u, ~q.z & 0x80808080u, ~q.w & 0x80808080u};
+      uint32_t m = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        // gather bits 7,15,23,31 into 4 consecutive bits
+        const uint32_t x = w[k];
+        m |= (((x >> 7) & 1u) | ((x >> 14) & 2u) | ((x >> 21) & 4u) | ((x >> 28) & 8u)) << (4 * k);
+      }
+      tmask[vv] = m;
+      cnt += __popc(m);
+    }
+    // thread order must follow byte order: vector vv of thread t sits at (vv*kThreads + t)*16, so scan per vv
+    uint32_t vbase[kDecVecPerThread];
+    uint32_t tile_values = 0;
+#pragma unroll
+    for (int vv = 0; vv < kDecVecPerThread; ++vv) {
+      uint32_t tot;
+      const uint32_t ex = block_exclusive_scan(__popc(tmask[vv]), sh.scan, &tot);
+      vbase[vv] = tile_values + ex;
+      tile_values += tot;
+      __syncthreads();
+    }
+    const uint32_t done = sh.values_done;
+    const uint32_t want = V - done;                       // values still missing
+    const uint32_t take = tile_values < want ? tile_values : want;
+
+    // ---- pass A2: reassemble the varint behind every terminator and park it at its tile-local value index ----
+    for (uint32_t i = threadIdx.x; i < (take + 31u) / 32u; i += blockDim.x) nanbits[i] = 0;
+    __syncthreads();
+#pragma unroll
+    for (int vv = 0; vv < kDecVecPerThread; ++vv) {
+      uint32_t m = tmask[vv];
+      uint32_t vi = vbase[vv];
+      const uint32_t i0 = (vv * kThreads + threadIdx.x) * 16u;
+      while (m && vi < take) {
+        const int j = __ffs(m) - 1;
+        m &= m - 1;
+        const uint8_t* endp = tile_bytes + kLookBehind + i0 + j;  // terminator byte
+        // walk back over continuation bytes (at most 9; byte -1 of the stream reads as a terminator-less 0x80 guard
+        // only inside the look-behind, where the stream start is protected by the explicit bound below)
+        const int64_t spos = tile_b0 + i0 + j;  // stream offset of the terminator
+        int nb = 1;
+        while (nb < 11 && spos - nb >= 0 && (endp[-nb] & 0x80u)) ++nb;
+        bool bad = false;
+        unsigned long long u = 0;
+        if (nb > 10) { bad = true; report_error(err, DEV_ERR_VARINT_OVERFLOW); }
+        else {
+#pragma unroll 1
+          for (int k = 0; k < nb; ++k) {
+            const unsigned long long payload = endp[-(nb - 1) + k] & 0x7Fu;
+            if (k == 9 && payload > 1) { bad = true; report_error(err, DEV_ERR_VARINT_OVERFLOW); }  // encoding_utils.hpp:127-129
+            u |= payload << (7 * k);
+          }
+        }
+        bool nan = false;
+        AccT delta = 0;
+        if (!bad) {
+          if (u == 0) {
+            // single 0x00 = NaN marker for float slots; anything else is "unexpected NaN marker"
+            const DecSlot& s = slots[(done + vi) % static_cast<uint32_t>(K)];
+            if (nb == 1 && s.kind != SLOT_INT) nan = true;
+            else report_error(err, DEV_ERR_NAN_MARKER);
+          } else {
+            delta = static_cast<AccT>(unzigzag(u - 1ull));
+          }
+        }
+        vals[vi] = delta;
+        if (nan) atomicOr(&nanbits[vi >> 5], 1u << (vi & 31));
+        if (done + vi + 1 == V) sh.stream_end = static_cast<uint32_t>(spos + 1);
+        ++vi;
+      }
+    }
+    __syncthreads();
+
+    // ---- pass B: per point / per slot prefix sums and scatter ----
+    if (take > 0) {
+      const uint32_t first_pt = done / K;
+      const uint32_t last_pt = (done + take - 1) / K;
+      const uint32_t npts = last_pt - first_pt + 1;
+      const uint32_t per_thread = (npts + kThreads - 1) / kThreads;
+      const uint32_t my0 = first_pt + threadIdx.x * per_thread;
+      uint32_t my1 = my0 + per_thread;
+      if (my1 > last_pt + 1) my1 = last_pt + 1;
+      if (KT > 0) {
+        constexpr int NS = KT > 0 ? KT : 1;
+        Seg<AccT, NS> mine;
+#pragma unroll
+        for (int j = 0; j < NS; ++j) mine.sum[j] = 0;
+        mine.rst = 0;
+        for (uint32_t p = my0; p < my1; ++p) {
+#pragma unroll
+          for (int j = 0; j < NS; ++j) {
+            const int64_t lv = static_cast<int64_t>(p) * NS + j - done;
+            if (lv >= 0 && lv < static_cast<int64_t>(take)) {
+              if ((nanbits[lv >> 5] >> (lv & 31)) & 1u) { mine.sum[j] = 0; mine.rst |= 1u << j; }
+              else mine.sum[j] = wadd(mine.sum[j], vals[lv]);
+            }
+          }
+        }
+        Seg<AccT, NS> total;
+        Seg<AccT, NS> ex = block_seg_exclusive<AccT, NS>(mine, sh.seg_sum, sh.seg_rst, &total);
+        AccT cur[NS];
+#pragma unroll
+        for (int j = 0; j < NS; ++j) {
+          cur[j] = ((ex.rst >> j) & 1u) ? ex.sum[j] : wadd(static_cast<AccT>(sh.carry[j]), ex.sum[j]);
+        }
+        for (uint32_t p = my0; p < my1; ++p) {
+          uint8_t* point = out + static_cast<size_t>(p) * step;
+#pragma unroll
+          for (int j = 0; j < NS; ++j) {
+            const int64_t lv = static_cast<int64_t>(p) * NS + j - done;
+            if (lv >= 0 && lv < static_cast<int64_t>(take)) {
+              const bool nan = (nanbits[lv >> 5] >> (lv & 31)) & 1u;
+              if (nan) cur[j] = 0; else cur[j] = wadd(cur[j], vals[lv]);
+              store_slot_value<AccT>(point, slots[j], cur[j], nan);
+            }
+          }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+#pragma unroll
+          for (int j = 0; j < NS; ++j) {
+            sh.carry[j] = ((total.rst >> j) & 1u) ? static_cast<long long>(total.sum[j])
+                                                  : static_cast<long long>(wadd(static_cast<AccT>(sh.carry[j]), total.sum[j]));
+          }
+        }
+      } else {
+        // run-time K: one slot at a time with 64-bit accumulators
+        for (int j = 0; j < K; ++j) {
+          Seg<long long, 1> mine;
+          mine.sum[0] = 0;
+          mine.rst = 0;
+          for (uint32_t p = my0; p < my1; ++p) {
+            const int64_t lv = static_cast<int64_t>(p) * K + j - done;
+            if (lv >= 0 && lv < static_cast<int64_t>(take)) {
+              if ((nanbits[lv >> 5] >> (lv & 31)) & 1u) { mine.sum[0] = 0; mine.rst = 1u; }
+              else mine.sum[0] = wadd(mine.sum[0], static_cast<long long>(vals[lv]));
+            }
+          }
+          Seg<long long, 1> total;
+          Seg<long long, 1> ex = block_seg_exclusive<long long, 1>(mine, sh.seg_sum, sh.seg_rst, &total);
+          long long cur = ex.rst ? ex.sum[0] : wadd(sh.carry[j], ex.sum[0]);
+          for (uint32_t p = my0; p < my1; ++p) {
+            const int64_t lv = static_cast<int64_t>(p) * K + j - done;
+            if (lv >= 0 && lv < static_cast<int64_t>(take)) {
+              const bool nan = (nanbits[lv >> 5] >> (lv & 31)) & 1u;
+              if (nan) cur = 0; else cur = wadd(cur, static_cast<long long>(vals[lv]));
+              store_slot_value<long long>(out + static_cast<size_t>(p) * step, slots[j], cur, nan);
+            }
+          }
+          __syncthreads();
+          if (threadIdx.x == 0) sh.carry[j] = total.rst ? total.sum[0] : wadd(sh.carry[j], total.sum[0]);
+        }
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      sh.values_done = done + take;
+      if (done + take == V) sh.stop = 1;
+    }
+    __syncthreads();
+    if (sh.stop) break;
+  }
+  return sh.stream_end;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// V5 adaptive integer sections (decodeV5AdaptiveIntSection, v5_codec.cpp:764-879). Executed by the whole CTA.
+__device__ __forceinline__ uint32_t bits_for_palette(uint32_t count) {  // bitsForPaletteIndex, v5_codec.cpp:196-207
+  if (count <= 1) return 0;
+  return 32u - __clz(count - 1u);
+}
+
+// plain LEB128 (readUVarint, v5_codec.cpp:176-194). Returns bytes consumed, 0 on error.
+__device__ __forceinline__ uint32_t read_uvarint(const uint8_t* p, uint32_t avail, unsigned long long* out, uint32_t* err) {
+  unsigned long long v = 0;
+  uint32_t shift = 0, n = 0;
+  while (true) {
+    if (n >= avail) { report_error(err, DEV_ERR_TRUNCATED); return 0; }
+    const uint8_t b = p[n++];
+    v |= static_cast<unsigned long long>(b & 0x7Fu) << shift;
+    if (!(b & 0x80u)) break;
+    shift += 7;
+    if (shift >= 64) { report_error(err, DEV_ERR_VARINT_OVERFLOW); return 0; }
+  }
+  *out = v;
+  return n;
+}
+// zigzag varint (decodeVarint, encoding_utils.hpp:98-148). Returns bytes consumed, 0 on error.
+__device__ __forceinline__ uint32_t read_varint(const uint8_t* p, uint32_t avail, long long* out, uint32_t* err) {
+  unsigned long long v = 0;
+  uint32_t n = 0;
+  while (true) {
+    if (n >= avail) { report_error(err, n == 0 ? DEV_ERR_TRUNCATED : DEV_ERR_TRUNCATED); return 0; }
+    const uint8_t b = p[n];
+    const unsigned long long payload = b & 0x7Fu;
+    if (n >= 10 || (n == 9 && payload > 1)) { report_error(err, DEV_ERR_VARINT_OVERFLOW); return 0; }
+    v |= payload << (7 * n);
+    ++n;
+    if (!(b & 0x80u)) break;
+  }
+  if (v == 0) { report_error(err, DEV_ERR_NAN_MARKER); return 0; }
+  *out = unzigzag(v - 1ull);
+  return n;
+}
+
+constexpr int kRunBatch = 512;
+struct RunBatch {
+  unsigned long long value[kRunBatch];  // Rle: raw value; DeltaRle: value BEFORE the run's first point
+  long long diff[kRunBatch];            // DeltaRle only
+  uint32_t start[kRunBatch + 1];        // chunk-local index of the run's first point
+  uint32_t n;
+  uint32_t pos;       // parse position (bytes into the section) after this batch
+  uint32_t runs_left;
+  uint32_t failed;
+};
+
+// Decodes one section starting at src (avail bytes). Returns bytes consumed or 0xFFFFFFFF on error.
+template <int KT>
+__device__ uint32_t decode_section(const uint8_t* __restrict__ src, uint32_t avail, uint32_t n_points,
+                                   const SectionField& sf, uint8_t* __restrict__ out, uint32_t step, DecShared& sh,
+                                   uint8_t* tile_bytes, uint8_t* vals_raw, uint32_t* nanbits, RunBatch& rb,
+                                   DecSlot* sec_slot, uint32_t* err) {
+  if (avail < 1) {
+    if (threadIdx.x == 0) report_error(err, DEV_ERR_BAD_MODE);  // "missing mode byte"
+    return 0xFFFFFFFFu;
+  }
+  const uint8_t mode = src[0];
+  if (mode > 3) {
+    if (threadIdx.x == 0) report_error(err, DEV_ERR_BAD_MODE);
+    return 0xFFFFFFFFu;
+  }
+  const uint32_t bpv = sf.bpv;
+  if (mode == 0) {  // DeltaVarint: n_points zigzag varints, prev = 0
+    if (threadIdx.x == 0) {
+      sec_slot->offset = sf.offset;
+      sec_slot->kind = SLOT_INT;
+      sec_slot->size = sf.bpv;
+    }
+    __syncthreads();
+    const uint32_t used = decode_varint_stream<0>(src + 1, avail - 1, n_points, 1, sec_slot, out, step, sh, tile_bytes,
+                                                  vals_raw, nanbits, err);
+    return used == 0xFFFFFFFFu ? used : used + 1;
+  }
+  if (mode == 1) {  // Palette
+    if (avail < 3) {
+      if (threadIdx.x == 0) report_error(err, DEV_ERR_TRUNCATED);
+      return 0xFFFFFFFFu;
+    }
+    const uint32_t count = load_u16(src + 1);
+    if (count == 0) {
+      if (threadIdx.x == 0) report_error(err, DEV_ERR_PALETTE);  // "empty palette"
+      return 0xFFFFFFFFu;
+    }
+    const uint64_t pal_bytes = static_cast<uint64_t>(count) * bpv;
+    const uint32_t bits = bits_for_palette(count);
+    const uint64_t idx_bytes = (static_cast<uint64_t>(bits) * n_points + 7u) / 8u;
+    if (3ull + pal_bytes + idx_bytes > avail) {
+      if (threadIdx.x == 0) report_error(err, DEV_ERR_PALETTE);  // truncated palette / indexes
+      return 0xFFFFFFFFu;
+    }
+    const uint8_t* pal = src + 3;
+    const uint8_t* idx = pal + pal_bytes;
+    for (uint32_t i = threadIdx.x; i < n_points; i += blockDim.x) {
+      uint32_t k = 0;
+      if (bits) {
+        const uint64_t bit = static_cast<uint64_t>(i) * bits;
+        const uint32_t byte = static_cast<uint32_t>(bit >> 3);
+        uint32_t w = idx[byte];
+        if (byte + 1 < idx_bytes) w |= static_cast<uint32_t>(idx[byte + 1]) << 8;
+        if (byte + 2 < idx_bytes) w |= static_cast<uint32_t>(idx[byte + 2]) << 16;
+        k = (w >> (bit & 7u)) & ((1u << bits) - 1u);
+      }
+      if (k >= count) { report_error(err, DEV_ERR_PALETTE); continue; }  // "palette index out of range"
+      store_low_bytes(out + static_cast<size_t>(i) * step + sf.offset, load_raw_bits(pal + static_cast<size_t>(k) * bpv, bpv), bpv);
+    }
+    return static_cast<uint32_t>(3ull + pal_bytes + idx_bytes);
+  }
+  // Rle (2) / DeltaRle (3): a run table is parsed sequentially in batches, then expanded by all threads.
+  if (avail < 5) {
+    if (threadIdx.x == 0) report_error(err, DEV_ERR_TRUNCATED);
+    return 0xFFFFFFFFu;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    rb.runs_left = load_u32(src + 1);
+    rb.pos = 5;
+    rb.start[0] = 0;
+    rb.failed = 0;
+    rb.value[0] = 0;
+  }
+  __syncthreads();
+  uint32_t out_index = 0;          // points produced so far (uniform)
+  unsigned long long prev = 0;     // DeltaRle running value (thread 0 only)
+  while (true) {
+    if (threadIdx.x == 0) {
+      uint32_t n = 0, pos = rb.pos, oi = out_index;
+      while (n < kRunBatch && rb.runs_left > 0) {
+        unsigned long long run_len = 0;
+        if (mode == 2) {
+          if (avail - pos < bpv) { report_error(err, DEV_ERR_RLE); rb.failed = 1; break; }  // "truncated RLE value"
+          rb.value[n] = load_raw_bits(src + pos, bpv);
+          pos += bpv;
+        } else {
+          long long diff;
+          const uint32_t c = read_varint(src + pos, avail - pos, &diff, err);
+          if (!c) { rb.failed = 1; break; }
+          pos += c;
+          rb.diff[n] = diff;
+          rb.value[n] = prev;
+        }
+        const uint32_t c2 = read_uvarint(src + pos, avail - pos, &run_len, err);
+        if (!c2) { rb.failed = 1; break; }
+        pos += c2;
+        if (run_len > static_cast<unsigned long long>(n_points - oi)) {  // "run exceeds point count"
+          report_error(err, DEV_ERR_RLE);
+          rb.failed = 1;
+          break;
+        }
+        if (mode == 3) prev += static_cast<unsigned long long>(rb.diff[n]) * run_len;
+        rb.start[n] = oi;
+        oi += static_cast<uint32_t>(run_len);
+        --rb.runs_left;
+        ++n;
+      }
+      rb.start[n] = oi;
+      rb.n = n;
+      rb.pos = pos;
+    }
+    __syncthreads();
+    if (rb.failed) return 0xFFFFFFFFu;
+    const uint32_t n = rb.n;
+    const uint32_t lo_pt = out_index, hi_pt = rb.start[n];
+    for (uint32_t i = lo_pt + threadIdx.x; i < hi_pt; i += blockDim.x) {
+      // last run with start <= i (empty runs share their start with the next run and are skipped by the search)
+      uint32_t lo = 0, hi = n - 1;
+      while (lo < hi) {
+        const uint32_t mid = (lo + hi + 1) >> 1;
+        if (rb.start[mid] <= i) lo = mid; else hi = mid - 1;
+      }
+      unsigned long long v = rb.value[lo];
+      if (mode == 3) v += static_cast<unsigned long long>(rb.diff[lo]) * static_cast<unsigned long long>(i - rb.start[lo] + 1);
+      store_low_bytes(out + static_cast<size_t>(i) * step + sf.offset, v, bpv);
+    }
+    out_index = hi_pt;
+    const uint32_t left = rb.runs_left;
+    __syncthreads();
+    if (left == 0) break;
+  }
+  if (out_index != n_points) {
+    if (threadIdx.x == 0) report_error(err, DEV_ERR_RLE);  // "run count does not fill chunk"
+    return 0xFFFFFFFFu;
+  }
+  return rb.pos;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// One CTA per chunk: regular stream (varint-coded plans) followed by the V5 sections.
+template <int KT>
+__global__ void __launch_bounds__(kThreads) decode_chunks_kernel(const DecLaunch L) {
+  extern __shared__ __align__(16) uint8_t dyn_smem[];
+  __shared__ DecShared sh;
+  __shared__ DecSlot s_slots[kMaxOps + 1];
+  __shared__ uint32_t s_frame;
+  // dynamic smem: tile bytes | values | nan bits | run batch
+  uint8_t* tile_bytes = dyn_smem;
+  uint8_t* vals_raw = tile_bytes + kLookBehind + kDecTileBytes + 16;
+  constexpr size_t kValBytes = static_cast<size_t>(kDecTileBytes) * (KT > 0 ? 4 : 8);
+  uint32_t* nanbits = reinterpret_cast<uint32_t*>(vals_raw + kValBytes);
+  RunBatch& rb = *reinterpret_cast<RunBatch*>(reinterpret_cast<uint8_t*>(nanbits) + kDecTileBytes / 8);
+
+  const uint32_t gc = blockIdx.x;
+  if (threadIdx.x == 0) {
+    uint32_t lo = 0, hi = L.n_frames - 1;
+    while (lo < hi) {
+      const uint32_t mid = (lo + hi + 1) >> 1;
+      if (L.frames[mid].chunk_begin <= gc) lo = mid; else hi = mid - 1;
+    }
+    s_frame = lo;
+  }
+  const Plan& plan = *L.plan;
+  // expand the regular ops into slots
+  if (threadIdx.x == 0) {
+    int ns = 0;
+    for (uint32_t k = 0; k < plan.n_ops; ++k) {
+      const RegOp& op = plan.ops[k];
+      for (int l = 0; l < op.lanes; ++l) {
+        DecSlot& s = s_slots[ns++];
+        s.offset = op.offset[l];
+        s.size = op.size;
+        s.mul_f = op.dec_mul_f[l];
+        s.mul_d = op.dec_mul_d;
+        s.kind = op.kind == OP_FLOATN ? SLOT_FLOATN : op.kind == OP_F32_LOSSY ? SLOT_F32 : op.kind == OP_F64_LOSSY ? SLOT_F64 : SLOT_INT;
+      }
+    }
+  }
+  __syncthreads();
+  const DecFrame F = L.frames[s_frame];
+  const uint32_t c = gc - F.chunk_begin;
+  const uint32_t n_points = min(kChunkPoints, F.n_points - c * kChunkPoints);
+  const uint8_t* body = F.payload + L.chunk_offsets[gc];
+  const uint32_t body_bytes = L.chunk_sizes[gc];
+  uint8_t* out = F.out + static_cast<size_t>(c) * kChunkPoints * plan.point_step;
+
+  uint32_t pos = 0;
+  if (plan.values_per_point > 0) {
+    const uint32_t used = decode_varint_stream<KT>(body, body_bytes, n_points, static_cast<int>(plan.values_per_point), s_slots,
+                                                   out, plan.point_step, sh, tile_bytes, vals_raw, nanbits, L.err);
+    if (used == 0xFFFFFFFFu) return;
+    pos = used;
+  }
+  for (uint32_t s = 0; s < plan.n_sections; ++s) {
+    const uint32_t used = decode_section<KT>(body + pos, body_bytes - pos, n_points, plan.sections[s], out, plan.point_step,
+                                             sh, tile_bytes, vals_raw, nanbits, rb, &s_slots[kMaxOps], L.err);
+    if (used == 0xFFFFFFFFu) return;
+    pos += used;
+    __syncthreads();
+  }
+  // DecodeV5Stage1Chunk rejects trailing bytes (v5_codec.cpp:1008-1010); DecodeV4Stage1Chunk does not check.
+  if (plan.uses_v5 && pos != body_bytes && threadIdx.x == 0) report_error(L.err, DEV_ERR_TRAILING);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// All-Copy plans (encoding NONE, or LOSSY clouds made of INT8 / resolution-less FLOAT32 fields only): fixed point
+// size, every point independent. One thread per point.
+__global__ void __launch_bounds__(kThreads) decode_fixed_kernel(const DecLaunch L) {
+  const Plan& plan = *L.plan;
+  const uint32_t gc = blockIdx.y;
+  uint32_t lo = 0, hi = L.n_frames - 1;
+  while (lo < hi) {
+    const uint32_t mid = (lo + hi + 1) >> 1;
+    if (L.frames[mid].chunk_begin <= gc) lo = mid; else hi = mid - 1;
+  }
+  const DecFrame F = L.frames[lo];
+  const uint32_t c = gc - F.chunk_begin;
+  const uint32_t n_points = min(kChunkPoints, F.n_points - c * kChunkPoints);
+  const uint8_t* body = F.payload + L.chunk_offsets[gc];
+  const uint32_t body_bytes = L.chunk_sizes[gc];
+  const uint32_t psize = plan.min_point_bytes;
+  if (static_cast<uint64_t>(n_points) * psize > body_bytes) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) report_error(L.err, DEV_ERR_TRUNCATED);
+    return;
+  }
+  uint8_t* out = F.out + static_cast<size_t>(c) * kChunkPoints * plan.point_step;
+  for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < n_points; p += gridDim.x * blockDim.x) {
+    const uint8_t* src = body + static_cast<size_t>(p) * psize;
+    uint8_t* dst = out + static_cast<size_t>(p) * plan.point_step;
+    for (uint32_t k = 0; k < plan.n_ops; ++k) {
+      const RegOp& op = plan.ops[k];
+      if (op.offset[0] != CLDN_SKIP_STORE_OFFSET) {
+        for (int b = 0; b < op.size; ++b) dst[op.offset[0] + b] = src[b];
+      }
+      src += op.size;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Sequential fallback for regular streams that mix raw (Copy) and varint fields: one thread per chunk walks the
+// stream exactly like DecodeV4Stage1Chunk. Sections (if any) are then decoded by the same thread.
+__global__ void decode_sequential_kernel(const DecLaunch L) {
+  const uint32_t gc = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gc >= L.n_chunks_total) return;
+  const Plan& plan = *L.plan;
+  uint32_t lo = 0, hi = L.n_frames - 1;
+  while (lo < hi) {
+    const uint32_t mid = (lo + hi + 1) >> 1;
+    if (L.frames[mid].chunk_begin <= gc) lo = mid; else hi = mid - 1;
+  }
+  const DecFrame F = L.frames[lo];
+  const uint32_t c = gc - F.chunk_begin;
+  const uint32_t n_points = min(kChunkPoints, F.n_points - c * kChunkPoints);
+  const uint8_t* p = F.payload + L.chunk_offsets[gc];
+  uint32_t avail = L.chunk_sizes[gc];
+  uint8_t* out = F.out + static_cast<size_t>(c) * kChunkPoints * plan.point_step;
+  long long prev[kMaxOps * 4];
+  for (int i = 0; i < kMaxOps * 4; ++i) prev[i] = 0;
+  for (uint32_t pt = 0; pt < n_points; ++pt) {
+    if (avail < plan.min_point_bytes) { report_error(L.err, DEV_ERR_TRUNCATED); return; }
+    uint8_t* point = out + static_cast<size_t>(pt) * plan.point_step;
+    int slot = 0;
+    for (uint32_t k = 0; k < plan.n_ops; ++k) {
+      const RegOp& op = plan.ops[k];
+      if (op.kind == OP_COPY) {
+        if (avail < op.size) { report_error(L.err, DEV_ERR_TRUNCATED); return; }
+        if (op.offset[0] != CLDN_SKIP_STORE_OFFSET) {
+          for (int b = 0; b < op.size; ++b) point[op.offset[0] + b] = p[b];
+        }
+        p += op.size; avail -= op.size;
+        ++slot;
+        continue;
+      }
+      for (int l = 0; l < op.lanes; ++l, ++slot) {
+        if (avail == 0) { report_error(L.err, DEV_ERR_TRUNCATED); return; }
+        DecSlot s;
+        s.offset = op.offset[l]; s.size = op.size; s.mul_f = op.dec_mul_f[l]; s.mul_d = op.dec_mul_d;
+        s.kind = op.kind == OP_FLOATN ? SLOT_FLOATN : op.kind == OP_F32_LOSSY ? SLOT_F32 : op.kind == OP_F64_LOSSY ? SLOT_F64 : SLOT_INT;
+        if (p[0] == 0 && s.kind != SLOT_INT) {
+          prev[slot] = 0;
+          store_slot_value<long long>(point, s, 0, true);
+          ++p; --avail;
+          continue;
+        }
+        long long diff;
+        const uint32_t n = read_varint(p, avail, &diff, L.err);
+        if (!n) return;
+        p += n; avail -= n;
+        if (s.kind == SLOT_FLOATN) prev[slot] = static_cast<int32_t>(static_cast<int32_t>(diff) + static_cast<int32_t>(prev[slot]));
+        else prev[slot] = wadd(prev[slot], diff);
+        store_slot_value<long long>(point, s, prev[slot], false);
+      }
+    }
+  }
+  if (plan.n_sections) report_error(L.err, DEV_ERR_BAD_MODE);  // mixed raw+varint V5 plans are routed elsewhere
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+static size_t dec_smem_bytes(bool k32) {
+  return kLookBehind + kDecTileBytes + 16 + static_cast<size_t>(kDecTileBytes) * (k32 ? 4 : 8) + kDecTileBytes / 8 +
+         sizeof(RunBatch) + 16;
+}
+
+int launch_decode(const Plan& plan, const DecLaunch& L, cudaStream_t stream) {
+  int launches = 0;
+  if (L.n_chunks_total == 0 && L.n_frames == 0) return 0;
+  walk_chunks_kernel<<<(L.n_frames + 127) / 128, 128, 0, stream>>>(L);
+  ++launches;
+  if (L.n_chunks_total > 0) {
+    const bool varint_ok = plan.all_varint || plan.n_ops == 0;
+    if (varint_ok) {
+      const int K = static_cast<int>(plan.values_per_point);
+      const bool f3 = plan.floatn_only && K == 3, f4 = plan.floatn_only && K == 4;
+      const size_t smem = dec_smem_bytes(f3 || f4);
+      if (f4) {
+        auto k = decode_chunks_kernel<4>;
+        if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess) return -1;
+        k<<<L.n_chunks_total, kThreads, smem, stream>>>(L);
+      } else if (f3) {
+        auto k = decode_chunks_kernel<3>;
+        if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess) return -1;
+        k<<<L.n_chunks_total, kThreads, smem, stream>>>(L);
+      } else {
+        auto k = decode_chunks_kernel<0>;
+        if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess) return -1;
+        k<<<L.n_chunks_total, kThreads, smem, stream>>>(L);
+      }
+    } else if (plan.all_fixed && plan.n_sections == 0) {
+      dim3 grid(kChunkPoints / kThreads / 4, L.n_chunks_total);
+      decode_fixed_kernel<<<grid, kThreads, 0, stream>>>(L);
+    } else {
+      decode_sequential_kernel<<<(L.n_chunks_total + 31) / 32, 32, 0, stream>>>(L);
+    }
+    ++launches;
+  }
+  count_launch(launches);
+  return launches;
+}
+
+}  // namespace cldn

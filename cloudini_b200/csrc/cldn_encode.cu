@@ -1,0 +1,502 @@
+// Stage-1 ENCODE kernels: interleaved regular stream + chunk framing, one fused launch for a batch of frames.
+//
+// Replaces the per-point x per-encoder loop of EncodeV4Stage1Chunk (cloudini_lib/src/v4_codec.cpp:66-83) /
+// EncodeV5Stage1's regular part (v5_codec.cpp:920-932) and WriteStage1Chunk's u32 framing (chunk_writer.cpp:27-48).
+//
+// Grid = one CTA per tile of T = 256*I points (T divides the 32768-point chunk, so tiles never straddle chunks).
+//  phase 1  every thread quantises its points, takes the delta to the previous point and sizes the varints;
+//  scan     CTA exclusive scan of per-point byte counts; decoupled look-back over the frame's tiles gives the tile's
+//           byte position without a second pass over the input (input is read exactly once from HBM);
+//  phase 2  bytes are packed into a shared-memory staging buffer at tile-local offsets;
+//  copy-out the staged bytes are streamed to their final (arbitrarily aligned) position with 16-byte stores;
+//  framing  the last tile of every chunk back-patches the chunk's u32 size prefix, the last tile of a frame writes
+//           the frame's total size.
+#include <stdio.h>
+
+#include "cldn_device.cuh"
+#include "cldn_kernels.h"
+
+namespace cldn {
+
+// ------------------------------------------------------------------------------------------------------------------
+// Per-point evaluation of an arbitrary regular-stream plan (generic path; also the 5-byte slow path of the FloatN
+// kernel). `prev` is the previous point of the same chunk or nullptr at a chunk start: every reference encoder only
+// keeps the previous point's quantised value (0 after reset() or after a NaN), so it is recomputed instead of carried.
+template <class Sink>
+__device__ __forceinline__ void encode_point_ops(const Plan& plan, const uint8_t* __restrict__ pt,
+                                                 const uint8_t* __restrict__ prev, Sink& sink) {
+  for (uint32_t k = 0; k < plan.n_ops; ++k) {
+    const RegOp& op = plan.ops[k];
+    switch (op.kind) {
+      case OP_FLOATN: {  // field_encoder.cpp:42-91
+        for (int l = 0; l < op.lanes; ++l) {
+          const float v = __uint_as_float(load_u32(pt + op.offset[l]));
+          if (isnan(v)) { sink.put_byte(0); continue; }
+          const int32_t q = quant_i32_x86(v, op.enc_mul_f[l]);
+          int32_t pq = 0;
+          if (prev) {
+            const float pv = __uint_as_float(load_u32(prev + op.offset[l]));
+            if (!isnan(pv)) pq = quant_i32_x86(pv, op.enc_mul_f[l]);
+          }
+          const int32_t d = static_cast<int32_t>(static_cast<uint32_t>(q) - static_cast<uint32_t>(pq));  // _mm_sub_epi32
+          sink.put_varint(zigzag_plus1(static_cast<int64_t>(d)));
+        }
+      } break;
+      case OP_F32_LOSSY: {  // field_encoder.hpp:343-357
+        const float v = __uint_as_float(load_u32(pt + op.offset[0]));
+        if (isnan(v)) { sink.put_byte(0); break; }
+        const int64_t q = quant_i64_f32(v, op.enc_mul_f[0]);
+        int64_t pq = 0;
+        if (prev) {
+          const float pv = __uint_as_float(load_u32(prev + op.offset[0]));
+          if (!isnan(pv)) pq = quant_i64_f32(pv, op.enc_mul_f[0]);
+        }
+        sink.put_varint(zigzag_plus1(static_cast<int64_t>(static_cast<uint64_t>(q) - static_cast<uint64_t>(pq))));
+      } break;
+      case OP_F64_LOSSY: {
+        const double v = __longlong_as_double(static_cast<long long>(load_u64(pt + op.offset[0])));
+        if (isnan(v)) { sink.put_byte(0); break; }
+        const int64_t q = quant_i64_f64(v, op.enc_mul_d);
+        int64_t pq = 0;
+        if (prev) {
+          const double pv = __longlong_as_double(static_cast<long long>(load_u64(prev + op.offset[0])));
+          if (!isnan(pv)) pq = quant_i64_f64(pv, op.enc_mul_d);
+        }
+        sink.put_varint(zigzag_plus1(static_cast<int64_t>(static_cast<uint64_t>(q) - static_cast<uint64_t>(pq))));
+      } break;
+      case OP_INT: {  // field_encoder.hpp:78-85
+        const int64_t v = load_int_as_i64(pt + op.offset[0], op.type);
+        const int64_t pv = prev ? load_int_as_i64(prev + op.offset[0], op.type) : 0;
+        sink.put_varint(zigzag_plus1(static_cast<int64_t>(static_cast<uint64_t>(v) - static_cast<uint64_t>(pv))));
+      } break;
+      default:  // OP_COPY, field_encoder.hpp:56-60
+        sink.put_raw(pt + op.offset[0], op.size);
+        break;
+    }
+  }
+}
+
+// Frame lookup: last frame whose tile_begin <= tile (empty frames share tile_begin with their successor).
+__device__ __forceinline__ uint32_t find_frame(const EncFrame* __restrict__ frames, uint32_t n_frames, uint32_t tile) {
+  uint32_t lo = 0, hi = n_frames - 1;
+  while (lo < hi) {
+    const uint32_t mid = (lo + hi + 1) >> 1;
+    if (frames[mid].tile_begin <= tile) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
+// Header copy + bookkeeping for frames without any tile (0 points); run by CTA 0.
+__device__ __forceinline__ void handle_empty_frames(const EncLaunch& L) {
+  for (uint32_t f = threadIdx.x; f < L.n_frames; f += blockDim.x) {
+    if (L.frames[f].n_tiles == 0) {
+      for (uint32_t i = 0; i < L.header_bytes; ++i) L.frames[f].out[i] = L.header[i];
+      L.sizes[f] = L.header_bytes;
+    }
+  }
+}
+
+// Common tail of both encode kernels: copy-out, chunk prefix back-patch, frame size.
+//  total   = bytes staged by this tile, excl = data bytes of all earlier tiles of the frame (look-back result)
+__device__ __forceinline__ void finish_tile(const EncLaunch& L, const EncFrame& F, uint32_t frame_idx, uint32_t t,
+                                            const uint8_t* stage, uint32_t total, uint64_t excl) {
+  const uint32_t T = L.tile_points;
+  const uint32_t tiles_per_chunk = kChunkPoints / T;
+  const uint32_t chunk = t / tiles_per_chunk;
+  const uint64_t sec_before = F.sec_excl ? F.sec_excl[chunk] : 0;
+  uint8_t* payload = F.out + L.header_bytes;
+  // data position: one u32 prefix per chunk up to and including mine, all earlier data, all earlier chunks' sections
+  copy_stage_to_global(stage, total, payload + 4ull * (chunk + 1) + excl + sec_before);
+  if (t == 0) {
+    for (uint32_t i = threadIdx.x; i < L.header_bytes; i += blockDim.x) F.out[i] = L.header[i];
+  }
+  const bool last_of_frame = (t + 1 == F.n_tiles);
+  const bool last_of_chunk = last_of_frame || ((t + 1) % tiles_per_chunk == 0);
+  if (last_of_chunk && threadIdx.x == 0) {
+    const uint32_t first = chunk * tiles_per_chunk;
+    const uint64_t data_before_chunk = (first == 0) ? 0 : wait_inclusive(L.status, F.tile_begin + first - 1, L.epoch);
+    const uint64_t sec_mine = F.sec_excl ? (F.sec_excl[chunk + 1] - F.sec_excl[chunk]) : 0;
+    const uint64_t body = (excl + total) - data_before_chunk + sec_mine;
+    store_u32(payload + 4ull * chunk + data_before_chunk + sec_before, static_cast<uint32_t>(body));  // chunk_writer.cpp:33-40
+    if (last_of_frame) {
+      L.sizes[frame_idx] = L.header_bytes + 4ull * F.n_chunks + excl + total + (F.sec_excl ? F.sec_excl[F.n_chunks] : 0);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Generic kernel: any supported plan. Thread-blocked point assignment (thread owns I consecutive points).
+template <int I>
+__global__ void __launch_bounds__(kThreads) encode_generic_kernel(const EncLaunch L) {
+  extern __shared__ __align__(16) uint8_t dyn_smem[];
+  __shared__ uint32_t s_scan[kThreads / 32 + 1];
+  __shared__ unsigned long long s_excl;
+  Plan& plan = *reinterpret_cast<Plan*>(dyn_smem);
+  uint8_t* stage = dyn_smem + ((sizeof(Plan) + 15) & ~size_t(15));
+
+  {  // plan -> shared memory (uniform reads afterwards)
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(L.plan);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&plan);
+    for (uint32_t i = threadIdx.x; i < sizeof(Plan) / 4; i += blockDim.x) dst[i] = src[i];
+  }
+  if (blockIdx.x == 0) handle_empty_frames(L);
+  const uint32_t tile = blockIdx.x;
+  const uint32_t fi = find_frame(L.frames, L.n_frames, tile);
+  const EncFrame F = L.frames[fi];
+  const uint32_t t = tile - F.tile_begin;
+  const uint32_t T = kThreads * I;
+  const uint32_t p0 = t * T + threadIdx.x * I;
+  const uint32_t step = L.plan->point_step;
+  __syncthreads();
+
+  uint32_t len[I];
+  uint32_t mine = 0;
+#pragma unroll
+  for (int i = 0; i < I; ++i) {
+    const uint32_t p = p0 + i;
+    len[i] = 0;
+    if (p < F.n_points) {
+      const uint8_t* pt = F.in + static_cast<size_t>(p) * step;
+      const uint8_t* prev = (p % kChunkPoints) ? pt - step : nullptr;
+      CountSink cs;
+      encode_point_ops(plan, pt, prev, cs);
+      len[i] = cs.n;
+    }
+    mine += len[i];
+  }
+  uint32_t total;
+  uint32_t off = block_exclusive_scan(mine, s_scan, &total);
+  if (threadIdx.x == 0) {
+    st_relaxed_u64(L.status + tile, pack_status(t == 0 ? kFlagIncl : kFlagAgg, L.epoch, total));
+  }
+#pragma unroll
+  for (int i = 0; i < I; ++i) {
+    const uint32_t p = p0 + i;
+    if (p < F.n_points) {
+      const uint8_t* pt = F.in + static_cast<size_t>(p) * step;
+      const uint8_t* prev = (p % kChunkPoints) ? pt - step : nullptr;
+      ByteSink bs{stage + off};
+      encode_point_ops(plan, pt, prev, bs);
+      off += len[i];
+    }
+  }
+  if (threadIdx.x < 32) {
+    const uint64_t e = tile_lookback(L.status, F.tile_begin, tile, L.epoch, total);
+    if (threadIdx.x == 0) s_excl = e;
+  }
+  __syncthreads();
+  finish_tile(L, F, fi, t, stage, total, s_excl);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Specialised kernel: the regular stream is exactly one FloatN op (C1/C2 XYZ / XYZI; also the float part of C3).
+//   VEC4 = packed XYZI float32x4 at a 16-byte aligned base: one coalesced LDG.128 per point.
+// Warp-blocked point assignment: warp w owns points [w*32*I, (w+1)*32*I), lane l takes point 32*i + l of iteration i,
+// so loads are perfectly coalesced, the previous point comes from a lane shuffle and each iteration's output is one
+// contiguous byte run that is packed with word stores.
+struct FloatNParams {
+  uint32_t offset[4];
+  float mul[4];
+  uint32_t point_step;
+};
+
+// u in [1, 2^28): LEB128 bytes of u packed little-endian into one word (continuation bits included).
+__device__ __forceinline__ uint32_t varint_word_28(uint32_t u) {
+  // 7-bit groups -> bytes: adding the masked upper part to itself shifts it left by one, three times.
+  uint32_t x = u + (u & 0xFFFFFF80u);
+  x = x + (x & 0xFFFF8000u);
+  x = x + (x & 0xFF800000u);
+  // continuation flag on every byte below the most significant non-zero byte
+  const uint32_t g = x >> 8;
+  const uint32_t h = g | (g >> 8) | (g >> 16);
+  return x | ((h + 0x007F7F7Fu) & 0x00808080u);
+}
+
+template <int N, int I, bool VEC4>
+__global__ void __launch_bounds__(kThreads) encode_floatn_kernel(const EncLaunch L, const FloatNParams P) {
+  extern __shared__ __align__(16) uint8_t dyn_smem[];
+  __shared__ uint32_t s_wtot[kThreads / 32];
+  __shared__ unsigned long long s_excl;
+  uint8_t* stage = dyn_smem;
+  uint32_t* stage32 = reinterpret_cast<uint32_t*>(dyn_smem);
+
+  if (blockIdx.x == 0) handle_empty_frames(L);
+  const uint32_t tile = blockIdx.x;
+  const uint32_t fi = find_frame(L.frames, L.n_frames, tile);
+  const EncFrame F = L.frames[fi];
+  const uint32_t t = tile - F.tile_begin;
+  constexpr uint32_t T = kThreads * I;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t tile_p0 = t * T;
+  const uint32_t warp_p0 = tile_p0 + warp * 32 * I;
+  const uint32_t step = P.point_step;
+
+  // ---- loads (all issued before use: I independent 16-byte requests per thread) ----
+  float v[I][N];
+#pragma unroll
+  for (int i = 0; i < I; ++i) {
+    const uint32_t p = warp_p0 + 32 * i + lane;
+    if (p < F.n_points) {
+      if (VEC4) {
+        const float4 q = __ldcs(reinterpret_cast<const float4*>(F.in) + p);
+        v[i][0] = q.x; v[i][1] = q.y; v[i][2] = q.z;
+        if (N == 4) v[i][N - 1] = q.w;
+      } else {
+        const uint8_t* pt = F.in + static_cast<size_t>(p) * step;
+#pragma unroll
+        for (int k = 0; k < N; ++k) v[i][k] = __uint_as_float(load_u32(pt + P.offset[k]));
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < N; ++k) v[i][k] = 0.f;
+    }
+  }
+  // previous point of the warp's first point (0 at a chunk start; T divides the chunk so only tile_p0 can be one)
+  int32_t carry[N];
+#pragma unroll
+  for (int k = 0; k < N; ++k) carry[k] = 0;
+  if (warp_p0 % kChunkPoints != 0 && warp_p0 < F.n_points) {
+    const uint8_t* pt = F.in + static_cast<size_t>(warp_p0 - 1) * step;
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      const float pv = __uint_as_float(load_u32(pt + P.offset[k]));
+      carry[k] = isnan(pv) ? 0 : quant_i32_x86(pv, P.mul[k]);
+    }
+  }
+
+  // ---- phase 1: quantise, delta, varint bytes (as words), per-point sizes, warp-level offsets ----
+  uint32_t r[I][N];   // LEB128 bytes of each value (<= 4 bytes on the fast path), 0 for the NaN marker
+  uint32_t off[I];    // byte offset of the point inside the warp's run
+  uint32_t big = 0;   // some value needs 5 bytes -> whole tile takes the byte-wise slow path
+  uint32_t run = 0;   // bytes of earlier iterations of this warp
+#pragma unroll
+  for (int i = 0; i < I; ++i) {
+    const bool valid = (warp_p0 + 32 * i + lane) < F.n_points;
+    uint32_t len = 0;
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      const bool nan = isnan(v[i][k]);
+      const int32_t q = quant_i32_x86(v[i][k], P.mul[k]);
+      const int32_t pass = nan ? 0 : q;                       // what the NEXT point sees as "previous" (field_encoder.cpp:79-82)
+      int32_t prev = __shfl_up_sync(0xffffffffu, pass, 1);
+      if (lane == 0) prev = carry[k];
+      carry[k] = __shfl_sync(0xffffffffu, pass, 31);
+      const uint32_t d = static_cast<uint32_t>(q) - static_cast<uint32_t>(prev);
+      const uint32_t zz = (d << 1) ^ static_cast<uint32_t>(static_cast<int32_t>(d) >> 31);
+      const bool five = !nan && zz >= 0x0FFFFFFFu;            // zz + 1 >= 2^28 -> 5 bytes
+      big |= five ? 1u : 0u;
+      const uint32_t w = nan ? 0u : varint_word_28(zz + 1u);
+      r[i][k] = w;
+      len += five ? 5u : 1u + __popc(w & 0x00808080u);
+    }
+    if (!valid) len = 0;
+    uint32_t inc = len;
+#pragma unroll
+    for (int dlt = 1; dlt < 32; dlt <<= 1) {
+      const uint32_t x = __shfl_up_sync(0xffffffffu, inc, dlt);
+      if (lane >= dlt) inc += x;
+    }
+    off[i] = run + inc - len;
+    run += __shfl_sync(0xffffffffu, inc, 31);
+  }
+  if (lane == 0) s_wtot[warp] = run;
+  const int any_big = __syncthreads_or(static_cast<int>(big));
+  uint32_t wbase = 0, total = 0;
+#pragma unroll
+  for (int w = 0; w < kThreads / 32; ++w) {
+    const uint32_t x = s_wtot[w];
+    if (w < warp) wbase += x;
+    total += x;
+  }
+  if (threadIdx.x == 0) {
+    st_relaxed_u64(L.status + tile, pack_status(t == 0 ? kFlagIncl : kFlagAgg, L.epoch, total));
+  }
+
+  // ---- phase 2: pack bytes into the staging buffer at tile-local offsets ----
+  if (!any_big) {
+    uint32_t tail_carry = 0;  // partial last word of the previous iteration's lane 31
+#pragma unroll
+    for (int i = 0; i < I; ++i) {
+      const uint32_t pidx = warp_p0 + 32 * i + lane;
+      const bool valid = pidx < F.n_points;
+      const uint32_t l0 = 1u + __popc(r[i][0] & 0x00808080u);
+      const uint32_t l1 = 1u + __popc(r[i][1] & 0x00808080u);
+      const uint32_t l2 = 1u + __popc(r[i][2] & 0x00808080u);
+      const uint32_t l3 = (N == 4) ? 1u + __popc(r[i][N - 1] & 0x00808080u) : 0u;
+      // A = value0 | value1 << 8*l0  (<= 8 bytes)
+      const uint32_t sa = 8u * l0;
+      const uint32_t a_lo = r[i][0] | (sa < 32u ? (r[i][1] << sa) : 0u);
+      const uint32_t a_hi = __funnelshift_lc(r[i][1], 0u, sa);
+      // B = value2 | value3 << 8*l2  (<= 8 bytes)
+      uint32_t b_lo = r[i][2], b_hi = 0u;
+      if (N == 4) {
+        const uint32_t sb = 8u * l2;
+        b_lo |= (sb < 32u ? (r[i][N - 1] << sb) : 0u);
+        b_hi = __funnelshift_lc(r[i][N - 1], 0u, sb);
+      }
+      // record = A | B << 8*(l0+l1): split the shift into a word part and a 8..32-bit part
+      const uint32_t c2 = l0 + l1;                  // 2..8
+      const uint32_t ws = (c2 - 1u) >> 2;           // 0 | 1
+      const uint32_t bs = 8u * (((c2 - 1u) & 3u) + 1u);  // 8,16,24,32
+      const uint32_t x0 = bs < 32u ? (b_lo << bs) : 0u;
+      const uint32_t x1 = __funnelshift_lc(b_lo, b_hi, bs);
+      const uint32_t x2 = __funnelshift_lc(b_hi, 0u, bs);
+      uint32_t w0 = a_lo | (ws ? 0u : x0);
+      uint32_t w1 = a_hi | (ws ? x0 : x1);
+      uint32_t w2 = ws ? x1 : x2;
+      uint32_t w3 = ws ? x2 : 0u;
+      const uint32_t len = l0 + l1 + l2 + l3;       // 3..16
+      // byte position inside the tile; shift the record to its position inside the first word
+      const uint32_t pos = wbase + off[i];
+      const uint32_t s = pos & 3u, sh = 8u * s;
+      const uint32_t S0 = w0 << sh;
+      const uint32_t S1 = __funnelshift_l(w0, w1, sh);
+      const uint32_t S2 = __funnelshift_l(w1, w2, sh);
+      const uint32_t S3 = __funnelshift_l(w2, w3, sh);
+      const uint32_t S4 = __funnelshift_l(w3, 0u, sh);
+      const uint32_t nw = (s + len + 3u) >> 2;      // words touched: 1..5
+      const uint32_t e = (pos + len) & 3u;          // != 0: last word is shared with the next point
+      uint32_t tailw = (nw == 1u) ? S0 : (nw == 2u) ? S1 : (nw == 3u) ? S2 : (nw == 4u) ? S3 : S4;
+      if (e == 0u || !valid) tailw = 0u;
+      uint32_t headw = __shfl_up_sync(0xffffffffu, tailw, 1);
+      if (lane == 0) headw = tail_carry;
+      tail_carry = __shfl_sync(0xffffffffu, tailw, 31);
+      if (valid) {
+        const uint32_t W0 = pos >> 2;
+        const bool first_of_warp = (i == 0 && lane == 0);
+        const bool last_of_warp = (i == I - 1 && lane == 31) || (pidx + 1 >= F.n_points);
+        const uint32_t full = (e != 0u) ? nw - 1u : nw;  // words I own completely (tail word belongs to the next point)
+        if (first_of_warp && s != 0u) {
+          // the first word also holds bytes of the previous warp's last point: byte stores for my part
+          for (uint32_t b = s; b < 4u; ++b) stage[4u * W0 + b] = static_cast<uint8_t>(S0 >> (8u * b));
+        } else if (full > 0u) {
+          stage32[W0] = S0 | headw;
+        }
+        if (full > 1u) stage32[W0 + 1] = S1;
+        if (full > 2u) stage32[W0 + 2] = S2;
+        if (full > 3u) stage32[W0 + 3] = S3;
+        if (full > 4u) stage32[W0 + 4] = S4;
+        if (last_of_warp && e != 0u) {
+          // nobody in this warp follows: byte stores for my part of the shared word
+          const uint32_t base = 4u * (W0 + nw - 1u);
+          const uint32_t tw = (nw == 1u) ? (S0 | headw) : tailw;
+          const uint32_t b0 = (nw == 1u) ? s : 0u;
+          for (uint32_t b = b0; b < e; ++b) stage[base + b] = static_cast<uint8_t>(tw >> (8u * b));
+        }
+      }
+    }
+  } else {
+    // slow path (some |delta| >= 2^27): re-evaluate byte-wise, exactly like the generic kernel
+#pragma unroll 1
+    for (int i = 0; i < I; ++i) {
+      const uint32_t p = warp_p0 + 32 * i + lane;
+      if (p < F.n_points) {
+        const uint8_t* pt = F.in + static_cast<size_t>(p) * step;
+        const uint8_t* prevp = (p % kChunkPoints) ? pt - step : nullptr;
+        ByteSink bs{stage + wbase + off[i]};
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+          const float x = __uint_as_float(load_u32(pt + P.offset[k]));
+          if (isnan(x)) { bs.put_byte(0); continue; }
+          const int32_t q = quant_i32_x86(x, P.mul[k]);
+          int32_t pq = 0;
+          if (prevp) {
+            const float px = __uint_as_float(load_u32(prevp + P.offset[k]));
+            if (!isnan(px)) pq = quant_i32_x86(px, P.mul[k]);
+          }
+          const int32_t d = static_cast<int32_t>(static_cast<uint32_t>(q) - static_cast<uint32_t>(pq));
+          bs.put_varint(zigzag_plus1(static_cast<int64_t>(d)));
+        }
+      }
+    }
+  }
+  if (threadIdx.x < 32) {
+    const uint64_t ex = tile_lookback(L.status, F.tile_begin, tile, L.epoch, total);
+    if (threadIdx.x == 0) s_excl = ex;
+  }
+  __syncthreads();
+  finish_tile(L, F, fi, t, stage, total, s_excl);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+static uint64_t g_launches = 0;
+uint64_t kernel_launch_count() { return g_launches; }
+void count_launch(int n) { g_launches += static_cast<uint64_t>(n); }
+
+template <typename K>
+static cudaError_t set_smem(K kernel, size_t bytes) {
+  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
+}
+
+template <int N, int I>
+static int launch_floatn(const Plan& plan, const EncLaunch& L, bool vec4, cudaStream_t stream) {
+  FloatNParams P;
+  for (int k = 0; k < 4; ++k) {
+    P.offset[k] = plan.ops[0].offset[k];
+    P.mul[k] = plan.ops[0].enc_mul_f[k];
+  }
+  P.point_step = plan.point_step;
+  const size_t smem = static_cast<size_t>(kThreads) * I * 5 * N + 64;
+  if (vec4) {
+    auto k = encode_floatn_kernel<N, I, true>;
+    if (set_smem(k, smem) != cudaSuccess) return -1;
+    k<<<L.n_tiles_total, kThreads, smem, stream>>>(L, P);
+  } else {
+    auto k = encode_floatn_kernel<N, I, false>;
+    if (set_smem(k, smem) != cudaSuccess) return -1;
+    k<<<L.n_tiles_total, kThreads, smem, stream>>>(L, P);
+  }
+  count_launch();
+  return 1;
+}
+
+// Header + size for a batch that only holds empty frames (no tile exists to do it).
+__global__ void empty_frames_kernel(const EncLaunch L) { handle_empty_frames(L); }
+
+// Points per tile for a plan: the largest I in {8,4,2,1} whose staging buffer fits comfortably.
+uint32_t choose_tile_points(const Plan& plan) {
+  if (plan.floatn_only) return kThreads * 8;
+  const size_t budget = 96 * 1024;
+  for (int I = 8; I >= 1; I >>= 1) {
+    if (static_cast<size_t>(kThreads) * I * plan.max_point_bytes + sizeof(Plan) + 64 <= budget) return kThreads * I;
+  }
+  return kThreads;
+}
+
+int launch_encode_regular(const Plan& plan, const EncLaunch& L, cudaStream_t stream) {
+  if (L.n_tiles_total == 0) {
+    empty_frames_kernel<<<1, kThreads, 0, stream>>>(L);
+    count_launch();
+    return 1;
+  }
+  const char* force = getenv("CLDN_B200_FORCE_GENERIC");
+  if (plan.floatn_only && !(force && force[0] == '1')) {
+    const RegOp& op = plan.ops[0];
+    const bool packed4 = op.lanes == 4 && plan.point_step == 16 && op.offset[0] == 0 && op.offset[1] == 4 &&
+                         op.offset[2] == 8 && op.offset[3] == 12;
+    const bool vec4 = packed4 && (L.flags & kEncInputsAligned16);  // LDG.128 needs 16-byte aligned frame bases
+    if (L.tile_points != kThreads * 8) return -1;
+    if (op.lanes == 4) return launch_floatn<4, 8>(plan, L, vec4, stream);
+    return launch_floatn<3, 8>(plan, L, false, stream);
+  }
+  const EncLaunch& LL = L;
+  const uint32_t I = LL.tile_points / kThreads;
+  const size_t smem = ((sizeof(Plan) + 15) & ~size_t(15)) + static_cast<size_t>(LL.tile_points) * plan.max_point_bytes + 64;
+#define CLDN_LAUNCH_GENERIC(II)                                                         \
+  {                                                                                     \
+    auto k = encode_generic_kernel<II>;                                                 \
+    if (set_smem(k, smem) != cudaSuccess) return -1;                                    \
+    k<<<LL.n_tiles_total, kThreads, smem, stream>>>(LL);                                \
+  }
+  switch (I) {
+    case 8: CLDN_LAUNCH_GENERIC(8) break;
+    case 4: CLDN_LAUNCH_GENERIC(4) break;
+    case 2: CLDN_LAUNCH_GENERIC(2) break;
+    default: CLDN_LAUNCH_GENERIC(1) break;
+  }
+#undef CLDN_LAUNCH_GENERIC
+  count_launch();
+  return 1;
+}
+
+}  // namespace cldn

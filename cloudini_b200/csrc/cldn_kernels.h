@@ -1,0 +1,88 @@
+// Internal launch interface between the C-ABI layer (cldn_api.cu) and the kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "cldn_plan.h"
+
+namespace cldn {
+
+// One frame (one PointcloudEncoder::encode call in the reference) of a fused batch launch.
+struct EncFrame {
+  const uint8_t* in;     // n_points * point_step bytes
+  uint8_t* out;          // start of the blob (header goes here when write_header)
+  uint32_t n_points;
+  uint32_t tile_begin;   // global index of this frame's first tile (exclusive scan of n_tiles over the batch)
+  uint32_t n_tiles;
+  uint32_t n_chunks;
+  // V5: exclusive scan over chunks of the total adaptive-section bytes ((n_chunks + 1) entries), else nullptr.
+  const uint32_t* sec_excl;
+};
+
+struct EncLaunch {
+  const EncFrame* frames;  // device
+  uint32_t n_frames;
+  uint32_t n_tiles_total;
+  const Plan* plan;        // device copy
+  const uint8_t* header;   // device copy of the blob header
+  uint32_t header_bytes;   // 0 when write_header == false
+  uint64_t* status;        // n_tiles_total tile status words
+  uint32_t epoch;
+  uint64_t* sizes;         // per frame: total bytes written (header included)
+  uint32_t* err;
+  uint32_t tile_points;    // 256 * I (choose_tile_points)
+  uint32_t flags;          // kEncInputsAligned16: every frame's input base is 16-byte aligned
+};
+constexpr uint32_t kEncInputsAligned16 = 1u;
+uint32_t choose_tile_points(const Plan& plan);
+
+// Interleaved regular stream + chunk framing. Returns the number of kernels launched.
+int launch_encode_regular(const Plan& host_plan, const EncLaunch& L, cudaStream_t stream);
+
+struct DecFrame {
+  const uint8_t* payload;  // header-less payload
+  uint64_t payload_bytes;
+  uint8_t* out;
+  uint32_t n_points;       // width * height
+  uint32_t n_chunks;
+  uint32_t chunk_begin;    // global index of this frame's first chunk
+  uint32_t pad_;
+};
+
+struct DecLaunch {
+  const DecFrame* frames;  // device
+  uint32_t n_frames;
+  uint32_t n_chunks_total;
+  const Plan* plan;          // device copy
+  uint64_t* chunk_offsets;   // per global chunk: byte offset of the chunk BODY inside its payload
+  uint32_t* chunk_sizes;     // per global chunk: body size
+  uint32_t* err;
+};
+
+int launch_decode(const Plan& host_plan, const DecLaunch& L, cudaStream_t stream);
+
+// V5 adaptive integer sections (encode side).
+struct SecLaunch {
+  const EncFrame* frames;
+  uint32_t n_frames;
+  uint32_t n_chunks_total;       // over the batch
+  const uint32_t* chunk_frame;   // per global chunk: frame index
+  const uint32_t* chunk_first;   // per frame: global index of its first chunk
+  const Plan* plan;
+  uint8_t* modes;                // [n_frames][n_sections] committed AdaptiveIntMode
+  uint8_t* scratch;              // [n_chunks_total][n_sections][sec_stride] section bytes
+  uint32_t sec_stride;
+  uint32_t* sec_sizes;           // [n_chunks_total][n_sections]
+  uint32_t* sec_excl;            // per frame region: (n_chunks + 1) entries, laid out at chunk_first[f] + f
+  uint64_t* hash_scratch;        // palette hash tables
+  uint32_t* err;
+  uint32_t header_bytes;
+};
+int launch_encode_sections(const Plan& host_plan, const SecLaunch& L, cudaStream_t stream);
+int launch_place_sections(const Plan& host_plan, const SecLaunch& L, const uint64_t* status, uint32_t epoch,
+                          uint32_t tile_points, cudaStream_t stream);
+
+uint64_t kernel_launch_count();
+void count_launch(int n = 1);
+
+}  // namespace cldn

@@ -1,0 +1,108 @@
+"""Seeded synthetic PointCloud2 workloads (BASELINE.json configs C1..C5).
+
+Host-side numpy only; the same bytes are handed to the GPU path and to the oracle.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import CompressionOption, EncodingInfo, EncodingOptions, FieldType, PointField
+
+
+def _lidar_xyz(n: int, rng: np.random.Generator, rings: int = 64, az_step: float = 2 * np.pi / 2048):
+    i = np.arange(n, dtype=np.int64)
+    ring = (i % rings).astype(np.float64)
+    az = (i // rings).astype(np.float64) * az_step
+    el = np.deg2rad(-24.8 + ring * (26.8 / max(rings - 1, 1)))
+    r = 20.0 + 10.0 * np.sin(3.0 * az) + 2.0 * np.cos(7.0 * az + ring * 0.05) + rng.normal(0.0, 0.01, n)
+    x = r * np.cos(el) * np.cos(az)
+    y = r * np.cos(el) * np.sin(az)
+    z = r * np.sin(el)
+    return x.astype(np.float32), y.astype(np.float32), z.astype(np.float32)
+
+
+def info_xyz(n: int, resolution: float = 0.001, version: int = 5) -> EncodingInfo:
+    return EncodingInfo(
+        fields=[PointField("x", 0, FieldType.FLOAT32, resolution), PointField("y", 4, FieldType.FLOAT32, resolution),
+                PointField("z", 8, FieldType.FLOAT32, resolution)],
+        width=n, height=1, point_step=12, encoding_opt=EncodingOptions.LOSSY, compression_opt=CompressionOption.NONE,
+        use_threads=False, version=version)
+
+
+def info_xyzi(n: int, resolution: float = 0.001, version: int = 5) -> EncodingInfo:
+    info = info_xyz(n, resolution, version)
+    info.fields.append(PointField("intensity", 12, FieldType.FLOAT32, resolution))
+    info.point_step = 16
+    return info
+
+
+def cloud_c1(n: int = 10_000, seed: int = 1, adversarial: bool = False):
+    """C1: XYZ float32, step 12. adversarial=True sprinkles NaN, +-inf, huge magnitudes and exact .5 ties."""
+    rng = np.random.default_rng(seed)
+    x, y, z = _lidar_xyz(n, rng)
+    pts = np.stack([x, y, z], axis=1)
+    if adversarial and n > 0:
+        k = max(n // 50, 1)
+        flat = pts.reshape(-1)
+        idx = rng.choice(flat.size, size=min(4 * k, flat.size), replace=False)
+        q = max(len(idx) // 4, 1)
+        flat[idx[:q]] = np.nan
+        flat[idx[q:2 * q]] = rng.choice(np.array([np.inf, -np.inf, 3e9, -3e9, 2.2e6, -2.2e6], dtype=np.float32), size=len(idx[q:2 * q]))
+        flat[idx[2 * q:3 * q]] = (rng.integers(-5000, 5000, size=len(idx[2 * q:3 * q])).astype(np.float32) + 0.5) * np.float32(0.001)
+        flat[idx[3 * q:]] = rng.normal(0, 1e-4, size=len(idx[3 * q:])).astype(np.float32)
+    return info_xyz(n), np.ascontiguousarray(pts, dtype=np.float32).view(np.uint8).reshape(-1)
+
+
+def cloud_c2(n: int = 1_000_000, seed: int = 2):
+    """C2: XYZI float32x4, step 16, intensity = integers 0..255 as float."""
+    rng = np.random.default_rng(seed)
+    x, y, z = _lidar_xyz(n, rng)
+    inten = rng.integers(0, 256, size=n).astype(np.float32)
+    pts = np.stack([x, y, z, inten], axis=1)
+    return info_xyzi(n), np.ascontiguousarray(pts, dtype=np.float32).view(np.uint8).reshape(-1)
+
+
+def cloud_c3(n: int = 1_000_000, seed: int = 3, version: int = 5):
+    """C3: XYZ f32 + rgba u32 @16 + ring u16 @20, ROS-style padded step 32, padding filled with 0xCD."""
+    rng = np.random.default_rng(seed)
+    x, y, z = _lidar_xyz(n, rng)
+    buf = np.full((n, 32), 0xCD, dtype=np.uint8)
+    buf[:, 0:4] = x.view(np.uint8).reshape(n, 4)
+    buf[:, 4:8] = y.view(np.uint8).reshape(n, 4)
+    buf[:, 8:12] = z.view(np.uint8).reshape(n, 4)
+    rgba = (np.uint32(0xFF000000) | (rng.integers(0, 8, size=n).astype(np.uint32) * np.uint32(0x101010))).astype(np.uint32)
+    ring = (np.arange(n) % 64).astype(np.uint16)
+    buf[:, 16:20] = rgba.view(np.uint8).reshape(n, 4)
+    buf[:, 20:22] = ring.view(np.uint8).reshape(n, 2)
+    info = EncodingInfo(
+        fields=[PointField("x", 0, FieldType.FLOAT32, 0.001), PointField("y", 4, FieldType.FLOAT32, 0.001),
+                PointField("z", 8, FieldType.FLOAT32, 0.001), PointField("rgba", 16, FieldType.UINT32, None),
+                PointField("ring", 20, FieldType.UINT16, None)],
+        width=n, height=1, point_step=32, encoding_opt=EncodingOptions.LOSSY, compression_opt=CompressionOption.NONE,
+        use_threads=False, version=version)
+    return info, buf.reshape(-1)
+
+
+def cloud_c4_frame(frame: int, seed: int = 4, rings: int = 64, az: int = 2032):
+    """C4: one Velodyne-style rolling frame (64 rings x 2032 azimuths = 130048 points), XYZI float32, step 16."""
+    n = rings * az
+    rng = np.random.default_rng(seed * 100003 + frame)
+    i = np.arange(n, dtype=np.int64)
+    ring = (i % rings).astype(np.float64)
+    a = (i // rings).astype(np.float64) * (2 * np.pi / az) + 0.002 * frame
+    el = np.deg2rad(-24.8 + ring * (26.8 / (rings - 1)))
+    r = 15.0 + 8.0 * np.sin(2.0 * a + 0.01 * frame) + 3.0 * np.cos(5.0 * a) + rng.normal(0.0, 0.008, n)
+    x = (r * np.cos(el) * np.cos(a) + 0.05 * frame).astype(np.float32)
+    y = (r * np.cos(el) * np.sin(a)).astype(np.float32)
+    z = (r * np.sin(el)).astype(np.float32)
+    inten = rng.integers(0, 256, size=n).astype(np.float32)
+    pts = np.stack([x, y, z, inten], axis=1)
+    return info_xyzi(n), np.ascontiguousarray(pts, dtype=np.float32).view(np.uint8).reshape(-1)
+
+
+def fnv1a64(data) -> int:
+    """FNV-1a 64-bit (the fingerprint mcap_codec_benchmark --hash prints, tools/src/mcap_codec_benchmark.cpp:103-109)."""
+    h = 0xCBF29CE484222325
+    for b in bytes(data):
+        h = ((h ^ b) * 0x100000001B3) & 0xFFFFFFFFFFFFFFFF
+    return h

@@ -1,0 +1,22 @@
+#!/usr/bin/env bash
+# TEST INFRASTRUCTURE ONLY (oracle). Compiles the UNMODIFIED reference codec sources where they lie under
+# /root/reference (never copied into this repo) plus oracle/ref_wrapper.cpp into oracle/_ref/libcloudini_ref.so.
+# The reference's own CMake build cannot run offline (CPM downloads lz4/zstd/mcap; gtest/PCL absent), so the eight
+# codec translation units are compiled directly. -msse4.1 is mandatory: without it cast_vector4f_to_vector4i
+# (cloudini_lib/include/cloudini_lib/intrinsics.hpp:288-300) silently switches from round-to-nearest-even to std::round.
+set -euo pipefail
+HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
+REF="${CLOUDINI_REFERENCE:-/root/reference}/cloudini_lib"
+OUT="$HERE/_ref"
+if [ ! -d "$REF/src" ]; then
+  echo "build_ref.sh: reference tree not found at $REF (expected on the GPU box: the prebuilt .so travels)" >&2
+  exit 3
+fi
+mkdir -p "$OUT"
+g++ -std=c++20 -O2 -msse4.1 -fPIC -shared \
+    -I"$REF/include" -I"$REF/src" -I"$HERE/shim" \
+    "$REF"/src/{chunk_writer,cloudini,codec_common,field_encoder,field_decoder,v4_codec,v5_codec}.cpp \
+    "$HERE/ref_wrapper.cpp" \
+    -l:liblz4.so.1 -l:libzstd.so.1 -lpthread \
+    -o "$OUT/libcloudini_ref.so"
+echo "built $OUT/libcloudini_ref.so"

@@ -1,0 +1,183 @@
+// TEST INFRASTRUCTURE ONLY (oracle). Not part of the product path.
+//
+// extern "C" façade over the UNMODIFIED reference library, compiled in place from
+// /root/reference/cloudini_lib by oracle/build_ref.sh into oracle/_ref/libcloudini_ref.so.
+// It lets the tests (ctypes) and bench.py's cpu_baseline / --impl reference leg call
+//   Cloudini::PointcloudEncoder::encode      (cloudini_lib/src/cloudini.cpp:501-623)
+//   Cloudini::PointcloudDecoder::decode      (cloudini_lib/src/cloudini.cpp:635-668)
+//   Cloudini::MaxCompressedSize              (cloudini_lib/src/cloudini.cpp:249-292)
+//   Cloudini::DecodeHeader / EncodingInfoToYAML (cloudini_lib/src/cloudini.cpp:165-190,353-428)
+// The configuration crosses the boundary as the reference's own YAML header text
+// (the same convention as cldn_EncodePointcloudData, wasm_functions.h:88-93).
+//
+// No reference source is copied: this file only #includes the reference's public headers.
+#include <chrono>
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "cloudini_lib/cloudini.hpp"
+
+namespace {
+thread_local std::string g_err;
+
+Cloudini::EncodingInfo infoFromYaml(const char* yaml, int version_override, int use_threads) {
+  Cloudini::EncodingInfo info = Cloudini::EncodingInfoFromYAML(yaml);
+  // EncodingInfoFromYAML parses "version" as a single character (see the comment at
+  // cloudini.cpp:389-392), so the caller passes the numeric version explicitly.
+  info.version = static_cast<uint8_t>(version_override);
+  info.use_threads = use_threads != 0;
+  return info;
+}
+}  // namespace
+
+extern "C" {
+
+const char* ref_last_error() { return g_err.c_str(); }
+
+// Returns total bytes written (header included when write_header != 0); -1 on exception.
+long long ref_encode(const char* yaml, int version, int use_threads, const uint8_t* cloud,
+                     size_t cloud_bytes, uint8_t* out, size_t out_capacity, int write_header) {
+  try {
+    Cloudini::EncodingInfo info = infoFromYaml(yaml, version, use_threads);
+    Cloudini::PointcloudEncoder enc(info);
+    Cloudini::ConstBufferView in(cloud, cloud_bytes);
+    Cloudini::BufferView view(out, out_capacity);
+    return static_cast<long long>(enc.encode(in, view, write_header != 0));
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return -1;
+  }
+}
+
+// Sizing helper. Returns 0 on exception.
+size_t ref_max_compressed_size(const char* yaml, int version, size_t points, int include_header) {
+  try {
+    Cloudini::EncodingInfo info = infoFromYaml(yaml, version, 0);
+    return Cloudini::MaxCompressedSize(info, points, include_header != 0);
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return 0;
+  }
+}
+
+// Parses the header of a full blob. Writes the YAML text (NUL-terminated) of the decoded info to
+// yaml_out, the numeric version to *version_out, and returns the header length in bytes (-1 on error).
+long long ref_decode_header(const uint8_t* blob, size_t blob_bytes, char* yaml_out, size_t yaml_capacity,
+                            int* version_out) {
+  try {
+    Cloudini::ConstBufferView view(blob, blob_bytes);
+    Cloudini::EncodingInfo info = Cloudini::DecodeHeader(view);
+    const std::string yaml = Cloudini::EncodingInfoToYAML(info);
+    if (yaml.size() + 1 > yaml_capacity) {
+      g_err = "yaml_out too small";
+      return -1;
+    }
+    std::memcpy(yaml_out, yaml.c_str(), yaml.size() + 1);
+    *version_out = info.version;
+    return static_cast<long long>(blob_bytes - view.size());
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return -1;
+  }
+}
+
+// Decodes a full blob (header + payload) into out (caller pre-fills it; the reference only
+// writes declared field bytes). Returns 0 on success, -1 on exception.
+int ref_decode(const uint8_t* blob, size_t blob_bytes, uint8_t* out, size_t out_capacity) {
+  try {
+    Cloudini::ConstBufferView view(blob, blob_bytes);
+    Cloudini::EncodingInfo info = Cloudini::DecodeHeader(view);
+    Cloudini::PointcloudDecoder dec;
+    dec.decode(info, view, Cloudini::BufferView(out, out_capacity));
+    return 0;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return -1;
+  }
+}
+
+// Decode a header-less payload with an explicit configuration.
+int ref_decode_payload(const char* yaml, int version, const uint8_t* payload, size_t payload_bytes,
+                       uint8_t* out, size_t out_capacity) {
+  try {
+    Cloudini::EncodingInfo info = infoFromYaml(yaml, version, 0);
+    Cloudini::PointcloudDecoder dec;
+    dec.decode(info, Cloudini::ConstBufferView(payload, payload_bytes), Cloudini::BufferView(out, out_capacity));
+    return 0;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return -1;
+  }
+}
+
+// ---- timing helpers for bench.py (cpu_baseline / --impl reference) -------------------------
+// Times exactly the region mcap_codec_benchmark.cpp:454-457 / 509-512 times: encoder.encode(in, view, true)
+// and decoder.decode(...), with a pre-sized output. `threads` independent encoder instances each
+// process `reps` frames (one instance per thread: the reference's stage 1 is single-threaded).
+// Returns elapsed seconds (wall clock over all threads), or -1 on error.
+double ref_time_encode(const char* yaml, int version, const uint8_t* cloud, size_t cloud_bytes, int reps,
+                       int threads, size_t* encoded_bytes_out) {
+  try {
+    Cloudini::EncodingInfo info = infoFromYaml(yaml, version, 0);
+    const size_t points = cloud_bytes / info.point_step;
+    const size_t cap = Cloudini::MaxCompressedSize(info, points, true);
+    std::vector<std::vector<uint8_t>> outs(threads, std::vector<uint8_t>(cap));
+    std::vector<size_t> sizes(threads, 0);
+    auto work = [&](int t) {
+      Cloudini::PointcloudEncoder enc(info);
+      for (int r = 0; r < reps; ++r) {
+        Cloudini::BufferView view(outs[t].data(), outs[t].size());
+        sizes[t] = enc.encode(Cloudini::ConstBufferView(cloud, cloud_bytes), view, true);
+      }
+    };
+    const auto t0 = std::chrono::steady_clock::now();
+    if (threads == 1) {
+      work(0);
+    } else {
+      std::vector<std::thread> pool;
+      for (int t = 0; t < threads; ++t) pool.emplace_back(work, t);
+      for (auto& th : pool) th.join();
+    }
+    const auto t1 = std::chrono::steady_clock::now();
+    if (encoded_bytes_out) *encoded_bytes_out = sizes[0];
+    return std::chrono::duration<double>(t1 - t0).count();
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return -1.0;
+  }
+}
+
+double ref_time_decode(const uint8_t* blob, size_t blob_bytes, int reps, int threads) {
+  try {
+    Cloudini::ConstBufferView probe(blob, blob_bytes);
+    Cloudini::EncodingInfo info = Cloudini::DecodeHeader(probe);
+    const size_t header_bytes = blob_bytes - probe.size();
+    const size_t out_bytes = static_cast<size_t>(info.width) * info.height * info.point_step;
+    std::vector<std::vector<uint8_t>> outs(threads, std::vector<uint8_t>(out_bytes));
+    auto work = [&](int t) {
+      Cloudini::PointcloudDecoder dec;
+      for (int r = 0; r < reps; ++r) {
+        dec.decode(info, Cloudini::ConstBufferView(blob + header_bytes, blob_bytes - header_bytes),
+                   Cloudini::BufferView(outs[t].data(), outs[t].size()));
+      }
+    };
+    const auto t0 = std::chrono::steady_clock::now();
+    if (threads == 1) {
+      work(0);
+    } else {
+      std::vector<std::thread> pool;
+      for (int t = 0; t < threads; ++t) pool.emplace_back(work, t);
+      for (auto& th : pool) th.join();
+    }
+    const auto t1 = std::chrono::steady_clock::now();
+    return std::chrono::duration<double>(t1 - t0).count();
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return -1.0;
+  }
+}
+
+}  // extern "C"

@@ -1,0 +1,57 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box via gpurun)")
+
+
+@pytest.fixture(scope="session")
+def lib_built():
+    """The C-ABI library, built once per session (nvcc cross-compiles sm_100a without a GPU)."""
+    from cloudini_b200 import build
+    return build.build()
+
+
+@pytest.fixture(scope="session")
+def port(lib_built):
+    from oracle.client import PortOracle
+    return PortOracle()
+
+
+@pytest.fixture(scope="session")
+def ref(lib_built):
+    from oracle.client import RefOracle, build_ref, have_ref
+    build_ref()
+    if not have_ref():
+        pytest.skip("oracle/_ref/libcloudini_ref.so unavailable (no /root/reference here and no prebuilt copy)")
+    return RefOracle()
+
+
+@pytest.fixture(scope="session")
+def oracle(lib_built):
+    """Best available checker: the compiled reference when present, else the C port (itself pinned by test_oracle.py)."""
+    from oracle.client import best_oracle, build_ref
+    build_ref()
+    return best_oracle()
+
+
+@pytest.fixture(scope="session")
+def golden(lib_built):
+    import cloudini_b200 as cb
+    z = np.load(os.path.join(ROOT, "tests", "golden", "golden_v1.npz"))
+    names = sorted({k.split("__")[0] for k in z.files})
+    out = {}
+    for n in names:
+        info = cb.EncodingInfoFromYAML(bytes(z[n + "__yaml"]).decode())
+        info.version = int(z[n + "__version"][0])
+        info.use_threads = False
+        out[n] = (info, z[n + "__input"], bytes(z[n + "__blob"]))
+    return out

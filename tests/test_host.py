@@ -1,0 +1,105 @@
+"""CPU tests of the host-side logic of the C-ABI library (no kernels are launched):
+the library loads, exports every symbol include/cloudini_b200.h declares, and its header / YAML / sizing / planning
+helpers agree with the oracle. Compute entry points must fail loudly without a GPU (there is no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import cloudini_b200 as cb
+from cloudini_b200 import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(lib_built):
+    text = open(os.path.join(ROOT, "include", "cloudini_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(cldn_b200_\w+)\s*\(", text)))
+    assert len(declared) >= 20
+    L = C.CDLL(lib_built)
+    missing = [s for s in declared if not hasattr(L, s)]
+    assert not missing, missing
+
+
+def test_info_struct_layout_matches_header(lib_built):
+    # the ctypes mirror must match the C struct: round-trip through the library's own YAML writer/parser
+    info, _ = synth.cloud_c3(10)
+    info.encoding_config = "abc"
+    y = cb.EncodingInfoToYAML(info)
+    back = cb.EncodingInfoFromYAML(y)
+    assert cb.EncodingInfoToYAML(back) == y
+    assert [f.name for f in back.fields] == ["x", "y", "z", "rgba", "ring"]
+    assert back.fields[0].resolution == pytest.approx(0.001) and back.fields[3].resolution is None
+
+
+def test_header_yaml_text(lib_built, port):
+    # test_header.cpp:107-140 (YAML round trip) and :142-163 (default V05 vs explicit V04)
+    for version in (5, 4, 3):
+        info, _ = synth.cloud_c3(123, version=version)
+        h = cb.EncodeHeader(info)
+        assert h.startswith(b"CLOUDINI_V0%d\n" % version) and h.endswith(b"\0")
+        assert h == port.header(info)
+        parsed, used = cb.DecodeHeader(h + b"payload")
+        assert used == len(h) and parsed.version == version
+        assert cb.EncodingInfoToYAML(parsed) == cb.EncodingInfoToYAML(info)
+    y = cb.EncodingInfoToYAML(synth.info_xyz(7))
+    assert "resolution: 0.001\n" in y and y.startswith("version: 5\nwidth: 7\nheight: 1\npoint_step: 12\nencoding_opt: LOSSY\n")
+
+
+def test_header_errors(lib_built):
+    with pytest.raises(RuntimeError, match="too small"):
+        cb.DecodeHeader(b"CLOUD")
+    with pytest.raises(RuntimeError, match="magic"):
+        cb.DecodeHeader(b"NOTCLOUDINI_V05\nversion: 5\n\0")
+    with pytest.raises(RuntimeError, match="[Uu]nsupported encoding version"):
+        cb.DecodeHeader(b"CLOUDINI_V09\nversion: 9\n\0")
+    with pytest.raises(RuntimeError, match="null terminator"):  # test_header.cpp:243-262
+        cb.DecodeHeader(cb.EncodeHeader(synth.info_xyz(3))[:-1])
+
+
+def test_legacy_binary_header(lib_built):
+    # cloudini.cpp:319-343 / 395-427: binary header written by old encoders is still readable
+    import struct
+    name = b"x"
+    blob = b"CLOUDINI_V03" + struct.pack("<IIIBBH", 11, 1, 4, 1, 0, 1) + struct.pack("<H", len(name)) + name + struct.pack("<IBf", 0, 7, 0.01)
+    info, used = cb.DecodeHeader(blob + b"xx")
+    assert used == len(blob) and info.version == 3 and info.width == 11 and info.point_step == 4
+    assert info.fields[0].name == "x" and info.fields[0].type == cb.FieldType.FLOAT32
+    assert info.fields[0].resolution == pytest.approx(0.01)
+
+
+@pytest.mark.parametrize("comp", [cb.CompressionOption.NONE, cb.CompressionOption.LZ4, cb.CompressionOption.ZSTD])
+def test_max_compressed_size_matches_oracle(lib_built, port, comp):
+    for info, _ in (synth.cloud_c1(1), synth.cloud_c2(1), synth.cloud_c3(1), synth.cloud_c3(1, version=4)):
+        info.compression_opt = comp
+        for n in (0, 1, 1000, 32768, 32769, 1_000_000):
+            for hdr in (True, False):
+                assert cb.MaxCompressedSize(info, n, hdr) == port.max_compressed_size(info, n, hdr)
+
+
+def test_max_compressed_size_matches_reference(lib_built, ref):
+    for comp in cb.CompressionOption:
+        for info, _ in (synth.cloud_c2(1), synth.cloud_c3(1)):
+            info.compression_opt = comp
+            for n in (0, 5, 40_000, 1_000_000):
+                assert cb.MaxCompressedSize(info, n, True) == ref.max_compressed_size(info, n, True)
+
+
+def test_point_step_zero_rejected(lib_built):
+    info = synth.info_xyz(1)
+    info.point_step = 0
+    with pytest.raises(RuntimeError, match="point_step cannot be 0"):
+        cb.MaxCompressedSize(info, 10)
+
+
+def test_no_cpu_fallback_without_gpu(lib_built):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    info, cloud = synth.cloud_c1(100)
+    with pytest.raises(RuntimeError, match="no CPU fallback|CUDA"):
+        cb.PointcloudEncoder(info)
+    with pytest.raises(RuntimeError, match="no CPU fallback|CUDA"):
+        cb.PointcloudDecoder()
