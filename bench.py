@@ -40,14 +40,61 @@ def parse():
 
 
 class ClockSampler:
-    """Samples SM clocks / throttle reasons with nvidia-smi while the timed region runs (B200_PROFILING.md)."""
+    """Samples SM clocks / throttle reasons while the timed region runs (B200_PROFILING.md's clocks line).
+    NVML in-process (2 ms period: the timed region of this byte-stream workload lasts milliseconds, far below
+    nvidia-smi's polling granularity); falls back to `nvidia-smi -lms` when pynvml is unavailable."""
 
     def __init__(self, index: int):
         self.index = index
         self.rows = []
         self.proc = None
+        self.nvml = None
+        self.samples = []
+        self.running = False
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.running = True
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
+        self._start_smi()
+
+    def _poll(self):
+        nv = self.nvml
+        while self.running:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)
+                try:
+                    reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                except Exception:
+                    reasons = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                self.samples.append((sm, reasons))
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def _stop_nvml(self):
+        nv = self.nvml
+        self.running = False
+        self.thread.join(timeout=1)
+        try:
+            mx = nv.nvmlDeviceGetMaxClockInfo(self.handle, nv.NVML_CLOCK_SM)
+        except Exception:
+            mx = None
+        bits = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
+        reasons = sorted({k for _, r in self.samples for k, b in bits.items() if r & b})
+        sm = [s for s, _ in self.samples]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": reasons, "samples": len(sm),
+                "source": "nvml, 2 ms period, timed region only"}
+
+    def _start_smi(self):
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
@@ -63,6 +110,8 @@ class ClockSampler:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
+        if self.nvml:
+            return self._stop_nvml()
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -163,7 +212,8 @@ def main():
 
     F = args.frames
     info = synth.info_xyzi(POINTS)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream(device=dev)  # the library's kernels and the timing events share this stream
+    torch.cuda.set_stream(stream)
     enc = cb.PointcloudEncoder(info, device=local_rank, stream=stream.cuda_stream)
     dec = cb.PointcloudDecoder(device=local_rank, stream=stream.cuda_stream)
 

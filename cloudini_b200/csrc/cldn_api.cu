@@ -183,10 +183,6 @@ int cldn_b200_encoder_create(const cldn_info_t* info, int device, void* stream, 
               static_cast<int>(info->compression_opt));
     return CLDN_ERR_UNSUPPORTED;
   }
-  if (plan.n_sections > 0 && !(plan.floatn_only || plan.n_ops == 0)) {
-    set_error("V5 clouds whose regular stream holds more than the leading XYZ(I) group are not accelerated in this build");
-    return CLDN_ERR_UNSUPPORTED;
-  }
   if (int rc = select_device(device)) return rc;
   cldn_encoder* e = new cldn_encoder();
   e->info = *info;
@@ -322,7 +318,13 @@ static int encode_batch_device(cldn_encoder* e, size_t n_frames, const void* con
   if (e->plan.n_sections > 0) {
     // V5: adaptive integer sections are produced first (they determine where every later chunk starts).
     const uint32_t ns = e->plan.n_sections;
-    const uint32_t stride = 16 + kChunkPoints * 11u;  // worst case of any mode: <= 1+4 + n*(10+1) bytes
+    // worst case of any mode is DeltaRle with one run per value: 5 + n * (max varint of the field + 1) bytes
+    uint32_t per_value = 0;
+    for (uint32_t s = 0; s < ns; ++s) {
+      const uint32_t bpv = e->plan.sections[s].bpv;
+      per_value = std::max<uint32_t>(per_value, (bpv == 2 ? 3u : bpv == 4 ? 5u : 10u) + 1u);
+    }
+    const uint32_t stride = 16 + kChunkPoints * per_value;
     if (int rc = e->d_modes.reserve(n_frames * ns)) return rc;
     if (int rc = e->d_sec_scratch.reserve(static_cast<size_t>(chunks) * ns * stride)) return rc;
     if (int rc = e->d_sec_sizes.reserve(static_cast<size_t>(chunks) * ns + 1)) return rc;
@@ -331,7 +333,7 @@ static int encode_batch_device(cldn_encoder* e, size_t n_frames, const void* con
     int hcf_slot = 0;
     if (int rc = e->h_chunk_frame.acquire(static_cast<size_t>(chunks) + n_frames + 1, &hcf, &hcf_slot)) return rc;
     if (int rc = e->d_chunk_frame.reserve(static_cast<size_t>(chunks) + n_frames + 1)) return rc;
-    if (int rc = e->d_hash.reserve(static_cast<size_t>(chunks) * 65536u * 2u)) return rc;
+    if (int rc = e->d_hash.reserve(palette_overflow_scratch_bytes() / 8 + 16)) return rc;
     uint32_t cb = 0;
     for (size_t f = 0; f < n_frames; ++f) {
       EncFrame& F = hf[f];

@@ -79,6 +79,7 @@ struct SecLaunch {
   uint32_t header_bytes;
 };
 int launch_encode_sections(const Plan& host_plan, const SecLaunch& L, cudaStream_t stream);
+size_t palette_overflow_scratch_bytes();
 int launch_place_sections(const Plan& host_plan, const SecLaunch& L, const uint64_t* status, uint32_t epoch,
                           uint32_t tile_points, cudaStream_t stream);
 
