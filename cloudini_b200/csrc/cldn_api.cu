@@ -460,6 +460,11 @@ struct cldn_decoder {
   DevBuf<uint32_t> d_err;
   PinBuf<uint32_t> h_err;
   DevBuf<uint8_t> d_in, d_out;
+  DevBuf<uint32_t> d_chunk_tiles, d_chunk_tile_begin, d_stream_end, d_tsums, d_chunk_frame, d_tile_chunk;
+  DevBuf<uint64_t> d_tstatus;
+  DevBuf<uint64_t> d_trace;
+  DevBuf<uint32_t> d_counter;
+  uint32_t epoch = 0;
 };
 
 static bool same_info(const cldn_info_t& a, const cldn_info_t& b) {
@@ -549,6 +554,48 @@ static int decode_batch_device(cldn_decoder* d, const cldn_info_t& info, size_t 
   L.chunk_offsets = d->d_chunk_offsets.p;
   L.chunk_sizes = d->d_chunk_sizes.p;
   L.err = d->d_err.p;
+  L.chunk_frame = nullptr; L.tile_chunk = nullptr;
+  L.chunk_tiles = nullptr; L.chunk_tile_begin = nullptr; L.stream_end = nullptr; L.tstatus = nullptr; L.tsums = nullptr;
+  L.tile_capacity = 0; L.tile_grid = 0; L.epoch = 0; L.trace = nullptr; L.chunk_counter = nullptr;
+  const char* force_chunk = getenv("CLDN_B200_FORCE_CHUNK_DECODE");
+  if (d->plan.floatn_only && chunks > 0 && !(force_chunk && force_chunk[0] == '1')) {
+    // tile-parallel path: host upper bound on the tile count (every chunk adds at most 2 tiles of rounding/misalignment)
+    uint64_t tiles = 0;
+    for (size_t f = 0; f < n_frames; ++f) tiles += payload_bytes[f] / decode_tile_bytes() + 2ull * hf[f].n_chunks + 1;
+    if (tiles > 0x7FFFFFFFull) { set_error("batch too large"); return CLDN_ERR_UNSUPPORTED; }
+    if (int rc = d->d_chunk_tiles.reserve(static_cast<size_t>(chunks) + 1)) return rc;
+    if (int rc = d->d_chunk_tile_begin.reserve(static_cast<size_t>(chunks) + 2)) return rc;
+    if (int rc = d->d_stream_end.reserve(static_cast<size_t>(chunks) + 1)) return rc;
+    if (int rc = d->d_chunk_frame.reserve(static_cast<size_t>(chunks) + 1)) return rc;
+    if (int rc = d->d_tile_chunk.reserve(static_cast<size_t>(tiles) + 1)) return rc;
+    const size_t old_cap = d->d_tstatus.cap;
+    if (int rc = d->d_tstatus.reserve(static_cast<size_t>(tiles) + 1, true)) return rc;
+    if (d->d_tstatus.cap != old_cap || d->d_tsums.cap < d->d_tstatus.cap * 16) {
+      if (int rc = d->d_tsums.reserve(d->d_tstatus.cap * 16, true)) return rc;
+    }
+    d->epoch = (d->epoch + 1) & 0x3FFFFFu;
+    if (d->epoch == 0) {
+      CUDA_TRY(cudaMemsetAsync(d->d_tstatus.p, 0, d->d_tstatus.cap * sizeof(uint64_t), d->stream));
+      CUDA_TRY(cudaMemsetAsync(d->d_tsums.p, 0, d->d_tsums.cap * sizeof(uint32_t), d->stream));
+      d->epoch = 1;
+    }
+    L.chunk_tiles = d->d_chunk_tiles.p;
+    L.chunk_tile_begin = d->d_chunk_tile_begin.p;
+    L.stream_end = d->d_stream_end.p;
+    L.chunk_frame = d->d_chunk_frame.p;
+    L.tile_chunk = d->d_tile_chunk.p;
+    L.tstatus = d->d_tstatus.p;
+    L.tsums = d->d_tsums.p;
+    L.tile_capacity = static_cast<uint32_t>(d->d_tstatus.cap);
+    L.tile_grid = static_cast<uint32_t>(tiles);
+    L.epoch = d->epoch;
+    if (int rc = d->d_counter.reserve(4, true)) return rc;
+    L.chunk_counter = d->d_counter.p;
+    if (getenv("CLDN_B200_TRACE")) {
+      if (int rc = d->d_trace.reserve(static_cast<size_t>(tiles) * 8 + 8, true)) return rc;
+      L.trace = d->d_trace.p;
+    }
+  }
   if (launch_decode(d->plan, L, d->stream) < 0) { set_error("decode kernel launch failed"); return CLDN_ERR_CUDA; }
   CUDA_TRY(cudaGetLastError());
   return CLDN_OK;
@@ -585,6 +632,7 @@ void cldn_b200_decoder_destroy(cldn_decoder_t* d) {
   if (d->stream) cudaStreamSynchronize(d->stream);
   d->d_plan.release(); d->d_frames.release(); d->h_frames.release(); d->d_chunk_offsets.release(); d->d_chunk_sizes.release();
   d->d_err.release(); d->h_err.release(); d->d_in.release(); d->d_out.release();
+  d->d_chunk_tiles.release(); d->d_chunk_tile_begin.release(); d->d_stream_end.release(); d->d_tsums.release(); d->d_tstatus.release(); d->d_chunk_frame.release(); d->d_tile_chunk.release(); d->d_trace.release(); d->d_counter.release();
   if (d->own_stream && d->stream) cudaStreamDestroy(d->stream);
   delete d;
 }
@@ -592,6 +640,14 @@ void cldn_b200_decoder_destroy(cldn_decoder_t* d) {
 int cldn_b200_decoder_sync(cldn_decoder_t* d) {
   if (!d) { set_error("null decoder"); return CLDN_ERR_INVALID_ARGUMENT; }
   CUDA_TRY(cudaSetDevice(d->device));
+  if (const char* tp = getenv("CLDN_B200_TRACE")) {  // development aid: dump the per-tile phase timestamps
+    if (d->d_trace.p) {
+      cudaStreamSynchronize(d->stream);
+      std::vector<uint64_t> h(d->d_trace.cap);
+      cudaMemcpy(h.data(), d->d_trace.p, h.size() * 8, cudaMemcpyDeviceToHost);
+      if (FILE* f = fopen(tp, "wb")) { fwrite(h.data(), 8, h.size(), f); fclose(f); }
+    }
+  }
   return check_device_error(d->stream, d->d_err.p, d->h_err.p);
 }
 

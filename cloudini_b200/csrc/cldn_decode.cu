@@ -659,7 +659,11 @@ __global__ void __launch_bounds__(kThreads) decode_chunks_kernel(const DecLaunch
   uint8_t* out = F.out + static_cast<size_t>(c) * kChunkPoints * plan.point_step;
 
   uint32_t pos = 0;
-  if (plan.values_per_point > 0) {
+  if (L.tile_grid > 0) {
+    // the regular stream was decoded by decode_tiles_kernel; sections start where it ended
+    pos = L.stream_end[gc];
+    if (pos > body_bytes) return;  // regular stream failed (error already reported)
+  } else if (plan.values_per_point > 0) {
     const uint32_t used = decode_varint_stream<KT>(body, body_bytes, n_points, static_cast<int>(plan.values_per_point), s_slots,
                                                    out, plan.point_step, sh, tile_bytes, vals_raw, nanbits, L.err);
     if (used == 0xFFFFFFFFu) return;
@@ -781,7 +785,19 @@ int launch_decode(const Plan& plan, const DecLaunch& L, cudaStream_t stream) {
   if (L.n_chunks_total == 0 && L.n_frames == 0) return 0;
   walk_chunks_kernel<<<(L.n_frames + 127) / 128, 128, 0, stream>>>(L);
   ++launches;
-  if (L.n_chunks_total > 0) {
+  if (L.n_chunks_total > 0 && L.tile_grid > 0) {
+    // FloatN-only regular stream: tile-parallel kernel; V5 sections (if any) by the per-chunk kernel afterwards
+    const int n = launch_decode_tiles(plan, L, stream);
+    if (n < 0) return -1;
+    launches += n;
+    if (plan.n_sections > 0) {
+      const size_t smem = dec_smem_bytes(false);
+      auto k = decode_chunks_kernel<0>;
+      if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess) return -1;
+      k<<<L.n_chunks_total, kThreads, smem, stream>>>(L);
+      ++launches;
+    }
+  } else if (L.n_chunks_total > 0) {
     const bool varint_ok = plan.all_varint || plan.n_ops == 0;
     if (varint_ok) {
       const int K = static_cast<int>(plan.values_per_point);

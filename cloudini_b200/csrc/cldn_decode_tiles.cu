@@ -1,0 +1,626 @@
+// Tile-parallel DECODE of FloatN-only regular streams (XYZ / XYZI: BASELINE configs C1, C2, C5 and the float part of C3).
+//
+// Same arithmetic as FieldDecoderFloatN_Lossy::decode (cloudini_lib/src/field_decoder.cpp:43-86), different shape:
+// the chunk's byte stream is cut into fixed 4 KB tiles, one CTA per tile, all tiles of all chunks of all frames in
+// one launch. Two decoupled look-backs over the tiles of a chunk replace the sequential walk:
+//   (1) number of values (terminator bytes) before the tile  -> which point / field every value belongs to,
+//   (2) per-field sum of deltas since the last NaN reset       -> absolute quantised value at the tile start.
+// Inside a tile: a byte with a clear MSB ends a value; a CTA scan ranks the terminators and compacts their positions;
+// then one thread per VALUE rebuilds the varint from two aligned shared-memory words (no byte loop), and one thread
+// per POINT run does the segmented prefix sum, the int->float conversion and the strided store.
+#include <stdio.h>
+
+#include "cldn_device.cuh"
+#include "cldn_kernels.h"
+
+namespace cldn {
+
+constexpr int kVec = 2;         // adjacent 16-byte vectors per thread
+constexpr int kTB = kThreads * 16 * kVec;  // stream bytes per tile (8192)
+constexpr int kTLook = 16;     // look-behind bytes staged in front of the tile
+constexpr uint32_t kRecWords = 8;  // look-back record: sum[4], rst, flag, pad, pad
+
+// ---- per-chunk tile counts and their exclusive scan (grid of the tile kernel is an upper bound computed on the host)
+__global__ void count_tiles_kernel(const DecLaunch L) {
+  const uint32_t gc = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gc >= L.n_chunks_total) return;
+  // frame of this chunk
+  uint32_t lo = 0, hi = L.n_frames - 1;
+  while (lo < hi) {
+    const uint32_t mid = (lo + hi + 1) >> 1;
+    if (L.frames[mid].chunk_begin <= gc) lo = mid; else hi = mid - 1;
+  }
+  const uint8_t* body = L.frames[lo].payload + L.chunk_offsets[gc];
+  const uint32_t mis = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(body) & 15u);
+  const uint32_t size = L.chunk_sizes[gc];
+  L.chunk_tiles[gc] = size ? (size + mis + kTB - 1) / kTB : 0;
+  L.chunk_frame[gc] = lo;
+  L.stream_end[gc] = 0xFFFFFFFFu;  // set by the tile that decodes the chunk's last regular value
+  const uint32_t chunk = gc - L.frames[lo].chunk_begin;
+  const uint32_t n_points = min(kChunkPoints, L.frames[lo].n_points - chunk * kChunkPoints);
+  if (size == 0 && n_points * L.plan->values_per_point > 0) report_error(L.err, DEV_ERR_TRUNCATED);
+}
+
+// single CTA: exclusive scan of chunk_tiles -> chunk_tile_begin[0..n], total in chunk_tile_begin[n]
+__global__ void scan_tiles_kernel(const DecLaunch L) {
+  __shared__ uint32_t s_scan[kThreads / 32 + 1];
+  uint32_t base = 0;
+  for (uint32_t c0 = 0; c0 < L.n_chunks_total; c0 += kThreads) {
+    const uint32_t c = c0 + threadIdx.x;
+    const uint32_t v = c < L.n_chunks_total ? L.chunk_tiles[c] : 0;
+    uint32_t total;
+    const uint32_t ex = block_exclusive_scan(v, s_scan, &total);
+    if (c < L.n_chunks_total) {
+      L.chunk_tile_begin[c] = base + ex;
+      for (uint32_t k = 0; k < v; ++k) L.tile_chunk[base + ex + k] = c;  // tile -> chunk table (<= ~60 tiles per chunk)
+    }
+    base += total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) L.chunk_tile_begin[L.n_chunks_total] = base;
+}
+
+// ---- segmented sums over K int32 slots ------------------------------------------------------------------------------
+template <int K>
+struct SegK {
+  int32_t sum[K];
+  uint32_t rst;
+};
+__device__ __forceinline__ int32_t wadd32(int32_t a, int32_t b) { return static_cast<int32_t>(static_cast<uint32_t>(a) + static_cast<uint32_t>(b)); }
+template <int K>
+__device__ __forceinline__ SegK<K> seg_then(const SegK<K>& a, const SegK<K>& b) {  // a earlier in the stream than b
+  SegK<K> r;
+#pragma unroll
+  for (int j = 0; j < K; ++j) r.sum[j] = ((b.rst >> j) & 1u) ? b.sum[j] : wadd32(a.sum[j], b.sum[j]);
+  r.rst = a.rst | b.rst;
+  return r;
+}
+template <int K>
+__device__ __forceinline__ SegK<K> seg_shfl_up(const SegK<K>& a, int d) {
+  SegK<K> r;
+#pragma unroll
+  for (int j = 0; j < K; ++j) r.sum[j] = __shfl_up_sync(0xffffffffu, a.sum[j], d);
+  r.rst = __shfl_up_sync(0xffffffffu, a.rst, d);
+  return r;
+}
+template <int K>
+__device__ __forceinline__ SegK<K> seg_shfl(const SegK<K>& a, int src) {
+  SegK<K> r;
+#pragma unroll
+  for (int j = 0; j < K; ++j) r.sum[j] = __shfl_sync(0xffffffffu, a.sum[j], src);
+  r.rst = __shfl_sync(0xffffffffu, a.rst, src);
+  return r;
+}
+template <int K>
+__device__ __forceinline__ SegK<K> seg_identity() {
+  SegK<K> r;
+#pragma unroll
+  for (int j = 0; j < K; ++j) r.sum[j] = 0;
+  r.rst = 0;
+  return r;
+}
+
+struct TileShared {
+  uint32_t scan[kThreads / 32 + 1];
+  uint32_t done;  // values of this chunk before the tile
+  int32_t w_sum[kThreads / 32][4];
+  uint32_t w_rst[kThreads / 32];
+  int32_t carry[4];
+};
+
+// ---- look-back 2 records: K self-validating 64-bit words per tile ---------------------------------------------------
+// word j = [63:42] epoch  [41:38] reset mask (word 0 only)  [33:32] state (1 aggregate, 2 inclusive)  [31:0] sum[j]
+// Every word carries its own tag, so no fence / flag ordering is needed: a reader retries until all K words show the
+// current epoch and the same state.
+__device__ __forceinline__ uint64_t rec_word(uint32_t epoch, uint32_t rst, uint32_t state, int32_t sum) {
+  return (static_cast<uint64_t>(epoch & 0x3FFFFFu) << 42) | (static_cast<uint64_t>(rst & 0xFu) << 38) |
+         (static_cast<uint64_t>(state & 3u) << 32) | static_cast<uint32_t>(sum);
+}
+template <int K>
+__device__ __forceinline__ void publish_words(uint64_t* rec, const SegK<K>& v, uint32_t epoch, uint32_t state) {
+#pragma unroll
+  for (int j = 0; j < K; ++j) st_relaxed_u64(rec + j, rec_word(epoch, j == 0 ? v.rst : 0u, state, v.sum[j]));
+}
+// Returns the state (0 = not ready / torn) and fills v.
+template <int K>
+__device__ __forceinline__ uint32_t read_words(const uint64_t* rec, uint32_t epoch, SegK<K>& v) {
+  uint64_t w[K];
+#pragma unroll
+  for (int j = 0; j < K; ++j) w[j] = ld_relaxed_u64(rec + j);
+  const uint32_t state = static_cast<uint32_t>(w[0] >> 32) & 3u;
+  bool ok = state != 0;
+#pragma unroll
+  for (int j = 0; j < K; ++j) {
+    ok = ok && (static_cast<uint32_t>(w[j] >> 42) == (epoch & 0x3FFFFFu)) && ((static_cast<uint32_t>(w[j] >> 32) & 3u) == state);
+    v.sum[j] = static_cast<int32_t>(static_cast<uint32_t>(w[j]));
+  }
+  v.rst = static_cast<uint32_t>(w[0] >> 38) & 0xFu;
+  return ok ? state : 0u;
+}
+
+// Warp-wide look-back over the records of the tiles [first, me) of a chunk; returns the combination of all
+// predecessors (stream order) to every lane.
+template <int K>
+__device__ __forceinline__ SegK<K> sums_lookback(const uint64_t* recs, uint32_t first, uint32_t me, uint32_t epoch) {
+  const int lane = threadIdx.x & 31;
+  SegK<K> acc = seg_identity<K>();  // combination of the predecessors inspected so far (they all FOLLOW the next batch)
+  int64_t idx = static_cast<int64_t>(me) - 1;
+  while (idx >= static_cast<int64_t>(first)) {
+    const int64_t mine = idx - lane;
+    SegK<K> r = seg_identity<K>();
+    bool is_incl = true;  // virtual tiles before the chunk start: inclusive identity
+    if (mine >= static_cast<int64_t>(first)) {
+      uint32_t st;
+      do { st = read_words<K>(recs + mine * 4, epoch, r); } while (st == 0);
+      is_incl = (st == 2u);
+    }
+    const uint32_t incl_mask = __ballot_sync(0xffffffffu, is_incl);
+    const int stop = incl_mask ? (__ffs(incl_mask) - 1) : 31;
+    if (lane > stop) r = seg_identity<K>();
+    // ordered reduction: lane index grows backwards in the stream, so lane l's partial (lanes 0..l) = r_l then partial(l-1)
+    SegK<K> inc = r;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const SegK<K> up = seg_shfl_up<K>(inc, d);
+      if (lane >= d) inc = seg_then<K>(inc, up);
+    }
+    const SegK<K> batch = seg_shfl<K>(inc, 31);  // lanes > stop hold identities, so lane 31 has the batch up to `stop`
+    acc = seg_then<K>(batch, acc);
+    if (incl_mask) break;
+    idx -= 32;
+  }
+  return acc;
+}
+
+// Rebuilds the varint that ends at tile byte `e` (biased by kTLook) and is `len` bytes long. Returns the int32 delta;
+// sets nan for the single-byte 0x00 marker and bad (a DevError code) when the bytes do not form a valid value.
+__device__ __forceinline__ int32_t decode_value(const uint8_t* tile_bytes, uint32_t e, uint32_t len, bool& nan, uint32_t& bad) {
+  int32_t delta = 0;
+  if (len <= 5u) {
+    const uint32_t* wp = reinterpret_cast<const uint32_t*>(tile_bytes) + (e >> 2);
+    const uint32_t W1 = wp[0], W0 = wp[-1];
+    const uint32_t shl = 8u * (3u - (e & 3u));
+    const uint32_t hi = __funnelshift_l(W0, W1, shl);  // byte e is now the top byte of hi
+    uint32_t x, b4 = 0;
+    if (len <= 4u) {
+      x = hi >> (32u - 8u * len);
+    } else {
+      x = __funnelshift_r(W0 << shl, hi, 24);
+      b4 = hi >> 24;
+    }
+    x &= 0x7F7F7F7Fu;
+    x = x - ((x & 0x7F007F00u) >> 1);              // 7-bit groups -> 14-bit groups
+    x = (x & 0x3FFFu) | ((x >> 2) & 0x0FFFC000u);  // -> 28-bit value
+    if ((x | b4) == 0u) {
+      if (len == 1u) nan = true; else bad = DEV_ERR_NAN_MARKER;
+    } else if (b4 == 0u) {
+      const uint32_t um = x - 1u;                    // (uval - 1) un-zigzagged, truncated to int32 (field_decoder.cpp:68)
+      delta = static_cast<int32_t>((um >> 1) ^ (0u - (um & 1u)));
+    } else {
+      const unsigned long long u = static_cast<unsigned long long>(x) | (static_cast<unsigned long long>(b4) << 28);
+      delta = static_cast<int32_t>(unzigzag(u - 1ull));
+    }
+  } else {
+    // long varint (never produced by the FloatN encoder, but decodable by the reference): byte loop, <= 10 bytes
+    unsigned long long u = 0;
+    if (len > 10u) bad = DEV_ERR_VARINT_OVERFLOW;
+    else {
+      for (uint32_t k = 0; k < len; ++k) {
+        const unsigned long long payload = tile_bytes[e - len + 1 + k] & 0x7Fu;
+        if (k == 9 && payload > 1) bad = DEV_ERR_VARINT_OVERFLOW;
+        u |= payload << (7 * k);
+      }
+    }
+    if (!bad) {
+      if (u == 0) bad = DEV_ERR_NAN_MARKER;
+      else delta = static_cast<int32_t>(unzigzag(u - 1ull));
+    }
+  }
+  return delta;
+}
+
+// Per-thread value run with the field phase PH known at compile time: value k of the run belongs to field (PH + k) % K.
+template <int K, int VTMAX, int PH>
+struct RunOps {
+  static __device__ __forceinline__ SegK<K> reduce(const int32_t (&d)[VTMAX], unsigned long long nanm, uint32_t n) {
+    SegK<K> m = seg_identity<K>();
+#pragma unroll
+    for (int k = 0; k < VTMAX; ++k) {
+      if (k >= static_cast<int>(n)) break;
+      constexpr int dummy = 0; (void)dummy;
+      const int j = (PH + k) % K;
+      if ((nanm >> k) & 1ull) { m.sum[j] = 0; m.rst |= 1u << j; }
+      else m.sum[j] = wadd32(m.sum[j], d[k]);
+    }
+    return m;
+  }
+  static __device__ __forceinline__ void emit(const int32_t (&d)[VTMAX], unsigned long long nanm, uint32_t n, int32_t (&cur)[K],
+                                              uint8_t* out, uint32_t pbase, uint32_t step, const float (&mul)[4],
+                                              const uint32_t (&off)[4]) {
+#pragma unroll
+    for (int k = 0; k < VTMAX; ++k) {
+      if (k >= static_cast<int>(n)) break;
+      const int j = (PH + k) % K;
+      const bool nan = (nanm >> k) & 1ull;
+      if (nan) cur[j] = 0; else cur[j] = wadd32(cur[j], d[k]);
+      if (off[j] != CLDN_SKIP_STORE_OFFSET) {
+        const float f = nan ? __uint_as_float(0x7FC00000u) : __fmul_rn(__int2float_rn(cur[j]), mul[j]);
+        store_u32(out + static_cast<size_t>(pbase + (PH + k) / K) * step + off[j], __float_as_uint(f));
+      }
+    }
+  }
+};
+
+__device__ __forceinline__ uint64_t gtimer() { uint64_t t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define TRACE(slot) do { if (L.trace && threadIdx.x == 0) L.trace[static_cast<size_t>(gt) * 8 + (slot)] = gtimer(); } while (0)
+
+// ---- tile building blocks shared by the tile-parallel and the chunk-sequential kernel -------------------------------
+// Loads tile `t` of a chunk body into tile_bytes (with a 16-byte look-behind) and returns this thread's terminator mask.
+// tile_bytes[kTLook + i] = stream byte tile_b0 + i; every thread owns kVec adjacent 16-byte vectors.
+// Bytes before the stream start read as 0x00 ("boundary": a value can never extend across them, and they are not
+// counted as values); bytes past the end read as 0x80 (never terminate anything).
+__device__ __forceinline__ uint32_t tile_load_masks(uint8_t* tile_bytes, const uint8_t* aligned, const uint8_t* body, uint32_t size,
+                                                    uint32_t t, int64_t tile_b0) {
+  uint32_t tmask = 0;  // bit j: byte j of my kVec*16 bytes ends a value (and lies inside the stream)
+#pragma unroll
+  for (int vv = 0; vv < kVec; ++vv) {
+    const uint32_t i = (threadIdx.x * kVec + vv) * 16u;
+    const int64_t b = tile_b0 + i;
+    uint32_t w0, w1, w2, w3;
+    if (b >= 0 && b + 16 <= static_cast<int64_t>(size)) {
+      const uint4 q = __ldcs(reinterpret_cast<const uint4*>(aligned + static_cast<size_t>(t) * kTB + i));
+      w0 = q.x; w1 = q.y; w2 = q.z; w3 = q.w;
+    } else {
+      w0 = w1 = w2 = w3 = 0;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        const int64_t bb = b + k;
+        uint32_t byte = 0x80u;
+        if (bb < 0) byte = 0u;
+        else if (bb < static_cast<int64_t>(size)) byte = body[bb];
+        const uint32_t v = byte << (8 * (k & 3));
+        if ((k >> 2) == 0) w0 |= v; else if ((k >> 2) == 1) w1 |= v; else if ((k >> 2) == 2) w2 |= v; else w3 |= v;
+      }
+    }
+    *reinterpret_cast<uint4*>(tile_bytes + kTLook + i) = make_uint4(w0, w1, w2, w3);
+    // terminator flags: bit 7 of every byte inverted; (x * 0x00204081) >> 28 collects bits 7,15,23,31 into a nibble
+    const uint32_t x0 = ~w0 & 0x80808080u, x1 = ~w1 & 0x80808080u, x2 = ~w2 & 0x80808080u, x3 = ~w3 & 0x80808080u;
+    uint32_t m16 = ((x0 * 0x00204081u) >> 28) | (((x1 * 0x00204081u) >> 28) << 4) | (((x2 * 0x00204081u) >> 28) << 8) |
+                   (((x3 * 0x00204081u) >> 28) << 12);
+    if (b < 0) {  // bytes before the stream start are not values
+      const int64_t nb = -b;
+      m16 &= nb >= 16 ? 0u : (0xFFFFu << nb);
+    }
+    tmask |= m16 << (16 * vv);
+  }
+  if (threadIdx.x < 4) {  // look-behind
+    uint32_t v = 0;  // before the stream start: boundaries
+    if (t > 0) {
+      v = *reinterpret_cast<const uint32_t*>(aligned + static_cast<size_t>(t) * kTB - 16 + 4 * threadIdx.x);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (tile_b0 - 16 + 4 * static_cast<int64_t>(threadIdx.x) + k < 0) v &= ~(0xFFu << (8 * k));
+      }
+    }
+    reinterpret_cast<uint32_t*>(tile_bytes)[threadIdx.x] = v;
+  }
+  return tmask;
+}
+
+// CTA scan of the terminator counts + compaction of their tile byte positions into pos16. Ends with a barrier.
+__device__ __forceinline__ uint32_t tile_rank_compact(uint32_t tmask, uint16_t* pos16, uint32_t* scan) {
+  uint32_t tile_cnt;
+  uint32_t rank = block_exclusive_scan(__popc(tmask), scan, &tile_cnt);
+  uint32_t m = tmask;
+  const uint32_t base = threadIdx.x * kVec * 16u;
+  while (m) {
+    const int j = __ffs(m) - 1;
+    m &= m - 1;
+    pos16[rank++] = static_cast<uint16_t>(base + j);
+  }
+  __syncthreads();
+  return tile_cnt;
+}
+
+// Decodes this thread's run of VT consecutive values (starting at value v0 of the tile) into registers.
+template <int VTMAX>
+__device__ __forceinline__ void tile_decode_run(const uint8_t* tile_bytes, const uint16_t* pos16, uint32_t tile_cnt, uint32_t VT,
+                                                uint32_t v0, int32_t (&d)[VTMAX], unsigned long long& nanm, uint32_t& badcode,
+                                                uint32_t& badk) {
+  nanm = 0;
+  badcode = 0;
+  badk = 0xFFFFFFFFu;
+  uint32_t prev_end;  // tile byte index (biased) of the byte before my first value
+  if (v0 == 0) {
+    // first byte of value 0: walk back from its terminator over continuation bytes (at most 10; stops at a boundary)
+    int s = kTLook;
+    if (tile_cnt > 0) {
+      const int e = kTLook + pos16[0];
+      s = e;
+      while (s > 0 && e - s < 11 && (tile_bytes[s - 1] & 0x80u)) --s;
+    }
+    prev_end = static_cast<uint32_t>(s) - 1u;
+  } else {
+    prev_end = (v0 - 1 < tile_cnt) ? kTLook + pos16[v0 - 1] : 0u;
+  }
+#pragma unroll
+  for (int k = 0; k < VTMAX; ++k) {
+    if (k >= static_cast<int>(VT)) break;
+    d[k] = 0;
+    const uint32_t vi = v0 + k;
+    if (vi < tile_cnt) {
+      const uint32_t e = kTLook + pos16[vi];
+      bool nan = false;
+      uint32_t bad = 0;
+      d[k] = decode_value(tile_bytes, e, e - prev_end, nan, bad);
+      if (nan) nanm |= 1ull << k;
+      if (bad && badk == 0xFFFFFFFFu) { badcode = bad; badk = k; }
+      prev_end = e;
+    }
+  }
+}
+
+template <int K, int VTMAX>
+__device__ __forceinline__ SegK<K> run_reduce(uint32_t phase, const int32_t (&d)[VTMAX], unsigned long long nanm, uint32_t n) {
+  switch (phase) {
+    case 0: return RunOps<K, VTMAX, 0>::reduce(d, nanm, n);
+    case 1: return RunOps<K, VTMAX, 1>::reduce(d, nanm, n);
+    case 2: return RunOps<K, VTMAX, 2>::reduce(d, nanm, n);
+    default: return RunOps<K, VTMAX, (K > 3 ? 3 : 0)>::reduce(d, nanm, n);
+  }
+}
+template <int K, int VTMAX>
+__device__ __forceinline__ void run_emit(uint32_t phase, const int32_t (&d)[VTMAX], unsigned long long nanm, uint32_t n, int32_t (&cur)[K],
+                                         uint8_t* out, uint32_t pbase, uint32_t step, const float (&mul)[4], const uint32_t (&off)[4]) {
+  switch (phase) {
+    case 0: RunOps<K, VTMAX, 0>::emit(d, nanm, n, cur, out, pbase, step, mul, off); break;
+    case 1: RunOps<K, VTMAX, 1>::emit(d, nanm, n, cur, out, pbase, step, mul, off); break;
+    case 2: RunOps<K, VTMAX, 2>::emit(d, nanm, n, cur, out, pbase, step, mul, off); break;
+    default: RunOps<K, VTMAX, (K > 3 ? 3 : 0)>::emit(d, nanm, n, cur, out, pbase, step, mul, off); break;
+  }
+}
+
+// CTA-wide exclusive segmented scan of one SegK per thread (two barriers); *total = combination of all threads.
+template <int K>
+__device__ __forceinline__ SegK<K> cta_seg_exclusive(const SegK<K>& mine, TileShared& sh, SegK<K>* total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  SegK<K> inc = mine;
+#pragma unroll
+  for (int dd = 1; dd < 32; dd <<= 1) {
+    const SegK<K> up = seg_shfl_up<K>(inc, dd);
+    if (lane >= dd) inc = seg_then<K>(up, inc);
+  }
+  if (lane == 31) {
+#pragma unroll
+    for (int j = 0; j < K; ++j) sh.w_sum[warp][j] = inc.sum[j];
+    sh.w_rst[warp] = inc.rst;
+  }
+  __syncthreads();
+  SegK<K> prefix = seg_identity<K>(), tot = seg_identity<K>();
+#pragma unroll
+  for (int ww = 0; ww < kThreads / 32; ++ww) {
+    SegK<K> x;
+#pragma unroll
+    for (int j = 0; j < K; ++j) x.sum[j] = sh.w_sum[ww][j];
+    x.rst = sh.w_rst[ww];
+    if (ww < warp) prefix = seg_then<K>(prefix, x);
+    tot = seg_then<K>(tot, x);
+  }
+  *total = tot;
+  SegK<K> ex = prefix;
+  const SegK<K> prev_lane = seg_shfl_up<K>(inc, 1);
+  if (lane > 0) ex = seg_then<K>(prefix, prev_lane);
+  return ex;
+}
+
+// ---- tile-parallel kernel: one CTA per 8 KB tile, two decoupled look-backs (small batches / single frames) ----------
+template <int K>
+__global__ void __launch_bounds__(kThreads, 3) decode_tiles_kernel(const DecLaunch L, float m0, float m1, float m2, float m3,
+                                                                   uint32_t o0, uint32_t o1, uint32_t o2, uint32_t o3) {
+  extern __shared__ __align__(16) uint8_t dyn_smem[];
+  __shared__ TileShared sh;
+  uint8_t* tile_bytes = dyn_smem;                                               // kTLook + kTB + 16
+  uint16_t* pos16 = reinterpret_cast<uint16_t*>(dyn_smem + kTLook + kTB + 16);  // kTB entries: tile byte index of every terminator
+  constexpr int VTMAX = ((kTB / kThreads) + K - 1) / K * K;                     // values per thread if every value is one byte
+
+  const uint32_t gt = blockIdx.x;
+  if (gt >= L.chunk_tile_begin[L.n_chunks_total]) return;
+  TRACE(0);
+  const uint32_t gc = L.tile_chunk[gt];
+  const DecFrame F = L.frames[L.chunk_frame[gc]];
+  const uint32_t chunk = gc - F.chunk_begin;
+  const uint32_t n_points = min(kChunkPoints, F.n_points - chunk * kChunkPoints);
+  const uint32_t V = n_points * K;
+  const uint32_t first_tile = L.chunk_tile_begin[gc];
+  const uint32_t t = gt - first_tile;
+  const uint8_t* body = F.payload + L.chunk_offsets[gc];
+  const uint32_t size = L.chunk_sizes[gc];
+  const uint32_t mis = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(body) & 15u);
+  const uint8_t* aligned = body - mis;
+  const int64_t tile_b0 = static_cast<int64_t>(t) * kTB - mis;  // stream offset of tile byte 0
+  const uint32_t step = L.plan->point_step;
+  uint8_t* out = F.out + static_cast<size_t>(chunk) * kChunkPoints * step;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint64_t* recs = reinterpret_cast<uint64_t*>(L.tsums);
+
+  const uint32_t tmask = tile_load_masks(tile_bytes, aligned, body, size, t, tile_b0);
+  const uint32_t tile_cnt = tile_rank_compact(tmask, pos16, sh.scan);
+  TRACE(1);
+  // ---- look-back 1 (warp 0): values before this tile; overlapped with the value decoding of the other warps ----
+  if (warp == 0) {
+    const uint64_t ex = tile_lookback(L.tstatus, first_tile, gt, L.epoch, tile_cnt);
+    if (lane == 0) sh.done = static_cast<uint32_t>(ex > 0xFFFFFFFFull ? 0xFFFFFFFFull : ex);
+  }
+  TRACE(2);
+  // ---- every thread decodes a run of VT consecutive values (VT a multiple of K) into registers ----
+  const uint32_t VT = ((tile_cnt + kThreads - 1) / kThreads + K - 1) / K * K;  // <= VTMAX
+  const uint32_t v0 = threadIdx.x * VT;
+  int32_t d[VTMAX];
+  unsigned long long nanm;
+  uint32_t badcode, badk;
+  tile_decode_run<VTMAX>(tile_bytes, pos16, tile_cnt, VT, v0, d, nanm, badcode, badk);
+  TRACE(3);
+  __syncthreads();
+  TRACE(4);
+  const uint32_t done = sh.done;
+  // Tiles past the end of the regular stream (V5 sections / trailing bytes) are never waited on by anyone.
+  if (done >= V) return;
+  const uint32_t take = min(tile_cnt, V - done);
+  // "ran out of bytes": the chunk's last tile still misses values (v4_codec.cpp:102-104)
+  if (t + 1 == L.chunk_tiles[gc] && done + tile_cnt < V && threadIdx.x == 0) report_error(L.err, DEV_ERR_TRUNCATED);
+  if (take > 0 && done + take == V && threadIdx.x == 0) {
+    L.stream_end[gc] = static_cast<uint32_t>(tile_b0 + pos16[take - 1] + 1);  // first byte after the regular stream
+  }
+  const uint32_t n_mine = v0 < take ? min(VT, take - v0) : 0u;  // my values that belong to the regular stream
+  if (badk < n_mine) report_error(L.err, badcode);            // bytes past the stream may be anything: only real values count
+
+  // ---- per-field segmented sums of my run; the field of value k is (done + v0 + k) % K = (done % K + k) % K ----
+  const uint32_t phase = done % K;
+  const SegK<K> mine = run_reduce<K, VTMAX>(phase, d, nanm, n_mine);
+  SegK<K> total;
+  const SegK<K> ex = cta_seg_exclusive<K>(mine, sh, &total);
+  TRACE(5);
+  // ---- look-back 2: per-field value at the tile start ----
+  if (warp == 0) {
+    SegK<K> carry_in = seg_identity<K>();
+    if (t == 0) {
+      if (lane == 0) publish_words<K>(recs + static_cast<size_t>(gt) * 4, total, L.epoch, 2u);
+    } else {
+      if (lane == 0) publish_words<K>(recs + static_cast<size_t>(gt) * 4, total, L.epoch, 1u);
+      carry_in = sums_lookback<K>(recs, first_tile, gt, L.epoch);
+      if (lane == 0) publish_words<K>(recs + static_cast<size_t>(gt) * 4, seg_then<K>(carry_in, total), L.epoch, 2u);
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int j = 0; j < K; ++j) sh.carry[j] = carry_in.sum[j];  // sum since the last reset == absolute value (0 at chunk start)
+    }
+  }
+  __syncthreads();
+  TRACE(6);
+  const float mul[4] = {m0, m1, m2, m3};
+  const uint32_t off[4] = {o0, o1, o2, o3};
+  int32_t cur[K];
+#pragma unroll
+  for (int j = 0; j < K; ++j) cur[j] = ((ex.rst >> j) & 1u) ? ex.sum[j] : wadd32(sh.carry[j], ex.sum[j]);
+  const uint32_t pbase = (done + v0) / K;  // point of my first value (v0 is a multiple of K, so all threads share `phase`)
+  run_emit<K, VTMAX>(phase, d, nanm, n_mine, cur, out, pbase, step, mul, off);
+  TRACE(7);
+}
+
+// ---- chunk-sequential kernel: a persistent CTA walks the tiles of one chunk after the other (large batches) ---------
+// No inter-CTA communication at all: the value count and the per-field running values are carried in shared memory
+// from tile to tile; chunks are claimed from an atomic counter so that the SMs stay balanced.
+template <int K>
+__global__ void __launch_bounds__(kThreads, 3) decode_chunks_seq_kernel(const DecLaunch L, float m0, float m1, float m2, float m3,
+                                                                        uint32_t o0, uint32_t o1, uint32_t o2, uint32_t o3) {
+  extern __shared__ __align__(16) uint8_t dyn_smem[];
+  __shared__ TileShared sh;
+  __shared__ uint32_t s_chunk;
+  uint8_t* tile_bytes = dyn_smem;
+  uint16_t* pos16 = reinterpret_cast<uint16_t*>(dyn_smem + kTLook + kTB + 16);
+  constexpr int VTMAX = ((kTB / kThreads) + K - 1) / K * K;
+  const float mul[4] = {m0, m1, m2, m3};
+  const uint32_t off[4] = {o0, o1, o2, o3};
+  const uint32_t step = L.plan->point_step;
+
+  while (true) {
+    if (threadIdx.x == 0) s_chunk = atomicAdd(L.chunk_counter, 1u);
+    __syncthreads();
+    const uint32_t gc = s_chunk;
+    if (gc >= L.n_chunks_total) return;
+    const DecFrame F = L.frames[L.chunk_frame[gc]];
+    const uint32_t chunk = gc - F.chunk_begin;
+    const uint32_t n_points = min(kChunkPoints, F.n_points - chunk * kChunkPoints);
+    const uint32_t V = n_points * K;
+    const uint8_t* body = F.payload + L.chunk_offsets[gc];
+    const uint32_t size = L.chunk_sizes[gc];
+    const uint32_t mis = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(body) & 15u);
+    const uint8_t* aligned = body - mis;
+    const uint32_t n_tiles = L.chunk_tiles[gc];
+    uint8_t* out = F.out + static_cast<size_t>(chunk) * kChunkPoints * step;
+    uint32_t done = 0;
+    int32_t carry[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) carry[j] = 0;
+    for (uint32_t t = 0; t < n_tiles && done < V; ++t) {
+      const int64_t tile_b0 = static_cast<int64_t>(t) * kTB - mis;
+      const uint32_t tmask = tile_load_masks(tile_bytes, aligned, body, size, t, tile_b0);
+      const uint32_t tile_cnt = tile_rank_compact(tmask, pos16, sh.scan);
+      const uint32_t VT = ((tile_cnt + kThreads - 1) / kThreads + K - 1) / K * K;
+      const uint32_t v0 = threadIdx.x * VT;
+      int32_t d[VTMAX];
+      unsigned long long nanm;
+      uint32_t badcode, badk;
+      tile_decode_run<VTMAX>(tile_bytes, pos16, tile_cnt, VT, v0, d, nanm, badcode, badk);
+      const uint32_t take = min(tile_cnt, V - done);
+      if (take > 0 && done + take == V && threadIdx.x == 0) L.stream_end[gc] = static_cast<uint32_t>(tile_b0 + pos16[take - 1] + 1);
+      const uint32_t n_mine = v0 < take ? min(VT, take - v0) : 0u;
+      if (badk < n_mine) report_error(L.err, badcode);
+      const uint32_t phase = done % K;
+      const SegK<K> mine = run_reduce<K, VTMAX>(phase, d, nanm, n_mine);
+      SegK<K> total;
+      const SegK<K> ex = cta_seg_exclusive<K>(mine, sh, &total);
+      int32_t cur[K];
+#pragma unroll
+      for (int j = 0; j < K; ++j) cur[j] = ((ex.rst >> j) & 1u) ? ex.sum[j] : wadd32(carry[j], ex.sum[j]);
+      run_emit<K, VTMAX>(phase, d, nanm, n_mine, cur, out, (done + v0) / K, step, mul, off);
+#pragma unroll
+      for (int j = 0; j < K; ++j) carry[j] = ((total.rst >> j) & 1u) ? total.sum[j] : wadd32(carry[j], total.sum[j]);
+      done += take;
+      __syncthreads();  // tile_bytes / pos16 / sh are reused by the next tile
+    }
+    if (done < V && threadIdx.x == 0) report_error(L.err, DEV_ERR_TRUNCATED);  // v4_codec.cpp:102-104
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+size_t decode_tiles_smem_bytes() { return kTLook + kTB + 16 + 2 * static_cast<size_t>(kTB) + 64; }
+uint32_t decode_tile_bytes() { return kTB; }
+
+template <int K>
+static int launch_floatn_decode(const RegOp& op, const DecLaunch& L, bool sequential, int sm_count, cudaStream_t stream) {
+  const size_t smem = decode_tiles_smem_bytes();
+  const float m3 = K == 4 ? op.dec_mul_f[3] : 0.f;
+  const uint32_t o3 = K == 4 ? op.offset[3] : 0u;
+  if (sequential) {
+    auto k = decode_chunks_seq_kernel<K>;
+    if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess) return -1;
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kThreads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    const uint32_t grid = min(L.n_chunks_total, static_cast<uint32_t>(per_sm * sm_count));
+    cudaMemsetAsync(L.chunk_counter, 0, sizeof(uint32_t), stream);
+    k<<<grid, kThreads, smem, stream>>>(L, op.dec_mul_f[0], op.dec_mul_f[1], op.dec_mul_f[2], m3, op.offset[0], op.offset[1], op.offset[2], o3);
+  } else {
+    auto k = decode_tiles_kernel<K>;
+    if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess) return -1;
+    k<<<L.tile_grid, kThreads, smem, stream>>>(L, op.dec_mul_f[0], op.dec_mul_f[1], op.dec_mul_f[2], m3, op.offset[0], op.offset[1], op.offset[2], o3);
+  }
+  return 1;
+}
+
+int launch_decode_tiles(const Plan& plan, const DecLaunch& L, cudaStream_t stream) {
+  const RegOp& op = plan.ops[0];
+  static int sm_count = 0;
+  if (sm_count == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+    if (sm_count <= 0) sm_count = 148;
+  }
+  // Large batches: one persistent CTA per chunk (no look-back latency); small ones: one CTA per tile (parallel inside a chunk).
+  const char* mode = getenv("CLDN_B200_DECODE_MODE");  // "seq" | "tile" (development override)
+  bool sequential = L.n_chunks_total >= static_cast<uint32_t>(4 * sm_count);
+  if (mode && mode[0] == 's') sequential = true;
+  if (mode && mode[0] == 't') sequential = false;
+  count_tiles_kernel<<<(L.n_chunks_total + 127) / 128, 128, 0, stream>>>(L);
+  int launches = 1;
+  if (!sequential) {
+    scan_tiles_kernel<<<1, kThreads, 0, stream>>>(L);
+    ++launches;
+  }
+  const int n = op.lanes == 4 ? launch_floatn_decode<4>(op, L, sequential, sm_count, stream)
+                              : launch_floatn_decode<3>(op, L, sequential, sm_count, stream);
+  return n < 0 ? -1 : launches + n;
+}
+
+}  // namespace cldn

@@ -212,8 +212,8 @@ __device__ __forceinline__ uint32_t varint_word_28(uint32_t u) {
   return x | ((h + 0x007F7F7Fu) & 0x00808080u);
 }
 
-template <int N, int I, bool VEC4>
-__global__ void __launch_bounds__(kThreads) encode_floatn_kernel(const EncLaunch L, const FloatNParams P) {
+template <int N, int I, bool VEC4, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB) encode_floatn_kernel(const EncLaunch L, const FloatNParams P) {
   extern __shared__ __align__(16) uint8_t dyn_smem[];
   __shared__ uint32_t s_wtot[kThreads / 32];
   __shared__ unsigned long long s_excl;
@@ -264,41 +264,66 @@ __global__ void __launch_bounds__(kThreads) encode_floatn_kernel(const EncLaunch
     }
   }
 
-  // ---- phase 1: quantise, delta, varint bytes (as words), per-point sizes, warp-level offsets ----
+  // ---- phase 1: quantise, delta, varint bytes (as words), per-point sizes ----
   uint32_t r[I][N];   // LEB128 bytes of each value (<= 4 bytes on the fast path), 0 for the NaN marker
-  uint32_t off[I];    // byte offset of the point inside the warp's run
-  uint32_t big = 0;   // some value needs 5 bytes -> whole tile takes the byte-wise slow path
-  uint32_t run = 0;   // bytes of earlier iterations of this warp
+  uint32_t pre[I];    // byte 0: len(v0), byte 1: len(v0..v1), byte 2: len(v0..v2), byte 3: total length of the point
+  uint32_t bmax = 0;  // highest set bit of any zz+1; >= 28 means a 5-byte varint -> whole tile takes the byte-wise slow path
 #pragma unroll
   for (int i = 0; i < I; ++i) {
     const bool valid = (warp_p0 + 32 * i + lane) < F.n_points;
-    uint32_t len = 0;
+    uint32_t acc = 0, packed = 0;
 #pragma unroll
     for (int k = 0; k < N; ++k) {
       const bool nan = isnan(v[i][k]);
-      const int32_t q = quant_i32_x86(v[i][k], P.mul[k]);
-      const int32_t pass = nan ? 0 : q;                       // what the NEXT point sees as "previous" (field_encoder.cpp:79-82)
-      int32_t prev = __shfl_up_sync(0xffffffffu, pass, 1);
-      if (lane == 0) prev = carry[k];
-      carry[k] = __shfl_sync(0xffffffffu, pass, 31);
+      // NaN input gives q = 0 here (cvt.rni of NaN), which is exactly what the next point must see as "previous"
+      // (field_encoder.cpp:79-82); +inf / overflow give INT_MIN like _mm_cvtps_epi32.
+      const float sc = __fmul_rn(v[i][k], P.mul[k]);
+      int32_t q = __float2int_rn(sc);
+      if (sc >= 2147483648.0f) q = static_cast<int32_t>(0x80000000u);
+      // previous point: lane-1 of this iteration; lane 0 takes lane 31 of the previous iteration (one rotate per value)
+      const int32_t rot = __shfl_sync(0xffffffffu, q, (lane + 31) & 31);
+      const int32_t prev = (lane == 0) ? carry[k] : rot;
+      carry[k] = rot;  // only lane 0 uses it (it holds lane 31's value of this iteration)
       const uint32_t d = static_cast<uint32_t>(q) - static_cast<uint32_t>(prev);
       const uint32_t zz = (d << 1) ^ static_cast<uint32_t>(static_cast<int32_t>(d) >> 31);
-      const bool five = !nan && zz >= 0x0FFFFFFFu;            // zz + 1 >= 2^28 -> 5 bytes
-      big |= five ? 1u : 0u;
-      const uint32_t w = nan ? 0u : varint_word_28(zz + 1u);
-      r[i][k] = w;
-      len += five ? 5u : 1u + __popc(w & 0x00808080u);
+      const uint32_t u = nan ? 0u : zz + 1u;           // u == 0 only for zz == 0xFFFFFFFF (5 bytes) or NaN
+      const bool wrap = !nan && zz == 0xFFFFFFFFu;
+      const uint32_t b = wrap ? 32u : 31u - __clz(u | 1u);
+      bmax = max(bmax, b);
+      const uint32_t lenm1 = (b * 37u) >> 8;            // floor(b / 7) for b <= 34
+      // 7-bit groups -> bytes: adding the masked upper part to itself shifts it left by one, three times
+      uint32_t x = u + (u & 0xFFFFFF80u);
+      x = x + (x & 0xFFFF8000u);
+      x = x + (x & 0xFF800000u);
+      r[i][k] = x | (0x00808080u >> (24u - 8u * min(lenm1, 3u)));  // continuation flags below the top byte
+      acc += lenm1 + 1u;
+      if (k < N - 1) packed |= acc << (8 * k);
     }
-    if (!valid) len = 0;
-    uint32_t inc = len;
+    if (!valid) acc = 0;
+    pre[i] = (N == 4) ? (packed | (acc << 24)) : (packed | (acc << 16) | (acc << 24));
+  }
+  // ---- warp-level exclusive offsets: 10-bit fields, three iterations per shuffle scan (32 * 20 = 640 < 1024) ----
+  uint32_t off[I];    // byte offset of the point inside the warp's run
+  uint32_t run = 0;   // bytes of earlier iterations of this warp
+#pragma unroll
+  for (int g = 0; g < I; g += 3) {
+    uint32_t pk = pre[g] >> 24;
+    if (g + 1 < I) pk |= (pre[g + 1] >> 24) << 10;
+    if (g + 2 < I) pk |= (pre[g + 2] >> 24) << 20;
+    uint32_t inc = pk;
 #pragma unroll
     for (int dlt = 1; dlt < 32; dlt <<= 1) {
       const uint32_t x = __shfl_up_sync(0xffffffffu, inc, dlt);
       if (lane >= dlt) inc += x;
     }
-    off[i] = run + inc - len;
-    run += __shfl_sync(0xffffffffu, inc, 31);
+    const uint32_t tot = __shfl_sync(0xffffffffu, inc, 31);
+    const uint32_t exc = inc - pk;
+    off[g] = run + (exc & 1023u);
+    run += tot & 1023u;
+    if (g + 1 < I) { off[g + 1] = run + ((exc >> 10) & 1023u); run += (tot >> 10) & 1023u; }
+    if (g + 2 < I) { off[g + 2] = run + ((exc >> 20) & 1023u); run += (tot >> 20) & 1023u; }
   }
+  const uint32_t big = bmax >= 28u ? 1u : 0u;
   if (lane == 0) s_wtot[warp] = run;
   const int any_big = __syncthreads_or(static_cast<int>(big));
   uint32_t wbase = 0, total = 0;
@@ -319,10 +344,10 @@ __global__ void __launch_bounds__(kThreads) encode_floatn_kernel(const EncLaunch
     for (int i = 0; i < I; ++i) {
       const uint32_t pidx = warp_p0 + 32 * i + lane;
       const bool valid = pidx < F.n_points;
-      const uint32_t l0 = 1u + __popc(r[i][0] & 0x00808080u);
-      const uint32_t l1 = 1u + __popc(r[i][1] & 0x00808080u);
-      const uint32_t l2 = 1u + __popc(r[i][2] & 0x00808080u);
-      const uint32_t l3 = (N == 4) ? 1u + __popc(r[i][N - 1] & 0x00808080u) : 0u;
+      const uint32_t l0 = pre[i] & 0xFFu;
+      const uint32_t c2 = (pre[i] >> 8) & 0xFFu;          // len(v0) + len(v1): 2..8
+      const uint32_t l2 = ((pre[i] >> 16) & 0xFFu) - c2;
+      const uint32_t len = valid ? (pre[i] >> 24) : 0u;   // 3..16
       // A = value0 | value1 << 8*l0  (<= 8 bytes)
       const uint32_t sa = 8u * l0;
       const uint32_t a_lo = r[i][0] | (sa < 32u ? (r[i][1] << sa) : 0u);
@@ -335,7 +360,6 @@ __global__ void __launch_bounds__(kThreads) encode_floatn_kernel(const EncLaunch
         b_hi = __funnelshift_lc(r[i][N - 1], 0u, sb);
       }
       // record = A | B << 8*(l0+l1): split the shift into a word part and a 8..32-bit part
-      const uint32_t c2 = l0 + l1;                  // 2..8
       const uint32_t ws = (c2 - 1u) >> 2;           // 0 | 1
       const uint32_t bs = 8u * (((c2 - 1u) & 3u) + 1u);  // 8,16,24,32
       const uint32_t x0 = bs < 32u ? (b_lo << bs) : 0u;
@@ -345,7 +369,6 @@ __global__ void __launch_bounds__(kThreads) encode_floatn_kernel(const EncLaunch
       uint32_t w1 = a_hi | (ws ? x0 : x1);
       uint32_t w2 = ws ? x1 : x2;
       uint32_t w3 = ws ? x2 : 0u;
-      const uint32_t len = l0 + l1 + l2 + l3;       // 3..16
       // byte position inside the tile; shift the record to its position inside the first word
       const uint32_t pos = wbase + off[i];
       const uint32_t s = pos & 3u, sh = 8u * s;
@@ -428,7 +451,18 @@ static cudaError_t set_smem(K kernel, size_t bytes) {
   return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
 }
 
-template <int N, int I>
+// Tuning variant of the FloatN kernel: 0 = I=8 / 2 CTAs per SM (128 regs), 1 = I=8 / 3 CTAs (80 regs),
+// 2 = I=4 / 4 CTAs (64 regs). Chosen once per process (env CLDN_B200_ENC_VARIANT overrides the default).
+static int floatn_variant() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("CLDN_B200_ENC_VARIANT");
+    v = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 0;
+  }
+  return v;
+}
+
+template <int N, int I, int MINB>
 static int launch_floatn(const Plan& plan, const EncLaunch& L, bool vec4, cudaStream_t stream) {
   FloatNParams P;
   for (int k = 0; k < 4; ++k) {
@@ -438,11 +472,11 @@ static int launch_floatn(const Plan& plan, const EncLaunch& L, bool vec4, cudaSt
   P.point_step = plan.point_step;
   const size_t smem = static_cast<size_t>(kThreads) * I * 5 * N + 64;
   if (vec4) {
-    auto k = encode_floatn_kernel<N, I, true>;
+    auto k = encode_floatn_kernel<N, I, true, MINB>;
     if (set_smem(k, smem) != cudaSuccess) return -1;
     k<<<L.n_tiles_total, kThreads, smem, stream>>>(L, P);
   } else {
-    auto k = encode_floatn_kernel<N, I, false>;
+    auto k = encode_floatn_kernel<N, I, false, MINB>;
     if (set_smem(k, smem) != cudaSuccess) return -1;
     k<<<L.n_tiles_total, kThreads, smem, stream>>>(L, P);
   }
@@ -455,7 +489,7 @@ __global__ void empty_frames_kernel(const EncLaunch L) { handle_empty_frames(L);
 
 // Points per tile for a plan: the largest I in {8,4,2,1} whose staging buffer fits comfortably.
 uint32_t choose_tile_points(const Plan& plan) {
-  if (plan.floatn_only) return kThreads * 8;
+  if (plan.floatn_only) return floatn_variant() == 2 ? kThreads * 4 : kThreads * 8;
   const size_t budget = 96 * 1024;
   for (int I = 8; I >= 1; I >>= 1) {
     if (static_cast<size_t>(kThreads) * I * plan.max_point_bytes + sizeof(Plan) + 64 <= budget) return kThreads * I;
@@ -470,14 +504,28 @@ int launch_encode_regular(const Plan& plan, const EncLaunch& L, cudaStream_t str
     return 1;
   }
   const char* force = getenv("CLDN_B200_FORCE_GENERIC");
-  if (plan.floatn_only && !(force && force[0] == '1')) {
+  bool muls_ok = true;  // the fast kernel relies on 0 < mul < inf (a NaN product then implies a NaN input)
+  if (plan.floatn_only) {
+    for (int k = 0; k < plan.ops[0].lanes; ++k) {
+      const float m = plan.ops[0].enc_mul_f[k];
+      if (!(m > 0.0f) || m > 3.0e38f) muls_ok = false;
+    }
+  }
+  if (plan.floatn_only && muls_ok && !(force && force[0] == '1')) {
     const RegOp& op = plan.ops[0];
     const bool packed4 = op.lanes == 4 && plan.point_step == 16 && op.offset[0] == 0 && op.offset[1] == 4 &&
                          op.offset[2] == 8 && op.offset[3] == 12;
     const bool vec4 = packed4 && (L.flags & kEncInputsAligned16);  // LDG.128 needs 16-byte aligned frame bases
-    if (L.tile_points != kThreads * 8) return -1;
-    if (op.lanes == 4) return launch_floatn<4, 8>(plan, L, vec4, stream);
-    return launch_floatn<3, 8>(plan, L, false, stream);
+    const int variant = floatn_variant();
+    if (L.tile_points != (variant == 2 ? kThreads * 4 : kThreads * 8)) return -1;
+    if (op.lanes == 4) {
+      if (variant == 0) return launch_floatn<4, 8, 2>(plan, L, vec4, stream);
+      if (variant == 1) return launch_floatn<4, 8, 3>(plan, L, vec4, stream);
+      return launch_floatn<4, 4, 4>(plan, L, vec4, stream);
+    }
+    if (variant == 0) return launch_floatn<3, 8, 2>(plan, L, false, stream);
+    if (variant == 1) return launch_floatn<3, 8, 3>(plan, L, false, stream);
+    return launch_floatn<3, 4, 4>(plan, L, false, stream);
   }
   const EncLaunch& LL = L;
   const uint32_t I = LL.tile_points / kThreads;

@@ -57,9 +57,24 @@ struct DecLaunch {
   uint64_t* chunk_offsets;   // per global chunk: byte offset of the chunk BODY inside its payload
   uint32_t* chunk_sizes;     // per global chunk: body size
   uint32_t* err;
+  // tile-parallel path (FloatN-only regular streams)
+  uint32_t* chunk_tiles;       // per global chunk: number of 4 KB byte tiles
+  uint32_t* chunk_tile_begin;  // exclusive scan of chunk_tiles, (n_chunks_total + 1) entries
+  uint32_t* stream_end;        // per global chunk: bytes of the regular stream (start of the V5 sections)
+  uint32_t* chunk_frame;       // per global chunk: frame index
+  uint32_t* tile_chunk;        // per tile: global chunk index
+  uint64_t* tstatus;           // per tile: look-back 1 (value counts)
+  uint32_t* tsums;             // per tile: 2 x 8 words, look-back 2 (aggregate record, inclusive record)
+  uint64_t* trace;             // optional (CLDN_B200_TRACE): 8 globaltimer stamps per tile
+  uint32_t* chunk_counter;     // work counter of the chunk-sequential kernel
+  uint32_t tile_capacity;      // records allocated (== tile_grid)
+  uint32_t tile_grid;          // host upper bound on the number of tiles
+  uint32_t epoch;
 };
 
 int launch_decode(const Plan& host_plan, const DecLaunch& L, cudaStream_t stream);
+int launch_decode_tiles(const Plan& host_plan, const DecLaunch& L, cudaStream_t stream);
+uint32_t decode_tile_bytes();
 
 // V5 adaptive integer sections (encode side).
 struct SecLaunch {

@@ -196,10 +196,22 @@ def test_v5_all_modes_and_types(oracle):
             ("neg", F.INT32, (200000 - 5 * i).astype(np.int32)),
             ("s16", F.INT16, (rng.integers(-300, 300, n)).astype(np.int16)),
             ("big", F.INT64, (rng.integers(-2**60, 2**60, n)).astype(np.int64)),
-            ("u64", F.UINT64, (np.uint64(2**63) + (i // 7).astype(np.uint64))),
+            ("u64", F.UINT64, (np.uint64(2**63 + 5) + (i // 7).astype(np.uint64))),
             ("t", F.FLOAT32, (i * 1e-3).astype(np.float32))]                   # scalar lossy float stays in the regular stream
     _roundtrip_check(*_int_cloud(cols, n), oracle)
     _roundtrip_check(*_int_cloud(cols[:4], n, with_xyz=False), oracle)       # no regular stream at all: sections only
+
+
+def test_int64_min_delta_matches_reference_quirk(oracle):
+    # A delta of exactly INT64_MIN zigzags to 2^64-1, "+1" wraps to 0 and the reference ENCODER emits the single byte 0x00
+    # (encoding_utils.hpp:56-57) which its own decoder then rejects as "unexpected NaN marker". The encoder must still
+    # match byte for byte; decode is not exercised.
+    F = cb.FieldType
+    n = 5000
+    v = (np.uint64(2**63) + (np.arange(n) // 7).astype(np.uint64))
+    for version in (5, 4):
+        info, cloud = _int_cloud([("u64", F.UINT64, v)], n, version=version)
+        assert cb.PointcloudEncoder(info).encode(cloud) == oracle.encode(info, cloud)
 
 
 def test_v5_palette_overflow_and_mode_commit(oracle):
@@ -233,3 +245,14 @@ def test_v5_section_decode_errors():
         # a corrupted run table may still decode to wrong values without a structural error: compare to force a failure
         assert np.array_equal(out, dec.decode(dinfo, bytes(blob[hdr:])))
         raise RuntimeError("silent corruption")
+
+
+@pytest.mark.parametrize("mode", ["seq", "tile"])
+def test_floatn_decode_modes(oracle, monkeypatch, mode):
+    # the chunk-sequential (large batch) and the tile-parallel (small batch) decoders must agree with the oracle
+    monkeypatch.setenv("CLDN_B200_DECODE_MODE", mode)
+    for n in (1, 700, 32768, 32769, 150_001):
+        _roundtrip_check(*synth.cloud_c1(n, seed=n + 11), oracle)
+        _roundtrip_check(*synth.cloud_c2(n, seed=n + 12), oracle, fill=0x42)
+    _roundtrip_check(*synth.cloud_c1(20_000, seed=3, adversarial=True), oracle)
+    _roundtrip_check(*synth.cloud_c3(70_000, seed=8), oracle, fill=0x99)

@@ -1,0 +1,38 @@
+"""Development aid: decodes 8 frames once with CLDN_B200_TRACE and prints per-phase tile latencies."""
+import os, sys
+os.environ["CLDN_B200_TRACE"] = "/tmp/cldn_trace.bin"
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import numpy as np, torch
+import cloudini_b200 as cb
+from cloudini_b200 import synth
+F, N = 8, 1_000_000
+info = synth.info_xyzi(N)
+s = torch.cuda.Stream(); torch.cuda.set_stream(s)
+enc = cb.PointcloudEncoder(info, stream=s.cuda_stream); dec = cb.PointcloudDecoder(stream=s.cuda_stream)
+clouds = [torch.from_numpy(synth.cloud_c2(N, seed=50 + k)[1]).cuda() for k in range(F)]
+cap = cb.MaxCompressedSize(info, N, True)
+blobs = [torch.empty(cap, dtype=torch.uint8, device="cuda") for _ in range(F)]
+outs = [torch.zeros(N * 16, dtype=torch.uint8, device="cuda") for _ in range(F)]
+eb = enc.make_device_batch([t.data_ptr() for t in clouds], [N * 16] * F, [t.data_ptr() for t in blobs], [cap] * F)
+sizes = enc.encode_batch_device(eb, True, want_sizes=True)
+hdr = len(enc.getHeader())
+db = dec.make_device_batch([t.data_ptr() + hdr for t in blobs], [x - hdr for x in sizes], [t.data_ptr() for t in outs], [N * 16] * F)
+for _ in range(3):
+    dec.decode_batch_device(info, db, sync=False)
+dec.sync()
+tr = np.fromfile("/tmp/cldn_trace.bin", dtype=np.uint64).reshape(-1, 8)
+tr = tr[tr[:, 0] > 0]
+t0 = tr[:, 0].min()
+rel = (tr.astype(np.int64) - np.int64(t0)) / 1000.0
+print("tiles", len(tr), "kernel span us", rel[:, 7].max())
+names = ["start->scan", "scan->LB1done(w0)", "LB1->decoded", "decoded->sync", "sync->reduce", "reduce->LB2", "LB2->end"]
+for k in range(7):
+    dur = rel[:, k + 1] - rel[:, k]
+    dur = dur[(tr[:, k + 1] > 0)]
+    print(f"{names[k]:22s} mean {dur.mean():7.2f} us  p50 {np.median(dur):7.2f}  p95 {np.percentile(dur,95):7.2f}  max {dur.max():7.2f}")
+tot = rel[:, 7] - rel[:, 0]
+print("tile total mean", tot[tr[:,7]>0].mean(), "us")
+# start time vs tile index
+idx = np.arange(len(tr))
+for q in (0, len(tr)//4, len(tr)//2, 3*len(tr)//4, len(tr)-1):
+    print("tile", q, "start", rel[q, 0], "end", rel[q, 7])
