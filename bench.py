@@ -314,12 +314,10 @@ def main():
         blob_bytes = int(sum(w))
         e2e = {"seconds": e2e_s, "steps": e2e_steps, "frames": Fe, "h2d": Fe * POINTS * 16 + blob_bytes - Fe * hdr, "d2h": blob_bytes + Fe * POINTS * 16}
 
-    # ---- reduce over ranks: time = max, points = sum ----
-    stats = torch.tensor([elapsed_ms, enc_ms, dec_ms, e2e["seconds"] if e2e else 0.0], dtype=torch.float64, device=dev)
-    if distributed:
-        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
-    elapsed_ms, enc_ms_max, dec_ms_max, e2e_s_max = [float(x) for x in stats.tolist()]
-    total_points = world * F * POINTS * args.steps
+    # ---- reduce over ranks: time = max, points = sum (no data-path collective: frames are independent) ----
+    from cloudini_b200 import dist as cdist
+    total_points, (elapsed_ms, enc_ms_max, dec_ms_max, e2e_s_max) = cdist.aggregate(
+        F * POINTS * args.steps, [elapsed_ms, enc_ms, dec_ms, e2e["seconds"] if e2e else 0.0], device=dev)
     value = total_points / (elapsed_ms * 1e-3) / 1e6
 
     if rank == 0:

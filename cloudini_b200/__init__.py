@@ -24,7 +24,7 @@ __all__ = [
 ]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "lib", "libcloudini_b200.so")
+_LIB_PATH = os.environ.get("CLDN_B200_LIB") or os.path.join(_HERE, "lib", "libcloudini_b200.so")
 CLDN_MAX_FIELDS = 32
 CLDN_MAX_NAME = 64
 kDecodeButSkipStore = 0xFFFFFFFF  # basic_types.hpp:71

@@ -30,18 +30,20 @@ def needs_build():
     return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
 
 
-def build(force=False, verbose=False):
-    """Compile every translation unit for sm_100a and link the shared library. Returns the library path."""
-    if not force and not needs_build():
+def build(force=False, verbose=False, defines=(), out=None):
+    """Compile every translation unit for sm_100a and link the shared library. Returns the library path.
+    `defines` / `out` build a tuning variant next to the default library (development only)."""
+    lib = out or LIB
+    if not force and not defines and not needs_build():
         return LIB
     os.makedirs(LIB_DIR, exist_ok=True)
-    obj_dir = os.path.join(HERE, "build")
+    obj_dir = os.path.join(HERE, "build" + ("_" + "_".join(defines).replace("=", "") if defines else ""))
     os.makedirs(obj_dir, exist_ok=True)
     nvcc = _nvcc()
     procs = []
     for src in SOURCES:
         obj = os.path.join(obj_dir, os.path.splitext(src)[0] + ".o")
-        cmd = [nvcc, *NVCC_FLAGS, "-x", "cu", "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc, *NVCC_FLAGS, *["-D" + d for d in defines], "-x", "cu", "-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     objs = []
     for src, obj, p in procs:
@@ -52,10 +54,12 @@ def build(force=False, verbose=False):
         if verbose:
             sys.stderr.write(out)
         objs.append(obj)
-    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB, *objs, "-lcudart"]
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", lib, *objs, "-lcudart"]
     subprocess.check_call(cmd)
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    defs = tuple(a[2:] for a in sys.argv if a.startswith("-D"))
+    outs = [a[6:] for a in sys.argv if a.startswith("--out=")]
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, defines=defs, out=outs[0] if outs else None))

@@ -15,7 +15,10 @@
 
 namespace cldn {
 
-constexpr int kVec = 2;         // adjacent 16-byte vectors per thread
+#ifndef CLDN_KVEC
+#define CLDN_KVEC 1
+#endif
+constexpr int kVec = CLDN_KVEC;  // adjacent 16-byte vectors per thread
 constexpr int kTB = kThreads * 16 * kVec;  // stream bytes per tile (8192)
 constexpr int kTLook = 16;     // look-behind bytes staged in front of the tile
 constexpr uint32_t kRecWords = 8;  // look-back record: sum[4], rst, flag, pad, pad
@@ -172,6 +175,20 @@ __device__ __forceinline__ SegK<K> sums_lookback(const uint64_t* recs, uint32_t 
   return acc;
 }
 
+// Long varint (6..10 bytes: never produced by the FloatN encoder, but decodable by the reference). Kept out of line.
+__device__ __noinline__ int32_t decode_long_value(const uint8_t* tile_bytes, uint32_t e, uint32_t len, uint32_t& bad) {
+  unsigned long long u = 0;
+  if (len > 10u) { bad = DEV_ERR_VARINT_OVERFLOW; return 0; }
+  for (uint32_t k = 0; k < len; ++k) {
+    const unsigned long long payload = tile_bytes[e - len + 1 + k] & 0x7Fu;
+    if (k == 9 && payload > 1) bad = DEV_ERR_VARINT_OVERFLOW;
+    u |= payload << (7 * k);
+  }
+  if (bad) return 0;
+  if (u == 0) { bad = DEV_ERR_NAN_MARKER; return 0; }
+  return static_cast<int32_t>(unzigzag(u - 1ull));
+}
+
 // Rebuilds the varint that ends at tile byte `e` (biased by kTLook) and is `len` bytes long. Returns the int32 delta;
 // sets nan for the single-byte 0x00 marker and bad (a DevError code) when the bytes do not form a valid value.
 __device__ __forceinline__ int32_t decode_value(const uint8_t* tile_bytes, uint32_t e, uint32_t len, bool& nan, uint32_t& bad) {
@@ -201,55 +218,71 @@ __device__ __forceinline__ int32_t decode_value(const uint8_t* tile_bytes, uint3
       delta = static_cast<int32_t>(unzigzag(u - 1ull));
     }
   } else {
-    // long varint (never produced by the FloatN encoder, but decodable by the reference): byte loop, <= 10 bytes
-    unsigned long long u = 0;
-    if (len > 10u) bad = DEV_ERR_VARINT_OVERFLOW;
-    else {
-      for (uint32_t k = 0; k < len; ++k) {
-        const unsigned long long payload = tile_bytes[e - len + 1 + k] & 0x7Fu;
-        if (k == 9 && payload > 1) bad = DEV_ERR_VARINT_OVERFLOW;
-        u |= payload << (7 * k);
-      }
-    }
-    if (!bad) {
-      if (u == 0) bad = DEV_ERR_NAN_MARKER;
-      else delta = static_cast<int32_t>(unzigzag(u - 1ull));
-    }
+    delta = decode_long_value(tile_bytes, e, len, bad);
   }
   return delta;
 }
 
-// Per-thread value run with the field phase PH known at compile time: value k of the run belongs to field (PH + k) % K.
-template <int K, int VTMAX, int PH>
-struct RunOps {
-  static __device__ __forceinline__ SegK<K> reduce(const int32_t (&d)[VTMAX], unsigned long long nanm, uint32_t n) {
-    SegK<K> m = seg_identity<K>();
+// Per-thread value run in LOCAL slot numbering: value k of the run is local slot k % K (runs start at a multiple of K
+// values); the global field is (phase + k) % K with phase = done % K uniform over the tile, so accumulators and
+// per-field constants are rotated once instead of specialising the unrolled loops per phase.
+template <int K, int VTMAX>
+__device__ __forceinline__ SegK<K> run_reduce_local(const int32_t (&d)[VTMAX], unsigned long long nanm, uint32_t n) {
+  SegK<K> m = seg_identity<K>();
 #pragma unroll
-    for (int k = 0; k < VTMAX; ++k) {
-      if (k >= static_cast<int>(n)) break;
-      constexpr int dummy = 0; (void)dummy;
-      const int j = (PH + k) % K;
-      if ((nanm >> k) & 1ull) { m.sum[j] = 0; m.rst |= 1u << j; }
-      else m.sum[j] = wadd32(m.sum[j], d[k]);
-    }
-    return m;
+  for (int k = 0; k < VTMAX; ++k) {
+    if (k >= static_cast<int>(n)) break;
+    const int j = k % K;
+    if ((nanm >> k) & 1ull) { m.sum[j] = 0; m.rst |= 1u << j; }
+    else m.sum[j] = wadd32(m.sum[j], d[k]);
   }
-  static __device__ __forceinline__ void emit(const int32_t (&d)[VTMAX], unsigned long long nanm, uint32_t n, int32_t (&cur)[K],
-                                              uint8_t* out, uint32_t pbase, uint32_t step, const float (&mul)[4],
-                                              const uint32_t (&off)[4]) {
+  return m;
+}
+// local slot l -> global field (l + phase) % K
+template <int K>
+__device__ __forceinline__ SegK<K> seg_to_global(const SegK<K>& a, uint32_t phase) {
+  SegK<K> r = seg_identity<K>();
 #pragma unroll
-    for (int k = 0; k < VTMAX; ++k) {
-      if (k >= static_cast<int>(n)) break;
-      const int j = (PH + k) % K;
-      const bool nan = (nanm >> k) & 1ull;
-      if (nan) cur[j] = 0; else cur[j] = wadd32(cur[j], d[k]);
-      if (off[j] != CLDN_SKIP_STORE_OFFSET) {
-        const float f = nan ? __uint_as_float(0x7FC00000u) : __fmul_rn(__int2float_rn(cur[j]), mul[j]);
-        store_u32(out + static_cast<size_t>(pbase + (PH + k) / K) * step + off[j], __float_as_uint(f));
-      }
+  for (int l = 0; l < K; ++l) {
+#pragma unroll
+    for (int g = 0; g < K; ++g) {
+      if (static_cast<uint32_t>(g) == (l + phase) % K) { r.sum[g] = a.sum[l]; r.rst |= ((a.rst >> l) & 1u) << g; }
     }
   }
-};
+  return r;
+}
+template <int K, int VTMAX, bool ALIGNED4>
+__device__ __forceinline__ void run_emit_local(const int32_t (&d)[VTMAX], unsigned long long nanm, uint32_t n, const int32_t (&cur_global)[K],
+                                               uint32_t phase, uint8_t* out, uint32_t pbase, uint32_t step, const float (&mul)[4],
+                                               const uint32_t (&off)[4]) {
+  // rotate the running values and the per-field constants into local numbering
+  int32_t cur[K];
+  float lmul[K];
+  uint32_t loff[K];
+#pragma unroll
+  for (int l = 0; l < K; ++l) {
+    cur[l] = 0; lmul[l] = 0.f; loff[l] = 0;
+#pragma unroll
+    for (int g = 0; g < K; ++g) {
+      if (static_cast<uint32_t>(g) == (l + phase) % K) { cur[l] = cur_global[g]; lmul[l] = mul[g]; loff[l] = off[g]; }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < VTMAX; ++k) {
+    if (k >= static_cast<int>(n)) break;
+    const int l = k % K;
+    const bool nan = (nanm >> k) & 1ull;
+    if (nan) cur[l] = 0; else cur[l] = wadd32(cur[l], d[k]);
+    if (loff[l] != CLDN_SKIP_STORE_OFFSET) {
+      const float f = nan ? __uint_as_float(0x7FC00000u) : __fmul_rn(__int2float_rn(cur[l]), lmul[l]);
+      // point of value k: pbase + (phase + k) / K = pbase + k / K + (k % K + phase >= K)
+      const uint32_t p = pbase + k / K + ((l + phase >= static_cast<uint32_t>(K)) ? 1u : 0u);
+      uint8_t* dst = out + static_cast<size_t>(p) * step + loff[l];
+      if (ALIGNED4) *reinterpret_cast<uint32_t*>(dst) = __float_as_uint(f);
+      else store_u32(dst, __float_as_uint(f));
+    }
+  }
+}
 
 __device__ __forceinline__ uint64_t gtimer() { uint64_t t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 #define TRACE(slot) do { if (L.trace && threadIdx.x == 0) L.trace[static_cast<size_t>(gt) * 8 + (slot)] = gtimer(); } while (0)
@@ -360,26 +393,6 @@ __device__ __forceinline__ void tile_decode_run(const uint8_t* tile_bytes, const
   }
 }
 
-template <int K, int VTMAX>
-__device__ __forceinline__ SegK<K> run_reduce(uint32_t phase, const int32_t (&d)[VTMAX], unsigned long long nanm, uint32_t n) {
-  switch (phase) {
-    case 0: return RunOps<K, VTMAX, 0>::reduce(d, nanm, n);
-    case 1: return RunOps<K, VTMAX, 1>::reduce(d, nanm, n);
-    case 2: return RunOps<K, VTMAX, 2>::reduce(d, nanm, n);
-    default: return RunOps<K, VTMAX, (K > 3 ? 3 : 0)>::reduce(d, nanm, n);
-  }
-}
-template <int K, int VTMAX>
-__device__ __forceinline__ void run_emit(uint32_t phase, const int32_t (&d)[VTMAX], unsigned long long nanm, uint32_t n, int32_t (&cur)[K],
-                                         uint8_t* out, uint32_t pbase, uint32_t step, const float (&mul)[4], const uint32_t (&off)[4]) {
-  switch (phase) {
-    case 0: RunOps<K, VTMAX, 0>::emit(d, nanm, n, cur, out, pbase, step, mul, off); break;
-    case 1: RunOps<K, VTMAX, 1>::emit(d, nanm, n, cur, out, pbase, step, mul, off); break;
-    case 2: RunOps<K, VTMAX, 2>::emit(d, nanm, n, cur, out, pbase, step, mul, off); break;
-    default: RunOps<K, VTMAX, (K > 3 ? 3 : 0)>::emit(d, nanm, n, cur, out, pbase, step, mul, off); break;
-  }
-}
-
 // CTA-wide exclusive segmented scan of one SegK per thread (two barriers); *total = combination of all threads.
 template <int K>
 __device__ __forceinline__ SegK<K> cta_seg_exclusive(const SegK<K>& mine, TileShared& sh, SegK<K>* total) {
@@ -415,7 +428,7 @@ __device__ __forceinline__ SegK<K> cta_seg_exclusive(const SegK<K>& mine, TileSh
 
 // ---- tile-parallel kernel: one CTA per 8 KB tile, two decoupled look-backs (small batches / single frames) ----------
 template <int K>
-__global__ void __launch_bounds__(kThreads, 3) decode_tiles_kernel(const DecLaunch L, float m0, float m1, float m2, float m3,
+__global__ void __launch_bounds__(kThreads, kVec == 1 ? 4 : 3) decode_tiles_kernel(const DecLaunch L, float m0, float m1, float m2, float m3,
                                                                    uint32_t o0, uint32_t o1, uint32_t o2, uint32_t o3) {
   extern __shared__ __align__(16) uint8_t dyn_smem[];
   __shared__ TileShared sh;
@@ -440,6 +453,8 @@ __global__ void __launch_bounds__(kThreads, 3) decode_tiles_kernel(const DecLaun
   const int64_t tile_b0 = static_cast<int64_t>(t) * kTB - mis;  // stream offset of tile byte 0
   const uint32_t step = L.plan->point_step;
   uint8_t* out = F.out + static_cast<size_t>(chunk) * kChunkPoints * step;
+  const bool aligned4 = (((reinterpret_cast<uintptr_t>(out) | step | o0 | o1 | o2 | (K == 4 ? o3 : 0u)) & 3u) == 0u) &&
+      o0 != CLDN_SKIP_STORE_OFFSET && o1 != CLDN_SKIP_STORE_OFFSET && o2 != CLDN_SKIP_STORE_OFFSET && (K < 4 || o3 != CLDN_SKIP_STORE_OFFSET);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint64_t* recs = reinterpret_cast<uint64_t*>(L.tsums);
 
@@ -476,7 +491,7 @@ __global__ void __launch_bounds__(kThreads, 3) decode_tiles_kernel(const DecLaun
 
   // ---- per-field segmented sums of my run; the field of value k is (done + v0 + k) % K = (done % K + k) % K ----
   const uint32_t phase = done % K;
-  const SegK<K> mine = run_reduce<K, VTMAX>(phase, d, nanm, n_mine);
+  const SegK<K> mine = seg_to_global<K>(run_reduce_local<K, VTMAX>(d, nanm, n_mine), phase);
   SegK<K> total;
   const SegK<K> ex = cta_seg_exclusive<K>(mine, sh, &total);
   TRACE(5);
@@ -503,7 +518,8 @@ __global__ void __launch_bounds__(kThreads, 3) decode_tiles_kernel(const DecLaun
 #pragma unroll
   for (int j = 0; j < K; ++j) cur[j] = ((ex.rst >> j) & 1u) ? ex.sum[j] : wadd32(sh.carry[j], ex.sum[j]);
   const uint32_t pbase = (done + v0) / K;  // point of my first value (v0 is a multiple of K, so all threads share `phase`)
-  run_emit<K, VTMAX>(phase, d, nanm, n_mine, cur, out, pbase, step, mul, off);
+  if (aligned4) run_emit_local<K, VTMAX, true>(d, nanm, n_mine, cur, phase, out, pbase, step, mul, off);
+  else run_emit_local<K, VTMAX, false>(d, nanm, n_mine, cur, phase, out, pbase, step, mul, off);
   TRACE(7);
 }
 
@@ -511,7 +527,7 @@ __global__ void __launch_bounds__(kThreads, 3) decode_tiles_kernel(const DecLaun
 // No inter-CTA communication at all: the value count and the per-field running values are carried in shared memory
 // from tile to tile; chunks are claimed from an atomic counter so that the SMs stay balanced.
 template <int K>
-__global__ void __launch_bounds__(kThreads, 3) decode_chunks_seq_kernel(const DecLaunch L, float m0, float m1, float m2, float m3,
+__global__ void __launch_bounds__(kThreads, kVec == 1 ? 4 : 3) decode_chunks_seq_kernel(const DecLaunch L, float m0, float m1, float m2, float m3,
                                                                         uint32_t o0, uint32_t o1, uint32_t o2, uint32_t o3) {
   extern __shared__ __align__(16) uint8_t dyn_smem[];
   __shared__ TileShared sh;
@@ -538,6 +554,8 @@ __global__ void __launch_bounds__(kThreads, 3) decode_chunks_seq_kernel(const De
     const uint8_t* aligned = body - mis;
     const uint32_t n_tiles = L.chunk_tiles[gc];
     uint8_t* out = F.out + static_cast<size_t>(chunk) * kChunkPoints * step;
+    const bool aligned4 = (((reinterpret_cast<uintptr_t>(out) | step | o0 | o1 | o2 | (K == 4 ? o3 : 0u)) & 3u) == 0u) &&
+      o0 != CLDN_SKIP_STORE_OFFSET && o1 != CLDN_SKIP_STORE_OFFSET && o2 != CLDN_SKIP_STORE_OFFSET && (K < 4 || o3 != CLDN_SKIP_STORE_OFFSET);
     uint32_t done = 0;
     int32_t carry[K];
 #pragma unroll
@@ -557,13 +575,14 @@ __global__ void __launch_bounds__(kThreads, 3) decode_chunks_seq_kernel(const De
       const uint32_t n_mine = v0 < take ? min(VT, take - v0) : 0u;
       if (badk < n_mine) report_error(L.err, badcode);
       const uint32_t phase = done % K;
-      const SegK<K> mine = run_reduce<K, VTMAX>(phase, d, nanm, n_mine);
+      const SegK<K> mine = seg_to_global<K>(run_reduce_local<K, VTMAX>(d, nanm, n_mine), phase);
       SegK<K> total;
       const SegK<K> ex = cta_seg_exclusive<K>(mine, sh, &total);
       int32_t cur[K];
 #pragma unroll
       for (int j = 0; j < K; ++j) cur[j] = ((ex.rst >> j) & 1u) ? ex.sum[j] : wadd32(carry[j], ex.sum[j]);
-      run_emit<K, VTMAX>(phase, d, nanm, n_mine, cur, out, (done + v0) / K, step, mul, off);
+      if (aligned4) run_emit_local<K, VTMAX, true>(d, nanm, n_mine, cur, phase, out, (done + v0) / K, step, mul, off);
+      else run_emit_local<K, VTMAX, false>(d, nanm, n_mine, cur, phase, out, (done + v0) / K, step, mul, off);
 #pragma unroll
       for (int j = 0; j < K; ++j) carry[j] = ((total.rst >> j) & 1u) ? total.sum[j] : wadd32(carry[j], total.sum[j]);
       done += take;

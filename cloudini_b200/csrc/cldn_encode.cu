@@ -457,7 +457,7 @@ static int floatn_variant() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("CLDN_B200_ENC_VARIANT");
-    v = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 0;
+    v = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 1;
   }
   return v;
 }

@@ -1,0 +1,8 @@
+#!/usr/bin/env bash
+# usage: tools_quick_bench.sh <label>   (env selects variants) — prints encode/decode ms per 32-frame step
+timeout 150 python bench.py --steps 20 --warmup 3 --no-e2e --cpu-seconds 0.2 2>&1 | tail -1 > /tmp/vb.json
+python - "$1" <<'PY'
+import json, sys
+d = json.load(open('/tmp/vb.json'))
+print("%-14s enc_ms %.4f dec_ms %.4f enc_frac %.3f dec_frac %.3f parity %s value %.0f" % (sys.argv[1], d["config"]["encode_ms_per_step"], d["config"]["decode_ms_per_step"], d["roofline"]["frac"], d["roofline"]["decode"]["frac"], d["config"]["parity"], d["value"]))
+PY
