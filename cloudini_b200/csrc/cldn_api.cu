@@ -103,6 +103,30 @@ struct PinRing {
   }
 };
 
+// Extra streams + an event pool for the host-pointer path: frame f+1 is uploaded while frame f is encoded and
+// frame f-1 is downloaded (PCIe is full duplex), instead of one serial copy-compute-copy sequence.
+struct CopyPipeline {
+  cudaStream_t h2d = nullptr, d2h = nullptr;
+  std::vector<cudaEvent_t> ev;
+  int ensure(size_t n_events) {
+    if (!h2d) CUDA_TRY(cudaStreamCreateWithFlags(&h2d, cudaStreamNonBlocking));
+    if (!d2h) CUDA_TRY(cudaStreamCreateWithFlags(&d2h, cudaStreamNonBlocking));
+    while (ev.size() < n_events) {
+      cudaEvent_t e;
+      CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      ev.push_back(e);
+    }
+    return CLDN_OK;
+  }
+  void release() {
+    for (cudaEvent_t e : ev) cudaEventDestroy(e);
+    ev.clear();
+    if (h2d) cudaStreamDestroy(h2d);
+    if (d2h) cudaStreamDestroy(d2h);
+    h2d = d2h = nullptr;
+  }
+};
+
 int select_device(int device) {
   int count = 0;
   cudaError_t e = cudaGetDeviceCount(&count);
@@ -154,6 +178,7 @@ struct cldn_encoder {
   PinBuf<uint32_t> h_err;
   // host-memory path staging
   DevBuf<uint8_t> d_in, d_out;
+  CopyPipeline pipe;
   // V5 section scratch
   DevBuf<uint8_t> d_modes;
   DevBuf<uint8_t> d_sec_scratch;
@@ -221,7 +246,7 @@ void cldn_b200_encoder_destroy(cldn_encoder_t* e) {
   e->d_plan.release(); e->d_header.release(); e->d_status.release(); e->d_frames.release(); e->h_frames.release();
   e->d_sizes.release(); e->h_sizes.release(); e->d_err.release(); e->h_err.release(); e->d_in.release(); e->d_out.release();
   e->d_modes.release(); e->d_sec_scratch.release(); e->d_sec_sizes.release(); e->d_sec_excl.release();
-  e->d_chunk_frame.release(); e->h_chunk_frame.release(); e->d_hash.release();
+  e->d_chunk_frame.release(); e->h_chunk_frame.release(); e->d_hash.release(); e->pipe.release();
   if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
   delete e;
 }
@@ -413,25 +438,29 @@ int cldn_b200_encode_batch(cldn_encoder_t* e, size_t n_frames, const void* const
   }
   if (int rc = e->d_in.reserve(in_total + 256)) return rc;
   if (int rc = e->d_out.reserve(out_total + 256)) return rc;
-  std::vector<const void*> din(n_frames);
-  std::vector<void*> dout(n_frames);
-  for (size_t f = 0; f < n_frames; ++f) {
-    din[f] = e->d_in.p + in_off[f];
-    dout[f] = e->d_out.p + out_off[f];
-    if (cloud_bytes[f]) CUDA_TRY(cudaMemcpyAsync(e->d_in.p + in_off[f], clouds[f], cloud_bytes[f], cudaMemcpyHostToDevice, e->stream));
-  }
-  if (int rc = encode_batch_device(e, n_frames, din.data(), cloud_bytes, dout.data(), caps.data(), write_header)) return rc;
+  if (int rc = e->pipe.ensure(2 * n_frames)) return rc;
   if (int rc = e->h_sizes.reserve(n_frames)) return rc;
-  CUDA_TRY(cudaMemcpyAsync(e->h_sizes.p, e->d_sizes.p, n_frames * sizeof(uint64_t), cudaMemcpyDeviceToHost, e->stream));
-  if (int rc = check_device_error(e->stream, e->d_err.p, e->h_err.p)) return rc;
+  // frame f: upload on the h2d stream -> encode on the handle's stream -> 8-byte size read-back
   for (size_t f = 0; f < n_frames; ++f) {
+    const void* din = e->d_in.p + in_off[f];
+    void* dout = e->d_out.p + out_off[f];
+    if (cloud_bytes[f]) CUDA_TRY(cudaMemcpyAsync(e->d_in.p + in_off[f], clouds[f], cloud_bytes[f], cudaMemcpyHostToDevice, e->pipe.h2d));
+    CUDA_TRY(cudaEventRecord(e->pipe.ev[2 * f], e->pipe.h2d));
+    CUDA_TRY(cudaStreamWaitEvent(e->stream, e->pipe.ev[2 * f], 0));
+    if (int rc = encode_batch_device(e, 1, &din, &cloud_bytes[f], &dout, &caps[f], write_header)) return rc;
+    CUDA_TRY(cudaMemcpyAsync(e->h_sizes.p + f, e->d_sizes.p, sizeof(uint64_t), cudaMemcpyDeviceToHost, e->stream));
+    CUDA_TRY(cudaEventRecord(e->pipe.ev[2 * f + 1], e->stream));
+  }
+  // as soon as a frame's size is known, its blob goes down on the d2h stream (exactly `size` bytes)
+  for (size_t f = 0; f < n_frames; ++f) {
+    CUDA_TRY(cudaEventSynchronize(e->pipe.ev[2 * f + 1]));
     const size_t sz = static_cast<size_t>(e->h_sizes.p[f]);
     if (sz > out_capacities[f]) { set_error("internal: encoded size exceeds capacity"); return CLDN_ERR_INTERNAL; }
-    if (sz) CUDA_TRY(cudaMemcpyAsync(outs[f], e->d_out.p + out_off[f], sz, cudaMemcpyDeviceToHost, e->stream));
+    if (sz) CUDA_TRY(cudaMemcpyAsync(outs[f], e->d_out.p + out_off[f], sz, cudaMemcpyDeviceToHost, e->pipe.d2h));
     if (written_host) written_host[f] = sz;
   }
-  CUDA_TRY(cudaStreamSynchronize(e->stream));
-  return CLDN_OK;
+  CUDA_TRY(cudaStreamSynchronize(e->pipe.d2h));
+  return check_device_error(e->stream, e->d_err.p, e->h_err.p);
 }
 
 int cldn_b200_encode(cldn_encoder_t* enc, const void* cloud, size_t cloud_bytes, void* out, size_t out_capacity,
@@ -464,6 +493,7 @@ struct cldn_decoder {
   DevBuf<uint64_t> d_tstatus;
   DevBuf<uint64_t> d_trace;
   DevBuf<uint32_t> d_counter;
+  CopyPipeline pipe;
   uint32_t epoch = 0;
 };
 
@@ -632,7 +662,7 @@ void cldn_b200_decoder_destroy(cldn_decoder_t* d) {
   if (d->stream) cudaStreamSynchronize(d->stream);
   d->d_plan.release(); d->d_frames.release(); d->h_frames.release(); d->d_chunk_offsets.release(); d->d_chunk_sizes.release();
   d->d_err.release(); d->h_err.release(); d->d_in.release(); d->d_out.release();
-  d->d_chunk_tiles.release(); d->d_chunk_tile_begin.release(); d->d_stream_end.release(); d->d_tsums.release(); d->d_tstatus.release(); d->d_chunk_frame.release(); d->d_tile_chunk.release(); d->d_trace.release(); d->d_counter.release();
+  d->d_chunk_tiles.release(); d->d_chunk_tile_begin.release(); d->d_stream_end.release(); d->d_tsums.release(); d->d_tstatus.release(); d->d_chunk_frame.release(); d->d_tile_chunk.release(); d->d_trace.release(); d->d_counter.release(); d->pipe.release();
   if (d->own_stream && d->stream) cudaStreamDestroy(d->stream);
   delete d;
 }
@@ -684,23 +714,24 @@ int cldn_b200_decode_batch(cldn_decoder_t* d, const cldn_info_t* info, size_t n_
   const size_t out_stride = (out_need + 255) & ~size_t(255);
   if (int rc = d->d_in.reserve(in_total + 256)) return rc;
   if (int rc = d->d_out.reserve(out_stride * n_frames + 256)) return rc;
-  std::vector<const void*> din(n_frames);
-  std::vector<void*> dout(n_frames);
-  std::vector<size_t> caps(n_frames, out_need);
+  if (int rc = d->pipe.ensure(2 * n_frames)) return rc;
+  // frame f: upload on the h2d stream -> decode on the handle's stream -> download on the d2h stream
   for (size_t f = 0; f < n_frames; ++f) {
-    din[f] = d->d_in.p + in_off[f];
-    dout[f] = d->d_out.p + out_stride * f;
-    if (payload_bytes[f]) CUDA_TRY(cudaMemcpyAsync(d->d_in.p + in_off[f], payloads[f], payload_bytes[f], cudaMemcpyHostToDevice, d->stream));
+    const void* din = d->d_in.p + in_off[f];
+    void* dout = d->d_out.p + out_stride * f;
+    if (payload_bytes[f]) CUDA_TRY(cudaMemcpyAsync(d->d_in.p + in_off[f], payloads[f], payload_bytes[f], cudaMemcpyHostToDevice, d->pipe.h2d));
     // only declared field bytes are written by the decoder: keep the caller's padding bytes intact
-    if (d->has_padding && out_need) CUDA_TRY(cudaMemcpyAsync(dout[f], outs[f], out_need, cudaMemcpyHostToDevice, d->stream));
+    if (d->has_padding && out_need) CUDA_TRY(cudaMemcpyAsync(dout, outs[f], out_need, cudaMemcpyHostToDevice, d->pipe.h2d));
+    CUDA_TRY(cudaEventRecord(d->pipe.ev[2 * f], d->pipe.h2d));
+    CUDA_TRY(cudaStreamWaitEvent(d->stream, d->pipe.ev[2 * f], 0));
+    if (int rc = decode_batch_device(d, *info, 1, &din, &payload_bytes[f], &dout, &out_need)) return rc;
+    CUDA_TRY(cudaEventRecord(d->pipe.ev[2 * f + 1], d->stream));
+    CUDA_TRY(cudaStreamWaitEvent(d->pipe.d2h, d->pipe.ev[2 * f + 1], 0));
+    if (out_need) CUDA_TRY(cudaMemcpyAsync(outs[f], dout, out_need, cudaMemcpyDeviceToHost, d->pipe.d2h));
   }
-  if (int rc = decode_batch_device(d, *info, n_frames, din.data(), payload_bytes, dout.data(), caps.data())) return rc;
-  if (int rc = check_device_error(d->stream, d->d_err.p, d->h_err.p)) return rc;
-  for (size_t f = 0; f < n_frames; ++f) {
-    if (out_need) CUDA_TRY(cudaMemcpyAsync(outs[f], dout[f], out_need, cudaMemcpyDeviceToHost, d->stream));
-  }
-  CUDA_TRY(cudaStreamSynchronize(d->stream));
-  return CLDN_OK;
+  CUDA_TRY(cudaStreamSynchronize(d->pipe.d2h));
+  // a failed decode must not hand back garbage silently: the error word is checked after everything has drained
+  return check_device_error(d->stream, d->d_err.p, d->h_err.p);
 }
 
 int cldn_b200_decode(cldn_decoder_t* dec, const cldn_info_t* info, const void* payload, size_t payload_bytes, void* out,
