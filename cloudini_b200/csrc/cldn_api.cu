@@ -622,7 +622,7 @@ static int decode_batch_device(cldn_decoder* d, const cldn_info_t& info, size_t 
     if (int rc = d->d_counter.reserve(4, true)) return rc;
     L.chunk_counter = d->d_counter.p;
     if (getenv("CLDN_B200_TRACE")) {
-      if (int rc = d->d_trace.reserve(static_cast<size_t>(tiles) * 8 + 8, true)) return rc;
+      if (int rc = d->d_trace.reserve(std::max<size_t>(static_cast<size_t>(tiles), static_cast<size_t>(chunks) * 80) * 8 + 8, true)) return rc;
       L.trace = d->d_trace.p;
     }
   }

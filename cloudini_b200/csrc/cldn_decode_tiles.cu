@@ -175,52 +175,42 @@ __device__ __forceinline__ SegK<K> sums_lookback(const uint64_t* recs, uint32_t 
   return acc;
 }
 
-// Long varint (6..10 bytes: never produced by the FloatN encoder, but decodable by the reference). Kept out of line.
-__device__ __noinline__ int32_t decode_long_value(const uint8_t* tile_bytes, uint32_t e, uint32_t len, uint32_t& bad) {
+// Values of 5..10 bytes (|delta| >= 2^27, or varints the FloatN encoder never writes but the reference decodes).
+// Kept out of line: the common path only handles <= 4 bytes.
+// Returns (error code << 32) | uint32(delta): no by-reference outputs, so the caller's state stays in registers.
+__device__ __noinline__ unsigned long long decode_wide_value(const uint8_t* tile_bytes, uint32_t e, uint32_t len) {
   unsigned long long u = 0;
-  if (len > 10u) { bad = DEV_ERR_VARINT_OVERFLOW; return 0; }
+  uint32_t bad = 0;
+  if (len > 10u) return static_cast<unsigned long long>(DEV_ERR_VARINT_OVERFLOW) << 32;
   for (uint32_t k = 0; k < len; ++k) {
     const unsigned long long payload = tile_bytes[e - len + 1 + k] & 0x7Fu;
-    if (k == 9 && payload > 1) bad = DEV_ERR_VARINT_OVERFLOW;
+    if (k == 9 && payload > 1) bad = DEV_ERR_VARINT_OVERFLOW;  // encoding_utils.hpp:127-129
     u |= payload << (7 * k);
   }
-  if (bad) return 0;
-  if (u == 0) { bad = DEV_ERR_NAN_MARKER; return 0; }
-  return static_cast<int32_t>(unzigzag(u - 1ull));
+  if (bad) return static_cast<unsigned long long>(bad) << 32;
+  if (u == 0) return static_cast<unsigned long long>(DEV_ERR_NAN_MARKER) << 32;
+  return static_cast<uint32_t>(static_cast<int32_t>(unzigzag(u - 1ull)));  // truncated to int32 like field_decoder.cpp:68
 }
 
 // Rebuilds the varint that ends at tile byte `e` (biased by kTLook) and is `len` bytes long. Returns the int32 delta;
 // sets nan for the single-byte 0x00 marker and bad (a DevError code) when the bytes do not form a valid value.
 __device__ __forceinline__ int32_t decode_value(const uint8_t* tile_bytes, uint32_t e, uint32_t len, bool& nan, uint32_t& bad) {
-  int32_t delta = 0;
-  if (len <= 5u) {
-    const uint32_t* wp = reinterpret_cast<const uint32_t*>(tile_bytes) + (e >> 2);
-    const uint32_t W1 = wp[0], W0 = wp[-1];
-    const uint32_t shl = 8u * (3u - (e & 3u));
-    const uint32_t hi = __funnelshift_l(W0, W1, shl);  // byte e is now the top byte of hi
-    uint32_t x, b4 = 0;
-    if (len <= 4u) {
-      x = hi >> (32u - 8u * len);
-    } else {
-      x = __funnelshift_r(W0 << shl, hi, 24);
-      b4 = hi >> 24;
-    }
-    x &= 0x7F7F7F7Fu;
-    x = x - ((x & 0x7F007F00u) >> 1);              // 7-bit groups -> 14-bit groups
-    x = (x & 0x3FFFu) | ((x >> 2) & 0x0FFFC000u);  // -> 28-bit value
-    if ((x | b4) == 0u) {
-      if (len == 1u) nan = true; else bad = DEV_ERR_NAN_MARKER;
-    } else if (b4 == 0u) {
-      const uint32_t um = x - 1u;                    // (uval - 1) un-zigzagged, truncated to int32 (field_decoder.cpp:68)
-      delta = static_cast<int32_t>((um >> 1) ^ (0u - (um & 1u)));
-    } else {
-      const unsigned long long u = static_cast<unsigned long long>(x) | (static_cast<unsigned long long>(b4) << 28);
-      delta = static_cast<int32_t>(unzigzag(u - 1ull));
-    }
-  } else {
-    delta = decode_long_value(tile_bytes, e, len, bad);
+  if (len > 4u) {
+    const unsigned long long r = decode_wide_value(tile_bytes, e, len);
+    bad = static_cast<uint32_t>(r >> 32);
+    return static_cast<int32_t>(static_cast<uint32_t>(r));
   }
-  return delta;
+  const uint32_t* wp = reinterpret_cast<const uint32_t*>(tile_bytes) + (e >> 2);
+  const uint32_t hi = __funnelshift_l(wp[-1], wp[0], 24u - 8u * (e & 3u));  // byte e becomes the top byte
+  uint32_t x = (hi >> (32u - 8u * len)) & 0x7F7F7F7Fu;                        // the value's bytes, first byte lowest
+  x = x - ((x & 0x7F007F00u) >> 1);                                          // 7-bit groups -> 14-bit groups
+  x = (x & 0x3FFFu) | ((x >> 2) & 0x0FFFC000u);                              // -> 28-bit uval
+  if (x == 0u) {  // uval 0: the NaN marker if it is the single byte 0x00, otherwise "unexpected NaN marker"
+    if (len == 1u) nan = true; else bad = DEV_ERR_NAN_MARKER;
+    return 0;
+  }
+  const uint32_t um = x - 1u;
+  return static_cast<int32_t>((um >> 1) ^ (0u - (um & 1u)));
 }
 
 // Per-thread value run in LOCAL slot numbering: value k of the run is local slot k % K (runs start at a multiple of K
@@ -292,8 +282,17 @@ __device__ __forceinline__ uint64_t gtimer() { uint64_t t; asm volatile("mov.u64
 // tile_bytes[kTLook + i] = stream byte tile_b0 + i; every thread owns kVec adjacent 16-byte vectors.
 // Bytes before the stream start read as 0x00 ("boundary": a value can never extend across them, and they are not
 // counted as values); bytes past the end read as 0x80 (never terminate anything).
+// True when this thread's vector vv of tile t lies completely inside the stream (plain aligned 16-byte load).
+__device__ __forceinline__ bool tile_vector_interior(uint32_t size, int64_t tile_b0, int vv) {
+  const int64_t b = tile_b0 + (threadIdx.x * kVec + vv) * 16u;
+  return b >= 0 && b + 16 <= static_cast<int64_t>(size);
+}
+__device__ __forceinline__ uint4 tile_vector_fetch(const uint8_t* aligned, uint32_t t, int vv) {
+  return __ldcs(reinterpret_cast<const uint4*>(aligned + static_cast<size_t>(t) * kTB + (threadIdx.x * kVec + vv) * 16u));
+}
+
 __device__ __forceinline__ uint32_t tile_load_masks(uint8_t* tile_bytes, const uint8_t* aligned, const uint8_t* body, uint32_t size,
-                                                    uint32_t t, int64_t tile_b0) {
+                                                    uint32_t t, int64_t tile_b0, bool have_pre = false, uint4 pre = uint4()) {
   uint32_t tmask = 0;  // bit j: byte j of my kVec*16 bytes ends a value (and lies inside the stream)
 #pragma unroll
   for (int vv = 0; vv < kVec; ++vv) {
@@ -301,7 +300,7 @@ __device__ __forceinline__ uint32_t tile_load_masks(uint8_t* tile_bytes, const u
     const int64_t b = tile_b0 + i;
     uint32_t w0, w1, w2, w3;
     if (b >= 0 && b + 16 <= static_cast<int64_t>(size)) {
-      const uint4 q = __ldcs(reinterpret_cast<const uint4*>(aligned + static_cast<size_t>(t) * kTB + i));
+      const uint4 q = (have_pre && vv == 0) ? pre : __ldcs(reinterpret_cast<const uint4*>(aligned + static_cast<size_t>(t) * kTB + i));
       w0 = q.x; w1 = q.y; w2 = q.z; w3 = q.w;
     } else {
       w0 = w1 = w2 = w3 = 0;
@@ -376,19 +375,24 @@ __device__ __forceinline__ void tile_decode_run(const uint8_t* tile_bytes, const
   } else {
     prev_end = (v0 - 1 < tile_cnt) ? kTLook + pos16[v0 - 1] : 0u;
   }
+  // Values past tile_cnt (only in the tile's last threads) are decoded from a clamped position and never used:
+  // callers only consume the first min(VT, take - v0) values of a run.
+  const uint32_t last = tile_cnt ? tile_cnt - 1u : 0u;
 #pragma unroll
-  for (int k = 0; k < VTMAX; ++k) {
-    if (k >= static_cast<int>(VT)) break;
-    d[k] = 0;
-    const uint32_t vi = v0 + k;
-    if (vi < tile_cnt) {
-      const uint32_t e = kTLook + pos16[vi];
-      bool nan = false;
-      uint32_t bad = 0;
-      d[k] = decode_value(tile_bytes, e, e - prev_end, nan, bad);
-      if (nan) nanm |= 1ull << k;
-      if (bad && badk == 0xFFFFFFFFu) { badcode = bad; badk = k; }
-      prev_end = e;
+  for (int g = 0; g < VTMAX; g += 4) {
+    if (g >= static_cast<int>(VT)) break;
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      const int k = g + kk;
+      if (k < VTMAX) {
+        const uint32_t e = kTLook + pos16[min(v0 + k, last)];
+        bool nan = false;
+        uint32_t bad = 0;
+        d[k] = decode_value(tile_bytes, e, e - prev_end, nan, bad);
+        if (nan) nanm |= 1ull << k;
+        if (bad && badk == 0xFFFFFFFFu) { badcode = bad; badk = k; }
+        prev_end = e;
+      }
     }
   }
 }
@@ -398,10 +402,22 @@ template <int K>
 __device__ __forceinline__ SegK<K> cta_seg_exclusive(const SegK<K>& mine, TileShared& sh, SegK<K>* total) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   SegK<K> inc = mine;
+  if (!__any_sync(0xffffffffu, mine.rst != 0u)) {
+    // no NaN reset in this warp (the common case): plain wrapping prefix sums
 #pragma unroll
-  for (int dd = 1; dd < 32; dd <<= 1) {
-    const SegK<K> up = seg_shfl_up<K>(inc, dd);
-    if (lane >= dd) inc = seg_then<K>(up, inc);
+    for (int dd = 1; dd < 32; dd <<= 1) {
+#pragma unroll
+      for (int j = 0; j < K; ++j) {
+        const int32_t up = __shfl_up_sync(0xffffffffu, inc.sum[j], dd);
+        if (lane >= dd) inc.sum[j] = wadd32(inc.sum[j], up);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int dd = 1; dd < 32; dd <<= 1) {
+      const SegK<K> up = seg_shfl_up<K>(inc, dd);
+      if (lane >= dd) inc = seg_then<K>(up, inc);
+    }
   }
   if (lane == 31) {
 #pragma unroll
@@ -560,16 +576,26 @@ __global__ void __launch_bounds__(kThreads, kVec == 1 ? 4 : 3) decode_chunks_seq
     int32_t carry[K];
 #pragma unroll
     for (int j = 0; j < K; ++j) carry[j] = 0;
+    // software prefetch: the next tile's (first) vector is requested before the current tile is processed
+    bool have_pre = false;
+    uint4 pre = make_uint4(0, 0, 0, 0);
     for (uint32_t t = 0; t < n_tiles && done < V; ++t) {
+      const size_t gt = static_cast<size_t>(gc) * 80 + t;  // trace slot (development aid)
+      TRACE(0);
       const int64_t tile_b0 = static_cast<int64_t>(t) * kTB - mis;
-      const uint32_t tmask = tile_load_masks(tile_bytes, aligned, body, size, t, tile_b0);
+      const uint32_t tmask = tile_load_masks(tile_bytes, aligned, body, size, t, tile_b0, have_pre, pre);
+      have_pre = (t + 1 < n_tiles) && tile_vector_interior(size, tile_b0 + kTB, 0);
+      if (have_pre) pre = tile_vector_fetch(aligned, t + 1, 0);
+      TRACE(1);
       const uint32_t tile_cnt = tile_rank_compact(tmask, pos16, sh.scan);
+      TRACE(2);
       const uint32_t VT = ((tile_cnt + kThreads - 1) / kThreads + K - 1) / K * K;
       const uint32_t v0 = threadIdx.x * VT;
       int32_t d[VTMAX];
       unsigned long long nanm;
       uint32_t badcode, badk;
       tile_decode_run<VTMAX>(tile_bytes, pos16, tile_cnt, VT, v0, d, nanm, badcode, badk);
+      TRACE(3);
       const uint32_t take = min(tile_cnt, V - done);
       if (take > 0 && done + take == V && threadIdx.x == 0) L.stream_end[gc] = static_cast<uint32_t>(tile_b0 + pos16[take - 1] + 1);
       const uint32_t n_mine = v0 < take ? min(VT, take - v0) : 0u;
@@ -578,6 +604,7 @@ __global__ void __launch_bounds__(kThreads, kVec == 1 ? 4 : 3) decode_chunks_seq
       const SegK<K> mine = seg_to_global<K>(run_reduce_local<K, VTMAX>(d, nanm, n_mine), phase);
       SegK<K> total;
       const SegK<K> ex = cta_seg_exclusive<K>(mine, sh, &total);
+      TRACE(4);
       int32_t cur[K];
 #pragma unroll
       for (int j = 0; j < K; ++j) cur[j] = ((ex.rst >> j) & 1u) ? ex.sum[j] : wadd32(carry[j], ex.sum[j]);
@@ -585,8 +612,10 @@ __global__ void __launch_bounds__(kThreads, kVec == 1 ? 4 : 3) decode_chunks_seq
       else run_emit_local<K, VTMAX, false>(d, nanm, n_mine, cur, phase, out, (done + v0) / K, step, mul, off);
 #pragma unroll
       for (int j = 0; j < K; ++j) carry[j] = ((total.rst >> j) & 1u) ? total.sum[j] : wadd32(carry[j], total.sum[j]);
+      TRACE(5);
       done += take;
       __syncthreads();  // tile_bytes / pos16 / sh are reused by the next tile
+      TRACE(6);
     }
     if (done < V && threadIdx.x == 0) report_error(L.err, DEV_ERR_TRUNCATED);  // v4_codec.cpp:102-104
   }

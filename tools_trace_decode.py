@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import numpy as np, torch
 import cloudini_b200 as cb
 from cloudini_b200 import synth
-F, N = 8, 1_000_000
+F, N = int(os.environ.get("TRACE_FRAMES", "8")), 1_000_000
 info = synth.info_xyzi(N)
 s = torch.cuda.Stream(); torch.cuda.set_stream(s)
 enc = cb.PointcloudEncoder(info, stream=s.cuda_stream); dec = cb.PointcloudDecoder(stream=s.cuda_stream)
@@ -24,15 +24,19 @@ tr = np.fromfile("/tmp/cldn_trace.bin", dtype=np.uint64).reshape(-1, 8)
 tr = tr[tr[:, 0] > 0]
 t0 = tr[:, 0].min()
 rel = (tr.astype(np.int64) - np.int64(t0)) / 1000.0
-print("tiles", len(tr), "kernel span us", rel[:, 7].max())
+print("tiles", len(tr), "kernel span us", rel.max())
 names = ["start->scan", "scan->LB1done(w0)", "LB1->decoded", "decoded->sync", "sync->reduce", "reduce->LB2", "LB2->end"]
+if os.environ.get("CLDN_B200_DECODE_MODE") == "seq":
+    names = ["load+masks", "rank+compact", "decode run", "reduce+scan", "emit", "end sync", "-"]
 for k in range(7):
-    dur = rel[:, k + 1] - rel[:, k]
-    dur = dur[(tr[:, k + 1] > 0)]
+    ok = (tr[:, k + 1] > 0) & (tr[:, k] > 0)
+    if not ok.any():
+        continue
+    dur = (rel[:, k + 1] - rel[:, k])[ok]
     print(f"{names[k]:22s} mean {dur.mean():7.2f} us  p50 {np.median(dur):7.2f}  p95 {np.percentile(dur,95):7.2f}  max {dur.max():7.2f}")
-tot = rel[:, 7] - rel[:, 0]
-print("tile total mean", tot[tr[:,7]>0].mean(), "us")
+last = 6 if os.environ.get("CLDN_B200_DECODE_MODE") == "seq" else 7
+tot = rel[:, last] - rel[:, 0]
+print("tile total mean", tot[tr[:,last]>0].mean(), "us")
 # start time vs tile index
 idx = np.arange(len(tr))
-for q in (0, len(tr)//4, len(tr)//2, 3*len(tr)//4, len(tr)-1):
-    print("tile", q, "start", rel[q, 0], "end", rel[q, 7])
+
