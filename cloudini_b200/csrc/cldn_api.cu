@@ -339,6 +339,12 @@ static int encode_batch_device(cldn_encoder* e, size_t n_frames, const void* con
   L.err = e->d_err.p;
   L.tile_points = T;
   L.flags = aligned16 ? kEncInputsAligned16 : 0u;
+  L.uniform_tiles = 0;
+  if (n_frames > 0 && hf[0].n_tiles > 0) {
+    bool uniform = true;
+    for (size_t f = 1; f < n_frames; ++f) uniform = uniform && hf[f].n_tiles == hf[0].n_tiles;
+    if (uniform) L.uniform_tiles = hf[0].n_tiles;
+  }
 
   if (e->plan.n_sections > 0) {
     // V5: adaptive integer sections are produced first (they determine where every later chunk starts).

@@ -98,10 +98,10 @@ __device__ __forceinline__ void handle_empty_frames(const EncLaunch& L) {
 
 // Common tail of both encode kernels: copy-out, chunk prefix back-patch, frame size.
 //  total   = bytes staged by this tile, excl = data bytes of all earlier tiles of the frame (look-back result)
+template <uint32_t T>  // points per tile: a power of two that divides the chunk, so the divisions below are shifts
 __device__ __forceinline__ void finish_tile(const EncLaunch& L, const EncFrame& F, uint32_t frame_idx, uint32_t t,
                                             const uint8_t* stage, uint32_t total, uint64_t excl) {
-  const uint32_t T = L.tile_points;
-  const uint32_t tiles_per_chunk = kChunkPoints / T;
+  constexpr uint32_t tiles_per_chunk = kChunkPoints / T;
   const uint32_t chunk = t / tiles_per_chunk;
   const uint64_t sec_before = F.sec_excl ? F.sec_excl[chunk] : 0;
   uint8_t* payload = F.out + L.header_bytes;
@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(kThreads) encode_generic_kernel(const EncLaunc
   }
   if (blockIdx.x == 0) handle_empty_frames(L);
   const uint32_t tile = blockIdx.x;
-  const uint32_t fi = find_frame(L.frames, L.n_frames, tile);
+  const uint32_t fi = L.uniform_tiles ? tile / L.uniform_tiles : find_frame(L.frames, L.n_frames, tile);
   const EncFrame F = L.frames[fi];
   const uint32_t t = tile - F.tile_begin;
   const uint32_t T = kThreads * I;
@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(kThreads) encode_generic_kernel(const EncLaunc
     if (threadIdx.x == 0) s_excl = e;
   }
   __syncthreads();
-  finish_tile(L, F, fi, t, stage, total, s_excl);
+  finish_tile<kThreads * I>(L, F, fi, t, stage, total, s_excl);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -222,7 +222,7 @@ __global__ void __launch_bounds__(kThreads, MINB) encode_floatn_kernel(const Enc
 
   if (blockIdx.x == 0) handle_empty_frames(L);
   const uint32_t tile = blockIdx.x;
-  const uint32_t fi = find_frame(L.frames, L.n_frames, tile);
+  const uint32_t fi = L.uniform_tiles ? tile / L.uniform_tiles : find_frame(L.frames, L.n_frames, tile);
   const EncFrame F = L.frames[fi];
   const uint32_t t = tile - F.tile_begin;
   constexpr uint32_t T = kThreads * I;
@@ -286,9 +286,10 @@ __global__ void __launch_bounds__(kThreads, MINB) encode_floatn_kernel(const Enc
       carry[k] = rot;  // only lane 0 uses it (it holds lane 31's value of this iteration)
       const uint32_t d = static_cast<uint32_t>(q) - static_cast<uint32_t>(prev);
       const uint32_t zz = (d << 1) ^ static_cast<uint32_t>(static_cast<int32_t>(d) >> 31);
-      const uint32_t u = nan ? 0u : zz + 1u;           // u == 0 only for zz == 0xFFFFFFFF (5 bytes) or NaN
-      const bool wrap = !nan && zz == 0xFFFFFFFFu;
-      const uint32_t b = wrap ? 32u : 31u - __clz(u | 1u);
+      // zz + 1 saturated at 2^32 - 1: the only wrapping input (zz = 2^32 - 1, a 5-byte varint) lands in the slow path
+      // either way, and lengths stay exact (bits >= 29 -> 5 bytes); NaN lanes become the single 0x00 byte
+      const uint32_t u = nan ? 0u : min(zz, 0xFFFFFFFEu) + 1u;
+      const uint32_t b = 31u - __clz(u | 1u);
       bmax = max(bmax, b);
       const uint32_t lenm1 = (b * 37u) >> 8;            // floor(b / 7) for b <= 34
       // 7-bit groups -> bytes: adding the masked upper part to itself shifts it left by one, three times
@@ -323,7 +324,8 @@ __global__ void __launch_bounds__(kThreads, MINB) encode_floatn_kernel(const Enc
     if (g + 1 < I) { off[g + 1] = run + ((exc >> 10) & 1023u); run += (tot >> 10) & 1023u; }
     if (g + 2 < I) { off[g + 2] = run + ((exc >> 20) & 1023u); run += (tot >> 20) & 1023u; }
   }
-  const uint32_t big = bmax >= 28u ? 1u : 0u;
+  // the word-packing fast path assumes a full tile; the (single) partial tile of a frame takes the byte-wise path too
+  const uint32_t big = (bmax >= 28u || tile_p0 + T > F.n_points) ? 1u : 0u;
   if (lane == 0) s_wtot[warp] = run;
   const int any_big = __syncthreads_or(static_cast<int>(big));
   uint32_t wbase = 0, total = 0;
@@ -333,8 +335,11 @@ __global__ void __launch_bounds__(kThreads, MINB) encode_floatn_kernel(const Enc
     if (w < warp) wbase += x;
     total += x;
   }
-  if (threadIdx.x == 0) {
-    st_relaxed_u64(L.status + tile, pack_status(t == 0 ? kFlagIncl : kFlagAgg, L.epoch, total));
+  // ---- tile base: warp 0 publishes the aggregate and resolves the look-back now, so that its wait overlaps with the
+  //      other warps' packing (warp 0 packs afterwards) ----
+  if (threadIdx.x < 32) {
+    const uint64_t ex = tile_lookback(L.status, F.tile_begin, tile, L.epoch, total);
+    if (threadIdx.x == 0) s_excl = ex;
   }
 
   // ---- phase 2: pack bytes into the staging buffer at tile-local offsets ----
@@ -342,12 +347,10 @@ __global__ void __launch_bounds__(kThreads, MINB) encode_floatn_kernel(const Enc
     uint32_t tail_carry = 0;  // partial last word of the previous iteration's lane 31
 #pragma unroll
     for (int i = 0; i < I; ++i) {
-      const uint32_t pidx = warp_p0 + 32 * i + lane;
-      const bool valid = pidx < F.n_points;
       const uint32_t l0 = pre[i] & 0xFFu;
       const uint32_t c2 = (pre[i] >> 8) & 0xFFu;          // len(v0) + len(v1): 2..8
       const uint32_t l2 = ((pre[i] >> 16) & 0xFFu) - c2;
-      const uint32_t len = valid ? (pre[i] >> 24) : 0u;   // 3..16
+      const uint32_t len = pre[i] >> 24;                  // 3..16
       // A = value0 | value1 << 8*l0  (<= 8 bytes)
       const uint32_t sa = 8u * l0;
       const uint32_t a_lo = r[i][0] | (sa < 32u ? (r[i][1] << sa) : 0u);
@@ -379,15 +382,18 @@ __global__ void __launch_bounds__(kThreads, MINB) encode_floatn_kernel(const Enc
       const uint32_t S4 = __funnelshift_l(w3, 0u, sh);
       const uint32_t nw = (s + len + 3u) >> 2;      // words touched: 1..5
       const uint32_t e = (pos + len) & 3u;          // != 0: last word is shared with the next point
-      uint32_t tailw = (nw == 1u) ? S0 : (nw == 2u) ? S1 : (nw == 3u) ? S2 : (nw == 4u) ? S3 : S4;
-      if (e == 0u || !valid) tailw = 0u;
+      // last word touched = S[nw - 1]: two-level select on the bits of (nw - 1)
+      const uint32_t li = nw - 1u;
+      const uint32_t t01 = (li & 1u) ? S1 : S0, t23 = (li & 1u) ? S3 : S2;
+      uint32_t tailw = (li & 4u) ? S4 : ((li & 2u) ? t23 : t01);
+      if (e == 0u) tailw = 0u;
       uint32_t headw = __shfl_up_sync(0xffffffffu, tailw, 1);
       if (lane == 0) headw = tail_carry;
       tail_carry = __shfl_sync(0xffffffffu, tailw, 31);
-      if (valid) {
+      {
         const uint32_t W0 = pos >> 2;
         const bool first_of_warp = (i == 0 && lane == 0);
-        const bool last_of_warp = (i == I - 1 && lane == 31) || (pidx + 1 >= F.n_points);
+        const bool last_of_warp = (i == I - 1 && lane == 31);
         const uint32_t full = (e != 0u) ? nw - 1u : nw;  // words I own completely (tail word belongs to the next point)
         if (first_of_warp && s != 0u) {
           // the first word also holds bytes of the previous warp's last point: byte stores for my part
@@ -433,12 +439,8 @@ __global__ void __launch_bounds__(kThreads, MINB) encode_floatn_kernel(const Enc
       }
     }
   }
-  if (threadIdx.x < 32) {
-    const uint64_t ex = tile_lookback(L.status, F.tile_begin, tile, L.epoch, total);
-    if (threadIdx.x == 0) s_excl = ex;
-  }
   __syncthreads();
-  finish_tile(L, F, fi, t, stage, total, s_excl);
+  finish_tile<kThreads * I>(L, F, fi, t, stage, total, s_excl);
 }
 
 // ------------------------------------------------------------------------------------------------------------------

@@ -32,6 +32,7 @@ struct EncLaunch {
   uint32_t* err;
   uint32_t tile_points;    // 256 * I (choose_tile_points)
   uint32_t flags;          // kEncInputsAligned16: every frame's input base is 16-byte aligned
+  uint32_t uniform_tiles;  // > 0: every frame has exactly this many tiles (frame = tile / uniform_tiles, no search)
 };
 constexpr uint32_t kEncInputsAligned16 = 1u;
 uint32_t choose_tile_points(const Plan& plan);

@@ -256,3 +256,48 @@ def test_floatn_decode_modes(oracle, monkeypatch, mode):
         _roundtrip_check(*synth.cloud_c2(n, seed=n + 12), oracle, fill=0x42)
     _roundtrip_check(*synth.cloud_c1(20_000, seed=3, adversarial=True), oracle)
     _roundtrip_check(*synth.cloud_c3(70_000, seed=8), oracle, fill=0x99)
+
+
+def test_batch_decode_device_and_host_apis(oracle):
+    import torch
+    info = synth.info_xyzi(50_000)
+    clouds = [synth.cloud_c2(50_000, seed=300 + k)[1] for k in range(5)]
+    enc, dec = cb.PointcloudEncoder(info), cb.PointcloudDecoder()
+    cap = cb.MaxCompressedSize(info, 50_000, True)
+    # host batch: blobs identical to one-by-one oracle encodes
+    outs = [np.zeros(cap, dtype=np.uint8) for _ in clouds]
+    sizes = enc.encode_batch_host(clouds, outs, write_header=True)
+    blobs = [bytes(o[:s]) for o, s in zip(outs, sizes)]
+    for c, b in zip(clouds, blobs):
+        assert b == oracle.encode(info, c)
+    hdr = len(enc.getHeader())
+    # device batch decode
+    d_blobs = [torch.from_numpy(np.frombuffer(b, dtype=np.uint8).copy()).cuda() for b in blobs]
+    d_outs = [torch.zeros(50_000 * 16, dtype=torch.uint8, device="cuda") for _ in blobs]
+    batch = dec.make_device_batch([t.data_ptr() + hdr for t in d_blobs], [len(b) - hdr for b in blobs], [t.data_ptr() for t in d_outs], [50_000 * 16] * 5)
+    dec.decode_batch_device(info, batch, sync=True)
+    h_outs = [np.zeros(50_000 * 16, dtype=np.uint8) for _ in blobs]
+    dec.decode_batch_host(info, [b[hdr:] for b in blobs], h_outs)
+    for b, d, h in zip(blobs, d_outs, h_outs):
+        want = np.zeros(50_000 * 16, dtype=np.uint8)
+        oracle.decode(b, want)
+        assert np.array_equal(d.cpu().numpy(), want) and np.array_equal(h, want)
+
+
+def test_one_shot_c_abi_like_wasm(oracle):
+    # cldn_b200_EncodePointcloudData / cldn_b200_DecodeCompressedData: same shape and "0 on failure" convention as
+    # cldn_EncodePointcloudData / cldn_DecodeCompressedData (wasm_functions.h:62-93)
+    import ctypes as C
+    info, cloud = synth.cloud_c2(20_000, seed=77)
+    L = cb.lib()
+    yaml = cb.EncodingInfoToYAML(info).encode()
+    out = np.zeros(cb.MaxCompressedSize(info, 20_000, True), dtype=np.uint8)
+    n = L.cldn_b200_EncodePointcloudData(yaml, cloud.ctypes.data, cloud.nbytes, out.ctypes.data, out.nbytes)
+    assert n > 0 and bytes(out[:n]) == oracle.encode(info, cloud)
+    dec = np.zeros(20_000 * 16, dtype=np.uint8)
+    m = L.cldn_b200_DecodeCompressedData(out.ctypes.data, n, dec.ctypes.data, dec.nbytes)
+    want = np.zeros_like(dec)
+    oracle.decode(bytes(out[:n]), want)
+    assert m == dec.nbytes and np.array_equal(dec, want)
+    assert L.cldn_b200_EncodePointcloudData(yaml, cloud.ctypes.data, cloud.nbytes - 16, out.ctypes.data, out.nbytes) == 0  # size mismatch
+    assert L.cldn_b200_DecodeCompressedData(out.ctypes.data, 5, dec.ctypes.data, dec.nbytes) == 0                           # bad header
