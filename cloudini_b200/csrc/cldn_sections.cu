@@ -22,6 +22,35 @@ constexpr uint32_t kSmemPaletteSlots = 4096;   // open addressing, at most half 
 constexpr uint32_t kGlobalPaletteSlots = 65536;  // 32768 values per chunk at most -> never more than half full
 constexpr uint64_t kEmptyKey = 0xFFFFFFFFFFFFFFFFull;
 constexpr uint32_t kOverflowTables = 64;
+constexpr int kSecThreads = 1024;  // one CTA per SM (shared-memory bound): use all its warp slots to hide the strided loads
+
+// CTA-wide exclusive scan for kSecThreads threads; scratch = 33 uint32. Same contract as block_exclusive_scan.
+__device__ __forceinline__ uint32_t sec_exclusive_scan(uint32_t v, uint32_t* scratch, uint32_t* total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t inc = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= d) inc += t;
+  }
+  if (lane == 31) scratch[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    const uint32_t w = scratch[lane];
+    uint32_t winc = w;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, winc, d);
+      if (lane >= d) winc += t;
+    }
+    scratch[lane] = winc - w;
+    if (lane == 31) scratch[32] = winc;
+  }
+  __syncthreads();
+  const uint32_t res = scratch[warp] + inc - v;
+  *total = scratch[32];
+  return res;
+}
 
 struct SecItem {
   const uint8_t* base;  // first point of the chunk + field offset
@@ -55,7 +84,7 @@ __device__ __forceinline__ uint64_t mix64(uint64_t x) {  // table placement only
 
 __device__ __forceinline__ uint32_t block_sum(uint32_t v, uint32_t* scratch) {
   uint32_t total;
-  block_exclusive_scan(v, scratch, &total);
+  sec_exclusive_scan(v, scratch, &total);
   __syncthreads();
   return total;
 }
@@ -74,7 +103,7 @@ __device__ __forceinline__ bool run_head(const SecItem& it, uint32_t i) {
 template <bool DELTA>
 __device__ uint32_t build_heads(const SecItem& it, uint32_t n, uint16_t* heads, uint32_t* scan) {
   uint32_t base = 0;
-  for (uint32_t t0 = 0; t0 < n; t0 += kThreads * 8) {
+  for (uint32_t t0 = 0; t0 < n; t0 += kSecThreads * 8) {
     uint32_t flags = 0;
     const uint32_t i0 = t0 + threadIdx.x * 8;
 #pragma unroll
@@ -82,7 +111,7 @@ __device__ uint32_t build_heads(const SecItem& it, uint32_t n, uint16_t* heads, 
       if (i0 + k < n && run_head<DELTA>(it, i0 + k)) flags |= 1u << k;
     }
     uint32_t total;
-    uint32_t rank = base + block_exclusive_scan(__popc(flags), scan, &total);
+    uint32_t rank = base + sec_exclusive_scan(__popc(flags), scan, &total);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       if (flags & (1u << k)) heads[rank++] = static_cast<uint16_t>(i0 + k);
@@ -105,7 +134,7 @@ __device__ __forceinline__ uint32_t run_bytes(const SecItem& it, uint32_t head, 
 __device__ uint32_t write_delta_section(const SecItem& it, uint8_t* out, uint32_t* scan) {
   if (threadIdx.x == 0) out[0] = 0;
   uint32_t base = 1;
-  for (uint32_t t0 = 0; t0 < it.n; t0 += kThreads * 8) {
+  for (uint32_t t0 = 0; t0 < it.n; t0 += kSecThreads * 8) {
     const uint32_t i0 = t0 + threadIdx.x * 8;
     uint64_t u[8];
     uint32_t mine = 0;
@@ -118,7 +147,7 @@ __device__ uint32_t write_delta_section(const SecItem& it, uint8_t* out, uint32_
       }
     }
     uint32_t total;
-    uint32_t off = base + block_exclusive_scan(mine, scan, &total);
+    uint32_t off = base + sec_exclusive_scan(mine, scan, &total);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       if (i0 + k < it.n) {
@@ -142,7 +171,7 @@ __device__ uint32_t write_run_section(const SecItem& it, uint8_t* out, uint16_t*
     store_u32(out + 1, runs);
   }
   uint32_t base = 5;
-  for (uint32_t r0 = 0; r0 < runs; r0 += kThreads * 8) {
+  for (uint32_t r0 = 0; r0 < runs; r0 += kSecThreads * 8) {
     const uint32_t q0 = r0 + threadIdx.x * 8;
     uint32_t mine = 0;
 #pragma unroll
@@ -155,7 +184,7 @@ __device__ uint32_t write_run_section(const SecItem& it, uint8_t* out, uint16_t*
       }
     }
     uint32_t total;
-    uint32_t off = base + block_exclusive_scan(mine, scan, &total);
+    uint32_t off = base + sec_exclusive_scan(mine, scan, &total);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const uint32_t r = q0 + k;
@@ -249,7 +278,7 @@ __device__ uint32_t write_palette_section(const PaletteTable& T, const SecItem& 
   if (!palette_insert_all(T, it, it.n, s_count)) return 0xFFFFFFFFu;
   // ranks in first-appearance order: value i is a "first" iff the table says its smallest index is i
   uint32_t base = 0;
-  for (uint32_t t0 = 0; t0 < it.n; t0 += kThreads * 8) {
+  for (uint32_t t0 = 0; t0 < it.n; t0 += kSecThreads * 8) {
     const uint32_t i0 = t0 + threadIdx.x * 8;
     uint32_t flags = 0;
     uint32_t slot[8];
@@ -262,7 +291,7 @@ __device__ uint32_t write_palette_section(const PaletteTable& T, const SecItem& 
       }
     }
     uint32_t total;
-    uint32_t rank = base + block_exclusive_scan(__popc(flags), scan, &total);
+    uint32_t rank = base + sec_exclusive_scan(__popc(flags), scan, &total);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       if (flags & (1u << k)) {
@@ -307,7 +336,7 @@ __device__ uint32_t write_palette_section(const PaletteTable& T, const SecItem& 
 
 // ---- shared memory layout of the section kernels -------------------------------------------------------------------
 struct SecShared {
-  uint32_t scan[kThreads / 32 + 1];
+  uint32_t scan[kSecThreads / 32 + 1];
   uint32_t count;
   uint32_t pad_[2];
   unsigned long long keys[kSmemPaletteSlots + 1];
@@ -328,7 +357,7 @@ __device__ __forceinline__ SecItem make_item(const EncFrame& F, const Plan& plan
 }
 
 // ---- probe: selectBestAdaptiveIntMode on the first min(4096, chunk 0) values (v5_codec.cpp:387-421, 934-949) ------
-__global__ void __launch_bounds__(kThreads) probe_modes_kernel(const SecLaunch L) {
+__global__ void __launch_bounds__(kSecThreads, 1) probe_modes_kernel(const SecLaunch L) {
   extern __shared__ __align__(16) uint8_t dyn_smem[];
   SecShared& sh = *reinterpret_cast<SecShared*>(dyn_smem);
   const Plan& plan = *L.plan;
@@ -395,7 +424,7 @@ __global__ void __launch_bounds__(kThreads) probe_modes_kernel(const SecLaunch L
 }
 
 // ---- sections ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads) encode_sections_kernel(const SecLaunch L) {
+__global__ void __launch_bounds__(kSecThreads, 1) encode_sections_kernel(const SecLaunch L) {
   extern __shared__ __align__(16) uint8_t dyn_smem[];
   SecShared& sh = *reinterpret_cast<SecShared*>(dyn_smem);
   const Plan& plan = *L.plan;
@@ -422,7 +451,7 @@ __global__ void __launch_bounds__(kThreads) encode_sections_kernel(const SecLaun
 
 // Chunks whose palette does not fit the shared-memory table: same algorithm on a 65536-slot table in global memory.
 // A fixed pool of kOverflowTables CTAs, each owning one table, sweeps the (normally empty) list of flagged items.
-__global__ void __launch_bounds__(kThreads) palette_overflow_kernel(const SecLaunch L) {
+__global__ void __launch_bounds__(kSecThreads, 1) palette_overflow_kernel(const SecLaunch L) {
   extern __shared__ __align__(16) uint8_t dyn_smem[];
   SecShared& sh = *reinterpret_cast<SecShared*>(dyn_smem);
   const Plan& plan = *L.plan;
@@ -498,9 +527,9 @@ int launch_encode_sections(const Plan& plan, const SecLaunch& L, cudaStream_t st
   if (cudaFuncSetAttribute(probe_modes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess) return -1;
   if (cudaFuncSetAttribute(encode_sections_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess) return -1;
   if (cudaFuncSetAttribute(palette_overflow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess) return -1;
-  probe_modes_kernel<<<L.n_frames * plan.n_sections, kThreads, smem, stream>>>(L);
-  encode_sections_kernel<<<L.n_chunks_total * plan.n_sections, kThreads, smem, stream>>>(L);
-  palette_overflow_kernel<<<kOverflowTables, kThreads, smem, stream>>>(L);
+  probe_modes_kernel<<<L.n_frames * plan.n_sections, kSecThreads, smem, stream>>>(L);
+  encode_sections_kernel<<<L.n_chunks_total * plan.n_sections, kSecThreads, smem, stream>>>(L);
+  palette_overflow_kernel<<<kOverflowTables, kSecThreads, smem, stream>>>(L);
   scan_sections_kernel<<<(L.n_frames + 127) / 128, 128, 0, stream>>>(L);
   count_launch(4);
   return 4;
