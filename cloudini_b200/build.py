@@ -54,7 +54,7 @@ def build(force=False, verbose=False, defines=(), out=None):
         if verbose:
             sys.stderr.write(out)
         objs.append(obj)
-    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", lib, *objs, "-lcudart"]
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", lib, *objs, "-lcudart", "-ldl"]
     subprocess.check_call(cmd)
     return lib
 

@@ -2,6 +2,7 @@
 // There is deliberately no CPU implementation of the codec here: if CUDA is unavailable every compute entry point
 // fails with CLDN_ERR_CUDA.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -127,6 +128,104 @@ struct CopyPipeline {
   }
 };
 
+// ---- stage 2 (general-purpose compression of every chunk) ---------------------------------------------------------
+// Not the product (north_star: delegated / bypassed) and not part of the GPU path: when a caller asks for LZ4 / ZSTD
+// through the HOST-pointer API, the stage-1 bytes produced by the kernels are handed chunk by chunk to the system's
+// liblz4 / libzstd (dlopen, like the reference links them: codec_common.cpp:220-299). Compressed bytes are not
+// expected to equal the reference's (different library versions); they decompress to the same stage-1 bytes.
+struct Stage2 {
+  void* lz4 = nullptr;
+  void* zstd = nullptr;
+  int (*lz4_compress)(const char*, char*, int, int) = nullptr;
+  int (*lz4_decompress)(const char*, char*, int, int) = nullptr;
+  size_t (*zstd_compress)(void*, size_t, const void*, size_t, int) = nullptr;
+  size_t (*zstd_decompress)(void*, size_t, const void*, size_t) = nullptr;
+  unsigned (*zstd_is_error)(size_t) = nullptr;
+  bool load(int option) {
+    if (option == CLDN_COMP_LZ4) {
+      if (!lz4) {
+        lz4 = dlopen("liblz4.so.1", RTLD_NOW);
+        if (!lz4) lz4 = dlopen("liblz4.so", RTLD_NOW);
+        if (lz4) {
+          lz4_compress = reinterpret_cast<int (*)(const char*, char*, int, int)>(dlsym(lz4, "LZ4_compress_default"));
+          lz4_decompress = reinterpret_cast<int (*)(const char*, char*, int, int)>(dlsym(lz4, "LZ4_decompress_safe"));
+        }
+      }
+      if (!lz4_compress || !lz4_decompress) { set_error("stage 2: liblz4 is not available on this host"); return false; }
+      return true;
+    }
+    if (!zstd) {
+      zstd = dlopen("libzstd.so.1", RTLD_NOW);
+      if (!zstd) zstd = dlopen("libzstd.so", RTLD_NOW);
+      if (zstd) {
+        zstd_compress = reinterpret_cast<size_t (*)(void*, size_t, const void*, size_t, int)>(dlsym(zstd, "ZSTD_compress"));
+        zstd_decompress = reinterpret_cast<size_t (*)(void*, size_t, const void*, size_t)>(dlsym(zstd, "ZSTD_decompress"));
+        zstd_is_error = reinterpret_cast<unsigned (*)(size_t)>(dlsym(zstd, "ZSTD_isError"));
+      }
+    }
+    if (!zstd_compress || !zstd_decompress || !zstd_is_error) { set_error("stage 2: libzstd is not available on this host"); return false; }
+    return true;
+  }
+};
+static Stage2 g_stage2;
+
+// Re-frames a stage-1 payload ([u32 size][body])* into ([u32 csize][compressed body])* — WriteStage1Chunk, chunk_writer.cpp:42-47.
+static int stage2_compress_payload(int option, const uint8_t* src, size_t src_bytes, uint8_t* dst, size_t dst_cap, size_t* written) {
+  size_t ip = 0, op = 0;
+  while (ip < src_bytes) {
+    uint32_t sz;
+    memcpy(&sz, src + ip, 4);
+    ip += 4;
+    if (dst_cap - op < 4) { set_error("Output buffer too small for compressed chunk"); return CLDN_ERR_BUFFER_TOO_SMALL; }
+    uint32_t csz = 0;
+    if (option == CLDN_COMP_LZ4) {  // codec_common.cpp:232-237
+      const int c = g_stage2.lz4_compress(reinterpret_cast<const char*>(src + ip), reinterpret_cast<char*>(dst + op + 4), static_cast<int>(sz),
+                                          static_cast<int>(std::min<size_t>(dst_cap - op - 4, 0x7FFFFFFF)));
+      if (c <= 0) { set_error("LZ4 compression failed"); return CLDN_ERR_BUFFER_TOO_SMALL; }
+      csz = static_cast<uint32_t>(c);
+    } else {                        // ZSTD level 1, codec_common.cpp:242
+      const size_t c = g_stage2.zstd_compress(dst + op + 4, dst_cap - op - 4, src + ip, sz, 1);
+      if (g_stage2.zstd_is_error(c)) { set_error("ZSTD compression failed"); return CLDN_ERR_BUFFER_TOO_SMALL; }
+      csz = static_cast<uint32_t>(c);
+    }
+    memcpy(dst + op, &csz, 4);
+    op += 4 + csz;
+    ip += sz;
+  }
+  *written = op;
+  return CLDN_OK;
+}
+
+// Inverse: ([u32 csize][compressed])* -> ([u32 size][stage-1 body])*; `max_body` bounds a decompressed chunk.
+static int stage2_decompress_payload(int option, const uint8_t* src, size_t src_bytes, std::vector<uint8_t>& dst, size_t max_body) {
+  size_t ip = 0;
+  dst.clear();
+  while (ip < src_bytes) {
+    if (src_bytes - ip < 4) { set_error("decode: not enough input data"); return CLDN_ERR_CORRUPT_DATA; }
+    uint32_t csz;
+    memcpy(&csz, src + ip, 4);
+    ip += 4;
+    if (csz > src_bytes - ip) { set_error("Invalid chunk size found while decoding"); return CLDN_ERR_CORRUPT_DATA; }
+    const size_t at = dst.size();
+    dst.resize(at + 4 + max_body);
+    uint32_t sz = 0;
+    if (option == CLDN_COMP_LZ4) {
+      const int r = g_stage2.lz4_decompress(reinterpret_cast<const char*>(src + ip), reinterpret_cast<char*>(dst.data() + at + 4), static_cast<int>(csz),
+                                            static_cast<int>(std::min<size_t>(max_body, 0x7FFFFFFF)));
+      if (r < 0) { set_error("LZ4 decompression failed"); return CLDN_ERR_CORRUPT_DATA; }
+      sz = static_cast<uint32_t>(r);
+    } else {
+      const size_t r = g_stage2.zstd_decompress(dst.data() + at + 4, max_body, src + ip, csz);
+      if (g_stage2.zstd_is_error(r)) { set_error("ZSTD decompression failed"); return CLDN_ERR_CORRUPT_DATA; }
+      sz = static_cast<uint32_t>(r);
+    }
+    memcpy(dst.data() + at, &sz, 4);
+    dst.resize(at + 4 + sz);
+    ip += csz;
+  }
+  return CLDN_OK;
+}
+
 int select_device(int device) {
   int count = 0;
   cudaError_t e = cudaGetDeviceCount(&count);
@@ -158,7 +257,9 @@ const char* dev_error_text(uint32_t code) {
 
 // =====================================================================================================================
 struct cldn_encoder {
-  cldn_info_t info;
+  cldn_info_t info;       // as given, except compression_opt = NONE (what the GPU path produces)
+  int stage2 = 0;         // the caller's compression_opt (host-pointer API only)
+  std::vector<uint8_t> s2_tmp;
   Plan plan;
   std::vector<uint8_t> header;
   int device = 0;
@@ -203,14 +304,13 @@ int cldn_b200_encoder_create(const cldn_info_t* info, int device, void* stream, 
     set_error("EncodingInfo needs a lossless float encoder (XOR / Gorilla) that this build does not accelerate");
     return CLDN_ERR_UNSUPPORTED;
   }
-  if (info->compression_opt != CLDN_COMP_NONE) {
-    set_error("compression_opt %d: stage 2 (LZ4/ZSTD) is delegated and not executed by this library; use NONE",
-              static_cast<int>(info->compression_opt));
-    return CLDN_ERR_UNSUPPORTED;
-  }
+  if (info->compression_opt > CLDN_COMP_ZSTD) { set_error("Unsupported compression option"); return CLDN_ERR_INVALID_ARGUMENT; }
+  if (info->compression_opt != CLDN_COMP_NONE && !g_stage2.load(info->compression_opt)) return CLDN_ERR_UNSUPPORTED;
   if (int rc = select_device(device)) return rc;
   cldn_encoder* e = new cldn_encoder();
   e->info = *info;
+  e->stage2 = info->compression_opt;        // the header declares it; the kernels always produce stage 1
+  e->info.compression_opt = CLDN_COMP_NONE;
   e->plan = plan;
   e->header = make_header(*info);
   cudaGetDevice(&e->device);
@@ -414,6 +514,44 @@ int cldn_b200_encode_batch(cldn_encoder_t* e, size_t n_frames, const void* const
   }
   if (n_frames == 0) return CLDN_OK;
   CUDA_TRY(cudaSetDevice(e->device));
+  if (mem == CLDN_MEM_DEVICE && e->stage2 != CLDN_COMP_NONE) {
+    set_error("compression_opt %d needs the host-pointer API: stage 2 (LZ4/ZSTD) is delegated to the host libraries", e->stage2);
+    return CLDN_ERR_UNSUPPORTED;
+  }
+  if (mem == CLDN_MEM_HOST && e->stage2 != CLDN_COMP_NONE) {
+    // stage 1 on the GPU, then every chunk through the system compressor (not pipelined: this is not the product path)
+    cldn_info_t full = e->info;
+    full.compression_opt = static_cast<uint8_t>(e->stage2);
+    const size_t hdr = write_header ? e->header.size() : 0;
+    for (size_t f = 0; f < n_frames; ++f) {
+      if (e->info.point_step == 0) { set_error("point_step cannot be 0"); return CLDN_ERR_INVALID_ARGUMENT; }
+      if (cloud_bytes[f] % e->info.point_step != 0) { set_error("Input cloud_data size is not a multiple of point_step"); return CLDN_ERR_INVALID_ARGUMENT; }
+      const size_t n = cloud_bytes[f] / e->info.point_step;
+      bool ok;
+      const size_t need = max_compressed_size(full, n, false, &ok) + hdr;  // cloudini.cpp:530-534
+      if (!ok) return CLDN_ERR_INVALID_ARGUMENT;
+      if (out_capacities[f] < need) { set_error("Output buffer too small for worst-case compressed size"); return CLDN_ERR_BUFFER_TOO_SMALL; }
+      size_t cap1 = max_compressed_size(e->info, n, false, &ok);
+      if (int rc = e->d_in.reserve(cloud_bytes[f] + 256)) return rc;
+      if (int rc = e->d_out.reserve(cap1 + 256)) return rc;
+      if (cloud_bytes[f]) CUDA_TRY(cudaMemcpyAsync(e->d_in.p, clouds[f], cloud_bytes[f], cudaMemcpyHostToDevice, e->stream));
+      const void* din = e->d_in.p;
+      void* dout = e->d_out.p;
+      if (int rc = encode_batch_device(e, 1, &din, &cloud_bytes[f], &dout, &cap1, 0)) return rc;
+      if (int rc = e->h_sizes.reserve(1)) return rc;
+      CUDA_TRY(cudaMemcpyAsync(e->h_sizes.p, e->d_sizes.p, sizeof(uint64_t), cudaMemcpyDeviceToHost, e->stream));
+      if (int rc = check_device_error(e->stream, e->d_err.p, e->h_err.p)) return rc;
+      const size_t s1 = static_cast<size_t>(e->h_sizes.p[0]);
+      e->s2_tmp.resize(s1 + 16);
+      if (s1) CUDA_TRY(cudaMemcpy(e->s2_tmp.data(), e->d_out.p, s1, cudaMemcpyDeviceToHost));
+      uint8_t* out = static_cast<uint8_t*>(outs[f]);
+      if (hdr) memcpy(out, e->header.data(), hdr);
+      size_t w = 0;
+      if (int rc = stage2_compress_payload(e->stage2, e->s2_tmp.data(), s1, out + hdr, out_capacities[f] - hdr, &w)) return rc;
+      if (written_host) written_host[f] = hdr + w;
+    }
+    return CLDN_OK;
+  }
   if (mem == CLDN_MEM_DEVICE) {
     if (int rc = encode_batch_device(e, n_frames, clouds, cloud_bytes, outs, out_capacities, write_header)) return rc;
     if (written_host) {
@@ -480,6 +618,7 @@ int cldn_b200_encode(cldn_encoder_t* enc, const void* cloud, size_t cloud_bytes,
 
 // =====================================================================================================================
 struct cldn_decoder {
+  std::vector<uint8_t> s2_tmp;  // stage-2 decompression scratch (host-pointer API only)
   int device = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
@@ -707,6 +846,25 @@ int cldn_b200_decode_batch(cldn_decoder_t* d, const cldn_info_t* info, size_t n_
       set_error("compressed_data contains the header. You should use DecodeHeader first");
       return CLDN_ERR_INVALID_ARGUMENT;
     }
+  }
+  if (info->compression_opt != CLDN_COMP_NONE) {
+    // stage 2 first (host libraries), then the ordinary stage-1 decode of the re-framed payload
+    if (info->compression_opt > CLDN_COMP_ZSTD) { set_error("Unsupported compression option"); return CLDN_ERR_INVALID_ARGUMENT; }
+    if (!g_stage2.load(info->compression_opt)) return CLDN_ERR_UNSUPPORTED;
+    cldn_info_t plain = *info;
+    plain.compression_opt = CLDN_COMP_NONE;
+    bool ok;
+    const size_t pts = static_cast<size_t>(info->width) * info->height;
+    size_t max_body = max_compressed_size(plain, std::min<size_t>(pts, kChunkPoints), false, &ok);
+    if (!ok) return CLDN_ERR_INVALID_ARGUMENT;
+    max_body = std::max<size_t>(max_body, pts * info->point_step) + 64;  // DecompressChunk's bound is w*h*step (cloudini.cpp:672-675)
+    for (size_t f = 0; f < n_frames; ++f) {
+      if (int rc = stage2_decompress_payload(info->compression_opt, static_cast<const uint8_t*>(payloads[f]), payload_bytes[f], d->s2_tmp, max_body)) return rc;
+      const void* p1 = d->s2_tmp.data();
+      const size_t b1 = d->s2_tmp.size();
+      if (int rc = cldn_b200_decode_batch(d, &plain, 1, &p1, &b1, &outs[f], &out_capacities[f], CLDN_MEM_HOST, 1)) return rc;
+    }
+    return CLDN_OK;
   }
   if (int rc = decoder_update_plan(d, *info)) return rc;
   const size_t out_need = static_cast<size_t>(info->width) * info->height * info->point_step;

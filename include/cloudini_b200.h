@@ -74,7 +74,8 @@ typedef struct cldn_info_t {
   uint32_t height;
   uint32_t point_step;
   uint8_t encoding_opt;    /* cldn_encoding_opt_t, default LOSSY */
-  uint8_t compression_opt; /* cldn_compression_opt_t; only NONE is executed on the GPU path (stage 2 is delegated) */
+  uint8_t compression_opt; /* cldn_compression_opt_t. Stage 2 is not the product: NONE everywhere; LZ4/ZSTD only through the
+                              host-pointer API, where each chunk is handed to the system liblz4/libzstd (dlopen) */
   uint8_t version;         /* wire version 2..5, default 5 */
   uint8_t use_threads;     /* accepted for API parity; ignored (there is no stage-2 worker thread here) */
   uint32_t n_fields;

@@ -301,3 +301,36 @@ def test_one_shot_c_abi_like_wasm(oracle):
     assert m == dec.nbytes and np.array_equal(dec, want)
     assert L.cldn_b200_EncodePointcloudData(yaml, cloud.ctypes.data, cloud.nbytes - 16, out.ctypes.data, out.nbytes) == 0  # size mismatch
     assert L.cldn_b200_DecodeCompressedData(out.ctypes.data, 5, dec.ctypes.data, dec.nbytes) == 0                           # bad header
+
+
+@pytest.mark.parametrize("comp", [cb.CompressionOption.LZ4, cb.CompressionOption.ZSTD])
+def test_stage2_interop_with_reference(ref, comp):
+    # Stage 2 is delegated to the host's liblz4 / libzstd (host-pointer API). Compressed bytes need not equal the
+    # reference's (library versions differ) but each side must decode the other's blobs to identical buffers
+    # (round-trip contract of test_field_encoders.cpp:605-631, test_header.cpp:173-241).
+    for info, cloud in (synth.cloud_c2(70_000, seed=5), synth.cloud_c3(70_000, seed=6)):
+        info.compression_opt = comp
+        n = info.width * info.point_step
+        ours = cb.PointcloudEncoder(info).encode(cloud)
+        theirs = ref.encode(info, cloud)
+        assert ours[:len(cb.EncodeHeader(info))] == theirs[:len(cb.EncodeHeader(info))]
+        want = np.full(n, 0x21, dtype=np.uint8)
+        ref.decode(theirs, want)
+        got_ref_on_ours = np.full(n, 0x21, dtype=np.uint8)
+        ref.decode(ours, got_ref_on_ours)                       # reference decodes our blob
+        assert np.array_equal(got_ref_on_ours, want)
+        dinfo, hdr = cb.DecodeHeader(theirs)
+        assert dinfo.compression_opt == comp
+        got = np.full(n, 0x21, dtype=np.uint8)
+        cb.PointcloudDecoder().decode(dinfo, theirs[hdr:], got)  # we decode the reference's blob
+        assert np.array_equal(got, want)
+        assert len(ours) < 0.9 * len(cb.PointcloudEncoder(synth.cloud_c2(1)[0]).getHeader()) + n  # actually compressed
+    # device-pointer API cannot run stage 2: loud error, no silent fallback
+    import torch
+    info, cloud = synth.cloud_c2(1000, seed=1)
+    info.compression_opt = comp
+    enc = cb.PointcloudEncoder(info)
+    t_in = torch.from_numpy(cloud.copy()).cuda()
+    t_out = torch.zeros(cb.MaxCompressedSize(info, 1000, True), dtype=torch.uint8, device="cuda")
+    with pytest.raises(RuntimeError, match="host-pointer API"):
+        enc.encode_batch_device(enc.make_device_batch([t_in.data_ptr()], [cloud.size], [t_out.data_ptr()], [t_out.numel()]), want_sizes=True)
