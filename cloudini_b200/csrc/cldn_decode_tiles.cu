@@ -175,44 +175,6 @@ __device__ __forceinline__ SegK<K> sums_lookback(const uint64_t* recs, uint32_t 
   return acc;
 }
 
-// Values of 5..10 bytes (|delta| >= 2^27, or varints the FloatN encoder never writes but the reference decodes).
-// Kept out of line: the common path only handles <= 4 bytes.
-// Returns (error code << 32) | uint32(delta): no by-reference outputs, so the caller's state stays in registers.
-__device__ __noinline__ unsigned long long decode_wide_value(const uint8_t* tile_bytes, uint32_t e, uint32_t len) {
-  unsigned long long u = 0;
-  uint32_t bad = 0;
-  if (len > 10u) return static_cast<unsigned long long>(DEV_ERR_VARINT_OVERFLOW) << 32;
-  for (uint32_t k = 0; k < len; ++k) {
-    const unsigned long long payload = tile_bytes[e - len + 1 + k] & 0x7Fu;
-    if (k == 9 && payload > 1) bad = DEV_ERR_VARINT_OVERFLOW;  // encoding_utils.hpp:127-129
-    u |= payload << (7 * k);
-  }
-  if (bad) return static_cast<unsigned long long>(bad) << 32;
-  if (u == 0) return static_cast<unsigned long long>(DEV_ERR_NAN_MARKER) << 32;
-  return static_cast<uint32_t>(static_cast<int32_t>(unzigzag(u - 1ull)));  // truncated to int32 like field_decoder.cpp:68
-}
-
-// Rebuilds the varint that ends at tile byte `e` (biased by kTLook) and is `len` bytes long. Returns the int32 delta;
-// sets nan for the single-byte 0x00 marker and bad (a DevError code) when the bytes do not form a valid value.
-__device__ __forceinline__ int32_t decode_value(const uint8_t* tile_bytes, uint32_t e, uint32_t len, bool& nan, uint32_t& bad) {
-  if (len > 4u) {
-    const unsigned long long r = decode_wide_value(tile_bytes, e, len);
-    bad = static_cast<uint32_t>(r >> 32);
-    return static_cast<int32_t>(static_cast<uint32_t>(r));
-  }
-  const uint32_t* wp = reinterpret_cast<const uint32_t*>(tile_bytes) + (e >> 2);
-  const uint32_t hi = __funnelshift_l(wp[-1], wp[0], 24u - 8u * (e & 3u));  // byte e becomes the top byte
-  uint32_t x = (hi >> (32u - 8u * len)) & 0x7F7F7F7Fu;                        // the value's bytes, first byte lowest
-  x = x - ((x & 0x7F007F00u) >> 1);                                          // 7-bit groups -> 14-bit groups
-  x = (x & 0x3FFFu) | ((x >> 2) & 0x0FFFC000u);                              // -> 28-bit uval
-  if (x == 0u) {  // uval 0: the NaN marker if it is the single byte 0x00, otherwise "unexpected NaN marker"
-    if (len == 1u) nan = true; else bad = DEV_ERR_NAN_MARKER;
-    return 0;
-  }
-  const uint32_t um = x - 1u;
-  return static_cast<int32_t>((um >> 1) ^ (0u - (um & 1u)));
-}
-
 // Per-thread value run in LOCAL slot numbering: value k of the run is local slot k % K (runs start at a multiple of K
 // values); the global field is (phase + k) % K with phase = done % K uniform over the tile, so accumulators and
 // per-field constants are rotated once instead of specialising the unrolled loops per phase.
@@ -339,62 +301,106 @@ __device__ __forceinline__ uint32_t tile_load_masks(uint8_t* tile_bytes, const u
   return tmask;
 }
 
-// CTA scan of the terminator counts + compaction of their tile byte positions into pos16. Ends with a barrier.
-__device__ __forceinline__ uint32_t tile_rank_compact(uint32_t tmask, uint16_t* pos16, uint32_t* scan) {
+// CTA scan of the terminator counts; then every run t of VT consecutive values gets the tile byte index (biased by
+// kTLook) of its first byte in start16[t]: value q starts right behind terminator q-1, which is found in the owner's
+// 16-bit mask. No per-value position list is built. Returns the number of values in the tile; ends with a barrier.
+template <int K>
+__device__ __forceinline__ uint32_t tile_rank_starts(uint32_t tmask, const uint8_t* tile_bytes, uint16_t* start16, uint32_t* scan,
+                                                     uint32_t* vt_out) {
   uint32_t tile_cnt;
-  uint32_t rank = block_exclusive_scan(__popc(tmask), scan, &tile_cnt);
-  uint32_t m = tmask;
-  const uint32_t base = threadIdx.x * kVec * 16u;
-  while (m) {
-    const int j = __ffs(m) - 1;
-    m &= m - 1;
-    pos16[rank++] = static_cast<uint16_t>(base + j);
+  const uint32_t c = __popc(tmask);
+  const uint32_t rank = block_exclusive_scan(c, scan, &tile_cnt);
+  const uint32_t VT = ((tile_cnt + kThreads - 1) / kThreads + K - 1) / K * K;  // values per thread, a multiple of K
+  *vt_out = VT;
+  const uint32_t base = kTLook + threadIdx.x * kVec * 16u;
+  if (c) {
+    if (rank == 0) {
+      // first byte of value 0: walk back from its terminator over continuation bytes (at most 10; stops at a boundary)
+      const int e = static_cast<int>(base) + __ffs(tmask) - 1;
+      int st = e;
+      while (st > 0 && e - st < 11 && (tile_bytes[st - 1] & 0x80u)) --st;
+      start16[0] = static_cast<uint16_t>(st);
+    }
+    uint32_t q = (rank / VT + 1u) * VT;  // smallest run start > rank, i.e. the first q with q - 1 >= rank
+    uint32_t m = tmask, skipped = 0;
+    while (q <= rank + c - 1u + 1u && q < tile_cnt) {  // terminator q-1 is one of mine
+      const uint32_t nth = q - 1u - rank;              // 0-based among my terminators
+      while (skipped < nth) { m &= m - 1u; ++skipped; }
+      start16[q / VT] = static_cast<uint16_t>(base + __ffs(m));  // byte after that terminator
+      q += VT;
+    }
   }
   __syncthreads();
   return tile_cnt;
 }
 
-// Decodes this thread's run of VT consecutive values (starting at value v0 of the tile) into registers.
+// Values of 5..10 bytes starting at tile byte `ptr`: returns (bad << 40) | (len << 32) | uint32(delta).
+__device__ __noinline__ unsigned long long decode_wide_at(const uint8_t* tile_bytes, uint32_t ptr) {
+  unsigned long long u = 0;
+  uint32_t len = 0, bad = 0;
+  while (true) {
+    if (len >= 10u) { bad = DEV_ERR_VARINT_OVERFLOW; break; }
+    const uint32_t byte = tile_bytes[ptr + len];
+    const unsigned long long payload = byte & 0x7Fu;
+    if (len == 9u && payload > 1) bad = DEV_ERR_VARINT_OVERFLOW;  // encoding_utils.hpp:127-129
+    u |= payload << (7 * len);
+    ++len;
+    if (!(byte & 0x80u)) break;
+  }
+  if (!bad && u == 0) bad = DEV_ERR_NAN_MARKER;
+  const uint32_t delta = bad ? 0u : static_cast<uint32_t>(static_cast<int32_t>(unzigzag(u - 1ull)));
+  return (static_cast<unsigned long long>(bad) << 40) | (static_cast<unsigned long long>(len) << 32) | delta;
+}
+
+// Streams this thread's run of n_run consecutive values (starting at tile byte `ptr`) into registers: every value is
+// cut out of a 4-byte window read at the current byte position; the window's terminator flags give its length.
 template <int VTMAX>
-__device__ __forceinline__ void tile_decode_run(const uint8_t* tile_bytes, const uint16_t* pos16, uint32_t tile_cnt, uint32_t VT,
-                                                uint32_t v0, int32_t (&d)[VTMAX], unsigned long long& nanm, uint32_t& badcode,
-                                                uint32_t& badk) {
+__device__ __forceinline__ void tile_decode_run(const uint8_t* tile_bytes, uint32_t ptr, uint32_t n_run, int32_t (&d)[VTMAX],
+                                                unsigned long long& nanm, uint32_t& badcode, uint32_t& badk) {
   nanm = 0;
   badcode = 0;
   badk = 0xFFFFFFFFu;
-  uint32_t prev_end;  // tile byte index (biased) of the byte before my first value
-  if (v0 == 0) {
-    // first byte of value 0: walk back from its terminator over continuation bytes (at most 10; stops at a boundary)
-    int s = kTLook;
-    if (tile_cnt > 0) {
-      const int e = kTLook + pos16[0];
-      s = e;
-      while (s > 0 && e - s < 11 && (tile_bytes[s - 1] & 0x80u)) --s;
-    }
-    prev_end = static_cast<uint32_t>(s) - 1u;
-  } else {
-    prev_end = (v0 - 1 < tile_cnt) ? kTLook + pos16[v0 - 1] : 0u;
-  }
-  // Values past tile_cnt (only in the tile's last threads) are decoded from a clamped position and never used:
-  // callers only consume the first min(VT, take - v0) values of a run.
-  const uint32_t last = tile_cnt ? tile_cnt - 1u : 0u;
 #pragma unroll
-  for (int g = 0; g < VTMAX; g += 4) {
-    if (g >= static_cast<int>(VT)) break;
-#pragma unroll
-    for (int kk = 0; kk < 4; ++kk) {
-      const int k = g + kk;
-      if (k < VTMAX) {
-        const uint32_t e = kTLook + pos16[min(v0 + k, last)];
-        bool nan = false;
-        uint32_t bad = 0;
-        d[k] = decode_value(tile_bytes, e, e - prev_end, nan, bad);
-        if (nan) nanm |= 1ull << k;
-        if (bad && badk == 0xFFFFFFFFu) { badcode = bad; badk = k; }
-        prev_end = e;
+  for (int k = 0; k < VTMAX; ++k) {
+    if (k >= static_cast<int>(n_run)) break;
+    const uint32_t* wp = reinterpret_cast<const uint32_t*>(tile_bytes) + (ptr >> 2);
+    const uint32_t lo = __funnelshift_r(wp[0], wp[1], 8u * (ptr & 3u));  // the 4 bytes at ptr
+    const uint32_t m = ~lo & 0x80808080u;                                 // terminators among them
+    int32_t delta = 0;
+    uint32_t len;
+    if (m) {
+      const uint32_t tz = __ffs(m);                                       // 8, 16, 24 or 32
+      len = tz >> 3;
+      uint32_t x = lo & (0xFFFFFFFFu >> (32u - tz)) & 0x7F7F7F7Fu;        // the value's bytes without their flags
+      x = x - ((x & 0x7F007F00u) >> 1);                                   // 7-bit groups -> 14-bit groups
+      x = (x & 0x3FFFu) | ((x >> 2) & 0x0FFFC000u);                       // -> 28-bit uval
+      if (x == 0u) {  // uval 0: the NaN marker if it is the single byte 0x00, otherwise "unexpected NaN marker"
+        if (len == 1u) nanm |= 1ull << k;
+        else if (badk == 0xFFFFFFFFu) { badcode = DEV_ERR_NAN_MARKER; badk = k; }
+      } else {
+        const uint32_t um = x - 1u;
+        delta = static_cast<int32_t>((um >> 1) ^ (0u - (um & 1u)));
       }
+    } else {
+      const unsigned long long r = decode_wide_at(tile_bytes, ptr);
+      const uint32_t bad = static_cast<uint32_t>(r >> 40);
+      len = static_cast<uint32_t>(r >> 32) & 0xFFu;
+      delta = static_cast<int32_t>(static_cast<uint32_t>(r));
+      if (bad && badk == 0xFFFFFFFFu) { badcode = bad; badk = k; }
     }
+    d[k] = delta;
+    ptr += len;
   }
+}
+
+// Tile byte index (biased) one past value `idx` of the run that starts at `ptr` (single thread; used for stream_end).
+__device__ __forceinline__ uint32_t run_end_after(const uint8_t* tile_bytes, uint32_t ptr, uint32_t idx) {
+  for (uint32_t k = 0; k <= idx; ++k) {
+    uint32_t n = 0;
+    while (n < 10u && (tile_bytes[ptr + n] & 0x80u)) ++n;
+    ptr += n + 1u;
+  }
+  return ptr;
 }
 
 // CTA-wide exclusive segmented scan of one SegK per thread (two barriers); *total = combination of all threads.
@@ -449,7 +455,7 @@ __global__ void __launch_bounds__(kThreads, kVec == 1 ? 4 : 3) decode_tiles_kern
   extern __shared__ __align__(16) uint8_t dyn_smem[];
   __shared__ TileShared sh;
   uint8_t* tile_bytes = dyn_smem;                                               // kTLook + kTB + 16
-  uint16_t* pos16 = reinterpret_cast<uint16_t*>(dyn_smem + kTLook + kTB + 16);  // kTB entries: tile byte index of every terminator
+  uint16_t* start16 = reinterpret_cast<uint16_t*>(dyn_smem + kTLook + kTB + 16);  // kThreads entries: first byte of every run
   constexpr int VTMAX = ((kTB / kThreads) + K - 1) / K * K;                     // values per thread if every value is one byte
 
   const uint32_t gt = blockIdx.x;
@@ -475,7 +481,8 @@ __global__ void __launch_bounds__(kThreads, kVec == 1 ? 4 : 3) decode_tiles_kern
   uint64_t* recs = reinterpret_cast<uint64_t*>(L.tsums);
 
   const uint32_t tmask = tile_load_masks(tile_bytes, aligned, body, size, t, tile_b0);
-  const uint32_t tile_cnt = tile_rank_compact(tmask, pos16, sh.scan);
+  uint32_t VT;
+  const uint32_t tile_cnt = tile_rank_starts<K>(tmask, tile_bytes, start16, sh.scan, &VT);
   TRACE(1);
   // ---- look-back 1 (warp 0): values before this tile; overlapped with the value decoding of the other warps ----
   if (warp == 0) {
@@ -484,12 +491,12 @@ __global__ void __launch_bounds__(kThreads, kVec == 1 ? 4 : 3) decode_tiles_kern
   }
   TRACE(2);
   // ---- every thread decodes a run of VT consecutive values (VT a multiple of K) into registers ----
-  const uint32_t VT = ((tile_cnt + kThreads - 1) / kThreads + K - 1) / K * K;  // <= VTMAX
   const uint32_t v0 = threadIdx.x * VT;
+  const uint32_t n_run = v0 < tile_cnt ? min(VT, tile_cnt - v0) : 0u;
   int32_t d[VTMAX];
   unsigned long long nanm;
   uint32_t badcode, badk;
-  tile_decode_run<VTMAX>(tile_bytes, pos16, tile_cnt, VT, v0, d, nanm, badcode, badk);
+  tile_decode_run<VTMAX>(tile_bytes, n_run ? start16[threadIdx.x] : 0u, n_run, d, nanm, badcode, badk);
   TRACE(3);
   __syncthreads();
   TRACE(4);
@@ -499,8 +506,8 @@ __global__ void __launch_bounds__(kThreads, kVec == 1 ? 4 : 3) decode_tiles_kern
   const uint32_t take = min(tile_cnt, V - done);
   // "ran out of bytes": the chunk's last tile still misses values (v4_codec.cpp:102-104)
   if (t + 1 == L.chunk_tiles[gc] && done + tile_cnt < V && threadIdx.x == 0) report_error(L.err, DEV_ERR_TRUNCATED);
-  if (take > 0 && done + take == V && threadIdx.x == 0) {
-    L.stream_end[gc] = static_cast<uint32_t>(tile_b0 + pos16[take - 1] + 1);  // first byte after the regular stream
+  if (take > 0 && done + take == V && threadIdx.x == (take - 1) / VT) {  // first byte after the regular stream
+    L.stream_end[gc] = static_cast<uint32_t>(tile_b0 + run_end_after(tile_bytes, start16[threadIdx.x], (take - 1) - v0) - kTLook);
   }
   const uint32_t n_mine = v0 < take ? min(VT, take - v0) : 0u;  // my values that belong to the regular stream
   if (badk < n_mine) report_error(L.err, badcode);            // bytes past the stream may be anything: only real values count
@@ -549,7 +556,7 @@ __global__ void __launch_bounds__(kThreads, kVec == 1 ? 4 : 3) decode_chunks_seq
   __shared__ TileShared sh;
   __shared__ uint32_t s_chunk;
   uint8_t* tile_bytes = dyn_smem;
-  uint16_t* pos16 = reinterpret_cast<uint16_t*>(dyn_smem + kTLook + kTB + 16);
+  uint16_t* start16 = reinterpret_cast<uint16_t*>(dyn_smem + kTLook + kTB + 16);
   constexpr int VTMAX = ((kTB / kThreads) + K - 1) / K * K;
   const float mul[4] = {m0, m1, m2, m3};
   const uint32_t off[4] = {o0, o1, o2, o3};
@@ -587,17 +594,20 @@ __global__ void __launch_bounds__(kThreads, kVec == 1 ? 4 : 3) decode_chunks_seq
       have_pre = (t + 1 < n_tiles) && tile_vector_interior(size, tile_b0 + kTB, 0);
       if (have_pre) pre = tile_vector_fetch(aligned, t + 1, 0);
       TRACE(1);
-      const uint32_t tile_cnt = tile_rank_compact(tmask, pos16, sh.scan);
+      uint32_t VT;
+      const uint32_t tile_cnt = tile_rank_starts<K>(tmask, tile_bytes, start16, sh.scan, &VT);
       TRACE(2);
-      const uint32_t VT = ((tile_cnt + kThreads - 1) / kThreads + K - 1) / K * K;
       const uint32_t v0 = threadIdx.x * VT;
+      const uint32_t n_run = v0 < tile_cnt ? min(VT, tile_cnt - v0) : 0u;
       int32_t d[VTMAX];
       unsigned long long nanm;
       uint32_t badcode, badk;
-      tile_decode_run<VTMAX>(tile_bytes, pos16, tile_cnt, VT, v0, d, nanm, badcode, badk);
+      tile_decode_run<VTMAX>(tile_bytes, n_run ? start16[threadIdx.x] : 0u, n_run, d, nanm, badcode, badk);
       TRACE(3);
       const uint32_t take = min(tile_cnt, V - done);
-      if (take > 0 && done + take == V && threadIdx.x == 0) L.stream_end[gc] = static_cast<uint32_t>(tile_b0 + pos16[take - 1] + 1);
+      if (take > 0 && done + take == V && threadIdx.x == (take - 1) / VT) {
+        L.stream_end[gc] = static_cast<uint32_t>(tile_b0 + run_end_after(tile_bytes, start16[threadIdx.x], (take - 1) - v0) - kTLook);
+      }
       const uint32_t n_mine = v0 < take ? min(VT, take - v0) : 0u;
       if (badk < n_mine) report_error(L.err, badcode);
       const uint32_t phase = done % K;
@@ -614,7 +624,7 @@ __global__ void __launch_bounds__(kThreads, kVec == 1 ? 4 : 3) decode_chunks_seq
       for (int j = 0; j < K; ++j) carry[j] = ((total.rst >> j) & 1u) ? total.sum[j] : wadd32(carry[j], total.sum[j]);
       TRACE(5);
       done += take;
-      __syncthreads();  // tile_bytes / pos16 / sh are reused by the next tile
+      __syncthreads();  // tile_bytes / start16 / sh are reused by the next tile
       TRACE(6);
     }
     if (done < V && threadIdx.x == 0) report_error(L.err, DEV_ERR_TRUNCATED);  // v4_codec.cpp:102-104
@@ -622,7 +632,7 @@ __global__ void __launch_bounds__(kThreads, kVec == 1 ? 4 : 3) decode_chunks_seq
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-size_t decode_tiles_smem_bytes() { return kTLook + kTB + 16 + 2 * static_cast<size_t>(kTB) + 64; }
+size_t decode_tiles_smem_bytes() { return kTLook + kTB + 16 + 2 * static_cast<size_t>(kThreads) + 64; }
 uint32_t decode_tile_bytes() { return kTB; }
 
 template <int K>
@@ -657,7 +667,7 @@ int launch_decode_tiles(const Plan& plan, const DecLaunch& L, cudaStream_t strea
   }
   // Large batches: one persistent CTA per chunk (no look-back latency); small ones: one CTA per tile (parallel inside a chunk).
   const char* mode = getenv("CLDN_B200_DECODE_MODE");  // "seq" | "tile" (development override)
-  bool sequential = L.n_chunks_total >= static_cast<uint32_t>(4 * sm_count);
+  bool sequential = L.n_chunks_total >= static_cast<uint32_t>(sm_count + sm_count / 8);  // measured crossover: ~1.1 chunks per SM
   if (mode && mode[0] == 's') sequential = true;
   if (mode && mode[0] == 't') sequential = false;
   count_tiles_kernel<<<(L.n_chunks_total + 127) / 128, 128, 0, stream>>>(L);
