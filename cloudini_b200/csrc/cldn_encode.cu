@@ -266,7 +266,9 @@ __global__ void __launch_bounds__(kThreads, MINB) encode_floatn_kernel(const Enc
 
   // ---- phase 1: quantise, delta, varint bytes (as words), per-point sizes ----
   uint32_t r[I][N];   // LEB128 bytes of each value (<= 4 bytes on the fast path), 0 for the NaN marker
-  uint32_t pre[I];    // byte 0: len(v0), byte 1: len(v0..v1), byte 2: len(v0..v2), byte 3: total length of the point
+  // one word of bookkeeping per point: [2:0] len(v0)  [6:3] len(v0..v1)  [10:7] len(v0..v2)  [15:11] total length
+  // [31:16] byte offset of the point inside the warp's run (filled in after the scan)
+  uint32_t meta[I];
   uint32_t bmax = 0;  // highest set bit of any zz+1; >= 28 means a 5-byte varint -> whole tile takes the byte-wise slow path
 #pragma unroll
   for (int i = 0; i < I; ++i) {
@@ -298,19 +300,18 @@ __global__ void __launch_bounds__(kThreads, MINB) encode_floatn_kernel(const Enc
       x = x + (x & 0xFF800000u);
       r[i][k] = x | (0x00808080u >> (24u - 8u * min(lenm1, 3u)));  // continuation flags below the top byte
       acc += lenm1 + 1u;
-      if (k < N - 1) packed |= acc << (8 * k);
+      if (k < N - 1) packed |= acc << (k == 0 ? 0 : k == 1 ? 3 : 7);
     }
     if (!valid) acc = 0;
-    pre[i] = (N == 4) ? (packed | (acc << 24)) : (packed | (acc << 16) | (acc << 24));
+    meta[i] = (N == 4) ? (packed | (acc << 11)) : (packed | (acc << 7) | (acc << 11));
   }
   // ---- warp-level exclusive offsets: 10-bit fields, three iterations per shuffle scan (32 * 20 = 640 < 1024) ----
-  uint32_t off[I];    // byte offset of the point inside the warp's run
   uint32_t run = 0;   // bytes of earlier iterations of this warp
 #pragma unroll
   for (int g = 0; g < I; g += 3) {
-    uint32_t pk = pre[g] >> 24;
-    if (g + 1 < I) pk |= (pre[g + 1] >> 24) << 10;
-    if (g + 2 < I) pk |= (pre[g + 2] >> 24) << 20;
+    uint32_t pk = meta[g] >> 11;
+    if (g + 1 < I) pk |= (meta[g + 1] >> 11) << 10;
+    if (g + 2 < I) pk |= (meta[g + 2] >> 11) << 20;
     uint32_t inc = pk;
 #pragma unroll
     for (int dlt = 1; dlt < 32; dlt <<= 1) {
@@ -319,10 +320,10 @@ __global__ void __launch_bounds__(kThreads, MINB) encode_floatn_kernel(const Enc
     }
     const uint32_t tot = __shfl_sync(0xffffffffu, inc, 31);
     const uint32_t exc = inc - pk;
-    off[g] = run + (exc & 1023u);
+    meta[g] |= (run + (exc & 1023u)) << 16;
     run += tot & 1023u;
-    if (g + 1 < I) { off[g + 1] = run + ((exc >> 10) & 1023u); run += (tot >> 10) & 1023u; }
-    if (g + 2 < I) { off[g + 2] = run + ((exc >> 20) & 1023u); run += (tot >> 20) & 1023u; }
+    if (g + 1 < I) { meta[g + 1] |= (run + ((exc >> 10) & 1023u)) << 16; run += (tot >> 10) & 1023u; }
+    if (g + 2 < I) { meta[g + 2] |= (run + ((exc >> 20) & 1023u)) << 16; run += (tot >> 20) & 1023u; }
   }
   // the word-packing fast path assumes a full tile; the (single) partial tile of a frame takes the byte-wise path too
   const uint32_t big = (bmax >= 28u || tile_p0 + T > F.n_points) ? 1u : 0u;
@@ -347,10 +348,10 @@ __global__ void __launch_bounds__(kThreads, MINB) encode_floatn_kernel(const Enc
     uint32_t tail_carry = 0;  // partial last word of the previous iteration's lane 31
 #pragma unroll
     for (int i = 0; i < I; ++i) {
-      const uint32_t l0 = pre[i] & 0xFFu;
-      const uint32_t c2 = (pre[i] >> 8) & 0xFFu;          // len(v0) + len(v1): 2..8
-      const uint32_t l2 = ((pre[i] >> 16) & 0xFFu) - c2;
-      const uint32_t len = pre[i] >> 24;                  // 3..16
+      const uint32_t l0 = meta[i] & 7u;
+      const uint32_t c2 = (meta[i] >> 3) & 15u;           // len(v0) + len(v1): 2..8
+      const uint32_t l2 = ((meta[i] >> 7) & 15u) - c2;
+      const uint32_t len = (meta[i] >> 11) & 31u;         // 3..16
       // A = value0 | value1 << 8*l0  (<= 8 bytes)
       const uint32_t sa = 8u * l0;
       const uint32_t a_lo = r[i][0] | (sa < 32u ? (r[i][1] << sa) : 0u);
@@ -373,7 +374,7 @@ __global__ void __launch_bounds__(kThreads, MINB) encode_floatn_kernel(const Enc
       uint32_t w2 = ws ? x1 : x2;
       uint32_t w3 = ws ? x2 : 0u;
       // byte position inside the tile; shift the record to its position inside the first word
-      const uint32_t pos = wbase + off[i];
+      const uint32_t pos = wbase + (meta[i] >> 16);
       const uint32_t s = pos & 3u, sh = 8u * s;
       const uint32_t S0 = w0 << sh;
       const uint32_t S1 = __funnelshift_l(w0, w1, sh);
@@ -422,7 +423,7 @@ __global__ void __launch_bounds__(kThreads, MINB) encode_floatn_kernel(const Enc
       if (p < F.n_points) {
         const uint8_t* pt = F.in + static_cast<size_t>(p) * step;
         const uint8_t* prevp = (p % kChunkPoints) ? pt - step : nullptr;
-        ByteSink bs{stage + wbase + off[i]};
+        ByteSink bs{stage + wbase + (meta[i] >> 16)};
 #pragma unroll
         for (int k = 0; k < N; ++k) {
           const float x = __uint_as_float(load_u32(pt + P.offset[k]));
