@@ -288,6 +288,7 @@ struct cldn_encoder {
   DevBuf<uint32_t> d_chunk_frame;
   PinRing<uint32_t> h_chunk_frame;
   DevBuf<uint64_t> d_hash;
+  DevBuf<uint8_t> d_gorilla;  // Gorilla pre-pass records: [frame][op][point][12]
   size_t last_frames = 0;
 };
 
@@ -301,7 +302,7 @@ int cldn_b200_encoder_create(const cldn_info_t* info, int device, void* stream, 
   Plan plan;
   if (int rc = build_encode_plan(*info, &plan)) return rc;
   if (!plan.supported) {
-    set_error("EncodingInfo needs a lossless float encoder (XOR / Gorilla) that this build does not accelerate");
+    set_error("EncodingInfo contains a field encoder this build cannot run");
     return CLDN_ERR_UNSUPPORTED;
   }
   if (info->compression_opt > CLDN_COMP_ZSTD) { set_error("Unsupported compression option"); return CLDN_ERR_INVALID_ARGUMENT; }
@@ -346,7 +347,7 @@ void cldn_b200_encoder_destroy(cldn_encoder_t* e) {
   e->d_plan.release(); e->d_header.release(); e->d_status.release(); e->d_frames.release(); e->h_frames.release();
   e->d_sizes.release(); e->h_sizes.release(); e->d_err.release(); e->h_err.release(); e->d_in.release(); e->d_out.release();
   e->d_modes.release(); e->d_sec_scratch.release(); e->d_sec_sizes.release(); e->d_sec_excl.release();
-  e->d_chunk_frame.release(); e->h_chunk_frame.release(); e->d_hash.release(); e->pipe.release();
+  e->d_chunk_frame.release(); e->h_chunk_frame.release(); e->d_hash.release(); e->d_gorilla.release(); e->pipe.release();
   if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
   delete e;
 }
@@ -420,6 +421,19 @@ static int encode_batch_device(cldn_encoder* e, size_t n_frames, const void* con
     if (reinterpret_cast<uintptr_t>(clouds[f]) & 15u) aligned16 = false;
   }
   if (tiles > 0x7FFFFFFFull) { set_error("batch too large"); return CLDN_ERR_UNSUPPORTED; }
+  for (size_t f = 0; f < n_frames; ++f) hf[f].side = nullptr;
+  if (e->plan.n_gorilla > 0) {
+    // FieldEncoderFloat_Gorilla keeps a leading/trailing-zero window across the points of a chunk: a pre-pass walks
+    // every chunk in order and leaves one 12-byte record per (op, point) for the (parallel) regular kernel to copy
+    size_t total_points = 0;
+    for (size_t f = 0; f < n_frames; ++f) total_points += hf[f].n_points;
+    if (int rc = e->d_gorilla.reserve(total_points * 12 * e->plan.n_gorilla + 16)) return rc;
+    size_t at = 0;
+    for (size_t f = 0; f < n_frames; ++f) {
+      hf[f].side = e->d_gorilla.p + at;
+      at += static_cast<size_t>(hf[f].n_points) * 12 * e->plan.n_gorilla;
+    }
+  }
   if (int rc = e->d_status.reserve(static_cast<size_t>(tiles) + 1, true)) return rc;
   e->epoch = (e->epoch + 1) & 0x3FFFFFu;
   if (e->epoch == 0) {  // epoch wrapped: stale words could alias
@@ -493,11 +507,13 @@ static int encode_batch_device(cldn_encoder* e, size_t n_frames, const void* con
     S.err = e->d_err.p;
     S.header_bytes = static_cast<uint32_t>(hdr);
     if (launch_encode_sections(e->plan, S, e->stream) < 0) { set_error("section kernel launch failed"); return CLDN_ERR_CUDA; }
+    if (launch_gorilla_prepass(e->plan, L, e->stream) < 0) { set_error("gorilla pre-pass launch failed"); return CLDN_ERR_CUDA; }
     if (launch_encode_regular(e->plan, L, e->stream) < 0) { set_error("encode kernel launch failed"); return CLDN_ERR_CUDA; }
     if (launch_place_sections(e->plan, S, e->d_status.p, e->epoch, T, e->stream) < 0) { set_error("section placement launch failed"); return CLDN_ERR_CUDA; }
   } else {
     CUDA_TRY(cudaMemcpyAsync(e->d_frames.p, hf, n_frames * sizeof(EncFrame), cudaMemcpyHostToDevice, e->stream));
     if (int rc = e->h_frames.commit(hf_slot, e->stream)) return rc;
+    if (launch_gorilla_prepass(e->plan, L, e->stream) < 0) { set_error("gorilla pre-pass launch failed"); return CLDN_ERR_CUDA; }
     if (launch_encode_regular(e->plan, L, e->stream) < 0) { set_error("encode kernel launch failed"); return CLDN_ERR_CUDA; }
   }
   CUDA_TRY(cudaGetLastError());
@@ -659,7 +675,7 @@ static int decoder_update_plan(cldn_decoder* d, const cldn_info_t& info) {
   Plan plan;
   if (int rc = build_decode_plan(info, &plan)) return rc;
   if (!plan.supported) {
-    set_error("EncodingInfo needs a lossless float decoder (XOR / Gorilla) that this build does not accelerate");
+    set_error("EncodingInfo contains a field decoder this build cannot run");
     return CLDN_ERR_UNSUPPORTED;
   }
   if (info.compression_opt != CLDN_COMP_NONE) {
@@ -667,10 +683,6 @@ static int decoder_update_plan(cldn_decoder* d, const cldn_info_t& info) {
     return CLDN_ERR_UNSUPPORTED;
   }
   if (info.version < 3) { set_error("wire version %d (single unframed chunk) is not supported", info.version); return CLDN_ERR_UNSUPPORTED; }
-  if (plan.n_sections > 0 && !(plan.all_varint || plan.n_ops == 0)) {
-    set_error("V5 clouds whose regular stream mixes raw and varint fields are not accelerated in this build");
-    return CLDN_ERR_UNSUPPORTED;
-  }
   if (int rc = d->d_plan.reserve(1)) return rc;
   CUDA_TRY(cudaMemcpyAsync(d->d_plan.p, &plan, sizeof(Plan), cudaMemcpyHostToDevice, d->stream));
   CUDA_TRY(cudaStreamSynchronize(d->stream));  // `plan` is a stack object
@@ -731,7 +743,12 @@ static int decode_batch_device(cldn_decoder* d, const cldn_info_t& info, size_t 
   L.err = d->d_err.p;
   L.chunk_frame = nullptr; L.tile_chunk = nullptr;
   L.chunk_tiles = nullptr; L.chunk_tile_begin = nullptr; L.stream_end = nullptr; L.tstatus = nullptr; L.tsums = nullptr;
-  L.tile_capacity = 0; L.tile_grid = 0; L.epoch = 0; L.trace = nullptr; L.chunk_counter = nullptr;
+  L.tile_capacity = 0; L.tile_grid = 0; L.epoch = 0; L.trace = nullptr; L.chunk_counter = nullptr; L.sections_only = 0;
+  if (d->plan.n_sections > 0 && chunks > 0 && !(d->plan.all_varint || d->plan.n_ops == 0)) {
+    // V5 with raw / XOR / Gorilla fields in the regular stream: the per-chunk parser records where the sections start
+    if (int rc = d->d_stream_end.reserve(static_cast<size_t>(chunks) + 1)) return rc;
+    L.stream_end = d->d_stream_end.p;
+  }
   const char* force_chunk = getenv("CLDN_B200_FORCE_CHUNK_DECODE");
   if (d->plan.floatn_only && chunks > 0 && !(force_chunk && force_chunk[0] == '1')) {
     // tile-parallel path: host upper bound on the tile count (every chunk adds at most 2 tiles of rounding/misalignment)

@@ -659,8 +659,8 @@ __global__ void __launch_bounds__(kThreads) decode_chunks_kernel(const DecLaunch
   uint8_t* out = F.out + static_cast<size_t>(c) * kChunkPoints * plan.point_step;
 
   uint32_t pos = 0;
-  if (L.tile_grid > 0) {
-    // the regular stream was decoded by decode_tiles_kernel; sections start where it ended
+  if (L.sections_only) {
+    // the regular stream was decoded by another kernel; sections start where it ended
     pos = L.stream_end[gc];
     if (pos > body_bytes) return;  // regular stream failed (error already reported)
   } else if (plan.values_per_point > 0) {
@@ -733,12 +733,15 @@ __global__ void decode_sequential_kernel(const DecLaunch L) {
   const uint8_t* p = F.payload + L.chunk_offsets[gc];
   uint32_t avail = L.chunk_sizes[gc];
   uint8_t* out = F.out + static_cast<size_t>(c) * kChunkPoints * plan.point_step;
-  long long prev[kMaxOps * 4];
-  for (int i = 0; i < kMaxOps * 4; ++i) prev[i] = 0;
+  long long prev[kMaxOps];      // per op: previous quantised value / previous raw bits (FloatN uses prev4)
+  int32_t prev4[4] = {0, 0, 0, 0};
+  uint8_t g_lead[kMaxOps], g_trail[kMaxOps], g_first[kMaxOps];
+  for (int i = 0; i < kMaxOps; ++i) { prev[i] = 0; g_lead[i] = 255; g_trail[i] = 0; g_first[i] = 1; }
+  const uint8_t* const body = p;
+  if (L.stream_end) L.stream_end[gc] = 0xFFFFFFFFu;  // stays so if the stream turns out to be malformed
   for (uint32_t pt = 0; pt < n_points; ++pt) {
-    if (avail < plan.min_point_bytes) { report_error(L.err, DEV_ERR_TRUNCATED); return; }
+    if (!plan.uses_v5 && avail < plan.min_point_bytes) { report_error(L.err, DEV_ERR_TRUNCATED); return; }  // v4_codec.cpp:102-104
     uint8_t* point = out + static_cast<size_t>(pt) * plan.point_step;
-    int slot = 0;
     for (uint32_t k = 0; k < plan.n_ops; ++k) {
       const RegOp& op = plan.ops[k];
       if (op.kind == OP_COPY) {
@@ -747,16 +750,35 @@ __global__ void decode_sequential_kernel(const DecLaunch L) {
           for (int b = 0; b < op.size; ++b) point[op.offset[0] + b] = p[b];
         }
         p += op.size; avail -= op.size;
-        ++slot;
         continue;
       }
-      for (int l = 0; l < op.lanes; ++l, ++slot) {
+      if (op.kind == OP_XOR32 || op.kind == OP_XOR64) {  // field_decoder.hpp:356-370
+        if (avail < op.size) { report_error(L.err, DEV_ERR_TRUNCATED); return; }
+        unsigned long long res = 0;
+        for (int b = 0; b < op.size; ++b) res |= static_cast<unsigned long long>(p[b]) << (8 * b);
+        p += op.size; avail -= op.size;
+        prev[k] = static_cast<long long>(static_cast<unsigned long long>(prev[k]) ^ res);
+        if (op.offset[0] != CLDN_SKIP_STORE_OFFSET) store_low_bytes(point + op.offset[0], static_cast<uint64_t>(prev[k]), op.size);
+        continue;
+      }
+      if (op.kind == OP_GORILLA64) {  // field_decoder.hpp:257-300
+        GorillaState st;
+        st.prev_bits = static_cast<uint64_t>(prev[k]); st.leading = g_lead[k]; st.trailing = g_trail[k]; st.first = g_first[k] != 0;
+        uint64_t v;
+        const uint32_t c = gorilla_decode(st, p, avail, &v);
+        if (!c) { report_error(L.err, DEV_ERR_TRUNCATED); return; }
+        p += c; avail -= c;
+        prev[k] = static_cast<long long>(st.prev_bits); g_lead[k] = static_cast<uint8_t>(st.leading); g_trail[k] = static_cast<uint8_t>(st.trailing); g_first[k] = 0;
+        if (op.offset[0] != CLDN_SKIP_STORE_OFFSET) store_u64(point + op.offset[0], v);
+        continue;
+      }
+      for (int l = 0; l < op.lanes; ++l) {
         if (avail == 0) { report_error(L.err, DEV_ERR_TRUNCATED); return; }
         DecSlot s;
         s.offset = op.offset[l]; s.size = op.size; s.mul_f = op.dec_mul_f[l]; s.mul_d = op.dec_mul_d;
         s.kind = op.kind == OP_FLOATN ? SLOT_FLOATN : op.kind == OP_F32_LOSSY ? SLOT_F32 : op.kind == OP_F64_LOSSY ? SLOT_F64 : SLOT_INT;
         if (p[0] == 0 && s.kind != SLOT_INT) {
-          prev[slot] = 0;
+          if (op.kind == OP_FLOATN) prev4[l] = 0; else prev[k] = 0;
           store_slot_value<long long>(point, s, 0, true);
           ++p; --avail;
           continue;
@@ -765,13 +787,14 @@ __global__ void decode_sequential_kernel(const DecLaunch L) {
         const uint32_t n = read_varint(p, avail, &diff, L.err);
         if (!n) return;
         p += n; avail -= n;
-        if (s.kind == SLOT_FLOATN) prev[slot] = static_cast<int32_t>(static_cast<int32_t>(diff) + static_cast<int32_t>(prev[slot]));
-        else prev[slot] = wadd(prev[slot], diff);
-        store_slot_value<long long>(point, s, prev[slot], false);
+        long long value;
+        if (op.kind == OP_FLOATN) { prev4[l] = wadd(static_cast<int32_t>(diff), prev4[l]); value = prev4[l]; }
+        else { prev[k] = wadd(prev[k], diff); value = prev[k]; }
+        store_slot_value<long long>(point, s, value, false);
       }
     }
   }
-  if (plan.n_sections) report_error(L.err, DEV_ERR_BAD_MODE);  // mixed raw+varint V5 plans are routed elsewhere
+  if (L.stream_end) L.stream_end[gc] = static_cast<uint32_t>(p - body);  // V5: the sections start here
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -794,7 +817,9 @@ int launch_decode(const Plan& plan, const DecLaunch& L, cudaStream_t stream) {
       const size_t smem = dec_smem_bytes(false);
       auto k = decode_chunks_kernel<0>;
       if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess) return -1;
-      k<<<L.n_chunks_total, kThreads, smem, stream>>>(L);
+      DecLaunch S = L;
+      S.sections_only = 1;
+      k<<<L.n_chunks_total, kThreads, smem, stream>>>(S);
       ++launches;
     }
   } else if (L.n_chunks_total > 0) {
@@ -816,13 +841,26 @@ int launch_decode(const Plan& plan, const DecLaunch& L, cudaStream_t stream) {
         if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess) return -1;
         k<<<L.n_chunks_total, kThreads, smem, stream>>>(L);
       }
+      ++launches;
     } else if (plan.all_fixed && plan.n_sections == 0) {
       dim3 grid(kChunkPoints / kThreads / 4, L.n_chunks_total);
       decode_fixed_kernel<<<grid, kThreads, 0, stream>>>(L);
+      ++launches;
     } else {
+      // raw / XOR / Gorilla fields mixed into the stream: one thread per chunk parses it like the reference does;
+      // V5 sections (if any) are then decoded by the per-chunk section reader from where the stream ended
       decode_sequential_kernel<<<(L.n_chunks_total + 31) / 32, 32, 0, stream>>>(L);
+      ++launches;
+      if (plan.n_sections > 0) {
+        DecLaunch S = L;
+        S.sections_only = 1;
+        const size_t smem = dec_smem_bytes(false);
+        auto k = decode_chunks_kernel<0>;
+        if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess) return -1;
+        k<<<L.n_chunks_total, kThreads, smem, stream>>>(S);
+        ++launches;
+      }
     }
-    ++launches;
   }
   count_launch(launches);
   return launches;

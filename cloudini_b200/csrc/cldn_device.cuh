@@ -159,6 +159,7 @@ struct CountSink {
   __device__ __forceinline__ void put_varint(uint64_t u) { n += varint_len(u); }
   __device__ __forceinline__ void put_byte(uint8_t) { n += 1; }
   __device__ __forceinline__ void put_raw(const uint8_t*, int size) { n += size; }
+  __device__ __forceinline__ void put_le(uint64_t, int size) { n += size; }
 };
 struct ByteSink {
   uint8_t* p;
@@ -173,7 +174,119 @@ struct ByteSink {
   __device__ __forceinline__ void put_raw(const uint8_t* src, int size) {
     for (int i = 0; i < size; ++i) *p++ = src[i];
   }
+  __device__ __forceinline__ void put_le(uint64_t v, int size) {  // low `size` bytes, little endian
+    for (int i = 0; i < size; ++i) *p++ = static_cast<uint8_t>(v >> (8 * i));
+  }
 };
+
+// ---- Gorilla / Chimp-style bit packing of one FLOAT64 (field_encoder.hpp:157-312) -----------------------------------
+// Bits are appended LSB-first and every value is flushed to a byte boundary. State = previous bits + the window
+// (leading, trailing) of the last "new window" record; leading == 255 is the reference's "no window yet" sentinel.
+struct GorillaState {
+  uint64_t prev_bits;
+  uint32_t leading, trailing;
+  bool first;
+  __device__ __forceinline__ void reset() { prev_bits = 0; leading = 255u; trailing = 0; first = true; }
+};
+struct BitAcc {  // up to 128 bits
+  uint64_t lo = 0, hi = 0;
+  uint32_t n = 0;
+  __device__ __forceinline__ void put(uint64_t bits, uint32_t nbits) {
+    if (nbits < 64u) bits &= (1ull << nbits) - 1ull;
+    if (n < 64u) {
+      lo |= bits << n;
+      if (n + nbits > 64u) hi |= bits >> (64u - n);  // n >= 1 here
+    } else {
+      hi |= bits << (n - 64u);
+    }
+    n += nbits;
+  }
+};
+// Encodes `cur`; writes the record to out[0..len) and returns len (1..10).
+__device__ __forceinline__ uint32_t gorilla_encode(GorillaState& st, uint64_t cur, uint8_t* out) {
+  BitAcc a;
+  if (st.first) {
+    st.first = false;
+    st.prev_bits = cur;
+    a.put(cur, 64);
+  } else {
+    const uint64_t x = cur ^ st.prev_bits;
+    st.prev_bits = cur;
+    if (x == 0) {
+      a.put(0, 1);
+    } else {
+      a.put(1, 1);
+      const uint32_t leading = static_cast<uint32_t>(__clzll(static_cast<long long>(x)));
+      const uint32_t trailing = static_cast<uint32_t>(__ffsll(static_cast<long long>(x)) - 1);
+      if (st.leading != 255u && leading >= st.leading && trailing >= st.trailing) {
+        a.put(0, 1);
+        a.put(x >> st.trailing, 64u - st.leading - st.trailing);
+      } else {
+        a.put(1, 1);
+        const uint32_t stored = leading > 31u ? 31u : leading;
+        const uint32_t meaningful = 64u - stored - trailing;
+        a.put(stored, 5);
+        a.put(meaningful - 1u, 6);
+        a.put(x >> trailing, meaningful);
+        st.leading = stored;
+        st.trailing = trailing;
+      }
+    }
+  }
+  const uint32_t bytes = (a.n + 7u) >> 3;
+  for (uint32_t i = 0; i < bytes; ++i) out[i] = static_cast<uint8_t>(i < 8u ? (a.lo >> (8u * i)) : (a.hi >> (8u * (i - 8u))));
+  return bytes;
+}
+// Reads nbits (<= 64) at bit position *bitpos of p (avail bytes). Returns false when the input is truncated.
+__device__ __forceinline__ bool read_bits(const uint8_t* p, uint32_t avail, uint32_t* bitpos, uint32_t nbits, uint64_t* out) {
+  if ((*bitpos + nbits + 7u) / 8u > avail) return false;
+  uint64_t v = 0;
+  for (uint32_t i = 0; i < nbits; ++i) {
+    const uint32_t b = *bitpos + i;
+    v |= static_cast<uint64_t>((p[b >> 3] >> (b & 7u)) & 1u) << i;
+  }
+  *bitpos += nbits;
+  *out = v;
+  return true;
+}
+// Decodes one value (field_decoder.hpp:257-300). Returns the bytes consumed, 0 when the input is truncated / malformed.
+__device__ __forceinline__ uint32_t gorilla_decode(GorillaState& st, const uint8_t* p, uint32_t avail, uint64_t* value) {
+  uint32_t bp = 0;
+  uint64_t v;
+  if (st.first) {
+    st.first = false;
+    if (!read_bits(p, avail, &bp, 64, &v)) return 0;
+    st.prev_bits = v;
+  } else {
+    uint64_t flag;
+    if (!read_bits(p, avail, &bp, 1, &flag)) return 0;
+    if (flag == 0) {
+      v = st.prev_bits;
+    } else {
+      uint64_t control, bits, x;
+      if (!read_bits(p, avail, &bp, 1, &control)) return 0;
+      if (control == 0) {
+        const uint32_t meaningful = (64u - st.leading - st.trailing) & 0xFFu;
+        if (meaningful > 64u) return 0;  // window reuse before any window: malformed
+        if (!read_bits(p, avail, &bp, meaningful, &bits)) return 0;
+        x = st.trailing < 64u ? bits << st.trailing : 0ull;
+      } else {
+        uint64_t lead, m1;
+        if (!read_bits(p, avail, &bp, 5, &lead) || !read_bits(p, avail, &bp, 6, &m1)) return 0;
+        const uint32_t meaningful = static_cast<uint32_t>(m1) + 1u;
+        if (!read_bits(p, avail, &bp, meaningful, &bits)) return 0;
+        const uint32_t trailing = (64u - static_cast<uint32_t>(lead) - meaningful) & 0xFFu;
+        x = trailing < 64u ? bits << trailing : 0ull;
+        st.leading = static_cast<uint32_t>(lead);
+        st.trailing = trailing;
+      }
+      v = x ^ st.prev_bits;
+      st.prev_bits = v;
+    }
+  }
+  *value = v;
+  return (bp + 7u) >> 3;
+}
 
 // ---- block-wide exclusive scan of one uint32 per thread (kThreads threads) --------------------------------------
 // Returns the exclusive prefix; *total receives the block sum. `scratch` = 8+1 uint32 in shared memory.

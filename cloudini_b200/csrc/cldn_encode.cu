@@ -24,10 +24,22 @@ namespace cldn {
 // keeps the previous point's quantised value (0 after reset() or after a NaN), so it is recomputed instead of carried.
 template <class Sink>
 __device__ __forceinline__ void encode_point_ops(const Plan& plan, const uint8_t* __restrict__ pt,
-                                                 const uint8_t* __restrict__ prev, Sink& sink) {
+                                                 const uint8_t* __restrict__ prev, Sink& sink,
+                                                 const uint8_t* __restrict__ side = nullptr, uint32_t side_stride = 0) {
+  uint32_t gorilla_idx = 0;
   for (uint32_t k = 0; k < plan.n_ops; ++k) {
     const RegOp& op = plan.ops[k];
     switch (op.kind) {
+      case OP_XOR32: case OP_XOR64: {  // field_encoder.hpp:360-370: residual = bits ^ previous point's bits (0 at a chunk start)
+        const uint64_t cur = load_raw_bits(pt + op.offset[0], op.size);
+        const uint64_t pb = prev ? load_raw_bits(prev + op.offset[0], op.size) : 0ull;
+        sink.put_le(cur ^ pb, op.size);
+      } break;
+      case OP_GORILLA64: {  // record built by gorilla_prepass_kernel (the window state is sequential along the chunk)
+        const uint8_t* rec = side + static_cast<size_t>(gorilla_idx) * side_stride;
+        sink.put_raw(rec, rec[11]);
+        ++gorilla_idx;
+      } break;
       case OP_FLOATN: {  // field_encoder.cpp:42-91
         for (int l = 0; l < op.lanes; ++l) {
           const float v = __uint_as_float(load_u32(pt + op.offset[l]));
@@ -159,7 +171,7 @@ __global__ void __launch_bounds__(kThreads) encode_generic_kernel(const EncLaunc
       const uint8_t* pt = F.in + static_cast<size_t>(p) * step;
       const uint8_t* prev = (p % kChunkPoints) ? pt - step : nullptr;
       CountSink cs;
-      encode_point_ops(plan, pt, prev, cs);
+      encode_point_ops(plan, pt, prev, cs, F.side ? F.side + static_cast<size_t>(p) * 12 : nullptr, F.n_points * 12u);
       len[i] = cs.n;
     }
     mine += len[i];
@@ -176,7 +188,7 @@ __global__ void __launch_bounds__(kThreads) encode_generic_kernel(const EncLaunc
       const uint8_t* pt = F.in + static_cast<size_t>(p) * step;
       const uint8_t* prev = (p % kChunkPoints) ? pt - step : nullptr;
       ByteSink bs{stage + off};
-      encode_point_ops(plan, pt, prev, bs);
+      encode_point_ops(plan, pt, prev, bs, F.side ? F.side + static_cast<size_t>(p) * 12 : nullptr, F.n_points * 12u);
       off += len[i];
     }
   }
@@ -483,6 +495,44 @@ static int launch_floatn(const Plan& plan, const EncLaunch& L, bool vec4, cudaSt
     if (set_smem(k, smem) != cudaSuccess) return -1;
     k<<<L.n_tiles_total, kThreads, smem, stream>>>(L, P);
   }
+  count_launch();
+  return 1;
+}
+
+// Gorilla pre-pass: one thread per (chunk, Gorilla op) walks its 32768 points in order (the window of the previous
+// "new window" record is inherently sequential) and leaves a 12-byte record per point: bytes 0..9 the encoded value,
+// byte 11 its length. The generic kernel then copies the record like any other field. Side layout: [op][point][12].
+__global__ void gorilla_prepass_kernel(const EncLaunch L) {
+  const EncFrame F = L.frames[blockIdx.x];
+  const Plan& plan = *L.plan;
+  const uint32_t items = F.n_chunks * plan.n_gorilla;
+  for (uint32_t it = threadIdx.x; it < items; it += blockDim.x) {
+    const uint32_t chunk = it / plan.n_gorilla, g = it % plan.n_gorilla;
+    uint32_t seen = 0, offset = 0;
+    for (uint32_t k = 0; k < plan.n_ops; ++k) {
+      if (plan.ops[k].kind == OP_GORILLA64) {
+        if (seen == g) offset = plan.ops[k].offset[0];
+        ++seen;
+      }
+    }
+    const uint32_t p0 = chunk * kChunkPoints;
+    const uint32_t n = min(kChunkPoints, F.n_points - p0);
+    uint8_t* side = const_cast<uint8_t*>(F.side) + (static_cast<size_t>(g) * F.n_points + p0) * 12;
+    GorillaState st;
+    st.reset();
+    for (uint32_t i = 0; i < n; ++i) {
+      const uint64_t cur = load_u64(F.in + static_cast<size_t>(p0 + i) * plan.point_step + offset);
+      uint8_t rec[12];
+      const uint32_t len = gorilla_encode(st, cur, rec);
+      for (uint32_t b = 0; b < len; ++b) side[i * 12 + b] = rec[b];
+      side[i * 12 + 11] = static_cast<uint8_t>(len);
+    }
+  }
+}
+
+int launch_gorilla_prepass(const Plan& plan, const EncLaunch& L, cudaStream_t stream) {
+  if (plan.n_gorilla == 0 || L.n_frames == 0) return 0;
+  gorilla_prepass_kernel<<<L.n_frames, 64, 0, stream>>>(L);
   count_launch();
   return 1;
 }

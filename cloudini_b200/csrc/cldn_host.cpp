@@ -371,6 +371,7 @@ static void finish_plan(Plan* p) {
   p->max_point_bytes = 0;
   p->min_point_bytes = 0;
   p->values_per_point = 0;
+  p->n_gorilla = 0;
   p->all_varint = 1;
   p->all_fixed = 1;
   for (uint32_t i = 0; i < p->n_ops; ++i) {
@@ -382,10 +383,10 @@ static void finish_plan(Plan* p) {
         p->max_point_bytes += 10; p->min_point_bytes += 1; p->values_per_point += 1; p->all_fixed = 0; break;
       case OP_COPY:
         p->max_point_bytes += op.size; p->min_point_bytes += op.size; p->all_varint = 0; break;
-      case OP_XOR32: case OP_XOR64:
-        p->max_point_bytes += op.size; p->min_point_bytes += op.size; p->all_varint = 0; p->all_fixed = 0; p->supported = 0; break;
-      default:  // Gorilla
-        p->max_point_bytes += 11; p->min_point_bytes += 1; p->all_varint = 0; p->all_fixed = 0; p->supported = 0; break;
+      case OP_XOR32: case OP_XOR64:  // raw residual of the previous point's bits (field_encoder.hpp:360-370)
+        p->max_point_bytes += op.size; p->min_point_bytes += op.size; p->all_varint = 0; p->all_fixed = 0; break;
+      default:  // Gorilla: at most 1+1+5+6+64 = 77 bits = 10 bytes per value; minInputBytes() = 0 (field_decoder.hpp:163-166)
+        p->max_point_bytes += 10; p->all_varint = 0; p->all_fixed = 0; ++p->n_gorilla; break;
     }
   }
   p->floatn_only = (p->n_ops == 1 && p->ops[0].kind == OP_FLOATN) ? 1 : 0;

@@ -17,6 +17,8 @@ struct EncFrame {
   uint32_t n_chunks;
   // V5: exclusive scan over chunks of the total adaptive-section bytes ((n_chunks + 1) entries), else nullptr.
   const uint32_t* sec_excl;
+  // Gorilla ops: records precomputed by the sequential pre-pass, 12 bytes per (op, point): bytes 0..9 record, byte 11 length
+  const uint8_t* side;
 };
 
 struct EncLaunch {
@@ -39,6 +41,7 @@ uint32_t choose_tile_points(const Plan& plan);
 
 // Interleaved regular stream + chunk framing. Returns the number of kernels launched.
 int launch_encode_regular(const Plan& host_plan, const EncLaunch& L, cudaStream_t stream);
+int launch_gorilla_prepass(const Plan& host_plan, const EncLaunch& L, cudaStream_t stream);
 
 struct DecFrame {
   const uint8_t* payload;  // header-less payload
@@ -68,6 +71,7 @@ struct DecLaunch {
   uint32_t* tsums;             // per tile: 2 x 8 words, look-back 2 (aggregate record, inclusive record)
   uint64_t* trace;             // optional (CLDN_B200_TRACE): 8 globaltimer stamps per tile
   uint32_t* chunk_counter;     // work counter of the chunk-sequential kernel
+  uint32_t sections_only;      // decode_chunks_kernel: the regular stream was decoded elsewhere, start at stream_end[]
   uint32_t tile_capacity;      // records allocated (== tile_grid)
   uint32_t tile_grid;          // host upper bound on the number of tiles
   uint32_t epoch;

@@ -24,9 +24,9 @@ enum OpKind : uint8_t {
   OP_F64_LOSSY = 2,  // FieldEncoderFloat_Lossy<double>
   OP_INT = 3,        // FieldEncoderInt<T>  field_encoder.hpp:72-94 (V4 interleaved delta varint)
   OP_COPY = 4,       // FieldEncoderCopy    field_encoder.hpp:51-67 (raw bytes)
-  OP_XOR32 = 5,      // FieldEncoderFloat_XOR<float>     (lossless; not accelerated in this round)
+  OP_XOR32 = 5,      // FieldEncoderFloat_XOR<float>     field_encoder.hpp:123-139,360-370 (raw XOR with the previous bits)
   OP_XOR64 = 6,      // FieldEncoderFloat_XOR<double>
-  OP_GORILLA64 = 7,  // FieldEncoderFloat_Gorilla<double>
+  OP_GORILLA64 = 7,  // FieldEncoderFloat_Gorilla<double> field_encoder.hpp:157-312 (bit-packed, byte-aligned per value)
 };
 
 struct RegOp {
@@ -62,8 +62,9 @@ struct Plan {
   uint8_t floatn_only;  // regular stream is exactly one OP_FLOATN  -> specialised kernels
   uint8_t all_varint;   // every regular op is varint/NaN-marker coded -> terminator-scan decode applies
   uint8_t all_fixed;    // every regular op is fixed size (COPY)
-  uint8_t supported;    // 0 if the plan contains ops this build does not accelerate (XOR / Gorilla)
-  uint8_t pad_[3];
+  uint8_t supported;    // 0 if the plan contains ops this build cannot run at all
+  uint8_t n_gorilla;    // number of OP_GORILLA64 ops (they need the sequential per-chunk pre-pass / decoder)
+  uint8_t pad_[2];
 };
 
 // Builds the ENCODER plan. Returns CLDN_OK or a negative status (message via set_error()).

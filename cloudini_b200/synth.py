@@ -100,6 +100,42 @@ def cloud_c4_frame(frame: int, seed: int = 4, rings: int = 64, az: int = 2032):
     return info_xyzi(n), np.ascontiguousarray(pts, dtype=np.float32).view(np.uint8).reshape(-1)
 
 
+def cloud_lossless(n: int = 40_000, seed: int = 6, lossless: bool = True, version: int = 5, stamp_res=None,
+                   hostile: bool = True):
+    """The reference's DDS / PCD layout (x, y, z, intensity f32, ring u16, timestamp f64; point_step 26) used to reach
+    the lossless float coders: EncodingOptions.LOSSLESS turns the f32 fields into XOR residuals and the resolution-less
+    FLOAT64 into Gorilla (wire version >= 4) or XOR (version 3) (codec_common.cpp:100-140). `hostile` sprinkles the
+    values that move the Gorilla window: repeats (xor == 0), NaN / inf / -0.0, denormals and full-entropy doubles."""
+    rng = np.random.default_rng(seed)
+    step = 26
+    buf = np.zeros((n, step), dtype=np.uint8)
+    xyz = np.cumsum(rng.normal(0, 0.02, (n, 3)), axis=0).astype(np.float32)
+    inten = rng.integers(0, 255, n).astype(np.float32)
+    ts = (1.7e9 + np.arange(n) * 1e-5 + (np.arange(n) // 2048) * 0.1).astype(np.float64)
+    if hostile and n > 64:
+        k = max(1, n // 200)
+        ts[rng.integers(1, n, k)] = ts[rng.integers(0, n, k)]                 # jumps backwards / forwards
+        idx = rng.integers(1, n, k); ts[idx] = ts[idx - 1]                     # exact repeats -> the single '0' bit
+        ts[rng.integers(0, n, k)] = rng.integers(0, 2**63, k, dtype=np.int64).view(np.float64)  # random bit patterns
+        ts[rng.integers(0, n, 8)] = np.array([np.nan, np.inf, -np.inf, -0.0, 0.0, 5e-324, 1.0, -1.0])
+        xyz[rng.integers(0, n, k), rng.integers(0, 3, k)] = np.nan
+        inten[rng.integers(0, n, 4)] = np.array([np.inf, -np.inf, -0.0, 1e-42], dtype=np.float32)
+    buf[:, 0:12] = xyz.view(np.uint8).reshape(n, 12)
+    buf[:, 12:16] = inten.view(np.uint8).reshape(n, 4)
+    buf[:, 16:18] = (np.arange(n) % 64).astype(np.uint16).view(np.uint8).reshape(n, 2)
+    buf[:, 18:26] = ts.view(np.uint8).reshape(n, 8)
+    res = None if lossless else 0.001
+    F = FieldType
+    info = EncodingInfo(
+        fields=[PointField("x", 0, F.FLOAT32, res), PointField("y", 4, F.FLOAT32, res), PointField("z", 8, F.FLOAT32, res),
+                PointField("intensity", 12, F.FLOAT32, res), PointField("ring", 16, F.UINT16, None),
+                PointField("timestamp", 18, F.FLOAT64, stamp_res)],
+        width=n, height=1, point_step=step,
+        encoding_opt=EncodingOptions.LOSSLESS if lossless else EncodingOptions.LOSSY,
+        compression_opt=CompressionOption.NONE, use_threads=False, version=version)
+    return info, np.ascontiguousarray(buf).reshape(-1)
+
+
 def fnv1a64(data) -> int:
     """FNV-1a 64-bit (the fingerprint mcap_codec_benchmark --hash prints, tools/src/mcap_codec_benchmark.cpp:103-109)."""
     h = 0xCBF29CE484222325

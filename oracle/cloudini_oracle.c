@@ -155,7 +155,7 @@ static uint64_t read_raw(const uint8_t* p, int bytes) {
 }
 
 /* ---------------------------------------------------------------- planning */
-enum { K_FLOATN, K_F32, K_F64, K_INT, K_COPY, K_UNSUPPORTED };
+enum { K_FLOATN, K_F32, K_F64, K_INT, K_COPY, K_XOR32, K_XOR64, K_GORILLA64, K_UNSUPPORTED };
 typedef struct {
   int kind, lanes, size;
   uint8_t type;
@@ -165,6 +165,8 @@ typedef struct {
   /* state */
   int32_t prev32[4];
   int64_t prev64;
+  uint64_t prev_bits; /* XOR / Gorilla */
+  int g_first, g_lead, g_trail; /* Gorilla window (field_encoder.hpp:157-183) */
 } op_t;
 typedef struct {
   uint32_t off;
@@ -242,7 +244,8 @@ static int make_plan(const cldn_info_t* in, int decoder, plan_t* pl) {
           if (!(f->resolution > 0.0f)) return fail("FieldEncoder(Float/Lossy) requires a resolution with value > 0.0");
           pl->min_point_bytes += 1;
         } else if (in->encoding_opt == CLDN_ENC_LOSSLESS) {
-          o->kind = K_UNSUPPORTED; /* XOR */
+          o->kind = K_XOR32; /* field_encoder.hpp:360-370 */
+          pl->min_point_bytes += 4;
         } else {
           o->kind = K_COPY;
           pl->min_point_bytes += 4;
@@ -255,8 +258,11 @@ static int make_plan(const cldn_info_t* in, int decoder, plan_t* pl) {
           o->dec_mul_d = (double)f->resolution;
           if (!(f->resolution > 0.0f)) return fail("FieldEncoder(Float/Lossy) requires a resolution with value > 0.0");
           pl->min_point_bytes += 1;
+        } else if (!f->has_resolution && in->version >= 4) {
+          o->kind = K_GORILLA64; /* codec_common.cpp:129-131; minInputBytes() = 0 (field_decoder.hpp:163-166) */
         } else {
-          o->kind = K_UNSUPPORTED; /* Gorilla / XOR */
+          o->kind = K_XOR64;
+          pl->min_point_bytes += 8;
         }
         break;
       case CLDN_INT16: case CLDN_UINT16: case CLDN_INT32: case CLDN_UINT32: case CLDN_INT64: case CLDN_UINT64:
@@ -270,7 +276,6 @@ static int make_plan(const cldn_info_t* in, int decoder, plan_t* pl) {
       default:
         return fail("Unsupported field type");
     }
-    if (o->kind == K_UNSUPPORTED) return fail("oracle: lossless float fields (XOR/Gorilla) are outside the restated path");
   }
   return 0;
 }
@@ -279,7 +284,108 @@ static void reset_ops(plan_t* pl) {
   for (int i = 0; i < pl->n_ops; ++i) {
     memset(pl->ops[i].prev32, 0, sizeof(pl->ops[i].prev32));
     pl->ops[i].prev64 = 0;
+    pl->ops[i].prev_bits = 0;
+    pl->ops[i].g_first = 1;
+    pl->ops[i].g_lead = 255; /* kLeadingSentinel */
+    pl->ops[i].g_trail = 0;
   }
+}
+
+/* ---- Gorilla / Chimp-style bit packing of FLOAT64 (field_encoder.hpp:157-312): every value is flushed to a byte
+ * boundary, bits are appended LSB-first. Returns the number of bytes written (<= 10). */
+typedef struct { uint64_t lo, hi; unsigned n; } bitacc_t;
+static void acc_put(bitacc_t* a, uint64_t bits, unsigned nbits) {
+  if (nbits < 64) bits &= ((uint64_t)1 << nbits) - 1;
+  if (a->n < 64) {
+    a->lo |= bits << a->n;
+    if (a->n + nbits > 64) a->hi |= bits >> (64 - a->n);
+  } else {
+    a->hi |= bits << (a->n - 64);
+  }
+  a->n += nbits;
+}
+static size_t gorilla_encode(op_t* o, uint64_t cur, uint8_t* out) {
+  bitacc_t a = {0, 0, 0};
+  if (o->g_first) {
+    o->g_first = 0;
+    o->prev_bits = cur;
+    acc_put(&a, cur, 64);
+  } else {
+    const uint64_t x = cur ^ o->prev_bits;
+    o->prev_bits = cur;
+    if (x == 0) {
+      acc_put(&a, 0, 1);
+    } else {
+      acc_put(&a, 1, 1);
+      const int leading = __builtin_clzll(x), trailing = __builtin_ctzll(x);
+      if (o->g_lead != 255 && leading >= o->g_lead && trailing >= o->g_trail) {
+        acc_put(&a, 0, 1);
+        acc_put(&a, x >> o->g_trail, (unsigned)(64 - o->g_lead - o->g_trail));
+      } else {
+        acc_put(&a, 1, 1);
+        const int stored = leading > 31 ? 31 : leading;
+        const unsigned meaningful = (unsigned)(64 - stored - trailing);
+        acc_put(&a, (uint64_t)stored, 5);
+        acc_put(&a, (uint64_t)(meaningful - 1), 6);
+        acc_put(&a, x >> trailing, meaningful);
+        o->g_lead = stored;
+        o->g_trail = trailing;
+      }
+    }
+  }
+  const size_t bytes = (a.n + 7) / 8;
+  for (size_t i = 0; i < bytes; ++i) out[i] = (uint8_t)(i < 8 ? (a.lo >> (8 * i)) : (a.hi >> (8 * (i - 8))));
+  return bytes;
+}
+/* bit reader over one value's bytes (field_decoder.hpp:200-300): returns bytes consumed, 0 on truncation */
+typedef struct { const uint8_t* p; size_t avail; unsigned bitpos; } bitrd_t;
+static int rd_bits(bitrd_t* r, unsigned nbits, uint64_t* out) {
+  if (((size_t)r->bitpos + nbits + 7) / 8 > r->avail) return fail("FieldDecoderFloat_Gorilla: truncated input");
+  uint64_t v = 0;
+  for (unsigned i = 0; i < nbits; ++i) {
+    const unsigned b = r->bitpos + i;
+    v |= (uint64_t)((r->p[b >> 3] >> (b & 7)) & 1u) << i;
+  }
+  r->bitpos += nbits;
+  *out = v;
+  return 0;
+}
+static size_t gorilla_decode(op_t* o, const uint8_t* p, size_t avail, uint64_t* value) {
+  bitrd_t r = {p, avail, 0};
+  uint64_t v;
+  if (o->g_first) {
+    o->g_first = 0;
+    if (rd_bits(&r, 64, &v)) return 0;
+    o->prev_bits = v;
+  } else {
+    uint64_t flag;
+    if (rd_bits(&r, 1, &flag)) return 0;
+    if (flag == 0) {
+      v = o->prev_bits;
+    } else {
+      uint64_t control, bits, x;
+      if (rd_bits(&r, 1, &control)) return 0;
+      if (control == 0) {
+        const unsigned meaningful = (unsigned)(uint8_t)(64 - o->g_lead - o->g_trail);
+        if (meaningful > 64) { fail("oracle: Gorilla window reuse before any window (malformed input)"); return 0; }
+        if (rd_bits(&r, meaningful, &bits)) return 0;
+        x = o->g_trail < 64 ? bits << o->g_trail : 0;
+      } else {
+        uint64_t lead, m1;
+        if (rd_bits(&r, 5, &lead) || rd_bits(&r, 6, &m1)) return 0;
+        const unsigned meaningful = (unsigned)m1 + 1;
+        if (rd_bits(&r, meaningful, &bits)) return 0;
+        const unsigned trailing = (unsigned)(uint8_t)(64 - lead - meaningful);
+        x = trailing < 64 ? bits << trailing : 0;
+        o->g_lead = (int)lead;
+        o->g_trail = (int)trailing;
+      }
+      v = x ^ o->prev_bits;
+      o->prev_bits = v;
+    }
+  }
+  *value = v;
+  return (r.bitpos + 7) / 8; /* leftover bits of the last byte are padding */
 }
 
 /* ---------------------------------------------------------------- per-point regular encoders */
@@ -326,6 +432,19 @@ static size_t encode_point(plan_t* pl, const uint8_t* pt, uint8_t* out) {
         const int64_t d = (int64_t)((uint64_t)v - (uint64_t)o->prev64);
         o->prev64 = v;
         n += put_varint(d, out + n);
+      } break;
+      case K_XOR32: case K_XOR64: { /* field_encoder.hpp:360-370: residual = bits ^ previous bits, raw */
+        uint64_t cur = 0;
+        memcpy(&cur, pt + o->off[0], (size_t)o->size);
+        const uint64_t res = cur ^ o->prev_bits;
+        o->prev_bits = cur;
+        memcpy(out + n, &res, (size_t)o->size);
+        n += (size_t)o->size;
+      } break;
+      case K_GORILLA64: {
+        uint64_t cur;
+        memcpy(&cur, pt + o->off[0], 8);
+        n += gorilla_encode(o, cur, out + n);
       } break;
       default: /* copy, field_encoder.hpp:56-60 */
         memcpy(out + n, pt + o->off[0], (size_t)o->size);
@@ -708,6 +827,23 @@ int orc_decode(const cldn_info_t* in, const uint8_t* payload, size_t bytes, uint
           if (a < (size_t)o->size) return fail("Span: trim_front out of range");
           if (o->off[0] != CLDN_SKIP_STORE_OFFSET) memcpy(pt + o->off[0], p, (size_t)o->size);
           p += o->size; a -= (size_t)o->size;
+          continue;
+        }
+        if (o->kind == K_XOR32 || o->kind == K_XOR64) { /* field_decoder.hpp:356-370 */
+          if (a < (size_t)o->size) return fail("Span: trim_front out of range");
+          uint64_t res = 0;
+          memcpy(&res, p, (size_t)o->size);
+          p += o->size; a -= (size_t)o->size;
+          o->prev_bits ^= res;
+          if (o->off[0] != CLDN_SKIP_STORE_OFFSET) memcpy(pt + o->off[0], &o->prev_bits, (size_t)o->size);
+          continue;
+        }
+        if (o->kind == K_GORILLA64) {
+          uint64_t v;
+          const size_t c = gorilla_decode(o, p, a, &v);
+          if (!c) return -1;
+          p += c; a -= c;
+          if (o->off[0] != CLDN_SKIP_STORE_OFFSET) memcpy(pt + o->off[0], &v, 8);
           continue;
         }
         for (int l = 0; l < o->lanes; ++l) {

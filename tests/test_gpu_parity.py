@@ -112,6 +112,30 @@ def test_scalar_and_int_fields_v4(oracle):
         _roundtrip_check(info, buf.reshape(-1), oracle)
 
 
+@pytest.mark.parametrize("version", [5, 4, 3])
+@pytest.mark.parametrize("lossless", [True, False])
+def test_lossless_float_fields(oracle, version, lossless):
+    # LOSSLESS: f32 -> XOR residuals, resolution-less f64 -> Gorilla (v>=4) / XOR (v3); LOSSY keeps Gorilla for the stamp.
+    # V5 adds the ring section after a regular stream that is not all-varint.
+    for n in (1, 5, 4133, 32768, 70_001):
+        info, cloud = synth.cloud_lossless(n, seed=n + version, lossless=lossless, version=version)
+        blob = _roundtrip_check(info, cloud, oracle, fill=0xA5)
+        if lossless:
+            dinfo, hdr = cb.DecodeHeader(blob)
+            got = np.zeros(cloud.size, dtype=np.uint8)
+            cb.PointcloudDecoder().decode(dinfo, blob[hdr:], got)
+            assert np.array_equal(got, cloud)  # size-independent property: lossless means bit-exact, NaN payloads too
+
+
+def test_lossless_truncated_stream_is_rejected():
+    info, cloud = synth.cloud_lossless(5000, seed=3, lossless=True, version=5)
+    blob = cb.PointcloudEncoder(info).encode(cloud)
+    dinfo, hdr = cb.DecodeHeader(blob)
+    out = np.zeros(cloud.size, dtype=np.uint8)
+    with pytest.raises(RuntimeError):
+        cb.PointcloudDecoder().decode(dinfo, blob[hdr:-7], out)
+
+
 def test_encoding_none_copy_only(oracle):
     info, cloud = synth.cloud_c3(33_000, seed=5)
     info.encoding_opt = cb.EncodingOptions.NONE

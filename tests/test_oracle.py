@@ -166,6 +166,20 @@ def test_port_vs_reference_double_and_two_floats(port, ref):
     assert np.array_equal(o1, o2)
 
 
+@pytest.mark.parametrize("version", [5, 4, 3])
+@pytest.mark.parametrize("lossless", [True, False])
+def test_port_vs_reference_lossless_floats(port, ref, version, lossless):
+    # XOR (f32 / f64 on version 3) and Gorilla (resolution-less f64, version >= 4): field_encoder.hpp:123-312
+    for n in (1, 5, 4133, 40_000):
+        info, cloud = synth.cloud_lossless(n, seed=n + version, lossless=lossless, version=version)
+        a = ref.encode(info, cloud)
+        assert port.encode(info, cloud) == a
+        want = _decode_zero(ref, a, info)
+        assert np.array_equal(_decode_zero(port, a, info), want)
+        if lossless:
+            assert np.array_equal(want, cloud)  # bit-exact round trip, NaN payloads included
+
+
 def test_port_decoder_hardening(port):
     # test_field_encoders.cpp:771-791 / test_header.cpp:165-171: missing chunks, trailing garbage, header in payload
     info, cloud = synth.cloud_c2(40_000, seed=9)
