@@ -62,4 +62,6 @@ def build(force=False, verbose=False, defines=(), out=None):
 if __name__ == "__main__":
     defs = tuple(a[2:] for a in sys.argv if a.startswith("-D"))
     outs = [a[6:] for a in sys.argv if a.startswith("--out=")]
+    if "--out" in sys.argv:
+        outs.append(sys.argv[sys.argv.index("--out") + 1])
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, defines=defs, out=outs[0] if outs else None))

@@ -19,9 +19,18 @@ namespace cldn {
 #define CLDN_KVEC 1
 #endif
 constexpr int kVec = CLDN_KVEC;  // adjacent 16-byte vectors per thread
-constexpr int kTB = kThreads * 16 * kVec;  // stream bytes per tile (8192)
+#ifndef CLDN_DT
+#define CLDN_DT 256
+#endif
+constexpr int kDT = CLDN_DT;     // threads per decode CTA (tile = kDT * 16 * kVec stream bytes)
+#ifndef CLDN_SEQ_MINB
+#define CLDN_SEQ_MINB 4
+#endif
+constexpr int kTB = kDT * 16 * kVec;  // stream bytes per tile (8192)
 constexpr int kTLook = 16;     // look-behind bytes staged in front of the tile
 constexpr uint32_t kRecWords = 8;  // look-back record: sum[4], rst, flag, pad, pad
+constexpr int kOStageOffset = (kTLook + kTB + 16 + 2 * kDT + 64 + 15) / 16 * 16;  // float staging of dense layouts
+constexpr int kOStageBytes = (3 + kTB + 4) * 4;  // at most one value per stream byte (+ alignment slack)
 
 // ---- per-chunk tile counts and their exclusive scan (grid of the tile kernel is an upper bound computed on the host)
 __global__ void count_tiles_kernel(const DecLaunch L) {
@@ -104,10 +113,10 @@ __device__ __forceinline__ SegK<K> seg_identity() {
 }
 
 struct TileShared {
-  uint32_t scan[kThreads / 32 + 1];
+  uint32_t scan[kDT / 32 + 1];
   uint32_t done;  // values of this chunk before the tile
-  int32_t w_sum[kThreads / 32][4];
-  uint32_t w_rst[kThreads / 32];
+  int32_t w_sum[kDT / 32][4];
+  uint32_t w_rst[kDT / 32];
   int32_t carry[4];
 };
 
@@ -175,9 +184,9 @@ __device__ __forceinline__ SegK<K> sums_lookback(const uint64_t* recs, uint32_t 
   return acc;
 }
 
-// Per-thread value run in LOCAL slot numbering: value k of the run is local slot k % K (runs start at a multiple of K
-// values); the global field is (phase + k) % K with phase = done % K uniform over the tile, so accumulators and
-// per-field constants are rotated once instead of specialising the unrolled loops per phase.
+// Per-thread value run in LOCAL slot numbering: value k of the run is local slot k % K; its global field is
+// (phase + k) % K with phase = (values before the run) % K, so accumulators and per-field constants are rotated once
+// per thread instead of specialising the unrolled loops per phase.
 template <int K, int VTMAX>
 __device__ __forceinline__ SegK<K> run_reduce_local(const int32_t (&d)[VTMAX], unsigned long long nanm, uint32_t n) {
   SegK<K> m = seg_identity<K>();
@@ -203,10 +212,15 @@ __device__ __forceinline__ SegK<K> seg_to_global(const SegK<K>& a, uint32_t phas
   }
   return r;
 }
-template <int K, int VTMAX, bool ALIGNED4>
+// MODE 0: any layout (byte-wise stores, skipped fields honoured); 1: 4-byte aligned fields, direct 4-byte stores;
+// 2: dense float32xK points (step == 4K, offsets 0,4,..): the floats are staged in shared memory (`ostage`, indexed by
+//    the value's position in the tile) and leave with coalesced 16-byte stores (copy_out_dense) -- a direct store
+//    would touch one 32-byte sector per value.
+template <int K, int VTMAX, int MODE>
 __device__ __forceinline__ void run_emit_local(const int32_t (&d)[VTMAX], unsigned long long nanm, uint32_t n, const int32_t (&cur_global)[K],
                                                uint32_t phase, uint8_t* out, uint32_t pbase, uint32_t step, const float (&mul)[4],
-                                               const uint32_t (&off)[4]) {
+                                               const uint32_t (&off)[4], uint32_t* ostage = nullptr) {
+  constexpr bool ALIGNED4 = MODE >= 1;
   // rotate the running values and the per-field constants into local numbering
   int32_t cur[K];
   float lmul[K];
@@ -225,13 +239,33 @@ __device__ __forceinline__ void run_emit_local(const int32_t (&d)[VTMAX], unsign
     const int l = k % K;
     const bool nan = (nanm >> k) & 1ull;
     if (nan) cur[l] = 0; else cur[l] = wadd32(cur[l], d[k]);
-    if (loff[l] != CLDN_SKIP_STORE_OFFSET) {
+    if (MODE == 2) {
+      const float f = nan ? __uint_as_float(0x7FC00000u) : __fmul_rn(__int2float_rn(cur[l]), lmul[l]);
+      ostage[k] = __float_as_uint(f);
+    } else if (ALIGNED4 || loff[l] != CLDN_SKIP_STORE_OFFSET) {  // ALIGNED4 implies that no field is skipped
       const float f = nan ? __uint_as_float(0x7FC00000u) : __fmul_rn(__int2float_rn(cur[l]), lmul[l]);
       // point of value k: pbase + (phase + k) / K = pbase + k / K + (k % K + phase >= K)
       const uint32_t p = pbase + k / K + ((l + phase >= static_cast<uint32_t>(K)) ? 1u : 0u);
       uint8_t* dst = out + static_cast<size_t>(p) * step + loff[l];
-      if (ALIGNED4) *reinterpret_cast<uint32_t*>(dst) = __float_as_uint(f);
+      if (ALIGNED4) __stcs(reinterpret_cast<unsigned int*>(dst), __float_as_uint(f));  // st.global (the pointer comes from a table)
       else store_u32(dst, __float_as_uint(f));
+    }
+  }
+}
+
+// Dense layouts: the tile's `take` floats (staged at ostage[(done & 3) + i]) are the floats [done, done + take) of the
+// chunk's output; staging index and global index agree modulo 4, so whole 16-byte vectors move with LDS.128 / STG.128.
+__device__ __forceinline__ void copy_out_dense(const uint32_t* ostage, uint8_t* out, uint32_t done, uint32_t take) {
+  const uint32_t a = done & 3u, end = a + take;
+  uint32_t* g = reinterpret_cast<uint32_t*>(out) + (done - a);
+  for (uint32_t s4 = threadIdx.x * 4u; s4 < end; s4 += kDT * 4u) {
+    if (s4 >= a && s4 + 4u <= end) {
+      __stcs(reinterpret_cast<uint4*>(g + s4), *reinterpret_cast<const uint4*>(ostage + s4));
+    } else {
+#pragma unroll
+      for (uint32_t j = 0; j < 4u; ++j) {
+        if (s4 + j >= a && s4 + j < end) __stcs(g + s4 + j, ostage[s4 + j]);
+      }
     }
   }
 }
@@ -304,13 +338,36 @@ __device__ __forceinline__ uint32_t tile_load_masks(uint8_t* tile_bytes, const u
 // CTA scan of the terminator counts; then every run t of VT consecutive values gets the tile byte index (biased by
 // kTLook) of its first byte in start16[t]: value q starts right behind terminator q-1, which is found in the owner's
 // 16-bit mask. No per-value position list is built. Returns the number of values in the tile; ends with a barrier.
+// CTA exclusive scan of one count per thread with a single barrier: every warp re-scans the warp totals itself.
+__device__ __forceinline__ uint32_t tile_count_scan(uint32_t v, uint32_t* scratch, uint32_t* total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int NW = kDT / 32;
+  uint32_t inc = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= d) inc += t;
+  }
+  if (lane == 31) scratch[warp] = inc;
+  __syncthreads();
+  uint32_t w = lane < NW ? scratch[lane] : 0u;
+#pragma unroll
+  for (int d = 1; d < NW; d <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, w, d);
+    if (lane >= d) w += t;
+  }
+  *total = __shfl_sync(0xffffffffu, w, NW - 1);
+  const uint32_t before = __shfl_sync(0xffffffffu, w, warp > 0 ? warp - 1 : 0);
+  return (warp > 0 ? before : 0u) + inc - v;
+}
+
 template <int K>
 __device__ __forceinline__ uint32_t tile_rank_starts(uint32_t tmask, const uint8_t* tile_bytes, uint16_t* start16, uint32_t* scan,
                                                      uint32_t* vt_out) {
   uint32_t tile_cnt;
   const uint32_t c = __popc(tmask);
-  const uint32_t rank = block_exclusive_scan(c, scan, &tile_cnt);
-  const uint32_t VT = ((tile_cnt + kThreads - 1) / kThreads + K - 1) / K * K;  // values per thread, a multiple of K
+  const uint32_t rank = tile_count_scan(c, scan, &tile_cnt);
+  const uint32_t VT = max(1u, (tile_cnt + kDT - 1) / kDT);  // values per thread (runs need not start at a field 0)
   *vt_out = VT;
   const uint32_t base = kTLook + threadIdx.x * kVec * 16u;
   if (c) {
@@ -431,16 +488,33 @@ __device__ __forceinline__ SegK<K> cta_seg_exclusive(const SegK<K>& mine, TileSh
     sh.w_rst[warp] = inc.rst;
   }
   __syncthreads();
-  SegK<K> prefix = seg_identity<K>(), tot = seg_identity<K>();
+  // every warp scans the kDT/32 warp totals with its first lanes (3 shuffle steps) instead of looping over them
+  constexpr int NW = kDT / 32;
+  SegK<K> wt = seg_identity<K>();
+  if (lane < NW) {
 #pragma unroll
-  for (int ww = 0; ww < kThreads / 32; ++ww) {
-    SegK<K> x;
-#pragma unroll
-    for (int j = 0; j < K; ++j) x.sum[j] = sh.w_sum[ww][j];
-    x.rst = sh.w_rst[ww];
-    if (ww < warp) prefix = seg_then<K>(prefix, x);
-    tot = seg_then<K>(tot, x);
+    for (int j = 0; j < K; ++j) wt.sum[j] = sh.w_sum[lane][j];
+    wt.rst = sh.w_rst[lane];
   }
+  if (!__any_sync(0xffffffffu, wt.rst != 0u)) {
+#pragma unroll
+    for (int dd = 1; dd < NW; dd <<= 1) {
+#pragma unroll
+      for (int j = 0; j < K; ++j) {
+        const int32_t up = __shfl_up_sync(0xffffffffu, wt.sum[j], dd);
+        if (lane >= dd) wt.sum[j] = wadd32(wt.sum[j], up);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int dd = 1; dd < NW; dd <<= 1) {
+      const SegK<K> up = seg_shfl_up<K>(wt, dd);
+      if (lane >= dd) wt = seg_then<K>(up, wt);
+    }
+  }
+  const SegK<K> tot = seg_shfl<K>(wt, NW - 1);
+  SegK<K> prefix = seg_shfl<K>(wt, warp > 0 ? warp - 1 : 0);
+  if (warp == 0) prefix = seg_identity<K>();
   *total = tot;
   SegK<K> ex = prefix;
   const SegK<K> prev_lane = seg_shfl_up<K>(inc, 1);
@@ -450,13 +524,14 @@ __device__ __forceinline__ SegK<K> cta_seg_exclusive(const SegK<K>& mine, TileSh
 
 // ---- tile-parallel kernel: one CTA per 8 KB tile, two decoupled look-backs (small batches / single frames) ----------
 template <int K>
-__global__ void __launch_bounds__(kThreads, kVec == 1 ? 4 : 3) decode_tiles_kernel(const DecLaunch L, float m0, float m1, float m2, float m3,
+__global__ void __launch_bounds__(kDT, (kVec == 1 ? 4 : 3) * (256 / kDT)) decode_tiles_kernel(const DecLaunch L, float m0, float m1, float m2, float m3,
                                                                    uint32_t o0, uint32_t o1, uint32_t o2, uint32_t o3) {
   extern __shared__ __align__(16) uint8_t dyn_smem[];
   __shared__ TileShared sh;
   uint8_t* tile_bytes = dyn_smem;                                               // kTLook + kTB + 16
-  uint16_t* start16 = reinterpret_cast<uint16_t*>(dyn_smem + kTLook + kTB + 16);  // kThreads entries: first byte of every run
-  constexpr int VTMAX = ((kTB / kThreads) + K - 1) / K * K;                     // values per thread if every value is one byte
+  uint16_t* start16 = reinterpret_cast<uint16_t*>(dyn_smem + kTLook + kTB + 16);  // kDT entries: first byte of every run
+  uint32_t* ostage = reinterpret_cast<uint32_t*>(dyn_smem + kOStageOffset);
+  constexpr int VTMAX = ((kTB / kDT) + K - 1) / K * K;                     // values per thread if every value is one byte
 
   const uint32_t gt = blockIdx.x;
   if (gt >= L.chunk_tile_begin[L.n_chunks_total]) return;
@@ -513,7 +588,7 @@ __global__ void __launch_bounds__(kThreads, kVec == 1 ? 4 : 3) decode_tiles_kern
   if (badk < n_mine) report_error(L.err, badcode);            // bytes past the stream may be anything: only real values count
 
   // ---- per-field segmented sums of my run; the field of value k is (done + v0 + k) % K = (done % K + k) % K ----
-  const uint32_t phase = done % K;
+  const uint32_t phase = (done + v0) % K;
   const SegK<K> mine = seg_to_global<K>(run_reduce_local<K, VTMAX>(d, nanm, n_mine), phase);
   SegK<K> total;
   const SegK<K> ex = cta_seg_exclusive<K>(mine, sh, &total);
@@ -540,9 +615,15 @@ __global__ void __launch_bounds__(kThreads, kVec == 1 ? 4 : 3) decode_tiles_kern
   int32_t cur[K];
 #pragma unroll
   for (int j = 0; j < K; ++j) cur[j] = ((ex.rst >> j) & 1u) ? ex.sum[j] : wadd32(sh.carry[j], ex.sum[j]);
-  const uint32_t pbase = (done + v0) / K;  // point of my first value (v0 is a multiple of K, so all threads share `phase`)
-  if (aligned4) run_emit_local<K, VTMAX, true>(d, nanm, n_mine, cur, phase, out, pbase, step, mul, off);
-  else run_emit_local<K, VTMAX, false>(d, nanm, n_mine, cur, phase, out, pbase, step, mul, off);
+  const uint32_t pbase = (done + v0) / K;  // point of my first value
+  const bool dense = aligned4 && step == 4u * K && o0 == 0u && o1 == 4u && o2 == 8u && (K < 4 || o3 == 12u) &&
+      (reinterpret_cast<uintptr_t>(out) & 15u) == 0u;
+  if (dense) {
+    run_emit_local<K, VTMAX, 2>(d, nanm, n_mine, cur, phase, out, pbase, step, mul, off, ostage + (done & 3u) + v0);
+    __syncthreads();
+    copy_out_dense(ostage, out, done, take);
+  } else if (aligned4) run_emit_local<K, VTMAX, 1>(d, nanm, n_mine, cur, phase, out, pbase, step, mul, off);
+  else run_emit_local<K, VTMAX, 0>(d, nanm, n_mine, cur, phase, out, pbase, step, mul, off);
   TRACE(7);
 }
 
@@ -550,14 +631,15 @@ __global__ void __launch_bounds__(kThreads, kVec == 1 ? 4 : 3) decode_tiles_kern
 // No inter-CTA communication at all: the value count and the per-field running values are carried in shared memory
 // from tile to tile; chunks are claimed from an atomic counter so that the SMs stay balanced.
 template <int K>
-__global__ void __launch_bounds__(kThreads, kVec == 1 ? 4 : 3) decode_chunks_seq_kernel(const DecLaunch L, float m0, float m1, float m2, float m3,
+__global__ void __launch_bounds__(kDT, (kVec == 1 ? CLDN_SEQ_MINB : 3) * (256 / kDT)) decode_chunks_seq_kernel(const DecLaunch L, float m0, float m1, float m2, float m3,
                                                                         uint32_t o0, uint32_t o1, uint32_t o2, uint32_t o3) {
   extern __shared__ __align__(16) uint8_t dyn_smem[];
   __shared__ TileShared sh;
   __shared__ uint32_t s_chunk;
   uint8_t* tile_bytes = dyn_smem;
   uint16_t* start16 = reinterpret_cast<uint16_t*>(dyn_smem + kTLook + kTB + 16);
-  constexpr int VTMAX = ((kTB / kThreads) + K - 1) / K * K;
+  uint32_t* ostage = reinterpret_cast<uint32_t*>(dyn_smem + kOStageOffset);
+  constexpr int VTMAX = ((kTB / kDT) + K - 1) / K * K;
   const float mul[4] = {m0, m1, m2, m3};
   const uint32_t off[4] = {o0, o1, o2, o3};
   const uint32_t step = L.plan->point_step;
@@ -579,6 +661,8 @@ __global__ void __launch_bounds__(kThreads, kVec == 1 ? 4 : 3) decode_chunks_seq
     uint8_t* out = F.out + static_cast<size_t>(chunk) * kChunkPoints * step;
     const bool aligned4 = (((reinterpret_cast<uintptr_t>(out) | step | o0 | o1 | o2 | (K == 4 ? o3 : 0u)) & 3u) == 0u) &&
       o0 != CLDN_SKIP_STORE_OFFSET && o1 != CLDN_SKIP_STORE_OFFSET && o2 != CLDN_SKIP_STORE_OFFSET && (K < 4 || o3 != CLDN_SKIP_STORE_OFFSET);
+    const bool dense = aligned4 && step == 4u * K && o0 == 0u && o1 == 4u && o2 == 8u && (K < 4 || o3 == 12u) &&
+        (reinterpret_cast<uintptr_t>(out) & 15u) == 0u;
     uint32_t done = 0;
     int32_t carry[K];
 #pragma unroll
@@ -610,7 +694,7 @@ __global__ void __launch_bounds__(kThreads, kVec == 1 ? 4 : 3) decode_chunks_seq
       }
       const uint32_t n_mine = v0 < take ? min(VT, take - v0) : 0u;
       if (badk < n_mine) report_error(L.err, badcode);
-      const uint32_t phase = done % K;
+      const uint32_t phase = (done + v0) % K;
       const SegK<K> mine = seg_to_global<K>(run_reduce_local<K, VTMAX>(d, nanm, n_mine), phase);
       SegK<K> total;
       const SegK<K> ex = cta_seg_exclusive<K>(mine, sh, &total);
@@ -618,13 +702,17 @@ __global__ void __launch_bounds__(kThreads, kVec == 1 ? 4 : 3) decode_chunks_seq
       int32_t cur[K];
 #pragma unroll
       for (int j = 0; j < K; ++j) cur[j] = ((ex.rst >> j) & 1u) ? ex.sum[j] : wadd32(carry[j], ex.sum[j]);
-      if (aligned4) run_emit_local<K, VTMAX, true>(d, nanm, n_mine, cur, phase, out, (done + v0) / K, step, mul, off);
-      else run_emit_local<K, VTMAX, false>(d, nanm, n_mine, cur, phase, out, (done + v0) / K, step, mul, off);
+      if (dense) run_emit_local<K, VTMAX, 2>(d, nanm, n_mine, cur, phase, out, (done + v0) / K, step, mul, off, ostage + (done & 3u) + v0);
+      else if (aligned4) run_emit_local<K, VTMAX, 1>(d, nanm, n_mine, cur, phase, out, (done + v0) / K, step, mul, off);
+      else run_emit_local<K, VTMAX, 0>(d, nanm, n_mine, cur, phase, out, (done + v0) / K, step, mul, off);
 #pragma unroll
       for (int j = 0; j < K; ++j) carry[j] = ((total.rst >> j) & 1u) ? total.sum[j] : wadd32(carry[j], total.sum[j]);
       TRACE(5);
+      __syncthreads();  // tile_bytes / start16 / sh are reused by the next tile; ostage is complete
+      // the staged floats leave while the next tile is loaded and ranked (ostage is not written again before the
+      // barriers of the next tile's scans)
+      if (dense) copy_out_dense(ostage, out, done, take);
       done += take;
-      __syncthreads();  // tile_bytes / start16 / sh are reused by the next tile
       TRACE(6);
     }
     if (done < V && threadIdx.x == 0) report_error(L.err, DEV_ERR_TRUNCATED);  // v4_codec.cpp:102-104
@@ -632,7 +720,7 @@ __global__ void __launch_bounds__(kThreads, kVec == 1 ? 4 : 3) decode_chunks_seq
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-size_t decode_tiles_smem_bytes() { return kTLook + kTB + 16 + 2 * static_cast<size_t>(kThreads) + 64; }
+size_t decode_tiles_smem_bytes() { return static_cast<size_t>(kOStageOffset) + kOStageBytes; }
 uint32_t decode_tile_bytes() { return kTB; }
 
 template <int K>
@@ -644,14 +732,14 @@ static int launch_floatn_decode(const RegOp& op, const DecLaunch& L, bool sequen
     auto k = decode_chunks_seq_kernel<K>;
     if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess) return -1;
     int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kThreads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kDT, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
     const uint32_t grid = min(L.n_chunks_total, static_cast<uint32_t>(per_sm * sm_count));
     cudaMemsetAsync(L.chunk_counter, 0, sizeof(uint32_t), stream);
-    k<<<grid, kThreads, smem, stream>>>(L, op.dec_mul_f[0], op.dec_mul_f[1], op.dec_mul_f[2], m3, op.offset[0], op.offset[1], op.offset[2], o3);
+    k<<<grid, kDT, smem, stream>>>(L, op.dec_mul_f[0], op.dec_mul_f[1], op.dec_mul_f[2], m3, op.offset[0], op.offset[1], op.offset[2], o3);
   } else {
     auto k = decode_tiles_kernel<K>;
     if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess) return -1;
-    k<<<L.tile_grid, kThreads, smem, stream>>>(L, op.dec_mul_f[0], op.dec_mul_f[1], op.dec_mul_f[2], m3, op.offset[0], op.offset[1], op.offset[2], o3);
+    k<<<L.tile_grid, kDT, smem, stream>>>(L, op.dec_mul_f[0], op.dec_mul_f[1], op.dec_mul_f[2], m3, op.offset[0], op.offset[1], op.offset[2], o3);
   }
   return 1;
 }
