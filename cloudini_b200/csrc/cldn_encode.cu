@@ -224,6 +224,9 @@ __device__ __forceinline__ uint32_t varint_word_28(uint32_t u) {
   return x | ((h + 0x007F7F7Fu) & 0x00808080u);
 }
 
+#ifndef CLDN_ENC_BYTESTORE
+#define CLDN_ENC_BYTESTORE 1
+#endif
 template <int N, int I, bool VEC4, int MINB>
 __global__ void __launch_bounds__(kThreads, MINB) encode_floatn_kernel(const EncLaunch L, const FloatNParams P) {
   extern __shared__ __align__(16) uint8_t dyn_smem[];
@@ -303,14 +306,18 @@ __global__ void __launch_bounds__(kThreads, MINB) encode_floatn_kernel(const Enc
       // zz + 1 saturated at 2^32 - 1: the only wrapping input (zz = 2^32 - 1, a 5-byte varint) lands in the slow path
       // either way, and lengths stay exact (bits >= 29 -> 5 bytes); NaN lanes become the single 0x00 byte
       const uint32_t u = nan ? 0u : min(zz, 0xFFFFFFFEu) + 1u;
-      const uint32_t b = 31u - __clz(u | 1u);
+      uint32_t b;  // index of the highest set bit (bfind, not 31 - clz: one instruction)
+      asm("bfind.u32 %0, %1;" : "=r"(b) : "r"(u | 1u));
       bmax = max(bmax, b);
       const uint32_t lenm1 = (b * 37u) >> 8;            // floor(b / 7) for b <= 34
       // 7-bit groups -> bytes: adding the masked upper part to itself shifts it left by one, three times
       uint32_t x = u + (u & 0xFFFFFF80u);
       x = x + (x & 0xFFFF8000u);
       x = x + (x & 0xFF800000u);
-      r[i][k] = x | (0x00808080u >> (24u - 8u * min(lenm1, 3u)));  // continuation flags below the top byte
+      // continuation flags below the top byte; lenm1 == 4 (slow path, r unused) shifts everything out: PTX shr clamps
+      uint32_t fl;
+      asm("shr.b32 %0, %1, %2;" : "=r"(fl) : "r"(0x00808080u), "r"(24u - 8u * lenm1));
+      r[i][k] = x | fl;
       acc += lenm1 + 1u;
       if (k < N - 1) packed |= acc << (k == 0 ? 0 : k == 1 ? 3 : 7);
     }
@@ -356,6 +363,25 @@ __global__ void __launch_bounds__(kThreads, MINB) encode_floatn_kernel(const Enc
   }
 
   // ---- phase 2: pack bytes into the staging buffer at tile-local offsets ----
+#if CLDN_ENC_BYTESTORE
+  if (!any_big) {
+    // every value leaves with byte stores straight at its position: a byte exists iff the one below it carries the
+    // continuation flag, so no record assembly, no shifts across word boundaries and no neighbour merging is needed
+#pragma unroll
+    for (int i = 0; i < I; ++i) {
+      uint8_t* dst = stage + wbase + (meta[i] >> 16);
+#pragma unroll
+      for (int k = 0; k < N; ++k) {
+        const uint32_t pre = k == 0 ? 0u : k == 1 ? (meta[i] & 7u) : k == 2 ? ((meta[i] >> 3) & 15u) : ((meta[i] >> 7) & 15u);
+        uint8_t* q = dst + pre;
+        const uint32_t x = r[i][k];
+        q[0] = static_cast<uint8_t>(x);
+        if (x & 0x80u) q[1] = static_cast<uint8_t>(x >> 8);
+        if (x & 0x8000u) q[2] = static_cast<uint8_t>(x >> 16);
+        if (x & 0x800000u) q[3] = static_cast<uint8_t>(x >> 24);
+      }
+    }
+#else
   if (!any_big) {
     uint32_t tail_carry = 0;  // partial last word of the previous iteration's lane 31
 #pragma unroll
@@ -427,6 +453,7 @@ __global__ void __launch_bounds__(kThreads, MINB) encode_floatn_kernel(const Enc
         }
       }
     }
+#endif
   } else {
     // slow path (some |delta| >= 2^27): re-evaluate byte-wise, exactly like the generic kernel
 #pragma unroll 1
