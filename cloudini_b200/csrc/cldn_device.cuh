@@ -360,6 +360,55 @@ __device__ __forceinline__ uint64_t tile_lookback(uint64_t* status, uint32_t fir
   return exclusive;
 }
 
+// The same look-back as a resumable state machine (one full warp): begin() publishes the aggregate, issue() requests
+// the status words of the current 32-tile window, eval() consumes them if every tile of the window has published at
+// least its aggregate (otherwise the window is simply asked for again later), finish() blocks until the exclusive
+// prefix is known and publishes the inclusive one. The caller interleaves issue()/eval() with useful work so that the
+// wait for the slowest predecessor does not stall the CTA.
+struct LookbackPoll {
+  int64_t idx;         // nearest tile not yet accounted for
+  uint64_t exclusive;  // sum of the tiles in (idx, me)
+  uint64_t s;          // this lane's status word in flight
+  bool done;
+
+  __device__ __forceinline__ void begin(uint64_t* status, uint32_t first, uint32_t me, uint32_t epoch, uint64_t aggregate) {
+    const int lane = threadIdx.x & 31;
+    exclusive = 0;
+    idx = static_cast<int64_t>(me) - 1;
+    done = (me == first);
+    s = 0;
+    if (lane == 0) st_relaxed_u64(status + me, pack_status(done ? kFlagIncl : kFlagAgg, epoch, aggregate));
+  }
+  __device__ __forceinline__ void issue(const uint64_t* status, uint32_t first, uint32_t epoch) {
+    if (done) return;
+    const int64_t mine = idx - (threadIdx.x & 31);
+    s = pack_status(kFlagIncl, epoch, 0);  // virtual tiles before `first` contribute an inclusive 0
+    if (mine >= static_cast<int64_t>(first)) s = ld_relaxed_u64(status + mine);
+  }
+  __device__ __forceinline__ void eval(uint32_t epoch) {
+    if (done) return;
+    const int lane = threadIdx.x & 31;
+    const uint32_t flag = status_flag(s, epoch);
+    if (!__all_sync(0xffffffffu, flag != 0u)) return;  // somebody in the window has not published yet: ask again later
+    const uint32_t incl_mask = __ballot_sync(0xffffffffu, flag == kFlagIncl);
+    const int stop = incl_mask ? (__ffs(incl_mask) - 1) : 31;
+    uint64_t v = (lane <= stop) ? status_value(s) : 0;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    exclusive += v;
+    if (incl_mask) done = true; else idx -= 32;
+  }
+  __device__ __forceinline__ uint64_t finish(uint64_t* status, uint32_t first, uint32_t me, uint32_t epoch, uint64_t aggregate) {
+    const bool was_first = (me == first);
+    while (!done) {
+      issue(status, first, epoch);
+      eval(epoch);
+    }
+    if (!was_first && (threadIdx.x & 31) == 0) st_relaxed_u64(status + me, pack_status(kFlagIncl, epoch, exclusive + aggregate));
+    return exclusive;
+  }
+};
+
 // Spins until tile `t` has published its inclusive prefix and returns it (one thread).
 __device__ __forceinline__ uint64_t wait_inclusive(const uint64_t* status, uint32_t t, uint32_t epoch) {
   uint64_t s;

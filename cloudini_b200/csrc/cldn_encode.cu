@@ -224,9 +224,6 @@ __device__ __forceinline__ uint32_t varint_word_28(uint32_t u) {
   return x | ((h + 0x007F7F7Fu) & 0x00808080u);
 }
 
-#ifndef CLDN_ENC_BYTESTORE
-#define CLDN_ENC_BYTESTORE 1
-#endif
 template <int N, int I, bool VEC4, int MINB>
 __global__ void __launch_bounds__(kThreads, MINB) encode_floatn_kernel(const EncLaunch L, const FloatNParams P) {
   extern __shared__ __align__(16) uint8_t dyn_smem[];
@@ -280,7 +277,7 @@ __global__ void __launch_bounds__(kThreads, MINB) encode_floatn_kernel(const Enc
   }
 
   // ---- phase 1: quantise, delta, varint bytes (as words), per-point sizes ----
-  uint32_t r[I][N];   // LEB128 bytes of each value (<= 4 bytes on the fast path), 0 for the NaN marker
+  uint32_t r[I][N];   // zigzag + 1 of each value (0 for the NaN marker)
   // one word of bookkeeping per point: [2:0] len(v0)  [6:3] len(v0..v1)  [10:7] len(v0..v2)  [15:11] total length
   // [31:16] byte offset of the point inside the warp's run (filled in after the scan)
   uint32_t meta[I];
@@ -310,14 +307,7 @@ __global__ void __launch_bounds__(kThreads, MINB) encode_floatn_kernel(const Enc
       asm("bfind.u32 %0, %1;" : "=r"(b) : "r"(u | 1u));
       bmax = max(bmax, b);
       const uint32_t lenm1 = (b * 37u) >> 8;            // floor(b / 7) for b <= 34
-      // 7-bit groups -> bytes: adding the masked upper part to itself shifts it left by one, three times
-      uint32_t x = u + (u & 0xFFFFFF80u);
-      x = x + (x & 0xFFFF8000u);
-      x = x + (x & 0xFF800000u);
-      // continuation flags below the top byte; lenm1 == 4 (slow path, r unused) shifts everything out: PTX shr clamps
-      uint32_t fl;
-      asm("shr.b32 %0, %1, %2;" : "=r"(fl) : "r"(0x00808080u), "r"(24u - 8u * lenm1));
-      r[i][k] = x | fl;
+      r[i][k] = u;  // the LEB128 bytes are formed in the packing loop, after the tile's size has been published
       acc += lenm1 + 1u;
       if (k < N - 1) packed |= acc << (k == 0 ? 0 : k == 1 ? 3 : 7);
     }
@@ -355,105 +345,44 @@ __global__ void __launch_bounds__(kThreads, MINB) encode_floatn_kernel(const Enc
     if (w < warp) wbase += x;
     total += x;
   }
-  // ---- tile base: warp 0 publishes the aggregate and resolves the look-back now, so that its wait overlaps with the
-  //      other warps' packing (warp 0 packs afterwards) ----
-  if (threadIdx.x < 32) {
-    const uint64_t ex = tile_lookback(L.status, F.tile_begin, tile, L.epoch, total);
-    if (threadIdx.x == 0) s_excl = ex;
+  // ---- tile base: warp 0 publishes the aggregate now and polls the look-back window between its packing
+  //      iterations, so that waiting for the slowest predecessor overlaps with useful work ----
+  LookbackPoll lb;
+  if (warp == 0) {
+    lb.begin(L.status, F.tile_begin, tile, L.epoch, total);
+    lb.issue(L.status, F.tile_begin, L.epoch);
   }
 
   // ---- phase 2: pack bytes into the staging buffer at tile-local offsets ----
-#if CLDN_ENC_BYTESTORE
   if (!any_big) {
     // every value leaves with byte stores straight at its position: a byte exists iff the one below it carries the
     // continuation flag, so no record assembly, no shifts across word boundaries and no neighbour merging is needed
 #pragma unroll
     for (int i = 0; i < I; ++i) {
+      if (warp == 0) {  // the status words asked for one iteration ago have arrived by now
+        lb.eval(L.epoch);
+        lb.issue(L.status, F.tile_begin, L.epoch);
+      }
       uint8_t* dst = stage + wbase + (meta[i] >> 16);
 #pragma unroll
       for (int k = 0; k < N; ++k) {
         const uint32_t pre = k == 0 ? 0u : k == 1 ? (meta[i] & 7u) : k == 2 ? ((meta[i] >> 3) & 15u) : ((meta[i] >> 7) & 15u);
+        const uint32_t nxt = k == 0 ? (meta[i] & 7u) : k == 1 ? ((meta[i] >> 3) & 15u) : k == 2 ? ((meta[i] >> 7) & 15u) : ((meta[i] >> 11) & 31u);
         uint8_t* q = dst + pre;
-        const uint32_t x = r[i][k];
+        // 7-bit groups -> bytes: adding the masked upper part to itself shifts it left by one, three times
+        const uint32_t u = r[i][k];
+        uint32_t x = u + (u & 0xFFFFFF80u);
+        x = x + (x & 0xFFFF8000u);
+        x = x + (x & 0xFF800000u);
+        uint32_t fl;  // continuation flags below the top byte (length 1..4 here)
+        asm("shr.b32 %0, %1, %2;" : "=r"(fl) : "r"(0x00808080u), "r"(32u - 8u * (nxt - pre)));
+        x |= fl;
         q[0] = static_cast<uint8_t>(x);
         if (x & 0x80u) q[1] = static_cast<uint8_t>(x >> 8);
         if (x & 0x8000u) q[2] = static_cast<uint8_t>(x >> 16);
         if (x & 0x800000u) q[3] = static_cast<uint8_t>(x >> 24);
       }
     }
-#else
-  if (!any_big) {
-    uint32_t tail_carry = 0;  // partial last word of the previous iteration's lane 31
-#pragma unroll
-    for (int i = 0; i < I; ++i) {
-      const uint32_t l0 = meta[i] & 7u;
-      const uint32_t c2 = (meta[i] >> 3) & 15u;           // len(v0) + len(v1): 2..8
-      const uint32_t l2 = ((meta[i] >> 7) & 15u) - c2;
-      const uint32_t len = (meta[i] >> 11) & 31u;         // 3..16
-      // A = value0 | value1 << 8*l0  (<= 8 bytes)
-      const uint32_t sa = 8u * l0;
-      const uint32_t a_lo = r[i][0] | (sa < 32u ? (r[i][1] << sa) : 0u);
-      const uint32_t a_hi = __funnelshift_lc(r[i][1], 0u, sa);
-      // B = value2 | value3 << 8*l2  (<= 8 bytes)
-      uint32_t b_lo = r[i][2], b_hi = 0u;
-      if (N == 4) {
-        const uint32_t sb = 8u * l2;
-        b_lo |= (sb < 32u ? (r[i][N - 1] << sb) : 0u);
-        b_hi = __funnelshift_lc(r[i][N - 1], 0u, sb);
-      }
-      // record = A | B << 8*(l0+l1): split the shift into a word part and a 8..32-bit part
-      const uint32_t ws = (c2 - 1u) >> 2;           // 0 | 1
-      const uint32_t bs = 8u * (((c2 - 1u) & 3u) + 1u);  // 8,16,24,32
-      const uint32_t x0 = bs < 32u ? (b_lo << bs) : 0u;
-      const uint32_t x1 = __funnelshift_lc(b_lo, b_hi, bs);
-      const uint32_t x2 = __funnelshift_lc(b_hi, 0u, bs);
-      uint32_t w0 = a_lo | (ws ? 0u : x0);
-      uint32_t w1 = a_hi | (ws ? x0 : x1);
-      uint32_t w2 = ws ? x1 : x2;
-      uint32_t w3 = ws ? x2 : 0u;
-      // byte position inside the tile; shift the record to its position inside the first word
-      const uint32_t pos = wbase + (meta[i] >> 16);
-      const uint32_t s = pos & 3u, sh = 8u * s;
-      const uint32_t S0 = w0 << sh;
-      const uint32_t S1 = __funnelshift_l(w0, w1, sh);
-      const uint32_t S2 = __funnelshift_l(w1, w2, sh);
-      const uint32_t S3 = __funnelshift_l(w2, w3, sh);
-      const uint32_t S4 = __funnelshift_l(w3, 0u, sh);
-      const uint32_t nw = (s + len + 3u) >> 2;      // words touched: 1..5
-      const uint32_t e = (pos + len) & 3u;          // != 0: last word is shared with the next point
-      // last word touched = S[nw - 1]: two-level select on the bits of (nw - 1)
-      const uint32_t li = nw - 1u;
-      const uint32_t t01 = (li & 1u) ? S1 : S0, t23 = (li & 1u) ? S3 : S2;
-      uint32_t tailw = (li & 4u) ? S4 : ((li & 2u) ? t23 : t01);
-      if (e == 0u) tailw = 0u;
-      uint32_t headw = __shfl_up_sync(0xffffffffu, tailw, 1);
-      if (lane == 0) headw = tail_carry;
-      tail_carry = __shfl_sync(0xffffffffu, tailw, 31);
-      {
-        const uint32_t W0 = pos >> 2;
-        const bool first_of_warp = (i == 0 && lane == 0);
-        const bool last_of_warp = (i == I - 1 && lane == 31);
-        const uint32_t full = (e != 0u) ? nw - 1u : nw;  // words I own completely (tail word belongs to the next point)
-        if (first_of_warp && s != 0u) {
-          // the first word also holds bytes of the previous warp's last point: byte stores for my part
-          for (uint32_t b = s; b < 4u; ++b) stage[4u * W0 + b] = static_cast<uint8_t>(S0 >> (8u * b));
-        } else if (full > 0u) {
-          stage32[W0] = S0 | headw;
-        }
-        if (full > 1u) stage32[W0 + 1] = S1;
-        if (full > 2u) stage32[W0 + 2] = S2;
-        if (full > 3u) stage32[W0 + 3] = S3;
-        if (full > 4u) stage32[W0 + 4] = S4;
-        if (last_of_warp && e != 0u) {
-          // nobody in this warp follows: byte stores for my part of the shared word
-          const uint32_t base = 4u * (W0 + nw - 1u);
-          const uint32_t tw = (nw == 1u) ? (S0 | headw) : tailw;
-          const uint32_t b0 = (nw == 1u) ? s : 0u;
-          for (uint32_t b = b0; b < e; ++b) stage[base + b] = static_cast<uint8_t>(tw >> (8u * b));
-        }
-      }
-    }
-#endif
   } else {
     // slow path (some |delta| >= 2^27): re-evaluate byte-wise, exactly like the generic kernel
 #pragma unroll 1
@@ -478,6 +407,10 @@ __global__ void __launch_bounds__(kThreads, MINB) encode_floatn_kernel(const Enc
         }
       }
     }
+  }
+  if (warp == 0) {
+    const uint64_t ex = lb.finish(L.status, F.tile_begin, tile, L.epoch, total);
+    if (lane == 0) s_excl = ex;
   }
   __syncthreads();
   finish_tile<kThreads * I>(L, F, fi, t, stage, total, s_excl);
