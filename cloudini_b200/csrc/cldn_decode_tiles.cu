@@ -199,17 +199,28 @@ __device__ __forceinline__ SegK<K> run_reduce_local(const int32_t (&d)[VTMAX], u
   }
   return m;
 }
+// out[l] = in[(l + phase) % K]: a two-stage barrel rotation (K == 4) / two selects per element (K == 3)
+template <int K, typename T>
+__device__ __forceinline__ void rotate_k(const T (&in)[K], uint32_t phase, T (&out)[K]) {
+  if (K == 4) {
+    const bool p1 = phase & 1u, p2 = phase & 2u;
+    T t[K];
+#pragma unroll
+    for (int l = 0; l < K; ++l) t[l] = p1 ? in[(l + 1) % K] : in[l];
+#pragma unroll
+    for (int l = 0; l < K; ++l) out[l] = p2 ? t[(l + 2) % K] : t[l];
+  } else {
+    const bool p1 = phase == 1u, p2 = phase == 2u;
+#pragma unroll
+    for (int l = 0; l < K; ++l) out[l] = p1 ? in[(l + 1) % K] : (p2 ? in[(l + 2) % K] : in[l]);
+  }
+}
 // local slot l -> global field (l + phase) % K
 template <int K>
 __device__ __forceinline__ SegK<K> seg_to_global(const SegK<K>& a, uint32_t phase) {
-  SegK<K> r = seg_identity<K>();
-#pragma unroll
-  for (int l = 0; l < K; ++l) {
-#pragma unroll
-    for (int g = 0; g < K; ++g) {
-      if (static_cast<uint32_t>(g) == (l + phase) % K) { r.sum[g] = a.sum[l]; r.rst |= ((a.rst >> l) & 1u) << g; }
-    }
-  }
+  SegK<K> r;
+  rotate_k<K, int32_t>(a.sum, (K - phase) % K, r.sum);  // r.sum[g] = a.sum[(g - phase) mod K]
+  r.rst = ((a.rst << phase) | (a.rst >> (K - phase))) & ((1u << K) - 1u);
   return r;
 }
 // MODE 0: any layout (byte-wise stores, skipped fields honoured); 1: 4-byte aligned fields, direct 4-byte stores;
@@ -223,16 +234,13 @@ __device__ __forceinline__ void run_emit_local(const int32_t (&d)[VTMAX], unsign
   constexpr bool ALIGNED4 = MODE >= 1;
   // rotate the running values and the per-field constants into local numbering
   int32_t cur[K];
-  float lmul[K];
-  uint32_t loff[K];
+  float lmul[K], gmul[K];
+  uint32_t loff[K], goff[K];
 #pragma unroll
-  for (int l = 0; l < K; ++l) {
-    cur[l] = 0; lmul[l] = 0.f; loff[l] = 0;
-#pragma unroll
-    for (int g = 0; g < K; ++g) {
-      if (static_cast<uint32_t>(g) == (l + phase) % K) { cur[l] = cur_global[g]; lmul[l] = mul[g]; loff[l] = off[g]; }
-    }
-  }
+  for (int g = 0; g < K; ++g) { gmul[g] = mul[g]; goff[g] = off[g]; }
+  rotate_k<K, int32_t>(cur_global, phase, cur);
+  rotate_k<K, float>(gmul, phase, lmul);
+  rotate_k<K, uint32_t>(goff, phase, loff);
 #pragma unroll
   for (int k = 0; k < VTMAX; ++k) {
     if (k >= static_cast<int>(n)) break;
@@ -271,7 +279,11 @@ __device__ __forceinline__ void copy_out_dense(const uint32_t* ostage, uint8_t* 
 }
 
 __device__ __forceinline__ uint64_t gtimer() { uint64_t t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#ifdef CLDN_TRACE  // development builds only (tools_trace_decode.py): per-phase timestamps of every tile
 #define TRACE(slot) do { if (L.trace && threadIdx.x == 0) L.trace[static_cast<size_t>(gt) * 8 + (slot)] = gtimer(); } while (0)
+#else
+#define TRACE(slot) do { (void)gt; } while (0)
+#endif
 
 // ---- tile building blocks shared by the tile-parallel and the chunk-sequential kernel -------------------------------
 // Loads tile `t` of a chunk body into tile_bytes (with a 16-byte look-behind) and returns this thread's terminator mask.
@@ -338,6 +350,51 @@ __device__ __forceinline__ uint32_t tile_load_masks(uint8_t* tile_bytes, const u
 // CTA scan of the terminator counts; then every run t of VT consecutive values gets the tile byte index (biased by
 // kTLook) of its first byte in start16[t]: value q starts right behind terminator q-1, which is found in the owner's
 // 16-bit mask. No per-value position list is built. Returns the number of values in the tile; ends with a barrier.
+// kNthBit[b] holds, 4 bits each, the positions of the set bits of the byte b in increasing order.
+__device__ const uint32_t kNthBit[256] = {
+    0x00000000u, 0x00000000u, 0x00000001u, 0x00000010u, 0x00000002u, 0x00000020u, 0x00000021u, 0x00000210u,
+    0x00000003u, 0x00000030u, 0x00000031u, 0x00000310u, 0x00000032u, 0x00000320u, 0x00000321u, 0x00003210u,
+    0x00000004u, 0x00000040u, 0x00000041u, 0x00000410u, 0x00000042u, 0x00000420u, 0x00000421u, 0x00004210u,
+    0x00000043u, 0x00000430u, 0x00000431u, 0x00004310u, 0x00000432u, 0x00004320u, 0x00004321u, 0x00043210u,
+    0x00000005u, 0x00000050u, 0x00000051u, 0x00000510u, 0x00000052u, 0x00000520u, 0x00000521u, 0x00005210u,
+    0x00000053u, 0x00000530u, 0x00000531u, 0x00005310u, 0x00000532u, 0x00005320u, 0x00005321u, 0x00053210u,
+    0x00000054u, 0x00000540u, 0x00000541u, 0x00005410u, 0x00000542u, 0x00005420u, 0x00005421u, 0x00054210u,
+    0x00000543u, 0x00005430u, 0x00005431u, 0x00054310u, 0x00005432u, 0x00054320u, 0x00054321u, 0x00543210u,
+    0x00000006u, 0x00000060u, 0x00000061u, 0x00000610u, 0x00000062u, 0x00000620u, 0x00000621u, 0x00006210u,
+    0x00000063u, 0x00000630u, 0x00000631u, 0x00006310u, 0x00000632u, 0x00006320u, 0x00006321u, 0x00063210u,
+    0x00000064u, 0x00000640u, 0x00000641u, 0x00006410u, 0x00000642u, 0x00006420u, 0x00006421u, 0x00064210u,
+    0x00000643u, 0x00006430u, 0x00006431u, 0x00064310u, 0x00006432u, 0x00064320u, 0x00064321u, 0x00643210u,
+    0x00000065u, 0x00000650u, 0x00000651u, 0x00006510u, 0x00000652u, 0x00006520u, 0x00006521u, 0x00065210u,
+    0x00000653u, 0x00006530u, 0x00006531u, 0x00065310u, 0x00006532u, 0x00065320u, 0x00065321u, 0x00653210u,
+    0x00000654u, 0x00006540u, 0x00006541u, 0x00065410u, 0x00006542u, 0x00065420u, 0x00065421u, 0x00654210u,
+    0x00006543u, 0x00065430u, 0x00065431u, 0x00654310u, 0x00065432u, 0x00654320u, 0x00654321u, 0x06543210u,
+    0x00000007u, 0x00000070u, 0x00000071u, 0x00000710u, 0x00000072u, 0x00000720u, 0x00000721u, 0x00007210u,
+    0x00000073u, 0x00000730u, 0x00000731u, 0x00007310u, 0x00000732u, 0x00007320u, 0x00007321u, 0x00073210u,
+    0x00000074u, 0x00000740u, 0x00000741u, 0x00007410u, 0x00000742u, 0x00007420u, 0x00007421u, 0x00074210u,
+    0x00000743u, 0x00007430u, 0x00007431u, 0x00074310u, 0x00007432u, 0x00074320u, 0x00074321u, 0x00743210u,
+    0x00000075u, 0x00000750u, 0x00000751u, 0x00007510u, 0x00000752u, 0x00007520u, 0x00007521u, 0x00075210u,
+    0x00000753u, 0x00007530u, 0x00007531u, 0x00075310u, 0x00007532u, 0x00075320u, 0x00075321u, 0x00753210u,
+    0x00000754u, 0x00007540u, 0x00007541u, 0x00075410u, 0x00007542u, 0x00075420u, 0x00075421u, 0x00754210u,
+    0x00007543u, 0x00075430u, 0x00075431u, 0x00754310u, 0x00075432u, 0x00754320u, 0x00754321u, 0x07543210u,
+    0x00000076u, 0x00000760u, 0x00000761u, 0x00007610u, 0x00000762u, 0x00007620u, 0x00007621u, 0x00076210u,
+    0x00000763u, 0x00007630u, 0x00007631u, 0x00076310u, 0x00007632u, 0x00076320u, 0x00076321u, 0x00763210u,
+    0x00000764u, 0x00007640u, 0x00007641u, 0x00076410u, 0x00007642u, 0x00076420u, 0x00076421u, 0x00764210u,
+    0x00007643u, 0x00076430u, 0x00076431u, 0x00764310u, 0x00076432u, 0x00764320u, 0x00764321u, 0x07643210u,
+    0x00000765u, 0x00007650u, 0x00007651u, 0x00076510u, 0x00007652u, 0x00076520u, 0x00076521u, 0x00765210u,
+    0x00007653u, 0x00076530u, 0x00076531u, 0x00765310u, 0x00076532u, 0x00765320u, 0x00765321u, 0x07653210u,
+    0x00007654u, 0x00076540u, 0x00076541u, 0x00765410u, 0x00076542u, 0x00765420u, 0x00765421u, 0x07654210u,
+    0x00076543u, 0x00765430u, 0x00765431u, 0x07654310u, 0x00765432u, 0x07654320u, 0x07654321u, 0x76543210u};
+// Position of the n-th (0-based) set bit of a mask of up to 32 bits (n < popc(m)).
+__device__ __forceinline__ uint32_t nth_set_bit(uint32_t m, uint32_t n) {
+  uint32_t base = 0;
+#pragma unroll
+  for (int by = 0; by < 2 * kVec - 1; ++by) {
+    const uint32_t c = __popc(m & 0xFFu);
+    if (n >= c) { n -= c; m >>= 8; base += 8u; }
+  }
+  return base + ((__ldg(&kNthBit[m & 0xFFu]) >> (4u * n)) & 7u);
+}
+
 // CTA exclusive scan of one count per thread with a single barrier: every warp re-scans the warp totals itself.
 __device__ __forceinline__ uint32_t tile_count_scan(uint32_t v, uint32_t* scratch, uint32_t* total) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -378,13 +435,9 @@ __device__ __forceinline__ uint32_t tile_rank_starts(uint32_t tmask, const uint8
       while (st > 0 && e - st < 11 && (tile_bytes[st - 1] & 0x80u)) --st;
       start16[0] = static_cast<uint16_t>(st);
     }
-    uint32_t q = (rank / VT + 1u) * VT;  // smallest run start > rank, i.e. the first q with q - 1 >= rank
-    uint32_t m = tmask, skipped = 0;
-    while (q <= rank + c - 1u + 1u && q < tile_cnt) {  // terminator q-1 is one of mine
-      const uint32_t nth = q - 1u - rank;              // 0-based among my terminators
-      while (skipped < nth) { m &= m - 1u; ++skipped; }
-      start16[q / VT] = static_cast<uint16_t>(base + __ffs(m));  // byte after that terminator
-      q += VT;
+    // run starts among my terminators: value q starts right behind terminator q - 1 = my (q - 1 - rank)-th one
+    for (uint32_t q = (rank / VT + 1u) * VT; q <= rank + c && q < tile_cnt; q += VT) {
+      start16[q / VT] = static_cast<uint16_t>(base + nth_set_bit(tmask, q - 1u - rank) + 1u);
     }
   }
   __syncthreads();
