@@ -16,7 +16,7 @@
 namespace cldn {
 
 #ifndef CLDN_KVEC
-#define CLDN_KVEC 1
+#define CLDN_KVEC 2
 #endif
 constexpr int kVec = CLDN_KVEC;  // adjacent 16-byte vectors per thread
 #ifndef CLDN_DT
@@ -24,7 +24,7 @@ constexpr int kVec = CLDN_KVEC;  // adjacent 16-byte vectors per thread
 #endif
 constexpr int kDT = CLDN_DT;     // threads per decode CTA (tile = kDT * 16 * kVec stream bytes)
 #ifndef CLDN_SEQ_MINB
-#define CLDN_SEQ_MINB 4
+#define CLDN_SEQ_MINB (CLDN_KVEC == 1 ? 4 : 3)
 #endif
 constexpr int kTB = kDT * 16 * kVec;  // stream bytes per tile (8192)
 constexpr int kTLook = 16;     // look-behind bytes staged in front of the tile
@@ -473,23 +473,26 @@ __device__ __forceinline__ void tile_decode_run(const uint8_t* tile_bytes, uint3
 #pragma unroll
   for (int k = 0; k < VTMAX; ++k) {
     if (k >= static_cast<int>(n_run)) break;
-    const uint32_t* wp = reinterpret_cast<const uint32_t*>(tile_bytes) + (ptr >> 2);
+    const uint32_t* wp = reinterpret_cast<const uint32_t*>(tile_bytes + (ptr & ~3u));
     const uint32_t lo = __funnelshift_r(wp[0], wp[1], 8u * (ptr & 3u));  // the 4 bytes at ptr
     const uint32_t m = ~lo & 0x80808080u;                                 // terminators among them
     int32_t delta = 0;
     uint32_t len;
     if (m) {
-      const uint32_t tz = __ffs(m);                                       // 8, 16, 24 or 32
-      len = tz >> 3;
-      uint32_t x = lo & (0xFFFFFFFFu >> (32u - tz)) & 0x7F7F7F7Fu;        // the value's bytes without their flags
+      const uint32_t lowbit = m & (0u - m);                               // flag bit of the value's last byte
+      uint32_t hb;
+      asm("bfind.u32 %0, %1;" : "=r"(hb) : "r"(lowbit));                  // 7, 15, 23 or 31
+      len = (hb >> 3) + 1u;
+      uint32_t x = lo & (lowbit * 2u - 1u) & 0x7F7F7F7Fu;                 // the value's bytes without their flags
       x = x - ((x & 0x7F007F00u) >> 1);                                   // 7-bit groups -> 14-bit groups
-      x = (x & 0x3FFFu) | ((x >> 2) & 0x0FFFC000u);                       // -> 28-bit uval
+      x = (x & 0x3FFFu) | ((x >> 2) & 0x0FFFC000u);                       // -> 28-bit uval = zigzag + 1
       if (x == 0u) {  // uval 0: the NaN marker if it is the single byte 0x00, otherwise "unexpected NaN marker"
         if (len == 1u) nanm |= 1ull << k;
         else if (badk == 0xFFFFFFFFu) { badcode = DEV_ERR_NAN_MARKER; badk = k; }
       } else {
-        const uint32_t um = x - 1u;
-        delta = static_cast<int32_t>((um >> 1) ^ (0u - (um & 1u)));
+        // un-zigzag of x - 1: odd x -> x >> 1, even x -> -(x >> 1)
+        const int32_t h = static_cast<int32_t>(x >> 1);
+        delta = (x & 1u) ? h : -h;
       }
     } else {
       const unsigned long long r = decode_wide_at(tile_bytes, ptr);
@@ -577,7 +580,7 @@ __device__ __forceinline__ SegK<K> cta_seg_exclusive(const SegK<K>& mine, TileSh
 
 // ---- tile-parallel kernel: one CTA per 8 KB tile, two decoupled look-backs (small batches / single frames) ----------
 template <int K>
-__global__ void __launch_bounds__(kDT, (kVec == 1 ? 4 : 3) * (256 / kDT)) decode_tiles_kernel(const DecLaunch L, float m0, float m1, float m2, float m3,
+__global__ void __launch_bounds__(kDT, CLDN_SEQ_MINB * (256 / kDT)) decode_tiles_kernel(const DecLaunch L, float m0, float m1, float m2, float m3,
                                                                    uint32_t o0, uint32_t o1, uint32_t o2, uint32_t o3) {
   extern __shared__ __align__(16) uint8_t dyn_smem[];
   __shared__ TileShared sh;
@@ -684,7 +687,7 @@ __global__ void __launch_bounds__(kDT, (kVec == 1 ? 4 : 3) * (256 / kDT)) decode
 // No inter-CTA communication at all: the value count and the per-field running values are carried in shared memory
 // from tile to tile; chunks are claimed from an atomic counter so that the SMs stay balanced.
 template <int K>
-__global__ void __launch_bounds__(kDT, (kVec == 1 ? CLDN_SEQ_MINB : 3) * (256 / kDT)) decode_chunks_seq_kernel(const DecLaunch L, float m0, float m1, float m2, float m3,
+__global__ void __launch_bounds__(kDT, CLDN_SEQ_MINB * (256 / kDT)) decode_chunks_seq_kernel(const DecLaunch L, float m0, float m1, float m2, float m3,
                                                                         uint32_t o0, uint32_t o1, uint32_t o2, uint32_t o3) {
   extern __shared__ __align__(16) uint8_t dyn_smem[];
   __shared__ TileShared sh;
