@@ -152,10 +152,13 @@ __global__ void __launch_bounds__(kThreads) encode_generic_kernel(const EncLaunc
     for (uint32_t i = threadIdx.x; i < sizeof(Plan) / 4; i += blockDim.x) dst[i] = src[i];
   }
   if (blockIdx.x == 0) handle_empty_frames(L);
-  const uint32_t tile = blockIdx.x;
-  const uint32_t fi = L.uniform_tiles ? tile / L.uniform_tiles : find_frame(L.frames, L.n_frames, tile);
+  // Batches of equally sized frames: consecutive CTAs take the same tile of consecutive frames, so the predecessors a
+  // tile has to look back at (same frame) were dispatched n_frames CTAs earlier and have usually published already.
+  // (Still in-order: a tile's predecessors always have a smaller blockIdx.)
+  const uint32_t fi = L.uniform_tiles ? blockIdx.x % L.n_frames : find_frame(L.frames, L.n_frames, blockIdx.x);
   const EncFrame F = L.frames[fi];
-  const uint32_t t = tile - F.tile_begin;
+  const uint32_t t = L.uniform_tiles ? blockIdx.x / L.n_frames : blockIdx.x - F.tile_begin;
+  const uint32_t tile = F.tile_begin + t;  // index of the tile's status word
   const uint32_t T = kThreads * I;
   const uint32_t p0 = t * T + threadIdx.x * I;
   const uint32_t step = L.plan->point_step;
@@ -233,10 +236,13 @@ __global__ void __launch_bounds__(kThreads, MINB) encode_floatn_kernel(const Enc
   uint32_t* stage32 = reinterpret_cast<uint32_t*>(dyn_smem);
 
   if (blockIdx.x == 0) handle_empty_frames(L);
-  const uint32_t tile = blockIdx.x;
-  const uint32_t fi = L.uniform_tiles ? tile / L.uniform_tiles : find_frame(L.frames, L.n_frames, tile);
+  // Batches of equally sized frames: consecutive CTAs take the same tile of consecutive frames, so the predecessors a
+  // tile has to look back at (same frame) were dispatched n_frames CTAs earlier and have usually published already.
+  // (Still in-order: a tile's predecessors always have a smaller blockIdx.)
+  const uint32_t fi = L.uniform_tiles ? blockIdx.x % L.n_frames : find_frame(L.frames, L.n_frames, blockIdx.x);
   const EncFrame F = L.frames[fi];
-  const uint32_t t = tile - F.tile_begin;
+  const uint32_t t = L.uniform_tiles ? blockIdx.x / L.n_frames : blockIdx.x - F.tile_begin;
+  const uint32_t tile = F.tile_begin + t;  // index of the tile's status word
   constexpr uint32_t T = kThreads * I;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t tile_p0 = t * T;
