@@ -524,6 +524,44 @@ __device__ __forceinline__ void tile_decode_run(const uint8_t* tile_bytes, uint3
   }
 }
 
+// Branch-free variant for the common case (every value at most 4 bytes, no malformed NaN marker): returns false if
+// the run has to be decoded again by tile_decode_run (d / nanm are then meaningless). With FUSED the per-field sums of
+// the run (local slot numbering, no NaN reset) are accumulated on the way.
+template <int K, int VTMAX, bool FUSED>
+__device__ __forceinline__ bool tile_decode_run_fast(const uint8_t* tile_bytes, uint32_t ptr, uint32_t n_run, int32_t (&d)[VTMAX],
+                                                     unsigned long long& nanm, int32_t (&sum)[K]) {
+  uint32_t nan_lo = 0, nan_hi = 0, mmin = 0xFFFFFFFFu, badacc = 0;
+#pragma unroll
+  for (int j = 0; j < K; ++j) sum[j] = 0;
+#pragma unroll
+  for (int k = 0; k < VTMAX; ++k) {
+    if (k >= static_cast<int>(n_run)) break;
+    const uint32_t* wp = reinterpret_cast<const uint32_t*>(tile_bytes + (ptr & ~3u));
+    const uint32_t lo = __funnelshift_r(wp[0], wp[1], 8u * (ptr & 3u));  // the 4 bytes at ptr
+    const uint32_t m = ~lo & 0x80808080u;                                 // terminators among them
+    mmin = min(mmin, m);                                                  // 0: a value longer than 4 bytes -> slow path
+    const uint32_t lowbit = m & (0u - m);                                 // flag bit of the value's last byte
+    uint32_t hb;
+    asm("bfind.u32 %0, %1;" : "=r"(hb) : "r"(lowbit));                    // 7, 15, 23 or 31 (all ones if m == 0)
+    const uint32_t lenm1 = (hb >> 3) & 3u;
+    uint32_t x = lo & (lowbit * 2u - 1u) & 0x7F7F7F7Fu;                   // the value's bytes without their flags
+    x = x - ((x & 0x7F007F00u) >> 1);                                     // 7-bit groups -> 14-bit groups
+    x = (x & 0x3FFFu) | ((x >> 2) & 0x0FFFC000u);                         // -> 28-bit uval = zigzag + 1
+    if (x == 0u) {  // NaN marker (must be the single byte 0x00; anything longer is malformed -> slow path reports it)
+      if (k < 32) nan_lo |= 1u << (k & 31); else nan_hi |= 1u << (k & 31);
+      badacc |= lenm1;
+    }
+    // un-zigzag of x - 1: odd x -> x >> 1, even x -> -(x >> 1) = (x * +-1) >> 1; x == 0 gives 0
+    const int32_t sgn = static_cast<int32_t>((x & 1u) * 2u) - 1;
+    const int32_t delta = (static_cast<int32_t>(x) * sgn) >> 1;
+    d[k] = delta;
+    if (FUSED) sum[k % K] = wadd32(sum[k % K], delta);
+    ptr += lenm1 + 1u;
+  }
+  nanm = (static_cast<unsigned long long>(nan_hi) << 32) | nan_lo;
+  return mmin != 0u && badacc == 0u;
+}
+
 // Tile byte index (biased) one past value `idx` of the run that starts at `ptr` (single thread; used for stream_end).
 __device__ __forceinline__ uint32_t run_end_after(const uint8_t* tile_bytes, uint32_t ptr, uint32_t idx) {
   for (uint32_t k = 0; k <= idx; ++k) {
@@ -756,20 +794,26 @@ __global__ void __launch_bounds__(kDT, CLDN_SEQ_MINB * (256 / kDT)) decode_chunk
       const uint32_t tile_cnt = tile_rank_starts<K>(tmask, tile_bytes, start16, sh.scan, &VT);
       TRACE(2);
       const uint32_t v0 = threadIdx.x * VT;
-      const uint32_t n_run = v0 < tile_cnt ? min(VT, tile_cnt - v0) : 0u;
+      const uint32_t take = min(tile_cnt, V - done);
+      const uint32_t n_mine = v0 < take ? min(VT, take - v0) : 0u;  // my values that belong to the regular stream
+      const uint32_t run_ptr = n_mine ? start16[threadIdx.x] : 0u;
       int32_t d[VTMAX];
       unsigned long long nanm;
-      uint32_t badcode, badk;
-      tile_decode_run<VTMAX>(tile_bytes, n_run ? start16[threadIdx.x] : 0u, n_run, d, nanm, badcode, badk);
+      SegK<K> local;  // per-field sums of my run in local slot numbering
+      local.rst = 0;
+      const bool fast_ok = tile_decode_run_fast<K, VTMAX, true>(tile_bytes, run_ptr, n_mine, d, nanm, local.sum);
+      if (!fast_ok) {  // a value longer than 4 bytes or a malformed marker: the careful reader decides
+        uint32_t badcode, badk;
+        tile_decode_run<VTMAX>(tile_bytes, run_ptr, n_mine, d, nanm, badcode, badk);
+        if (badk < n_mine) report_error(L.err, badcode);
+      }
+      if (!fast_ok || nanm != 0ull) local = run_reduce_local<K, VTMAX>(d, nanm, n_mine);  // sums with NaN resets
       TRACE(3);
-      const uint32_t take = min(tile_cnt, V - done);
       if (take > 0 && done + take == V && threadIdx.x == (take - 1) / VT) {
         L.stream_end[gc] = static_cast<uint32_t>(tile_b0 + run_end_after(tile_bytes, start16[threadIdx.x], (take - 1) - v0) - kTLook);
       }
-      const uint32_t n_mine = v0 < take ? min(VT, take - v0) : 0u;
-      if (badk < n_mine) report_error(L.err, badcode);
       const uint32_t phase = (done + v0) % K;
-      const SegK<K> mine = seg_to_global<K>(run_reduce_local<K, VTMAX>(d, nanm, n_mine), phase);
+      const SegK<K> mine = seg_to_global<K>(local, phase);
       SegK<K> total;
       const SegK<K> ex = cta_seg_exclusive<K>(mine, sh, &total);
       TRACE(4);
