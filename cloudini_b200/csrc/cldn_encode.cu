@@ -287,38 +287,68 @@ __global__ void __launch_bounds__(kThreads, MINB) encode_floatn_kernel(const Enc
   // one word of bookkeeping per point: [2:0] len(v0)  [6:3] len(v0..v1)  [10:7] len(v0..v2)  [15:11] total length
   // [31:16] byte offset of the point inside the warp's run (filled in after the scan)
   uint32_t meta[I];
-  uint32_t bmax = 0;  // highest set bit of any zz+1; >= 28 means a 5-byte varint -> whole tile takes the byte-wise slow path
+  // Anything the 4-byte fast path cannot represent sends the whole tile to the exact byte-wise path, which recomputes
+  // the sizes too: a zigzag value >= 2^28 - 1 (5-byte varint; `wide` collects the bits of zz and zz + 1) and a product
+  // >= 2^31 (cvt saturates to INT_MAX where the reference's cvtps2dq gives INT_MIN; `smax` tracks the largest product).
+  uint32_t wide = 0;
+  float smax = 0.0f;
 #pragma unroll
   for (int i = 0; i < I; ++i) {
-    const bool valid = (warp_p0 + 32 * i + lane) < F.n_points;
     uint32_t acc = 0, packed = 0;
 #pragma unroll
     for (int k = 0; k < N; ++k) {
       const bool nan = isnan(v[i][k]);
       // NaN input gives q = 0 here (cvt.rni of NaN), which is exactly what the next point must see as "previous"
-      // (field_encoder.cpp:79-82); +inf / overflow give INT_MIN like _mm_cvtps_epi32.
+      // (field_encoder.cpp:79-82)
       const float sc = __fmul_rn(v[i][k], P.mul[k]);
-      int32_t q = __float2int_rn(sc);
-      if (sc >= 2147483648.0f) q = static_cast<int32_t>(0x80000000u);
+      const int32_t q = __float2int_rn(sc);
+      smax = fmaxf(smax, sc);
       // previous point: lane-1 of this iteration; lane 0 takes lane 31 of the previous iteration (one rotate per value)
       const int32_t rot = __shfl_sync(0xffffffffu, q, (lane + 31) & 31);
       const int32_t prev = (lane == 0) ? carry[k] : rot;
       carry[k] = rot;  // only lane 0 uses it (it holds lane 31's value of this iteration)
       const uint32_t d = static_cast<uint32_t>(q) - static_cast<uint32_t>(prev);
       const uint32_t zz = (d << 1) ^ static_cast<uint32_t>(static_cast<int32_t>(d) >> 31);
-      // zz + 1 saturated at 2^32 - 1: the only wrapping input (zz = 2^32 - 1, a 5-byte varint) lands in the slow path
-      // either way, and lengths stay exact (bits >= 29 -> 5 bytes); NaN lanes become the single 0x00 byte
-      const uint32_t u = nan ? 0u : min(zz, 0xFFFFFFFEu) + 1u;
+      // zz + 1 may wrap for zz = 2^32 - 1 (then `wide` has bit 31 from zz); NaN lanes become the single 0x00 byte
+      const uint32_t u = nan ? 0u : zz + 1u;
+      wide |= nan ? 0u : (zz | u);
       uint32_t b;  // index of the highest set bit (bfind, not 31 - clz: one instruction)
       asm("bfind.u32 %0, %1;" : "=r"(b) : "r"(u | 1u));
-      bmax = max(bmax, b);
       const uint32_t lenm1 = (b * 37u) >> 8;            // floor(b / 7) for b <= 34
       r[i][k] = u;  // the LEB128 bytes are formed in the packing loop, after the tile's size has been published
       acc += lenm1 + 1u;
       if (k < N - 1) packed |= acc << (k == 0 ? 0 : k == 1 ? 3 : 7);
     }
-    if (!valid) acc = 0;
     meta[i] = (N == 4) ? (packed | (acc << 11)) : (packed | (acc << 7) | (acc << 11));
+  }
+  // the fast path also assumes a full tile; the (single) partial tile of a frame takes the byte-wise path too
+  const uint32_t big = ((wide >> 28) != 0u || smax >= 2147483648.0f || tile_p0 + T > F.n_points) ? 1u : 0u;
+  const int any_big = __syncthreads_or(static_cast<int>(big));
+  if (any_big) {
+    // exact sizes, evaluated like the reference does (field_encoder.cpp:42-91); the byte-wise emission below follows them
+#pragma unroll 1
+    for (int i = 0; i < I; ++i) {
+      const uint32_t p = warp_p0 + 32 * i + lane;
+      uint32_t len = 0;
+      if (p < F.n_points) {
+        const uint8_t* pt = F.in + static_cast<size_t>(p) * step;
+        const uint8_t* prevp = (p % kChunkPoints) ? pt - step : nullptr;
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+          const float x = __uint_as_float(load_u32(pt + P.offset[k]));
+          if (isnan(x)) { len += 1; continue; }
+          const int32_t q = quant_i32_x86(x, P.mul[k]);
+          int32_t pq = 0;
+          if (prevp) {
+            const float px = __uint_as_float(load_u32(prevp + P.offset[k]));
+            if (!isnan(px)) pq = quant_i32_x86(px, P.mul[k]);
+          }
+          const int32_t d = static_cast<int32_t>(static_cast<uint32_t>(q) - static_cast<uint32_t>(pq));
+          len += varint_len(zigzag_plus1(static_cast<int64_t>(d)));
+        }
+      }
+      meta[i] = len << 11;
+    }
   }
   // ---- warp-level exclusive offsets: 10-bit fields, three iterations per shuffle scan (32 * 20 = 640 < 1024) ----
   uint32_t run = 0;   // bytes of earlier iterations of this warp
@@ -340,10 +370,8 @@ __global__ void __launch_bounds__(kThreads, MINB) encode_floatn_kernel(const Enc
     if (g + 1 < I) { meta[g + 1] |= (run + ((exc >> 10) & 1023u)) << 16; run += (tot >> 10) & 1023u; }
     if (g + 2 < I) { meta[g + 2] |= (run + ((exc >> 20) & 1023u)) << 16; run += (tot >> 20) & 1023u; }
   }
-  // the word-packing fast path assumes a full tile; the (single) partial tile of a frame takes the byte-wise path too
-  const uint32_t big = (bmax >= 28u || tile_p0 + T > F.n_points) ? 1u : 0u;
   if (lane == 0) s_wtot[warp] = run;
-  const int any_big = __syncthreads_or(static_cast<int>(big));
+  __syncthreads();
   uint32_t wbase = 0, total = 0;
 #pragma unroll
   for (int w = 0; w < kThreads / 32; ++w) {
