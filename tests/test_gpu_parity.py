@@ -50,6 +50,25 @@ def test_c1_adversarial(oracle):
     _roundtrip_check(info, f.view(np.uint8), oracle)
 
 
+def test_int_min_delta_and_saturation_tiles(oracle):
+    # delta == INT_MIN (zigzag + 1 wraps in 32 bits), products >= 2^31 (cvt saturates, the reference gives INT_MIN),
+    # -inf, and a NaN right before them (previous value 0): the flagged tiles must re-derive sizes exactly
+    for n, seed in ((5000, 1), (40_000, 2)):
+        info, cloud = synth.cloud_c2(n, seed=seed)
+        f = cloud.view(np.float32).copy().reshape(n, 4)
+        f[0, 0] = np.inf                     # first point of the chunk: previous value is 0 -> delta INT_MIN
+        f[1, 0] = 1.0
+        f[100, 1] = np.nan; f[101, 1] = -np.inf
+        f[2047, 2] = 3.0e6; f[2048, 2] = 3.0e6    # both saturate across a tile boundary: delta 0 after the fix-up
+        f[3000, 3] = 2147483.6               # product just below / above 2^31 after the multiply by 1000
+        f[3001, 3] = 2147483.7
+        f[4000, 0] = -2147483.7
+        if n > 32768:
+            f[32768, 0] = np.inf             # chunk start again
+            f[32769, 0] = np.inf
+        _roundtrip_check(info, f.reshape(-1).view(np.uint8), oracle)
+
+
 def test_c2_full_size_bit_exact(oracle):
     info, cloud = synth.cloud_c2(1_000_000, seed=2)
     blob = _roundtrip_check(info, cloud, oracle)
