@@ -466,7 +466,7 @@ static int floatn_variant() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("CLDN_B200_ENC_VARIANT");
-    v = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 1;
+    v = (e && e[0] >= '0' && e[0] <= '3') ? e[0] - '0' : 1;
   }
   return v;
 }
@@ -568,10 +568,12 @@ int launch_encode_regular(const Plan& plan, const EncLaunch& L, cudaStream_t str
     if (op.lanes == 4) {
       if (variant == 0) return launch_floatn<4, 8, 2>(plan, L, vec4, stream);
       if (variant == 1) return launch_floatn<4, 8, 3>(plan, L, vec4, stream);
+      if (variant == 3) return launch_floatn<4, 8, 4>(plan, L, vec4, stream);
       return launch_floatn<4, 4, 4>(plan, L, vec4, stream);
     }
     if (variant == 0) return launch_floatn<3, 8, 2>(plan, L, false, stream);
     if (variant == 1) return launch_floatn<3, 8, 3>(plan, L, false, stream);
+    if (variant == 3) return launch_floatn<3, 8, 4>(plan, L, false, stream);
     return launch_floatn<3, 4, 4>(plan, L, false, stream);
   }
   const EncLaunch& LL = L;
