@@ -9,5 +9,5 @@ try:
 except Exception:
     print("%-14s FAILED: %s" % (sys.argv[1], " | ".join(open('/tmp/vb.out').read().strip().splitlines()[-3:])[:400]))
     sys.exit(0)
-print("%-14s enc_ms %.4f dec_ms %.4f enc_frac %.3f dec_frac %.3f parity %s value %.0f" % (sys.argv[1], d["config"]["encode_ms_per_step"], d["config"]["decode_ms_per_step"], d["roofline"]["frac"], d["roofline"]["decode"]["frac"], d["config"]["parity"], d["value"]))
+print("%-14s enc_ms %.4f dec_ms %.4f enc_frac %.3f dec_frac %.3f parity %s value %.0f" % (sys.argv[1], d["config"]["encode_ms_per_step"], d["config"]["decode_ms_per_step"], d["roofline"]["encode"]["frac"], d["roofline"]["frac"], d["config"]["parity"], d["value"]))
 PY

@@ -5,6 +5,6 @@ for v in 0 1 2; do
   python - <<PY
 import json
 d = json.load(open('/tmp/vb.json'))
-print("variant $v enc_ms %.4f dec_ms %.4f enc_frac %.3f dec_frac %.3f parity %s" % (d["config"]["encode_ms_per_step"], d["config"]["decode_ms_per_step"], d["roofline"]["frac"], d["roofline"]["decode"]["frac"], d["config"]["parity"]))
+print("variant $v enc_ms %.4f dec_ms %.4f enc_frac %.3f dec_frac %.3f parity %s" % (d["config"]["encode_ms_per_step"], d["config"]["decode_ms_per_step"], d["roofline"]["encode"]["frac"], d["roofline"]["frac"], d["config"]["parity"]))
 PY
 done
