@@ -654,6 +654,8 @@ struct cldn_decoder {
   DevBuf<uint64_t> d_tstatus;
   DevBuf<uint64_t> d_trace;
   DevBuf<uint32_t> d_counter;
+  DevBuf<uint64_t> d_chunk_desc;  // chunk-sequential kernel: self-validating chunk descriptors (see walk_frame_publish)
+  uint32_t desc_tag = 0;
   CopyPipeline pipe;
   uint32_t epoch = 0;
 };
@@ -744,6 +746,7 @@ static int decode_batch_device(cldn_decoder* d, const cldn_info_t& info, size_t 
   L.chunk_frame = nullptr; L.tile_chunk = nullptr;
   L.chunk_tiles = nullptr; L.chunk_tile_begin = nullptr; L.stream_end = nullptr; L.tstatus = nullptr; L.tsums = nullptr;
   L.tile_capacity = 0; L.tile_grid = 0; L.epoch = 0; L.trace = nullptr; L.chunk_counter = nullptr; L.sections_only = 0;
+  L.chunk_desc = nullptr; L.desc_tag = 0; L.uniform_chunks = 0;
   if (d->plan.n_sections > 0 && chunks > 0 && !(d->plan.all_varint || d->plan.n_ops == 0)) {
     // V5 with raw / XOR / Gorilla fields in the regular stream: the per-chunk parser records where the sections start
     if (int rc = d->d_stream_end.reserve(static_cast<size_t>(chunks) + 1)) return rc;
@@ -783,6 +786,20 @@ static int decode_batch_device(cldn_decoder* d, const cldn_info_t& info, size_t 
     L.epoch = d->epoch;
     if (int rc = d->d_counter.reserve(4, true)) return rc;
     L.chunk_counter = d->d_counter.p;
+    {
+      const size_t had = d->d_chunk_desc.cap;
+      if (int rc = d->d_chunk_desc.reserve(2 * static_cast<size_t>(chunks) + 2)) return rc;
+      d->desc_tag = (d->desc_tag + 1) & 0xFFFFFFu;
+      if (d->d_chunk_desc.cap != had || d->desc_tag == 0) {  // fresh memory or tag wrap: no stale word may carry a live tag
+        CUDA_TRY(cudaMemsetAsync(d->d_chunk_desc.p, 0, d->d_chunk_desc.cap * sizeof(uint64_t), d->stream));
+        if (d->desc_tag == 0) d->desc_tag = 1;
+      }
+      L.chunk_desc = d->d_chunk_desc.p;
+      L.desc_tag = d->desc_tag;
+      bool uniform = n_frames > 0 && hf[0].n_chunks > 0;
+      for (size_t f = 1; f < n_frames; ++f) uniform = uniform && hf[f].n_chunks == hf[0].n_chunks;
+      L.uniform_chunks = uniform ? hf[0].n_chunks : 0u;
+    }
     if (getenv("CLDN_B200_TRACE")) {
       if (int rc = d->d_trace.reserve(std::max<size_t>(static_cast<size_t>(tiles), static_cast<size_t>(chunks) * 80) * 8 + 8, true)) return rc;
       L.trace = d->d_trace.p;
@@ -824,7 +841,7 @@ void cldn_b200_decoder_destroy(cldn_decoder_t* d) {
   if (d->stream) cudaStreamSynchronize(d->stream);
   d->d_plan.release(); d->d_frames.release(); d->h_frames.release(); d->d_chunk_offsets.release(); d->d_chunk_sizes.release();
   d->d_err.release(); d->h_err.release(); d->d_in.release(); d->d_out.release();
-  d->d_chunk_tiles.release(); d->d_chunk_tile_begin.release(); d->d_stream_end.release(); d->d_tsums.release(); d->d_tstatus.release(); d->d_chunk_frame.release(); d->d_tile_chunk.release(); d->d_trace.release(); d->d_counter.release(); d->pipe.release();
+  d->d_chunk_tiles.release(); d->d_chunk_tile_begin.release(); d->d_stream_end.release(); d->d_tsums.release(); d->d_tstatus.release(); d->d_chunk_frame.release(); d->d_tile_chunk.release(); d->d_trace.release(); d->d_counter.release(); d->d_chunk_desc.release(); d->pipe.release();
   if (d->own_stream && d->stream) cudaStreamDestroy(d->stream);
   delete d;
 }

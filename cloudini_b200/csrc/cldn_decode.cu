@@ -806,8 +806,12 @@ static size_t dec_smem_bytes(bool k32) {
 int launch_decode(const Plan& plan, const DecLaunch& L, cudaStream_t stream) {
   int launches = 0;
   if (L.n_chunks_total == 0 && L.n_frames == 0) return 0;
-  walk_chunks_kernel<<<(L.n_frames + 127) / 128, 128, 0, stream>>>(L);
-  ++launches;
+  // the chunk-sequential FloatN kernel walks the chunk prefixes itself (CTA 0) while the other CTAs already decode
+  const bool fused_walk = L.n_chunks_total > 0 && L.tile_grid > 0 && L.chunk_desc != nullptr && decode_tiles_sequential(L.n_chunks_total);
+  if (!fused_walk) {
+    walk_chunks_kernel<<<(L.n_frames + 127) / 128, 128, 0, stream>>>(L);
+    ++launches;
+  }
   if (L.n_chunks_total > 0 && L.tile_grid > 0) {
     // FloatN-only regular stream: tile-parallel kernel; V5 sections (if any) by the per-chunk kernel afterwards
     const int n = launch_decode_tiles(plan, L, stream);

@@ -739,6 +739,42 @@ __global__ void __launch_bounds__(kDT, CLDN_SEQ_MINB * (256 / kDT)) decode_tiles
   TRACE(7);
 }
 
+// One thread follows the chunk prefixes of frame f (same checks and error codes as walk_chunks_kernel) and publishes
+// each chunk twice: plain tables for the kernels that run afterwards (V5 sections), and two self-validating words
+// ([tag:24][value:40]) that the decoding CTAs of this launch poll -- every word carries its own tag, so no fence orders
+// them. A chunk that cannot be located is published with size 0 (the decoder then reports the truncation).
+__device__ __forceinline__ void walk_frame_publish(const DecLaunch& L, uint32_t f) {
+  const DecFrame F = L.frames[f];
+  const unsigned long long tag = static_cast<unsigned long long>(L.desc_tag) << 40;
+  uint64_t pos = 0;
+  for (uint32_t c = 0; c < F.n_chunks; ++c) {
+    uint64_t body = 0;
+    uint32_t size = 0;
+    if (pos >= F.payload_bytes) {
+      report_error(L.err, DEV_ERR_CHUNK_COUNT);  // "Encoded data ended before all declared points were decoded"
+    } else if (F.payload_bytes - pos < 4) {
+      report_error(L.err, DEV_ERR_TRUNCATED);    // decode<uint32_t>: not enough input data
+      pos = F.payload_bytes;
+    } else {
+      size = load_u32(F.payload + pos);
+      pos += 4;
+      if (size > F.payload_bytes - pos) {
+        report_error(L.err, DEV_ERR_CHUNK_SIZE);  // "Invalid chunk size found while decoding"
+        size = 0;
+        pos = F.payload_bytes;
+      }
+      body = pos;
+      pos += size;
+    }
+    const uint32_t gc = F.chunk_begin + c;
+    L.chunk_offsets[gc] = body;
+    L.chunk_sizes[gc] = size;
+    st_relaxed_u64(L.chunk_desc + 2ull * gc, tag | (body & 0xFFFFFFFFFFull));
+    st_relaxed_u64(L.chunk_desc + 2ull * gc + 1, tag | size);
+  }
+  if (pos < F.payload_bytes) report_error(L.err, DEV_ERR_CHUNK_COUNT);  // "more chunks than declared points"
+}
+
 // ---- chunk-sequential kernel: a persistent CTA walks the tiles of one chunk after the other (large batches) ---------
 // No inter-CTA communication at all: the value count and the per-field running values are carried in shared memory
 // from tile to tile; chunks are claimed from an atomic counter so that the SMs stay balanced.
@@ -752,24 +788,60 @@ __global__ void __launch_bounds__(kDT, CLDN_SEQ_MINB * (256 / kDT)) decode_chunk
   uint16_t* start16 = reinterpret_cast<uint16_t*>(dyn_smem + kTLook + kTB + 16);
   uint32_t* ostage = reinterpret_cast<uint32_t*>(dyn_smem + kOStageOffset);
   constexpr int VTMAX = ((kTB / kDT) + K - 1) / K * K;
+  __shared__ unsigned long long s_desc[2];
   const float mul[4] = {m0, m1, m2, m3};
   const uint32_t off[4] = {o0, o1, o2, o3};
   const uint32_t step = L.plan->point_step;
 
+  // CTA 0 (always the first one resident) follows the u32 chunk prefixes of every frame (cloudini.cpp:645-664, the same
+  // checks as walk_chunks_kernel) and publishes every chunk as soon as it is known; the other CTAs start decoding at
+  // once and only wait for the descriptor of the chunk they claimed.
+  if (blockIdx.x == 0) {
+    for (uint32_t f = threadIdx.x; f < L.n_frames; f += kDT) walk_frame_publish(L, f);
+  }
+
   while (true) {
-    if (threadIdx.x == 0) s_chunk = atomicAdd(L.chunk_counter, 1u);
+    if (threadIdx.x == 0) {
+      const uint32_t i = atomicAdd(L.chunk_counter, 1u);
+      uint32_t gc_ = i;
+      if (i < L.n_chunks_total) {
+        // equal frames: claim chunk-index-major (all chunk 0s first), so early claims never wait long for the walk
+        if (L.uniform_chunks) gc_ = (i % L.n_frames) * L.uniform_chunks + i / L.n_frames;
+        unsigned long long w0, w1;
+        do {
+          w0 = ld_relaxed_u64(L.chunk_desc + 2ull * gc_);
+          w1 = ld_relaxed_u64(L.chunk_desc + 2ull * gc_ + 1);
+        } while (static_cast<uint32_t>(w0 >> 40) != L.desc_tag || static_cast<uint32_t>(w1 >> 40) != L.desc_tag);
+        s_desc[0] = w0 & 0xFFFFFFFFFFull;
+        s_desc[1] = w1 & 0xFFFFFFFFull;
+        L.stream_end[gc_] = 0xFFFFFFFFu;  // set by the tile that decodes the chunk's last regular value
+      }
+      s_chunk = gc_;
+    }
     __syncthreads();
     const uint32_t gc = s_chunk;
     if (gc >= L.n_chunks_total) return;
-    const DecFrame F = L.frames[L.chunk_frame[gc]];
+    uint32_t fidx;
+    if (L.uniform_chunks) {
+      fidx = gc / L.uniform_chunks;
+    } else {
+      uint32_t lo = 0, hi = L.n_frames - 1;
+      while (lo < hi) {
+        const uint32_t mid = (lo + hi + 1) >> 1;
+        if (L.frames[mid].chunk_begin <= gc) lo = mid; else hi = mid - 1;
+      }
+      fidx = lo;
+    }
+    const DecFrame F = L.frames[fidx];
     const uint32_t chunk = gc - F.chunk_begin;
     const uint32_t n_points = min(kChunkPoints, F.n_points - chunk * kChunkPoints);
     const uint32_t V = n_points * K;
-    const uint8_t* body = F.payload + L.chunk_offsets[gc];
-    const uint32_t size = L.chunk_sizes[gc];
+    const uint8_t* body = F.payload + s_desc[0];
+    const uint32_t size = static_cast<uint32_t>(s_desc[1]);
     const uint32_t mis = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(body) & 15u);
     const uint8_t* aligned = body - mis;
-    const uint32_t n_tiles = L.chunk_tiles[gc];
+    const uint32_t n_tiles = size ? (size + mis + kTB - 1) / kTB : 0u;
+    __syncthreads();  // everybody has read s_chunk / s_desc before thread 0 may claim the next chunk
     uint8_t* out = F.out + static_cast<size_t>(chunk) * kChunkPoints * step;
     const bool aligned4 = (((reinterpret_cast<uintptr_t>(out) | step | o0 | o1 | o2 | (K == 4 ? o3 : 0u)) & 3u) == 0u) &&
       o0 != CLDN_SKIP_STORE_OFFSET && o1 != CLDN_SKIP_STORE_OFFSET && o2 != CLDN_SKIP_STORE_OFFSET && (K < 4 || o3 != CLDN_SKIP_STORE_OFFSET);
@@ -862,8 +934,7 @@ static int launch_floatn_decode(const RegOp& op, const DecLaunch& L, bool sequen
   return 1;
 }
 
-int launch_decode_tiles(const Plan& plan, const DecLaunch& L, cudaStream_t stream) {
-  const RegOp& op = plan.ops[0];
+static int device_sm_count() {
   static int sm_count = 0;
   if (sm_count == 0) {
     int dev = 0;
@@ -871,13 +942,29 @@ int launch_decode_tiles(const Plan& plan, const DecLaunch& L, cudaStream_t strea
     cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
     if (sm_count <= 0) sm_count = 148;
   }
-  // Large batches: one persistent CTA per chunk (no look-back latency); small ones: one CTA per tile (parallel inside a chunk).
+  return sm_count;
+}
+
+// Large batches: one persistent CTA per chunk (no look-back latency); small ones: one CTA per tile (parallel inside a chunk).
+bool decode_tiles_sequential(uint32_t n_chunks_total) {
+  const int sm_count = device_sm_count();
   const char* mode = getenv("CLDN_B200_DECODE_MODE");  // "seq" | "tile" (development override)
-  bool sequential = L.n_chunks_total >= static_cast<uint32_t>(sm_count + sm_count / 8);  // measured crossover: ~1.1 chunks per SM
+  bool sequential = n_chunks_total >= static_cast<uint32_t>(sm_count + sm_count / 8);  // measured crossover: ~1.1 chunks per SM
   if (mode && mode[0] == 's') sequential = true;
   if (mode && mode[0] == 't') sequential = false;
-  count_tiles_kernel<<<(L.n_chunks_total + 127) / 128, 128, 0, stream>>>(L);
-  int launches = 1;
+  return sequential;
+}
+
+int launch_decode_tiles(const Plan& plan, const DecLaunch& L, cudaStream_t stream) {
+  const RegOp& op = plan.ops[0];
+  const int sm_count = device_sm_count();
+  const bool sequential = decode_tiles_sequential(L.n_chunks_total);
+  if (sequential && !L.chunk_desc) return -1;
+  int launches = 0;
+  if (!(sequential && L.chunk_desc)) {  // the sequential kernel derives these per chunk itself
+    count_tiles_kernel<<<(L.n_chunks_total + 127) / 128, 128, 0, stream>>>(L);
+    ++launches;
+  }
   if (!sequential) {
     scan_tiles_kernel<<<1, kThreads, 0, stream>>>(L);
     ++launches;

@@ -71,6 +71,10 @@ struct DecLaunch {
   uint32_t* tsums;             // per tile: 2 x 8 words, look-back 2 (aggregate record, inclusive record)
   uint64_t* trace;             // optional (CLDN_B200_TRACE): 8 globaltimer stamps per tile
   uint32_t* chunk_counter;     // work counter of the chunk-sequential kernel
+  uint64_t* chunk_desc;        // chunk-sequential kernel: 2 self-validating words per chunk, [tag:24][offset:40] and
+                               // [tag:24][size:32], published by CTA 0 while it walks the chunk prefixes
+  uint32_t desc_tag;           // tag of this launch (never 0)
+  uint32_t uniform_chunks;     // > 0: every frame has this many chunks (chunks are then claimed chunk-index-major)
   uint32_t sections_only;      // decode_chunks_kernel: the regular stream was decoded elsewhere, start at stream_end[]
   uint32_t tile_capacity;      // records allocated (== tile_grid)
   uint32_t tile_grid;          // host upper bound on the number of tiles
@@ -79,6 +83,7 @@ struct DecLaunch {
 
 int launch_decode(const Plan& host_plan, const DecLaunch& L, cudaStream_t stream);
 int launch_decode_tiles(const Plan& host_plan, const DecLaunch& L, cudaStream_t stream);
+bool decode_tiles_sequential(uint32_t n_chunks_total);  // which of the two FloatN kernels launch_decode_tiles will pick
 uint32_t decode_tile_bytes();
 
 // V5 adaptive integer sections (encode side).
