@@ -30,7 +30,7 @@ WORKLOAD = "C2/C5: 1M-point synthetic XYZI float32x4 clouds, 1 mm, stage 1 only 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--frames", type=int, default=32, help="distinct 1M-point clouds per GPU per step")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])

@@ -1,13 +1,16 @@
-// Tile-parallel DECODE of FloatN-only regular streams (XYZ / XYZI: BASELINE configs C1, C2, C5 and the float part of C3).
+// DECODE of FloatN-only regular streams (XYZ / XYZI: BASELINE configs C1, C2, C5 and the float part of C3).
 //
 // Same arithmetic as FieldDecoderFloatN_Lossy::decode (cloudini_lib/src/field_decoder.cpp:43-86), different shape:
-// the chunk's byte stream is cut into fixed 4 KB tiles, one CTA per tile, all tiles of all chunks of all frames in
-// one launch. Two decoupled look-backs over the tiles of a chunk replace the sequential walk:
-//   (1) number of values (terminator bytes) before the tile  -> which point / field every value belongs to,
-//   (2) per-field sum of deltas since the last NaN reset       -> absolute quantised value at the tile start.
-// Inside a tile: a byte with a clear MSB ends a value; a CTA scan ranks the terminators and compacts their positions;
-// then one thread per VALUE rebuilds the varint from two aligned shared-memory words (no byte loop), and one thread
-// per POINT run does the segmented prefix sum, the int->float conversion and the strided store.
+// the chunk's byte stream is cut into fixed 8 KB tiles (256 threads x 2 16-byte vectors). Inside a tile a byte with a
+// clear MSB ends a value: a CTA scan ranks the terminators, every thread takes a run of ceil(values / 256) consecutive
+// values (the start of the run is the byte behind the (run * VT - 1)-th terminator, found with a small table), decodes
+// them with a streaming 4-byte window, and the per-field running values come from a CTA segmented scan (reset at NaN).
+// Two kernels share these building blocks:
+//   decode_chunks_seq_kernel  large batches: persistent CTAs claim whole chunks from a counter and carry the value
+//                             count and the per-field values from tile to tile in registers; CTA 0 also walks the u32
+//                             chunk prefixes and publishes them while the others are already decoding;
+//   decode_tiles_kernel       small batches: one CTA per tile of every chunk, two decoupled look-backs over the tiles
+//                             of a chunk: (1) number of values before the tile, (2) per-field sum since the last reset.
 #include <stdio.h>
 
 #include "cldn_device.cuh"

@@ -4,10 +4,11 @@
 // EncodeV5Stage1's regular part (v5_codec.cpp:920-932) and WriteStage1Chunk's u32 framing (chunk_writer.cpp:27-48).
 //
 // Grid = one CTA per tile of T = 256*I points (T divides the 32768-point chunk, so tiles never straddle chunks).
-//  phase 1  every thread quantises its points, takes the delta to the previous point and sizes the varints;
-//  scan     CTA exclusive scan of per-point byte counts; decoupled look-back over the frame's tiles gives the tile's
-//           byte position without a second pass over the input (input is read exactly once from HBM);
-//  phase 2  bytes are packed into a shared-memory staging buffer at tile-local offsets;
+//  pass A   every thread quantises its points, takes the delta to the previous point and sizes the varints;
+//  scan     warp scans of per-point byte counts give tile-local offsets and the tile's size, which is published at once
+//           as the aggregate of a decoupled look-back over the frame's tiles (input is read exactly once from HBM);
+//  pass B   the LEB128 bytes are formed and stored byte-wise into a shared-memory staging buffer at their offsets,
+//           while warp 0 polls the look-back window between its iterations;
 //  copy-out the staged bytes are streamed to their final (arbitrarily aligned) position with 16-byte stores;
 //  framing  the last tile of every chunk back-patches the chunk's u32 size prefix, the last tile of a frame writes
 //           the frame's total size.
@@ -208,7 +209,7 @@ __global__ void __launch_bounds__(kThreads) encode_generic_kernel(const EncLaunc
 //   VEC4 = packed XYZI float32x4 at a 16-byte aligned base: one coalesced LDG.128 per point.
 // Warp-blocked point assignment: warp w owns points [w*32*I, (w+1)*32*I), lane l takes point 32*i + l of iteration i,
 // so loads are perfectly coalesced, the previous point comes from a lane shuffle and each iteration's output is one
-// contiguous byte run that is packed with word stores.
+// contiguous byte run.
 struct FloatNParams {
   uint32_t offset[4];
   float mul[4];

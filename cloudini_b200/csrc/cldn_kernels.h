@@ -62,7 +62,7 @@ struct DecLaunch {
   uint32_t* chunk_sizes;     // per global chunk: body size
   uint32_t* err;
   // tile-parallel path (FloatN-only regular streams)
-  uint32_t* chunk_tiles;       // per global chunk: number of 4 KB byte tiles
+  uint32_t* chunk_tiles;       // per global chunk: number of 8 KB byte tiles
   uint32_t* chunk_tile_begin;  // exclusive scan of chunk_tiles, (n_chunks_total + 1) entries
   uint32_t* stream_end;        // per global chunk: bytes of the regular stream (start of the V5 sections)
   uint32_t* chunk_frame;       // per global chunk: frame index
