@@ -87,6 +87,25 @@ def test_max_compressed_size_matches_reference(lib_built, ref):
                 assert cb.MaxCompressedSize(info, n, True) == ref.max_compressed_size(info, n, True)
 
 
+@pytest.mark.parametrize("version", [3, 4, 5])
+@pytest.mark.parametrize("lossless", [True, False])
+def test_lossless_layout_header_and_sizing_match_reference(lib_built, ref, version, lossless):
+    # the DDS-like layout that reaches the XOR / Gorilla coders: header text and capacity rule are host-side logic
+    info, cloud = synth.cloud_lossless(1000, seed=1, lossless=lossless, version=version)
+    blob = ref.encode(info, cloud)
+    assert blob.startswith(cb.EncodeHeader(info))  # the reference writes exactly this header in front of the chunks
+    back, used = cb.DecodeHeader(cb.EncodeHeader(info) + b"xyz")
+    assert used == len(cb.EncodeHeader(info)) and back.encoding_opt == info.encoding_opt
+    for a, b in zip(back.fields, info.fields):  # resolutions are float32 in the header
+        assert (a.resolution is None) == (b.resolution is None)
+        assert a.resolution is None or np.float32(a.resolution) == np.float32(b.resolution)
+    for n in (0, 1, 5, 4133, 100_000):
+        for hdr in (False, True):
+            assert cb.MaxCompressedSize(info, n, hdr) == ref.max_compressed_size(info, n, hdr)
+    # the stage-1 blob of the reference fits the capacity rule (sanity of the rule itself for these coders)
+    assert len(blob) <= cb.MaxCompressedSize(info, 1000, True)
+
+
 def test_point_step_zero_rejected(lib_built):
     info = synth.info_xyz(1)
     info.point_step = 0
