@@ -301,8 +301,13 @@ def test_floatn_decode_modes(oracle, monkeypatch, mode):
     _roundtrip_check(*synth.cloud_c3(70_000, seed=8), oracle, fill=0x99)
 
 
-def test_batch_decode_device_and_host_apis(oracle):
+@pytest.mark.parametrize("mode", [None, "seq", "tile"])
+def test_batch_decode_device_and_host_apis(oracle, monkeypatch, mode):
+    # mode "seq": several frames x several chunks through the persistent kernel (chunks claimed chunk-index-major,
+    # chunk prefixes walked by CTA 0 inside the kernel); every frame of the batch is compared, not only the first
     import torch
+    if mode:
+        monkeypatch.setenv("CLDN_B200_DECODE_MODE", mode)
     info = synth.info_xyzi(50_000)
     clouds = [synth.cloud_c2(50_000, seed=300 + k)[1] for k in range(5)]
     enc, dec = cb.PointcloudEncoder(info), cb.PointcloudDecoder()
