@@ -46,12 +46,12 @@ def oracle(lib_built):
 @pytest.fixture(scope="session")
 def golden(lib_built):
     import cloudini_b200 as cb
-    z = np.load(os.path.join(ROOT, "tests", "golden", "golden_v1.npz"))
-    names = sorted({k.split("__")[0] for k in z.files})
     out = {}
-    for n in names:
-        info = cb.EncodingInfoFromYAML(bytes(z[n + "__yaml"]).decode())
-        info.version = int(z[n + "__version"][0])
-        info.use_threads = False
-        out[n] = (info, z[n + "__input"], bytes(z[n + "__blob"]))
+    for fname in ("golden_v1.npz", "golden_v2.npz"):  # v2: the lossless float coders (XOR / Gorilla)
+        z = np.load(os.path.join(ROOT, "tests", "golden", fname))
+        for n in sorted({k.split("__")[0] for k in z.files}):
+            info = cb.EncodingInfoFromYAML(bytes(z[n + "__yaml"]).decode())
+            info.version = int(z[n + "__version"][0])
+            info.use_threads = False
+            out[n] = (info, z[n + "__input"], bytes(z[n + "__blob"]))
     return out

@@ -1,4 +1,4 @@
-"""Generates tests/golden/golden_v1.npz from the UNMODIFIED reference (oracle/_ref/libcloudini_ref.so).
+"""Generates tests/golden/golden_v1.npz and golden_v2.npz from the UNMODIFIED reference (oracle/_ref/libcloudini_ref.so).
 
 Run in the build container (where /root/reference exists):  python tests/golden/make_golden.py
 Each case stores the EncodingInfo (as the reference's YAML text + numeric version), the raw input bytes and the
@@ -66,20 +66,38 @@ def cases():
     return out
 
 
-def main():
-    build_ref()
-    ref = RefOracle()
+def cases_v2():
+    """Lossless float coders (XOR / Gorilla, field_encoder.hpp:123-312) on the DDS-like x,y,z,intensity,ring,timestamp
+    layout of the reference's sample message: every wire version, LOSSLESS and LOSSY (the resolution-less FLOAT64 stays
+    Gorilla / XOR either way), with the hostile values (repeats, NaN / inf / -0.0, denormals, random bit patterns)."""
+    out = {}
+    for version in (5, 4, 3):
+        out[f"lossless_v{version}"] = synth.cloud_lossless(3000, seed=40 + version, lossless=True, version=version)
+        out[f"gorilla_lossy_v{version}"] = synth.cloud_lossless(3000, seed=50 + version, lossless=False, version=version)
+    out["lossless_v5_2chunks"] = synth.cloud_lossless(33_000, seed=60, lossless=True, version=5)
+    return out
+
+
+def write(ref, path, table):
     blob = {}
-    for name, (info, cloud) in cases().items():
+    for name, (info, cloud) in table.items():
         enc = ref.encode(info, cloud)
         blob[name + "__yaml"] = np.frombuffer(cb.EncodingInfoToYAML(info).encode(), dtype=np.uint8)
         blob[name + "__version"] = np.array([info.version], dtype=np.int32)
         blob[name + "__input"] = np.asarray(cloud, dtype=np.uint8)
         blob[name + "__blob"] = np.frombuffer(enc, dtype=np.uint8)
         print(f"{name:18s} points={info.width:6d} step={info.point_step:2d} blob={len(enc)}")
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden_v1.npz")
     np.savez_compressed(path, **blob)
     print("wrote", path, os.path.getsize(path), "bytes")
+
+
+def main():
+    build_ref()
+    ref = RefOracle()
+    here = os.path.dirname(os.path.abspath(__file__))
+    if "--v2-only" not in sys.argv:
+        write(ref, os.path.join(here, "golden_v1.npz"), cases())
+    write(ref, os.path.join(here, "golden_v2.npz"), cases_v2())
 
 
 if __name__ == "__main__":
