@@ -136,6 +136,55 @@ def cloud_lossless(n: int = 40_000, seed: int = 6, lossless: bool = True, versio
     return info, np.ascontiguousarray(buf).reshape(-1)
 
 
+def random_layout_case(seed: int):
+    """A random EncodingInfo (field types, offsets with padding, resolutions, encoding option, wire version 3/4/5) with
+    matching data: the planner's every branch is hit over a few hundred seeds (codec_common.cpp:69-198, v5_codec.cpp:883-892).
+    Used to pin the C oracle against the compiled reference; the GPU path can be swept with the same seeds."""
+    F = FieldType
+    types = [F.INT8, F.UINT8, F.INT16, F.UINT16, F.INT32, F.UINT32, F.FLOAT32, F.FLOAT64, F.INT64, F.UINT64]
+    npt = {F.INT8: np.int8, F.UINT8: np.uint8, F.INT16: np.int16, F.UINT16: np.uint16, F.INT32: np.int32, F.UINT32: np.uint32,
+           F.FLOAT32: np.float32, F.FLOAT64: np.float64, F.INT64: np.int64, F.UINT64: np.uint64}
+    size = {F.INT8: 1, F.UINT8: 1, F.INT16: 2, F.UINT16: 2, F.INT32: 4, F.UINT32: 4, F.FLOAT32: 4, F.FLOAT64: 8, F.INT64: 8, F.UINT64: 8}
+    rng = np.random.default_rng(seed)
+    nf = int(rng.integers(1, 7))
+    n = int(rng.choice([1, 2, 17, 300, 4097, 33000 if seed % 7 == 0 else 500]))
+    names = [(nm, F.FLOAT32) for nm in "xyz"] if rng.random() < 0.6 else []
+    names += [(f"f{k}", types[int(rng.integers(0, len(types)))]) for k in range(nf)]
+    fields, cols, off = [], [], 0
+    for nm, t in names:
+        off += int(rng.integers(0, 3)) if rng.random() < 0.3 else 0  # padding in front of the field
+        res = None
+        if t in (F.FLOAT32, F.FLOAT64):
+            res = float(rng.choice([0.001, 0.01, 0.5])) if rng.random() < 0.7 else None
+            v = np.cumsum(rng.normal(0, 0.05, n)).astype(npt[t])
+            if n > 10:
+                v[rng.integers(0, n, 2)] = np.nan
+                if rng.random() < 0.3:
+                    v[rng.integers(0, n)] = np.inf
+        else:
+            lim = np.iinfo(npt[t])
+            kind = int(rng.integers(0, 4))
+            if kind == 0:
+                v = (np.arange(n) * int(rng.integers(1, 5)) + int(rng.integers(0, 100))).astype(npt[t])
+            elif kind == 1:
+                v = rng.integers(0, 4, n).astype(npt[t])
+            elif kind == 2:
+                v = ((np.arange(n) // 64) % 5).astype(npt[t])
+            else:
+                v = rng.integers(max(lim.min, -2**62), min(lim.max, 2**62), n, dtype=np.int64 if lim.min < 0 else np.uint64).astype(npt[t])
+        fields.append(PointField(nm, off, t, res))
+        cols.append((off, size[t], v))
+        off += size[t]
+    step = off + (int(rng.integers(0, 4)) if rng.random() < 0.3 else 0)
+    buf = np.full((n, step), 0xCD, dtype=np.uint8)
+    for o, sz, v in cols:
+        buf[:, o:o + sz] = np.ascontiguousarray(v).view(np.uint8).reshape(n, sz)
+    enc = [EncodingOptions.LOSSY, EncodingOptions.LOSSLESS, EncodingOptions.NONE][int(rng.integers(0, 3))]
+    info = EncodingInfo(fields=fields, width=n, height=1, point_step=step, encoding_opt=enc,
+                        compression_opt=CompressionOption.NONE, use_threads=False, version=int(rng.choice([3, 4, 5])))
+    return info, np.ascontiguousarray(buf).reshape(-1)
+
+
 def fnv1a64(data) -> int:
     """FNV-1a 64-bit (the fingerprint mcap_codec_benchmark --hash prints, tools/src/mcap_codec_benchmark.cpp:103-109)."""
     h = 0xCBF29CE484222325

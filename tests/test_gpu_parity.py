@@ -1,6 +1,8 @@
 """GPU parity tests (B200): every byte the CUDA path produces is compared with the oracle on the same input.
 Encode: blob == oracle blob (header + every chunk). Decode: decoded buffer == oracle-decoded buffer, starting from the
 same pre-filled buffer (the decoder only writes declared field bytes). All calls go through the C ABI."""
+import os
+
 import numpy as np
 import pytest
 
@@ -153,6 +155,18 @@ def test_lossless_truncated_stream_is_rejected():
     out = np.zeros(cloud.size, dtype=np.uint8)
     with pytest.raises(RuntimeError):
         cb.PointcloudDecoder().decode(dinfo, blob[hdr:-7], out)
+
+
+@pytest.mark.skipif(not os.environ.get("CLDN_B200_FUZZ"), reason="opt-in sweep (CLDN_B200_FUZZ=1): random layouts through the generic kernels")
+def test_random_layouts_sweep(oracle):
+    # same seeds as tests/test_oracle.py::test_port_vs_reference_random_layouts; layouts the reference rejects are skipped
+    for seed in range(int(os.environ.get("CLDN_B200_FUZZ_SEEDS", "120"))):
+        info, cloud = synth.random_layout_case(seed)
+        try:
+            expected = oracle.encode(info, cloud)
+        except RuntimeError:
+            continue
+        _roundtrip_check(info, cloud, oracle, blob_expected=expected, fill=0x5A)
 
 
 def test_encoding_none_copy_only(oracle):

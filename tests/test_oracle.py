@@ -180,6 +180,30 @@ def test_port_vs_reference_lossless_floats(port, ref, version, lossless):
             assert np.array_equal(want, cloud)  # bit-exact round trip, NaN payloads included
 
 
+def test_port_vs_reference_random_layouts(port, ref):
+    # 160 random EncodingInfos (types, padding, resolutions, LOSSY / LOSSLESS / NONE, wire versions 3/4/5): same blob, same
+    # decoded bytes (untouched padding included), same accept / reject decision
+    for seed in range(160):
+        info, cloud = synth.random_layout_case(seed)
+        try:
+            a = ref.encode(info, cloud)
+        except RuntimeError:
+            with pytest.raises(RuntimeError):
+                port.encode(info, cloud)
+            continue
+        assert port.encode(info, cloud) == a, f"seed {seed}"
+        o1 = np.full(cloud.size, 0x5A, dtype=np.uint8)
+        o2 = o1.copy()
+        try:
+            ref.decode(a, o1)
+        except RuntimeError:
+            with pytest.raises(RuntimeError):
+                port.decode(a, o2)
+            continue
+        port.decode(a, o2)
+        assert np.array_equal(o1, o2), f"seed {seed}"
+
+
 def test_port_decoder_hardening(port):
     # test_field_encoders.cpp:771-791 / test_header.cpp:165-171: missing chunks, trailing garbage, header in payload
     info, cloud = synth.cloud_c2(40_000, seed=9)
