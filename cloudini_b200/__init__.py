@@ -119,6 +119,7 @@ def lib():
     L.cldn_b200_info_to_yaml.argtypes = [C.POINTER(_CInfo), C.c_char_p, sz, C.POINTER(sz)]
     L.cldn_b200_info_from_yaml.argtypes = [C.c_char_p, sz, C.POINTER(_CInfo)]
     L.cldn_b200_encode_header.argtypes = [C.POINTER(_CInfo), vp, sz, C.POINTER(sz)]
+    L.cldn_b200_encode_header_binary.argtypes = [C.POINTER(_CInfo), vp, sz, C.POINTER(sz)]
     L.cldn_b200_decode_header.argtypes = [vp, sz, C.POINTER(_CInfo), C.POINTER(sz)]
     L.cldn_b200_max_compressed_size.argtypes = [C.POINTER(_CInfo), sz, C.c_int]
     L.cldn_b200_max_compressed_size.restype = sz
@@ -206,12 +207,14 @@ def EncodingInfoFromYAML(yaml: str) -> EncodingInfo:  # cloudini.cpp:192-230
     return _from_c(c)
 
 
-def EncodeHeader(info: EncodingInfo) -> bytes:  # cloudini.cpp:294-318 (YAML flavour)
+def EncodeHeader(info: EncodingInfo, binary: bool = False) -> bytes:
+    """cloudini.cpp:294-344: the YAML header every encoder writes, or (binary=True) HeaderEncoding::BINARY."""
     c = _to_c(info)
+    fn = lib().cldn_b200_encode_header_binary if binary else lib().cldn_b200_encode_header
     need = C.c_size_t(0)
-    lib().cldn_b200_encode_header(C.byref(c), None, 0, C.byref(need))
+    fn(C.byref(c), None, 0, C.byref(need))
     buf = (C.c_uint8 * need.value)()
-    _check(lib().cldn_b200_encode_header(C.byref(c), buf, need.value, None))
+    _check(fn(C.byref(c), buf, need.value, None))
     return bytes(buf)
 
 

@@ -492,6 +492,38 @@ int cldn_b200_encode_header(const cldn_info_t* info, uint8_t* out, size_t capaci
   return CLDN_OK;
 }
 
+// EncodeHeader, HeaderEncoding::BINARY (cloudini.cpp:319-344; size: ComputeHeaderSize :232-247)
+int cldn_b200_encode_header_binary(const cldn_info_t* info, uint8_t* out, size_t capacity, size_t* written) {
+  if (!info) { set_error("null info"); return CLDN_ERR_INVALID_ARGUMENT; }
+  if (info->n_fields > CLDN_MAX_FIELDS) { set_error("too many fields"); return CLDN_ERR_INVALID_ARGUMENT; }
+  std::vector<uint8_t> h;
+  auto put = [&h](const void* p, size_t k) { const uint8_t* b = static_cast<const uint8_t*>(p); h.insert(h.end(), b, b + k); };
+  put("CLOUDINI_V", 10);
+  const char digits[2] = {static_cast<char>('0' + info->version / 10), static_cast<char>('0' + info->version % 10)};
+  put(digits, 2);
+  put(&info->width, 4);
+  put(&info->height, 4);
+  put(&info->point_step, 4);
+  put(&info->encoding_opt, 1);
+  put(&info->compression_opt, 1);
+  const uint16_t nf = static_cast<uint16_t>(info->n_fields);
+  put(&nf, 2);
+  for (uint32_t i = 0; i < info->n_fields; ++i) {
+    const cldn_field_t& f = info->fields[i];
+    const uint16_t len = static_cast<uint16_t>(strnlen(f.name, CLDN_MAX_NAME));
+    put(&len, 2);
+    put(f.name, len);
+    put(&f.offset, 4);
+    put(&f.type, 1);
+    const float res = f.has_resolution ? f.resolution : -1.0f;  // "no resolution" travels as -1
+    put(&res, 4);
+  }
+  if (written) *written = h.size();
+  if (!out || capacity < h.size()) { set_error("header buffer too small"); return CLDN_ERR_BUFFER_TOO_SMALL; }
+  memcpy(out, h.data(), h.size());
+  return CLDN_OK;
+}
+
 // DecodeHeader, cloudini.cpp:353-428
 int cldn_b200_decode_header(const uint8_t* blob, size_t n, cldn_info_t* info, size_t* header_bytes) {
   if (!blob || !info) { set_error("null argument"); return CLDN_ERR_INVALID_ARGUMENT; }

@@ -103,6 +103,10 @@ int cldn_b200_info_from_yaml(const char* yaml, size_t yaml_len, cldn_info_t* inf
 /* ---- header + sizing (host only) ----------------------------------------------------------------------------- */
 /* EncodeHeader, YAML flavour (cloudini.cpp:294-318): "CLOUDINI_V" + 2 digits + '\n' + yaml + '\0'. */
 int cldn_b200_encode_header(const cldn_info_t* info, uint8_t* out, size_t capacity, size_t* written);
+/* EncodeHeader, HeaderEncoding::BINARY (cloudini.cpp:319-344): the legacy fixed-layout header (magic + version digits,
+ * width, height, point_step, options, fields). PointcloudEncoder never writes it (cloudini.cpp:430-440 uses YAML);
+ * it exists for callers of the free function. Call with out == NULL to query the size through *written. */
+int cldn_b200_encode_header_binary(const cldn_info_t* info, uint8_t* out, size_t capacity, size_t* written);
 /* DecodeHeader (cloudini.cpp:353-428): YAML and legacy binary headers. `blob` must be host memory.
  * *header_bytes = number of bytes consumed (the reference advances the caller's view by the same amount). */
 int cldn_b200_decode_header(const uint8_t* blob, size_t blob_bytes, cldn_info_t* info, size_t* header_bytes);

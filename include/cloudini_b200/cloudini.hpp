@@ -156,12 +156,12 @@ inline EncodingInfo EncodingInfoFromYAML(std::string_view yaml) {
 }
 
 inline void EncodeHeader(const EncodingInfo& header, std::vector<uint8_t>& output, HeaderEncoding encoding = HeaderEncoding::YAML) {
-  if (encoding != HeaderEncoding::YAML) throw std::runtime_error("cloudini_b200 writes YAML headers only (the legacy binary header is read-only)");
   const cldn_info_t c = detail::to_c(header);
+  auto write = encoding == HeaderEncoding::YAML ? cldn_b200_encode_header : cldn_b200_encode_header_binary;
   size_t need = 0;
-  cldn_b200_encode_header(&c, nullptr, 0, &need);
+  write(&c, nullptr, 0, &need);
   output.resize(need);
-  detail::check(cldn_b200_encode_header(&c, output.data(), output.size(), nullptr));
+  detail::check(write(&c, output.data(), output.size(), nullptr));
 }
 
 // Advances `input` past the header, like the reference.

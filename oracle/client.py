@@ -58,6 +58,9 @@ class RefOracle:
         L.ref_encode.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int]
         L.ref_max_compressed_size.restype = C.c_size_t
         L.ref_max_compressed_size.argtypes = [C.c_char_p, C.c_int, C.c_size_t, C.c_int]
+        if hasattr(L, "ref_encode_header"):  # older prebuilt wrappers do not have it
+            L.ref_encode_header.restype = C.c_longlong
+            L.ref_encode_header.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t]
         L.ref_decode_header.restype = C.c_longlong
         L.ref_decode_header.argtypes = [C.c_void_p, C.c_size_t, C.c_char_p, C.c_size_t, C.POINTER(C.c_int)]
         L.ref_decode.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
@@ -83,6 +86,13 @@ class RefOracle:
         if w < 0:
             raise RuntimeError(self._err())
         return out[:w].tobytes()
+
+    def header(self, info: cb.EncodingInfo, binary: bool = False) -> bytes:
+        out = np.empty(1 << 16, dtype=np.uint8)
+        n = self.L.ref_encode_header(_yaml(info), info.version, int(binary), out.ctypes.data, out.nbytes)
+        if n < 0:
+            raise RuntimeError(self._err())
+        return out[:n].tobytes()
 
     def decode_header(self, blob: bytes):
         buf = C.create_string_buffer(1 << 16)

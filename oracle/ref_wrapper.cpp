@@ -52,6 +52,21 @@ long long ref_encode(const char* yaml, int version, int use_threads, const uint8
   }
 }
 
+// Cloudini::EncodeHeader(info, out, binary ? BINARY : YAML). Returns the header size; -1 on exception / small buffer.
+long long ref_encode_header(const char* yaml, int version, int binary, uint8_t* out, size_t out_capacity) {
+  try {
+    Cloudini::EncodingInfo info = infoFromYaml(yaml, version, 0);
+    std::vector<uint8_t> h;
+    Cloudini::EncodeHeader(info, h, binary ? Cloudini::HeaderEncoding::BINARY : Cloudini::HeaderEncoding::YAML);
+    if (h.size() > out_capacity) { g_err = "header buffer too small"; return -1; }
+    memcpy(out, h.data(), h.size());
+    return static_cast<long long>(h.size());
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return -1;
+  }
+}
+
 // Sizing helper. Returns 0 on exception.
 size_t ref_max_compressed_size(const char* yaml, int version, size_t points, int include_header) {
   try {
