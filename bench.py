@@ -161,7 +161,7 @@ def cpu_reference_numbers(oracle, info, cloud, blob, seconds, threads):
     """Times the CPU path on a bounded sample: `reps` encode + decode passes of one 1M-point cloud per thread."""
     t1, _ = oracle.time_encode(info, cloud, 1, 1)
     t2 = oracle.time_decode(blob, 1, 1)
-    reps = max(2, int(seconds / max(t1 + t2, 1e-3)))
+    reps = max(1, int(seconds / max(t1 + t2, 1e-3)))
     te, _ = oracle.time_encode(info, cloud, reps, threads)
     td = oracle.time_decode(blob, reps, threads)
     pts = reps * threads * POINTS
@@ -181,7 +181,8 @@ def run_reference(args, rank, world):
     blob = oracle.encode(info, cloud)
     threads = os.cpu_count() or 1
     steps = []
-    per_step_seconds = max(2.0, min(20.0, 120.0 / max(args.steps + args.warmup, 1)))
+    # one step = a bounded sample (>= one pass per thread); the whole run stays within a couple of minutes for any --steps
+    per_step_seconds = min(20.0, 120.0 / max(args.steps + args.warmup, 1))
     for s in range(args.warmup + args.steps):
         r = cpu_reference_numbers(oracle, info, cloud, blob, per_step_seconds / max(threads, 1) * 1.0, threads)
         if s >= args.warmup:
