@@ -216,6 +216,8 @@ def main():
     import cloudini_b200 as cb
     from cloudini_b200 import synth
 
+    if b"cusim" in cb.lib().cldn_b200_version():  # tests/cusim is a CPU emulation for kernel-logic tests, never a bench target
+        raise SystemExit("bench.py: CLDN_B200_LIB points at the cusim test emulation — refusing to measure it")
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — cloudini_b200 has no CPU fallback")
     torch.cuda.set_device(local_rank)

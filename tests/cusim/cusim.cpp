@@ -1,0 +1,342 @@
+// cusim scheduler — TEST INFRASTRUCTURE ONLY (see cuda_runtime.h in this directory for what this is and is not).
+// One OS worker runs one CTA at a time; its threads are fibers (hand-rolled x86-64 context switch) scheduled
+// round-robin, blocked fibers are skipped until their barrier / warp generation changes. A full pass without a
+// runnable fiber is a deadlock (a lane skipped a collective, a barrier inside divergent code, ...) and aborts with a
+// per-fiber report.
+#include "cuda_runtime.h"
+
+#include <sys/mman.h>
+
+#include <atomic>
+#include <chrono>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#if !defined(__x86_64__)
+#error "cusim's context switch is written for x86-64"
+#endif
+
+extern "C" void cusim_switch(void** save_sp, void* new_sp);
+asm(R"(
+.text
+.globl cusim_switch
+.type cusim_switch,@function
+cusim_switch:
+  pushq %rbp
+  pushq %rbx
+  pushq %r12
+  pushq %r13
+  pushq %r14
+  pushq %r15
+  movq %rsp, (%rdi)
+  movq %rsi, %rsp
+  popq %r15
+  popq %r14
+  popq %r13
+  popq %r12
+  popq %rbx
+  popq %rbp
+  ret
+.size cusim_switch,.-cusim_switch
+)");
+
+namespace cusim {
+
+thread_local ThreadCoords tc;
+
+namespace {
+
+constexpr size_t kStackBytes = 256 * 1024;
+constexpr unsigned kMaxThreads = 1024;
+
+enum Wait : uint8_t { RUNNABLE = 0, WAIT_BARRIER, WAIT_WARP, WAIT_POLL, DONE };
+
+struct Fiber {
+  void* sp = nullptr;
+  char* stack = nullptr;
+  Wait wait = RUNNABLE;
+  uint32_t wait_gen = 0;
+  uint32_t wait_warp = 0;
+  uint3 tid{0, 0, 0};
+};
+
+struct Warp {
+  uint64_t slot[2][32];
+  unsigned arrived[2];
+  unsigned arrived_final[2];
+  uint32_t gen;
+  unsigned live;  // lanes that exist and have not exited
+};
+
+struct Cta {
+  Fiber fibers[kMaxThreads];
+  Warp warps[kMaxThreads / 32];
+  void* sched_sp = nullptr;
+  unsigned n_threads = 0, cur = 0;
+  unsigned live = 0, bar_arrived = 0;
+  uint32_t bar_gen = 0;
+  int bar_or_acc = 0, bar_or_res[2] = {0, 0};
+  void* dyn = nullptr;
+  size_t dyn_cap = 0;
+  const std::function<void()>* body = nullptr;
+  char* stacks = nullptr;
+};
+
+thread_local Cta* g_cta = nullptr;
+std::mutex g_pool_mutex;
+std::vector<Cta*> g_pool;  // CTA contexts (fiber stacks) are recycled between launches
+
+Cta* acquire_cta() {
+  {
+    std::lock_guard<std::mutex> lock(g_pool_mutex);
+    if (!g_pool.empty()) { Cta* c = g_pool.back(); g_pool.pop_back(); g_cta = c; return c; }
+  }
+  Cta* c = new Cta();
+  c->stacks = static_cast<char*>(mmap(nullptr, kStackBytes * kMaxThreads, PROT_READ | PROT_WRITE,
+                                      MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0));
+  if (c->stacks == MAP_FAILED) { fprintf(stderr, "cusim: mmap of fiber stacks failed\n"); abort(); }
+  for (unsigned i = 0; i < kMaxThreads; ++i) c->fibers[i].stack = c->stacks + kStackBytes * i;
+  g_cta = c;
+  return c;
+}
+void release_cta(Cta* c) {
+  g_cta = nullptr;
+  std::lock_guard<std::mutex> lock(g_pool_mutex);
+  g_pool.push_back(c);
+}
+
+void yield_to_scheduler() {
+  Cta* c = g_cta;
+  Fiber& f = c->fibers[c->cur];
+  cusim_switch(&f.sp, c->sched_sp);
+}
+
+void release_barrier_if_complete(Cta* c) {
+  if (c->live > 0 && c->bar_arrived >= c->live) {
+    c->bar_arrived = 0;
+    c->bar_or_res[c->bar_gen & 1u] = c->bar_or_acc;
+    c->bar_or_acc = 0;
+    c->bar_gen++;
+  }
+}
+
+void release_warp_if_complete(Warp& w, unsigned mask_expected) {
+  const unsigned b = w.gen & 1u;
+  const unsigned need = mask_expected & w.live;
+  if (need != 0 && (w.arrived[b] & need) == need) {
+    w.arrived_final[b] = w.arrived[b];
+    w.arrived[b] = 0;
+    w.gen++;
+  }
+}
+
+void fiber_main() {
+  Cta* c = g_cta;
+  (*c->body)();
+  // thread exit: it no longer takes part in barriers or warp collectives
+  Fiber& f = c->fibers[c->cur];
+  f.wait = DONE;
+  c->live--;
+  release_barrier_if_complete(c);
+  const unsigned linear = c->cur;
+  Warp& w = c->warps[linear >> 5];
+  w.live &= ~(1u << (linear & 31u));
+  // a collective that was only waiting for this lane completes (CUDA ignores exited lanes)
+  const unsigned b = w.gen & 1u;
+  if (w.arrived[b] != 0 && w.live != 0 && (w.arrived[b] & w.live) == w.live) release_warp_if_complete(w, w.arrived[b]);
+  cusim_switch(&f.sp, c->sched_sp);
+  fprintf(stderr, "cusim: finished fiber resumed\n");
+  abort();
+}
+
+extern "C" void cusim_fiber_entry() { fiber_main(); }
+
+void prepare_fiber(Fiber& f) {
+  // initial frame consumed by cusim_switch: r15 r14 r13 r12 rbx rbp, then the "return address" = entry point
+  uintptr_t top = reinterpret_cast<uintptr_t>(f.stack) + kStackBytes;
+  top &= ~static_cast<uintptr_t>(15);
+  uint64_t* p = reinterpret_cast<uint64_t*>(top);
+  *--p = 0;                                                   // fake return address of the entry function
+  *--p = reinterpret_cast<uint64_t>(&cusim_fiber_entry);      // popped by `ret`
+  for (int i = 0; i < 6; ++i) *--p = 0;
+  f.sp = p;
+  f.wait = RUNNABLE;
+}
+
+void deadlock_report(Cta* c) {
+  fprintf(stderr, "cusim: DEADLOCK in CTA (%u,%u,%u): no runnable thread. live=%u barrier arrived=%u\n", tc.bid.x, tc.bid.y,
+          tc.bid.z, c->live, c->bar_arrived);
+  unsigned shown = 0;
+  for (unsigned i = 0; i < c->n_threads && shown < 40; ++i) {
+    const Fiber& f = c->fibers[i];
+    if (f.wait == DONE) continue;
+    fprintf(stderr, "  thread %u: %s\n", i, f.wait == WAIT_BARRIER ? "at __syncthreads" : f.wait == WAIT_WARP ? "at a warp collective" : "?");
+    ++shown;
+  }
+  abort();
+}
+
+void run_cta(Cta* c, dim3 grid, dim3 block, uint3 bid) {
+  const unsigned n = block.x * block.y * block.z;
+  c->n_threads = n;
+  c->live = n;
+  c->bar_arrived = 0;
+  c->bar_or_acc = 0;
+  for (unsigned w = 0; w < (n + 31) / 32; ++w) {
+    Warp& W = c->warps[w];
+    W.arrived[0] = W.arrived[1] = 0;
+    W.gen = 0;
+    const unsigned lanes = n - w * 32 >= 32 ? 32 : n - w * 32;
+    W.live = lanes == 32 ? 0xffffffffu : ((1u << lanes) - 1u);
+  }
+  for (unsigned i = 0; i < n; ++i) {
+    Fiber& f = c->fibers[i];
+    f.tid = uint3{i % block.x, (i / block.x) % block.y, i / (block.x * block.y)};
+    prepare_fiber(f);
+  }
+  tc.bid = bid;
+  tc.bdim = block;
+  tc.gdim = grid;
+  // CUSIM_ORDER: fwd (default) | rev | rand — the order in which runnable threads are resumed within a pass. Results
+  // must not depend on it; "rand" reshuffles every pass with a per-CTA seed.
+  static const int order = [] { const char* e = getenv("CUSIM_ORDER"); return !e ? 0 : e[0] == 'r' && e[1] == 'e' ? 1 : e[0] == 'r' ? 2 : 0; }();
+  uint64_t rng = 0x9E3779B97F4A7C15ull * (bid.x + 1u) + bid.y;
+  unsigned done = 0;
+  while (done < n) {
+    bool progressed = false;
+    unsigned rot = 0, stride = 1;
+    if (order == 2) {
+      rng = rng * 6364136223846793005ull + 1442695040888963407ull;
+      rot = static_cast<unsigned>(rng >> 33) % n;
+      stride = (n % 7u) ? 7u : ((n % 5u) ? 5u : ((n % 3u) ? 3u : 1u));  // co-prime with n for the usual block sizes
+    }
+    for (unsigned k = 0; k < n; ++k) {
+      const unsigned i = order == 0 ? k : order == 1 ? n - 1 - k : static_cast<unsigned>((rot + static_cast<uint64_t>(k) * stride) % n);
+      Fiber& f = c->fibers[i];
+      if (f.wait == DONE) continue;
+      if (f.wait == WAIT_BARRIER && c->bar_gen == f.wait_gen) continue;
+      if (f.wait == WAIT_WARP && c->warps[f.wait_warp].gen == f.wait_gen) continue;
+      f.wait = RUNNABLE;
+      c->cur = i;
+      tc.tid = f.tid;
+      cusim_switch(&c->sched_sp, f.sp);
+      progressed = true;
+      if (f.wait == DONE) ++done;
+    }
+    if (!progressed) deadlock_report(c);
+  }
+}
+
+}  // namespace
+
+int sm_count() {
+  const char* e = getenv("CUSIM_SMS");
+  const int v = e ? atoi(e) : 0;
+  return v > 0 ? v : 148;
+}
+
+uint64_t globaltimer_ns() {
+  return static_cast<uint64_t>(std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count());
+}
+
+unsigned lane_id() { return g_cta->cur & 31u; }
+
+void* dyn_smem() { return g_cta->dyn; }
+
+void syncthreads() {
+  Cta* c = g_cta;
+  Fiber& f = c->fibers[c->cur];
+  const uint32_t gen = c->bar_gen;
+  c->bar_arrived++;
+  release_barrier_if_complete(c);
+  if (c->bar_gen != gen) return;  // last arriver
+  f.wait = WAIT_BARRIER;
+  f.wait_gen = gen;
+  yield_to_scheduler();
+}
+
+int syncthreads_or(int pred) {
+  Cta* c = g_cta;
+  Fiber& f = c->fibers[c->cur];
+  const uint32_t gen = c->bar_gen;
+  c->bar_or_acc |= (pred != 0);
+  c->bar_arrived++;
+  release_barrier_if_complete(c);
+  if (c->bar_gen == gen) {
+    f.wait = WAIT_BARRIER;
+    f.wait_gen = gen;
+    yield_to_scheduler();
+  }
+  return c->bar_or_res[gen & 1u];
+}
+
+void poll_yield() {
+  Cta* c = g_cta;
+  if (!c || c->n_threads <= 1) { std::this_thread::yield(); return; }
+  c->fibers[c->cur].wait = WAIT_POLL;
+  yield_to_scheduler();
+}
+
+const uint64_t* warp_exchange(unsigned mask, uint64_t v, unsigned* arrived_mask) {
+  Cta* c = g_cta;
+  const unsigned linear = c->cur, lane = linear & 31u;
+  Warp& w = c->warps[linear >> 5];
+  if (!((mask >> lane) & 1u)) {
+    fprintf(stderr, "cusim: thread %u called a warp collective with mask %08x that excludes its own lane\n", linear, mask);
+    abort();
+  }
+  const uint32_t gen = w.gen;
+  const unsigned b = gen & 1u;
+  w.slot[b][lane] = v;
+  w.arrived[b] |= 1u << lane;
+  release_warp_if_complete(w, mask);
+  if (w.gen == gen) {
+    Fiber& f = c->fibers[linear];
+    f.wait = WAIT_WARP;
+    f.wait_gen = gen;
+    f.wait_warp = linear >> 5;
+    yield_to_scheduler();
+  }
+  *arrived_mask = w.arrived_final[b];
+  return w.slot[b];
+}
+
+void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()>& body) {
+  const uint64_t n_ctas = static_cast<uint64_t>(grid.x) * grid.y * grid.z;
+  const unsigned n_threads = block.x * block.y * block.z;
+  if (n_ctas == 0 || n_threads == 0) return;
+  if (n_threads > kMaxThreads) { fprintf(stderr, "cusim: block of %u threads\n", n_threads); abort(); }
+  unsigned workers = std::thread::hardware_concurrency();
+  if (const char* e = getenv("CUSIM_WORKERS")) workers = static_cast<unsigned>(atoi(e));
+  if (workers < 1) workers = 1;
+  if (workers > 16) workers = 16;
+  if (workers > n_ctas) workers = static_cast<unsigned>(n_ctas);
+  std::atomic<uint64_t> next{0};
+  auto worker = [&]() {
+    Cta* c = acquire_cta();
+    c->body = &body;
+    if (smem_bytes + 64 > c->dyn_cap) {
+      free(c->dyn);
+      c->dyn_cap = smem_bytes + 64 < (256u << 10) ? (256u << 10) : smem_bytes + 64;
+      if (posix_memalign(&c->dyn, 1024, c->dyn_cap) != 0) abort();
+    }
+    for (;;) {
+      const uint64_t i = next.fetch_add(1);  // in-order dispatch, like the hardware's block scheduler
+      if (i >= n_ctas) break;
+      // poison the dynamic shared memory so that reads of never-written bytes are reproducible and loud
+      memset(c->dyn, 0xA5, smem_bytes + 64);
+      const uint3 bid{static_cast<unsigned>(i % grid.x), static_cast<unsigned>((i / grid.x) % grid.y),
+                      static_cast<unsigned>(i / (static_cast<uint64_t>(grid.x) * grid.y))};
+      run_cta(c, grid, block, bid);
+    }
+    release_cta(c);
+  };
+  // always on fresh OS threads: the caller's thread keeps its own (possibly small) stack out of the picture
+  std::vector<std::thread> pool;
+  pool.reserve(workers);
+  for (unsigned w = 0; w < workers; ++w) pool.emplace_back(worker);
+  for (auto& t : pool) t.join();
+}
+
+}  // namespace cusim

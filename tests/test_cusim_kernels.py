@@ -1,0 +1,58 @@
+"""Kernel logic without a GPU: the `-m gpu` parity suite re-run against tests/cusim (TEST INFRASTRUCTURE ONLY).
+
+tests/cusim compiles the *unmodified* CUDA sources of cloudini_b200/csrc with g++ against a shim of <cuda_runtime.h>
+that emulates the CUDA execution model on the CPU (CTA threads = fibers, exact __syncthreads / warp-collective
+semantics, CTAs dispatched in order on several OS threads so the decoupled look-backs really run concurrently). It is
+not a fallback of the product — cloudini_b200/lib never contains it and bench.py / smoke() refuse it — and it proves
+nothing about performance; it lets this CPU-only container catch indexing / scan / packing / protocol bugs before the
+B200 run, which stays the parity gate. Every parity test of tests/test_gpu_parity.py runs unchanged, each
+thread-resume order (forward, reverse, shuffled) must give identical bytes.
+"""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests", "cusim"))
+
+
+@pytest.fixture(scope="module")
+def cusim_lib(lib_built):
+    import platform
+    if platform.machine() != "x86_64":
+        pytest.skip("cusim's context switch is x86-64 only")
+    import build_cusim
+    return build_cusim.build()
+
+
+def _run_gpu_suite(cusim_lib, extra_env, selection):
+    env = dict(os.environ, CLDN_B200_LIB=cusim_lib, **extra_env)
+    cmd = [sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", "-p", "no:cacheprovider", *selection]
+    r = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=1500)
+    assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-2000:]
+    return r.stdout
+
+
+def test_parity_suite_under_emulation(cusim_lib):
+    out = _run_gpu_suite(cusim_lib, {"CLDN_B200_FUZZ": "1", "CLDN_B200_FUZZ_SEEDS": "60"}, ["tests/test_gpu_parity.py"])
+    assert " passed" in out and "failed" not in out
+
+
+@pytest.mark.parametrize("order,workers", [("rev", "8"), ("rand", "3"), ("fwd", "1")])
+def test_thread_order_and_cta_concurrency_do_not_matter(cusim_lib, order, workers):
+    # reverse / shuffled resume order inside a CTA, 1..8 OS threads running CTAs: same bytes (look-backs, persistent
+    # chunk claims and the in-kernel chunk walk are the protocols this exercises)
+    sel = ["tests/test_gpu_parity.py", "-k",
+           "float_clouds_sizes or adversarial or int_min or decode_modes or batch or c3_padded or v5_ or lossless or padded_and_unaligned"]
+    _run_gpu_suite(cusim_lib, {"CUSIM_ORDER": order, "CUSIM_WORKERS": workers}, sel)
+
+
+def test_product_entry_points_refuse_the_emulation(cusim_lib):
+    # bench.py and smoke() must never report numbers / parity from the emulated library
+    env = dict(os.environ, CLDN_B200_LIB=cusim_lib)
+    r = subprocess.run([sys.executable, "bench.py", "--steps", "1", "--warmup", "1"], cwd=ROOT, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode != 0 and "cusim" in (r.stdout + r.stderr)
+    r = subprocess.run([sys.executable, "-c", "import __graft_entry__ as g; g.smoke()"], cwd=ROOT, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode != 0 and "cusim" in (r.stdout + r.stderr)

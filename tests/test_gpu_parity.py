@@ -12,6 +12,29 @@ from cloudini_b200 import synth
 pytestmark = pytest.mark.gpu
 
 
+def _emulated():
+    """True when the suite is re-run by tests/test_cusim_kernels.py against the CPU emulation of the CUDA model
+    (tests/cusim: test infrastructure, the kernels' logic checked without a GPU). There "device" memory is host memory."""
+    return b"cusim" in cb.lib().cldn_b200_version()
+
+
+class _Dev:
+    """A device buffer for the device-pointer API: a torch CUDA tensor on the GPU box, a numpy array under cusim."""
+
+    def __init__(self, src=None, size=None):
+        if _emulated():
+            self.t = np.array(src, dtype=np.uint8, copy=True) if src is not None else np.zeros(size, dtype=np.uint8)
+            self.ptr = self.t.ctypes.data
+        else:
+            import torch
+            self.t = (torch.from_numpy(np.array(src, dtype=np.uint8, copy=True)).cuda() if src is not None
+                      else torch.zeros(size, dtype=torch.uint8, device="cuda"))
+            self.ptr = self.t.data_ptr()
+
+    def numpy(self):
+        return self.t if _emulated() else self.t.cpu().numpy()
+
+
 def _roundtrip_check(info, cloud, oracle, blob_expected=None, fill=0):
     enc = cb.PointcloudEncoder(info)
     blob = enc.encode(cloud)
@@ -198,18 +221,17 @@ def test_argument_errors():
 
 
 def test_batch_device_api(oracle):
-    import torch
     frames = [synth.cloud_c2(n, seed=100 + i) for i, n in enumerate([1000, 70_000, 0, 32768, 5])]
     info = synth.info_xyzi(0)
     enc = cb.PointcloudEncoder(info)
-    ins = [torch.from_numpy(c.copy()).cuda() if c.size else torch.empty(16, dtype=torch.uint8, device="cuda") for _, c in frames]
+    ins = [_Dev(src=c) if c.size else _Dev(size=16) for _, c in frames]
     caps = [cb.MaxCompressedSize(info, fi.width, True) for fi, _ in frames]
-    outs = [torch.zeros(c, dtype=torch.uint8, device="cuda") for c in caps]
-    batch = enc.make_device_batch([t.data_ptr() for t in ins], [c.size for _, c in frames], [t.data_ptr() for t in outs], caps)
+    outs = [_Dev(size=c) for c in caps]
+    batch = enc.make_device_batch([t.ptr for t in ins], [c.size for _, c in frames], [t.ptr for t in outs], caps)
     sizes = enc.encode_batch_device(batch, write_header=True, want_sizes=True)
     for (fi, c), o, s in zip(frames, outs, sizes):
         expect = oracle.encode(info, c)  # header says width 0 (one encoder for all frames): compare payloads + header
-        assert bytes(o[:s].cpu().numpy()) == expect
+        assert bytes(o.numpy()[:s]) == expect
 
 
 # ---- V5 adaptive integer sections (v5_codec.cpp) -----------------------------------------------------------------------
@@ -319,7 +341,6 @@ def test_floatn_decode_modes(oracle, monkeypatch, mode):
 def test_batch_decode_device_and_host_apis(oracle, monkeypatch, mode):
     # mode "seq": several frames x several chunks through the persistent kernel (chunks claimed chunk-index-major,
     # chunk prefixes walked by CTA 0 inside the kernel); every frame of the batch is compared, not only the first
-    import torch
     if mode:
         monkeypatch.setenv("CLDN_B200_DECODE_MODE", mode)
     info = synth.info_xyzi(50_000)
@@ -334,16 +355,16 @@ def test_batch_decode_device_and_host_apis(oracle, monkeypatch, mode):
         assert b == oracle.encode(info, c)
     hdr = len(enc.getHeader())
     # device batch decode
-    d_blobs = [torch.from_numpy(np.frombuffer(b, dtype=np.uint8).copy()).cuda() for b in blobs]
-    d_outs = [torch.zeros(50_000 * 16, dtype=torch.uint8, device="cuda") for _ in blobs]
-    batch = dec.make_device_batch([t.data_ptr() + hdr for t in d_blobs], [len(b) - hdr for b in blobs], [t.data_ptr() for t in d_outs], [50_000 * 16] * 5)
+    d_blobs = [_Dev(src=np.frombuffer(b, dtype=np.uint8)) for b in blobs]
+    d_outs = [_Dev(size=50_000 * 16) for _ in blobs]
+    batch = dec.make_device_batch([t.ptr + hdr for t in d_blobs], [len(b) - hdr for b in blobs], [t.ptr for t in d_outs], [50_000 * 16] * 5)
     dec.decode_batch_device(info, batch, sync=True)
     h_outs = [np.zeros(50_000 * 16, dtype=np.uint8) for _ in blobs]
     dec.decode_batch_host(info, [b[hdr:] for b in blobs], h_outs)
     for b, d, h in zip(blobs, d_outs, h_outs):
         want = np.zeros(50_000 * 16, dtype=np.uint8)
         oracle.decode(b, want)
-        assert np.array_equal(d.cpu().numpy(), want) and np.array_equal(h, want)
+        assert np.array_equal(d.numpy(), want) and np.array_equal(h, want)
 
 
 def test_one_shot_c_abi_like_wasm(oracle):
@@ -388,11 +409,10 @@ def test_stage2_interop_with_reference(ref, comp):
         assert np.array_equal(got, want)
         assert len(ours) < 0.9 * len(cb.PointcloudEncoder(synth.cloud_c2(1)[0]).getHeader()) + n  # actually compressed
     # device-pointer API cannot run stage 2: loud error, no silent fallback
-    import torch
     info, cloud = synth.cloud_c2(1000, seed=1)
     info.compression_opt = comp
     enc = cb.PointcloudEncoder(info)
-    t_in = torch.from_numpy(cloud.copy()).cuda()
-    t_out = torch.zeros(cb.MaxCompressedSize(info, 1000, True), dtype=torch.uint8, device="cuda")
+    t_in, cap = _Dev(src=cloud), cb.MaxCompressedSize(info, 1000, True)
+    t_out = _Dev(size=cap)
     with pytest.raises(RuntimeError, match="host-pointer API"):
-        enc.encode_batch_device(enc.make_device_batch([t_in.data_ptr()], [cloud.size], [t_out.data_ptr()], [t_out.numel()]), want_sizes=True)
+        enc.encode_batch_device(enc.make_device_batch([t_in.ptr], [cloud.size], [t_out.ptr], [cap]), want_sizes=True)
