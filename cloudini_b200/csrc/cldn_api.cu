@@ -359,6 +359,13 @@ int cldn_b200_encoder_header(const cldn_encoder_t* enc, const uint8_t** header, 
   return CLDN_OK;
 }
 
+int cldn_b200_encoder_info(const cldn_encoder_t* enc, cldn_info_t* info) {
+  if (!enc || !info) { set_error("null argument"); return CLDN_ERR_INVALID_ARGUMENT; }
+  *info = enc->info;
+  info->compression_opt = static_cast<uint8_t>(enc->stage2);  // as the caller gave it
+  return CLDN_OK;
+}
+
 const uint64_t* cldn_b200_encoder_sizes_device(const cldn_encoder_t* enc) { return enc ? enc->d_sizes.p : nullptr; }
 
 static int check_device_error(cudaStream_t stream, uint32_t* d_err, uint32_t* h_err) {

@@ -1,0 +1,270 @@
+// SURVEY.md §8(f) N2 — the DDS / ROS 2 envelope around the codec (cloudini_lib/src/ros_msg_utils.cpp:54-238).
+// Host code: the CDR header of a PointCloud2 message is a few hundred bytes of text-like fields; the point payload is
+// never touched here — it goes to the GPU codec through the C ABI (cldn_b200_encode / cldn_b200_decode).
+// CDR rules restated from the reference's vendored nanocdr (include/cloudini_lib/contrib/nanocdr.hpp:252-293 decoder
+// header checks, :346-368 / :391-414 primitives aligned to their size relative to the byte after the 4-byte
+// encapsulation header, :313-333 / :417-424 strings = u32 length including the NUL + bytes).
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/cloudini_b200_ros.h"
+#include "cldn_plan.h"
+
+using cldn::set_error;
+
+namespace {
+
+struct CdrReader {
+  const uint8_t* base;
+  size_t size, pos = 4;
+  bool big = false;
+  bool ok = true;
+  const char* why = "";
+  size_t remaining() const { return size - pos; }
+  void align(size_t n) {  // nanocdr.hpp:135-138 (origin = buffer + 4)
+    const size_t a = (n - ((pos - 4) % n)) & (n - 1);
+    pos += (a <= remaining()) ? a : remaining();  // trim_front clamps; the size check that follows reports the error
+  }
+  uint32_t u32() {
+    align(4);
+    if (remaining() < 4) { fail("Decode: not enough data to decode"); return 0; }
+    uint32_t v;
+    memcpy(&v, base + pos, 4);
+    pos += 4;
+    return big ? __builtin_bswap32(v) : v;
+  }
+  uint8_t u8() {
+    if (remaining() < 1) { fail("Decode: not enough data to decode"); return 0; }
+    return base[pos++];
+  }
+  // returns offset / length (NUL stripped) of a string
+  void str(size_t* off, uint32_t* len) {
+    const uint32_t n = u32();
+    if (!ok) return;
+    if (remaining() < n) { fail("Decode: not enough data to decode (string)"); return; }
+    *off = pos;
+    *len = (n > 0 && base[pos + n - 1] == 0) ? n - 1 : n;
+    pos += n;
+  }
+  void fail(const char* w) { if (ok) { ok = false; why = w; } }
+};
+
+struct CdrWriter {
+  std::vector<uint8_t> buf;
+  bool big = false;
+  void align(size_t n) {  // nanocdr.hpp:196-199: (size - 4) % n
+    const size_t a = (n - ((buf.size() - 4) % n)) & (n - 1);
+    buf.resize(buf.size() + a);
+  }
+  void u32(uint32_t v) {
+    align(4);
+    if (big) v = __builtin_bswap32(v);
+    const size_t at = buf.size();
+    buf.resize(at + 4);
+    memcpy(buf.data() + at, &v, 4);
+  }
+  void u8(uint8_t v) { buf.push_back(v); }
+  void str(const char* s, size_t len) {
+    u32(static_cast<uint32_t>(len + 1));
+    buf.insert(buf.end(), reinterpret_cast<const uint8_t*>(s), reinterpret_cast<const uint8_t*>(s) + len);
+    buf.push_back(0);
+  }
+};
+
+// writePointCloudHeader (ros_msg_utils.cpp:97-120) after the 4-byte encapsulation header
+void write_pc_header(CdrWriter& w, const uint8_t* dds_msg, const cldn_ros_msg_t& m) {
+  w.buf.assign({0, m.cdr_header[1], 0, 0});  // nanocdr.hpp:381-387
+  w.big = (m.cdr_header[1] & 1u) == 0;
+  w.u32(static_cast<uint32_t>(m.stamp_sec));
+  w.u32(m.stamp_nsec);
+  w.str(reinterpret_cast<const char*>(dds_msg) + m.frame_id_offset, m.frame_id_len);
+  w.u32(m.height);
+  w.u32(m.width);
+  w.u32(m.n_fields);
+  for (uint32_t i = 0; i < m.n_fields; ++i) {
+    w.str(m.fields[i].name, strlen(m.fields[i].name));
+    w.u32(m.fields[i].offset);
+    w.u8(m.fields[i].type);
+    w.u32(1);  // count, not used
+  }
+  w.u8(0);  // is_bigendian, not used
+  w.u32(m.point_step);
+  w.u32(m.point_step * m.width);
+}
+
+}  // namespace
+
+extern "C" {
+
+int cldn_b200_ros_parse(const void* dds_msg, size_t msg_bytes, cldn_ros_msg_t* out) {
+  if (!dds_msg || !out) { set_error("null argument"); return CLDN_ERR_INVALID_ARGUMENT; }
+  memset(out, 0, sizeof(*out));
+  const uint8_t* p = static_cast<const uint8_t*>(dds_msg);
+  if (msg_bytes < 4) { set_error("Decode: not enough data to decode"); return CLDN_ERR_CORRUPT_DATA; }
+  if (p[0] != 0) { set_error("Invalid CDR header: expected first byte to be 0"); return CLDN_ERR_CORRUPT_DATA; }
+  if ((p[1] & 0xFEu) != 0) { set_error("Unexpected encoding received."); return CLDN_ERR_CORRUPT_DATA; }  // only PLAIN_CDR (DDS_CDR default)
+  if (p[2] != 0 || p[3] != 0) { set_error("Extended header not supported"); return CLDN_ERR_CORRUPT_DATA; }
+  memcpy(out->cdr_header, p, 4);
+  CdrReader r{p, msg_bytes};
+  r.big = (p[1] & 1u) == 0;
+  out->stamp_sec = static_cast<int32_t>(r.u32());
+  out->stamp_nsec = r.u32();
+  r.str(&out->frame_id_offset, &out->frame_id_len);
+  out->height = r.u32();
+  out->width = r.u32();
+  const uint32_t n_fields = r.u32();
+  if (r.ok && n_fields > CLDN_MAX_FIELDS) {
+    set_error("PointCloud2 with %u fields: this build handles at most %d", n_fields, CLDN_MAX_FIELDS);
+    return CLDN_ERR_UNSUPPORTED;
+  }
+  for (uint32_t i = 0; r.ok && i < n_fields; ++i) {
+    size_t off = 0;
+    uint32_t len = 0;
+    r.str(&off, &len);
+    if (!r.ok) break;
+    if (len >= CLDN_MAX_NAME) { set_error("field name longer than %d characters", CLDN_MAX_NAME - 1); return CLDN_ERR_UNSUPPORTED; }
+    cldn_field_t& f = out->fields[i];
+    memcpy(f.name, p + off, len);
+    f.name[len] = 0;
+    f.offset = r.u32();
+    f.type = r.u8();
+    (void)r.u32();  // count
+  }
+  out->n_fields = r.ok ? n_fields : 0;
+  out->is_bigendian = r.u8();
+  out->point_step = r.u32();
+  out->row_step = r.u32();
+  const uint32_t data_len = r.u32();
+  if (r.ok && r.remaining() < data_len) r.fail("Decode: not enough data to decode (string)");
+  if (r.ok) {
+    out->data_offset = r.pos;
+    out->data_bytes = data_len;
+    r.pos += data_len;
+  }
+  out->is_dense = r.u8();
+  if (!r.ok) { set_error("%s", r.why); return CLDN_ERR_CORRUPT_DATA; }
+  return CLDN_OK;
+}
+
+int cldn_b200_ros_to_encoding_info(const cldn_ros_msg_t* msg, cldn_info_t* info) {
+  if (!msg || !info) { set_error("null argument"); return CLDN_ERR_INVALID_ARGUMENT; }
+  cldn_b200_info_init(info);  // LOSSY + ZSTD are the EncodingInfo defaults toEncodingInfo sets again (:127-128)
+  info->height = msg->height;
+  info->width = msg->width;
+  info->point_step = msg->point_step;
+  info->encoding_opt = CLDN_ENC_LOSSY;
+  info->compression_opt = CLDN_COMP_ZSTD;
+  info->n_fields = msg->n_fields;
+  memcpy(info->fields, msg->fields, sizeof(cldn_field_t) * msg->n_fields);
+  return CLDN_OK;
+}
+
+int cldn_b200_ros_apply_resolution_profile(cldn_field_t* fields, uint32_t* n_fields, const char* const* names,
+                                           const float* resolutions, size_t n_profile, const float* default_resolution) {
+  if (!fields || !n_fields || (n_profile && (!names || !resolutions))) { set_error("null argument"); return CLDN_ERR_INVALID_ARGUMENT; }
+  if (*n_fields > CLDN_MAX_FIELDS) { set_error("too many fields"); return CLDN_ERR_INVALID_ARGUMENT; }
+  // std::map semantics: the profile is keyed by name; with duplicate names in the arrays the LAST entry is the one a
+  // caller building the map with operator[] would end up with
+  auto find = [&](const char* name) -> const float* {
+    for (size_t k = n_profile; k-- > 0;) if (strcmp(names[k], name) == 0) return &resolutions[k];
+    return nullptr;
+  };
+  uint32_t w = 0;
+  for (uint32_t i = 0; i < *n_fields; ++i) {  // erase-remove of fields whose profile resolution is 0 (:221-229)
+    const float* r = find(fields[i].name);
+    if (r && *r == 0.0f) continue;
+    if (w != i) fields[w] = fields[i];
+    ++w;
+  }
+  for (uint32_t i = w; i < *n_fields; ++i) memset(&fields[i], 0, sizeof(cldn_field_t));
+  *n_fields = w;
+  for (uint32_t i = 0; i < w; ++i) {  // :231-237
+    cldn_field_t& f = fields[i];
+    if (const float* r = find(f.name)) {
+      f.has_resolution = 1;
+      f.resolution = *r;
+    } else if (default_resolution && f.type == CLDN_FLOAT32) {
+      f.has_resolution = 1;
+      f.resolution = *default_resolution;
+    }
+  }
+  return CLDN_OK;
+}
+
+int cldn_b200_ros_compress_msg(cldn_encoder_t* enc, const void* dds_msg, const cldn_ros_msg_t* msg, const void* point_data,
+                               size_t point_bytes, void* out, size_t out_capacity, size_t* written) {
+  if (!enc || !dds_msg || !msg) { set_error("null argument"); return CLDN_ERR_INVALID_ARGUMENT; }
+  const uint8_t* data = point_data ? static_cast<const uint8_t*>(point_data) : static_cast<const uint8_t*>(dds_msg) + msg->data_offset;
+  const size_t data_bytes = point_data ? point_bytes : msg->data_bytes;
+  cldn_info_t info;
+  if (int rc = cldn_b200_encoder_info(enc, &info)) return rc;
+  CdrWriter w;
+  write_pc_header(w, static_cast<const uint8_t*>(dds_msg), *msg);
+  w.u32(0);  // compressed_data length, patched below (:177-181)
+  const size_t size_at = w.buf.size() - 4, prev = w.buf.size();
+  size_t blob_cap = 0;
+  if (data_bytes != 0) {
+    if (info.point_step == 0) { set_error("convertPointCloud2ToCompressedCloud: point_step cannot be 0"); return CLDN_ERR_INVALID_ARGUMENT; }
+    blob_cap = cldn_b200_max_compressed_size(&info, data_bytes / info.point_step, 1);  // :193-196
+    if (blob_cap == 0) return CLDN_ERR_INVALID_ARGUMENT;
+  }
+  const size_t worst = prev + blob_cap + 1 + 3 + 4 + 9;
+  if (!out) {
+    if (written) *written = worst;
+    return CLDN_OK;
+  }
+  if (out_capacity < worst) { set_error("output buffer smaller than the worst-case message (%zu bytes)", worst); return CLDN_ERR_BUFFER_TOO_SMALL; }
+  uint8_t* o = static_cast<uint8_t*>(out);
+  memcpy(o, w.buf.data(), prev);
+  size_t blob = 0;
+  if (data_bytes != 0) {
+    if (int rc = cldn_b200_encode(enc, data, data_bytes, o + prev, blob_cap, 1, &blob, CLDN_MEM_HOST)) return rc;
+    const uint32_t sz = static_cast<uint32_t>(blob);
+    memcpy(o + size_at, &sz, 4);  // the reference memcpy's the native value, whatever the message's endianness (:203)
+  }
+  // trailing fields (:209-212): is_dense (1 byte, no alignment), format = "cloudini"
+  CdrWriter t;
+  t.buf.resize(prev + blob);  // only the length matters for the alignment arithmetic
+  t.big = w.big;
+  t.u8(msg->is_dense);
+  t.str("cloudini", 8);
+  memcpy(o + prev + blob, t.buf.data() + prev + blob, t.buf.size() - prev - blob);
+  if (written) *written = t.buf.size();
+  return CLDN_OK;
+}
+
+int cldn_b200_ros_decompress_msg(cldn_decoder_t* dec, const void* dds_msg, const cldn_ros_msg_t* msg, void* out,
+                                 size_t out_capacity, size_t* written) {
+  if (!dec || !dds_msg || !msg) { set_error("null argument"); return CLDN_ERR_INVALID_ARGUMENT; }
+  // uint32 arithmetic like the reference (width * height * point_step, :136)
+  const size_t cloud_bytes = static_cast<uint32_t>(msg->width * msg->height * msg->point_step);
+  CdrWriter w;
+  write_pc_header(w, static_cast<const uint8_t*>(dds_msg), *msg);
+  w.u32(static_cast<uint32_t>(cloud_bytes));
+  const size_t prev = w.buf.size();
+  const size_t total = prev + cloud_bytes + 1;
+  if (!out) {
+    if (written) *written = total;
+    return CLDN_OK;
+  }
+  if (out_capacity < total) { set_error("output buffer smaller than the message (%zu bytes)", total); return CLDN_ERR_BUFFER_TOO_SMALL; }
+  uint8_t* o = static_cast<uint8_t*>(out);
+  memcpy(o, w.buf.data(), prev);
+  if (cloud_bytes != 0) {
+    const uint8_t* blob = static_cast<const uint8_t*>(dds_msg) + msg->data_offset;
+    cldn_info_t info;
+    size_t hdr = 0;
+    if (int rc = cldn_b200_decode_header(blob, msg->data_bytes, &info, &hdr)) return rc;
+    memset(o + prev, 0, cloud_bytes);  // std::vector::resize zero-fills; the decoder only writes declared field bytes (:153)
+    if (int rc = cldn_b200_decode(dec, &info, blob + hdr, msg->data_bytes - hdr, o + prev, cloud_bytes, CLDN_MEM_HOST)) return rc;
+  }
+  o[prev + cloud_bytes] = msg->is_dense;
+  if (written) *written = total;
+  return CLDN_OK;
+}
+
+}  // extern "C"

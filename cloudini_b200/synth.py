@@ -185,6 +185,79 @@ def random_layout_case(seed: int):
     return info, np.ascontiguousarray(buf).reshape(-1)
 
 
+def pointcloud2_msg(fields, point_step: int, cloud, width=None, height: int = 1, frame_id: str = "lidar_link",
+                    stamp=(1700000000, 123456789), is_dense: bool = True, row_step=None, big_endian: bool = False) -> bytes:
+    """A DDS (PLAIN_CDR) serialised sensor_msgs/msg/PointCloud2: 4-byte encapsulation header, then the members in
+    declaration order, every primitive aligned to its size relative to the byte after the header. `fields` is a list of
+    (name, offset, FieldType). Test input for the envelope functions (ros_msg_utils.cpp:54-95 reads exactly this)."""
+    import struct
+    e = ">" if big_endian else "<"
+    b = bytearray([0, 0 if big_endian else 1, 0, 0])
+
+    def align(n):
+        while (len(b) - 4) % n:
+            b.append(0)
+
+    def u32(v):
+        align(4)
+        b.extend(struct.pack(e + "I", v & 0xFFFFFFFF))
+
+    def string(t: str):
+        raw = t.encode()
+        u32(len(raw) + 1)
+        b.extend(raw + b"\0")
+
+    data = np.ascontiguousarray(cloud).view(np.uint8).reshape(-1)
+    n = data.size // point_step if point_step else 0
+    width = n // height if width is None else width
+    align(4)
+    b.extend(struct.pack(e + "i", stamp[0]))
+    u32(stamp[1])
+    string(frame_id)
+    u32(height)
+    u32(width)
+    u32(len(fields))
+    for name, offset, ftype in fields:
+        string(name)
+        u32(offset)
+        b.append(int(ftype))
+        u32(1)
+    b.append(1 if big_endian else 0)
+    u32(point_step)
+    u32(point_step * width if row_step is None else row_step)
+    u32(data.size)
+    b.extend(data.tobytes())
+    b.append(1 if is_dense else 0)
+    return bytes(b)
+
+
+def cloud_viz(n: int = 50_000, seed: int = 7, step: int = 16, dup_rate: float = 0.3, nan_rate: float = 0.02):
+    """Input for applyVizLossyPreprocessing: a lidar-like XYZ cloud in which a share of the points repeats an EARLIER
+    point's voxel (same coordinates +- a sub-resolution jitter) and a share has a NaN / inf coordinate. Extra bytes of
+    the point (intensity / ring / padding) are random so that 'first occurrence wins' is visible in the output."""
+    rng = np.random.default_rng(seed)
+    xyz = np.stack(_lidar_xyz(n, rng), axis=1) if n else np.zeros((0, 3), dtype=np.float32)
+    if n > 1:
+        k = int(n * dup_rate)
+        dst = rng.integers(1, n, k)
+        src = (dst * rng.random(k)).astype(np.int64)  # an earlier index
+        jitter = (rng.random((k, 3)).astype(np.float32) - 0.5) * np.float32(2e-4)
+        # snap the source to a voxel centre first so that the jitter stays inside the voxel
+        xyz[src] = np.round(xyz[src] * 1000.0).astype(np.float32) / np.float32(1000.0)
+        xyz[dst] = xyz[src] + jitter
+        bad = rng.integers(0, n, int(n * nan_rate))
+        xyz[bad, rng.integers(0, 3, bad.size)] = rng.choice(np.array([np.nan, np.inf, -np.inf], dtype=np.float32), bad.size)
+    buf = rng.integers(0, 256, (n, step), dtype=np.uint8)
+    buf[:, :12] = xyz.view(np.uint8).reshape(n, 12)
+    info = EncodingInfo(width=n, height=1, point_step=step, encoding_opt=EncodingOptions.LOSSY,
+                        compression_opt=CompressionOption.NONE, use_threads=False)
+    info.fields = [PointField("x", 0, FieldType.FLOAT32, 0.001), PointField("y", 4, FieldType.FLOAT32, 0.001),
+                   PointField("z", 8, FieldType.FLOAT32, 0.001)]
+    if step >= 16:
+        info.fields.append(PointField("intensity", 12, FieldType.FLOAT32, 0.01))
+    return info, buf.reshape(-1)
+
+
 def fnv1a64(data) -> int:
     """FNV-1a 64-bit (the fingerprint mcap_codec_benchmark --hash prints, tools/src/mcap_codec_benchmark.cpp:103-109)."""
     h = 0xCBF29CE484222325

@@ -120,6 +120,8 @@ int cldn_b200_encoder_create(const cldn_info_t* info, int device, void* stream, 
 void cldn_b200_encoder_destroy(cldn_encoder_t* enc);
 /* getHeader() (cloudini.hpp:176-178) */
 int cldn_b200_encoder_header(const cldn_encoder_t* enc, const uint8_t** header, size_t* header_bytes);
+/* getEncodingInfo() (cloudini.hpp:171-173): the EncodingInfo the encoder was created from. */
+int cldn_b200_encoder_info(const cldn_encoder_t* enc, cldn_info_t* info);
 
 /* PointcloudEncoder::encode(ConstBufferView, BufferView&, bool write_header) (cloudini.cpp:522-623).
  * Point count = cloud_bytes / point_step (width*height of the info is NOT consulted, as in the reference).

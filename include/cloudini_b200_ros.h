@@ -1,0 +1,90 @@
+/*
+ * cloudini_b200 — C ABI of the callers either side of the codec:
+ *   N3  applyVizLossyPreprocessing  (cloudini_lib/src/ros_msg_utils.cpp:249-341): NaN/inf drop + order-preserving voxel
+ *       de-duplication as sm_100a kernels directly in front of the encode launch;
+ *   N2  the DDS / ROS 2 envelope    (cloudini_lib/src/ros_msg_utils.cpp:54-238): CDR (de)serialisation of
+ *       sensor_msgs/msg/PointCloud2 and point_cloud_interfaces/msg/CompressedPointCloud2 around the codec.
+ * Same conventions as cloudini_b200.h (status codes, cldn_b200_last_error(), caller-owned buffers, no CPU fallback for
+ * anything that touches point data: the envelope functions parse / write the small CDR header on the host and hand the
+ * point payload to the GPU codec).
+ */
+#ifndef CLOUDINI_B200_ROS_H_
+#define CLOUDINI_B200_ROS_H_
+
+#include "cloudini_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- N3: visualisation-oriented lossy preprocessing ------------------------------------------------------------- */
+typedef struct cldn_preproc cldn_preproc_t; /* owns the voxel hash table, tile status words and staging buffers */
+
+int cldn_b200_preproc_create(int device, void* stream, cldn_preproc_t** out);
+void cldn_b200_preproc_destroy(cldn_preproc_t* pp);
+
+/* applyVizLossyPreprocessing(RosPointCloud2&) (ros_msg_utils.cpp:249-341, contract ros_msg_utils.hpp:198-221).
+ *  - the geometry triple is detected structurally: fields[0..2] FLOAT32 with the same resolution at offsets b, b+4, b+8
+ *    (names are never read); without it, with a non-positive / non-finite resolution or with an empty cloud the call is
+ *    a no-op exactly like the reference: *applied = 0, `info` and `out` untouched, *kept_points = input point count;
+ *  - points whose x, y or z is NaN / +-inf are dropped; of the points that quantise (lround(v * (1/res)), 21 bits per
+ *    axis, packVoxelKey21 ros_msg_utils.cpp:42-49) to the same voxel only the FIRST survives; survivors keep their order
+ *    and all `point_step` bytes;
+ *  - on success `info` is updated like pc_info: width = kept, height = 1, every FLOAT64 field without a resolution gets
+ *    1e-6 (so the planner routes it through the lossy coder).
+ * `cloud` / `out` live in `mem` memory; `out_capacity` >= cloud_bytes is always enough. CLDN_MEM_DEVICE: the kernels run
+ * on the handle's stream and the call waits for the 4-byte survivor count. */
+int cldn_b200_viz_lossy_preprocess(cldn_preproc_t* pp, cldn_info_t* info, const void* cloud, size_t cloud_bytes,
+                                   void* out, size_t out_capacity, size_t* kept_points, int* applied, int mem);
+
+/* ---- N2: DDS envelope ------------------------------------------------------------------------------------------- */
+/* Parsed view of a CDR-serialised sensor_msgs/msg/PointCloud2 or point_cloud_interfaces/msg/CompressedPointCloud2
+ * (cloudini_ros::RosPointCloud2, ros_msg_utils.hpp:32-148). Offsets point into the caller's message buffer. */
+typedef struct cldn_ros_msg_t {
+  uint8_t cdr_header[4];     /* nanocdr::CdrHeader as found on the wire: {0, encapsulation, 0, 0} */
+  int32_t stamp_sec;
+  uint32_t stamp_nsec;
+  size_t frame_id_offset;    /* first character of header.frame_id inside the message */
+  uint32_t frame_id_len;     /* without the trailing NUL */
+  uint32_t height, width;
+  uint32_t n_fields;
+  cldn_field_t fields[CLDN_MAX_FIELDS]; /* has_resolution = 0 after parsing (the message carries none) */
+  uint8_t is_bigendian, is_dense;
+  uint32_t point_step, row_step;
+  size_t data_offset;        /* PointCloud2::data / CompressedPointCloud2::compressed_data */
+  size_t data_bytes;
+} cldn_ros_msg_t;
+
+/* getDeserializedPointCloudMessage (ros_msg_utils.cpp:54-95). Host memory. Little-endian PLAIN_CDR like the reference's
+ * callers produce; CLDN_ERR_CORRUPT_DATA where nanocdr throws ("not enough data", bad header). */
+int cldn_b200_ros_parse(const void* dds_msg, size_t msg_bytes, cldn_ros_msg_t* out);
+
+/* toEncodingInfo (ros_msg_utils.cpp:122-131): LOSSY + ZSTD defaults, fields copied. */
+int cldn_b200_ros_to_encoding_info(const cldn_ros_msg_t* msg, cldn_info_t* info);
+
+/* applyResolutionProfile (ros_msg_utils.cpp:217-238) on a field list (msg->fields / &msg->n_fields — the reference's
+ * converter applies it to the message's own fields, tools/src/mcap_converter.cpp:189, so removed fields also leave the
+ * re-written message header): a profile entry of 0 removes the field, other entries set the field's resolution,
+ * FLOAT32 fields without an entry get *default_resolution when it is non-NULL. */
+int cldn_b200_ros_apply_resolution_profile(cldn_field_t* fields, uint32_t* n_fields, const char* const* names,
+                                           const float* resolutions, size_t n_profile, const float* default_resolution);
+
+/* convertPointCloud2ToCompressedCloud (ros_msg_utils.cpp:167-213): PointCloud2 message -> CompressedPointCloud2
+ * message (same CDR header, width/height/fields/point_step, compressed_data = Cloudini blob with header, is_dense,
+ * format "cloudini"). The point payload is encoded on the GPU through `enc` (created from `encoding_info`; its
+ * compression_opt may be LZ4/ZSTD: host-pointer API). `point_data` overrides the payload (e.g. the output of
+ * cldn_b200_viz_lossy_preprocess, with msg->width already updated); NULL = the message's own data.
+ * Query the worst-case size with out == NULL (*written receives it). */
+int cldn_b200_ros_compress_msg(cldn_encoder_t* enc, const void* dds_msg, const cldn_ros_msg_t* msg,
+                               const void* point_data, size_t point_bytes, void* out, size_t out_capacity,
+                               size_t* written);
+
+/* convertCompressedCloudToPointCloud2 (ros_msg_utils.cpp:134-165): CompressedPointCloud2 message -> PointCloud2 message,
+ * the blob decoded on the GPU through `dec` straight into the output message. out == NULL queries the exact size. */
+int cldn_b200_ros_decompress_msg(cldn_decoder_t* dec, const void* dds_msg, const cldn_ros_msg_t* msg, void* out,
+                                 size_t out_capacity, size_t* written);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CLOUDINI_B200_ROS_H_ */

@@ -69,10 +69,58 @@ class RefOracle:
         L.ref_time_encode.argtypes = [C.c_char_p, C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.POINTER(C.c_size_t)]
         L.ref_time_decode.restype = C.c_double
         L.ref_time_decode.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int]
+        if hasattr(L, "ref_viz_preprocess"):  # N2 / N3 (ros_msg_utils.cpp); older prebuilt wrappers do not have them
+            L.ref_viz_preprocess.restype = C.c_longlong
+            L.ref_viz_preprocess.argtypes = [C.c_char_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_char_p, C.c_size_t]
+            L.ref_ros_describe.restype = C.c_longlong
+            L.ref_ros_describe.argtypes = [C.c_void_p, C.c_size_t, C.c_char_p, C.c_size_t]
+            L.ref_ros_compress.restype = C.c_longlong
+            L.ref_ros_compress.argtypes = [C.c_void_p, C.c_size_t, C.c_char_p, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t]
+            L.ref_ros_decompress.restype = C.c_longlong
+            L.ref_ros_decompress.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
         self.L = L
 
     def _err(self):
         return self.L.ref_last_error().decode("utf-8", "replace")
+
+    # ---- N3 / N2: cloudini_ros (ros_msg_utils.cpp) ----
+    def viz_preprocess(self, info: cb.EncodingInfo, cloud):
+        """applyVizLossyPreprocessing on a raw cloud. Returns (EncodingInfo after, surviving bytes)."""
+        a = _u8(cloud)
+        out = np.zeros(max(a.size, 1), dtype=np.uint8)
+        ybuf = C.create_string_buffer(1 << 16)
+        n = self.L.ref_viz_preprocess(_yaml(info), int(info.version), a.ctypes.data, a.size, out.ctypes.data, out.size, ybuf, len(ybuf))
+        if n < 0:
+            raise RuntimeError(self._err())
+        after = cb.EncodingInfoFromYAML(ybuf.value.decode())
+        after.version = info.version
+        return after, out[:n * info.point_step]
+
+    def ros_describe(self, msg: bytes) -> str:
+        a = _u8(msg)
+        buf = C.create_string_buffer(1 << 16)
+        if self.L.ref_ros_describe(a.ctypes.data, a.size, buf, len(buf)) < 0:
+            raise RuntimeError(self._err())
+        return buf.value.decode()
+
+    def ros_compress(self, msg: bytes, profile=None, default_resolution=None, viz=False, encoding_opt=1, compression_opt=0, version=5) -> bytes:
+        """The converter's per-message step (tools/src/mcap_converter.cpp:184-204)."""
+        a = _u8(msg)
+        text = ";".join(f"{k}={float(v)!r}" for k, v in (profile or {}).items()).encode()
+        out = np.zeros(2 * a.size + (1 << 16), dtype=np.uint8)
+        n = self.L.ref_ros_compress(a.ctypes.data, a.size, text, -1.0 if default_resolution is None else float(default_resolution),
+                                    1 if viz else 0, int(encoding_opt), int(compression_opt), int(version), out.ctypes.data, out.size)
+        if n < 0:
+            raise RuntimeError(self._err())
+        return bytes(out[:n])
+
+    def ros_decompress(self, msg: bytes, capacity: int) -> bytes:
+        a = _u8(msg)
+        out = np.zeros(capacity, dtype=np.uint8)
+        n = self.L.ref_ros_decompress(a.ctypes.data, a.size, out.ctypes.data, out.size)
+        if n < 0:
+            raise RuntimeError(self._err())
+        return bytes(out[:n])
 
     def max_compressed_size(self, info: cb.EncodingInfo, points: int, include_header: bool = True) -> int:
         return int(self.L.ref_max_compressed_size(_yaml(info), info.version, points, int(include_header)))

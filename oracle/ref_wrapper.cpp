@@ -10,6 +10,10 @@
 // The configuration crosses the boundary as the reference's own YAML header text
 // (the same convention as cldn_EncodePointcloudData, wasm_functions.h:88-93).
 //
+// and, for SURVEY.md §8(f) N2 / N3 (the callers either side of the codec),
+//   cloudini_ros::getDeserializedPointCloudMessage / applyResolutionProfile / toEncodingInfo /
+//   convertPointCloud2ToCompressedCloud / convertCompressedCloudToPointCloud2 / applyVizLossyPreprocessing
+//                                            (cloudini_lib/src/ros_msg_utils.cpp:54-341)
 // No reference source is copied: this file only #includes the reference's public headers.
 #include <chrono>
 #include <cstdint>
@@ -19,6 +23,7 @@
 #include <vector>
 
 #include "cloudini_lib/cloudini.hpp"
+#include "cloudini_lib/ros_msg_utils.hpp"
 
 namespace {
 thread_local std::string g_err;
@@ -192,6 +197,117 @@ double ref_time_decode(const uint8_t* blob, size_t blob_bytes, int reps, int thr
   } catch (const std::exception& e) {
     g_err = e.what();
     return -1.0;
+  }
+}
+
+// ---- N3: applyVizLossyPreprocessing on a raw cloud described by the YAML header text ------------------------------------
+// Returns the number of surviving points (-1 on exception); the rewritten cloud goes to `out`, the updated EncodingInfo
+// (width, height, FLOAT64 resolutions) to yaml_out.
+long long ref_viz_preprocess(const char* yaml, int version, const uint8_t* cloud, size_t cloud_bytes, uint8_t* out,
+                             size_t out_capacity, char* yaml_out, size_t yaml_capacity) {
+  try {
+    Cloudini::EncodingInfo info = infoFromYaml(yaml, version, 0);
+    cloudini_ros::RosPointCloud2 pc;
+    pc.height = info.height;
+    pc.width = info.width;
+    pc.fields = info.fields;
+    pc.point_step = info.point_step;
+    pc.row_step = info.point_step * info.width;
+    pc.data = Cloudini::ConstBufferView(cloud, cloud_bytes);
+    cloudini_ros::applyVizLossyPreprocessing(pc);
+    if (pc.data.size() > out_capacity) { g_err = "output too small"; return -1; }
+    if (pc.data.size()) memcpy(out, pc.data.data(), pc.data.size());
+    Cloudini::EncodingInfo after = cloudini_ros::toEncodingInfo(pc);
+    after.encoding_opt = info.encoding_opt;
+    after.compression_opt = info.compression_opt;
+    after.version = info.version;
+    const std::string y = Cloudini::EncodingInfoToYAML(after);
+    if (y.size() + 1 > yaml_capacity) { g_err = "yaml buffer too small"; return -1; }
+    memcpy(yaml_out, y.c_str(), y.size() + 1);
+    return pc.point_step ? static_cast<long long>(pc.data.size() / pc.point_step) : 0;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return -1;
+  }
+}
+
+// ---- N2: DDS envelope ------------------------------------------------------------------------------------------------------
+static cloudini_ros::ResolutionProfile parseProfile(const char* text) {  // "name=res;name=res"
+  cloudini_ros::ResolutionProfile p;
+  std::string t = text ? text : "";
+  size_t pos = 0;
+  while (pos < t.size()) {
+    size_t end = t.find(';', pos);
+    if (end == std::string::npos) end = t.size();
+    const std::string item = t.substr(pos, end - pos);
+    const size_t eq = item.find('=');
+    if (eq != std::string::npos) p[item.substr(0, eq)] = std::stof(item.substr(eq + 1));
+    pos = end + 1;
+  }
+  return p;
+}
+
+// Canonical one-line-per-item description of a parsed message (compared verbatim with the product's parser).
+long long ref_ros_describe(const uint8_t* msg, size_t msg_bytes, char* out, size_t capacity) {
+  try {
+    auto pc = cloudini_ros::getDeserializedPointCloudMessage(Cloudini::ConstBufferView(msg, msg_bytes));
+    std::string t;
+    t += "stamp " + std::to_string(pc.ros_header.stamp_sec) + " " + std::to_string(pc.ros_header.stamp_nsec) + "\n";
+    t += "frame_id " + pc.ros_header.frame_id + "\n";
+    t += "height " + std::to_string(pc.height) + " width " + std::to_string(pc.width) + "\n";
+    for (const auto& f : pc.fields) {
+      t += "field " + f.name + " " + std::to_string(f.offset) + " " + std::to_string(static_cast<int>(f.type)) + "\n";
+    }
+    t += "point_step " + std::to_string(pc.point_step) + " row_step " + std::to_string(pc.row_step) + "\n";
+    t += "data " + std::to_string(pc.data.data() - msg) + " " + std::to_string(pc.data.size()) + "\n";
+    t += "is_dense " + std::to_string(pc.is_dense ? 1 : 0) + "\n";
+    if (t.size() + 1 > capacity) { g_err = "text buffer too small"; return -1; }
+    memcpy(out, t.c_str(), t.size() + 1);
+    return static_cast<long long>(t.size());
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return -1;
+  }
+}
+
+// The per-message step of the reference's converter (tools/src/mcap_converter.cpp:184-204): parse, apply the resolution
+// profile, optionally the viz preprocessing, toEncodingInfo, convertPointCloud2ToCompressedCloud.
+// default_resolution < 0 = none. Returns the size of the CompressedPointCloud2 message, -1 on exception.
+long long ref_ros_compress(const uint8_t* msg, size_t msg_bytes, const char* profile, float default_resolution, int viz,
+                           int encoding_opt, int compression_opt, int version, uint8_t* out, size_t out_capacity) {
+  try {
+    auto pc = cloudini_ros::getDeserializedPointCloudMessage(Cloudini::ConstBufferView(msg, msg_bytes));
+    std::optional<float> def;
+    if (default_resolution >= 0.0f) def = default_resolution;
+    cloudini_ros::applyResolutionProfile(parseProfile(profile), pc.fields, def);
+    if (viz) cloudini_ros::applyVizLossyPreprocessing(pc);
+    auto info = cloudini_ros::toEncodingInfo(pc);
+    info.encoding_opt = static_cast<Cloudini::EncodingOptions>(encoding_opt);
+    info.compression_opt = static_cast<Cloudini::CompressionOption>(compression_opt);
+    info.version = static_cast<uint8_t>(version);
+    info.use_threads = false;
+    std::vector<uint8_t> result;
+    cloudini_ros::convertPointCloud2ToCompressedCloud(pc, info, result);
+    if (result.size() > out_capacity) { g_err = "output too small"; return -1; }
+    memcpy(out, result.data(), result.size());
+    return static_cast<long long>(result.size());
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return -1;
+  }
+}
+
+long long ref_ros_decompress(const uint8_t* msg, size_t msg_bytes, uint8_t* out, size_t out_capacity) {
+  try {
+    auto pc = cloudini_ros::getDeserializedPointCloudMessage(Cloudini::ConstBufferView(msg, msg_bytes));
+    std::vector<uint8_t> result;
+    cloudini_ros::convertCompressedCloudToPointCloud2(pc, result);
+    if (result.size() > out_capacity) { g_err = "output too small"; return -1; }
+    memcpy(out, result.data(), result.size());
+    return static_cast<long long>(result.size());
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return -1;
   }
 }
 

@@ -18,7 +18,8 @@ CSRC = os.path.join(ROOT, "cloudini_b200", "csrc")
 OUT_DIR = os.path.join(HERE, "_build")
 GEN = os.path.join(OUT_DIR, "csrc")
 LIB = os.path.join(OUT_DIR, "libcloudini_b200_cusim.so")
-SOURCES = ["cldn_host.cpp", "cldn_encode.cu", "cldn_decode.cu", "cldn_decode_tiles.cu", "cldn_sections.cu", "cldn_api.cu"]
+sys.path.insert(0, ROOT)
+from cloudini_b200.build import SOURCES  # noqa: E402  (the same translation units as the product build)
 
 PTX = {
     "ld.relaxed.gpu.global.u64": lambda outs, ins: f"{outs[0]} = __atomic_load_n({ins[0]}, __ATOMIC_RELAXED); ::cusim::poll_yield();",
@@ -129,7 +130,7 @@ def _rewrite_asm(text, fname):
 
 
 def transform(text, fname):
-    text = text.replace('#include "../../include/cloudini_b200.h"', f'#include "{os.path.join(ROOT, "include", "cloudini_b200.h")}"')
+    text = re.sub(r'#include "\.\./\.\./include/(\w+\.h)"', lambda m: f'#include "{os.path.join(ROOT, "include", m.group(1))}"', text)
     text = re.sub(r"extern\s+__shared__\s+(?:__align__\(\d+\)\s+)?uint8_t\s+(\w+)\[\];",
                   r"uint8_t* const \1 = static_cast<uint8_t*>(::cusim::dyn_smem());", text)
     text = re.sub(r"\b__noinline__\b", "__attribute__((noinline))", text)  # a macro of that name would break libstdc++
@@ -144,7 +145,7 @@ def needs_build():
         return True
     t = os.path.getmtime(LIB)
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, f) for f in ("cuda_runtime.h", "cusim.cpp", "build_cusim.py")]
-    deps.append(os.path.join(ROOT, "include", "cloudini_b200.h"))
+    deps += [os.path.join(ROOT, "include", f) for f in ("cloudini_b200.h", "cloudini_b200_ros.h")]
     return any(os.path.getmtime(d) > t for d in deps)
 
 

@@ -36,7 +36,7 @@ def _run_gpu_suite(cusim_lib, extra_env, selection):
 
 
 def test_parity_suite_under_emulation(cusim_lib):
-    out = _run_gpu_suite(cusim_lib, {"CLDN_B200_FUZZ": "1", "CLDN_B200_FUZZ_SEEDS": "60"}, ["tests/test_gpu_parity.py"])
+    out = _run_gpu_suite(cusim_lib, {"CLDN_B200_FUZZ": "1", "CLDN_B200_FUZZ_SEEDS": "60"}, ["tests/test_gpu_parity.py", "tests/test_gpu_ros.py"])
     assert " passed" in out and "failed" not in out
 
 
@@ -44,8 +44,8 @@ def test_parity_suite_under_emulation(cusim_lib):
 def test_thread_order_and_cta_concurrency_do_not_matter(cusim_lib, order, workers):
     # reverse / shuffled resume order inside a CTA, 1..8 OS threads running CTAs: same bytes (look-backs, persistent
     # chunk claims and the in-kernel chunk walk are the protocols this exercises)
-    sel = ["tests/test_gpu_parity.py", "-k",
-           "float_clouds_sizes or adversarial or int_min or decode_modes or batch or c3_padded or v5_ or lossless or padded_and_unaligned"]
+    sel = ["tests/test_gpu_parity.py", "tests/test_gpu_ros.py", "-k",
+           "float_clouds_sizes or adversarial or int_min or decode_modes or batch or c3_padded or v5_ or lossless or padded_and_unaligned or viz_"]
     _run_gpu_suite(cusim_lib, {"CUSIM_ORDER": order, "CUSIM_WORKERS": workers}, sel)
 
 

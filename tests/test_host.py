@@ -15,9 +15,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_library_exports_every_declared_symbol(lib_built):
-    text = open(os.path.join(ROOT, "include", "cloudini_b200.h")).read()
+    text = "".join(open(os.path.join(ROOT, "include", h)).read() for h in ("cloudini_b200.h", "cloudini_b200_ros.h"))
     declared = sorted(set(re.findall(r"\b(cldn_b200_\w+)\s*\(", text)))
-    assert len(declared) >= 20
+    assert len(declared) >= 28
     L = C.CDLL(lib_built)
     missing = [s for s in declared if not hasattr(L, s)]
     assert not missing, missing
@@ -152,3 +152,6 @@ def test_no_cpu_fallback_without_gpu(lib_built):
         cb.PointcloudEncoder(info)
     with pytest.raises(RuntimeError, match="no CPU fallback|CUDA"):
         cb.PointcloudDecoder()
+    from cloudini_b200 import ros
+    with pytest.raises(RuntimeError, match="no CPU fallback|CUDA"):
+        ros.VizPreprocessor()
