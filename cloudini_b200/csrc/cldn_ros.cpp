@@ -76,12 +76,12 @@ struct CdrWriter {
 };
 
 // writePointCloudHeader (ros_msg_utils.cpp:97-120) after the 4-byte encapsulation header
-void write_pc_header(CdrWriter& w, const uint8_t* dds_msg, const cldn_ros_msg_t& m) {
+void write_pc_header(CdrWriter& w, const cldn_ros_msg_t& m) {
   w.buf.assign({0, m.cdr_header[1], 0, 0});  // nanocdr.hpp:381-387
   w.big = (m.cdr_header[1] & 1u) == 0;
   w.u32(static_cast<uint32_t>(m.stamp_sec));
   w.u32(m.stamp_nsec);
-  w.str(reinterpret_cast<const char*>(dds_msg) + m.frame_id_offset, m.frame_id_len);
+  w.str(m.frame_id ? m.frame_id : "", m.frame_id ? m.frame_id_len : 0);
   w.u32(m.height);
   w.u32(m.width);
   w.u32(m.n_fields);
@@ -113,7 +113,9 @@ int cldn_b200_ros_parse(const void* dds_msg, size_t msg_bytes, cldn_ros_msg_t* o
   r.big = (p[1] & 1u) == 0;
   out->stamp_sec = static_cast<int32_t>(r.u32());
   out->stamp_nsec = r.u32();
-  r.str(&out->frame_id_offset, &out->frame_id_len);
+  size_t frame_off = 4;
+  r.str(&frame_off, &out->frame_id_len);
+  out->frame_id = reinterpret_cast<const char*>(p) + frame_off;
   out->height = r.u32();
   out->width = r.u32();
   const uint32_t n_fields = r.u32();
@@ -141,7 +143,7 @@ int cldn_b200_ros_parse(const void* dds_msg, size_t msg_bytes, cldn_ros_msg_t* o
   const uint32_t data_len = r.u32();
   if (r.ok && r.remaining() < data_len) r.fail("Decode: not enough data to decode (string)");
   if (r.ok) {
-    out->data_offset = r.pos;
+    out->data = p + r.pos;
     out->data_bytes = data_len;
     r.pos += data_len;
   }
@@ -195,15 +197,14 @@ int cldn_b200_ros_apply_resolution_profile(cldn_field_t* fields, uint32_t* n_fie
   return CLDN_OK;
 }
 
-int cldn_b200_ros_compress_msg(cldn_encoder_t* enc, const void* dds_msg, const cldn_ros_msg_t* msg, const void* point_data,
-                               size_t point_bytes, void* out, size_t out_capacity, size_t* written) {
-  if (!enc || !dds_msg || !msg) { set_error("null argument"); return CLDN_ERR_INVALID_ARGUMENT; }
-  const uint8_t* data = point_data ? static_cast<const uint8_t*>(point_data) : static_cast<const uint8_t*>(dds_msg) + msg->data_offset;
-  const size_t data_bytes = point_data ? point_bytes : msg->data_bytes;
+int cldn_b200_ros_compress_msg(cldn_encoder_t* enc, const cldn_ros_msg_t* msg, void* out, size_t out_capacity, size_t* written) {
+  if (!enc || !msg || (!msg->data && msg->data_bytes)) { set_error("null argument"); return CLDN_ERR_INVALID_ARGUMENT; }
+  const uint8_t* data = msg->data;
+  const size_t data_bytes = msg->data_bytes;
   cldn_info_t info;
   if (int rc = cldn_b200_encoder_info(enc, &info)) return rc;
   CdrWriter w;
-  write_pc_header(w, static_cast<const uint8_t*>(dds_msg), *msg);
+  write_pc_header(w, *msg);
   w.u32(0);  // compressed_data length, patched below (:177-181)
   const size_t size_at = w.buf.size() - 4, prev = w.buf.size();
   size_t blob_cap = 0;
@@ -237,13 +238,12 @@ int cldn_b200_ros_compress_msg(cldn_encoder_t* enc, const void* dds_msg, const c
   return CLDN_OK;
 }
 
-int cldn_b200_ros_decompress_msg(cldn_decoder_t* dec, const void* dds_msg, const cldn_ros_msg_t* msg, void* out,
-                                 size_t out_capacity, size_t* written) {
-  if (!dec || !dds_msg || !msg) { set_error("null argument"); return CLDN_ERR_INVALID_ARGUMENT; }
+int cldn_b200_ros_decompress_msg(cldn_decoder_t* dec, const cldn_ros_msg_t* msg, void* out, size_t out_capacity, size_t* written) {
+  if (!dec || !msg || (!msg->data && msg->data_bytes)) { set_error("null argument"); return CLDN_ERR_INVALID_ARGUMENT; }
   // uint32 arithmetic like the reference (width * height * point_step, :136)
   const size_t cloud_bytes = static_cast<uint32_t>(msg->width * msg->height * msg->point_step);
   CdrWriter w;
-  write_pc_header(w, static_cast<const uint8_t*>(dds_msg), *msg);
+  write_pc_header(w, *msg);
   w.u32(static_cast<uint32_t>(cloud_bytes));
   const size_t prev = w.buf.size();
   const size_t total = prev + cloud_bytes + 1;
@@ -255,7 +255,7 @@ int cldn_b200_ros_decompress_msg(cldn_decoder_t* dec, const void* dds_msg, const
   uint8_t* o = static_cast<uint8_t*>(out);
   memcpy(o, w.buf.data(), prev);
   if (cloud_bytes != 0) {
-    const uint8_t* blob = static_cast<const uint8_t*>(dds_msg) + msg->data_offset;
+    const uint8_t* blob = msg->data;
     cldn_info_t info;
     size_t hdr = 0;
     if (int rc = cldn_b200_decode_header(blob, msg->data_bytes, &info, &hdr)) return rc;

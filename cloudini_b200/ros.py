@@ -24,10 +24,10 @@ __all__ = ["RosPointCloud2", "getDeserializedPointCloudMessage", "applyResolutio
 
 class _CRosMsg(C.Structure):
     _fields_ = [("cdr_header", C.c_uint8 * 4), ("stamp_sec", C.c_int32), ("stamp_nsec", C.c_uint32),
-                ("frame_id_offset", C.c_size_t), ("frame_id_len", C.c_uint32), ("height", C.c_uint32),
+                ("frame_id", C.c_void_p), ("frame_id_len", C.c_uint32), ("height", C.c_uint32),
                 ("width", C.c_uint32), ("n_fields", C.c_uint32), ("fields", _CField * CLDN_MAX_FIELDS),
                 ("is_bigendian", C.c_uint8), ("is_dense", C.c_uint8), ("point_step", C.c_uint32),
-                ("row_step", C.c_uint32), ("data_offset", C.c_size_t), ("data_bytes", C.c_size_t)]
+                ("row_step", C.c_uint32), ("data", C.c_void_p), ("data_bytes", C.c_size_t)]
 
 
 _bound = False
@@ -46,8 +46,8 @@ def _L():
         L.cldn_b200_ros_to_encoding_info.argtypes = [C.POINTER(_CRosMsg), C.POINTER(_CInfo)]
         L.cldn_b200_ros_apply_resolution_profile.argtypes = [C.POINTER(_CField), C.POINTER(C.c_uint32), C.POINTER(C.c_char_p),
                                                              C.POINTER(C.c_float), sz, C.POINTER(C.c_float)]
-        L.cldn_b200_ros_compress_msg.argtypes = [vp, vp, C.POINTER(_CRosMsg), vp, sz, vp, sz, C.POINTER(sz)]
-        L.cldn_b200_ros_decompress_msg.argtypes = [vp, vp, C.POINTER(_CRosMsg), vp, sz, C.POINTER(sz)]
+        L.cldn_b200_ros_compress_msg.argtypes = [vp, C.POINTER(_CRosMsg), vp, sz, C.POINTER(sz)]
+        L.cldn_b200_ros_decompress_msg.argtypes = [vp, C.POINTER(_CRosMsg), vp, sz, C.POINTER(sz)]
         L.cldn_b200_encoder_info.argtypes = [vp, C.POINTER(_CInfo)]
         _bound = True
     return L
@@ -55,9 +55,10 @@ def _L():
 
 @dataclass
 class RosPointCloud2:
-    """cloudini_ros::RosPointCloud2 (ros_msg_utils.hpp:32-148). ``data`` is a view of the point payload (or of the
-    compressed blob for a CompressedPointCloud2); ``msg`` keeps the serialised message it was parsed from."""
+    """cloudini_ros::RosPointCloud2 (ros_msg_utils.hpp:32-148). ``data`` is the point payload (or the compressed blob of
+    a CompressedPointCloud2) as a uint8 array; after parsing it is a view into ``msg``."""
     msg: bytes = b""
+    cdr_header: bytes = bytes([0, 1, 0, 0])
     stamp_sec: int = 0
     stamp_nsec: int = 0
     frame_id: str = ""
@@ -69,13 +70,18 @@ class RosPointCloud2:
     is_bigendian: bool = False
     is_dense: bool = True
     data: np.ndarray = field(default_factory=lambda: np.zeros(0, dtype=np.uint8))
-    _c: Optional[_CRosMsg] = None
+    data_offset: int = 0  # where `data` started inside `msg` when it was parsed
 
-    def _sync_c(self) -> _CRosMsg:
-        """The C view with this object's (possibly edited) width / height / fields / point_step."""
+    def _c_view(self):
+        """(C struct, keepalive objects) describing this object for the header writer."""
         c = _CRosMsg()
-        C.memmove(C.byref(c), C.byref(self._c), C.sizeof(_CRosMsg))
-        c.height, c.width, c.point_step, c.is_dense = self.height, self.width, self.point_step, 1 if self.is_dense else 0
+        c.cdr_header[:] = list(self.cdr_header)
+        c.stamp_sec, c.stamp_nsec = self.stamp_sec, self.stamp_nsec
+        frame = self.frame_id.encode()
+        fbuf = C.create_string_buffer(frame, len(frame) + 1)
+        c.frame_id, c.frame_id_len = C.cast(fbuf, C.c_void_p).value, len(frame)
+        c.height, c.width, c.point_step, c.row_step = self.height, self.width, self.point_step, self.row_step
+        c.is_bigendian, c.is_dense = (1 if self.is_bigendian else 0), (1 if self.is_dense else 0)
         if len(self.fields) > CLDN_MAX_FIELDS:
             raise RuntimeError("too many fields")
         c.n_fields = len(self.fields)
@@ -84,7 +90,9 @@ class RosPointCloud2:
             c.fields[i].offset, c.fields[i].type = f.offset, int(f.type)
             c.fields[i].has_resolution = 0 if f.resolution is None else 1
             c.fields[i].resolution = 0.0 if f.resolution is None else float(f.resolution)
-        return c
+        data = np.ascontiguousarray(self.data, dtype=np.uint8)
+        c.data, c.data_bytes = (data.ctypes.data if data.size else None), data.size
+        return c, (fbuf, data)
 
 
 def getDeserializedPointCloudMessage(dds_msg) -> RosPointCloud2:  # ros_msg_utils.cpp:54-95
@@ -92,11 +100,14 @@ def getDeserializedPointCloudMessage(dds_msg) -> RosPointCloud2:  # ros_msg_util
     c = _CRosMsg()
     buf = np.frombuffer(raw, dtype=np.uint8)
     _check(_L().cldn_b200_ros_parse(buf.ctypes.data if len(raw) else None, len(raw), C.byref(c)))
-    pc = RosPointCloud2(msg=raw, stamp_sec=c.stamp_sec, stamp_nsec=c.stamp_nsec,
-                        frame_id=raw[c.frame_id_offset:c.frame_id_offset + c.frame_id_len].decode("utf-8", "replace"),
+    base = buf.ctypes.data
+    f0 = (c.frame_id or base) - base
+    d0 = (c.data or base) - base
+    pc = RosPointCloud2(msg=raw, cdr_header=bytes(c.cdr_header), stamp_sec=c.stamp_sec, stamp_nsec=c.stamp_nsec,
+                        frame_id=raw[f0:f0 + c.frame_id_len].decode("utf-8", "replace"),
                         height=c.height, width=c.width, point_step=c.point_step, row_step=c.row_step,
                         is_bigendian=bool(c.is_bigendian), is_dense=bool(c.is_dense),
-                        data=buf[c.data_offset:c.data_offset + c.data_bytes], _c=c)
+                        data=buf[d0:d0 + c.data_bytes], data_offset=d0)
     for i in range(c.n_fields):
         f = c.fields[i]
         pc.fields.append(PointField(f.name.decode(), f.offset, FieldType(f.type) if f.type <= 10 else FieldType.UNKNOWN, None))
@@ -122,7 +133,7 @@ def applyResolutionProfile(profile: Dict[str, float], fields: List[PointField], 
 
 def toEncodingInfo(pc: RosPointCloud2) -> EncodingInfo:  # ros_msg_utils.cpp:122-131
     c = _CInfo()
-    m = pc._sync_c()
+    m, _keep = pc._c_view()
     _check(_L().cldn_b200_ros_to_encoding_info(C.byref(m), C.byref(c)))
     return _from_c(c)
 
@@ -130,30 +141,24 @@ def toEncodingInfo(pc: RosPointCloud2) -> EncodingInfo:  # ros_msg_utils.cpp:122
 def convertPointCloud2ToCompressedCloud(pc: RosPointCloud2, encoding_info: EncodingInfo, device: int = -1) -> bytes:
     """ros_msg_utils.cpp:167-213. Returns the serialised CompressedPointCloud2 message."""
     enc = PointcloudEncoder(encoding_info, device=device)  # a fresh encoder per message, like the reference (:198)
-    m = pc._sync_c()
-    msg = np.frombuffer(pc.msg, dtype=np.uint8)
-    data = np.ascontiguousarray(pc.data, dtype=np.uint8)
+    m, _keep = pc._c_view()
     need = C.c_size_t(0)
-    _check(_L().cldn_b200_ros_compress_msg(enc._h, msg.ctypes.data, C.byref(m), data.ctypes.data if data.size else None, data.size,
-                                           None, 0, C.byref(need)))
+    _check(_L().cldn_b200_ros_compress_msg(enc._h, C.byref(m), None, 0, C.byref(need)))
     out = np.zeros(need.value, dtype=np.uint8)
     w = C.c_size_t(0)
-    # point_data is always passed (it may be the preprocessed cloud); an empty cloud passes NULL + the message's own (empty) data
-    ptr = data.ctypes.data if data.size else (msg.ctypes.data + m.data_offset)
-    _check(_L().cldn_b200_ros_compress_msg(enc._h, msg.ctypes.data, C.byref(m), ptr, data.size, out.ctypes.data, out.size, C.byref(w)))
+    _check(_L().cldn_b200_ros_compress_msg(enc._h, C.byref(m), out.ctypes.data, out.size, C.byref(w)))
     return bytes(out[:w.value])
 
 
 def convertCompressedCloudToPointCloud2(pc: RosPointCloud2, device: int = -1) -> bytes:
     """ros_msg_utils.cpp:134-165. Returns the serialised PointCloud2 message."""
     dec = PointcloudDecoder(device=device)
-    m = pc._sync_c()
-    msg = np.frombuffer(pc.msg, dtype=np.uint8)
+    m, _keep = pc._c_view()
     need = C.c_size_t(0)
-    _check(_L().cldn_b200_ros_decompress_msg(dec._h, msg.ctypes.data, C.byref(m), None, 0, C.byref(need)))
+    _check(_L().cldn_b200_ros_decompress_msg(dec._h, C.byref(m), None, 0, C.byref(need)))
     out = np.zeros(need.value, dtype=np.uint8)
     w = C.c_size_t(0)
-    _check(_L().cldn_b200_ros_decompress_msg(dec._h, msg.ctypes.data, C.byref(m), out.ctypes.data, out.size, C.byref(w)))
+    _check(_L().cldn_b200_ros_decompress_msg(dec._h, C.byref(m), out.ctypes.data, out.size, C.byref(w)))
     return bytes(out[:w.value])
 
 

@@ -39,19 +39,20 @@ int cldn_b200_viz_lossy_preprocess(cldn_preproc_t* pp, cldn_info_t* info, const 
 
 /* ---- N2: DDS envelope ------------------------------------------------------------------------------------------- */
 /* Parsed view of a CDR-serialised sensor_msgs/msg/PointCloud2 or point_cloud_interfaces/msg/CompressedPointCloud2
- * (cloudini_ros::RosPointCloud2, ros_msg_utils.hpp:32-148). Offsets point into the caller's message buffer. */
+ * (cloudini_ros::RosPointCloud2, ros_msg_utils.hpp:32-148). `frame_id` and `data` are views (into the message that was
+ * parsed, or into whatever buffers the caller sets them to before re-serialising). */
 typedef struct cldn_ros_msg_t {
   uint8_t cdr_header[4];     /* nanocdr::CdrHeader as found on the wire: {0, encapsulation, 0, 0} */
   int32_t stamp_sec;
   uint32_t stamp_nsec;
-  size_t frame_id_offset;    /* first character of header.frame_id inside the message */
+  const char* frame_id;      /* header.frame_id, NOT NUL-terminated */
   uint32_t frame_id_len;     /* without the trailing NUL */
   uint32_t height, width;
   uint32_t n_fields;
   cldn_field_t fields[CLDN_MAX_FIELDS]; /* has_resolution = 0 after parsing (the message carries none) */
   uint8_t is_bigendian, is_dense;
   uint32_t point_step, row_step;
-  size_t data_offset;        /* PointCloud2::data / CompressedPointCloud2::compressed_data */
+  const uint8_t* data;       /* PointCloud2::data / CompressedPointCloud2::compressed_data */
   size_t data_bytes;
 } cldn_ros_msg_t;
 
@@ -72,17 +73,16 @@ int cldn_b200_ros_apply_resolution_profile(cldn_field_t* fields, uint32_t* n_fie
 /* convertPointCloud2ToCompressedCloud (ros_msg_utils.cpp:167-213): PointCloud2 message -> CompressedPointCloud2
  * message (same CDR header, width/height/fields/point_step, compressed_data = Cloudini blob with header, is_dense,
  * format "cloudini"). The point payload is encoded on the GPU through `enc` (created from `encoding_info`; its
- * compression_opt may be LZ4/ZSTD: host-pointer API). `point_data` overrides the payload (e.g. the output of
- * cldn_b200_viz_lossy_preprocess, with msg->width already updated); NULL = the message's own data.
+ * compression_opt may be LZ4/ZSTD: host-pointer API). The payload is msg->data / msg->data_bytes — after
+ * cldn_b200_viz_lossy_preprocess point them (and msg->width / height) at the preprocessed cloud, like pc_info.data.
  * Query the worst-case size with out == NULL (*written receives it). */
-int cldn_b200_ros_compress_msg(cldn_encoder_t* enc, const void* dds_msg, const cldn_ros_msg_t* msg,
-                               const void* point_data, size_t point_bytes, void* out, size_t out_capacity,
+int cldn_b200_ros_compress_msg(cldn_encoder_t* enc, const cldn_ros_msg_t* msg, void* out, size_t out_capacity,
                                size_t* written);
 
 /* convertCompressedCloudToPointCloud2 (ros_msg_utils.cpp:134-165): CompressedPointCloud2 message -> PointCloud2 message,
  * the blob decoded on the GPU through `dec` straight into the output message. out == NULL queries the exact size. */
-int cldn_b200_ros_decompress_msg(cldn_decoder_t* dec, const void* dds_msg, const cldn_ros_msg_t* msg, void* out,
-                                 size_t out_capacity, size_t* written);
+int cldn_b200_ros_decompress_msg(cldn_decoder_t* dec, const cldn_ros_msg_t* msg, void* out, size_t out_capacity,
+                                 size_t* written);
 
 #ifdef __cplusplus
 }

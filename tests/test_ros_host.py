@@ -21,7 +21,7 @@ def _describe(pc: ros.RosPointCloud2) -> str:  # the same text oracle/ref_wrappe
     for f in pc.fields:
         t += f"field {f.name} {f.offset} {int(f.type)}\n"
     t += f"point_step {pc.point_step} row_step {pc.row_step}\n"
-    t += f"data {pc._c.data_offset} {pc._c.data_bytes}\nis_dense {1 if pc.is_dense else 0}\n"
+    t += f"data {pc.data_offset} {pc.data.size}\nis_dense {1 if pc.is_dense else 0}\n"
     return t
 
 
