@@ -30,10 +30,13 @@ def build_port(force: bool = False) -> str:
 
 def build_ref(force: bool = False):
     """Builds the reference-backed oracle when /root/reference is present (never on the GPU box)."""
-    if os.path.exists(REF_LIB) and not force:
+    have_tree = os.path.isdir(os.path.join(REFERENCE_TREE, "cloudini_lib", "src"))
+    wrapper = os.path.join(HERE, "ref_wrapper.cpp")
+    stale = os.path.exists(REF_LIB) and have_tree and os.path.getmtime(REF_LIB) < os.path.getmtime(wrapper)
+    if os.path.exists(REF_LIB) and not force and not stale:
         return REF_LIB
-    if not os.path.isdir(os.path.join(REFERENCE_TREE, "cloudini_lib", "src")):
-        return None
+    if not have_tree:
+        return REF_LIB if os.path.exists(REF_LIB) else None
     subprocess.check_call([os.path.join(HERE, "build_ref.sh")], stdout=subprocess.DEVNULL)
     return REF_LIB
 
@@ -205,10 +208,26 @@ class PortOracle:
         L.orc_time_encode.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int, C.POINTER(C.c_longlong)]
         L.orc_time_decode.restype = C.c_double
         L.orc_time_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int]
+        L.orc_viz_preprocess.restype = C.c_longlong
+        L.orc_viz_preprocess.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
         self.L = L
 
     def _err(self):
         return self.L.orc_last_error().decode("utf-8", "replace")
+
+    def viz_preprocess(self, info, cloud):
+        """applyVizLossyPreprocessing restated (ros_msg_utils.cpp:249-341). Returns (EncodingInfo after, surviving bytes)."""
+        a = _u8(cloud)
+        c = cb._to_c(info)
+        out = np.zeros(max(a.size, 1), dtype=np.uint8)
+        n = self.L.orc_viz_preprocess(C.byref(c), a.ctypes.data, a.size, out.ctypes.data, out.size)
+        if n == -1:  # the reference's no-op conditions
+            return info, a
+        if n < 0:
+            raise RuntimeError("orc_viz_preprocess failed")
+        after = cb._from_c(c)
+        after.version = info.version
+        return after, out[:n * info.point_step]
 
     def header(self, info) -> bytes:
         c = cb._to_c(info)

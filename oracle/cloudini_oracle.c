@@ -908,3 +908,74 @@ double orc_time_decode(const cldn_info_t* in, const uint8_t* payload, size_t byt
   clock_gettime(CLOCK_MONOTONIC, &t1);
   return rc ? -1.0 : (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
 }
+
+/* ---- applyVizLossyPreprocessing (src/ros_msg_utils.cpp:249-341), restated --------------------------
+ * Sequential: for every point in order, drop it when x, y or z is not finite (:311-313); quantise with
+ * lround(v * (1/res)) truncated to int32 (:314-317), pack 21 bits per axis with a 2^20 bias (packVoxelKey21, :42-49), and
+ * keep the point only if the key was not seen before (:318-320). The reference uses ankerl::unordered_dense::set; any
+ * exact set gives the same survivors, so a plain open-addressing table is used here.
+ * Returns the number of survivors (their bytes are written to `out`), or -1 when the call is one of the reference's
+ * no-ops (no geometry triple, bad resolution, empty cloud: :250-278) — then nothing is written and `info` is untouched.
+ * On success info->width / height and the FLOAT64 resolutions are updated like pc_info (:327-340). */
+static uint64_t orc_voxel_key(int32_t qx, int32_t qy, int32_t qz) {
+  const uint64_t mask = (1ull << 21) - 1ull;
+  const int64_t bias = 1ll << 20;
+  const uint64_t ux = (uint64_t)((int64_t)qx + bias) & mask;
+  const uint64_t uy = (uint64_t)((int64_t)qy + bias) & mask;
+  const uint64_t uz = (uint64_t)((int64_t)qz + bias) & mask;
+  return ux | (uy << 21) | (uz << 42);
+}
+long long orc_viz_preprocess(cldn_info_t* info, const uint8_t* cloud, size_t cloud_bytes, uint8_t* out, size_t out_capacity) {
+  if (info->n_fields < 3 || info->point_step == 0) return -1;
+  const cldn_field_t* f0 = &info->fields[0];
+  const cldn_field_t* f1 = &info->fields[1];
+  const cldn_field_t* f2 = &info->fields[2];
+  if (!(f0->type == CLDN_FLOAT32 && f1->type == CLDN_FLOAT32 && f2->type == CLDN_FLOAT32 && f0->has_resolution &&
+        f1->has_resolution && f2->has_resolution && f0->resolution == f1->resolution && f0->resolution == f2->resolution &&
+        f1->offset == f0->offset + 4u && f2->offset == f0->offset + 8u)) {
+    return -1;
+  }
+  const float res = f0->resolution;
+  if (!(res > 0.0f) || !isfinite(res)) return -1;
+  const float inv_res = 1.0f / res;
+  const size_t step = info->point_step, n_in = cloud_bytes / step;
+  if (n_in == 0) return -1;
+  size_t cap = 16;
+  while (cap < 2 * n_in) cap <<= 1;
+  uint64_t* table = (uint64_t*)malloc(cap * sizeof(uint64_t));
+  if (!table) return -2;
+  memset(table, 0xFF, cap * sizeof(uint64_t)); /* keys use 63 bits: all-ones is free */
+  size_t kept = 0;
+  for (size_t i = 0; i < n_in; ++i) {
+    const uint8_t* p = cloud + i * step;
+    float v[3];
+    memcpy(&v[0], p + f0->offset, 4);
+    memcpy(&v[1], p + f1->offset, 4);
+    memcpy(&v[2], p + f2->offset, 4);
+    if (!isfinite(v[0]) || !isfinite(v[1]) || !isfinite(v[2])) continue;
+    const uint64_t key = orc_voxel_key((int32_t)lroundf(v[0] * inv_res), (int32_t)lroundf(v[1] * inv_res), (int32_t)lroundf(v[2] * inv_res));
+    uint64_t h = key * 0x9E3779B97F4A7C15ull;
+    h ^= h >> 29;
+    size_t s = (size_t)h & (cap - 1);
+    int seen = 0;
+    while (table[s] != ~0ull) {
+      if (table[s] == key) { seen = 1; break; }
+      s = (s + 1) & (cap - 1);
+    }
+    if (seen) continue;
+    table[s] = key;
+    if ((kept + 1) * step > out_capacity) { free(table); return -2; }
+    memcpy(out + kept * step, p, step);
+    ++kept;
+  }
+  free(table);
+  info->width = (uint32_t)kept;
+  info->height = 1;
+  for (uint32_t i = 0; i < info->n_fields; ++i) {
+    if (info->fields[i].type == CLDN_FLOAT64 && !info->fields[i].has_resolution) {
+      info->fields[i].has_resolution = 1;
+      info->fields[i].resolution = 1e-6f;
+    }
+  }
+  return (long long)kept;
+}

@@ -62,10 +62,23 @@ def golden_ros(lib_built):
     """DDS messages + what the reference's converter made of them (tests/golden/make_golden_ros.py)."""
     z = np.load(os.path.join(ROOT, "tests", "golden", "golden_ros_v1.npz"))
     out = {}
-    for n in sorted({k.split("__")[0] for k in z.files}):
+    for n in sorted({k.split("__")[0] for k in z.files if not k.startswith("VIZ_")}):
         text = bytes(z[n + "__profile"]).decode()
         profile = {kv.split("=")[0]: float(kv.split("=")[1]) for kv in text.split(";") if kv}
         out[n] = {"msg": bytes(z[n + "__msg"]), "profile": profile, "default_resolution": float(z[n + "__opts"][0]),
                   "viz": bool(z[n + "__opts"][1]), "describe": bytes(z[n + "__describe"]).decode(),
                   "compressed": bytes(z[n + "__compressed"]), "restored": bytes(z[n + "__restored"])}
+    return out
+
+
+@pytest.fixture(scope="session")
+def golden_viz(lib_built):
+    """Raw clouds + what the reference's applyVizLossyPreprocessing made of them (tests/golden/make_golden_ros.py)."""
+    import cloudini_b200 as cb
+    z = np.load(os.path.join(ROOT, "tests", "golden", "golden_ros_v1.npz"))
+    out = {}
+    for n in sorted({k.split("__")[0] for k in z.files if k.startswith("VIZ_")}):
+        info = cb.EncodingInfoFromYAML(bytes(z[n + "__yaml"]).decode())
+        after = cb.EncodingInfoFromYAML(bytes(z[n + "__yaml_after"]).decode())
+        out[n[4:]] = (info, z[n + "__input"], after, z[n + "__output"])
     return out

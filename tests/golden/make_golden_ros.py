@@ -53,6 +53,16 @@ def main():
         arrays[name + "__compressed"] = np.frombuffer(comp, dtype=np.uint8)
         arrays[name + "__restored"] = np.frombuffer(ref.ros_decompress(comp, len(msg) + 4096), dtype=np.uint8)
         print(f"{name}: msg {len(msg)} B -> compressed {len(comp)} B")
+    # N3 alone: raw clouds through applyVizLossyPreprocessing (input, EncodingInfo as YAML, survivors, info afterwards)
+    import cloudini_b200 as cb
+    for name, (info, cloud) in {"viz_xyzi_8k": synth.cloud_viz(8000, seed=31), "viz_step32_3k": synth.cloud_viz(3000, seed=32, step=32),
+                                "viz_xyz_500": synth.cloud_viz(500, seed=33, step=12)}.items():
+        after, kept = ref.viz_preprocess(info, cloud)
+        arrays["VIZ_" + name + "__input"] = cloud
+        arrays["VIZ_" + name + "__yaml"] = np.frombuffer(cb.EncodingInfoToYAML(info).encode(), dtype=np.uint8)
+        arrays["VIZ_" + name + "__yaml_after"] = np.frombuffer(cb.EncodingInfoToYAML(after).encode(), dtype=np.uint8)
+        arrays["VIZ_" + name + "__output"] = kept
+        print(f"{name}: {info.width} -> {after.width} points")
     path = os.path.join(ROOT, "tests", "golden", "golden_ros_v1.npz")
     np.savez_compressed(path, **arrays)
     print("wrote", path, os.path.getsize(path), "bytes")

@@ -25,11 +25,11 @@ def _same_info(a, b):
 
 # ---- N3: applyVizLossyPreprocessing ------------------------------------------------------------------------------------
 @pytest.mark.parametrize("n,step", [(1, 16), (2, 16), (255, 16), (256, 12), (2049, 16), (40_000, 16), (100_003, 32), (30_000, 22), (5_000, 280)])
-def test_viz_preprocess_matches_reference(ref, n, step):
+def test_viz_preprocess_matches_reference(oracle, n, step):
     info, cloud = synth.cloud_viz(n, seed=n, step=step)
     pp = ros.VizPreprocessor()
     got_info, got, applied = pp.run(info, cloud)
-    want_info, want = ref.viz_preprocess(info, cloud)
+    want_info, want = oracle.viz_preprocess(info, cloud)
     assert applied and got.size == want.size and np.array_equal(got, want)
     assert _same_info(got_info, want_info)
     if n >= 2049:
@@ -37,10 +37,17 @@ def test_viz_preprocess_matches_reference(ref, n, step):
     # the handle is reusable (epoch-tagged status words, re-cleared table): same answer again, then a different cloud
     assert np.array_equal(pp.run(info, cloud)[1], want)
     info2, cloud2 = synth.cloud_viz(max(1, n // 3), seed=n + 1, step=step)
-    assert np.array_equal(pp.run(info2, cloud2)[1], ref.viz_preprocess(info2, cloud2)[1])
+    assert np.array_equal(pp.run(info2, cloud2)[1], oracle.viz_preprocess(info2, cloud2)[1])
 
 
-def test_viz_preprocess_edge_cases(ref):
+def test_viz_preprocess_golden(golden_viz):
+    pp = ros.VizPreprocessor()
+    for name, (info, cloud, after, kept) in golden_viz.items():
+        got_info, got, applied = pp.run(info, cloud)
+        assert applied and np.array_equal(got, kept) and _same_info(got_info, after), name
+
+
+def test_viz_preprocess_edge_cases(oracle):
     pp = ros.VizPreprocessor()
     # all points in one voxel / all NaN / huge coordinates (21-bit truncation of the key, lround overflow) / res 0.5 ties
     info, cloud = synth.cloud_viz(5000, seed=3)
@@ -63,7 +70,7 @@ def test_viz_preprocess_edge_cases(ref):
             for k in range(3):
                 inf.fields[k].resolution = 0.5
         got_info, got, applied = pp.run(inf, g.reshape(-1).view(np.uint8))
-        want_info, want = ref.viz_preprocess(inf, g.reshape(-1).view(np.uint8))
+        want_info, want = oracle.viz_preprocess(inf, g.reshape(-1).view(np.uint8))
         assert applied and np.array_equal(got, want), case
         assert _same_info(got_info, want_info), case
     # FLOAT64 fields without a resolution get 1e-6; with one they keep it
@@ -74,12 +81,12 @@ def test_viz_preprocess_edge_cases(ref):
     inf.fields = [cb.PointField("a", 0, FT.FLOAT32, 0.01), cb.PointField("b", 4, FT.FLOAT32, 0.01), cb.PointField("c", 8, FT.FLOAT32, 0.01),
                   cb.PointField("t", 16, FT.FLOAT64, None), cb.PointField("u", 24, FT.FLOAT64, 0.5)]
     got_info, got, applied = pp.run(inf, raw)
-    want_info, want = ref.viz_preprocess(inf, raw)
+    want_info, want = oracle.viz_preprocess(inf, raw)
     assert applied and np.array_equal(got, want) and _same_info(got_info, want_info)
     assert got_info.fields[3].resolution == pytest.approx(1e-6) and got_info.fields[4].resolution == 0.5
 
 
-def test_viz_preprocess_no_op_conditions(ref):
+def test_viz_preprocess_no_op_conditions(oracle):
     pp = ros.VizPreprocessor()
     info, cloud = synth.cloud_viz(1000, seed=1)
     variants = []
@@ -94,26 +101,26 @@ def test_viz_preprocess_no_op_conditions(ref):
     for v in variants:
         got_info, got, applied = pp.run(v, cloud)
         assert not applied and got_info is v and np.array_equal(got, cloud)
-        want_info, want = ref.viz_preprocess(v, cloud)
+        want_info, want = oracle.viz_preprocess(v, cloud)
         assert np.array_equal(want, cloud)
     assert pp.run(info, np.zeros(0, dtype=np.uint8))[2] is False                                        # empty cloud
 
 
-def test_viz_preprocess_device_pointers(ref):
+def test_viz_preprocess_device_pointers(oracle):
     from test_gpu_parity import _Dev
     info, cloud = synth.cloud_viz(70_000, seed=11)
     d_in, d_out = _Dev(src=cloud), _Dev(size=cloud.size)
     new_info, kept, applied = ros.VizPreprocessor().run_device(info, d_in.ptr, cloud.size, d_out.ptr, cloud.size)
-    want_info, want = ref.viz_preprocess(info, cloud)
+    want_info, want = oracle.viz_preprocess(info, cloud)
     assert applied and kept == want_info.width and np.array_equal(d_out.numpy()[:kept * 16], want)
 
 
-def test_viz_then_encode_matches_reference_pipeline(ref):
+def test_viz_then_encode_matches_reference_pipeline(oracle):
     # preprocessing feeds the encoder: the blob equals the reference's encode of the reference's preprocessed cloud
     info, cloud = synth.cloud_viz(60_000, seed=21)
     new_info, kept, _ = ros.VizPreprocessor().run(info, cloud)
-    want_info, want = ref.viz_preprocess(info, cloud)
-    assert cb.PointcloudEncoder(new_info).encode(kept) == ref.encode(want_info, want)
+    want_info, want = oracle.viz_preprocess(info, cloud)
+    assert cb.PointcloudEncoder(new_info).encode(kept) == oracle.encode(want_info, want)
 
 
 # ---- N2: DDS envelope ----------------------------------------------------------------------------------------------------

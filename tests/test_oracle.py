@@ -217,3 +217,31 @@ def test_port_decoder_hardening(port):
     first = int.from_bytes(blob[hdr:hdr + 4], "little")
     with pytest.raises(RuntimeError):
         port.decode_payload(info, blob[hdr:hdr + 4 + first], out)  # only one of two chunks
+
+
+# ---- the restated applyVizLossyPreprocessing ----------------------------------------------------------
+def _info_key(i):
+    return (i.width, i.height, i.point_step, [(f.name, f.offset, int(f.type), None if f.resolution is None else np.float32(f.resolution)) for f in i.fields])
+
+
+def test_port_viz_preprocess_matches_golden(port, golden_viz):
+    for name, (info, cloud, after, kept) in golden_viz.items():
+        got_info, got = port.viz_preprocess(info, cloud)
+        assert np.array_equal(got, kept), name
+        assert _info_key(got_info) == _info_key(after), name
+
+
+@pytest.mark.parametrize("n,step", [(1, 16), (257, 12), (20_000, 16), (7_777, 32), (3_000, 22)])
+def test_port_viz_preprocess_matches_reference(port, ref, n, step):
+    info, cloud = synth.cloud_viz(n, seed=100 + n, step=step)
+    f = cloud.reshape(n, step)[:, :12].copy().view(np.float32)
+    if n > 1000:  # 21-bit key truncation, lround overflow, signed zero
+        f[5] = (1048.576, -1048.577, 2097.152)
+        f[6] = (3.0e9, -3.0e9, 1.0e30)
+        f[7] = (-0.0, 0.0004, -0.0004)
+        f[8] = (0.0, 0.0, 0.0)
+        cloud = cloud.copy()
+        cloud.reshape(n, step)[:, :12] = f.view(np.uint8)
+    got_info, got = port.viz_preprocess(info, cloud)
+    want_info, want = ref.viz_preprocess(info, cloud)
+    assert np.array_equal(got, want) and _info_key(got_info) == _info_key(want_info)
