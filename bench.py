@@ -36,6 +36,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary measurements (tools_extras_bench.py, child process)")
     ap.add_argument("--e2e-frames", type=int, default=8, help="frames per end-to-end step (pinned host buffers)")
     return ap.parse_args()
 
@@ -167,6 +168,19 @@ def cpu_reference_numbers(oracle, info, cloud, blob, seconds, threads):
     pts = reps * threads * POINTS
     return {"enc_mpts": pts / te / 1e6, "dec_mpts": pts / td / 1e6, "rt_mpts": pts / (te + td) / 1e6,
             "sample": f"{reps} x {threads} encode+decode passes of one 1M-point XYZI cloud ({(te + td):.1f} s)", "seconds": te + td}
+
+
+def run_extras(timeout_s=240):
+    """Secondary measurements (N3 kernels, C3 / V5 sections, DDS converter step) in a CHILD process: whatever happens
+    there — exception, CUDA error, crash, timeout — ends up as a string in `extras`, never in the headline numbers."""
+    try:
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tools_extras_bench.py")], capture_output=True, text=True, timeout=timeout_s)
+        lines = [ln for ln in r.stdout.strip().splitlines() if ln.startswith("{")]
+        if r.returncode != 0 or not lines:
+            return {"error": f"exit {r.returncode}: {(r.stderr or r.stdout)[-300:]}"}
+        return json.loads(lines[-1])
+    except Exception as e:  # noqa: BLE001
+        return {"error": f"{type(e).__name__}: {e}"[:300]}
 
 
 def run_reference(args, rank, world):
@@ -429,6 +443,8 @@ def main():
                                         "encode_mpts": r["enc_mpts"], "decode_mpts": r["dec_mpts"], "host_cores_available": os.cpu_count()}
             except Exception as e:
                 line["cpu_baseline"] = {"value": None, "unit": "Mpoints/s", "cores": 0, "kind": "unavailable", "sample": str(e)}
+        if world == 1 and not args.no_extras:
+            line["extras"] = run_extras()
         print(json.dumps(line), flush=True)
     if distributed:
         dist.destroy_process_group()
