@@ -153,7 +153,8 @@ struct Buf {
     const size_t want = std::max<size_t>(n + n / 4, 64);
     if (cudaMalloc(reinterpret_cast<void**>(&p), want * sizeof(T)) != cudaSuccess) return false;
     cap = want;
-    if (zero && cudaMemset(p, 0, want * sizeof(T)) != cudaSuccess) return false;
+    // the handle's stream is non-blocking (it does not order itself after the legacy stream the memset runs on)
+    if (zero && (cudaMemset(p, 0, want * sizeof(T)) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess)) return false;
     return true;
   }
   void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
