@@ -28,7 +28,12 @@ int main(int argc, char** argv) {
     auto pc_info = cloudini_ros::getDeserializedPointCloudMessage(raw_dds_msg);
     cloudini_ros::applyResolutionProfile(cloudini_ros::ResolutionProfile{}, pc_info.fields, static_cast<float>(std::atof(argv[4])));
     if (std::atoi(argv[5])) cloudini_ros::applyVizLossyPreprocessing(pc_info);
-    auto copy = pc_info;  // the copy must re-bind its data view to its own owned_data (ros_msg_utils.hpp:155-159)
+    auto copy = pc_info;  // the copy must re-bind its data view to its own owned_data (ros_msg_utils.hpp:155-159,
+                          // cloudini_lib/test/test_ros_msg.cpp:146-156 RosPointCloud2CopyRebindsOwnedDataView)
+    if (!pc_info.owned_data.empty() && (copy.data.data() != copy.owned_data.data() || copy.data.size() != copy.owned_data.size())) {
+      std::puts("ros_shim_convert: copy did not re-bind its data view");
+      return 3;
+    }
     auto encoding_info = cloudini_ros::toEncodingInfo(copy);
     encoding_info.compression_opt = Cloudini::CompressionOption::NONE;
     encoding_info.use_threads = false;

@@ -188,3 +188,30 @@ def test_golden_messages(golden_ros):
         assert got == g["compressed"], name
         back = ros.convertCompressedCloudToPointCloud2(ros.getDeserializedPointCloudMessage(g["compressed"]))
         assert back == g["restored"], name
+
+
+def test_dds_roundtrip_like_the_reference_test(golden_ros):
+    # cloudini_lib/test/test_ros_msg.cpp:91-144 (DDS_Roundtrip) on the committed excerpt of samples/dds_message.bin:
+    # parsed infos, then encode / decode with xyz + intensity at 1 mm: floats within the resolution, ring and the
+    # (unaligned, offset 18) FLOAT64 timestamp exactly (Gorilla), default ZSTD stage 2
+    if "dds_sample_4000" not in golden_ros:
+        pytest.skip("golden excerpt of the reference's sample message not present")
+    pc = ros.getDeserializedPointCloudMessage(golden_ros["dds_sample_4000"]["msg"])
+    info = ros.toEncodingInfo(pc)
+    assert [(f.name, f.offset, f.type) for f in info.fields] == [("x", 0, FT.FLOAT32), ("y", 4, FT.FLOAT32), ("z", 8, FT.FLOAT32),
+                                                                ("intensity", 12, FT.FLOAT32), ("ring", 16, FT.UINT16), ("timestamp", 18, FT.FLOAT64)]
+    assert (info.width, info.height, info.point_step) == (4000, 1, 26)
+    assert info.encoding_opt == cb.EncodingOptions.LOSSY and info.compression_opt == cb.CompressionOption.ZSTD and info.version == 5
+    for k in range(4):
+        info.fields[k].resolution = 0.001
+    original = np.array(pc.data)
+    blob = cb.PointcloudEncoder(info).encode(original)
+    dinfo, hdr = cb.DecodeHeader(blob)
+    assert [(f.name, f.offset, f.type) for f in dinfo.fields] == [(f.name, f.offset, f.type) for f in info.fields]
+    decoded = np.zeros(original.size, dtype=np.uint8)
+    cb.PointcloudDecoder().decode(dinfo, blob[hdr:], decoded)
+    a, b = original.reshape(4000, 26), decoded.reshape(4000, 26)
+    fa, fb = a[:, :16].copy().view(np.float32), b[:, :16].copy().view(np.float32)
+    ok = np.isfinite(fa)
+    assert np.all(np.abs(fa[ok] - fb[ok]) <= 0.001) and np.array_equal(np.isnan(fa), np.isnan(fb))
+    assert np.array_equal(a[:, 16:18], b[:, 16:18]) and np.array_equal(a[:, 18:26], b[:, 18:26])
