@@ -149,8 +149,11 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, opt="-O1"):
-    if not force and not needs_build():
+def build(force=False, opt="-O1", asan=False):
+    """asan=True builds libcloudini_b200_cusim_asan.so (AddressSanitizer: out-of-bounds accesses of the kernels on
+    "device" = heap memory are reported). Load it with LD_PRELOAD=$(gcc -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0."""
+    lib = LIB.replace(".so", "_asan.so") if asan else LIB
+    if not force and not asan and not needs_build():
         return LIB
     os.makedirs(GEN, exist_ok=True)
     for f in os.listdir(CSRC):
@@ -159,10 +162,12 @@ def build(force=False, opt="-O1"):
         with open(os.path.join(GEN, f), "w") as fh:
             fh.write(transform(text, f))
     flags = ["-std=c++17", opt, "-g", "-fPIC", "-ffp-contract=off", "-fno-strict-aliasing", "-pthread", "-I", HERE, "-w"]
+    if asan:
+        flags += ["-fsanitize=address", "-fno-omit-frame-pointer"]
     procs = []
     for src in SOURCES + ["cusim.cpp"]:
         path = os.path.join(HERE, src) if src == "cusim.cpp" else os.path.join(GEN, src)
-        obj = os.path.join(OUT_DIR, os.path.splitext(src)[0] + ".o")
+        obj = os.path.join(OUT_DIR, os.path.splitext(src)[0] + ("_asan.o" if asan else ".o"))
         cmd = ["g++", *flags, "-x", "c++", "-c", path, "-o", obj]
         procs.append((src, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     objs = []
@@ -172,9 +177,9 @@ def build(force=False, opt="-O1"):
             sys.stderr.write(out[-6000:])
             raise RuntimeError(f"cusim: g++ failed on {src}")
         objs.append(obj)
-    subprocess.check_call(["g++", "-shared", "-pthread", "-o", LIB, *objs, "-ldl"])
-    return LIB
+    subprocess.check_call(["g++", "-shared", "-pthread", *(["-fsanitize=address"] if asan else []), "-o", lib, *objs, "-ldl"])
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv))
+    print(build(force="--force" in sys.argv, asan="--asan" in sys.argv))

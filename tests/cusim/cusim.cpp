@@ -13,6 +13,16 @@
 #include <thread>
 #include <vector>
 
+#if defined(__SANITIZE_ADDRESS__)
+// AddressSanitizer build (tests/cusim/build_cusim.py --asan): the fiber switches are announced to the runtime so that
+// its shadow stack bookkeeping follows them; "device" memory is then the instrumented heap, i.e. an out-of-bounds access
+// of a kernel is reported like compute-sanitizer's memcheck would on the GPU.
+#include <sanitizer/common_interface_defs.h>
+#define CUSIM_ASAN 1
+#else
+#define CUSIM_ASAN 0
+#endif
+
 #if !defined(__x86_64__)
 #error "cusim's context switch is written for x86-64"
 #endif
@@ -53,6 +63,7 @@ constexpr unsigned kMaxThreads = 1024;
 enum Wait : uint8_t { RUNNABLE = 0, WAIT_BARRIER, WAIT_WARP, WAIT_POLL, DONE };
 
 struct Fiber {
+  void* fake_stack = nullptr;  // ASAN fake-stack handle while the fiber is switched out
   void* sp = nullptr;
   char* stack = nullptr;
   Wait wait = RUNNABLE;
@@ -81,6 +92,9 @@ struct Cta {
   size_t dyn_cap = 0;
   const std::function<void()>* body = nullptr;
   char* stacks = nullptr;
+  void* sched_fake_stack = nullptr;       // ASAN bookkeeping of the scheduler's (OS thread's) stack
+  const void* sched_stack_bottom = nullptr;
+  size_t sched_stack_size = 0;
 };
 
 thread_local Cta* g_cta = nullptr;
@@ -109,7 +123,13 @@ void release_cta(Cta* c) {
 void yield_to_scheduler() {
   Cta* c = g_cta;
   Fiber& f = c->fibers[c->cur];
+#if CUSIM_ASAN
+  __sanitizer_start_switch_fiber(&f.fake_stack, c->sched_stack_bottom, c->sched_stack_size);
+#endif
   cusim_switch(&f.sp, c->sched_sp);
+#if CUSIM_ASAN
+  __sanitizer_finish_switch_fiber(f.fake_stack, &c->sched_stack_bottom, &c->sched_stack_size);
+#endif
 }
 
 void release_barrier_if_complete(Cta* c) {
@@ -133,6 +153,9 @@ void release_warp_if_complete(Warp& w, unsigned mask_expected) {
 
 void fiber_main() {
   Cta* c = g_cta;
+#if CUSIM_ASAN
+  __sanitizer_finish_switch_fiber(nullptr, &c->sched_stack_bottom, &c->sched_stack_size);
+#endif
   (*c->body)();
   // thread exit: it no longer takes part in barriers or warp collectives
   Fiber& f = c->fibers[c->cur];
@@ -145,6 +168,9 @@ void fiber_main() {
   // a collective that was only waiting for this lane completes (CUDA ignores exited lanes)
   const unsigned b = w.gen & 1u;
   if (w.arrived[b] != 0 && w.live != 0 && (w.arrived[b] & w.live) == w.live) release_warp_if_complete(w, w.arrived[b]);
+#if CUSIM_ASAN
+  __sanitizer_start_switch_fiber(nullptr, c->sched_stack_bottom, c->sched_stack_size);  // this fiber is finished
+#endif
   cusim_switch(&f.sp, c->sched_sp);
   fprintf(stderr, "cusim: finished fiber resumed\n");
   abort();
@@ -220,7 +246,13 @@ void run_cta(Cta* c, dim3 grid, dim3 block, uint3 bid) {
       f.wait = RUNNABLE;
       c->cur = i;
       tc.tid = f.tid;
+#if CUSIM_ASAN
+      __sanitizer_start_switch_fiber(&c->sched_fake_stack, f.stack, kStackBytes);
+#endif
       cusim_switch(&c->sched_sp, f.sp);
+#if CUSIM_ASAN
+      __sanitizer_finish_switch_fiber(c->sched_fake_stack, nullptr, nullptr);
+#endif
       progressed = true;
       if (f.wait == DONE) ++done;
     }
@@ -316,16 +348,24 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()
   auto worker = [&]() {
     Cta* c = acquire_cta();
     c->body = &body;
+#if CUSIM_ASAN
+    // exactly the bytes the launch asked for (rounded to the 16-byte granularity the kernels' staged copies may read),
+    // so that a kernel running past its dynamic shared memory hits a redzone
+    free(c->dyn);
+    c->dyn_cap = ((smem_bytes + 15) & ~static_cast<size_t>(15)) + 64;
+    if (posix_memalign(&c->dyn, 1024, c->dyn_cap - 64 ? c->dyn_cap - 64 : 16) != 0) abort();
+#else
     if (smem_bytes + 64 > c->dyn_cap) {
       free(c->dyn);
       c->dyn_cap = smem_bytes + 64 < (256u << 10) ? (256u << 10) : smem_bytes + 64;
       if (posix_memalign(&c->dyn, 1024, c->dyn_cap) != 0) abort();
     }
+#endif
     for (;;) {
       const uint64_t i = next.fetch_add(1);  // in-order dispatch, like the hardware's block scheduler
       if (i >= n_ctas) break;
       // poison the dynamic shared memory so that reads of never-written bytes are reproducible and loud
-      memset(c->dyn, 0xA5, smem_bytes + 64);
+      memset(c->dyn, 0xA5, CUSIM_ASAN ? c->dyn_cap - 64 : smem_bytes + 64);
       const uint3 bid{static_cast<unsigned>(i % grid.x), static_cast<unsigned>((i / grid.x) % grid.y),
                       static_cast<unsigned>(i / (static_cast<uint64_t>(grid.x) * grid.y))};
       run_cta(c, grid, block, bid);

@@ -56,3 +56,19 @@ def test_product_entry_points_refuse_the_emulation(cusim_lib):
     assert r.returncode != 0 and "cusim" in (r.stdout + r.stderr)
     r = subprocess.run([sys.executable, "-c", "import __graft_entry__ as g; g.smoke()"], cwd=ROOT, env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode != 0 and "cusim" in (r.stdout + r.stderr)
+
+
+@pytest.mark.skipif(not os.environ.get("CLDN_CUSIM_ASAN"), reason="opt-in (CLDN_CUSIM_ASAN=1, ~10 min): the parity suite under an AddressSanitizer build of the emulation")
+def test_no_out_of_bounds_access_under_asan(lib_built):
+    # memcheck without a GPU: "device" memory is the instrumented heap, dynamic shared memory is allocated to the exact
+    # size a launch asks for, so a kernel that reads or writes out of bounds is a reported error
+    import build_cusim
+    lib = build_cusim.build(asan=True)
+    libasan = subprocess.check_output(["gcc", "-print-file-name=libasan.so"], text=True).strip()
+    libstdcxx = subprocess.check_output(["gcc", "-print-file-name=libstdc++.so.6"], text=True).strip()
+    env = dict(os.environ, CLDN_B200_LIB=lib, LD_PRELOAD=f"{libasan} {libstdcxx}", ASAN_OPTIONS="detect_leaks=0", CLDN_B200_FUZZ="1",
+               CLDN_B200_FUZZ_SEEDS="40")
+    cmd = [sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", "-p", "no:cacheprovider", "-k", "not c2_full_size",
+           "tests/test_gpu_parity.py", "tests/test_gpu_ros.py"]
+    r = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=3000)
+    assert r.returncode == 0 and "AddressSanitizer" not in (r.stdout + r.stderr), r.stdout[-3000:] + r.stderr[-3000:]

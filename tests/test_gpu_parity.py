@@ -416,3 +416,45 @@ def test_stage2_interop_with_reference(ref, comp):
     t_out = _Dev(size=cap)
     with pytest.raises(RuntimeError, match="host-pointer API"):
         enc.encode_batch_device(enc.make_device_batch([t_in.ptr], [cloud.size], [t_out.ptr], [cap]), want_sizes=True)
+
+
+def test_corrupted_blobs_decode_like_the_reference(ref):
+    # hardened-decoder parity (encoding_utils.hpp:98-148, v4_codec.cpp:85-117, v5_codec.cpp:764-879, cloudini.cpp:645-664):
+    # bit flips, truncations, forged marker bytes and forged chunk prefixes either fail in BOTH decoders or decode to the
+    # same bytes in both. The payload goes through the device-pointer API in an exact-size buffer (under the ASAN build
+    # of tests/cusim an over-read of a kernel is a reported error, like compute-sanitizer memcheck on the GPU).
+    rng = np.random.default_rng(int(os.environ.get("CLDN_B200_CORRUPT_SEED", "0")))
+    trials = int(os.environ.get("CLDN_B200_CORRUPT_TRIALS", "40"))
+    dec = cb.PointcloudDecoder()
+    cases = [synth.cloud_c2(5000, seed=1), synth.cloud_c1(3000, seed=2), synth.cloud_c3(6000, seed=3), synth.cloud_c2(40_000, seed=4),
+             synth.cloud_lossless(3000, seed=5)]
+    for info, cloud in cases:
+        blob = ref.encode(info, cloud)
+        dinfo, hdr = cb.DecodeHeader(blob)
+        n = info.width * info.height * info.point_step
+        for _ in range(trials):
+            b = bytearray(blob)
+            kind = int(rng.integers(0, 4))
+            if kind == 0:
+                for _k in range(int(rng.integers(1, 4))):
+                    b[int(rng.integers(hdr, len(b)))] ^= 1 << int(rng.integers(0, 8))
+            elif kind == 1:
+                b = b[:int(rng.integers(hdr, len(b)))]
+            elif kind == 2:
+                b[int(rng.integers(hdr, len(b)))] = (0x00, 0x80, 0xFF)[int(rng.integers(0, 3))]
+            else:
+                b[hdr + int(rng.integers(0, 4))] ^= 1 << int(rng.integers(0, 8))
+            b = bytes(b)
+            want, ref_ok = np.full(n, 0x33, dtype=np.uint8), True
+            try:
+                ref.decode(b, want)
+            except RuntimeError:
+                ref_ok = False
+            payload, out, ours_ok = _Dev(src=np.frombuffer(b[hdr:], dtype=np.uint8)) if len(b) > hdr else _Dev(size=1), _Dev(src=np.full(n, 0x33, dtype=np.uint8)), True
+            try:
+                dec.decode_batch_device(dinfo, dec.make_device_batch([payload.ptr], [len(b) - hdr], [out.ptr], [n]), sync=True)
+            except RuntimeError:
+                ours_ok = False
+            assert ours_ok == ref_ok, (kind, [f.name for f in info.fields])
+            if ref_ok:
+                assert np.array_equal(out.numpy(), want), (kind, [f.name for f in info.fields])
