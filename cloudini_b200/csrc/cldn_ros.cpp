@@ -227,14 +227,16 @@ int cldn_b200_ros_compress_msg(cldn_encoder_t* enc, const cldn_ros_msg_t* msg, v
     const uint32_t sz = static_cast<uint32_t>(blob);
     memcpy(o + size_at, &sz, 4);  // the reference memcpy's the native value, whatever the message's endianness (:203)
   }
-  // trailing fields (:209-212): is_dense (1 byte, no alignment), format = "cloudini"
-  CdrWriter t;
-  t.buf.resize(prev + blob);  // only the length matters for the alignment arithmetic
-  t.big = w.big;
-  t.u8(msg->is_dense);
-  t.str("cloudini", 8);
-  memcpy(o + prev + blob, t.buf.data() + prev + blob, t.buf.size() - prev - blob);
-  if (written) *written = t.buf.size();
+  // trailing fields (:209-212): is_dense (1 byte, no alignment), then format = "cloudini" (u32 length 9 aligned to 4
+  // relative to the byte after the encapsulation header, characters, NUL)
+  size_t pos = prev + blob;
+  o[pos++] = msg->is_dense;
+  while ((pos - 4) % 4) o[pos++] = 0;
+  uint32_t len = 9;
+  if (w.big) len = __builtin_bswap32(len);
+  memcpy(o + pos, &len, 4);
+  memcpy(o + pos + 4, "cloudini", 9);
+  if (written) *written = pos + 13;
   return CLDN_OK;
 }
 
@@ -265,6 +267,100 @@ int cldn_b200_ros_decompress_msg(cldn_decoder_t* dec, const cldn_ros_msg_t* msg,
   o[prev + cloud_bytes] = msg->is_dense;
   if (written) *written = total;
   return CLDN_OK;
+}
+
+// ---- the DDS-message half of the reference's own C ABI (src/wasm_functions.cpp:24-226) ------------------------------------
+uint32_t cldn_b200_GetHeaderAsYAML(const void* encoded_data, uint32_t encoded_data_size, char* output_yaml, uint32_t capacity) {
+  if (!encoded_data || !output_yaml) { set_error("null argument"); return 0; }
+  cldn_info_t info;
+  size_t hdr = 0, need = 0;
+  if (cldn_b200_decode_header(static_cast<const uint8_t*>(encoded_data), encoded_data_size, &info, &hdr) != CLDN_OK) return 0;
+  cldn_b200_info_to_yaml(&info, nullptr, 0, &need);  // strlen + 1
+  std::vector<char> text(need);
+  if (cldn_b200_info_to_yaml(&info, text.data(), text.size(), nullptr) != CLDN_OK) return 0;
+  const uint32_t n = static_cast<uint32_t>(need ? need - 1 : 0);
+  if (n > capacity) { set_error("output buffer too small for the YAML text (%u bytes)", n); return 0; }
+  memcpy(output_yaml, text.data(), n);  // like the reference: no terminator is written (:36-38)
+  return n;
+}
+
+uint32_t cldn_b200_GetHeaderAsYAMLFromDDS(const void* raw_dds_msg, uint32_t dds_msg_size, char* output_yaml, uint32_t capacity) {
+  cldn_ros_msg_t m;
+  if (cldn_b200_ros_parse(raw_dds_msg, dds_msg_size, &m) != CLDN_OK) return 0;
+  return cldn_b200_GetHeaderAsYAML(m.data, static_cast<uint32_t>(m.data_bytes), output_yaml, capacity);
+}
+
+uint32_t cldn_b200_GetDecompressedSize(const void* encoded_dds_msg, uint32_t encoded_dds_size) {
+  cldn_ros_msg_t m;
+  if (cldn_b200_ros_parse(encoded_dds_msg, encoded_dds_size, &m) != CLDN_OK) return 0;
+  return m.height * m.width * m.point_step;
+}
+
+// parse + toEncodingInfo + "every FLOAT32 field gets `resolution`" (wasm_functions.cpp:63-73, 184-194)
+static bool message_encoding_info(const void* msg, uint32_t size, float resolution, cldn_ros_msg_t* m, cldn_info_t* info) {
+  if (cldn_b200_ros_parse(msg, size, m) != CLDN_OK || cldn_b200_ros_to_encoding_info(m, info) != CLDN_OK) return false;
+  for (uint32_t i = 0; i < info->n_fields; ++i) {
+    if (info->fields[i].type == CLDN_FLOAT32) {
+      info->fields[i].has_resolution = 1;
+      info->fields[i].resolution = resolution;
+    }
+  }
+  return true;
+}
+
+static uint32_t encode_message_payload(const cldn_ros_msg_t& m, const cldn_info_t& info, std::vector<uint8_t>* blob) {
+  cldn_encoder_t* enc = nullptr;
+  if (cldn_b200_encoder_create(&info, -1, nullptr, &enc) != CLDN_OK) return 0;
+  const size_t cap = info.point_step ? cldn_b200_max_compressed_size(&info, m.data_bytes / info.point_step, 1) : 0;
+  blob->resize(cap);
+  size_t written = 0;
+  const int rc = cap ? cldn_b200_encode(enc, m.data, m.data_bytes, blob->data(), blob->size(), 1, &written, CLDN_MEM_HOST) : CLDN_ERR_INVALID_ARGUMENT;
+  cldn_b200_encoder_destroy(enc);
+  return rc == CLDN_OK ? static_cast<uint32_t>(written) : 0;
+}
+
+uint32_t cldn_b200_ComputeCompressedSize(const void* dds_msg, uint32_t dds_msg_size, float resolution) {
+  cldn_ros_msg_t m;
+  cldn_info_t info;
+  if (!message_encoding_info(dds_msg, dds_msg_size, resolution, &m, &info)) return 0;
+  const size_t expected = static_cast<size_t>(m.width) * m.height * m.point_step;
+  if (m.data_bytes != expected && (m.width == 0 || m.height == 0)) return 0;  // :81-86
+  std::vector<uint8_t> blob;
+  return encode_message_payload(m, info, &blob);
+}
+
+uint32_t cldn_b200_EncodePointcloudMessage(const void* pointcloud_msg, uint32_t msg_size, float resolution, void* output_data,
+                                           uint32_t capacity) {
+  if (!output_data) { set_error("null argument"); return 0; }
+  cldn_ros_msg_t m;
+  cldn_info_t info;
+  if (!message_encoding_info(pointcloud_msg, msg_size, resolution, &m, &info)) return 0;
+  const size_t expected = static_cast<size_t>(m.width) * m.height * m.point_step;
+  if (m.data_bytes != expected) { set_error("Data size mismatch"); return 0; }  // :197-201
+  std::vector<uint8_t> blob;
+  const uint32_t n = encode_message_payload(m, info, &blob);
+  if (n == 0) return 0;
+  if (n > capacity) { set_error("Output buffer too small for encoded message"); return 0; }  // :217-220
+  memcpy(output_data, blob.data(), n);
+  return n;
+}
+
+uint32_t cldn_b200_ConvertCompressedMsgToPointCloud2Msg(const void* compressed_msg, uint32_t msg_size, void* output_msg, uint32_t capacity) {
+  if (!output_msg) { set_error("null argument"); return 0; }
+  cldn_ros_msg_t m;
+  if (cldn_b200_ros_parse(compressed_msg, msg_size, &m) != CLDN_OK) return 0;
+  cldn_decoder_t* dec = nullptr;
+  if (cldn_b200_decoder_create(-1, nullptr, &dec) != CLDN_OK) return 0;
+  size_t written = 0;
+  const int rc = cldn_b200_ros_decompress_msg(dec, &m, output_msg, capacity, &written);
+  cldn_b200_decoder_destroy(dec);
+  return rc == CLDN_OK ? static_cast<uint32_t>(written) : 0;
+}
+
+uint32_t cldn_b200_DecodeCompressedMessage(const void* compressed_msg, uint32_t msg_size, void* output_data, uint32_t capacity) {
+  cldn_ros_msg_t m;
+  if (cldn_b200_ros_parse(compressed_msg, msg_size, &m) != CLDN_OK) return 0;
+  return cldn_b200_DecodeCompressedData(m.data, static_cast<uint32_t>(m.data_bytes), output_data, capacity);
 }
 
 }  // extern "C"

@@ -84,6 +84,28 @@ int cldn_b200_ros_compress_msg(cldn_encoder_t* enc, const cldn_ros_msg_t* msg, v
 int cldn_b200_ros_decompress_msg(cldn_decoder_t* dec, const cldn_ros_msg_t* msg, void* out, size_t out_capacity,
                                  size_t* written);
 
+/* ---- the rest of the reference's own C ABI (include/cloudini_lib/wasm_functions.h:30-93, src/wasm_functions.cpp), the
+ * functions that take DDS messages. Same shape and "return 0 on any failure" convention; every output pointer is
+ * followed by its capacity (the WASM module trusts the caller's allocation instead). Host memory. ------------------- */
+/* cldn_GetHeaderAsYAML (wasm_functions.cpp:24-44): YAML text of the blob's header (not NUL-terminated); returns its size. */
+uint32_t cldn_b200_GetHeaderAsYAML(const void* encoded_data, uint32_t encoded_data_size, char* output_yaml, uint32_t capacity);
+/* cldn_GetHeaderAsYAMLFromDDS (:46-56): same, the blob is the compressed_data of a CompressedPointCloud2 message. */
+uint32_t cldn_b200_GetHeaderAsYAMLFromDDS(const void* raw_dds_msg, uint32_t dds_msg_size, char* output_yaml, uint32_t capacity);
+/* cldn_ComputeCompressedSize (:58-93): full GPU encode of a PointCloud2 message (every FLOAT32 field at `resolution`,
+ * toEncodingInfo defaults: LOSSY + ZSTD), only the size is returned. */
+uint32_t cldn_b200_ComputeCompressedSize(const void* dds_msg, uint32_t dds_msg_size, float resolution);
+/* cldn_GetDecompressedSize (:95-106): height * width * point_step of the message; nothing is decoded. */
+uint32_t cldn_b200_GetDecompressedSize(const void* encoded_dds_msg, uint32_t encoded_dds_size);
+/* cldn_ConvertCompressedMsgToPointCloud2Msg (:108-125): CompressedPointCloud2 message -> PointCloud2 message. */
+uint32_t cldn_b200_ConvertCompressedMsgToPointCloud2Msg(const void* compressed_msg, uint32_t msg_size, void* output_msg,
+                                                        uint32_t capacity);
+/* cldn_DecodeCompressedMessage (:127-148): CompressedPointCloud2 message -> raw point data. */
+uint32_t cldn_b200_DecodeCompressedMessage(const void* compressed_msg, uint32_t msg_size, void* output_data, uint32_t capacity);
+/* cldn_EncodePointcloudMessage (:178-226): PointCloud2 message -> Cloudini blob with header (every FLOAT32 field at
+ * `resolution`); 0 when data size != width * height * point_step or the blob does not fit `capacity`. */
+uint32_t cldn_b200_EncodePointcloudMessage(const void* pointcloud_msg, uint32_t msg_size, float resolution, void* output_data,
+                                           uint32_t capacity);
+
 #ifdef __cplusplus
 }
 #endif

@@ -215,3 +215,41 @@ def test_dds_roundtrip_like_the_reference_test(golden_ros):
     ok = np.isfinite(fa)
     assert np.all(np.abs(fa[ok] - fb[ok]) <= 0.001) and np.array_equal(np.isnan(fa), np.isnan(fb))
     assert np.array_equal(a[:, 16:18], b[:, 16:18]) and np.array_equal(a[:, 18:26], b[:, 18:26])
+
+
+def test_wasm_shaped_message_functions(ref):
+    # the DDS-message half of the reference's C ABI (wasm_functions.cpp:58-226) through the GPU codec
+    import ctypes as C
+    L = cb.lib()
+    vp, u32 = C.c_void_p, C.c_uint32
+    L.cldn_b200_ComputeCompressedSize.restype, L.cldn_b200_ComputeCompressedSize.argtypes = u32, [vp, u32, C.c_float]
+    L.cldn_b200_EncodePointcloudMessage.restype, L.cldn_b200_EncodePointcloudMessage.argtypes = u32, [vp, u32, C.c_float, vp, u32]
+    L.cldn_b200_DecodeCompressedMessage.restype, L.cldn_b200_DecodeCompressedMessage.argtypes = u32, [vp, u32, vp, u32]
+    L.cldn_b200_ConvertCompressedMsgToPointCloud2Msg.restype, L.cldn_b200_ConvertCompressedMsgToPointCloud2Msg.argtypes = u32, [vp, u32, vp, u32]
+    info, cloud = synth.cloud_c2(30_000, seed=8)
+    msg = np.frombuffer(synth.pointcloud2_msg(XYZI, 16, cloud), dtype=np.uint8)
+    out = np.zeros(msg.size, dtype=np.uint8)
+    n = L.cldn_b200_EncodePointcloudMessage(msg.ctypes.data, msg.size, 0.001, out.ctypes.data, out.size)
+    assert n > 0 and n == L.cldn_b200_ComputeCompressedSize(msg.ctypes.data, msg.size, 0.001)
+    blob = bytes(out[:n])
+    dinfo, hdr = cb.DecodeHeader(blob)
+    assert dinfo.compression_opt == cb.CompressionOption.ZSTD and all(f.resolution == pytest.approx(0.001) for f in dinfo.fields)
+    want = np.zeros(cloud.size, dtype=np.uint8)
+    ref.decode(blob, want)                                     # the reference reads what the message encoder wrote
+    pc = ros.getDeserializedPointCloudMessage(bytes(msg))
+    pc.data = np.frombuffer(blob, dtype=np.uint8)              # wrap the blob like the publisher does: a CompressedPointCloud2 message
+    einfo = ros.toEncodingInfo(pc)
+    for f in einfo.fields:
+        f.resolution = 0.001
+    comp = np.frombuffer(ref.ros_compress(bytes(msg), {}, 0.001, False, 1, 2, 5), dtype=np.uint8)   # the reference's own compressed message (ZSTD)
+    raw = np.zeros(cloud.size, dtype=np.uint8)
+    assert L.cldn_b200_DecodeCompressedMessage(comp.ctypes.data, comp.size, raw.ctypes.data, raw.size) == cloud.size
+    assert np.array_equal(raw, want)
+    full = np.zeros(msg.size + 64, dtype=np.uint8)
+    m = L.cldn_b200_ConvertCompressedMsgToPointCloud2Msg(comp.ctypes.data, comp.size, full.ctypes.data, full.size)
+    assert m > 0 and bytes(full[:m]) == ref.ros_decompress(bytes(comp), msg.size + 64)
+    # failures return 0: size mismatch (width * height * point_step != data), output too small, garbage
+    bad = np.frombuffer(synth.pointcloud2_msg(XYZI, 16, cloud, width=29_999), dtype=np.uint8)
+    assert L.cldn_b200_EncodePointcloudMessage(bad.ctypes.data, bad.size, 0.001, out.ctypes.data, out.size) == 0
+    assert L.cldn_b200_EncodePointcloudMessage(msg.ctypes.data, msg.size, 0.001, out.ctypes.data, 100) == 0
+    assert L.cldn_b200_DecodeCompressedMessage(comp.ctypes.data, 40, raw.ctypes.data, raw.size) == 0

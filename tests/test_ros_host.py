@@ -73,3 +73,29 @@ def test_golden_messages_parse(golden_ros):
     for name, g in golden_ros.items():
         pc = ros.getDeserializedPointCloudMessage(g["msg"])
         assert _describe(pc) == g["describe"], name
+
+
+def test_wasm_shaped_host_functions(ref, golden_ros):
+    # cldn_GetHeaderAsYAML / cldn_GetHeaderAsYAMLFromDDS / cldn_GetDecompressedSize (wasm_functions.cpp:24-56,95-106): host only
+    import ctypes as C
+    L = cb.lib()
+    for f in (L.cldn_b200_GetHeaderAsYAML, L.cldn_b200_GetHeaderAsYAMLFromDDS):
+        f.restype, f.argtypes = C.c_uint32, [C.c_void_p, C.c_uint32, C.c_char_p, C.c_uint32]
+    L.cldn_b200_GetDecompressedSize.restype, L.cldn_b200_GetDecompressedSize.argtypes = C.c_uint32, [C.c_void_p, C.c_uint32]
+    for name, g in golden_ros.items():
+        comp = np.frombuffer(g["compressed"], dtype=np.uint8)
+        pc = ros.getDeserializedPointCloudMessage(g["compressed"])
+        assert L.cldn_b200_GetDecompressedSize(comp.ctypes.data, comp.size) == pc.width * pc.height * pc.point_step
+        buf = C.create_string_buffer(1 << 16)
+        n = L.cldn_b200_GetHeaderAsYAMLFromDDS(comp.ctypes.data, comp.size, buf, len(buf))
+        if pc.data.size == 0:   # empty cloud: no blob, hence no header -> 0 like the reference (DecodeHeader throws)
+            assert n == 0
+            continue
+        blob = np.ascontiguousarray(pc.data)
+        assert n > 0 and n == L.cldn_b200_GetHeaderAsYAML(blob.ctypes.data, blob.size, buf, len(buf))
+        text = buf.raw[:n].decode()
+        assert text == cb.EncodingInfoToYAML(cb.DecodeHeader(bytes(blob))[0])
+        assert L.cldn_b200_GetHeaderAsYAML(blob.ctypes.data, blob.size, buf, 10) == 0          # capacity too small
+    junk = np.zeros(64, dtype=np.uint8)
+    assert L.cldn_b200_GetHeaderAsYAML(junk.ctypes.data, junk.size, C.create_string_buffer(64), 64) == 0
+    assert L.cldn_b200_GetDecompressedSize(junk.ctypes.data, 3) == 0
