@@ -100,6 +100,28 @@ def cloud_c4_frame(frame: int, seed: int = 4, rings: int = 64, az: int = 2032):
     return info_xyzi(n), np.ascontiguousarray(pts, dtype=np.float32).view(np.uint8).reshape(-1)
 
 
+def cloud_c4_mixed_frame(frame: int, seed: int = 4, rings: int = 64, az: int = 2032):
+    """C4 with the sensor's full layout: Velodyne PointXYZIRT-like, x y z intensity f32 + ring u16 @16 +
+    time f32 @18, point_step 22 (unaligned on purpose, as ROS drivers pack it). Planner: FloatN(4) + V5 section (ring)
+    + scalar lossy float (time, resolution 1e-5 s) in the regular stream."""
+    info16, xyzi = cloud_c4_frame(frame, seed, rings, az)
+    n = info16.width
+    buf = np.zeros((n, 22), dtype=np.uint8)
+    buf[:, :16] = xyzi.reshape(n, 16)
+    i = np.arange(n, dtype=np.int64)
+    buf[:, 16:18] = (i % rings).astype(np.uint16).view(np.uint8).reshape(n, 2)
+    t = ((i // rings).astype(np.float64) * (0.1 / az)).astype(np.float32)  # one revolution = 100 ms
+    buf[:, 18:22] = t.view(np.uint8).reshape(n, 4)
+    F = FieldType
+    info = EncodingInfo(
+        fields=[PointField("x", 0, F.FLOAT32, 0.001), PointField("y", 4, F.FLOAT32, 0.001), PointField("z", 8, F.FLOAT32, 0.001),
+                PointField("intensity", 12, F.FLOAT32, 0.001), PointField("ring", 16, F.UINT16, None),
+                PointField("time", 18, F.FLOAT32, 1e-5)],
+        width=n, height=1, point_step=22, encoding_opt=EncodingOptions.LOSSY, compression_opt=CompressionOption.NONE,
+        use_threads=False, version=5)
+    return info, np.ascontiguousarray(buf).reshape(-1)
+
+
 def cloud_lossless(n: int = 40_000, seed: int = 6, lossless: bool = True, version: int = 5, stamp_res=None,
                    hostile: bool = True):
     """The reference's DDS / PCD layout (x, y, z, intensity f32, ring u16, timestamp f64; point_step 26) used to reach

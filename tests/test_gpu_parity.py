@@ -458,3 +458,19 @@ def test_corrupted_blobs_decode_like_the_reference(ref):
             assert ours_ok == ref_ok, (kind, [f.name for f in info.fields])
             if ref_ok:
                 assert np.array_equal(out.numpy(), want), (kind, [f.name for f in info.fields])
+
+
+def test_c4_velodyne_mixed_layout(oracle):
+    # BASELINE configs[3] with the sensor's own point layout (XYZI + ring u16 + time f32, step 22): FloatN(4) + one V5
+    # section + a scalar lossy float in the regular stream, every field after the first four unaligned
+    for frame in (0, 7):
+        info, cloud = synth.cloud_c4_mixed_frame(frame)
+        _roundtrip_check(info, cloud, oracle, fill=0x11)
+    info, _ = synth.cloud_c4_mixed_frame(0)
+    frames = [synth.cloud_c4_mixed_frame(k)[1] for k in range(3)]
+    enc = cb.PointcloudEncoder(info)
+    cap = cb.MaxCompressedSize(info, info.width, True)
+    outs = [np.zeros(cap, dtype=np.uint8) for _ in frames]
+    sizes = enc.encode_batch_host(frames, outs, write_header=True)
+    for c, o, s in zip(frames, outs, sizes):
+        assert bytes(o[:s]) == oracle.encode(info, c)

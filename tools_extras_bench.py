@@ -4,6 +4,7 @@ runs this file in a child process with a timeout and records whatever JSON line 
   viz   applyVizLossyPreprocessing kernels on a device-resident 1M-point XYZI cloud: ms per call,
         survivors checked against a numpy restatement of "finite && first point of its voxel" (no oracle involved)
   c3    BASELINE configs[2]: 1M-point XYZ + rgba u32 + ring u16 (V5 adaptive sections), 8 frames, encode / decode ms
+  c4    BASELINE configs[3] with the Velodyne XYZIRT layout (step 22), 64 frames of 130 048 points, encode / decode ms
   msg   the DDS converter step (parse -> profile -> viz -> compress message) on one 1M-point PointCloud2, host buffers
 """
 import json
@@ -114,6 +115,47 @@ def bench_c3(out):
                              "decode_gbs": algo / td / 1e6, "ints_roundtrip_exact": ints_ok, "max_float_error": f_err}
 
 
+def bench_c4_mixed(out):
+    """BASELINE configs[3] with the sensor's own layout (XYZI + ring u16 + time f32, step 22, generic kernels + V5 section)."""
+    F = 64
+    info, _ = synth.cloud_c4_mixed_frame(0)
+    clouds = [synth.cloud_c4_mixed_frame(k)[1] for k in range(F)]
+    n, step = info.width, info.point_step
+    s = torch.cuda.Stream()
+    torch.cuda.set_stream(s)
+    enc, dec = cb.PointcloudEncoder(info, stream=s.cuda_stream), cb.PointcloudDecoder(stream=s.cuda_stream)
+    d_in = [torch.from_numpy(c).cuda() for c in clouds]
+    cap = cb.MaxCompressedSize(info, n, True)
+    d_blob = [torch.empty(cap, dtype=torch.uint8, device="cuda") for _ in range(F)]
+    d_out = [torch.zeros(n * step, dtype=torch.uint8, device="cuda") for _ in range(F)]
+    eb = enc.make_device_batch([t.data_ptr() for t in d_in], [n * step] * F, [t.data_ptr() for t in d_blob], [cap] * F)
+    sizes = enc.encode_batch_device(eb, True, want_sizes=True)
+    hdr = len(enc.getHeader())
+    db = dec.make_device_batch([t.data_ptr() + hdr for t in d_blob], [x - hdr for x in sizes], [t.data_ptr() for t in d_out], [n * step] * F)
+    dec.decode_batch_device(info, db, sync=True)
+    got, src = d_out[0].cpu().numpy().reshape(n, step), clouds[0].reshape(n, step)
+    ring_ok = bool(np.array_equal(got[:, 16:18], src[:, 16:18]))
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    te = td = 0.0
+    reps = 10
+    for _ in range(2):
+        enc.encode_batch_device(eb, True)
+        dec.decode_batch_device(info, db, sync=False)
+    for _ in range(reps):
+        ev[0].record()
+        enc.encode_batch_device(eb, True)
+        ev[1].record()
+        dec.decode_batch_device(info, db, sync=False)
+        ev[2].record()
+        torch.cuda.synchronize()
+        te += ev[0].elapsed_time(ev[1])
+        td += ev[1].elapsed_time(ev[2])
+    te, td = te / reps, td / reps
+    S = float(np.mean(sizes)) - hdr
+    out["c4_velodyne_xyzirt"] = {"frames": F, "points": n, "point_step": step, "stage1_B_per_pt": S / n, "encode_ms": te, "decode_ms": td,
+                                 "encode_mpts": F * n / te / 1e3, "decode_mpts": F * n / td / 1e3, "ring_roundtrip_exact": ring_ok}
+
+
 def bench_msg(out):
     from cloudini_b200 import FieldType as FT
     n = 1_000_000
@@ -144,7 +186,7 @@ def bench_msg(out):
 
 if __name__ == "__main__":
     out = {}
-    for name, fn in (("viz", bench_viz), ("c3", bench_c3), ("msg", bench_msg)):
+    for name, fn in (("viz", bench_viz), ("c3", bench_c3), ("c4", bench_c4_mixed), ("msg", bench_msg)):
         try:
             fn(out)
         except Exception as e:  # noqa: BLE001 — an extra must never take the others down
