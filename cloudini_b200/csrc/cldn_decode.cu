@@ -746,16 +746,13 @@ __global__ void decode_sequential_kernel(const DecLaunch L) {
       const RegOp& op = plan.ops[k];
       if (op.kind == OP_COPY) {
         if (avail < op.size) { report_error(L.err, DEV_ERR_TRUNCATED); return; }
-        if (op.offset[0] != CLDN_SKIP_STORE_OFFSET) {
-          for (int b = 0; b < op.size; ++b) point[op.offset[0] + b] = p[b];
-        }
+        if (op.offset[0] != CLDN_SKIP_STORE_OFFSET) store_low_bytes(point + op.offset[0], load_raw_bits(p, op.size), op.size);
         p += op.size; avail -= op.size;
         continue;
       }
       if (op.kind == OP_XOR32 || op.kind == OP_XOR64) {  // field_decoder.hpp:356-370
         if (avail < op.size) { report_error(L.err, DEV_ERR_TRUNCATED); return; }
-        unsigned long long res = 0;
-        for (int b = 0; b < op.size; ++b) res |= static_cast<unsigned long long>(p[b]) << (8 * b);
+        const unsigned long long res = load_raw_bits(p, op.size);
         p += op.size; avail -= op.size;
         prev[k] = static_cast<long long>(static_cast<unsigned long long>(prev[k]) ^ res);
         if (op.offset[0] != CLDN_SKIP_STORE_OFFSET) store_low_bytes(point + op.offset[0], static_cast<uint64_t>(prev[k]), op.size);

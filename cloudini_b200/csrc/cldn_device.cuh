@@ -237,44 +237,59 @@ __device__ __forceinline__ uint32_t gorilla_encode(GorillaState& st, uint64_t cu
   for (uint32_t i = 0; i < bytes; ++i) out[i] = static_cast<uint8_t>(i < 8u ? (a.lo >> (8u * i)) : (a.hi >> (8u * (i - 8u))));
   return bytes;
 }
-// Reads nbits (<= 64) at bit position *bitpos of p (avail bytes). Returns false when the input is truncated.
-__device__ __forceinline__ bool read_bits(const uint8_t* p, uint32_t avail, uint32_t* bitpos, uint32_t nbits, uint64_t* out) {
-  if ((*bitpos + nbits + 7u) / 8u > avail) return false;
-  uint64_t v = 0;
-  for (uint32_t i = 0; i < nbits; ++i) {
-    const uint32_t b = *bitpos + i;
-    v |= static_cast<uint64_t>((p[b >> 3] >> (b & 7u)) & 1u) << i;
+// The next <= 10 bytes of the stream (one Gorilla record is at most 2 + 5 + 6 + 64 = 77 bits) as a 128-bit window;
+// bit fields are then cut out of registers instead of being gathered bit by bit from memory.
+struct BitWindow {
+  uint64_t lo = 0, hi = 0;
+  uint32_t avail;  // bytes that really exist behind p
+  uint32_t bp = 0; // bit position of the next field
+  __device__ __forceinline__ BitWindow(const uint8_t* p, uint32_t avail_) : avail(avail_) {
+    if (avail_ >= 10u) {
+      lo = load_u64(p);
+      hi = load_u16(p + 8);
+    } else {
+#pragma unroll
+      for (uint32_t b = 0; b < 8u; ++b) if (b < avail_) lo |= static_cast<uint64_t>(p[b]) << (8u * b);
+      if (avail_ > 8u) hi = p[8];
+    }
   }
-  *bitpos += nbits;
-  *out = v;
-  return true;
-}
+  // Reads nbits (<= 64). Returns false when the field does not lie inside the available bytes (same test, in the same
+  // order, as the reference's bit reader: truncated input is reported at the first field that crosses the end).
+  __device__ __forceinline__ bool read(uint32_t nbits, uint64_t* out) {
+    if ((bp + nbits + 7u) / 8u > avail) return false;
+    uint64_t v = bp == 0 ? lo : (bp < 64u ? ((lo >> bp) | (hi << (64u - bp))) : (hi >> (bp - 64u)));
+    if (nbits < 64u) v &= (1ull << nbits) - 1ull;
+    bp += nbits;
+    *out = v;
+    return true;
+  }
+};
 // Decodes one value (field_decoder.hpp:257-300). Returns the bytes consumed, 0 when the input is truncated / malformed.
 __device__ __forceinline__ uint32_t gorilla_decode(GorillaState& st, const uint8_t* p, uint32_t avail, uint64_t* value) {
-  uint32_t bp = 0;
+  BitWindow w(p, avail);
   uint64_t v;
   if (st.first) {
     st.first = false;
-    if (!read_bits(p, avail, &bp, 64, &v)) return 0;
+    if (!w.read(64, &v)) return 0;
     st.prev_bits = v;
   } else {
     uint64_t flag;
-    if (!read_bits(p, avail, &bp, 1, &flag)) return 0;
+    if (!w.read(1, &flag)) return 0;
     if (flag == 0) {
       v = st.prev_bits;
     } else {
       uint64_t control, bits, x;
-      if (!read_bits(p, avail, &bp, 1, &control)) return 0;
+      if (!w.read(1, &control)) return 0;
       if (control == 0) {
         const uint32_t meaningful = (64u - st.leading - st.trailing) & 0xFFu;
         if (meaningful > 64u) return 0;  // window reuse before any window: malformed
-        if (!read_bits(p, avail, &bp, meaningful, &bits)) return 0;
+        if (!w.read(meaningful, &bits)) return 0;
         x = st.trailing < 64u ? bits << st.trailing : 0ull;
       } else {
         uint64_t lead, m1;
-        if (!read_bits(p, avail, &bp, 5, &lead) || !read_bits(p, avail, &bp, 6, &m1)) return 0;
+        if (!w.read(5, &lead) || !w.read(6, &m1)) return 0;
         const uint32_t meaningful = static_cast<uint32_t>(m1) + 1u;
-        if (!read_bits(p, avail, &bp, meaningful, &bits)) return 0;
+        if (!w.read(meaningful, &bits)) return 0;
         const uint32_t trailing = (64u - static_cast<uint32_t>(lead) - meaningful) & 0xFFu;
         x = trailing < 64u ? bits << trailing : 0ull;
         st.leading = static_cast<uint32_t>(lead);
@@ -285,7 +300,7 @@ __device__ __forceinline__ uint32_t gorilla_decode(GorillaState& st, const uint8
     }
   }
   *value = v;
-  return (bp + 7u) >> 3;
+  return (w.bp + 7u) >> 3;
 }
 
 // ---- block-wide exclusive scan of one uint32 per thread (kThreads threads) --------------------------------------

@@ -494,14 +494,20 @@ static int launch_floatn(const Plan& plan, const EncLaunch& L, bool vec4, cudaSt
   return 1;
 }
 
-// Gorilla pre-pass: one thread per (chunk, Gorilla op) walks its 32768 points in order (the window of the previous
-// "new window" record is inherently sequential) and leaves a 12-byte record per point: bytes 0..9 the encoded value,
-// byte 11 its length. The generic kernel then copies the record like any other field. Side layout: [op][point][12].
-__global__ void gorilla_prepass_kernel(const EncLaunch L) {
+// Gorilla pre-pass: one WARP per (chunk, Gorilla op) leaves a 12-byte record per point (bytes 0..9 the encoded value,
+// byte 11 its length); the generic kernel then copies the record like any other field. Side layout: [op][point][12].
+// The only sequential part of the coder is the (leading, trailing) window of the last "new window" record
+// (field_encoder.hpp:262-296): a value keeps the window when its XOR fits into it, otherwise it starts a new one. The warp
+// takes 32 consecutive values at a time; every lane knows its own XOR / leading / trailing zeros, and the window each lane
+// sees is resolved with one ballot per window change inside the group (the first lane that does not fit becomes the
+// new window for the lanes behind it) instead of 32 dependent steps.
+constexpr int kGorillaThreads = 256;
+__global__ void __launch_bounds__(kGorillaThreads) gorilla_prepass_kernel(const EncLaunch L) {
   const EncFrame F = L.frames[blockIdx.x];
   const Plan& plan = *L.plan;
   const uint32_t items = F.n_chunks * plan.n_gorilla;
-  for (uint32_t it = threadIdx.x; it < items; it += blockDim.x) {
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+  for (uint32_t it = warp; it < items; it += n_warps) {  // warp-uniform
     const uint32_t chunk = it / plan.n_gorilla, g = it % plan.n_gorilla;
     uint32_t seen = 0, offset = 0;
     for (uint32_t k = 0; k < plan.n_ops; ++k) {
@@ -513,21 +519,50 @@ __global__ void gorilla_prepass_kernel(const EncLaunch L) {
     const uint32_t p0 = chunk * kChunkPoints;
     const uint32_t n = min(kChunkPoints, F.n_points - p0);
     uint8_t* side = const_cast<uint8_t*>(F.side) + (static_cast<size_t>(g) * F.n_points + p0) * 12;
-    GorillaState st;
-    st.reset();
-    for (uint32_t i = 0; i < n; ++i) {
-      const uint64_t cur = load_u64(F.in + static_cast<size_t>(p0 + i) * plan.point_step + offset);
-      uint8_t rec[12];
-      const uint32_t len = gorilla_encode(st, cur, rec);
-      for (uint32_t b = 0; b < len; ++b) side[i * 12 + b] = rec[b];
-      side[i * 12 + 11] = static_cast<uint8_t>(len);
+    uint32_t win_lead = 255u, win_trail = 0u;  // GorillaState::reset(): no window yet
+    uint64_t last = 0;                         // bits of the value before this group
+    for (uint32_t base = 0; base < n; base += 32u) {  // warp-uniform
+      const uint32_t i = base + lane;
+      const bool valid = i < n;
+      const uint64_t cur = valid ? load_u64(F.in + static_cast<size_t>(p0 + i) * plan.point_step + offset) : 0ull;
+      uint64_t prev = __shfl_up_sync(0xffffffffu, cur, 1);
+      if (lane == 0) prev = last;
+      last = __shfl_sync(0xffffffffu, cur, 31);
+      const bool first = (i == 0);
+      const uint64_t x = cur ^ prev;
+      const uint32_t lz = static_cast<uint32_t>(__clzll(static_cast<long long>(x)));
+      const uint32_t tz = x ? static_cast<uint32_t>(__ffsll(static_cast<long long>(x)) - 1) : 0u;
+      const bool uses_window = valid && !first && x != 0ull;
+      // resolve the window every lane sees: lanes up to and including the first one that does not fit see the current
+      // window; that lane's (min(lz, 31), tz) is the window of the lanes behind it, and so on
+      uint32_t my_lead = win_lead, my_trail = win_trail;
+      uint32_t cursor = 0;  // lanes below it are settled
+      while (true) {        // warp-uniform trip count
+        const bool fits = win_lead != 255u && lz >= win_lead && tz >= win_trail;
+        const uint32_t misfit = __ballot_sync(0xffffffffu, uses_window && !fits && lane >= cursor);
+        if (lane >= cursor) { my_lead = win_lead; my_trail = win_trail; }
+        if (misfit == 0u) break;
+        const int j = __ffs(misfit) - 1;
+        win_lead = __shfl_sync(0xffffffffu, lz > 31u ? 31u : lz, j);
+        win_trail = __shfl_sync(0xffffffffu, tz, j);
+        cursor = static_cast<uint32_t>(j) + 1u;
+      }
+      if (valid) {
+        GorillaState st;
+        st.prev_bits = prev; st.leading = my_lead; st.trailing = my_trail; st.first = first;
+        uint8_t rec[12];
+        const uint32_t len = gorilla_encode(st, cur, rec);
+        uint8_t* dst = side + static_cast<size_t>(i) * 12;
+        for (uint32_t b = 0; b < len; ++b) dst[b] = rec[b];
+        dst[11] = static_cast<uint8_t>(len);
+      }
     }
   }
 }
 
 int launch_gorilla_prepass(const Plan& plan, const EncLaunch& L, cudaStream_t stream) {
   if (plan.n_gorilla == 0 || L.n_frames == 0) return 0;
-  gorilla_prepass_kernel<<<L.n_frames, 64, 0, stream>>>(L);
+  gorilla_prepass_kernel<<<L.n_frames, kGorillaThreads, 0, stream>>>(L);
   count_launch();
   return 1;
 }
