@@ -181,5 +181,40 @@ def build(force=False, opt="-O1", asan=False):
     return lib
 
 
+def build_racecheck():
+    """ThreadSanitizer build: tests/cusim/_build/racecheck (an executable: TSAN wants to own the process from the start).
+    Kernel sources + C ABI + racecheck_main.cpp are instrumented; the scheduler (cusim.cpp) is not (see the comment there)."""
+    os.makedirs(GEN, exist_ok=True)
+    for f in os.listdir(CSRC):
+        with open(os.path.join(CSRC, f)) as fh:
+            text = fh.read()
+        with open(os.path.join(GEN, f), "w") as fh:
+            fh.write(transform(text, f))
+    # -O0: with optimisation gcc's tsan pass drops enough of the kernels' plain loads / stores that the detector's own
+    # positive control (racecheck --control-racy) goes silent
+    common = ["-std=c++17", "-O0", "-g", "-fPIC", "-ffp-contract=off", "-fno-strict-aliasing", "-pthread", "-I", HERE, "-w"]
+    procs, objs = [], []
+    for src in SOURCES + ["cusim.cpp", "racecheck_main.cpp"]:
+        own = src in ("cusim.cpp", "racecheck_main.cpp")
+        path = os.path.join(HERE, src) if own else os.path.join(GEN, src)
+        obj = os.path.join(OUT_DIR, os.path.splitext(src)[0] + "_tsan.o")
+        flags = list(common) + (["-DCUSIM_TSAN=1"] if src == "cusim.cpp" else ["-fsanitize=thread"])
+        if src == "racecheck_main.cpp":
+            flags += ["-I", os.path.join(ROOT, "include")]
+        procs.append((src, obj, subprocess.Popen(["g++", *flags, "-x", "c++", "-c", path, "-o", obj], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    for src, obj, p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0:
+            sys.stderr.write(out[-6000:])
+            raise RuntimeError(f"cusim: g++ failed on {src}")
+        objs.append(obj)
+    exe = os.path.join(OUT_DIR, "racecheck")
+    subprocess.check_call(["g++", "-fsanitize=thread", "-pthread", "-o", exe, *objs, "-ldl"])
+    return exe
+
+
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, asan="--asan" in sys.argv))
+    if "--tsan" in sys.argv:
+        print(build_racecheck())
+    else:
+        print(build(force="--force" in sys.argv, asan="--asan" in sys.argv))

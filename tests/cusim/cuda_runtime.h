@@ -58,7 +58,7 @@ static inline ulonglong2 make_ulonglong2(unsigned long long x, unsigned long lon
 
 // ---- scheduler interface (cusim.cpp) ---------------------------------------------------------------------------------
 namespace cusim {
-struct ThreadCoords { uint3 tid, bid; dim3 bdim, gdim; };
+struct ThreadCoords { uint3 tid, bid, bdim, gdim; };  // plain data: written only by the (uninstrumented) scheduler
 extern thread_local ThreadCoords tc;
 void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()>& body);
 void* dyn_smem();
@@ -66,7 +66,9 @@ void syncthreads();
 int syncthreads_or(int pred);
 void poll_yield();  // called by the spin-wait loads so that a producer in the same CTA can run
 // Warp collective: deposits `v`, waits until every live lane of `mask` has arrived, returns the 32 deposited values.
-const uint64_t* warp_exchange(unsigned mask, uint64_t v, unsigned* arrived_mask);
+// kind 0: value collective (shuffle / ballot / vote), kind 1: __syncwarp (the only warp-level primitive that CUDA defines as
+// a memory fence among the participating lanes; the racecheck build can be told to honour exactly that: CUSIM_TSAN_STRICT=1)
+const uint64_t* warp_exchange(unsigned mask, uint64_t v, unsigned* arrived_mask, int kind = 0);
 unsigned lane_id();
 uint64_t globaltimer_ns();
 }  // namespace cusim
@@ -79,7 +81,7 @@ constexpr int warpSize = 32;
 
 static inline void __syncthreads() { cusim::syncthreads(); }
 static inline int __syncthreads_or(int p) { return cusim::syncthreads_or(p); }
-static inline void __syncwarp(unsigned mask = 0xffffffffu) { unsigned a; cusim::warp_exchange(mask, 0, &a); }
+static inline void __syncwarp(unsigned mask = 0xffffffffu) { unsigned a; cusim::warp_exchange(mask, 0, &a, 1); }
 static inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 static inline void __threadfence_block() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 

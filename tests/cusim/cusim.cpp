@@ -23,6 +23,29 @@
 #define CUSIM_ASAN 0
 #endif
 
+#if defined(CUSIM_TSAN)
+// ThreadSanitizer build (tests/cusim/build_cusim.py --tsan -> racecheck executable): every CUDA thread is a TSAN fiber and
+// the switches carry NO implicit synchronisation, so two threads of a CTA touching the same shared / global memory without
+// a __syncthreads(), a warp collective or an atomic between them are reported — compute-sanitizer's racecheck without a
+// GPU. This file itself is compiled uninstrumented (the scheduler's own bookkeeping is not kernel state); barriers and
+// warp collectives publish their happens-before edges through __tsan_release / __tsan_acquire.
+extern "C" {
+void* __tsan_get_current_fiber(void);
+void* __tsan_create_fiber(unsigned flags);
+void __tsan_destroy_fiber(void* fiber);
+void __tsan_switch_to_fiber(void* fiber, unsigned flags);
+void __tsan_acquire(void* addr);
+void __tsan_release(void* addr);
+}
+#define TSAN_SWITCH(f) __tsan_switch_to_fiber((f), 1u /* no_sync */)
+#define TSAN_RELEASE(a) __tsan_release(a)
+#define TSAN_ACQUIRE(a) __tsan_acquire(a)
+#else
+#define TSAN_SWITCH(f) ((void)0)
+#define TSAN_RELEASE(a) ((void)0)
+#define TSAN_ACQUIRE(a) ((void)0)
+#endif
+
 #if !defined(__x86_64__)
 #error "cusim's context switch is written for x86-64"
 #endif
@@ -63,6 +86,7 @@ constexpr unsigned kMaxThreads = 1024;
 enum Wait : uint8_t { RUNNABLE = 0, WAIT_BARRIER, WAIT_WARP, WAIT_POLL, DONE };
 
 struct Fiber {
+  void* tsan = nullptr;        // TSAN fiber context (racecheck build)
   void* fake_stack = nullptr;  // ASAN fake-stack handle while the fiber is switched out
   void* sp = nullptr;
   char* stack = nullptr;
@@ -92,6 +116,10 @@ struct Cta {
   size_t dyn_cap = 0;
   const std::function<void()>* body = nullptr;
   char* stacks = nullptr;
+  void* sched_tsan = nullptr;             // TSAN context of the scheduler (the OS thread itself)
+  char bar_sync = 0;                      // address the CTA barrier's happens-before edges hang on
+  char start_sync = 0, end_sync = 0;      // launch -> thread start / thread exit -> CTA retired (two addresses: a thread that
+                                          // exits must not become ordered before a thread that starts later)
   void* sched_fake_stack = nullptr;       // ASAN bookkeeping of the scheduler's (OS thread's) stack
   const void* sched_stack_bottom = nullptr;
   size_t sched_stack_size = 0;
@@ -126,6 +154,7 @@ void yield_to_scheduler() {
 #if CUSIM_ASAN
   __sanitizer_start_switch_fiber(&f.fake_stack, c->sched_stack_bottom, c->sched_stack_size);
 #endif
+  TSAN_SWITCH(c->sched_tsan);
   cusim_switch(&f.sp, c->sched_sp);
 #if CUSIM_ASAN
   __sanitizer_finish_switch_fiber(f.fake_stack, &c->sched_stack_bottom, &c->sched_stack_size);
@@ -156,7 +185,9 @@ void fiber_main() {
 #if CUSIM_ASAN
   __sanitizer_finish_switch_fiber(nullptr, &c->sched_stack_bottom, &c->sched_stack_size);
 #endif
+  TSAN_ACQUIRE(&c->start_sync);  // everything the host did before the launch is visible to the kernel
   (*c->body)();
+  TSAN_RELEASE(&c->end_sync);  // ... and the kernel's accesses are ordered before whatever follows the launch
   // thread exit: it no longer takes part in barriers or warp collectives
   Fiber& f = c->fibers[c->cur];
   f.wait = DONE;
@@ -171,6 +202,7 @@ void fiber_main() {
 #if CUSIM_ASAN
   __sanitizer_start_switch_fiber(nullptr, c->sched_stack_bottom, c->sched_stack_size);  // this fiber is finished
 #endif
+  TSAN_SWITCH(c->sched_tsan);
   cusim_switch(&f.sp, c->sched_sp);
   fprintf(stderr, "cusim: finished fiber resumed\n");
   abort();
@@ -220,10 +252,17 @@ void run_cta(Cta* c, dim3 grid, dim3 block, uint3 bid) {
     Fiber& f = c->fibers[i];
     f.tid = uint3{i % block.x, (i / block.x) % block.y, i / (block.x * block.y)};
     prepare_fiber(f);
+#if defined(CUSIM_TSAN)
+    f.tsan = __tsan_create_fiber(0);
+#endif
   }
+#if defined(CUSIM_TSAN)
+  c->sched_tsan = __tsan_get_current_fiber();
+  TSAN_RELEASE(&c->start_sync);
+#endif
   tc.bid = bid;
-  tc.bdim = block;
-  tc.gdim = grid;
+  tc.bdim = uint3{block.x, block.y, block.z};
+  tc.gdim = uint3{grid.x, grid.y, grid.z};
   // CUSIM_ORDER: fwd (default) | rev | rand — the order in which runnable threads are resumed within a pass. Results
   // must not depend on it; "rand" reshuffles every pass with a per-CTA seed.
   static const int order = [] { const char* e = getenv("CUSIM_ORDER"); return !e ? 0 : e[0] == 'r' && e[1] == 'e' ? 1 : e[0] == 'r' ? 2 : 0; }();
@@ -249,6 +288,7 @@ void run_cta(Cta* c, dim3 grid, dim3 block, uint3 bid) {
 #if CUSIM_ASAN
       __sanitizer_start_switch_fiber(&c->sched_fake_stack, f.stack, kStackBytes);
 #endif
+      TSAN_SWITCH(f.tsan);
       cusim_switch(&c->sched_sp, f.sp);
 #if CUSIM_ASAN
       __sanitizer_finish_switch_fiber(c->sched_fake_stack, nullptr, nullptr);
@@ -258,6 +298,10 @@ void run_cta(Cta* c, dim3 grid, dim3 block, uint3 bid) {
     }
     if (!progressed) deadlock_report(c);
   }
+#if defined(CUSIM_TSAN)
+  TSAN_ACQUIRE(&c->end_sync);
+  for (unsigned i = 0; i < n; ++i) __tsan_destroy_fiber(c->fibers[i].tsan);
+#endif
 }
 
 }  // namespace
@@ -280,18 +324,22 @@ void syncthreads() {
   Cta* c = g_cta;
   Fiber& f = c->fibers[c->cur];
   const uint32_t gen = c->bar_gen;
+  TSAN_RELEASE(&c->bar_sync);
   c->bar_arrived++;
   release_barrier_if_complete(c);
-  if (c->bar_gen != gen) return;  // last arriver
-  f.wait = WAIT_BARRIER;
-  f.wait_gen = gen;
-  yield_to_scheduler();
+  if (c->bar_gen == gen) {  // not the last arriver
+    f.wait = WAIT_BARRIER;
+    f.wait_gen = gen;
+    yield_to_scheduler();
+  }
+  TSAN_ACQUIRE(&c->bar_sync);
 }
 
 int syncthreads_or(int pred) {
   Cta* c = g_cta;
   Fiber& f = c->fibers[c->cur];
   const uint32_t gen = c->bar_gen;
+  TSAN_RELEASE(&c->bar_sync);
   c->bar_or_acc |= (pred != 0);
   c->bar_arrived++;
   release_barrier_if_complete(c);
@@ -300,6 +348,7 @@ int syncthreads_or(int pred) {
     f.wait_gen = gen;
     yield_to_scheduler();
   }
+  TSAN_ACQUIRE(&c->bar_sync);
   return c->bar_or_res[gen & 1u];
 }
 
@@ -310,7 +359,13 @@ void poll_yield() {
   yield_to_scheduler();
 }
 
-const uint64_t* warp_exchange(unsigned mask, uint64_t v, unsigned* arrived_mask) {
+const uint64_t* warp_exchange(unsigned mask, uint64_t v, unsigned* arrived_mask, int kind) {
+#if defined(CUSIM_TSAN)
+  static const bool strict = getenv("CUSIM_TSAN_STRICT") != nullptr;
+  const bool fence = kind == 1 || !strict;
+#else
+  (void)kind;
+#endif
   Cta* c = g_cta;
   const unsigned linear = c->cur, lane = linear & 31u;
   Warp& w = c->warps[linear >> 5];
@@ -320,6 +375,9 @@ const uint64_t* warp_exchange(unsigned mask, uint64_t v, unsigned* arrived_mask)
   }
   const uint32_t gen = w.gen;
   const unsigned b = gen & 1u;
+#if defined(CUSIM_TSAN)
+  if (fence) TSAN_RELEASE(&w.gen);  // the collective orders the memory accesses of the lanes that take part in it
+#endif
   w.slot[b][lane] = v;
   w.arrived[b] |= 1u << lane;
   release_warp_if_complete(w, mask);
@@ -330,6 +388,9 @@ const uint64_t* warp_exchange(unsigned mask, uint64_t v, unsigned* arrived_mask)
     f.wait_warp = linear >> 5;
     yield_to_scheduler();
   }
+#if defined(CUSIM_TSAN)
+  if (fence) TSAN_ACQUIRE(&w.gen);
+#endif
   *arrived_mask = w.arrived_final[b];
   return w.slot[b];
 }

@@ -72,3 +72,37 @@ def test_no_out_of_bounds_access_under_asan(lib_built):
            "tests/test_gpu_parity.py", "tests/test_gpu_ros.py"]
     r = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=3000)
     assert r.returncode == 0 and "AddressSanitizer" not in (r.stdout + r.stderr), r.stdout[-3000:] + r.stderr[-3000:]
+
+
+def test_racecheck_under_thread_sanitizer(lib_built):
+    # racecheck without a GPU: every CUDA thread is a ThreadSanitizer fiber (switches carry no synchronisation), barriers and
+    # __syncwarp publish their happens-before edges, so an unsynchronised pair of accesses to shared or global memory is a
+    # report. The detector is checked against its own controls first, then every kernel family runs in strict mode (a
+    # shuffle is NOT a memory fence, as the CUDA model defines it).
+    import platform
+    if platform.machine() != "x86_64":
+        pytest.skip("cusim's context switch is x86-64 only")
+    import build_cusim
+    try:
+        exe = build_cusim.build_racecheck()
+    except (RuntimeError, subprocess.CalledProcessError) as e:
+        pytest.skip(f"ThreadSanitizer toolchain unavailable: {e}")
+
+    def warnings(args, strict=False):
+        env = dict(os.environ, TSAN_OPTIONS="halt_on_error=0 report_signal_unsafe=0", CUSIM_WORKERS="4")
+        env.pop("LD_PRELOAD", None)
+        if strict:
+            env["CUSIM_TSAN_STRICT"] = "1"
+        r = subprocess.run([exe, *args], env=env, capture_output=True, text=True, timeout=900)
+        return (r.stdout + r.stderr).count("WARNING: ThreadSanitizer"), r
+
+    probe, r = warnings(["--control-fixed"])
+    if "FATAL: ThreadSanitizer" in r.stderr:
+        pytest.skip("ThreadSanitizer cannot run in this environment: " + r.stderr[-200:])
+    assert probe == 0
+    assert warnings(["--control-racy"])[0] > 0                       # missing __syncthreads is seen
+    assert warnings(["--control-shfl"])[0] == 0                      # shuffle as fence (lenient model)
+    assert warnings(["--control-shfl"], strict=True)[0] > 0          # ... and not a fence in the strict model
+    n, r = warnings([], strict=True)
+    assert r.returncode == 0 and "racecheck_main: done" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+    assert n == 0, r.stderr[-4000:]
