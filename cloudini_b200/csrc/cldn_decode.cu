@@ -795,6 +795,351 @@ __global__ void decode_sequential_kernel(const DecLaunch L) {
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// Mixed plans: varint-coded fields AND raw (Copy) / XOR fields in the regular stream (sensor layouts with uint8 fields,
+// LOSSLESS float clouds). Raw bytes carry no terminator structure, so the terminator ranking of decode_varint_stream does
+// not find value boundaries; the one-thread-per-chunk parser above does, at the speed of a single GPU thread.
+// This kernel finds the POINT boundaries in parallel instead (one CTA per chunk, tiles of kMixTile candidate positions):
+//   1. bytes of the tile (+ kMixLook look-ahead) are staged in shared memory, one terminator bit per byte;
+//   2. every byte position b computes next(b): where the following point would start IF a point started at b (skip
+//      n varints = n terminator bits, skip the fixed bytes, segment by segment) — independent of everything before b;
+//   3. the true boundaries are the orbit of the tile's entry position under next(): pointer doubling builds the 2^k-hop
+//      table and the list of the first 2^(k+1) boundaries in round k (log2 rounds, all threads);
+//   4. one thread per point then decodes its tokens with the careful readers (errors exactly where the reference's
+//      decoders throw), and per-field CTA scans (segmented sums with NaN reset, XOR scans) turn deltas into values.
+// Gorilla fields stay with the per-chunk parser: a record's length depends on the running window, so next(b) is not a
+// function of b alone.
+constexpr uint32_t kMixTile = 8192;   // candidate point starts per tile (tile-local positions [0, kMixTile))
+constexpr uint32_t kMixLook = 512;    // a point that starts inside the tile may extend this far behind it
+constexpr uint32_t kMixBatch = kThreads;
+constexpr uint32_t kMixNone = 0xFFFFu;
+constexpr uint32_t kMixBitWords = (kMixTile + kMixLook) / 32 + 4;
+
+enum MixKind : uint8_t { MIX_VAR = 0, MIX_COPY = 1, MIX_XOR = 2 };
+struct MixToken {
+  uint8_t kind;    // MixKind
+  uint8_t size;    // raw bytes (COPY / XOR), stored bytes (INT)
+  uint16_t index;  // index among the VAR tokens or among the fixed tokens of a point
+  DecSlot slot;    // VAR: how to turn the accumulated value into the field
+  uint32_t offset; // COPY / XOR: byte offset inside the point
+};
+struct MixShared {
+  MixToken tok[kMaxOps + 4];
+  uint8_t seg_nvar[kMaxOps + 4], seg_nfix[kMaxOps + 4];  // next(): n varints, then n fixed bytes, segment by segment
+  uint32_t n_tok, n_seg, n_var, n_fix;
+  uint32_t n_found;   // boundaries found in this tile
+  uint32_t fail;
+  long long carry[kMaxOps + 4];            // per VAR token: last absolute value
+  unsigned long long xcarry[kMaxOps + 4];  // per fixed token (XOR): last raw bits
+  unsigned long long xscan[kThreads / 32];
+};
+
+// 64 terminator bits starting at bit position p
+__device__ __forceinline__ uint64_t mix_window(const uint32_t* tbits, uint32_t p) {
+  const uint32_t w = p >> 5, sh = p & 31u;
+  const uint32_t a = tbits[w], b = tbits[w + 1], c = tbits[w + 2];
+  return static_cast<uint64_t>(__funnelshift_r(a, b, sh)) | (static_cast<uint64_t>(__funnelshift_r(b, c, sh)) << 32);
+}
+// Start of the point that follows a point starting at local position p (kMixNone if it cannot be told from this tile).
+__device__ __forceinline__ uint32_t mix_next(const MixShared& ms, const uint32_t* tbits, uint32_t p, uint32_t limit) {
+  for (uint32_t s = 0; s < ms.n_seg; ++s) {
+    uint32_t k = ms.seg_nvar[s];
+    while (k) {
+      if (p >= limit) return kMixNone;
+      uint64_t w = mix_window(tbits, p);
+      const uint32_t c = static_cast<uint32_t>(__popcll(w));
+      if (c >= k) {
+        for (uint32_t i = 1; i < k; ++i) w &= w - 1ull;
+        p += static_cast<uint32_t>(__ffsll(static_cast<long long>(w)));
+        k = 0;
+      } else {
+        k -= c;
+        p += 64u;
+      }
+    }
+    p += ms.seg_nfix[s];
+    if (p > limit) return kMixNone;
+  }
+  return p;
+}
+__device__ __forceinline__ unsigned long long mix_block_xor_exclusive(unsigned long long v, unsigned long long* scratch,
+                                                                     unsigned long long* total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned long long inc = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const unsigned long long t = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= d) inc ^= t;
+  }
+  if (lane == 31) scratch[warp] = inc;
+  __syncthreads();
+  unsigned long long before = 0, all = 0;
+#pragma unroll
+  for (int w = 0; w < kThreads / 32; ++w) {
+    const unsigned long long x = scratch[w];
+    if (w < warp) before ^= x;
+    all ^= x;
+  }
+  *total = all;
+  __syncthreads();  // scratch is reused by the next scan
+  return before ^ inc ^ v;
+}
+
+__global__ void __launch_bounds__(kThreads) decode_mixed_kernel(const DecLaunch L) {
+  extern __shared__ __align__(16) uint8_t dyn_smem[];
+  __shared__ DecShared sh;
+  __shared__ MixShared ms;
+  __shared__ uint32_t s_frame;
+  // dynamic smem: bytes | terminator bits | 2 jump tables | boundary list | per-batch values
+  uint8_t* bytes = dyn_smem;
+  uint32_t* tbits = reinterpret_cast<uint32_t*>(bytes + kMixTile + kMixLook + 32);
+  uint16_t* jump0 = reinterpret_cast<uint16_t*>(tbits + kMixBitWords);
+  uint16_t* jump1 = jump0 + kMixTile;
+  uint16_t* starts = jump1 + kMixTile;  // [kMixTile + 2]
+  long long* vals = reinterpret_cast<long long*>(reinterpret_cast<uint8_t*>(starts) + ((kMixTile + 2) * 2 + 15) / 16 * 16);
+
+  const uint32_t gc = blockIdx.x;
+  const Plan& plan = *L.plan;
+  if (threadIdx.x == 0) {
+    uint32_t lo = 0, hi = L.n_frames - 1;
+    while (lo < hi) {
+      const uint32_t mid = (lo + hi + 1) >> 1;
+      if (L.frames[mid].chunk_begin <= gc) lo = mid; else hi = mid - 1;
+    }
+    s_frame = lo;
+    // token program of one point, in stream order
+    uint32_t nt = 0, nv = 0, nf = 0, nseg = 0;
+    uint32_t run_var = 0, run_fix = 0;
+    for (uint32_t k = 0; k < plan.n_ops; ++k) {
+      const RegOp& op = plan.ops[k];
+      const bool fixed = op.kind == OP_COPY || op.kind == OP_XOR32 || op.kind == OP_XOR64;
+      for (int l = 0; l < (fixed ? 1 : op.lanes); ++l) {
+        MixToken& t = ms.tok[nt++];
+        if (fixed) {
+          t.kind = op.kind == OP_COPY ? MIX_COPY : MIX_XOR;
+          t.size = op.size;
+          t.index = static_cast<uint16_t>(nf++);
+          t.offset = op.offset[0];
+          run_fix += op.size;
+        } else {
+          if (run_fix) { ms.seg_nvar[nseg] = static_cast<uint8_t>(run_var); ms.seg_nfix[nseg] = static_cast<uint8_t>(run_fix); ++nseg; run_var = run_fix = 0; }
+          t.kind = MIX_VAR;
+          t.size = op.size;
+          t.index = static_cast<uint16_t>(nv++);
+          t.offset = op.offset[l];
+          t.slot.offset = op.offset[l];
+          t.slot.size = op.size;
+          t.slot.mul_f = op.dec_mul_f[l];
+          t.slot.mul_d = op.dec_mul_d;
+          t.slot.kind = op.kind == OP_FLOATN ? SLOT_FLOATN : op.kind == OP_F32_LOSSY ? SLOT_F32 : op.kind == OP_F64_LOSSY ? SLOT_F64 : SLOT_INT;
+          ++run_var;
+        }
+      }
+    }
+    if (run_var || run_fix) { ms.seg_nvar[nseg] = static_cast<uint8_t>(run_var); ms.seg_nfix[nseg] = static_cast<uint8_t>(run_fix); ++nseg; }
+    ms.n_tok = nt; ms.n_var = nv; ms.n_fix = nf; ms.n_seg = nseg;
+    ms.fail = 0;
+    for (uint32_t i = 0; i < kMaxOps + 4; ++i) { ms.carry[i] = 0; ms.xcarry[i] = 0; }
+  }
+  __syncthreads();
+  const DecFrame F = L.frames[s_frame];
+  const uint32_t c = gc - F.chunk_begin;
+  const uint32_t n_points = min(kChunkPoints, F.n_points - c * kChunkPoints);
+  const uint8_t* body = F.payload + L.chunk_offsets[gc];
+  const uint32_t size = L.chunk_sizes[gc];
+  uint8_t* out = F.out + static_cast<size_t>(c) * kChunkPoints * plan.point_step;
+  const uint32_t n_var = ms.n_var, n_fix = ms.n_fix, n_tok = ms.n_tok;
+  uint8_t* nanflag = reinterpret_cast<uint8_t*>(vals + static_cast<size_t>(kMixBatch) * n_var);
+  unsigned long long* raws = reinterpret_cast<unsigned long long*>(nanflag + ((static_cast<size_t>(kMixBatch) * n_var + 15) / 16) * 16);
+  if (L.stream_end && threadIdx.x == 0) L.stream_end[gc] = 0xFFFFFFFFu;  // stays so if the stream turns out to be malformed
+
+  uint32_t done = 0;   // points decoded so far
+  uint32_t t0 = 0;     // chunk-body offset of the next point
+  while (done < n_points) {
+    if (t0 >= size) {  // points are still missing but the bytes are used up: "Truncated encoded data" (v4_codec.cpp:102-104)
+      if (threadIdx.x == 0) report_error(L.err, DEV_ERR_TRUNCATED);
+      return;
+    }
+    // ---- 1. stage [a0, a0 + kMixTile + kMixLook) with a0 = t0 rounded down to a 16-byte aligned ADDRESS ----
+    const uint32_t mis = static_cast<uint32_t>((reinterpret_cast<uintptr_t>(body) + t0) & 15u);
+    const int64_t a0 = static_cast<int64_t>(t0) - mis;  // may be negative at the chunk start: those bytes are never read
+    const int64_t avail_local = static_cast<int64_t>(size) - a0;
+    const uint32_t limit = static_cast<uint32_t>(avail_local < static_cast<int64_t>(kMixTile + kMixLook) ? avail_local : kMixTile + kMixLook);
+    for (uint32_t v = threadIdx.x; v < (kMixTile + kMixLook) / 16; v += blockDim.x) {
+      const int64_t b = a0 + static_cast<int64_t>(v) * 16;
+      uint4 q = make_uint4(0x80808080u, 0x80808080u, 0x80808080u, 0x80808080u);
+      if (b >= 0 && b + 16 <= static_cast<int64_t>(size)) {
+        q = *reinterpret_cast<const uint4*>(body + b);
+      } else if (b + 16 > 0 && b < static_cast<int64_t>(size)) {
+        uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          const int64_t bb = b + k;
+          if (bb >= 0 && bb < static_cast<int64_t>(size)) w[k >> 2] = (w[k >> 2] & ~(0xFFu << (8 * (k & 3)))) | (static_cast<uint32_t>(body[bb]) << (8 * (k & 3)));
+        }
+        q = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+      *reinterpret_cast<uint4*>(bytes + v * 16) = q;
+    }
+    __syncthreads();
+    for (uint32_t w = threadIdx.x; w < kMixBitWords; w += blockDim.x) {
+      uint32_t m = 0;
+      if (w * 32u < limit) {
+        const uint4 lo = *reinterpret_cast<const uint4*>(bytes + w * 32u);
+        const uint4 hi = *reinterpret_cast<const uint4*>(bytes + w * 32u + 16u);
+        const uint32_t x[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint32_t t = ~x[k] & 0x80808080u;  // MSB clear = the byte ends a varint
+          m |= (((t >> 7) & 1u) | ((t >> 14) & 2u) | ((t >> 21) & 4u) | ((t >> 28) & 8u)) << (4 * k);
+        }
+        if (w * 32u + 32u > limit) m &= (1u << (limit - w * 32u)) - 1u;  // nothing behind the last byte
+        if (w * 32u < mis) m &= ~((1u << (mis - w * 32u > 31u ? 31u : mis - w * 32u)) - 1u);  // bytes in front of the entry are not ours
+      }
+      tbits[w] = m;
+    }
+    __syncthreads();
+    // ---- 2. next(b) for every candidate start ----
+    for (uint32_t b = threadIdx.x; b < kMixTile; b += blockDim.x) {
+      uint32_t nx = kMixNone;
+      if (b >= mis && b < limit) nx = mix_next(ms, tbits, b, limit);
+      jump0[b] = static_cast<uint16_t>(nx);
+      starts[b] = static_cast<uint16_t>(kMixNone);
+    }
+    if (threadIdx.x == 0) {  // (thread 0 also owns b = 0 in the loop above: program order)
+      starts[0] = static_cast<uint16_t>(mis);  // boundary 0 = the tile's entry
+      starts[kMixTile] = starts[kMixTile + 1] = static_cast<uint16_t>(kMixNone);
+      ms.n_found = 1;
+    }
+    __syncthreads();
+    // ---- 3. pointer doubling: round k appends boundaries 2^k .. 2^(k+1)-1 and squares the jump table ----
+    uint16_t* jt = jump0;
+    uint16_t* jn = jump1;
+    uint32_t exit_pos = kMixNone;
+    for (uint32_t step = 1; step < kMixTile; step <<= 1) {  // a tile holds at most kMixTile boundaries (one per byte)
+      int grew = 0;
+      for (uint32_t i = threadIdx.x; i < step; i += blockDim.x) {
+        const uint32_t b = starts[i];
+        if (b != kMixNone) {
+          const uint32_t t = jt[b];
+          if (t < kMixTile) { starts[i + step] = static_cast<uint16_t>(t); grew = 1; }
+        }
+      }
+      if (!__syncthreads_or(grew)) { exit_pos = jt[mis]; break; }  // no boundary beyond 2^k: jt[entry] already left the tile
+      for (uint32_t b = threadIdx.x; b < kMixTile; b += blockDim.x) {
+        const uint32_t t = jt[b];
+        jn[b] = (t < kMixTile) ? jt[t] : static_cast<uint16_t>(t);
+      }
+      __syncthreads();
+      uint16_t* sw = jt; jt = jn; jn = sw;
+      exit_pos = jt[mis];
+    }
+    {  // number of boundaries = first unset entry of the list
+      uint32_t mine = 0;
+      for (uint32_t i = threadIdx.x; i < kMixTile; i += blockDim.x) if (starts[i] != kMixNone) mine = i + 1;
+      atomicMax(&ms.n_found, mine);
+    }
+    __syncthreads();
+    const uint32_t found = ms.n_found;
+    const uint32_t take = found < n_points - done ? found : n_points - done;
+    if (threadIdx.x == 0) starts[found] = static_cast<uint16_t>(exit_pos);  // end of the last point of the tile
+    __syncthreads();
+    // ---- 4. + 5. batches of one point per thread ----
+    for (uint32_t b0 = 0; b0 < take; b0 += kMixBatch) {
+      const uint32_t i = b0 + threadIdx.x;
+      const bool active = i < take;
+      bool bad = false;
+      if (active) {
+        uint32_t p = starts[i];
+        for (uint32_t t = 0; t < n_tok; ++t) {
+          const MixToken& tk = ms.tok[t];
+          if (tk.kind == MIX_VAR) {
+            long long diff = 0;
+            uint8_t nan = 0;
+            if (p >= limit) { report_error(L.err, DEV_ERR_TRUNCATED); bad = true; break; }
+            if (bytes[p] == 0 && tk.slot.kind != SLOT_INT) { nan = 1; ++p; }  // NaN marker (field_decoder.cpp:57-61)
+            else {
+              const uint32_t n = read_varint(bytes + p, limit - p, &diff, L.err);
+              if (!n) { bad = true; break; }
+              p += n;
+            }
+            vals[static_cast<size_t>(threadIdx.x) * n_var + tk.index] = diff;
+            nanflag[static_cast<size_t>(threadIdx.x) * n_var + tk.index] = nan;
+          } else {
+            if (p + tk.size > limit) { report_error(L.err, DEV_ERR_TRUNCATED); bad = true; break; }
+            raws[static_cast<size_t>(threadIdx.x) * n_fix + tk.index] = load_raw_bits(bytes + p, tk.size);
+            p += tk.size;
+          }
+        }
+      }
+      if (__syncthreads_or(bad ? 1 : 0)) return;  // the error word is set; the host reports it
+      uint8_t* point = out + static_cast<size_t>(done + i) * plan.point_step;
+      for (uint32_t t = 0; t < n_tok; ++t) {
+        const MixToken& tk = ms.tok[t];
+        if (tk.kind == MIX_VAR) {
+          const long long d = active ? vals[static_cast<size_t>(threadIdx.x) * n_var + tk.index] : 0;
+          const bool nan = active && nanflag[static_cast<size_t>(threadIdx.x) * n_var + tk.index] != 0;
+          Seg<long long, 1> mine;
+          mine.sum[0] = nan ? 0 : d;
+          mine.rst = nan ? 1u : 0u;
+          Seg<long long, 1> total;
+          const Seg<long long, 1> ex = block_seg_exclusive<long long, 1>(mine, sh.seg_sum, sh.seg_rst, &total);
+          const long long before = ex.rst ? ex.sum[0] : wadd(ms.carry[tk.index], ex.sum[0]);
+          if (active) store_slot_value<long long>(point, tk.slot, nan ? 0 : wadd(before, d), nan);
+          __syncthreads();
+          if (threadIdx.x == 0) ms.carry[tk.index] = total.rst ? total.sum[0] : wadd(ms.carry[tk.index], total.sum[0]);
+        } else if (tk.kind == MIX_XOR) {  // field_decoder.hpp:356-370: value = residual ^ previous value
+          const unsigned long long r = active ? raws[static_cast<size_t>(threadIdx.x) * n_fix + tk.index] : 0ull;
+          unsigned long long total;
+          const unsigned long long ex = mix_block_xor_exclusive(r, ms.xscan, &total);
+          const unsigned long long v = ms.xcarry[tk.index] ^ ex ^ r;
+          if (active && tk.offset != CLDN_SKIP_STORE_OFFSET) store_low_bytes(point + tk.offset, v, tk.size);
+          __syncthreads();
+          if (threadIdx.x == 0) ms.xcarry[tk.index] ^= total;
+        } else if (active && tk.offset != CLDN_SKIP_STORE_OFFSET) {
+          store_low_bytes(point + tk.offset, raws[static_cast<size_t>(threadIdx.x) * n_fix + tk.index], tk.size);
+        }
+      }
+      __syncthreads();
+    }
+    done += take;
+    const uint32_t end_local = starts[take];  // start of the first point that was NOT taken (or the tile's exit)
+    __syncthreads();                          // everybody has read the list before the next tile rewrites it
+    if (done < n_points) {
+      if (end_local == kMixNone || end_local <= mis) {  // the path left the tile through a point this tile cannot delimit
+        if (threadIdx.x == 0) report_error(L.err, DEV_ERR_TRUNCATED);
+        return;
+      }
+      t0 = static_cast<uint32_t>(a0 + end_local);
+    } else {
+      if (end_local == kMixNone) { if (threadIdx.x == 0) report_error(L.err, DEV_ERR_TRUNCATED); return; }
+      if (L.stream_end && threadIdx.x == 0) L.stream_end[gc] = static_cast<uint32_t>(a0 + end_local);  // V5: the sections start here
+    }
+  }
+  if (n_points == 0 && L.stream_end && threadIdx.x == 0) L.stream_end[gc] = 0;
+}
+
+static size_t mixed_smem_bytes(const Plan& plan) {
+  size_t n_var = 0, n_fix = 0;
+  for (uint32_t k = 0; k < plan.n_ops; ++k) {
+    const RegOp& op = plan.ops[k];
+    if (op.kind == OP_COPY || op.kind == OP_XOR32 || op.kind == OP_XOR64) ++n_fix; else n_var += op.lanes;
+  }
+  size_t bytes = kMixTile + kMixLook + 32 + kMixBitWords * 4 + 2 * kMixTile * 2;
+  bytes += ((kMixTile + 2) * 2 + 15) / 16 * 16;
+  bytes += kMixBatch * n_var * 8;
+  bytes += (kMixBatch * n_var + 15) / 16 * 16;
+  bytes += kMixBatch * n_fix * 8 + 64;
+  return bytes;
+}
+// The parallel boundary search applies when a point's length is a function of its own bytes (no Gorilla window) and a
+// point fits the look-ahead of a tile.
+static bool mixed_plan_ok(const Plan& plan) {
+  if (plan.n_gorilla != 0 || plan.max_point_bytes > kMixLook || plan.n_ops == 0) return false;
+  const char* e = getenv("CLDN_B200_MIXED_DECODE");  // "seq": development override, the per-chunk parser
+  return !(e && e[0] == 's');
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 static size_t dec_smem_bytes(bool k32) {
   return kLookBehind + kDecTileBytes + 16 + static_cast<size_t>(kDecTileBytes) * (k32 ? 4 : 8) + kDecTileBytes / 8 +
          sizeof(RunBatch) + 16;
@@ -848,9 +1193,16 @@ int launch_decode(const Plan& plan, const DecLaunch& L, cudaStream_t stream) {
       decode_fixed_kernel<<<grid, kThreads, 0, stream>>>(L);
       ++launches;
     } else {
-      // raw / XOR / Gorilla fields mixed into the stream: one thread per chunk parses it like the reference does;
+      // raw / XOR fields mixed into the stream: point boundaries by parallel pointer jumping (decode_mixed_kernel);
+      // Gorilla fields: one thread per chunk parses the stream like the reference does.
       // V5 sections (if any) are then decoded by the per-chunk section reader from where the stream ended
-      decode_sequential_kernel<<<(L.n_chunks_total + 31) / 32, 32, 0, stream>>>(L);
+      if (mixed_plan_ok(plan)) {
+        const size_t msmem = mixed_smem_bytes(plan);
+        if (cudaFuncSetAttribute(decode_mixed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(msmem)) != cudaSuccess) return -1;
+        decode_mixed_kernel<<<L.n_chunks_total, kThreads, msmem, stream>>>(L);
+      } else {
+        decode_sequential_kernel<<<(L.n_chunks_total + 31) / 32, 32, 0, stream>>>(L);
+      }
       ++launches;
       if (plan.n_sections > 0) {
         DecLaunch S = L;

@@ -122,6 +122,32 @@ def cloud_c4_mixed_frame(frame: int, seed: int = 4, rings: int = 64, az: int = 2
     return info, np.ascontiguousarray(buf).reshape(-1)
 
 
+def cloud_livox(n: int = 40_000, seed: int = 8, version: int = 5):
+    """Livox-style layout (x y z intensity f32, tag u8, line u8, offset_time u32; point_step 22): the uint8 fields are raw
+    Copy bytes in the middle of the varint stream (field_encoder.hpp:51-67), so value boundaries cannot be ranked by
+    terminator bits — the layout that exercises the pointer-jumping decoder. Random tag / line bytes on purpose (every
+    bit pattern, including 0x00 and 0x80, appears as a raw byte)."""
+    rng = np.random.default_rng(seed)
+    step = 22
+    buf = rng.integers(0, 256, (n, step), dtype=np.uint8)
+    xyz = np.cumsum(rng.normal(0, 0.02, (n, 3)), axis=0).astype(np.float32)
+    if n:
+        k = max(1, n // 100)
+        xyz[rng.integers(0, n, k), rng.integers(0, 3, k)] = np.nan
+        xyz[rng.integers(0, n, max(1, n // 2000)), 0] = np.float32(-3.0e6)  # 5-byte varints
+    buf[:, :12] = xyz.view(np.uint8).reshape(n, 12)
+    buf[:, 12:16] = rng.integers(0, 255, n).astype(np.float32).view(np.uint8).reshape(n, 4)
+    buf[:, 18:22] = (np.arange(n) * 100).astype(np.uint32).view(np.uint8).reshape(n, 4)
+    F = FieldType
+    info = EncodingInfo(
+        fields=[PointField("x", 0, F.FLOAT32, 0.001), PointField("y", 4, F.FLOAT32, 0.001), PointField("z", 8, F.FLOAT32, 0.001),
+                PointField("intensity", 12, F.FLOAT32, 0.01), PointField("tag", 16, F.UINT8, None), PointField("line", 17, F.UINT8, None),
+                PointField("offset_time", 18, F.UINT32, None)],
+        width=n, height=1, point_step=step, encoding_opt=EncodingOptions.LOSSY, compression_opt=CompressionOption.NONE,
+        use_threads=False, version=version)
+    return info, np.ascontiguousarray(buf).reshape(-1)
+
+
 def cloud_lossless(n: int = 40_000, seed: int = 6, lossless: bool = True, version: int = 5, stamp_res=None,
                    hostile: bool = True):
     """The reference's DDS / PCD layout (x, y, z, intensity f32, ring u16, timestamp f64; point_step 26) used to reach

@@ -157,6 +157,22 @@ int main(int argc, char** argv) {
     }
     bad += roundtrip("dds-layout/gorilla", info, cloud, nullptr);
   }
+  // ---- Livox-like: XYZI + two uint8 (raw Copy bytes in the stream) + u32, step 22: pointer-jumping decoder ----
+  {
+    cldn_info_t info; cldn_b200_info_init(&info);
+    info.width = n; info.height = 1; info.point_step = 22; info.compression_opt = CLDN_COMP_NONE;
+    add_field(info, "x", 0, CLDN_FLOAT32, 0.001f); add_field(info, "y", 4, CLDN_FLOAT32, 0.001f);
+    add_field(info, "z", 8, CLDN_FLOAT32, 0.001f); add_field(info, "intensity", 12, CLDN_FLOAT32, 0.01f);
+    add_field(info, "tag", 16, CLDN_UINT8, 0); add_field(info, "line", 17, CLDN_UINT8, 0); add_field(info, "offset_time", 18, CLDN_UINT32, 0);
+    std::vector<uint8_t> cloud(n * 22);
+    for (size_t i = 0; i < n; ++i) {
+      float p[4] = {5.f * std::sin(0.002f * i), 5.f * std::cos(0.002f * i), 0.02f * float(i % 32), float(rnd() % 100)};
+      uint8_t tag = uint8_t(rnd()), line = uint8_t(rnd());
+      uint32_t ot = uint32_t(i * 100);
+      memcpy(&cloud[i * 22], p, 16); cloud[i * 22 + 16] = tag; cloud[i * 22 + 17] = line; memcpy(&cloud[i * 22 + 18], &ot, 4);
+    }
+    bad += roundtrip("livox-layout/raw bytes in the stream", info, cloud, nullptr);
+  }
   printf("racecheck_main: %s\n", bad ? "FAILED" : "done");
   return bad ? 1 : 0;
 }

@@ -427,7 +427,7 @@ def test_corrupted_blobs_decode_like_the_reference(ref):
     trials = int(os.environ.get("CLDN_B200_CORRUPT_TRIALS", "40"))
     dec = cb.PointcloudDecoder()
     cases = [synth.cloud_c2(5000, seed=1), synth.cloud_c1(3000, seed=2), synth.cloud_c3(6000, seed=3), synth.cloud_c2(40_000, seed=4),
-             synth.cloud_lossless(3000, seed=5)]
+             synth.cloud_lossless(3000, seed=5), synth.cloud_livox(6000, seed=6), synth.cloud_livox(3000, seed=7, version=4)]
     for info, cloud in cases:
         blob = ref.encode(info, cloud)
         dinfo, hdr = cb.DecodeHeader(blob)
@@ -474,3 +474,16 @@ def test_c4_velodyne_mixed_layout(oracle):
     sizes = enc.encode_batch_host(frames, outs, write_header=True)
     for c, o, s in zip(frames, outs, sizes):
         assert bytes(o[:s]) == oracle.encode(info, c)
+
+
+@pytest.mark.parametrize("mode", ["par", "seq"])
+@pytest.mark.parametrize("version", [5, 4])
+def test_raw_fields_in_the_stream(oracle, monkeypatch, mode, version):
+    # uint8 fields are raw Copy bytes between the varints: point boundaries by pointer jumping (decode_mixed_kernel, "par")
+    # or by the per-chunk parser ("seq"); both must reproduce the reference, for every size around the tile / chunk edges
+    monkeypatch.setenv("CLDN_B200_MIXED_DECODE", mode)
+    for n in (1, 2, 255, 1100, 1366, 1367, 9000, 32768, 32769, 70_001):
+        _roundtrip_check(*synth.cloud_livox(n, seed=n, version=version), oracle, fill=0x3C)
+    # LOSSLESS clouds: FLOAT32 -> XOR residuals (field_encoder.hpp:123-139): XOR scan across points, tiles and batches
+    info, cloud = synth.cloud_lossless(20_000, seed=9, lossless=True, version=3)   # version 3: FLOAT64 is XOR too (no Gorilla)
+    _roundtrip_check(info, cloud, oracle, fill=0)
