@@ -1140,6 +1140,366 @@ static bool mixed_plan_ok(const Plan& plan) {
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// Plans with ONE Gorilla field (FLOAT64 without a resolution — the timestamps of most sensor drivers) next to varint /
+// raw / XOR fields. A Gorilla record is byte aligned but its length is not a function of its own bytes: a "reuse window"
+// record is 2 + meaningful(window) bits long. Only the BYTE length of such a record matters for the boundaries, i.e. one
+// of 10 classes (0 = no window yet, 1..9 = bytes of a reuse record), and a "new window" record announces the class that
+// follows it. So next() becomes a function of (position, class): every thread fills next(b, c) for its positions and all
+// classes (the work in front of the record is shared), ONE thread then follows the tile's entry through the table (one
+// shared-memory load per point instead of a full parse) and all threads decode: varints / raw fields as in
+// decode_mixed_kernel, the Gorilla values by a "last new-window record" scan (which window does a reuse record see) and
+// an XOR scan (value = xor of all residuals so far).
+constexpr uint32_t kGorTile = 2048;
+constexpr uint32_t kGorClasses = 10;
+constexpr uint32_t kGorBitWords = (kGorTile + kMixLook) / 32 + 4;
+constexpr uint32_t kGorNone = 0xFFFFFFFFu;
+constexpr uint8_t MIX_GORILLA = 3;
+
+// Header of the Gorilla record at p (field_decoder.hpp:257-300), read with the same truncation tests as gorilla_decode.
+// kind: 0 same value (1 byte), 1 reuse window, 2 new window; returns false when the header itself is truncated.
+struct GorHeader { uint32_t kind, lead, meaningful; };
+__device__ __forceinline__ bool gor_header(const uint8_t* p, uint32_t avail, GorHeader* h) {
+  BitWindow w(p, avail);
+  uint64_t flag, control, lead, m1;
+  h->kind = 0; h->lead = 0; h->meaningful = 0;
+  if (!w.read(1, &flag)) return false;
+  if (flag == 0) return true;
+  if (!w.read(1, &control)) return false;
+  if (control == 0) { h->kind = 1; return true; }
+  if (!w.read(5, &lead) || !w.read(6, &m1)) return false;
+  h->kind = 2; h->lead = static_cast<uint32_t>(lead); h->meaningful = static_cast<uint32_t>(m1) + 1u;
+  return true;
+}
+// position after one varint that starts at p (kMixNone if its terminator is not within 64 bytes / the data)
+__device__ __forceinline__ uint32_t gor_skip_varint(const uint32_t* tbits, uint32_t p, uint32_t limit) {
+  if (p >= limit) return kMixNone;
+  const uint64_t w = mix_window(tbits, p);
+  if (w == 0ull) return kMixNone;
+  return p + static_cast<uint32_t>(__ffsll(static_cast<long long>(w)));
+}
+// Walks tokens [t_begin, t_end) that hold no Gorilla record.
+__device__ __forceinline__ uint32_t gor_skip_tokens(const MixShared& ms, const uint32_t* tbits, uint32_t p, uint32_t limit,
+                                                    uint32_t t_begin, uint32_t t_end) {
+  for (uint32_t t = t_begin; t < t_end && p != kMixNone; ++t) {
+    if (ms.tok[t].kind == MIX_VAR) p = gor_skip_varint(tbits, p, limit);
+    else { p += ms.tok[t].size; if (p > limit) p = kMixNone; }
+  }
+  return p;
+}
+// exclusive "latest valid entry" scan: v = (1 << 16) | payload for threads that define a window, 0 otherwise
+__device__ __forceinline__ uint32_t gor_block_last_exclusive(uint32_t v, uint32_t* scratch, uint32_t* total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t inc = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= d && inc == 0u) inc = t;
+  }
+  if (lane == 31) scratch[warp] = inc;
+  uint32_t prev = __shfl_up_sync(0xffffffffu, inc, 1);
+  if (lane == 0) prev = 0;
+  __syncthreads();
+  uint32_t before = 0, all = 0;
+#pragma unroll
+  for (int w = 0; w < kThreads / 32; ++w) {
+    const uint32_t x = scratch[w];
+    if (w < warp && x) before = x;
+    if (x) all = x;
+  }
+  *total = all;
+  __syncthreads();
+  return prev ? prev : before;
+}
+
+__global__ void __launch_bounds__(kThreads) decode_gorilla_kernel(const DecLaunch L) {
+  extern __shared__ __align__(16) uint8_t dyn_smem[];
+  __shared__ DecShared sh;
+  __shared__ MixShared ms;
+  __shared__ uint32_t s_frame, s_gtok, s_found, s_exit, s_exit_class, s_window, s_class;
+  __shared__ uint32_t s_lastscan[kThreads / 32];
+  uint8_t* bytes = dyn_smem;
+  uint32_t* tbits = reinterpret_cast<uint32_t*>(bytes + kGorTile + kMixLook + 32);
+  uint32_t* table = tbits + kGorBitWords;                       // [kGorClasses][kGorTile]: next position | next class << 16
+  uint8_t* q = reinterpret_cast<uint8_t*>(table + kGorClasses * kGorTile);
+  uint16_t* starts = reinterpret_cast<uint16_t*>(q);  // [kGorTile + 2]
+  q += ((kGorTile + 2) * 2 + 15) / 16 * 16;
+  uint8_t* cls = q;                                    // [kGorTile + 2] class in front of every point
+  q += (kGorTile + 2 + 15) / 16 * 16;
+  long long* vals = reinterpret_cast<long long*>(q);
+
+  const uint32_t gc = blockIdx.x;
+  const Plan& plan = *L.plan;
+  if (threadIdx.x == 0) {
+    uint32_t lo = 0, hi = L.n_frames - 1;
+    while (lo < hi) {
+      const uint32_t mid = (lo + hi + 1) >> 1;
+      if (L.frames[mid].chunk_begin <= gc) lo = mid; else hi = mid - 1;
+    }
+    s_frame = lo;
+    uint32_t nt = 0, nv = 0, nf = 0;
+    for (uint32_t k = 0; k < plan.n_ops; ++k) {
+      const RegOp& op = plan.ops[k];
+      const bool fixed = op.kind == OP_COPY || op.kind == OP_XOR32 || op.kind == OP_XOR64;
+      const int lanes = (fixed || op.kind == OP_GORILLA64) ? 1 : op.lanes;
+      for (int l = 0; l < lanes; ++l) {
+        MixToken& t = ms.tok[nt];
+        t.size = op.size;
+        t.offset = op.offset[l];
+        if (op.kind == OP_GORILLA64) { t.kind = MIX_GORILLA; t.index = 0; s_gtok = nt; }
+        else if (fixed) { t.kind = op.kind == OP_COPY ? MIX_COPY : MIX_XOR; t.index = static_cast<uint16_t>(nf++); }
+        else {
+          t.kind = MIX_VAR;
+          t.index = static_cast<uint16_t>(nv++);
+          t.slot.offset = op.offset[l]; t.slot.size = op.size; t.slot.mul_f = op.dec_mul_f[l]; t.slot.mul_d = op.dec_mul_d;
+          t.slot.kind = op.kind == OP_FLOATN ? SLOT_FLOATN : op.kind == OP_F32_LOSSY ? SLOT_F32 : op.kind == OP_F64_LOSSY ? SLOT_F64 : SLOT_INT;
+        }
+        ++nt;
+      }
+    }
+    ms.n_tok = nt; ms.n_var = nv; ms.n_fix = nf; ms.n_seg = 0;
+    for (uint32_t i = 0; i < kMaxOps + 4; ++i) { ms.carry[i] = 0; ms.xcarry[i] = 0; }
+    s_window = 0;  // no window yet ((1 << 16) | lead << 8 | trail once there is one)
+    s_class = 0;
+  }
+  __syncthreads();
+  const DecFrame F = L.frames[s_frame];
+  const uint32_t c = gc - F.chunk_begin;
+  const uint32_t n_points = min(kChunkPoints, F.n_points - c * kChunkPoints);
+  const uint8_t* body = F.payload + L.chunk_offsets[gc];
+  const uint32_t size = L.chunk_sizes[gc];
+  uint8_t* out = F.out + static_cast<size_t>(c) * kChunkPoints * plan.point_step;
+  const uint32_t n_var = ms.n_var, n_fix = ms.n_fix, n_tok = ms.n_tok, gtok = s_gtok;
+  uint8_t* nanflag = reinterpret_cast<uint8_t*>(vals + static_cast<size_t>(kMixBatch) * n_var);
+  unsigned long long* raws = reinterpret_cast<unsigned long long*>(nanflag + ((static_cast<size_t>(kMixBatch) * n_var + 15) / 16) * 16);
+  if (L.stream_end && threadIdx.x == 0) L.stream_end[gc] = 0xFFFFFFFFu;
+
+  uint32_t done = 0, t0 = 0;
+  while (done < n_points) {
+    if (t0 >= size) { if (threadIdx.x == 0) report_error(L.err, DEV_ERR_TRUNCATED); return; }
+    // ---- 1. stage the tile and its terminator bits (as in decode_mixed_kernel) ----
+    const uint32_t mis = static_cast<uint32_t>((reinterpret_cast<uintptr_t>(body) + t0) & 15u);
+    const int64_t a0 = static_cast<int64_t>(t0) - mis;
+    const int64_t avail_local = static_cast<int64_t>(size) - a0;
+    const uint32_t limit = static_cast<uint32_t>(avail_local < static_cast<int64_t>(kGorTile + kMixLook) ? avail_local : kGorTile + kMixLook);
+    for (uint32_t v = threadIdx.x; v < (kGorTile + kMixLook) / 16; v += blockDim.x) {
+      const int64_t b = a0 + static_cast<int64_t>(v) * 16;
+      uint4 q = make_uint4(0x80808080u, 0x80808080u, 0x80808080u, 0x80808080u);
+      if (b >= 0 && b + 16 <= static_cast<int64_t>(size)) {
+        q = *reinterpret_cast<const uint4*>(body + b);
+      } else if (b + 16 > 0 && b < static_cast<int64_t>(size)) {
+        uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          const int64_t bb = b + k;
+          if (bb >= 0 && bb < static_cast<int64_t>(size)) w[k >> 2] = (w[k >> 2] & ~(0xFFu << (8 * (k & 3)))) | (static_cast<uint32_t>(body[bb]) << (8 * (k & 3)));
+        }
+        q = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+      *reinterpret_cast<uint4*>(bytes + v * 16) = q;
+    }
+    __syncthreads();
+    for (uint32_t w = threadIdx.x; w < kGorBitWords; w += blockDim.x) {
+      uint32_t m = 0;
+      if (w * 32u < limit) {
+        const uint4 lo = *reinterpret_cast<const uint4*>(bytes + w * 32u);
+        const uint4 hi = *reinterpret_cast<const uint4*>(bytes + w * 32u + 16u);
+        const uint32_t x[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint32_t t = ~x[k] & 0x80808080u;
+          m |= (((t >> 7) & 1u) | ((t >> 14) & 2u) | ((t >> 21) & 4u) | ((t >> 28) & 8u)) << (4 * k);
+        }
+        if (w * 32u + 32u > limit) m &= (1u << (limit - w * 32u)) - 1u;
+      }
+      tbits[w] = m;
+    }
+    __syncthreads();
+    // ---- 2. next(b, class) ----
+    for (uint32_t b = threadIdx.x; b < kGorTile; b += blockDim.x) {
+      uint32_t pg = kMixNone;
+      if (b >= mis && b < limit) pg = gor_skip_tokens(ms, tbits, b, limit, 0, gtok);
+      GorHeader h;
+      const bool header_ok = pg != kMixNone && pg < limit && gor_header(bytes + pg, limit - pg, &h);
+      for (uint32_t cl = 0; cl < kGorClasses; ++cl) {
+        uint32_t e = kGorNone;
+        if (header_ok) {
+          uint32_t len = 1, ncl = cl;
+          bool ok = true;
+          if (h.kind == 1) { len = cl; ok = cl != 0; }                                   // reuse: the class IS the length
+          else if (h.kind == 2) { len = (13u + h.meaningful + 7u) >> 3; ncl = (2u + h.meaningful + 7u) >> 3; }
+          if (ok && pg + len <= limit) {
+            const uint32_t pe = gor_skip_tokens(ms, tbits, pg + len, limit, gtok + 1, n_tok);
+            if (pe != kMixNone) e = pe | (ncl << 16);
+          }
+        }
+        table[cl * kGorTile + b] = e;
+      }
+    }
+    __syncthreads();
+    // ---- 3. one thread follows the entry through the table ----
+    if (threadIdx.x == 0) {
+      uint32_t i = 0, p = mis, cl = s_class;
+      while (p < kGorTile && i < kGorTile) {
+        starts[i] = static_cast<uint16_t>(p);
+        cls[i] = static_cast<uint8_t>(cl);
+        uint32_t e;
+        if (done == 0 && i == 0) {  // first point of the chunk: the record is the 64 raw bits, no window afterwards
+          const uint32_t pg = gor_skip_tokens(ms, tbits, p, limit, 0, gtok);
+          e = kGorNone;
+          if (pg != kMixNone && pg + 8u <= limit) {
+            const uint32_t pe = gor_skip_tokens(ms, tbits, pg + 8u, limit, gtok + 1, n_tok);
+            if (pe != kMixNone) e = pe;  // class 0
+          }
+        } else {
+          e = table[cl * kGorTile + p];
+        }
+        ++i;
+        if (e == kGorNone) { p = kMixNone; break; }
+        p = e & 0xFFFFu;
+        cl = e >> 16;
+      }
+      s_found = i;
+      s_exit = p;
+      s_exit_class = cl;
+      starts[i] = static_cast<uint16_t>(p);
+    }
+    __syncthreads();
+    const uint32_t found = s_found;
+    const uint32_t take = found < n_points - done ? found : n_points - done;
+    // ---- 4. + 5. batches of one point per thread ----
+    for (uint32_t b0 = 0; b0 < take; b0 += kMixBatch) {
+      const uint32_t i = b0 + threadIdx.x;
+      const bool active = i < take;
+      bool bad = false;
+      uint32_t g_pos = 0, g_new = 0;  // g_new: (1 << 16) | lead << 8 | trail when this point's record opens a window
+      const bool g_first = active && done == 0 && i == 0;
+      if (active) {
+        uint32_t p = starts[i];
+        for (uint32_t t = 0; t < n_tok; ++t) {
+          const MixToken& tk = ms.tok[t];
+          if (tk.kind == MIX_VAR) {
+            long long diff = 0;
+            uint8_t nan = 0;
+            if (p >= limit) { report_error(L.err, DEV_ERR_TRUNCATED); bad = true; break; }
+            if (bytes[p] == 0 && tk.slot.kind != SLOT_INT) { nan = 1; ++p; }
+            else {
+              const uint32_t n = read_varint(bytes + p, limit - p, &diff, L.err);
+              if (!n) { bad = true; break; }
+              p += n;
+            }
+            vals[static_cast<size_t>(threadIdx.x) * n_var + tk.index] = diff;
+            nanflag[static_cast<size_t>(threadIdx.x) * n_var + tk.index] = nan;
+          } else if (tk.kind == MIX_GORILLA) {
+            g_pos = p;
+            uint32_t len = 8;
+            if (!g_first) {
+              GorHeader h;
+              if (p >= limit || !gor_header(bytes + p, limit - p, &h)) { report_error(L.err, DEV_ERR_TRUNCATED); bad = true; break; }
+              if (h.kind == 0) len = 1;
+              else if (h.kind == 1) { len = cls[i]; if (len == 0) { report_error(L.err, DEV_ERR_TRUNCATED); bad = true; break; } }  // reuse before any window
+              else {
+                len = (13u + h.meaningful + 7u) >> 3;
+                g_new = (1u << 16) | (h.lead << 8) | ((64u - h.lead - h.meaningful) & 0xFFu);
+              }
+            }
+            if (p + len > limit) { report_error(L.err, DEV_ERR_TRUNCATED); bad = true; break; }
+            p += len;
+          } else {
+            if (p + tk.size > limit) { report_error(L.err, DEV_ERR_TRUNCATED); bad = true; break; }
+            raws[static_cast<size_t>(threadIdx.x) * n_fix + tk.index] = load_raw_bits(bytes + p, tk.size);
+            p += tk.size;
+          }
+        }
+      }
+      if (__syncthreads_or(bad ? 1 : 0)) return;
+      // the window every record sees: the latest "new window" record in front of it (this batch, else the carry)
+      uint32_t win_total;
+      const uint32_t win_ex = gor_block_last_exclusive(g_new, s_lastscan, &win_total);
+      const uint32_t win = win_ex ? win_ex : s_window;
+      unsigned long long xres = 0;
+      if (active) {
+        GorillaState st;
+        st.prev_bits = 0;
+        st.first = g_first;
+        st.leading = win ? ((win >> 8) & 0xFFu) : 255u;
+        st.trailing = win ? (win & 0xFFu) : 0u;
+        uint64_t v = 0;
+        if (!gorilla_decode(st, bytes + g_pos, limit - g_pos, &v)) { report_error(L.err, DEV_ERR_TRUNCATED); bad = true; }
+        xres = v;  // previous bits 0: the value IS the residual (the first record: the raw bits)
+      }
+      if (__syncthreads_or(bad ? 1 : 0)) return;
+      uint8_t* point = out + static_cast<size_t>(done + i) * plan.point_step;
+      for (uint32_t t = 0; t < n_tok; ++t) {
+        const MixToken& tk = ms.tok[t];
+        if (tk.kind == MIX_VAR) {
+          const long long d = active ? vals[static_cast<size_t>(threadIdx.x) * n_var + tk.index] : 0;
+          const bool nan = active && nanflag[static_cast<size_t>(threadIdx.x) * n_var + tk.index] != 0;
+          Seg<long long, 1> mine;
+          mine.sum[0] = nan ? 0 : d;
+          mine.rst = nan ? 1u : 0u;
+          Seg<long long, 1> total;
+          const Seg<long long, 1> ex = block_seg_exclusive<long long, 1>(mine, sh.seg_sum, sh.seg_rst, &total);
+          const long long before = ex.rst ? ex.sum[0] : wadd(ms.carry[tk.index], ex.sum[0]);
+          if (active) store_slot_value<long long>(point, tk.slot, nan ? 0 : wadd(before, d), nan);
+          __syncthreads();
+          if (threadIdx.x == 0) ms.carry[tk.index] = total.rst ? total.sum[0] : wadd(ms.carry[tk.index], total.sum[0]);
+        } else if (tk.kind == MIX_XOR || tk.kind == MIX_GORILLA) {
+          const bool g = tk.kind == MIX_GORILLA;
+          const uint32_t ci = g ? static_cast<uint32_t>(kMaxOps + 3) : tk.index;  // the Gorilla field's carry lives in the last slot
+          const unsigned long long r = !active ? 0ull : g ? xres : raws[static_cast<size_t>(threadIdx.x) * n_fix + tk.index];
+          unsigned long long total;
+          const unsigned long long ex = mix_block_xor_exclusive(r, ms.xscan, &total);
+          const unsigned long long v = ms.xcarry[ci] ^ ex ^ r;
+          if (active && tk.offset != CLDN_SKIP_STORE_OFFSET) {
+            if (g) store_u64(point + tk.offset, v); else store_low_bytes(point + tk.offset, v, tk.size);
+          }
+          __syncthreads();
+          if (threadIdx.x == 0) ms.xcarry[ci] ^= total;
+        } else if (active && tk.offset != CLDN_SKIP_STORE_OFFSET) {
+          store_low_bytes(point + tk.offset, raws[static_cast<size_t>(threadIdx.x) * n_fix + tk.index], tk.size);
+        }
+      }
+      if (threadIdx.x == 0 && win_total) s_window = win_total;
+      __syncthreads();
+    }
+    done += take;
+    const uint32_t end_local = starts[take];
+    const uint32_t exit_class = s_exit_class;
+    __syncthreads();
+    if (done < n_points) {
+      if (end_local == kMixNone || end_local <= mis) { if (threadIdx.x == 0) report_error(L.err, DEV_ERR_TRUNCATED); return; }
+      t0 = static_cast<uint32_t>(a0 + end_local);
+      if (threadIdx.x == 0) s_class = exit_class;
+      __syncthreads();
+    } else {
+      if (end_local == kMixNone) { if (threadIdx.x == 0) report_error(L.err, DEV_ERR_TRUNCATED); return; }
+      if (L.stream_end && threadIdx.x == 0) L.stream_end[gc] = static_cast<uint32_t>(a0 + end_local);
+    }
+  }
+  if (n_points == 0 && L.stream_end && threadIdx.x == 0) L.stream_end[gc] = 0;
+}
+
+static size_t gorilla_smem_bytes(const Plan& plan) {
+  size_t n_var = 0, n_fix = 0;
+  for (uint32_t k = 0; k < plan.n_ops; ++k) {
+    const RegOp& op = plan.ops[k];
+    if (op.kind == OP_GORILLA64) continue;
+    if (op.kind == OP_COPY || op.kind == OP_XOR32 || op.kind == OP_XOR64) ++n_fix; else n_var += op.lanes;
+  }
+  size_t bytes = kGorTile + kMixLook + 32 + kGorBitWords * 4 + kGorClasses * kGorTile * 4;
+  bytes += ((kGorTile + 2) * 2 + 15) / 16 * 16 + (kGorTile + 2 + 15) / 16 * 16;
+  bytes += kMixBatch * n_var * 8;
+  bytes += (kMixBatch * n_var + 15) / 16 * 16;
+  bytes += kMixBatch * n_fix * 8 + 64;
+  return bytes;
+}
+static bool gorilla_plan_ok(const Plan& plan) {
+  if (plan.n_gorilla != 1 || plan.max_point_bytes > kMixLook) return false;
+  const char* e = getenv("CLDN_B200_MIXED_DECODE");
+  return !(e && e[0] == 's');
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 static size_t dec_smem_bytes(bool k32) {
   return kLookBehind + kDecTileBytes + 16 + static_cast<size_t>(kDecTileBytes) * (k32 ? 4 : 8) + kDecTileBytes / 8 +
          sizeof(RunBatch) + 16;
@@ -1200,6 +1560,10 @@ int launch_decode(const Plan& plan, const DecLaunch& L, cudaStream_t stream) {
         const size_t msmem = mixed_smem_bytes(plan);
         if (cudaFuncSetAttribute(decode_mixed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(msmem)) != cudaSuccess) return -1;
         decode_mixed_kernel<<<L.n_chunks_total, kThreads, msmem, stream>>>(L);
+      } else if (gorilla_plan_ok(plan)) {
+        const size_t gsmem = gorilla_smem_bytes(plan);
+        if (cudaFuncSetAttribute(decode_gorilla_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(gsmem)) != cudaSuccess) return -1;
+        decode_gorilla_kernel<<<L.n_chunks_total, kThreads, gsmem, stream>>>(L);
       } else {
         decode_sequential_kernel<<<(L.n_chunks_total + 31) / 32, 32, 0, stream>>>(L);
       }

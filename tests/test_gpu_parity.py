@@ -427,7 +427,8 @@ def test_corrupted_blobs_decode_like_the_reference(ref):
     trials = int(os.environ.get("CLDN_B200_CORRUPT_TRIALS", "40"))
     dec = cb.PointcloudDecoder()
     cases = [synth.cloud_c2(5000, seed=1), synth.cloud_c1(3000, seed=2), synth.cloud_c3(6000, seed=3), synth.cloud_c2(40_000, seed=4),
-             synth.cloud_lossless(3000, seed=5), synth.cloud_livox(6000, seed=6), synth.cloud_livox(3000, seed=7, version=4)]
+             synth.cloud_lossless(3000, seed=5), synth.cloud_livox(6000, seed=6), synth.cloud_livox(3000, seed=7, version=4),
+             synth.cloud_lossless(5000, seed=8, lossless=False)]
     for info, cloud in cases:
         blob = ref.encode(info, cloud)
         dinfo, hdr = cb.DecodeHeader(blob)
@@ -487,3 +488,33 @@ def test_raw_fields_in_the_stream(oracle, monkeypatch, mode, version):
     # LOSSLESS clouds: FLOAT32 -> XOR residuals (field_encoder.hpp:123-139): XOR scan across points, tiles and batches
     info, cloud = synth.cloud_lossless(20_000, seed=9, lossless=True, version=3)   # version 3: FLOAT64 is XOR too (no Gorilla)
     _roundtrip_check(info, cloud, oracle, fill=0)
+
+
+@pytest.mark.parametrize("mode", ["par", "seq"])
+def test_gorilla_field_positions(oracle, monkeypatch, mode):
+    # a Gorilla record (FLOAT64 without a resolution) in the middle of the point, next to scalar lossy floats and a raw
+    # uint8; two Gorilla fields in one point (the parallel decoder handles one: the per-chunk parser takes over);
+    # sizes around the 2048-byte tiles and the chunk edge
+    monkeypatch.setenv("CLDN_B200_MIXED_DECODE", mode)
+    F = cb.FieldType
+    rng = np.random.default_rng(12)
+    for n in (1, 2, 200, 3000, 32768, 40_000):
+        buf = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+        xyz = np.cumsum(rng.normal(0, 0.02, (n, 3)), axis=0).astype(np.float32)
+        stamp = (1.7e9 + np.arange(n) * 1e-5 + (np.arange(n) // 500) * 0.05).astype(np.float64)
+        if n > 100:
+            stamp[rng.integers(1, n, n // 50)] = rng.integers(0, 2**63, n // 50, dtype=np.int64).view(np.float64)   # window churn
+            idx = rng.integers(1, n, n // 20); stamp[idx] = stamp[idx - 1]                                          # "same value" records
+        buf[:, 0:4] = xyz[:, 0].copy().view(np.uint8).reshape(n, 4)
+        buf[:, 4:12] = stamp.view(np.uint8).reshape(n, 8)
+        buf[:, 12:16] = xyz[:, 1].copy().view(np.uint8).reshape(n, 4)
+        buf[:, 16:20] = xyz[:, 2].copy().view(np.uint8).reshape(n, 4)
+        with np.errstate(all="ignore"):
+            buf[:, 21:29] = (stamp * 2.0).view(np.uint8).reshape(n, 8)
+        one = cb.EncodingInfo(width=n, height=1, point_step=32, compression_opt=cb.CompressionOption.NONE, use_threads=False)
+        one.fields = [cb.PointField("x", 0, F.FLOAT32, 0.001), cb.PointField("stamp", 4, F.FLOAT64, None), cb.PointField("y", 12, F.FLOAT32, 0.001),
+                      cb.PointField("z", 16, F.FLOAT32, 0.002), cb.PointField("tag", 20, F.UINT8, None)]
+        _roundtrip_check(one, buf.reshape(-1), oracle, fill=0x42)
+        two = cb.EncodingInfo(width=n, height=1, point_step=32, compression_opt=cb.CompressionOption.NONE, use_threads=False)
+        two.fields = one.fields + [cb.PointField("stamp2", 21, F.FLOAT64, None)]
+        _roundtrip_check(two, buf.reshape(-1), oracle, fill=0x42)
