@@ -163,7 +163,8 @@ def build(force=False, opt="-O1", asan=False):
             fh.write(transform(text, f))
     flags = ["-std=c++17", opt, "-g", "-fPIC", "-ffp-contract=off", "-fno-strict-aliasing", "-pthread", "-I", HERE, "-w"]
     if asan:
-        flags += ["-fsanitize=address", "-fno-omit-frame-pointer"]
+        # + alignment: x86 tolerates a misaligned uint4 / uint64 access, the GPU raises "misaligned address"
+        flags += ["-fsanitize=address", "-fsanitize=alignment", "-fno-sanitize-recover=alignment", "-fno-omit-frame-pointer"]
     procs = []
     for src in SOURCES + ["cusim.cpp"]:
         path = os.path.join(HERE, src) if src == "cusim.cpp" else os.path.join(GEN, src)
@@ -177,7 +178,7 @@ def build(force=False, opt="-O1", asan=False):
             sys.stderr.write(out[-6000:])
             raise RuntimeError(f"cusim: g++ failed on {src}")
         objs.append(obj)
-    subprocess.check_call(["g++", "-shared", "-pthread", *(["-fsanitize=address"] if asan else []), "-o", lib, *objs, "-ldl"])
+    subprocess.check_call(["g++", "-shared", "-pthread", *(["-fsanitize=address", "-fsanitize=alignment"] if asan else []), "-o", lib, *objs, "-ldl"])
     return lib
 
 
