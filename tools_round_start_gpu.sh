@@ -37,7 +37,10 @@ if hdr:
         print(f"{t / 1e3:10.1f} us total {n:5d} launches  {name}")
 PY
 echo "== ncu --set full: viz kernels, decode_mixed, decode_gorilla (one launch each)" | tee -a "$OUT/summary.txt"
-for k in viz_insert_kernel viz_compact_kernel decode_mixed_kernel decode_gorilla_kernel gorilla_prepass_kernel; do
+for k in viz_insert_kernel viz_compact_kernel; do
+  timeout 600 ncu --set full --clock-control none --import-source on -k "regex:$k" -c 1 -o "$OUT/full_$k" -f python tools_extras_bench.py > "$OUT/full_$k.log" 2>&1 || true
+done
+for k in decode_mixed_kernel decode_gorilla_kernel gorilla_prepass_kernel; do
   timeout 600 ncu --set full --clock-control none --import-source on -k "regex:$k" -c 1 -o "$OUT/full_$k" -f python tools_ab_decode_paths.py > "$OUT/full_$k.log" 2>&1 || true
 done
 ls -la "$OUT" | tee -a "$OUT/summary.txt"
