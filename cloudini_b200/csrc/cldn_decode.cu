@@ -1012,26 +1012,42 @@ __global__ void __launch_bounds__(kThreads) decode_mixed_kernel(const DecLaunch 
     }
     __syncthreads();
     // ---- 3. pointer doubling: round k appends boundaries 2^k .. 2^(k+1)-1 and squares the jump table ----
+    //         (or, L.mix_chase: one thread follows next() through the tile — 1/10 of the work, one dependent
+    //         shared-memory load per point; which one wins depends on how many chunks are in flight)
     uint16_t* jt = jump0;
     uint16_t* jn = jump1;
     uint32_t exit_pos = kMixNone;
-    for (uint32_t step = 1; step < kMixTile; step <<= 1) {  // a tile holds at most kMixTile boundaries (one per byte)
-      int grew = 0;
-      for (uint32_t i = threadIdx.x; i < step; i += blockDim.x) {
-        const uint32_t b = starts[i];
-        if (b != kMixNone) {
-          const uint32_t t = jt[b];
-          if (t < kMixTile) { starts[i + step] = static_cast<uint16_t>(t); grew = 1; }
+    if (L.mix_chase) {
+      if (threadIdx.x == 0) {
+        uint32_t i = 0, p = mis;
+        while (p < kMixTile && i < kMixTile) {
+          starts[i++] = static_cast<uint16_t>(p);
+          p = jump0[p];
         }
-      }
-      if (!__syncthreads_or(grew)) { exit_pos = jt[mis]; break; }  // no boundary beyond 2^k: jt[entry] already left the tile
-      for (uint32_t b = threadIdx.x; b < kMixTile; b += blockDim.x) {
-        const uint32_t t = jt[b];
-        jn[b] = (t < kMixTile) ? jt[t] : static_cast<uint16_t>(t);
+        ms.n_found = i;
+        jump1[0] = static_cast<uint16_t>(p);  // the exit position travels through shared memory
       }
       __syncthreads();
-      uint16_t* sw = jt; jt = jn; jn = sw;
-      exit_pos = jt[mis];
+      exit_pos = jump1[0];
+    } else {
+      for (uint32_t step = 1; step < kMixTile; step <<= 1) {  // a tile holds at most kMixTile boundaries (one per byte)
+        int grew = 0;
+        for (uint32_t i = threadIdx.x; i < step; i += blockDim.x) {
+          const uint32_t b = starts[i];
+          if (b != kMixNone) {
+            const uint32_t t = jt[b];
+            if (t < kMixTile) { starts[i + step] = static_cast<uint16_t>(t); grew = 1; }
+          }
+        }
+        if (!__syncthreads_or(grew)) { exit_pos = jt[mis]; break; }  // no boundary beyond 2^k: jt[entry] already left the tile
+        for (uint32_t b = threadIdx.x; b < kMixTile; b += blockDim.x) {
+          const uint32_t t = jt[b];
+          jn[b] = (t < kMixTile) ? jt[t] : static_cast<uint16_t>(t);
+        }
+        __syncthreads();
+        uint16_t* sw = jt; jt = jn; jn = sw;
+        exit_pos = jt[mis];
+      }
     }
     {  // number of boundaries = first unset entry of the list
       uint32_t mine = 0;
@@ -1559,7 +1575,10 @@ int launch_decode(const Plan& plan, const DecLaunch& L, cudaStream_t stream) {
       if (mixed_plan_ok(plan)) {
         const size_t msmem = mixed_smem_bytes(plan);
         if (cudaFuncSetAttribute(decode_mixed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(msmem)) != cudaSuccess) return -1;
-        decode_mixed_kernel<<<L.n_chunks_total, kThreads, msmem, stream>>>(L);
+        DecLaunch M = L;
+        const char* mm = getenv("CLDN_B200_MIXED_DECODE");  // "chase": development override (see the kernel)
+        M.mix_chase = (mm && mm[0] == 'c') ? 1u : 0u;
+        decode_mixed_kernel<<<L.n_chunks_total, kThreads, msmem, stream>>>(M);
       } else if (gorilla_plan_ok(plan)) {
         const size_t gsmem = gorilla_smem_bytes(plan);
         if (cudaFuncSetAttribute(decode_gorilla_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(gsmem)) != cudaSuccess) return -1;

@@ -79,6 +79,7 @@ struct DecLaunch {
   uint32_t tile_capacity;      // records allocated (== tile_grid)
   uint32_t tile_grid;          // host upper bound on the number of tiles
   uint32_t epoch;
+  uint32_t mix_chase;          // decode_mixed_kernel: 1 = one thread follows next() through the tile instead of pointer doubling
 };
 
 int launch_decode(const Plan& host_plan, const DecLaunch& L, cudaStream_t stream);

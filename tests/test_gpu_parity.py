@@ -477,7 +477,7 @@ def test_c4_velodyne_mixed_layout(oracle):
         assert bytes(o[:s]) == oracle.encode(info, c)
 
 
-@pytest.mark.parametrize("mode", ["par", "seq"])
+@pytest.mark.parametrize("mode", ["par", "chase", "seq"])
 @pytest.mark.parametrize("version", [5, 4])
 def test_raw_fields_in_the_stream(oracle, monkeypatch, mode, version):
     # uint8 fields are raw Copy bytes between the varints: point boundaries by pointer jumping (decode_mixed_kernel, "par")

@@ -32,7 +32,7 @@ def run(name, info, clouds, reps=10):
     hdr = len(enc.getHeader())
     res = {"case": name, "frames": F, "points": n, "point_step": step, "stage1_B_per_pt": (float(np.mean(sizes)) - hdr) / n, "encode_ms": enc_ms}
     outs = {}
-    for mode in ("par", "seq"):
+    for mode in ("par", "chase", "seq"):
         os.environ["CLDN_B200_MIXED_DECODE"] = mode
         dec = cb.PointcloudDecoder()
         db = dec.make_device_batch([t.data_ptr() + hdr for t in d_blob], [x - hdr for x in sizes], [t.data_ptr() for t in d_out], [n * step] * F)
@@ -44,7 +44,7 @@ def run(name, info, clouds, reps=10):
             dec.decode_batch_device(info, db, sync=False)
         dec.sync()
         res[f"decode_{mode}_ms"] = (time.perf_counter() - t0) / reps * 1e3
-    res["modes_agree"] = bool(np.array_equal(outs["par"], outs["seq"]))
+    res["modes_agree"] = bool(np.array_equal(outs["par"], outs["seq"]) and np.array_equal(outs["chase"], outs["seq"]))
     print(json.dumps(res), flush=True)
 
 
