@@ -169,9 +169,9 @@ def _to_c(info: EncodingInfo) -> _CInfo:
     c.encoding_opt, c.compression_opt = int(info.encoding_opt), int(info.compression_opt)
     c.version, c.use_threads = int(info.version), 1 if info.use_threads else 0
     c.n_fields = len(info.fields)
-    c.encoding_config = info.encoding_config.encode()
+    c.encoding_config = info.encoding_config.encode("utf-8", "surrogateescape")
     for i, f in enumerate(info.fields):
-        c.fields[i].name = f.name.encode()
+        c.fields[i].name = f.name.encode("utf-8", "surrogateescape")
         c.fields[i].offset = f.offset
         c.fields[i].type = int(f.type)
         c.fields[i].has_resolution = 0 if f.resolution is None else 1
@@ -183,10 +183,10 @@ def _from_c(c: _CInfo) -> EncodingInfo:
     info = EncodingInfo(width=c.width, height=c.height, point_step=c.point_step,
                         encoding_opt=EncodingOptions(c.encoding_opt), compression_opt=CompressionOption(c.compression_opt),
                         use_threads=bool(c.use_threads), version=c.version,
-                        encoding_config=c.encoding_config.decode())
+                        encoding_config=c.encoding_config.decode("utf-8", "surrogateescape"))
     for i in range(c.n_fields):
         f = c.fields[i]
-        info.fields.append(PointField(f.name.decode(), f.offset, FieldType(f.type),
+        info.fields.append(PointField(f.name.decode("utf-8", "surrogateescape"), f.offset, FieldType(f.type),
                                       float(f.resolution) if f.has_resolution else None))
     return info
 
@@ -197,12 +197,12 @@ def EncodingInfoToYAML(info: EncodingInfo) -> str:  # cloudini.cpp:165-190
     lib().cldn_b200_info_to_yaml(C.byref(c), None, 0, C.byref(need))
     buf = C.create_string_buffer(need.value)
     _check(lib().cldn_b200_info_to_yaml(C.byref(c), buf, need.value, None))
-    return buf.value.decode()
+    return buf.value.decode("utf-8", "surrogateescape")
 
 
 def EncodingInfoFromYAML(yaml: str) -> EncodingInfo:  # cloudini.cpp:192-230
     c = _CInfo()
-    raw = yaml.encode()
+    raw = yaml.encode("utf-8", "surrogateescape")
     _check(lib().cldn_b200_info_from_yaml(raw, len(raw), C.byref(c)))
     return _from_c(c)
 

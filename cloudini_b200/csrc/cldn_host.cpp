@@ -125,6 +125,19 @@ static std::string unquote(const std::string& s) {
   return s;
 }
 
+// `iss >> uint32_t` of the reference's parseScalar (yaml_parser.hpp:99-108): leading blanks, then at least one digit;
+// whatever follows the digits is ignored ("30O" reads as 30), no digit at all is an error.
+static bool parse_u32_prefix(const std::string& text, uint32_t* out) {
+  const char* p = text.c_str();
+  while (*p == ' ' || *p == '\t') ++p;
+  if (*p == '+') ++p;
+  if (*p < '0' || *p > '9') return false;
+  unsigned long long v = 0;
+  while (*p >= '0' && *p <= '9') { v = v * 10 + static_cast<unsigned>(*p - '0'); if (v > 0xFFFFFFFFull) return false; ++p; }
+  *out = static_cast<uint32_t>(v);
+  return true;
+}
+
 // EncodingInfoFromYAML (cloudini.cpp:192-230). Like the reference's parser (yaml_parser.hpp) this understands the
 // exact shape EncodingInfoToYAML emits: top-level "key: value" lines and a "fields:" sequence of 4-key maps.
 int info_from_yaml(const char* yaml, size_t len, cldn_info_t* info) {
@@ -132,6 +145,8 @@ int info_from_yaml(const char* yaml, size_t len, cldn_info_t* info) {
   info->n_fields = 0;
   bool in_fields = false;
   bool have[4] = {false, false, false, false};  // width height point_step version
+  bool have_opts[2] = {false, false};            // encoding_opt compression_opt (as<> of a missing node throws, cloudini.cpp:203-204)
+  uint8_t field_keys[CLDN_MAX_FIELDS] = {};      // per field: name | offset | type | resolution seen (all four are read, :216-221)
   int cur = -1;
   size_t pos = 0;
   auto fail = [&](const char* what, const std::string& v) {
@@ -156,12 +171,20 @@ int info_from_yaml(const char* yaml, size_t len, cldn_info_t* info) {
     const std::string val = unquote(trim(line.substr(colon + 1)));
     if (!in_fields) {
       if (key == "fields") { in_fields = true; continue; }
-      if (key == "version") { int v; if (!parse_int_in_range(val, 0, 255, &v)) return fail("bad version", val); info->version = static_cast<uint8_t>(v); have[3] = true; }
-      else if (key == "width") { info->width = static_cast<uint32_t>(strtoul(val.c_str(), nullptr, 10)); have[0] = true; }
-      else if (key == "height") { info->height = static_cast<uint32_t>(strtoul(val.c_str(), nullptr, 10)); have[1] = true; }
-      else if (key == "point_step") { info->point_step = static_cast<uint32_t>(strtoul(val.c_str(), nullptr, 10)); have[2] = true; }
-      else if (key == "encoding_opt") { if (!enc_from_string(val, &info->encoding_opt)) return fail("Invalid EncodingOptions string:", val); }
-      else if (key == "compression_opt") { if (!comp_from_string(val, &info->compression_opt)) return fail("Invalid CompressionOption string:", val); }
+      if (key == "version") {
+        // the reference reads this scalar into a uint8_t, i.e. as ONE CHARACTER (yaml_parser.hpp:99-108), and DecodeHeader
+        // then overrides it with the two digits of the magic (cloudini.cpp:389-392): any non-empty text is accepted;
+        // a number is used as such (that is what EncodingInfoToYAML writes), anything else leaves the default
+        int v;
+        if (val.empty()) return fail("Failed to convert scalar:", val);
+        if (parse_int_in_range(val, 0, 255, &v)) info->version = static_cast<uint8_t>(v);
+        have[3] = true;
+      }
+      else if (key == "width") { if (!parse_u32_prefix(val, &info->width)) return fail("Failed to convert scalar:", val); have[0] = true; }
+      else if (key == "height") { if (!parse_u32_prefix(val, &info->height)) return fail("Failed to convert scalar:", val); have[1] = true; }
+      else if (key == "point_step") { if (!parse_u32_prefix(val, &info->point_step)) return fail("Failed to convert scalar:", val); have[2] = true; }
+      else if (key == "encoding_opt") { if (!enc_from_string(val, &info->encoding_opt)) return fail("Invalid EncodingOptions string:", val); have_opts[0] = true; }
+      else if (key == "compression_opt") { if (!comp_from_string(val, &info->compression_opt)) return fail("Invalid CompressionOption string:", val); have_opts[1] = true; }
       else if (key == "encoding_config") { snprintf(info->encoding_config, sizeof(info->encoding_config), "%s", val.c_str()); }
       continue;
     }
@@ -172,10 +195,11 @@ int info_from_yaml(const char* yaml, size_t len, cldn_info_t* info) {
     }
     if (cur < 0) continue;
     cldn_field_t& f = info->fields[cur];
-    if (key == "name") snprintf(f.name, sizeof(f.name), "%s", val.c_str());
-    else if (key == "offset") f.offset = static_cast<uint32_t>(strtoul(val.c_str(), nullptr, 10));
-    else if (key == "type") { if (!type_from_string(val, &f.type)) return fail("Invalid FieldType string:", val); }
+    if (key == "name") { snprintf(f.name, sizeof(f.name), "%s", val.c_str()); field_keys[cur] |= 1; }
+    else if (key == "offset") { if (!parse_u32_prefix(val, &f.offset)) return fail("Failed to convert scalar:", val); field_keys[cur] |= 2; }
+    else if (key == "type") { if (!type_from_string(val, &f.type)) return fail("Invalid FieldType string:", val); field_keys[cur] |= 4; }
     else if (key == "resolution") {
+      field_keys[cur] |= 8;
       if (val != "null") {  // cloudini.cpp:220-223: std::stof of the text
         char* end = nullptr;
         f.resolution = strtof(val.c_str(), &end);
@@ -184,9 +208,15 @@ int info_from_yaml(const char* yaml, size_t len, cldn_info_t* info) {
       }
     }
   }
-  if (!have[0] || !have[1] || !have[2] || !have[3]) {
-    set_error("EncodingInfoFromYAML: missing width/height/point_step/version");
+  if (!have[0] || !have[1] || !have[2] || !have[3] || !have_opts[0] || !have_opts[1]) {
+    set_error("EncodingInfoFromYAML: missing version/width/height/point_step/encoding_opt/compression_opt (Node is not a string)");
     return CLDN_ERR_BAD_HEADER;
+  }
+  for (uint32_t i = 0; i < info->n_fields; ++i) {
+    if (field_keys[i] != 15) {
+      set_error("EncodingInfoFromYAML: field %u lacks name / offset / type / resolution (Node is not a string)", i);
+      return CLDN_ERR_BAD_HEADER;
+    }
   }
   return CLDN_OK;
 }
@@ -396,6 +426,17 @@ static void finish_plan(Plan* p) {
 static int build_plan(const cldn_info_t& info, bool decoder, Plan* p) {
   init_plan(info, p);
   if (info.n_fields > CLDN_MAX_FIELDS) { set_error("too many fields"); return CLDN_ERR_UNSUPPORTED; }
+  // Memory safety: every field must lie inside the point. The reference never checks this (a forged header makes its
+  // decoders write past the output buffer: field_decoder.cpp:74-78 stores at offset + i * point_step unconditionally);
+  // the kernels would do the same to device memory, so such an EncodingInfo is refused here, loudly.
+  for (uint32_t i = 0; i < info.n_fields; ++i) {
+    const cldn_field_t& f = info.fields[i];
+    const uint64_t end = static_cast<uint64_t>(f.offset) + static_cast<uint64_t>(size_of_type(f.type));
+    if (!(decoder && f.offset == CLDN_SKIP_STORE_OFFSET) && end > info.point_step) {
+      set_error("field '%s' (offset %u, %d bytes) does not fit a point of %u bytes", f.name, f.offset, size_of_type(f.type), info.point_step);
+      return CLDN_ERR_INVALID_ARGUMENT;
+    }
+  }
   const bool v5 = uses_v5_codec(info);
   p->uses_v5 = v5 ? 1 : 0;
   if (!v5 && info.encoding_opt == CLDN_ENC_NONE) {  // BuildV4Encoders, v4_codec.cpp:29-34: everything is a raw copy

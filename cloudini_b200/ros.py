@@ -77,7 +77,7 @@ class RosPointCloud2:
         c = _CRosMsg()
         c.cdr_header[:] = list(self.cdr_header)
         c.stamp_sec, c.stamp_nsec = self.stamp_sec, self.stamp_nsec
-        frame = self.frame_id.encode()
+        frame = self.frame_id.encode("utf-8", "surrogateescape")
         fbuf = C.create_string_buffer(frame, len(frame) + 1)
         c.frame_id, c.frame_id_len = C.cast(fbuf, C.c_void_p).value, len(frame)
         c.height, c.width, c.point_step, c.row_step = self.height, self.width, self.point_step, self.row_step
@@ -86,7 +86,7 @@ class RosPointCloud2:
             raise RuntimeError("too many fields")
         c.n_fields = len(self.fields)
         for i, f in enumerate(self.fields):
-            c.fields[i].name = f.name.encode()
+            c.fields[i].name = f.name.encode("utf-8", "surrogateescape")
             c.fields[i].offset, c.fields[i].type = f.offset, int(f.type)
             c.fields[i].has_resolution = 0 if f.resolution is None else 1
             c.fields[i].resolution = 0.0 if f.resolution is None else float(f.resolution)
@@ -104,13 +104,13 @@ def getDeserializedPointCloudMessage(dds_msg) -> RosPointCloud2:  # ros_msg_util
     f0 = (c.frame_id or base) - base
     d0 = (c.data or base) - base
     pc = RosPointCloud2(msg=raw, cdr_header=bytes(c.cdr_header), stamp_sec=c.stamp_sec, stamp_nsec=c.stamp_nsec,
-                        frame_id=raw[f0:f0 + c.frame_id_len].decode("utf-8", "replace"),
+                        frame_id=raw[f0:f0 + c.frame_id_len].decode("utf-8", "surrogateescape"),
                         height=c.height, width=c.width, point_step=c.point_step, row_step=c.row_step,
                         is_bigendian=bool(c.is_bigendian), is_dense=bool(c.is_dense),
                         data=buf[d0:d0 + c.data_bytes], data_offset=d0)
     for i in range(c.n_fields):
         f = c.fields[i]
-        pc.fields.append(PointField(f.name.decode(), f.offset, FieldType(f.type) if f.type <= 10 else FieldType.UNKNOWN, None))
+        pc.fields.append(PointField(f.name.decode("utf-8", "surrogateescape"), f.offset, FieldType(f.type) if f.type <= 10 else f.type, None))
     return pc
 
 
@@ -119,15 +119,15 @@ def applyResolutionProfile(profile: Dict[str, float], fields: List[PointField], 
     n = C.c_uint32(len(fields))
     arr = (_CField * CLDN_MAX_FIELDS)()
     for i, f in enumerate(fields):
-        arr[i].name = f.name.encode()
+        arr[i].name = f.name.encode("utf-8", "surrogateescape")
         arr[i].offset, arr[i].type = f.offset, int(f.type)
         arr[i].has_resolution = 0 if f.resolution is None else 1
         arr[i].resolution = 0.0 if f.resolution is None else float(f.resolution)
-    names = (C.c_char_p * max(1, len(profile)))(*[k.encode() for k in profile])
+    names = (C.c_char_p * max(1, len(profile)))(*[k.encode("utf-8", "surrogateescape") for k in profile])
     res = (C.c_float * max(1, len(profile)))(*[float(v) for v in profile.values()])
     dflt = C.byref(C.c_float(default_resolution)) if default_resolution is not None else None
     _check(_L().cldn_b200_ros_apply_resolution_profile(arr, C.byref(n), names, res, len(profile), dflt))
-    fields[:] = [PointField(arr[i].name.decode(), arr[i].offset, FieldType(arr[i].type),
+    fields[:] = [PointField(arr[i].name.decode("utf-8", "surrogateescape"), arr[i].offset, FieldType(arr[i].type) if arr[i].type <= 10 else arr[i].type,
                             float(arr[i].resolution) if arr[i].has_resolution else None) for i in range(n.value)]
 
 

@@ -104,7 +104,7 @@ class RefOracle:
         buf = C.create_string_buffer(1 << 16)
         if self.L.ref_ros_describe(a.ctypes.data, a.size, buf, len(buf)) < 0:
             raise RuntimeError(self._err())
-        return buf.value.decode()
+        return buf.value.decode("utf-8", "replace")
 
     def ros_compress(self, msg: bytes, profile=None, default_resolution=None, viz=False, encoding_opt=1, compression_opt=0, version=5) -> bytes:
         """The converter's per-message step (tools/src/mcap_converter.cpp:184-204)."""

@@ -155,3 +155,24 @@ def test_no_cpu_fallback_without_gpu(lib_built):
     from cloudini_b200 import ros
     with pytest.raises(RuntimeError, match="no CPU fallback|CUDA"):
         ros.VizPreprocessor()
+
+
+def test_forged_headers_are_refused_not_executed(lib_built):
+    # a field that does not fit inside the point would make the decoders write past the output buffer (the reference
+    # does exactly that: field_decoder.cpp:74-78 has no bound). Planning refuses such an EncodingInfo on both sides.
+    info, cloud = synth.cloud_c2(100, seed=1)
+    blob = cb.EncodeHeader(info)
+    for bad in (blob.replace(b"offset: 12", b"offset: 92"), blob.replace(b"point_step: 16", b"point_step: 11"),
+                blob.replace(b"offset: 8", b"offset: 4294967290")):
+        dinfo, _ = cb.DecodeHeader(bad + b"\0" * 8)   # the text itself parses
+        with pytest.raises(RuntimeError, match="does not fit a point"):
+            cb.MaxCompressedSize(dinfo, 10) and cb.PointcloudEncoder(dinfo)
+    # required keys (the reference's as<>() of a missing node throws "Node is not a string", cloudini.cpp:199-221)
+    for drop in (b"    offset: 12\n", b"    resolution: 0.001\n", b"compression_opt: NONE\n", b"point_step: 16\n"):
+        text = blob[13:].rstrip(b"\0").replace(drop, b"", 1)
+        with pytest.raises(RuntimeError, match="Node is not a string|missing"):
+            cb.EncodingInfoFromYAML(text.decode())
+    # numbers: digits then anything (iss >> uint32_t), but at least one digit
+    assert cb.EncodingInfoFromYAML(blob[13:].rstrip(b"\0").replace(b"width: 100", b"width: 10O").decode()).width == 10
+    with pytest.raises(RuntimeError, match="Failed to convert scalar"):
+        cb.EncodingInfoFromYAML(blob[13:].rstrip(b"\0").replace(b"width: 100", b"width: x100").decode())
