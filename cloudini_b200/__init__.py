@@ -181,12 +181,14 @@ def _to_c(info: EncodingInfo) -> _CInfo:
 
 def _from_c(c: _CInfo) -> EncodingInfo:
     info = EncodingInfo(width=c.width, height=c.height, point_step=c.point_step,
-                        encoding_opt=EncodingOptions(c.encoding_opt), compression_opt=CompressionOption(c.compression_opt),
+                        encoding_opt=EncodingOptions(c.encoding_opt) if c.encoding_opt <= 2 else int(c.encoding_opt),
+                        compression_opt=CompressionOption(c.compression_opt) if c.compression_opt <= 2 else int(c.compression_opt),
                         use_threads=bool(c.use_threads), version=c.version,
                         encoding_config=c.encoding_config.decode("utf-8", "surrogateescape"))
     for i in range(c.n_fields):
         f = c.fields[i]
-        info.fields.append(PointField(f.name.decode("utf-8", "surrogateescape"), f.offset, FieldType(f.type),
+        # a forged legacy header can carry any type byte (the reference casts it unchecked, cloudini.cpp:405): keep the number
+        info.fields.append(PointField(f.name.decode("utf-8", "surrogateescape"), f.offset, FieldType(f.type) if f.type <= 10 else int(f.type),
                                       float(f.resolution) if f.has_resolution else None))
     return info
 
