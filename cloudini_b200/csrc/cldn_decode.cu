@@ -469,7 +469,48 @@ struct RunBatch {
   uint32_t pos;       // parse position (bytes into the section) after this batch
   uint32_t runs_left;
   uint32_t failed;
+  unsigned long long prev;  // DeltaRle: running value in front of the next batch
 };
+
+// ---- parallel parse of a run table (Rle: raw value + uvarint length, DeltaRle: varint delta + uvarint length) -----------
+// The table is a chain of variable-length records, so the reference (and the first version of this reader) walks it
+// with one dependent parse per run. Here the next kRunPar * 20 bytes are staged in shared memory, every byte position
+// computes where the following record would start IF a record started there (one or two terminator bits, plus the raw
+// bytes of an Rle value), ONE thread follows that table from the batch's first byte (one shared-memory load per run) and
+// then every thread decodes one run with the careful readers; run starts and DeltaRle values come from two CTA scans.
+constexpr uint32_t kRunPar = kThreads;        // runs per iteration (one per thread)
+constexpr uint32_t kRunRecMax = 20;           // a record is at most 10 + 10 bytes (8 + 10 for Rle)
+constexpr uint32_t kRunStage = 5632;          // >= kRunPar * kRunRecMax, multiple of 32
+constexpr uint32_t kRunNone = 0xFFFFu;
+
+__device__ __forceinline__ uint32_t run_skip_varint(const uint32_t* tb, uint32_t p, uint32_t S) {
+  if (p >= S) return kRunNone;
+  const uint32_t w = p >> 5, sh = p & 31u;
+  const uint32_t lo = __funnelshift_r(tb[w], tb[w + 1], sh);  // 32 terminator bits from p on: a varint has at most 10 bytes
+  if (lo == 0u) return kRunNone;
+  return p + static_cast<uint32_t>(__ffs(static_cast<int>(lo)));
+}
+__device__ __forceinline__ unsigned long long block_exclusive_sum_u64(unsigned long long v, long long (*scratch)[4], unsigned long long* total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned long long inc = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const unsigned long long t = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= d) inc += t;
+  }
+  if (lane == 31) scratch[warp][0] = static_cast<long long>(inc);
+  __syncthreads();
+  unsigned long long before = 0, all = 0;
+#pragma unroll
+  for (int w = 0; w < kThreads / 32; ++w) {
+    const unsigned long long x = static_cast<unsigned long long>(scratch[w][0]);
+    if (w < warp) before += x;
+    all += x;
+  }
+  *total = all;
+  __syncthreads();
+  return before + inc - v;
+}
 
 // Decodes one section starting at src (avail bytes). Returns bytes consumed or 0xFFFFFFFF on error.
 template <int KT>
@@ -547,41 +588,104 @@ __device__ uint32_t decode_section(const uint8_t* __restrict__ src, uint32_t ava
   }
   __syncthreads();
   uint32_t out_index = 0;          // points produced so far (uniform)
-  unsigned long long prev = 0;     // DeltaRle running value (thread 0 only)
+  if (threadIdx.x == 0) rb.prev = 0;
+  uint8_t* sb = vals_raw;                                                        // staged bytes of the run table
+  uint32_t* tb = reinterpret_cast<uint32_t*>(sb + kRunStage + 32);              // terminator bits
+  uint16_t* nx = reinterpret_cast<uint16_t*>(tb + kRunStage / 32 + 4);          // next record start per byte position
+  uint16_t* rs = nx + kRunStage;                                                 // record starts of this batch [kRunPar + 2]
   while (true) {
-    if (threadIdx.x == 0) {
-      uint32_t n = 0, pos = rb.pos, oi = out_index;
-      while (n < kRunBatch && rb.runs_left > 0) {
-        unsigned long long run_len = 0;
-        if (mode == 2) {
-          if (avail - pos < bpv) { report_error(err, DEV_ERR_RLE); rb.failed = 1; break; }  // "truncated RLE value"
-          rb.value[n] = load_raw_bits(src + pos, bpv);
-          pos += bpv;
-        } else {
-          long long diff;
-          const uint32_t c = read_varint(src + pos, avail - pos, &diff, err);
-          if (!c) { rb.failed = 1; break; }
-          pos += c;
-          rb.diff[n] = diff;
-          rb.value[n] = prev;
+    const uint32_t pos = rb.pos;
+    const uint32_t want = rb.runs_left < kRunPar ? rb.runs_left : kRunPar;
+    const uint32_t rest = avail - pos;
+    const uint32_t S = rest < kRunStage ? rest : kRunStage;
+    const bool more_behind = rest > kRunStage;
+    for (uint32_t i = threadIdx.x; i < kRunStage + 32; i += blockDim.x) sb[i] = i < S ? src[pos + i] : 0x80u;
+    __syncthreads();
+    for (uint32_t w = threadIdx.x; w < kRunStage / 32 + 4; w += blockDim.x) {
+      uint32_t m = 0;
+      if (w * 32u < S) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint32_t t = ~*reinterpret_cast<const uint32_t*>(sb + w * 32u + 4 * k) & 0x80808080u;
+          m |= (((t >> 7) & 1u) | ((t >> 14) & 2u) | ((t >> 21) & 4u) | ((t >> 28) & 8u)) << (4 * k);
         }
-        const uint32_t c2 = read_uvarint(src + pos, avail - pos, &run_len, err);
-        if (!c2) { rb.failed = 1; break; }
-        pos += c2;
-        if (run_len > static_cast<unsigned long long>(n_points - oi)) {  // "run exceeds point count"
-          report_error(err, DEV_ERR_RLE);
-          rb.failed = 1;
-          break;
-        }
-        if (mode == 3) prev += static_cast<unsigned long long>(rb.diff[n]) * run_len;
-        rb.start[n] = oi;
-        oi += static_cast<uint32_t>(run_len);
-        --rb.runs_left;
-        ++n;
       }
-      rb.start[n] = oi;
+      tb[w] = m;  // bytes behind S read as 0x80: no terminator there
+    }
+    __syncthreads();
+    for (uint32_t b = threadIdx.x; b < S; b += blockDim.x) {
+      uint32_t p = b;
+      if (mode == 2) { p += bpv; if (p > S) p = kRunNone; }
+      else p = run_skip_varint(tb, p, S);
+      if (p != kRunNone) p = run_skip_varint(tb, p, S);
+      nx[b] = static_cast<uint16_t>(p);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t n = 0, p = 0;
+      while (n < want) {
+        if (n > 0 && more_behind && p + kRunRecMax > S) break;  // the record may continue behind the staged bytes: next batch
+        rs[n++] = static_cast<uint16_t>(p);
+        p = p < S ? nx[p] : kRunNone;  // a record that would start behind the last byte is a truncated table
+        if (p == kRunNone) break;      // truncated / malformed record: the careful readers below say what is wrong with it
+      }
+      rs[n] = static_cast<uint16_t>(p);
       rb.n = n;
-      rb.pos = pos;
+      rb.failed = 0;
+    }
+    __syncthreads();
+    {
+      const uint32_t n = rb.n;
+      const uint32_t r = threadIdx.x;
+      bool bad = false;
+      unsigned long long run_len = 0, raw = 0;
+      long long diff = 0;
+      uint32_t q = 0;
+      if (r < n) {
+        q = rs[r];
+        if (mode == 2) {
+          if (rest - q < bpv) { report_error(err, DEV_ERR_RLE); bad = true; }  // "truncated RLE value"
+          else { raw = load_raw_bits(sb + q, bpv); q += bpv; }
+        } else {
+          const uint32_t lim = (rest - q) < (S - q) ? (rest - q) : (S - q);
+          const uint32_t c = read_varint(sb + q, lim, &diff, err);
+          if (!c) bad = true;
+          q += c;
+        }
+        if (!bad) {
+          const uint32_t lim = (rest - q) < (S - q) ? (rest - q) : (S - q);
+          const uint32_t c2 = read_uvarint(sb + q, lim, &run_len, err);
+          if (!c2) bad = true;
+          q += c2;
+        }
+      }
+      if (__syncthreads_or(bad ? 1 : 0)) return 0xFFFFFFFFu;
+      // run starts: exclusive sum of the lengths (64-bit: a forged length must not wrap)
+      unsigned long long len_total, prod_total;
+      const unsigned long long before = block_exclusive_sum_u64(r < n ? run_len : 0ull, sh.seg_sum, &len_total);
+      const unsigned long long oi = static_cast<unsigned long long>(out_index) + before;
+      if (r < n && (oi > n_points || run_len > static_cast<unsigned long long>(n_points) - oi)) {  // "run exceeds point count"
+        report_error(err, DEV_ERR_RLE);
+        bad = true;
+      }
+      // DeltaRle: the value in front of run r is prev + sum over earlier runs of diff * length (wrapping like the reference)
+      const unsigned long long prod = (r < n && mode == 3) ? static_cast<unsigned long long>(diff) * run_len : 0ull;
+      const unsigned long long pbefore = block_exclusive_sum_u64(prod, sh.seg_sum, &prod_total);
+      if (__syncthreads_or(bad ? 1 : 0)) return 0xFFFFFFFFu;
+      if (r < n) {
+        rb.start[r] = static_cast<uint32_t>(oi);
+        rb.value[r] = mode == 2 ? raw : rb.prev + pbefore;
+        rb.diff[r] = diff;
+        if (r == n - 1) {
+          rb.start[n] = static_cast<uint32_t>(oi + run_len);
+          rb.pos = pos + q;
+        }
+      }
+      __syncthreads();  // everybody has read rb.prev / rb.runs_left
+      if (threadIdx.x == 0) {
+        rb.prev += prod_total;
+        rb.runs_left -= n;
+      }
     }
     __syncthreads();
     if (rb.failed) return 0xFFFFFFFFu;

@@ -429,6 +429,12 @@ def test_corrupted_blobs_decode_like_the_reference(ref):
     cases = [synth.cloud_c2(5000, seed=1), synth.cloud_c1(3000, seed=2), synth.cloud_c3(6000, seed=3), synth.cloud_c2(40_000, seed=4),
              synth.cloud_lossless(3000, seed=5), synth.cloud_livox(6000, seed=6), synth.cloud_livox(3000, seed=7, version=4),
              synth.cloud_lossless(5000, seed=8, lossless=False)]
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    from make_golden import int_field_cloud
+    run_id = np.arange(9000) // 7                                                   # long Rle / DeltaRle run tables
+    cases.append(int_field_cloud(np.random.default_rng(3).integers(0, 2**32, run_id.max() + 1, dtype=np.uint64).astype(np.uint32)[run_id], cb.FieldType.UINT32))
+    cases.append(int_field_cloud(np.cumsum(np.random.default_rng(4).integers(-40_000, 40_000, run_id.max() + 1)[run_id]).astype(np.int32), cb.FieldType.INT32))
     for info, cloud in cases:
         blob = ref.encode(info, cloud)
         dinfo, hdr = cb.DecodeHeader(blob)
@@ -518,3 +524,29 @@ def test_gorilla_field_positions(oracle, monkeypatch, mode):
         two = cb.EncodingInfo(width=n, height=1, point_step=32, compression_opt=cb.CompressionOption.NONE, use_threads=False)
         two.fields = one.fields + [cb.PointField("stamp2", 21, F.FLOAT64, None)]
         _roundtrip_check(two, buf.reshape(-1), oracle, fill=0x42)
+
+
+def test_v5_long_run_tables(oracle):
+    # Rle / DeltaRle sections with thousands of runs per chunk: the run table is parsed 256 records at a time (staged
+    # bytes, next-record table, one thread follows it, one thread per run decodes), so batches, the 20-byte guard at the
+    # end of the staged window and the carries (run start, DeltaRle value) across batches all get exercised
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    from make_golden import int_field_cloud
+    rng = np.random.default_rng(21)
+    n = 32768 * 2 + 4321
+    for ftype, dt in ((cb.FieldType.UINT32, np.uint32), (cb.FieldType.INT64, np.int64), (cb.FieldType.UINT16, np.uint16)):
+        # Rle: a new random value every 3..12 points
+        lens = rng.integers(3, 13, n)
+        heads = np.cumsum(lens)
+        run_id = np.searchsorted(heads, np.arange(n), side="right")
+        pool = rng.integers(0, np.iinfo(dt).max, run_id.max() + 1, dtype=np.uint64).astype(dt)
+        _roundtrip_check(*int_field_cloud(pool[run_id], ftype), oracle)
+        # DeltaRle: piecewise linear, the slope changes every 3..12 points (slopes up to +-40000: 3-byte varints)
+        slopes = rng.integers(-40_000, 40_000, run_id.max() + 1)
+        vals = np.cumsum(slopes[run_id]).astype(np.int64).astype(dt)
+        _roundtrip_check(*int_field_cloud(vals, ftype), oracle)
+    # every point its own run is never chosen by the mode selection, but the reader must still cope with a table whose
+    # records are as short as 2 bytes (256 runs = 512 bytes per batch) and as long as 18
+    short = (np.arange(n) // 2 % 2).astype(np.uint16)
+    _roundtrip_check(*int_field_cloud(short, cb.FieldType.UINT16), oracle)
