@@ -811,9 +811,7 @@ __global__ void __launch_bounds__(kThreads) decode_fixed_kernel(const DecLaunch 
     uint8_t* dst = out + static_cast<size_t>(p) * plan.point_step;
     for (uint32_t k = 0; k < plan.n_ops; ++k) {
       const RegOp& op = plan.ops[k];
-      if (op.offset[0] != CLDN_SKIP_STORE_OFFSET) {
-        for (int b = 0; b < op.size; ++b) dst[op.offset[0] + b] = src[b];
-      }
+      if (op.offset[0] != CLDN_SKIP_STORE_OFFSET) store_low_bytes(dst + op.offset[0], load_raw_bits(src, op.size), op.size);
       src += op.size;
     }
   }
