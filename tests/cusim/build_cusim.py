@@ -129,6 +129,24 @@ def _rewrite_asm(text, fname):
         pos = end + 1
 
 
+def _register_static_shared(text):
+    """`__shared__ T a, b[4];` -> the same line + `::cusim::register_shared(&a, sizeof(a)); ...` (see cuda_runtime.h)."""
+    out = []
+    for line in text.split("\n"):
+        m = re.match(r"^(\s*)__shared__\s+(.*);\s*(//.*)?$", line)
+        if not m or "extern" in line:
+            out.append(line)
+            continue
+        parts = _split_top(m.group(2))
+        names = []
+        first = re.match(r"^(.*?)(\w+)\s*((?:\[[^\]]*\])*)$", parts[0].strip())
+        names.append(first.group(2))
+        for extra in parts[1:]:
+            names.append(re.match(r"^\s*(\w+)", extra).group(1))
+        out.append(line + " " + " ".join(f"::cusim::register_shared(&{n}, sizeof({n}));" for n in names))
+    return "\n".join(out)
+
+
 def transform(text, fname):
     text = re.sub(r'#include "\.\./\.\./include/(\w+\.h)"', lambda m: f'#include "{os.path.join(ROOT, "include", m.group(1))}"', text)
     text = re.sub(r"extern\s+__shared__\s+(?:__align__\(\d+\)\s+)?uint8_t\s+(\w+)\[\];",
@@ -136,6 +154,7 @@ def transform(text, fname):
     text = re.sub(r"\b__noinline__\b", "__attribute__((noinline))", text)  # a macro of that name would break libstdc++
     text = _rewrite_asm(text, fname)
     text = _rewrite_launches(text, fname)
+    text = _register_static_shared(text)
     text = text.replace('"cloudini_b200 0.1.0 (wire v5, sm_100a)"', '"cloudini_b200 0.1.0 cusim (CPU emulation of the CUDA model: TEST ONLY)"')
     return text
 

@@ -62,6 +62,10 @@ struct ThreadCoords { uint3 tid, bid, bdim, gdim; };  // plain data: written onl
 extern thread_local ThreadCoords tc;
 void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()>& body);
 void* dyn_smem();
+// static __shared__ variables announce themselves (build_cusim.py adds the call behind every declaration) so that the
+// scheduler can fill them with 0xA5 before a CTA starts: shared memory is NOT zero on the GPU, and a kernel whose
+// result depends on an unwritten static shared variable must not pass here
+void register_shared(void* p, size_t bytes);
 void syncthreads();
 int syncthreads_or(int pred);
 void poll_yield();  // called by the spin-wait loads so that a producer in the same CTA can run

@@ -126,6 +126,7 @@ struct Cta {
 };
 
 thread_local Cta* g_cta = nullptr;
+thread_local std::vector<std::pair<void*, size_t>> g_shared_regs;  // static __shared__ variables seen on this OS thread
 std::mutex g_pool_mutex;
 std::vector<Cta*> g_pool;  // CTA contexts (fiber stacks) are recycled between launches
 
@@ -320,6 +321,11 @@ unsigned lane_id() { return g_cta->cur & 31u; }
 
 void* dyn_smem() { return g_cta->dyn; }
 
+void register_shared(void* p, size_t bytes) {
+  for (const auto& r : g_shared_regs) if (r.first == p) return;
+  g_shared_regs.emplace_back(p, bytes);
+}
+
 void syncthreads() {
   Cta* c = g_cta;
   Fiber& f = c->fibers[c->cur];
@@ -425,7 +431,9 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()
     for (;;) {
       const uint64_t i = next.fetch_add(1);  // in-order dispatch, like the hardware's block scheduler
       if (i >= n_ctas) break;
-      // poison the dynamic shared memory so that reads of never-written bytes are reproducible and loud
+      // poison shared memory so that reads of never-written bytes are reproducible and loud: the dynamic part always,
+      // the static variables from the second CTA of this OS thread on (they register when their declaration first runs)
+      for (const auto& r : g_shared_regs) memset(r.first, 0xA5, r.second);
       memset(c->dyn, 0xA5, CUSIM_ASAN ? c->dyn_cap - 64 : smem_bytes + 64);
       const uint3 bid{static_cast<unsigned>(i % grid.x), static_cast<unsigned>((i / grid.x) % grid.y),
                       static_cast<unsigned>(i / (static_cast<uint64_t>(grid.x) * grid.y))};
