@@ -243,7 +243,13 @@ static inline cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
 static inline cudaError_t cudaSetDevice(int d) { return d == 0 ? cudaSuccess : cudaErrorInvalidValue; }
 static inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
 static inline cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr a, int) { *v = (a == cudaDevAttrMultiProcessorCount) ? cusim::sm_count() : 0; return cudaSuccess; }
-static inline cudaError_t cudaMalloc(void** p, size_t n) { return posix_memalign(p, 256, n ? n : 256) == 0 ? cudaSuccess : cudaErrorMemoryAllocation; }
+// fresh device memory holds whatever the previous owner left there: fill it with a pattern, so that code that relies on
+// cudaMalloc returning zeros (it often does on a fresh process, not after memory has been recycled) fails here
+static inline cudaError_t cudaMalloc(void** p, size_t n) {
+  if (posix_memalign(p, 256, n ? n : 256) != 0) return cudaErrorMemoryAllocation;
+  memset(*p, 0xCD, n ? n : 256);
+  return cudaSuccess;
+}
 template <class T> static inline cudaError_t cudaMalloc(T** p, size_t n) { return cudaMalloc(reinterpret_cast<void**>(p), n); }
 static inline cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }
 static inline cudaError_t cudaMallocHost(void** p, size_t n) { return cudaMalloc(p, n); }
