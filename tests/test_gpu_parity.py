@@ -550,3 +550,25 @@ def test_v5_long_run_tables(oracle):
     # records are as short as 2 bytes (256 runs = 512 bytes per batch) and as long as 18
     short = (np.arange(n) // 2 % 2).astype(np.uint16)
     _roundtrip_check(*int_field_cloud(short, cb.FieldType.UINT16), oracle)
+
+
+def test_headline_batch_every_frame(oracle):
+    # the bench's own shape (BASELINE configs[1] / C5): a batch of 1M-point XYZI frames through the device-pointer API —
+    # uniform tiles (frame-interleaved CTA order in the encoder), persistent chunk-sequential decoder with the in-kernel
+    # chunk walk, chunks claimed chunk-index-major — with EVERY frame compared, not only frame 0 like bench.py does
+    F, N = 8, 1_000_000
+    info = synth.info_xyzi(N)
+    clouds = [synth.cloud_c2(N, seed=1000 + k)[1] for k in range(F)]
+    enc, dec = cb.PointcloudEncoder(info), cb.PointcloudDecoder()
+    cap = cb.MaxCompressedSize(info, N, True)
+    d_in, d_blob, d_out = [_Dev(src=c) for c in clouds], [_Dev(size=cap) for _ in range(F)], [_Dev(size=N * 16) for _ in range(F)]
+    sizes = enc.encode_batch_device(enc.make_device_batch([t.ptr for t in d_in], [N * 16] * F, [t.ptr for t in d_blob], [cap] * F),
+                                    write_header=True, want_sizes=True)
+    hdr = len(enc.getHeader())
+    dec.decode_batch_device(info, dec.make_device_batch([t.ptr + hdr for t in d_blob], [s - hdr for s in sizes], [t.ptr for t in d_out], [N * 16] * F), sync=True)
+    for k in range(F):
+        expect = oracle.encode(info, clouds[k])
+        want = np.zeros(N * 16, dtype=np.uint8)
+        oracle.decode(expect, want)
+        assert bytes(d_blob[k].numpy()[:sizes[k]]) == expect, k
+        assert np.array_equal(d_out[k].numpy(), want), k
