@@ -359,6 +359,8 @@ int syncthreads_or(int pred) {
 }
 
 void poll_yield() {
+  static const bool jitter = getenv("CUSIM_JITTER") != nullptr;
+  if (jitter && (globaltimer_ns() & 63u) == 0u) std::this_thread::yield();
   Cta* c = g_cta;
   if (!c || c->n_threads <= 1) { std::this_thread::yield(); return; }
   c->fibers[c->cur].wait = WAIT_POLL;
@@ -435,6 +437,13 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()
       // the static variables from the second CTA of this OS thread on (they register when their declaration first runs)
       for (const auto& r : g_shared_regs) memset(r.first, 0xA5, r.second);
       memset(c->dyn, 0xA5, CUSIM_ASAN ? c->dyn_cap - 64 : smem_bytes + 64);
+      // CUSIM_JITTER=1: CTAs start after a random delay (and pollers give up their time slice now and then), so that the
+      // inter-CTA protocols see many more interleavings than the OS scheduler produces on its own
+      static const bool jitter = getenv("CUSIM_JITTER") != nullptr;
+      if (jitter) {
+        const uint64_t h = (i + 1) * 0x9E3779B97F4A7C15ull ^ static_cast<uint64_t>(globaltimer_ns());
+        std::this_thread::sleep_for(std::chrono::microseconds((h >> 40) % 300));
+      }
       const uint3 bid{static_cast<unsigned>(i % grid.x), static_cast<unsigned>((i / grid.x) % grid.y),
                       static_cast<unsigned>(i / (static_cast<uint64_t>(grid.x) * grid.y))};
       run_cta(c, grid, block, bid);

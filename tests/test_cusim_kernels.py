@@ -42,11 +42,15 @@ def test_parity_suite_under_emulation(cusim_lib):
 
 @pytest.mark.parametrize("order,workers", [("rev", "8"), ("rand", "3"), ("fwd", "1")])
 def test_thread_order_and_cta_concurrency_do_not_matter(cusim_lib, order, workers):
+    # (the "rand" run also delays every CTA start at random: CUSIM_JITTER)
     # reverse / shuffled resume order inside a CTA, 1..8 OS threads running CTAs: same bytes (look-backs, persistent
     # chunk claims and the in-kernel chunk walk are the protocols this exercises)
     sel = ["tests/test_gpu_parity.py", "tests/test_gpu_ros.py", "-k",
            "float_clouds_sizes or adversarial or int_min or decode_modes or batch or c3_padded or v5_ or lossless or padded_and_unaligned or viz_ or raw_fields or gorilla_field or long_run"]
-    _run_gpu_suite(cusim_lib, {"CUSIM_ORDER": order, "CUSIM_WORKERS": workers}, sel)
+    env = {"CUSIM_ORDER": order, "CUSIM_WORKERS": workers}
+    if order == "rand":
+        env["CUSIM_JITTER"] = "1"
+    _run_gpu_suite(cusim_lib, env, sel)
 
 
 def test_product_entry_points_refuse_the_emulation(cusim_lib):
