@@ -569,7 +569,11 @@ __device__ uint32_t decode_section(const uint8_t* __restrict__ src, uint32_t ava
         k = (w >> (bit & 7u)) & ((1u << bits) - 1u);
       }
       if (k >= count) { report_error(err, DEV_ERR_PALETTE); continue; }  // "palette index out of range"
-      store_low_bytes(out + static_cast<size_t>(i) * step + sf.offset, load_raw_bits(pal + static_cast<size_t>(k) * bpv, bpv), bpv);
+      // kDecodeButSkipStore: the reference's section reader stores at `offset` unconditionally (v5_codec.cpp:787-789),
+      // i.e. 4 GB behind the buffer; here the value is validated and dropped like the regular decoders do
+      if (sf.offset != CLDN_SKIP_STORE_OFFSET) {
+        store_low_bytes(out + static_cast<size_t>(i) * step + sf.offset, load_raw_bits(pal + static_cast<size_t>(k) * bpv, bpv), bpv);
+      }
     }
     return static_cast<uint32_t>(3ull + pal_bytes + idx_bytes);
   }
@@ -700,7 +704,7 @@ __device__ uint32_t decode_section(const uint8_t* __restrict__ src, uint32_t ava
       }
       unsigned long long v = rb.value[lo];
       if (mode == 3) v += static_cast<unsigned long long>(rb.diff[lo]) * static_cast<unsigned long long>(i - rb.start[lo] + 1);
-      store_low_bytes(out + static_cast<size_t>(i) * step + sf.offset, v, bpv);
+      if (sf.offset != CLDN_SKIP_STORE_OFFSET) store_low_bytes(out + static_cast<size_t>(i) * step + sf.offset, v, bpv);
     }
     out_index = hi_pt;
     const uint32_t left = rb.runs_left;

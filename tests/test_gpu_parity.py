@@ -572,3 +572,62 @@ def test_headline_batch_every_frame(oracle):
         oracle.decode(expect, want)
         assert bytes(d_blob[k].numpy()[:sizes[k]]) == expect, k
         assert np.array_equal(d_out[k].numpy(), want), k
+
+
+@pytest.mark.parametrize("mode", ["seq", "tile"])
+def test_decode_but_skip_store(oracle, monkeypatch, mode):
+    # kDecodeButSkipStore (basic_types.hpp:71): a field whose offset is 0xFFFFFFFF is decoded (the stream position and
+    # the deltas of later points depend on it) but not stored — the PCL bridge decodes into narrower point types this way
+    # (pcl_conversion.hpp:144-155). Regular decoders honour it in the reference (field_decoder.cpp:74-78,
+    # field_decoder.hpp:93-95); compared against the reference with the same modified EncodingInfo.
+    monkeypatch.setenv("CLDN_B200_DECODE_MODE", mode)
+    cases = [synth.cloud_c2(40_000, seed=3), synth.cloud_c1(5000, seed=4), synth.cloud_livox(9000, seed=5, version=4),
+             synth.cloud_lossless(6000, seed=6, lossless=False, version=4)]
+    for info, cloud in cases:
+        blob = oracle.encode(info, cloud)
+        dinfo, hdr = cb.DecodeHeader(blob)
+        for skip in range(len(dinfo.fields)):
+            if dinfo.version >= 5 and dinfo.fields[skip].type in (cb.FieldType.INT16, cb.FieldType.UINT16, cb.FieldType.INT32, cb.FieldType.UINT32,
+                                                                   cb.FieldType.INT64, cb.FieldType.UINT64):
+                continue  # V5 sections: the reference stores at `offset` unconditionally (v5_codec.cpp:787-789), i.e. out of bounds
+            mod, _ = cb.DecodeHeader(blob)
+            mod.fields[skip].offset = cb.kDecodeButSkipStore
+            n = info.width * info.point_step
+            want = np.full(n, 0x6B, dtype=np.uint8)
+            oracle.decode_payload(mod, blob[hdr:], want)
+            got = np.full(n, 0x6B, dtype=np.uint8)
+            cb.PointcloudDecoder().decode(mod, blob[hdr:], got)
+            assert np.array_equal(got, want), (skip, [f.name for f in info.fields])
+            f = info.fields[skip]
+            view = got.reshape(info.width, info.point_step)[:, f.offset:f.offset + cb.SizeOf(f.type)]
+            assert np.all(view == 0x6B)   # really untouched
+
+
+def test_skip_store_in_v5_sections_is_honoured_here():
+    # documented deviation: the reference's section reader ignores kDecodeButSkipStore and writes at offset 0xFFFFFFFF
+    # (v5_codec.cpp:787-789); here the section value is decoded (validated) and dropped — for every section mode
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    from make_golden import int_field_cloud
+    info, cloud = synth.cloud_c3(9000, seed=2)
+    blob = cb.PointcloudEncoder(info).encode(cloud)
+    for skip, lo, hi, other in ((4, 20, 22, (16, 20)), (3, 16, 20, (20, 22))):   # ring (DeltaRle), rgba (Palette)
+        mod, hdr = cb.DecodeHeader(blob)
+        mod.fields[skip].offset = cb.kDecodeButSkipStore
+        got = np.full(cloud.size, 0x6B, dtype=np.uint8)
+        cb.PointcloudDecoder().decode(mod, blob[hdr:], got)
+        g, c = got.reshape(9000, 32), cloud.reshape(9000, 32)
+        assert np.all(g[:, lo:hi] == 0x6B) and np.array_equal(g[:, other[0]:other[1]], c[:, other[0]:other[1]])
+        assert np.array_equal(g[:, 0:12].copy().view(np.float32).round(2), c[:, 0:12].copy().view(np.float32).round(2))
+    n = 40_000
+    rng = np.random.default_rng(5)
+    run_id = np.arange(n) // 9
+    for values in (rng.integers(0, 2**31, n).astype(np.uint32),                                              # DeltaVarint
+                   rng.integers(0, 2**32, run_id.max() + 1, dtype=np.uint64).astype(np.uint32)[run_id]):      # Rle
+        info, cloud = int_field_cloud(values, cb.FieldType.UINT32)
+        blob = cb.PointcloudEncoder(info).encode(cloud)
+        mod, hdr = cb.DecodeHeader(blob)
+        mod.fields[3].offset = cb.kDecodeButSkipStore
+        got = np.full(cloud.size, 0x6B, dtype=np.uint8)
+        cb.PointcloudDecoder().decode(mod, blob[hdr:], got)
+        assert np.all(got.reshape(n, 16)[:, 12:16] == 0x6B)
