@@ -1447,7 +1447,7 @@ __global__ void __launch_bounds__(kThreads) decode_gorilla_kernel(const DecLaunc
         if (header_ok) {
           uint32_t len = 1, ncl = cl;
           bool ok = true;
-          if (h.kind == 1) { len = cl; ok = cl != 0; }                                   // reuse: the class IS the length
+          if (h.kind == 1) len = cl ? cl : 9u;  // reuse: the class IS the length (no window yet: 2 + 65 bits, see gorilla_decode)
           else if (h.kind == 2) { len = (13u + h.meaningful + 7u) >> 3; ncl = (2u + h.meaningful + 7u) >> 3; }
           if (ok && pg + len <= limit) {
             const uint32_t pe = gor_skip_tokens(ms, tbits, pg + len, limit, gtok + 1, n_tok);
@@ -1518,7 +1518,7 @@ __global__ void __launch_bounds__(kThreads) decode_gorilla_kernel(const DecLaunc
               GorHeader h;
               if (p >= limit || !gor_header(bytes + p, limit - p, &h)) { report_error(L.err, DEV_ERR_TRUNCATED); bad = true; break; }
               if (h.kind == 0) len = 1;
-              else if (h.kind == 1) { len = cls[i]; if (len == 0) { report_error(L.err, DEV_ERR_TRUNCATED); bad = true; break; } }  // reuse before any window
+              else if (h.kind == 1) len = cls[i] ? cls[i] : 9u;  // reuse (before any window: a 65-bit field, like the reference)
               else {
                 len = (13u + h.meaningful + 7u) >> 3;
                 g_new = (1u << 16) | (h.lead << 8) | ((64u - h.lead - h.meaningful) & 0xFFu);

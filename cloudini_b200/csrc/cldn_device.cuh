@@ -281,17 +281,23 @@ __device__ __forceinline__ uint32_t gorilla_decode(GorillaState& st, const uint8
       uint64_t control, bits, x;
       if (!w.read(1, &control)) return 0;
       if (control == 0) {
+        // uint8_t(64 - prev_leading - prev_trailing) (field_decoder.hpp:274). After a new-window record this is that
+        // record's bit count again (1..64) whatever the stored leading / trailing were; before any window the sentinel
+        // 255 makes it 65: the reference then reads a 65-bit field and keeps its low 64 bits (getBits, :213-241).
         const uint32_t meaningful = (64u - st.leading - st.trailing) & 0xFFu;
-        if (meaningful > 64u) return 0;  // window reuse before any window: malformed
-        if (!w.read(meaningful, &bits)) return 0;
-        x = st.trailing < 64u ? bits << st.trailing : 0ull;
+        if (meaningful > 65u) return 0;  // unreachable with the states this decoder can be in
+        if (!w.read(meaningful > 64u ? 64u : meaningful, &bits)) return 0;
+        if (meaningful > 64u) { uint64_t dropped; if (!w.read(1, &dropped)) return 0; }
+        // `bits << prev_trailing_` with a uint8_t count: a forged new-window record (leading + bits > 64) leaves a count
+        // of 192..255 behind; the reference's shift is the x86 one (count mod 64), which is what its blobs decode to
+        x = bits << (st.trailing & 63u);
       } else {
         uint64_t lead, m1;
         if (!w.read(5, &lead) || !w.read(6, &m1)) return 0;
         const uint32_t meaningful = static_cast<uint32_t>(m1) + 1u;
         if (!w.read(meaningful, &bits)) return 0;
         const uint32_t trailing = (64u - static_cast<uint32_t>(lead) - meaningful) & 0xFFu;
-        x = trailing < 64u ? bits << trailing : 0ull;
+        x = bits << (trailing & 63u);  // see above: x86 shift semantics for forged records (trailing >= 64)
         st.leading = static_cast<uint32_t>(lead);
         st.trailing = trailing;
       }

@@ -366,17 +366,20 @@ static size_t gorilla_decode(op_t* o, const uint8_t* p, size_t avail, uint64_t* 
       uint64_t control, bits, x;
       if (rd_bits(&r, 1, &control)) return 0;
       if (control == 0) {
+        /* uint8_t(64 - prev_leading - prev_trailing): 65 before any window (sentinel 255): the reference's getBits then
+         * consumes 65 bits and keeps the low 64 (field_decoder.hpp:213-241, 274-276) */
         const unsigned meaningful = (unsigned)(uint8_t)(64 - o->g_lead - o->g_trail);
-        if (meaningful > 64) { fail("oracle: Gorilla window reuse before any window (malformed input)"); return 0; }
-        if (rd_bits(&r, meaningful, &bits)) return 0;
-        x = o->g_trail < 64 ? bits << o->g_trail : 0;
+        if (meaningful > 65) { fail("oracle: impossible Gorilla window"); return 0; }
+        if (rd_bits(&r, meaningful > 64 ? 64 : meaningful, &bits)) return 0;
+        if (meaningful > 64) { uint64_t dropped; if (rd_bits(&r, 1, &dropped)) return 0; }
+        x = bits << ((unsigned)o->g_trail & 63u); /* uint8_t shift count, x86 semantics (count mod 64) for forged windows */
       } else {
         uint64_t lead, m1;
         if (rd_bits(&r, 5, &lead) || rd_bits(&r, 6, &m1)) return 0;
         const unsigned meaningful = (unsigned)m1 + 1;
         if (rd_bits(&r, meaningful, &bits)) return 0;
         const unsigned trailing = (unsigned)(uint8_t)(64 - lead - meaningful);
-        x = trailing < 64 ? bits << trailing : 0;
+        x = bits << (trailing & 63u);
         o->g_lead = (int)lead;
         o->g_trail = (int)trailing;
       }
