@@ -12,6 +12,10 @@ echo "== random-layout sweep through the generic kernels" | tee -a "$OUT/summary
 CLDN_B200_FUZZ=1 timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -k random_layouts_sweep 2>&1 | tail -3 | tee -a "$OUT/summary.txt"
 echo "== corrupted blobs, more seeds" | tee -a "$OUT/summary.txt"
 for s in 1 2 3; do CLDN_B200_CORRUPT_SEED=$s CLDN_B200_CORRUPT_TRIALS=100 timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -k corrupted 2>&1 | tail -1 | tee -a "$OUT/summary.txt"; done
+echo "== differential fuzzers on the hardware (tests/fuzz)" | tee -a "$OUT/summary.txt"
+timeout 600 python tests/fuzz/fuzz_corrupt_blobs.py 1 150 2>&1 | tail -15 | tee -a "$OUT/summary.txt"
+timeout 300 python tests/fuzz/fuzz_gorilla_records.py 1 500 2>&1 | tail -2 | tee -a "$OUT/summary.txt"
+timeout 300 python tests/fuzz/fuzz_encode_inputs.py 1 100 2>&1 | tail -2 | tee -a "$OUT/summary.txt"
 echo "== bench.py (N=1)" | tee -a "$OUT/summary.txt"
 timeout 900 python bench.py > "$OUT/bench_n1.json" 2> "$OUT/bench_n1.err"; tail -c 3000 "$OUT/bench_n1.json" | tee -a "$OUT/summary.txt"
 echo "== config table / decode-path A-B" | tee -a "$OUT/summary.txt"
