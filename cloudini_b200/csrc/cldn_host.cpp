@@ -1,6 +1,7 @@
 // Host-side (no CUDA) part of libcloudini_b200: configuration <-> YAML text, blob header, worst-case sizing and
 // the planner that turns an EncodingInfo into the flat op table the kernels consume.
 // Behavioural contract = the reference functions cited at each definition (paths relative to cloudini_lib/).
+#include <errno.h>
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
@@ -202,8 +203,10 @@ int info_from_yaml(const char* yaml, size_t len, cldn_info_t* info) {
       field_keys[cur] |= 8;
       if (val != "null") {  // cloudini.cpp:220-223: std::stof of the text
         char* end = nullptr;
+        errno = 0;
         f.resolution = strtof(val.c_str(), &end);
         if (end == val.c_str()) return fail("bad resolution", val);
+        if (errno == ERANGE) return fail("stof: resolution out of range", val);  // std::stof throws std::out_of_range (overflow and subnormal results)
         f.has_resolution = 1;
       }
     }
