@@ -631,3 +631,34 @@ def test_skip_store_in_v5_sections_is_honoured_here():
         got = np.full(cloud.size, 0x6B, dtype=np.uint8)
         cb.PointcloudDecoder().decode(mod, blob[hdr:], got)
         assert np.all(got.reshape(n, 16)[:, 12:16] == 0x6B)
+
+
+def _reference_samples():
+    """The reference's own sample data (cloudini_lib/samples). Only where the reference tree exists (the build container:
+    under tests/cusim); the files never travel to the GPU box — there the committed excerpts in tests/golden stand in."""
+    base = os.path.join(os.environ.get("CLOUDINI_REFERENCE", "/root/reference"), "cloudini_lib", "samples")
+    if not os.path.exists(os.path.join(base, "lidar.pcd")):
+        pytest.skip("reference sample files not present here")
+    raw = open(os.path.join(base, "lidar.pcd"), "rb").read()
+    n = int(raw[raw.index(b"POINTS ") + 7:raw.index(b"\n", raw.index(b"POINTS "))])
+    body = raw[raw.index(b"DATA binary\n") + 12:]
+    yield "lidar.pcd", synth.info_xyzi(n), np.frombuffer(body[:n * 16], dtype=np.uint8), {5: ("d8b95f6208899099", "dcd32492c331c988", 567_028)}
+    from cloudini_b200 import ros
+    pc = ros.getDeserializedPointCloudMessage(open(os.path.join(base, "dds_message.bin"), "rb").read())
+    info = ros.toEncodingInfo(pc)
+    info.compression_opt, info.use_threads = cb.CompressionOption.NONE, False
+    for f in info.fields:
+        if f.type == cb.FieldType.FLOAT32:
+            f.resolution = 0.001
+    yield "dds_message.bin", info, np.array(pc.data), {5: ("56c03cc916e47320", "ee5ff9fe2202fa15", 442_082), 4: ("e1fd0ae6cc727690", "ee5ff9fe2202fa15", 498_072)}
+
+
+def test_reference_sample_files(oracle):
+    # SURVEY 8(c): the FNV-1a(64) hashes of the full encoded blob / decoded buffer of the reference's two sample files
+    for name, info, cloud, expected in _reference_samples():
+        for version, (blob_hash, decoded_hash, size) in expected.items():
+            info.version = version
+            blob = _roundtrip_check(info, cloud, oracle)
+            out = np.zeros(cloud.size, dtype=np.uint8)
+            cb.PointcloudDecoder().decode(cb.DecodeHeader(blob)[0], blob[cb.DecodeHeader(blob)[1]:], out)
+            assert (len(blob), "%016x" % synth.fnv1a64(blob), "%016x" % synth.fnv1a64(out)) == (size, blob_hash, decoded_hash), (name, version)
