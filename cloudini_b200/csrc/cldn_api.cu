@@ -744,6 +744,7 @@ static int decode_batch_device(cldn_decoder* d, const cldn_info_t& info, size_t 
   if (int rc = d->h_frames.commit(hf_slot, d->stream)) return rc;
   DecLaunch L;
   L.mix_chase = 0;
+  L.par_runs = unmeasured_kernels_enabled() ? 1u : 0u;
   L.frames = d->d_frames.p;
   L.n_frames = static_cast<uint32_t>(n_frames);
   L.n_chunks_total = static_cast<uint32_t>(chunks);

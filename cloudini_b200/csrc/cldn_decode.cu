@@ -517,7 +517,7 @@ template <int KT>
 __device__ uint32_t decode_section(const uint8_t* __restrict__ src, uint32_t avail, uint32_t n_points,
                                    const SectionField& sf, uint8_t* __restrict__ out, uint32_t step, DecShared& sh,
                                    uint8_t* tile_bytes, uint8_t* vals_raw, uint32_t* nanbits, RunBatch& rb,
-                                   DecSlot* sec_slot, uint32_t* err) {
+                                   DecSlot* sec_slot, uint32_t* err, bool par_runs) {
   if (avail < 1) {
     if (threadIdx.x == 0) report_error(err, DEV_ERR_BAD_MODE);  // "missing mode byte"
     return 0xFFFFFFFFu;
@@ -597,98 +597,136 @@ __device__ uint32_t decode_section(const uint8_t* __restrict__ src, uint32_t ava
   uint32_t* tb = reinterpret_cast<uint32_t*>(sb + kRunStage + 32);              // terminator bits
   uint16_t* nx = reinterpret_cast<uint16_t*>(tb + kRunStage / 32 + 4);          // next record start per byte position
   uint16_t* rs = nx + kRunStage;                                                 // record starts of this batch [kRunPar + 2]
+  unsigned long long prev = 0;     // DeltaRle running value of the sequential parser (thread 0 only)
   while (true) {
-    const uint32_t pos = rb.pos;
-    const uint32_t want = rb.runs_left < kRunPar ? rb.runs_left : kRunPar;
-    const uint32_t rest = avail - pos;
-    const uint32_t S = rest < kRunStage ? rest : kRunStage;
-    const bool more_behind = rest > kRunStage;
-    for (uint32_t i = threadIdx.x; i < kRunStage + 32; i += blockDim.x) sb[i] = i < S ? src[pos + i] : 0x80u;
-    __syncthreads();
-    for (uint32_t w = threadIdx.x; w < kRunStage / 32 + 4; w += blockDim.x) {
-      uint32_t m = 0;
-      if (w * 32u < S) {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const uint32_t t = ~*reinterpret_cast<const uint32_t*>(sb + w * 32u + 4 * k) & 0x80808080u;
-          m |= (((t >> 7) & 1u) | ((t >> 14) & 2u) | ((t >> 21) & 4u) | ((t >> 28) & 8u)) << (4 * k);
+    if (par_runs) {
+      const uint32_t pos = rb.pos;
+      const uint32_t want = rb.runs_left < kRunPar ? rb.runs_left : kRunPar;
+      const uint32_t rest = avail - pos;
+      const uint32_t S = rest < kRunStage ? rest : kRunStage;
+      const bool more_behind = rest > kRunStage;
+      for (uint32_t i = threadIdx.x; i < kRunStage + 32; i += blockDim.x) sb[i] = i < S ? src[pos + i] : 0x80u;
+      __syncthreads();
+      for (uint32_t w = threadIdx.x; w < kRunStage / 32 + 4; w += blockDim.x) {
+        uint32_t m = 0;
+        if (w * 32u < S) {
+  #pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const uint32_t t = ~*reinterpret_cast<const uint32_t*>(sb + w * 32u + 4 * k) & 0x80808080u;
+            m |= (((t >> 7) & 1u) | ((t >> 14) & 2u) | ((t >> 21) & 4u) | ((t >> 28) & 8u)) << (4 * k);
+          }
         }
+        tb[w] = m;  // bytes behind S read as 0x80: no terminator there
       }
-      tb[w] = m;  // bytes behind S read as 0x80: no terminator there
-    }
-    __syncthreads();
-    for (uint32_t b = threadIdx.x; b < S; b += blockDim.x) {
-      uint32_t p = b;
-      if (mode == 2) { p += bpv; if (p > S) p = kRunNone; }
-      else p = run_skip_varint(tb, p, S);
-      if (p != kRunNone) p = run_skip_varint(tb, p, S);
-      nx[b] = static_cast<uint16_t>(p);
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      uint32_t n = 0, p = 0;
-      while (n < want) {
-        if (n > 0 && more_behind && p + kRunRecMax > S) break;  // the record may continue behind the staged bytes: next batch
-        rs[n++] = static_cast<uint16_t>(p);
-        p = p < S ? nx[p] : kRunNone;  // a record that would start behind the last byte is a truncated table
-        if (p == kRunNone) break;      // truncated / malformed record: the careful readers below say what is wrong with it
+      __syncthreads();
+      for (uint32_t b = threadIdx.x; b < S; b += blockDim.x) {
+        uint32_t p = b;
+        if (mode == 2) { p += bpv; if (p > S) p = kRunNone; }
+        else p = run_skip_varint(tb, p, S);
+        if (p != kRunNone) p = run_skip_varint(tb, p, S);
+        nx[b] = static_cast<uint16_t>(p);
       }
-      rs[n] = static_cast<uint16_t>(p);
-      rb.n = n;
-      rb.failed = 0;
-    }
-    __syncthreads();
-    {
-      const uint32_t n = rb.n;
-      const uint32_t r = threadIdx.x;
-      bool bad = false;
-      unsigned long long run_len = 0, raw = 0;
-      long long diff = 0;
-      uint32_t q = 0;
-      if (r < n) {
-        q = rs[r];
-        if (mode == 2) {
-          if (rest - q < bpv) { report_error(err, DEV_ERR_RLE); bad = true; }  // "truncated RLE value"
-          else { raw = load_raw_bits(sb + q, bpv); q += bpv; }
-        } else {
-          const uint32_t lim = (rest - q) < (S - q) ? (rest - q) : (S - q);
-          const uint32_t c = read_varint(sb + q, lim, &diff, err);
-          if (!c) bad = true;
-          q += c;
-        }
-        if (!bad) {
-          const uint32_t lim = (rest - q) < (S - q) ? (rest - q) : (S - q);
-          const uint32_t c2 = read_uvarint(sb + q, lim, &run_len, err);
-          if (!c2) bad = true;
-          q += c2;
-        }
-      }
-      if (__syncthreads_or(bad ? 1 : 0)) return 0xFFFFFFFFu;
-      // run starts: exclusive sum of the lengths (64-bit: a forged length must not wrap)
-      unsigned long long len_total, prod_total;
-      const unsigned long long before = block_exclusive_sum_u64(r < n ? run_len : 0ull, sh.seg_sum, &len_total);
-      const unsigned long long oi = static_cast<unsigned long long>(out_index) + before;
-      if (r < n && (oi > n_points || run_len > static_cast<unsigned long long>(n_points) - oi)) {  // "run exceeds point count"
-        report_error(err, DEV_ERR_RLE);
-        bad = true;
-      }
-      // DeltaRle: the value in front of run r is prev + sum over earlier runs of diff * length (wrapping like the reference)
-      const unsigned long long prod = (r < n && mode == 3) ? static_cast<unsigned long long>(diff) * run_len : 0ull;
-      const unsigned long long pbefore = block_exclusive_sum_u64(prod, sh.seg_sum, &prod_total);
-      if (__syncthreads_or(bad ? 1 : 0)) return 0xFFFFFFFFu;
-      if (r < n) {
-        rb.start[r] = static_cast<uint32_t>(oi);
-        rb.value[r] = mode == 2 ? raw : rb.prev + pbefore;
-        rb.diff[r] = diff;
-        if (r == n - 1) {
-          rb.start[n] = static_cast<uint32_t>(oi + run_len);
-          rb.pos = pos + q;
-        }
-      }
-      __syncthreads();  // everybody has read rb.prev / rb.runs_left
+      __syncthreads();
       if (threadIdx.x == 0) {
-        rb.prev += prod_total;
-        rb.runs_left -= n;
+        uint32_t n = 0, p = 0;
+        while (n < want) {
+          if (n > 0 && more_behind && p + kRunRecMax > S) break;  // the record may continue behind the staged bytes: next batch
+          rs[n++] = static_cast<uint16_t>(p);
+          p = p < S ? nx[p] : kRunNone;  // a record that would start behind the last byte is a truncated table
+          if (p == kRunNone) break;      // truncated / malformed record: the careful readers below say what is wrong with it
+        }
+        rs[n] = static_cast<uint16_t>(p);
+        rb.n = n;
+        rb.failed = 0;
+      }
+      __syncthreads();
+      {
+        const uint32_t n = rb.n;
+        const uint32_t r = threadIdx.x;
+        bool bad = false;
+        unsigned long long run_len = 0, raw = 0;
+        long long diff = 0;
+        uint32_t q = 0;
+        if (r < n) {
+          q = rs[r];
+          if (mode == 2) {
+            if (rest - q < bpv) { report_error(err, DEV_ERR_RLE); bad = true; }  // "truncated RLE value"
+            else { raw = load_raw_bits(sb + q, bpv); q += bpv; }
+          } else {
+            const uint32_t lim = (rest - q) < (S - q) ? (rest - q) : (S - q);
+            const uint32_t c = read_varint(sb + q, lim, &diff, err);
+            if (!c) bad = true;
+            q += c;
+          }
+          if (!bad) {
+            const uint32_t lim = (rest - q) < (S - q) ? (rest - q) : (S - q);
+            const uint32_t c2 = read_uvarint(sb + q, lim, &run_len, err);
+            if (!c2) bad = true;
+            q += c2;
+          }
+        }
+        if (__syncthreads_or(bad ? 1 : 0)) return 0xFFFFFFFFu;
+        // run starts: exclusive sum of the lengths (64-bit: a forged length must not wrap)
+        unsigned long long len_total, prod_total;
+        const unsigned long long before = block_exclusive_sum_u64(r < n ? run_len : 0ull, sh.seg_sum, &len_total);
+        const unsigned long long oi = static_cast<unsigned long long>(out_index) + before;
+        if (r < n && (oi > n_points || run_len > static_cast<unsigned long long>(n_points) - oi)) {  // "run exceeds point count"
+          report_error(err, DEV_ERR_RLE);
+          bad = true;
+        }
+        // DeltaRle: the value in front of run r is prev + sum over earlier runs of diff * length (wrapping like the reference)
+        const unsigned long long prod = (r < n && mode == 3) ? static_cast<unsigned long long>(diff) * run_len : 0ull;
+        const unsigned long long pbefore = block_exclusive_sum_u64(prod, sh.seg_sum, &prod_total);
+        if (__syncthreads_or(bad ? 1 : 0)) return 0xFFFFFFFFu;
+        if (r < n) {
+          rb.start[r] = static_cast<uint32_t>(oi);
+          rb.value[r] = mode == 2 ? raw : rb.prev + pbefore;
+          rb.diff[r] = diff;
+          if (r == n - 1) {
+            rb.start[n] = static_cast<uint32_t>(oi + run_len);
+            rb.pos = pos + q;
+          }
+        }
+        __syncthreads();  // everybody has read rb.prev / rb.runs_left
+        if (threadIdx.x == 0) {
+          rb.prev += prod_total;
+          rb.runs_left -= n;
+        }
+      }
+    } else {  // hardware-verified sequential parse: thread 0 walks up to kRunBatch records
+      if (threadIdx.x == 0) {
+        uint32_t n = 0, pos = rb.pos, oi = out_index;
+        while (n < kRunBatch && rb.runs_left > 0) {
+          unsigned long long run_len = 0;
+          if (mode == 2) {
+            if (avail - pos < bpv) { report_error(err, DEV_ERR_RLE); rb.failed = 1; break; }  // "truncated RLE value"
+            rb.value[n] = load_raw_bits(src + pos, bpv);
+            pos += bpv;
+          } else {
+            long long diff;
+            const uint32_t c = read_varint(src + pos, avail - pos, &diff, err);
+            if (!c) { rb.failed = 1; break; }
+            pos += c;
+            rb.diff[n] = diff;
+            rb.value[n] = prev;
+          }
+          const uint32_t c2 = read_uvarint(src + pos, avail - pos, &run_len, err);
+          if (!c2) { rb.failed = 1; break; }
+          pos += c2;
+          if (run_len > static_cast<unsigned long long>(n_points - oi)) {  // "run exceeds point count"
+            report_error(err, DEV_ERR_RLE);
+            rb.failed = 1;
+            break;
+          }
+          if (mode == 3) prev += static_cast<unsigned long long>(rb.diff[n]) * run_len;
+          rb.start[n] = oi;
+          oi += static_cast<uint32_t>(run_len);
+          --rb.runs_left;
+          ++n;
+        }
+        rb.start[n] = oi;
+        rb.n = n;
+        rb.pos = pos;
       }
     }
     __syncthreads();
@@ -779,7 +817,7 @@ __global__ void __launch_bounds__(kThreads) decode_chunks_kernel(const DecLaunch
   }
   for (uint32_t s = 0; s < plan.n_sections; ++s) {
     const uint32_t used = decode_section<KT>(body + pos, body_bytes - pos, n_points, plan.sections[s], out, plan.point_step,
-                                             sh, tile_bytes, vals_raw, nanbits, rb, &s_slots[kMaxOps], L.err);
+                                             sh, tile_bytes, vals_raw, nanbits, rb, &s_slots[kMaxOps], L.err, L.par_runs != 0);
     if (used == 0xFFFFFFFFu) return;
     pos += used;
     __syncthreads();
@@ -1257,8 +1295,8 @@ static size_t mixed_smem_bytes(const Plan& plan) {
 // point fits the look-ahead of a tile.
 static bool mixed_plan_ok(const Plan& plan) {
   if (plan.n_gorilla != 0 || plan.max_point_bytes > kMixLook || plan.n_ops == 0) return false;
-  const char* e = getenv("CLDN_B200_MIXED_DECODE");  // "seq": development override, the per-chunk parser
-  return !(e && e[0] == 's');
+  const char* e = getenv("CLDN_B200_MIXED_DECODE");  // "par" / "chase" / "seq": explicit choice
+  return e ? e[0] != 's' : unmeasured_kernels_enabled();
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -1618,7 +1656,7 @@ static size_t gorilla_smem_bytes(const Plan& plan) {
 static bool gorilla_plan_ok(const Plan& plan) {
   if (plan.n_gorilla != 1 || plan.max_point_bytes > kMixLook) return false;
   const char* e = getenv("CLDN_B200_MIXED_DECODE");
-  return !(e && e[0] == 's');
+  return e ? e[0] != 's' : unmeasured_kernels_enabled();
 }
 
 // ------------------------------------------------------------------------------------------------------------------

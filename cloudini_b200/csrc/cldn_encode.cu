@@ -560,9 +560,46 @@ __global__ void __launch_bounds__(kGorillaThreads) gorilla_prepass_kernel(const 
   }
 }
 
+// Gorilla pre-pass, hardware-verified version (the default until the warp-parallel one above has run on a GPU): one thread per (chunk, Gorilla op) walks its 32768 points in order (the window of the previous
+// "new window" record is inherently sequential) and leaves a 12-byte record per point: bytes 0..9 the encoded value,
+// byte 11 its length. The generic kernel then copies the record like any other field. Side layout: [op][point][12].
+__global__ void gorilla_prepass_seq_kernel(const EncLaunch L) {
+  const EncFrame F = L.frames[blockIdx.x];
+  const Plan& plan = *L.plan;
+  const uint32_t items = F.n_chunks * plan.n_gorilla;
+  for (uint32_t it = threadIdx.x; it < items; it += blockDim.x) {
+    const uint32_t chunk = it / plan.n_gorilla, g = it % plan.n_gorilla;
+    uint32_t seen = 0, offset = 0;
+    for (uint32_t k = 0; k < plan.n_ops; ++k) {
+      if (plan.ops[k].kind == OP_GORILLA64) {
+        if (seen == g) offset = plan.ops[k].offset[0];
+        ++seen;
+      }
+    }
+    const uint32_t p0 = chunk * kChunkPoints;
+    const uint32_t n = min(kChunkPoints, F.n_points - p0);
+    uint8_t* side = const_cast<uint8_t*>(F.side) + (static_cast<size_t>(g) * F.n_points + p0) * 12;
+    GorillaState st;
+    st.reset();
+    for (uint32_t i = 0; i < n; ++i) {
+      const uint64_t cur = load_u64(F.in + static_cast<size_t>(p0 + i) * plan.point_step + offset);
+      uint8_t rec[12];
+      const uint32_t len = gorilla_encode(st, cur, rec);
+      for (uint32_t b = 0; b < len; ++b) side[i * 12 + b] = rec[b];
+      side[i * 12 + 11] = static_cast<uint8_t>(len);
+    }
+  }
+}
+
+bool unmeasured_kernels_enabled() {
+  const char* e = getenv("CLDN_B200_UNMEASURED");
+  return e && e[0] == '1';
+}
+
 int launch_gorilla_prepass(const Plan& plan, const EncLaunch& L, cudaStream_t stream) {
   if (plan.n_gorilla == 0 || L.n_frames == 0) return 0;
-  gorilla_prepass_kernel<<<L.n_frames, kGorillaThreads, 0, stream>>>(L);
+  if (unmeasured_kernels_enabled()) gorilla_prepass_kernel<<<L.n_frames, kGorillaThreads, 0, stream>>>(L);
+  else gorilla_prepass_seq_kernel<<<L.n_frames, 64, 0, stream>>>(L);
   count_launch();
   return 1;
 }

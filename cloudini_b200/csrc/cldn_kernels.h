@@ -80,7 +80,14 @@ struct DecLaunch {
   uint32_t tile_grid;          // host upper bound on the number of tiles
   uint32_t epoch;
   uint32_t mix_chase;          // decode_mixed_kernel: 1 = one thread follows next() through the tile instead of pointer doubling
+  uint32_t par_runs;           // V5 Rle / DeltaRle readers: 1 = parallel run-table parse (see unmeasured_kernels_enabled)
 };
+
+// Kernels written after the round-1 GPU budget was spent (parallel boundary-search decoders, warp-parallel Gorilla
+// pre-pass, parallel run-table parse): bit-exact, memcheck- and racecheck-clean under tests/cusim, but not yet run on
+// hardware. Until they are, the hardware-verified kernels stay the default and CLDN_B200_UNMEASURED=1 selects these
+// (tests/test_gpu_zz_unmeasured.py runs the parity suite that way, last).
+bool unmeasured_kernels_enabled();
 
 int launch_decode(const Plan& host_plan, const DecLaunch& L, cudaStream_t stream);
 int launch_decode_tiles(const Plan& host_plan, const DecLaunch& L, cudaStream_t stream);

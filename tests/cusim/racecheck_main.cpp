@@ -79,6 +79,10 @@ int main(int argc, char** argv) {
   if (argc > 1 && !strcmp(argv[1], "--control-fixed")) { cusim::launch(dim3(1), dim3(256), 0, [] { control_kernel(true); }); puts("control: fixed kernel ran"); return 0; }
   int bad = 0;
   const size_t n = 70000;  // three chunks: look-backs, chunk walk, partial last tile
+  // two passes: the hardware-verified default kernels, then the ones selected by CLDN_B200_UNMEASURED=1
+  for (int pass = 0; pass < 2; ++pass) {
+  if (pass) setenv("CLDN_B200_UNMEASURED", "1", 1); else unsetenv("CLDN_B200_UNMEASURED");
+  printf("---- pass %d: %s kernels\n", pass, pass ? "CLDN_B200_UNMEASURED=1" : "default");
   // ---- C2: XYZI step 16 (FloatN fast kernels; sequential and tile-parallel decoders) ----
   {
     cldn_info_t info; cldn_b200_info_init(&info);
@@ -172,6 +176,7 @@ int main(int argc, char** argv) {
       memcpy(&cloud[i * 22], p, 16); cloud[i * 22 + 16] = tag; cloud[i * 22 + 17] = line; memcpy(&cloud[i * 22 + 18], &ot, 4);
     }
     bad += roundtrip("livox-layout/raw bytes in the stream", info, cloud, nullptr);
+  }
   }
   printf("racecheck_main: %s\n", bad ? "FAILED" : "done");
   return bad ? 1 : 0;

@@ -12,15 +12,20 @@ echo "== random-layout sweep through the generic kernels" | tee -a "$OUT/summary
 CLDN_B200_FUZZ=1 timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -k random_layouts_sweep 2>&1 | tail -3 | tee -a "$OUT/summary.txt"
 echo "== corrupted blobs, more seeds" | tee -a "$OUT/summary.txt"
 for s in 1 2 3; do CLDN_B200_CORRUPT_SEED=$s CLDN_B200_CORRUPT_TRIALS=100 timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -k corrupted 2>&1 | tail -1 | tee -a "$OUT/summary.txt"; done
-echo "== differential fuzzers on the hardware (tests/fuzz)" | tee -a "$OUT/summary.txt"
+echo "== differential fuzzers on the hardware (tests/fuzz), new kernels selected" | tee -a "$OUT/summary.txt"
+export CLDN_B200_UNMEASURED=1
 timeout 600 python tests/fuzz/fuzz_corrupt_blobs.py 1 150 2>&1 | tail -15 | tee -a "$OUT/summary.txt"
 timeout 300 python tests/fuzz/fuzz_gorilla_records.py 1 500 2>&1 | tail -2 | tee -a "$OUT/summary.txt"
 timeout 300 python tests/fuzz/fuzz_encode_inputs.py 1 100 2>&1 | tail -2 | tee -a "$OUT/summary.txt"
+unset CLDN_B200_UNMEASURED
 echo "== bench.py (N=1)" | tee -a "$OUT/summary.txt"
 timeout 900 python bench.py > "$OUT/bench_n1.json" 2> "$OUT/bench_n1.err"; tail -c 3000 "$OUT/bench_n1.json" | tee -a "$OUT/summary.txt"
 echo "== config table / decode-path A-B" | tee -a "$OUT/summary.txt"
 timeout 600 python tools_config_bench.py > "$OUT/config_table.jsonl" 2>&1; cat "$OUT/config_table.jsonl" | tee -a "$OUT/summary.txt"
 timeout 900 python tools_ab_decode_paths.py > "$OUT/ab_decode_paths.jsonl" 2>&1; cat "$OUT/ab_decode_paths.jsonl" | tee -a "$OUT/summary.txt"
+echo "== extras with the default kernels and with CLDN_B200_UNMEASURED=1 (parallel run-table reader in C3, ...)" | tee -a "$OUT/summary.txt"
+timeout 600 python tools_extras_bench.py 2>&1 | tail -1 | tee "$OUT/extras_default.json" | tee -a "$OUT/summary.txt"
+CLDN_B200_UNMEASURED=1 timeout 600 python tools_extras_bench.py 2>&1 | tail -1 | tee "$OUT/extras_unmeasured.json" | tee -a "$OUT/summary.txt"
 echo "== ncu launch list of the extras (new kernels)" | tee -a "$OUT/summary.txt"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file "$OUT/extras_launches.csv" python tools_extras_bench.py > "$OUT/extras_under_ncu.log" 2>&1
 python - <<'PY' | tee -a gpurun_out/round_start/summary.txt
