@@ -56,18 +56,5 @@ def test_ros_shim_compiles_and_links(lib_built):
     assert os.path.exists(ROS_EXE)
 
 
-@pytest.mark.gpu
-def test_ros_shim_converter_step_matches_golden(lib_built, golden_ros, tmp_path):
-    # the C++ shim reproduces the reference converter's output (golden messages generated from the reference)
-    _compile_ros(lib_built)
-    for name in ("xyzi_viz", "xyz_organized", "dds_sample_4000"):
-        if name not in golden_ros:  # the sample excerpt exists only when the goldens were generated next to the reference tree
-            continue
-        g = golden_ros[name]
-        src, comp, rest = tmp_path / "in.msg", tmp_path / "out.comp", tmp_path / "out.rest"
-        src.write_bytes(g["msg"])
-        out = subprocess.run([ROS_EXE, str(src), str(comp), str(rest), repr(g["default_resolution"]), "1" if g["viz"] else "0"],
-                             capture_output=True, text=True, timeout=120, env=_run_env(tmp_path))
-        assert out.returncode == 0 and "ros_shim_convert: ok" in out.stdout, out.stdout + out.stderr
-        assert comp.read_bytes() == g["compressed"], name
-        assert rest.read_bytes() == g["restored"], name
+# (the GPU run of this executable lives at the end of tests/test_gpu_ros.py: it needs the N3 kernels, which have not
+# had a hardware run yet, and this file sorts first)

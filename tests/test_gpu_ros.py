@@ -2,6 +2,7 @@
 kernels and the DDS envelope conversions, byte-for-byte against the reference (cloudini_lib/src/ros_msg_utils.cpp) or,
 where the reference .so is unavailable, against the committed golden messages generated from it."""
 import os
+import subprocess
 
 import numpy as np
 import pytest
@@ -11,6 +12,7 @@ from cloudini_b200 import ros, synth
 from cloudini_b200 import FieldType as FT
 
 pytestmark = pytest.mark.gpu
+# order: the N2 envelope (host code around hardware-verified kernels) first, the N3 kernels (no hardware run yet) last
 
 XYZI = [("x", 0, FT.FLOAT32), ("y", 4, FT.FLOAT32), ("z", 8, FT.FLOAT32), ("intensity", 12, FT.FLOAT32)]
 VELO = [("x", 0, FT.FLOAT32), ("y", 4, FT.FLOAT32), ("z", 8, FT.FLOAT32), ("intensity", 12, FT.FLOAT32),
@@ -21,106 +23,6 @@ def _same_info(a, b):
     return (a.width, a.height, a.point_step) == (b.width, b.height, b.point_step) and \
         [(f.name, f.offset, int(f.type), None if f.resolution is None else np.float32(f.resolution)) for f in a.fields] == \
         [(f.name, f.offset, int(f.type), None if f.resolution is None else np.float32(f.resolution)) for f in b.fields]
-
-
-# ---- N3: applyVizLossyPreprocessing ------------------------------------------------------------------------------------
-@pytest.mark.parametrize("n,step", [(1, 16), (2, 16), (255, 16), (256, 12), (2049, 16), (40_000, 16), (100_003, 32), (30_000, 22), (5_000, 280)])
-def test_viz_preprocess_matches_reference(oracle, n, step):
-    info, cloud = synth.cloud_viz(n, seed=n, step=step)
-    pp = ros.VizPreprocessor()
-    got_info, got, applied = pp.run(info, cloud)
-    want_info, want = oracle.viz_preprocess(info, cloud)
-    assert applied and got.size == want.size and np.array_equal(got, want)
-    assert _same_info(got_info, want_info)
-    if n >= 2049:
-        assert want_info.width < n  # the input really has NaNs / duplicates
-    # the handle is reusable (epoch-tagged status words, re-cleared table): same answer again, then a different cloud
-    assert np.array_equal(pp.run(info, cloud)[1], want)
-    info2, cloud2 = synth.cloud_viz(max(1, n // 3), seed=n + 1, step=step)
-    assert np.array_equal(pp.run(info2, cloud2)[1], oracle.viz_preprocess(info2, cloud2)[1])
-
-
-def test_viz_preprocess_golden(golden_viz):
-    pp = ros.VizPreprocessor()
-    for name, (info, cloud, after, kept) in golden_viz.items():
-        got_info, got, applied = pp.run(info, cloud)
-        assert applied and np.array_equal(got, kept) and _same_info(got_info, after), name
-
-
-def test_viz_preprocess_edge_cases(oracle):
-    pp = ros.VizPreprocessor()
-    # all points in one voxel / all NaN / huge coordinates (21-bit truncation of the key, lround overflow) / res 0.5 ties
-    info, cloud = synth.cloud_viz(5000, seed=3)
-    f = cloud.view(np.float32).reshape(-1, 4).copy()
-    f[:, :3] = np.float32(1.2344)
-    for case in ("one_voxel", "all_nan", "huge", "ties"):
-        g = f.copy()
-        if case == "all_nan":
-            g[:, 1] = np.nan
-        elif case == "huge":
-            rng = np.random.default_rng(1)
-            g[:, :3] = rng.choice(np.array([1.0e4, -1.0e4, 1048.575, 1048.576, -1048.577, 3.0e9, -3.0e9, 1.0e30, 2097.152, 0.0005, -0.0005, 4194.304],
-                                           dtype=np.float32), (5000, 3))
-        elif case == "ties":
-            g[:, :3] = (np.arange(15000, dtype=np.float32).reshape(5000, 3) % 7) * np.float32(0.25) - np.float32(0.75)
-        inf = info
-        if case == "ties":
-            inf = synth.cloud_viz(1, seed=1)[0]
-            inf.width = 5000
-            for k in range(3):
-                inf.fields[k].resolution = 0.5
-        got_info, got, applied = pp.run(inf, g.reshape(-1).view(np.uint8))
-        want_info, want = oracle.viz_preprocess(inf, g.reshape(-1).view(np.uint8))
-        assert applied and np.array_equal(got, want), case
-        assert _same_info(got_info, want_info), case
-    # FLOAT64 fields without a resolution get 1e-6; with one they keep it
-    rng = np.random.default_rng(2)
-    raw = rng.integers(0, 256, 32 * 1000, dtype=np.uint8)
-    raw.reshape(1000, 32)[:, :12] = np.stack(synth._lidar_xyz(1000, rng), axis=1).view(np.uint8)
-    inf = cb.EncodingInfo(width=1000, height=1, point_step=32, compression_opt=cb.CompressionOption.NONE, use_threads=False)
-    inf.fields = [cb.PointField("a", 0, FT.FLOAT32, 0.01), cb.PointField("b", 4, FT.FLOAT32, 0.01), cb.PointField("c", 8, FT.FLOAT32, 0.01),
-                  cb.PointField("t", 16, FT.FLOAT64, None), cb.PointField("u", 24, FT.FLOAT64, 0.5)]
-    got_info, got, applied = pp.run(inf, raw)
-    want_info, want = oracle.viz_preprocess(inf, raw)
-    assert applied and np.array_equal(got, want) and _same_info(got_info, want_info)
-    assert got_info.fields[3].resolution == pytest.approx(1e-6) and got_info.fields[4].resolution == 0.5
-
-
-def test_viz_preprocess_no_op_conditions(oracle):
-    pp = ros.VizPreprocessor()
-    info, cloud = synth.cloud_viz(1000, seed=1)
-    variants = []
-    a = synth.cloud_viz(1000, seed=1)[0]; a.fields[1].resolution = 0.002; variants.append(a)          # resolutions differ
-    b = synth.cloud_viz(1000, seed=1)[0]; b.fields[2].offset = 12; variants.append(b)                  # not consecutive
-    c = synth.cloud_viz(1000, seed=1)[0]; c.fields[0].type = FT.INT32; variants.append(c)              # not FLOAT32
-    d = synth.cloud_viz(1000, seed=1)[0]; d.fields = d.fields[:2]; variants.append(d)                  # fewer than 3 fields
-    e = synth.cloud_viz(1000, seed=1)[0]
-    for k in range(3):
-        e.fields[k].resolution = None
-    variants.append(e)                                                                                  # no resolution
-    for v in variants:
-        got_info, got, applied = pp.run(v, cloud)
-        assert not applied and got_info is v and np.array_equal(got, cloud)
-        want_info, want = oracle.viz_preprocess(v, cloud)
-        assert np.array_equal(want, cloud)
-    assert pp.run(info, np.zeros(0, dtype=np.uint8))[2] is False                                        # empty cloud
-
-
-def test_viz_preprocess_device_pointers(oracle):
-    from test_gpu_parity import _Dev
-    info, cloud = synth.cloud_viz(70_000, seed=11)
-    d_in, d_out = _Dev(src=cloud), _Dev(size=cloud.size)
-    new_info, kept, applied = ros.VizPreprocessor().run_device(info, d_in.ptr, cloud.size, d_out.ptr, cloud.size)
-    want_info, want = oracle.viz_preprocess(info, cloud)
-    assert applied and kept == want_info.width and np.array_equal(d_out.numpy()[:kept * 16], want)
-
-
-def test_viz_then_encode_matches_reference_pipeline(oracle):
-    # preprocessing feeds the encoder: the blob equals the reference's encode of the reference's preprocessed cloud
-    info, cloud = synth.cloud_viz(60_000, seed=21)
-    new_info, kept, _ = ros.VizPreprocessor().run(info, cloud)
-    want_info, want = oracle.viz_preprocess(info, cloud)
-    assert cb.PointcloudEncoder(new_info).encode(kept) == oracle.encode(want_info, want)
 
 
 # ---- N2: DDS envelope ----------------------------------------------------------------------------------------------------
@@ -253,3 +155,121 @@ def test_wasm_shaped_message_functions(ref):
     assert L.cldn_b200_EncodePointcloudMessage(bad.ctypes.data, bad.size, 0.001, out.ctypes.data, out.size) == 0
     assert L.cldn_b200_EncodePointcloudMessage(msg.ctypes.data, msg.size, 0.001, out.ctypes.data, 100) == 0
     assert L.cldn_b200_DecodeCompressedMessage(comp.ctypes.data, 40, raw.ctypes.data, raw.size) == 0
+
+
+# ---- N3: applyVizLossyPreprocessing ------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,step", [(1, 16), (2, 16), (255, 16), (256, 12), (2049, 16), (40_000, 16), (100_003, 32), (30_000, 22), (5_000, 280)])
+def test_viz_preprocess_matches_reference(oracle, n, step):
+    info, cloud = synth.cloud_viz(n, seed=n, step=step)
+    pp = ros.VizPreprocessor()
+    got_info, got, applied = pp.run(info, cloud)
+    want_info, want = oracle.viz_preprocess(info, cloud)
+    assert applied and got.size == want.size and np.array_equal(got, want)
+    assert _same_info(got_info, want_info)
+    if n >= 2049:
+        assert want_info.width < n  # the input really has NaNs / duplicates
+    # the handle is reusable (epoch-tagged status words, re-cleared table): same answer again, then a different cloud
+    assert np.array_equal(pp.run(info, cloud)[1], want)
+    info2, cloud2 = synth.cloud_viz(max(1, n // 3), seed=n + 1, step=step)
+    assert np.array_equal(pp.run(info2, cloud2)[1], oracle.viz_preprocess(info2, cloud2)[1])
+
+
+def test_viz_preprocess_golden(golden_viz):
+    pp = ros.VizPreprocessor()
+    for name, (info, cloud, after, kept) in golden_viz.items():
+        got_info, got, applied = pp.run(info, cloud)
+        assert applied and np.array_equal(got, kept) and _same_info(got_info, after), name
+
+
+def test_viz_preprocess_edge_cases(oracle):
+    pp = ros.VizPreprocessor()
+    # all points in one voxel / all NaN / huge coordinates (21-bit truncation of the key, lround overflow) / res 0.5 ties
+    info, cloud = synth.cloud_viz(5000, seed=3)
+    f = cloud.view(np.float32).reshape(-1, 4).copy()
+    f[:, :3] = np.float32(1.2344)
+    for case in ("one_voxel", "all_nan", "huge", "ties"):
+        g = f.copy()
+        if case == "all_nan":
+            g[:, 1] = np.nan
+        elif case == "huge":
+            rng = np.random.default_rng(1)
+            g[:, :3] = rng.choice(np.array([1.0e4, -1.0e4, 1048.575, 1048.576, -1048.577, 3.0e9, -3.0e9, 1.0e30, 2097.152, 0.0005, -0.0005, 4194.304],
+                                           dtype=np.float32), (5000, 3))
+        elif case == "ties":
+            g[:, :3] = (np.arange(15000, dtype=np.float32).reshape(5000, 3) % 7) * np.float32(0.25) - np.float32(0.75)
+        inf = info
+        if case == "ties":
+            inf = synth.cloud_viz(1, seed=1)[0]
+            inf.width = 5000
+            for k in range(3):
+                inf.fields[k].resolution = 0.5
+        got_info, got, applied = pp.run(inf, g.reshape(-1).view(np.uint8))
+        want_info, want = oracle.viz_preprocess(inf, g.reshape(-1).view(np.uint8))
+        assert applied and np.array_equal(got, want), case
+        assert _same_info(got_info, want_info), case
+    # FLOAT64 fields without a resolution get 1e-6; with one they keep it
+    rng = np.random.default_rng(2)
+    raw = rng.integers(0, 256, 32 * 1000, dtype=np.uint8)
+    raw.reshape(1000, 32)[:, :12] = np.stack(synth._lidar_xyz(1000, rng), axis=1).view(np.uint8)
+    inf = cb.EncodingInfo(width=1000, height=1, point_step=32, compression_opt=cb.CompressionOption.NONE, use_threads=False)
+    inf.fields = [cb.PointField("a", 0, FT.FLOAT32, 0.01), cb.PointField("b", 4, FT.FLOAT32, 0.01), cb.PointField("c", 8, FT.FLOAT32, 0.01),
+                  cb.PointField("t", 16, FT.FLOAT64, None), cb.PointField("u", 24, FT.FLOAT64, 0.5)]
+    got_info, got, applied = pp.run(inf, raw)
+    want_info, want = oracle.viz_preprocess(inf, raw)
+    assert applied and np.array_equal(got, want) and _same_info(got_info, want_info)
+    assert got_info.fields[3].resolution == pytest.approx(1e-6) and got_info.fields[4].resolution == 0.5
+
+
+def test_viz_preprocess_no_op_conditions(oracle):
+    pp = ros.VizPreprocessor()
+    info, cloud = synth.cloud_viz(1000, seed=1)
+    variants = []
+    a = synth.cloud_viz(1000, seed=1)[0]; a.fields[1].resolution = 0.002; variants.append(a)          # resolutions differ
+    b = synth.cloud_viz(1000, seed=1)[0]; b.fields[2].offset = 12; variants.append(b)                  # not consecutive
+    c = synth.cloud_viz(1000, seed=1)[0]; c.fields[0].type = FT.INT32; variants.append(c)              # not FLOAT32
+    d = synth.cloud_viz(1000, seed=1)[0]; d.fields = d.fields[:2]; variants.append(d)                  # fewer than 3 fields
+    e = synth.cloud_viz(1000, seed=1)[0]
+    for k in range(3):
+        e.fields[k].resolution = None
+    variants.append(e)                                                                                  # no resolution
+    for v in variants:
+        got_info, got, applied = pp.run(v, cloud)
+        assert not applied and got_info is v and np.array_equal(got, cloud)
+        want_info, want = oracle.viz_preprocess(v, cloud)
+        assert np.array_equal(want, cloud)
+    assert pp.run(info, np.zeros(0, dtype=np.uint8))[2] is False                                        # empty cloud
+
+
+def test_viz_preprocess_device_pointers(oracle):
+    from test_gpu_parity import _Dev
+    info, cloud = synth.cloud_viz(70_000, seed=11)
+    d_in, d_out = _Dev(src=cloud), _Dev(size=cloud.size)
+    new_info, kept, applied = ros.VizPreprocessor().run_device(info, d_in.ptr, cloud.size, d_out.ptr, cloud.size)
+    want_info, want = oracle.viz_preprocess(info, cloud)
+    assert applied and kept == want_info.width and np.array_equal(d_out.numpy()[:kept * 16], want)
+
+
+def test_viz_then_encode_matches_reference_pipeline(oracle):
+    # preprocessing feeds the encoder: the blob equals the reference's encode of the reference's preprocessed cloud
+    info, cloud = synth.cloud_viz(60_000, seed=21)
+    new_info, kept, _ = ros.VizPreprocessor().run(info, cloud)
+    want_info, want = oracle.viz_preprocess(info, cloud)
+    assert cb.PointcloudEncoder(new_info).encode(kept) == oracle.encode(want_info, want)
+
+
+# ---- the cloudini_ros C++ shim (include/cloudini_b200/ros_msg_utils.hpp) through its converter-step executable ---------
+def test_ros_shim_converter_step_matches_golden(lib_built, golden_ros, tmp_path):
+    # the C++ shim reproduces the reference converter's output (golden messages generated from the reference)
+    from test_cpp_shim import ROS_EXE, _compile_ros, _run_env
+    _compile_ros(lib_built)
+    for name in ("xyzi_viz", "xyz_organized", "dds_sample_4000"):
+        if name not in golden_ros:  # the sample excerpt exists only when the goldens were generated next to the reference tree
+            continue
+        g = golden_ros[name]
+        src, comp, rest = tmp_path / "in.msg", tmp_path / "out.comp", tmp_path / "out.rest"
+        src.write_bytes(g["msg"])
+        out = subprocess.run([ROS_EXE, str(src), str(comp), str(rest), repr(g["default_resolution"]), "1" if g["viz"] else "0"],
+                             capture_output=True, text=True, timeout=120, env=_run_env(tmp_path))
+        assert out.returncode == 0 and "ros_shim_convert: ok" in out.stdout, out.stdout + out.stderr
+        assert comp.read_bytes() == g["compressed"], name
+        assert rest.read_bytes() == g["restored"], name
