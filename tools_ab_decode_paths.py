@@ -23,14 +23,21 @@ def run(name, info, clouds, reps=10):
     d_out = [torch.zeros(n * step, dtype=torch.uint8, device="cuda") for _ in range(F)]
     eb = enc.make_device_batch([t.data_ptr() for t in d_in], [n * step] * F, [t.data_ptr() for t in d_blob], [cap] * F)
     sizes = enc.encode_batch_device(eb, True, want_sizes=True)
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(reps):
-        enc.encode_batch_device(eb, True)
-    enc.sync()
-    enc_ms = (time.perf_counter() - t0) / reps * 1e3
     hdr = len(enc.getHeader())
-    res = {"case": name, "frames": F, "points": n, "point_step": step, "stage1_B_per_pt": (float(np.mean(sizes)) - hdr) / n, "encode_ms": enc_ms}
+    res = {"case": name, "frames": F, "points": n, "point_step": step, "stage1_B_per_pt": (float(np.mean(sizes)) - hdr) / n}
+    for label, flag in (("encode_ms", None), ("encode_unmeasured_ms", "1")):  # the second: warp-parallel Gorilla pre-pass
+        if flag:
+            os.environ["CLDN_B200_UNMEASURED"] = flag
+        else:
+            os.environ.pop("CLDN_B200_UNMEASURED", None)
+        enc.encode_batch_device(eb, True)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            enc.encode_batch_device(eb, True)
+        enc.sync()
+        res[label] = (time.perf_counter() - t0) / reps * 1e3
+    os.environ.pop("CLDN_B200_UNMEASURED", None)
     outs = {}
     for mode in ("par", "chase", "seq"):
         os.environ["CLDN_B200_MIXED_DECODE"] = mode
