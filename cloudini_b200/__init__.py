@@ -113,6 +113,11 @@ def lib():
     L = C.CDLL(_LIB_PATH)
     vp, sz, u8p = C.c_void_p, C.c_size_t, C.POINTER(C.c_uint8)
     L.cldn_b200_version.restype = C.c_char_p
+    if b"cusim" in L.cldn_b200_version() and os.environ.get("CLDN_B200_ALLOW_EMULATION") != "tests-only":
+        # tests/cusim (the CUDA model emulated on the CPU) exists to test kernel logic without a GPU; it is not a way to
+        # run this package without one
+        raise RuntimeError(f"{_LIB_PATH} is the cusim test emulation, not the product library: refusing to load it "
+                           "(tests/test_cusim_kernels.py sets CLDN_B200_ALLOW_EMULATION=tests-only for its sub-runs)")
     L.cldn_b200_last_error.restype = C.c_char_p
     L.cldn_b200_kernel_launch_count.restype = C.c_uint64
     L.cldn_b200_info_init.argtypes = [C.POINTER(_CInfo)]

@@ -28,7 +28,7 @@ def cusim_lib(lib_built):
 
 
 def _run_gpu_suite(cusim_lib, extra_env, selection):
-    env = dict(os.environ, CLDN_B200_LIB=cusim_lib, **extra_env)
+    env = dict(os.environ, CLDN_B200_LIB=cusim_lib, CLDN_B200_ALLOW_EMULATION="tests-only", **extra_env)
     cmd = [sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", "-p", "no:cacheprovider", *selection]
     r = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=1500)
     assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-2000:]
@@ -56,6 +56,10 @@ def test_thread_order_and_cta_concurrency_do_not_matter(cusim_lib, order, worker
 def test_product_entry_points_refuse_the_emulation(cusim_lib):
     # bench.py and smoke() must never report numbers / parity from the emulated library
     env = dict(os.environ, CLDN_B200_LIB=cusim_lib)
+    env.pop("CLDN_B200_ALLOW_EMULATION", None)
+    r = subprocess.run([sys.executable, "-c", "import cloudini_b200 as cb; cb.lib()"], cwd=ROOT, env=env, capture_output=True, text=True, timeout=120)
+    assert r.returncode != 0 and "cusim test emulation" in r.stderr          # the package itself refuses it without the test flag
+    env["CLDN_B200_ALLOW_EMULATION"] = "tests-only"                           # ... and bench / smoke refuse it even with the flag
     r = subprocess.run([sys.executable, "bench.py", "--steps", "1", "--warmup", "1"], cwd=ROOT, env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode != 0 and "cusim" in (r.stdout + r.stderr)
     r = subprocess.run([sys.executable, "-c", "import __graft_entry__ as g; g.smoke()"], cwd=ROOT, env=env, capture_output=True, text=True, timeout=600)
@@ -70,7 +74,7 @@ def test_no_out_of_bounds_access_under_asan(lib_built):
     lib = build_cusim.build(asan=True)
     libasan = subprocess.check_output(["gcc", "-print-file-name=libasan.so"], text=True).strip()
     libstdcxx = subprocess.check_output(["gcc", "-print-file-name=libstdc++.so.6"], text=True).strip()
-    env = dict(os.environ, CLDN_B200_LIB=lib, LD_PRELOAD=f"{libasan} {libstdcxx}", ASAN_OPTIONS="detect_leaks=0", CLDN_B200_FUZZ="1",
+    env = dict(os.environ, CLDN_B200_LIB=lib, CLDN_B200_ALLOW_EMULATION="tests-only", LD_PRELOAD=f"{libasan} {libstdcxx}", ASAN_OPTIONS="detect_leaks=0", CLDN_B200_FUZZ="1",
                CLDN_B200_FUZZ_SEEDS="40")
     cmd = [sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", "-p", "no:cacheprovider", "-k", "not c2_full_size",
            "tests/test_gpu_parity.py", "tests/test_gpu_ros.py", "tests/test_gpu_zz_unmeasured.py"]
