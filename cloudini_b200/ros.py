@@ -81,7 +81,7 @@ class RosPointCloud2:
         fbuf = C.create_string_buffer(frame, len(frame) + 1)
         c.frame_id, c.frame_id_len = C.cast(fbuf, C.c_void_p).value, len(frame)
         c.height, c.width, c.point_step, c.row_step = self.height, self.width, self.point_step, self.row_step
-        c.is_bigendian, c.is_dense = (1 if self.is_bigendian else 0), (1 if self.is_dense else 0)
+        c.is_bigendian, c.is_dense = (1 if self.is_bigendian else 0), int(self.is_dense) & 0xFF
         if len(self.fields) > CLDN_MAX_FIELDS:
             raise RuntimeError("too many fields")
         c.n_fields = len(self.fields)
@@ -106,7 +106,10 @@ def getDeserializedPointCloudMessage(dds_msg) -> RosPointCloud2:  # ros_msg_util
     pc = RosPointCloud2(msg=raw, cdr_header=bytes(c.cdr_header), stamp_sec=c.stamp_sec, stamp_nsec=c.stamp_nsec,
                         frame_id=raw[f0:f0 + c.frame_id_len].decode("utf-8", "surrogateescape"),
                         height=c.height, width=c.width, point_step=c.point_step, row_step=c.row_step,
-                        is_bigendian=bool(c.is_bigendian), is_dense=bool(c.is_dense),
+                        is_bigendian=bool(c.is_bigendian),
+                        # a non-canonical CDR bool (byte > 1) leaves the reference the way it came in (it memcpy's the
+                        # byte into a C++ bool and back, ros_msg_utils.cpp:89,164): keep the byte, truthiness unchanged
+                        is_dense=(bool(c.is_dense) if c.is_dense <= 1 else int(c.is_dense)),
                         data=buf[d0:d0 + c.data_bytes], data_offset=d0)
     for i in range(c.n_fields):
         f = c.fields[i]

@@ -125,6 +125,8 @@ inline RosPointCloud2 getDeserializedPointCloudMessage(Cloudini::ConstBufferView
   pc.ros_header.stamp_nsec = m.stamp_nsec;
   pc.ros_header.frame_id.assign(m.frame_id, m.frame_id_len);
   pc.height = m.height; pc.width = m.width; pc.point_step = m.point_step; pc.row_step = m.row_step;
+  // a non-canonical CDR bool (byte > 1) is normalised to true here; the reference memcpy's the byte into its bool and
+  // back (undefined, in practice the byte survives) — the C ABI (cldn_ros_msg_t::is_dense) and the Python mirror carry it
   pc.is_dense = m.is_dense != 0;
   detail::fields_from_c(m.fields, m.n_fields, pc.fields);
   pc.data = Cloudini::ConstBufferView(m.data, m.data_bytes);

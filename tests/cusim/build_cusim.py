@@ -183,7 +183,11 @@ def build(force=False, opt="-O1", asan=False):
     flags = ["-std=c++17", opt, "-g", "-fPIC", "-ffp-contract=off", "-fno-strict-aliasing", "-pthread", "-I", HERE, "-w"]
     if asan:
         # + alignment: x86 tolerates a misaligned uint4 / uint64 access, the GPU raises "misaligned address"
-        flags += ["-fsanitize=address", "-fsanitize=alignment", "-fno-sanitize-recover=alignment", "-fno-omit-frame-pointer"]
+        # + shift-exponent / float-cast-overflow / integer-divide-by-zero: where C++ leaves the result open the two
+        #   machines differ (a shift by >= the width wraps on x86 and clamps on the GPU, an out-of-range float -> int
+        #   cast gives INT_MIN on x86 and saturates on the GPU), so emulated parity would prove nothing there
+        ub = "alignment,shift-exponent,float-cast-overflow,integer-divide-by-zero"
+        flags += ["-fsanitize=address", "-fsanitize=" + ub, "-fno-sanitize-recover=" + ub, "-fno-omit-frame-pointer"]
     procs = []
     for src in SOURCES + ["cusim.cpp"]:
         path = os.path.join(HERE, src) if src == "cusim.cpp" else os.path.join(GEN, src)
@@ -197,7 +201,7 @@ def build(force=False, opt="-O1", asan=False):
             sys.stderr.write(out[-6000:])
             raise RuntimeError(f"cusim: g++ failed on {src}")
         objs.append(obj)
-    subprocess.check_call(["g++", "-shared", "-pthread", *(["-fsanitize=address", "-fsanitize=alignment"] if asan else []), "-o", lib, *objs, "-ldl"])
+    subprocess.check_call(["g++", "-shared", "-pthread", *(["-fsanitize=address", "-fsanitize=alignment,shift-exponent,float-cast-overflow,integer-divide-by-zero"] if asan else []), "-o", lib, *objs, "-ldl"])
     return lib
 
 

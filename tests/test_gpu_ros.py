@@ -60,6 +60,18 @@ def test_compress_message_matches_reference(ref, viz):
             assert got == want, (name, version, len(got), len(want))
 
 
+def test_non_canonical_is_dense_byte_is_carried_like_the_reference(ref):
+    # found by tests/fuzz/fuzz_dds_messages.py: a CDR bool that is neither 0 nor 1 leaves the reference unchanged
+    msg = bytearray(synth.pointcloud2_msg(XYZI, 16, synth.cloud_viz(300, seed=2)[1]))
+    assert msg[-1] == 1  # is_dense is the last byte of a PointCloud2 message
+    msg[-1] = 0x7C
+    msg = bytes(msg)
+    comp = _convert(msg, {}, 0.001, False, cb.CompressionOption.NONE)
+    assert comp == ref.ros_compress(msg, {}, 0.001, False, 1, 0, 5)
+    back = ros.convertCompressedCloudToPointCloud2(ros.getDeserializedPointCloudMessage(comp))
+    assert back == ref.ros_decompress(comp, len(msg) + 4096) and back[-1] == 0x7C
+
+
 def test_decompress_message_matches_reference(ref):
     for name, msg, profile, res in _cases():
         comp = ref.ros_compress(msg, profile, res, False, 1, 0, 5)
