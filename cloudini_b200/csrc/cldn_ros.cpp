@@ -129,6 +129,9 @@ int cldn_b200_ros_parse(const void* dds_msg, size_t msg_bytes, cldn_ros_msg_t* o
     r.str(&off, &len);
     if (!r.ok) break;
     if (len >= CLDN_MAX_NAME) { set_error("field name longer than %d characters", CLDN_MAX_NAME - 1); return CLDN_ERR_UNSUPPORTED; }
+    // the reference keeps such a name as a std::string with the NUL inside and writes it back at full length; a C
+    // string cannot, and silently shortening it would change the bytes of the converted message
+    if (memchr(p + off, 0, len)) { set_error("field name with an embedded NUL character"); return CLDN_ERR_UNSUPPORTED; }
     cldn_field_t& f = out->fields[i];
     memcpy(f.name, p + off, len);
     f.name[len] = 0;

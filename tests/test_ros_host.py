@@ -56,6 +56,22 @@ def test_parse_errors_match_reference(ref):
             ros.getDeserializedPointCloudMessage(bytes(bad))
 
 
+def test_non_canonical_inputs_found_by_the_fuzzer():
+    good = synth.pointcloud2_msg(XYZI, 16, synth.cloud_c2(100, seed=3)[1])
+    # is_dense byte that is neither 0 nor 1: kept as it came in (the reference writes it back unchanged), still truthy
+    odd = bytearray(good)
+    odd[-1] = 0x7C
+    pc = ros.getDeserializedPointCloudMessage(bytes(odd))
+    assert pc.is_dense == 0x7C and pc.is_dense and pc._c_view()[0].is_dense == 0x7C
+    assert ros.getDeserializedPointCloudMessage(good).is_dense is True
+    # a field name whose CDR string has a NUL inside ("x\0" declared 4 bytes long): refused, not silently shortened
+    at = good.index(b"\x02\x00\x00\x00x\x00")
+    forged = bytearray(good)
+    forged[at] = 4
+    with pytest.raises(RuntimeError, match="embedded NUL"):
+        ros.getDeserializedPointCloudMessage(bytes(forged))
+
+
 def test_to_encoding_info_and_profile():
     pc = ros.getDeserializedPointCloudMessage(synth.pointcloud2_msg(VELO, 22, np.zeros(22 * 5, dtype=np.uint8)))
     ros.applyResolutionProfile({"intensity": 0.0, "time": 0.5, "ring": 2.0}, pc.fields, 0.001)
