@@ -83,7 +83,8 @@ def _rewrite_launches(text, fname):
         args = text[k + 1:e]
         smem = cfg[2] if len(cfg) > 2 else "0"
         out += text[pos:name_start]
-        out += f"::cusim::launch(dim3({cfg[0]}), dim3({cfg[1]}), static_cast<size_t>({smem}), [&]() {{ {m.group(1)}({args}); }})"
+        out += (f"::cusim::launch(dim3({cfg[0]}), dim3({cfg[1]}), static_cast<size_t>({smem}), [&]() {{ {m.group(1)}({args}); }}, "
+                f"reinterpret_cast<const void*>(+{m.group(1)}))")
         pos = e + 1
 
 

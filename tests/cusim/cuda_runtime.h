@@ -60,7 +60,11 @@ static inline ulonglong2 make_ulonglong2(unsigned long long x, unsigned long lon
 namespace cusim {
 struct ThreadCoords { uint3 tid, bid, bdim, gdim; };  // plain data: written only by the (uninstrumented) scheduler
 extern thread_local ThreadCoords tc;
-void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()>& body);
+void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()>& body, const void* kernel = nullptr);
+// the hardware's dynamic shared memory rules: 48 KB per CTA unless cudaFuncSetAttribute raised the kernel's limit
+// (at most 227 KB); a launch beyond it fails with cudaErrorInvalidValue and runs nothing
+int set_max_dyn_smem(const void* kernel, int bytes);
+int take_last_error();
 void* dyn_smem();
 // static __shared__ variables announce themselves (build_cusim.py adds the call behind every declaration) so that the
 // scheduler can fill them with 0xA5 before a CTA starts: shared memory is NOT zero on the GPU, and a kernel whose
@@ -236,7 +240,7 @@ enum { cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2, cudaEventDefault =
 namespace cusim { int sm_count(); }
 static inline const char* cudaGetErrorString(cudaError_t e) { return e == 0 ? "no error" : "cusim error"; }
 static inline const char* cudaGetErrorName(cudaError_t e) { return e == 0 ? "cudaSuccess" : "cusimError"; }
-static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+static inline cudaError_t cudaGetLastError() { return static_cast<cudaError_t>(::cusim::take_last_error()); }
 static inline cudaError_t cudaPeekAtLastError() { return cudaSuccess; }
 static inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
 static inline cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
@@ -270,5 +274,5 @@ static inline cudaError_t cudaEventDestroy(cudaEvent_t e) { free(e); return cuda
 static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t = nullptr) { return cudaSuccess; }
 static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
 static inline cudaError_t cudaEventQuery(cudaEvent_t) { return cudaSuccess; }
-template <class F> static inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }
+template <class F> static inline cudaError_t cudaFuncSetAttribute(F f, cudaFuncAttribute, int v) { return static_cast<cudaError_t>(::cusim::set_max_dyn_smem(reinterpret_cast<const void*>(f), v)); }
 template <class F> static inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int* n, F, int, size_t) { *n = 3; return cudaSuccess; }

@@ -8,6 +8,7 @@
 #include <sys/mman.h>
 
 #include <atomic>
+#include <map>
 #include <chrono>
 #include <mutex>
 #include <thread>
@@ -403,10 +404,41 @@ const uint64_t* warp_exchange(unsigned mask, uint64_t v, unsigned* arrived_mask,
   return w.slot[b];
 }
 
-void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()>& body) {
+static std::mutex g_attr_mutex;
+static std::map<const void*, size_t> g_max_dyn_smem;
+static std::atomic<int> g_last_error{0};
+
+int set_max_dyn_smem(const void* kernel, int bytes) {
+  if (bytes < 0 || bytes > 227 * 1024) return 1;  // cudaErrorInvalidValue
+  std::lock_guard<std::mutex> lock(g_attr_mutex);
+  g_max_dyn_smem[kernel] = static_cast<size_t>(bytes);
+  return 0;
+}
+int take_last_error() { return g_last_error.exchange(0); }
+
+void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()>& body, const void* kernel) {
   const uint64_t n_ctas = static_cast<uint64_t>(grid.x) * grid.y * grid.z;
   const unsigned n_threads = block.x * block.y * block.z;
-  if (n_ctas == 0 || n_threads == 0) return;
+  if (kernel) {
+    size_t allowed = 48 * 1024;
+    {
+      std::lock_guard<std::mutex> lock(g_attr_mutex);
+      auto it = g_max_dyn_smem.find(kernel);
+      if (it != g_max_dyn_smem.end() && it->second > allowed) allowed = it->second;
+    }
+    if (smem_bytes > allowed) {
+      fprintf(stderr, "cusim: launch with %zu bytes of dynamic shared memory, the kernel's limit is %zu (cudaFuncSetAttribute missing?)\n", smem_bytes, allowed);
+      g_last_error = 1;
+      return;
+    }
+  }
+  if (n_ctas == 0 || n_threads == 0 || grid.y > 65535u || grid.z > 65535u || grid.x > 0x7FFFFFFFu || n_threads > 1024u) {
+    // cudaErrorInvalidConfiguration on the GPU (an empty grid included): nothing runs and the error is left for
+    // cudaGetLastError — a caller that launches unconditionally must see it here too
+    fprintf(stderr, "cusim: invalid launch configuration: grid (%u,%u,%u) block (%u,%u,%u)\n", grid.x, grid.y, grid.z, block.x, block.y, block.z);
+    g_last_error = 9;
+    return;
+  }
   if (n_threads > kMaxThreads) { fprintf(stderr, "cusim: block of %u threads\n", n_threads); abort(); }
   unsigned workers = std::thread::hardware_concurrency();
   if (const char* e = getenv("CUSIM_WORKERS")) workers = static_cast<unsigned>(atoi(e));

@@ -114,3 +114,17 @@ def test_racecheck_under_thread_sanitizer(lib_built):
     n, r = warnings([], strict=True)
     assert r.returncode == 0 and "racecheck_main: done" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
     assert n == 0, r.stderr[-4000:]
+
+
+def test_emulation_enforces_the_dynamic_shared_memory_launch_rule(tmp_path):
+    # a launch with more than 48 KB of dynamic shared memory and no cudaFuncSetAttribute fails on the GPU with
+    # cudaErrorInvalidValue; the emulation must not be more forgiving (tests/cusim/selftest_smem_rule.cpp)
+    import platform
+    if platform.machine() != "x86_64":
+        pytest.skip("cusim's context switch is x86-64 only")
+    here = os.path.join(ROOT, "tests", "cusim")
+    exe = str(tmp_path / "smem_rule")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-pthread", "-w", "-I", here, os.path.join(here, "selftest_smem_rule.cpp"),
+                           os.path.join(here, "cusim.cpp"), "-o", exe, "-ldl"])
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0, r.stdout + r.stderr
