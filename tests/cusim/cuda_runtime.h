@@ -65,6 +65,18 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()
 // (at most 227 KB); a launch beyond it fails with cudaErrorInvalidValue and runs nothing
 int set_max_dyn_smem(const void* kernel, int bytes);
 int take_last_error();
+// "Device" memory is host memory here, so host code that dereferences a device pointer (a segmentation fault on the real
+// machine) would go unnoticed. With CUSIM_HOSTCHECK=1 every cudaMalloc region is its own mapping that is only
+// accessible while a kernel runs or a cudaMemcpy / cudaMemset is in progress (DeviceAccess); any other touch is reported
+// and aborts. Not in the sanitizer builds (they need the instrumented heap).
+void* device_alloc(size_t bytes);
+void device_free(void* p);
+void device_access_begin();
+void device_access_end();
+struct DeviceAccess {
+  DeviceAccess() { device_access_begin(); }
+  ~DeviceAccess() { device_access_end(); }
+};
 void* dyn_smem();
 // static __shared__ variables announce themselves (build_cusim.py adds the call behind every declaration) so that the
 // scheduler can fill them with 0xA5 before a CTA starts: shared memory is NOT zero on the GPU, and a kernel whose
@@ -250,19 +262,22 @@ static inline cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr a, int) 
 // fresh device memory holds whatever the previous owner left there: fill it with a pattern, so that code that relies on
 // cudaMalloc returning zeros (it often does on a fresh process, not after memory has been recycled) fails here
 static inline cudaError_t cudaMalloc(void** p, size_t n) {
+  *p = ::cusim::device_alloc(n ? n : 256);
+  return *p ? cudaSuccess : cudaErrorMemoryAllocation;
+}
+template <class T> static inline cudaError_t cudaMalloc(T** p, size_t n) { return cudaMalloc(reinterpret_cast<void**>(p), n); }
+static inline cudaError_t cudaFree(void* p) { ::cusim::device_free(p); return cudaSuccess; }
+static inline cudaError_t cudaMallocHost(void** p, size_t n) {
   if (posix_memalign(p, 256, n ? n : 256) != 0) return cudaErrorMemoryAllocation;
   memset(*p, 0xCD, n ? n : 256);
   return cudaSuccess;
 }
-template <class T> static inline cudaError_t cudaMalloc(T** p, size_t n) { return cudaMalloc(reinterpret_cast<void**>(p), n); }
-static inline cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }
-static inline cudaError_t cudaMallocHost(void** p, size_t n) { return cudaMalloc(p, n); }
-template <class T> static inline cudaError_t cudaMallocHost(T** p, size_t n) { return cudaMalloc(reinterpret_cast<void**>(p), n); }
+template <class T> static inline cudaError_t cudaMallocHost(T** p, size_t n) { return cudaMallocHost(reinterpret_cast<void**>(p), n); }
 static inline cudaError_t cudaFreeHost(void* p) { free(p); return cudaSuccess; }
-static inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { if (n) memmove(d, s, n); return cudaSuccess; }
-static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t = nullptr) { if (n) memmove(d, s, n); return cudaSuccess; }
-static inline cudaError_t cudaMemset(void* d, int v, size_t n) { if (n) memset(d, v, n); return cudaSuccess; }
-static inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t = nullptr) { if (n) memset(d, v, n); return cudaSuccess; }
+static inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { ::cusim::DeviceAccess da; if (n) memmove(d, s, n); return cudaSuccess; }
+static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t = nullptr) { ::cusim::DeviceAccess da; if (n) memmove(d, s, n); return cudaSuccess; }
+static inline cudaError_t cudaMemset(void* d, int v, size_t n) { ::cusim::DeviceAccess da; if (n) memset(d, v, n); return cudaSuccess; }
+static inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t = nullptr) { ::cusim::DeviceAccess da; if (n) memset(d, v, n); return cudaSuccess; }
 static inline cudaError_t cudaStreamCreate(cudaStream_t* s) { *s = reinterpret_cast<cudaStream_t>(malloc(8)); return cudaSuccess; }
 static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { return cudaStreamCreate(s); }
 static inline cudaError_t cudaStreamDestroy(cudaStream_t s) { free(s); return cudaSuccess; }

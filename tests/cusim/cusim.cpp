@@ -5,7 +5,9 @@
 // per-fiber report.
 #include "cuda_runtime.h"
 
+#include <signal.h>
 #include <sys/mman.h>
+#include <unistd.h>
 
 #include <atomic>
 #include <map>
@@ -404,6 +406,74 @@ const uint64_t* warp_exchange(unsigned mask, uint64_t v, unsigned* arrived_mask,
   return w.slot[b];
 }
 
+// ---- CUSIM_HOSTCHECK: device allocations the host may not touch ---------------------------------------------------------
+static std::mutex g_dev_mutex;
+static std::map<uintptr_t, size_t> g_dev_regions;  // base -> mapped bytes
+static int g_dev_access = 0;
+static bool hostcheck() {
+#if CUSIM_ASAN || defined(CUSIM_TSAN)
+  return false;
+#else
+  static const bool on = [] { const char* e = getenv("CUSIM_HOSTCHECK"); return e && e[0] == '1'; }();
+  return on;
+#endif
+}
+static void hostcheck_segv(int, siginfo_t* si, void*) {
+  const uintptr_t a = reinterpret_cast<uintptr_t>(si->si_addr);
+  bool ours = false;
+  for (const auto& r : g_dev_regions) ours |= (a >= r.first && a < r.first + r.second);  // no lock: we are about to die
+  if (ours) {
+    static const char msg[] = "cusim hostcheck: host code touched device memory outside a kernel / cudaMemcpy (a segmentation fault on the GPU box)\n";
+    (void)!write(2, msg, sizeof(msg) - 1);
+  }
+  signal(SIGSEGV, SIG_DFL);
+  raise(SIGSEGV);
+}
+void* device_alloc(size_t bytes) {
+  if (!hostcheck()) {
+    void* p = nullptr;
+    if (posix_memalign(&p, 256, bytes) != 0) return nullptr;
+    memset(p, 0xCD, bytes);
+    return p;
+  }
+  static const bool installed = [] {
+    struct sigaction sa;
+    memset(&sa, 0, sizeof(sa));
+    sa.sa_sigaction = hostcheck_segv;
+    sa.sa_flags = SA_SIGINFO;
+    sigaction(SIGSEGV, &sa, nullptr);
+    return true;
+  }();
+  (void)installed;
+  const size_t mapped = (bytes + 4095) & ~static_cast<size_t>(4095);
+  void* p = mmap(nullptr, mapped, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+  if (p == MAP_FAILED) return nullptr;
+  memset(p, 0xCD, mapped);
+  std::lock_guard<std::mutex> lock(g_dev_mutex);
+  g_dev_regions[reinterpret_cast<uintptr_t>(p)] = mapped;
+  if (g_dev_access == 0) mprotect(p, mapped, PROT_NONE);
+  return p;
+}
+void device_free(void* p) {
+  if (!p) return;
+  if (!hostcheck()) { free(p); return; }
+  std::lock_guard<std::mutex> lock(g_dev_mutex);
+  auto it = g_dev_regions.find(reinterpret_cast<uintptr_t>(p));
+  if (it == g_dev_regions.end()) { fprintf(stderr, "cusim hostcheck: cudaFree of a pointer cudaMalloc did not return\n"); abort(); }
+  munmap(p, it->second);
+  g_dev_regions.erase(it);
+}
+void device_access_begin() {
+  if (!hostcheck()) return;
+  std::lock_guard<std::mutex> lock(g_dev_mutex);
+  if (g_dev_access++ == 0) for (const auto& r : g_dev_regions) mprotect(reinterpret_cast<void*>(r.first), r.second, PROT_READ | PROT_WRITE);
+}
+void device_access_end() {
+  if (!hostcheck()) return;
+  std::lock_guard<std::mutex> lock(g_dev_mutex);
+  if (--g_dev_access == 0) for (const auto& r : g_dev_regions) mprotect(reinterpret_cast<void*>(r.first), r.second, PROT_NONE);
+}
+
 static std::mutex g_attr_mutex;
 static std::map<const void*, size_t> g_max_dyn_smem;
 static std::atomic<int> g_last_error{0};
@@ -419,6 +489,7 @@ int take_last_error() { return g_last_error.exchange(0); }
 void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()>& body, const void* kernel) {
   const uint64_t n_ctas = static_cast<uint64_t>(grid.x) * grid.y * grid.z;
   const unsigned n_threads = block.x * block.y * block.z;
+  DeviceAccess device_access;
   if (kernel) {
     size_t allowed = 48 * 1024;
     {

@@ -128,3 +128,19 @@ def test_emulation_enforces_the_dynamic_shared_memory_launch_rule(tmp_path):
                            os.path.join(here, "cusim.cpp"), "-o", exe, "-ldl"])
     r = subprocess.run([exe], capture_output=True, text=True, timeout=60)
     assert r.returncode == 0, r.stdout + r.stderr
+
+
+def test_host_code_never_dereferences_device_memory(cusim_lib, tmp_path):
+    # "device" memory is host memory in the emulation, so a host-side `*device_ptr` (a segmentation fault on the GPU box)
+    # would pass unnoticed. CUSIM_HOSTCHECK=1 maps every cudaMalloc region inaccessible except while a kernel runs or a
+    # cudaMemcpy / cudaMemset is in progress; the detector is checked against its own control first.
+    here = os.path.join(ROOT, "tests", "cusim")
+    exe = str(tmp_path / "hostcheck")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-pthread", "-w", "-I", here, os.path.join(here, "selftest_hostcheck.cpp"),
+                           os.path.join(here, "cusim.cpp"), "-o", exe, "-ldl"])
+    env = dict(os.environ, CUSIM_HOSTCHECK="1")
+    assert subprocess.run([exe], env=env, capture_output=True, text=True, timeout=60).returncode == 0
+    r = subprocess.run([exe, "--touch"], env=env, capture_output=True, text=True, timeout=60)
+    assert r.returncode != 0 and "touched device memory" in r.stderr
+    out = _run_gpu_suite(cusim_lib, {"CUSIM_HOSTCHECK": "1"}, ["tests/test_gpu_parity.py", "tests/test_gpu_ros.py", "tests/test_gpu_zz_unmeasured.py"])
+    assert " passed" in out and "failed" not in out
