@@ -69,6 +69,15 @@ int take_last_error();
 // machine) would go unnoticed. With CUSIM_HOSTCHECK=1 every cudaMalloc region is its own mapping that is only
 // accessible while a kernel runs or a cudaMemcpy / cudaMemset is in progress (DeviceAccess); any other touch is reported
 // and aborts. Not in the sanitizer builds (they need the instrumented heap).
+// CUSIM_ASYNC=1: a cudaMemcpyAsync(DeviceToHost) delivers its bytes (captured at enqueue time, i.e. in stream order) only
+// when the host synchronises with the stream — cudaStreamSynchronize, an event recorded behind it, cudaDeviceSynchronize —
+// and the destination holds 0xEE until then, so host code that reads a result before synchronising gets garbage as it
+// (sometimes) would on the GPU box.
+bool defer_d2h(void* dst, const void* src, size_t n, void* stream);
+void flush_d2h(void* stream, bool all);
+void event_record(void* event, void* stream);
+void event_sync(void* event);
+void event_forget(void* event);
 void* device_alloc(size_t bytes);
 void device_free(void* p);
 void device_access_begin();
@@ -257,7 +266,7 @@ static inline cudaError_t cudaPeekAtLastError() { return cudaSuccess; }
 static inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
 static inline cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
 static inline cudaError_t cudaSetDevice(int d) { return d == 0 ? cudaSuccess : cudaErrorInvalidValue; }
-static inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
+static inline cudaError_t cudaDeviceSynchronize() { ::cusim::flush_d2h(nullptr, true); return cudaSuccess; }
 static inline cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr a, int) { *v = (a == cudaDevAttrMultiProcessorCount) ? cusim::sm_count() : 0; return cudaSuccess; }
 // fresh device memory holds whatever the previous owner left there: fill it with a pattern, so that code that relies on
 // cudaMalloc returning zeros (it often does on a fresh process, not after memory has been recycled) fails here
@@ -273,21 +282,26 @@ static inline cudaError_t cudaMallocHost(void** p, size_t n) {
   return cudaSuccess;
 }
 template <class T> static inline cudaError_t cudaMallocHost(T** p, size_t n) { return cudaMallocHost(reinterpret_cast<void**>(p), n); }
-static inline cudaError_t cudaFreeHost(void* p) { free(p); return cudaSuccess; }
+static inline cudaError_t cudaFreeHost(void* p) { ::cusim::flush_d2h(nullptr, true); free(p); return cudaSuccess; }
 static inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { ::cusim::DeviceAccess da; if (n) memmove(d, s, n); return cudaSuccess; }
-static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t = nullptr) { ::cusim::DeviceAccess da; if (n) memmove(d, s, n); return cudaSuccess; }
+static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind kind, cudaStream_t stream = nullptr) {
+  ::cusim::DeviceAccess da;
+  if (kind == cudaMemcpyDeviceToHost && ::cusim::defer_d2h(d, s, n, stream)) return cudaSuccess;
+  if (n) memmove(d, s, n);
+  return cudaSuccess;
+}
 static inline cudaError_t cudaMemset(void* d, int v, size_t n) { ::cusim::DeviceAccess da; if (n) memset(d, v, n); return cudaSuccess; }
 static inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t = nullptr) { ::cusim::DeviceAccess da; if (n) memset(d, v, n); return cudaSuccess; }
 static inline cudaError_t cudaStreamCreate(cudaStream_t* s) { *s = reinterpret_cast<cudaStream_t>(malloc(8)); return cudaSuccess; }
 static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { return cudaStreamCreate(s); }
-static inline cudaError_t cudaStreamDestroy(cudaStream_t s) { free(s); return cudaSuccess; }
-static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+static inline cudaError_t cudaStreamDestroy(cudaStream_t s) { ::cusim::flush_d2h(s, false); free(s); return cudaSuccess; }
+static inline cudaError_t cudaStreamSynchronize(cudaStream_t s) { ::cusim::flush_d2h(s, false); return cudaSuccess; }
 static inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned = 0) { return cudaSuccess; }
 static inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = reinterpret_cast<cudaEvent_t>(malloc(8)); return cudaSuccess; }
 static inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { return cudaEventCreate(e); }
-static inline cudaError_t cudaEventDestroy(cudaEvent_t e) { free(e); return cudaSuccess; }
-static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t = nullptr) { return cudaSuccess; }
-static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
-static inline cudaError_t cudaEventQuery(cudaEvent_t) { return cudaSuccess; }
+static inline cudaError_t cudaEventDestroy(cudaEvent_t e) { ::cusim::event_forget(e); free(e); return cudaSuccess; }
+static inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t s = nullptr) { ::cusim::event_record(e, s); return cudaSuccess; }
+static inline cudaError_t cudaEventSynchronize(cudaEvent_t e) { ::cusim::event_sync(e); return cudaSuccess; }
+static inline cudaError_t cudaEventQuery(cudaEvent_t e) { ::cusim::event_sync(e); return cudaSuccess; }
 template <class F> static inline cudaError_t cudaFuncSetAttribute(F f, cudaFuncAttribute, int v) { return static_cast<cudaError_t>(::cusim::set_max_dyn_smem(reinterpret_cast<const void*>(f), v)); }
 template <class F> static inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int* n, F, int, size_t) { *n = 3; return cudaSuccess; }

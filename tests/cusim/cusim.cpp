@@ -10,6 +10,7 @@
 #include <unistd.h>
 
 #include <atomic>
+#include <deque>
 #include <map>
 #include <chrono>
 #include <mutex>
@@ -472,6 +473,56 @@ void device_access_end() {
   if (!hostcheck()) return;
   std::lock_guard<std::mutex> lock(g_dev_mutex);
   if (--g_dev_access == 0) for (const auto& r : g_dev_regions) mprotect(reinterpret_cast<void*>(r.first), r.second, PROT_NONE);
+}
+
+// ---- CUSIM_ASYNC: device-to-host copies complete at the next synchronisation with their stream -----------------------------
+struct PendingCopy { void* dst; std::vector<uint8_t> data; uint64_t seq; };
+static std::mutex g_async_mutex;
+static std::map<void*, std::deque<PendingCopy>> g_pending;         // per stream, in enqueue order
+static std::map<void*, uint64_t> g_stream_seq;                      // copies enqueued so far on a stream
+static std::map<void*, std::pair<void*, uint64_t>> g_events;        // event -> (stream, copies enqueued before the record)
+static bool async_mode() {
+  static const bool on = [] { const char* e = getenv("CUSIM_ASYNC"); return e && e[0] == '1'; }();
+  return on;
+}
+static void deliver_locked(void* stream, uint64_t up_to) {
+  auto it = g_pending.find(stream);
+  if (it == g_pending.end()) return;
+  while (!it->second.empty() && it->second.front().seq <= up_to) {
+    PendingCopy& c = it->second.front();
+    memcpy(c.dst, c.data.data(), c.data.size());
+    it->second.pop_front();
+  }
+}
+bool defer_d2h(void* dst, const void* src, size_t n, void* stream) {
+  if (!async_mode() || n == 0) return false;
+  std::lock_guard<std::mutex> lock(g_async_mutex);
+  PendingCopy c{dst, std::vector<uint8_t>(static_cast<const uint8_t*>(src), static_cast<const uint8_t*>(src) + n), ++g_stream_seq[stream]};
+  memset(dst, 0xEE, n);
+  g_pending[stream].push_back(std::move(c));
+  return true;
+}
+void flush_d2h(void* stream, bool all) {
+  if (!async_mode()) return;
+  std::lock_guard<std::mutex> lock(g_async_mutex);
+  if (all) { for (auto& q : g_pending) deliver_locked(q.first, ~0ull); return; }
+  deliver_locked(stream, ~0ull);
+}
+void event_record(void* event, void* stream) {
+  if (!async_mode()) return;
+  std::lock_guard<std::mutex> lock(g_async_mutex);
+  g_events[event] = {stream, g_stream_seq[stream]};
+}
+void event_sync(void* event) {
+  if (!async_mode()) return;
+  std::lock_guard<std::mutex> lock(g_async_mutex);
+  auto it = g_events.find(event);
+  if (it != g_events.end()) deliver_locked(it->second.first, it->second.second);
+}
+void event_forget(void* event) {
+  if (!async_mode()) return;
+  std::lock_guard<std::mutex> lock(g_async_mutex);
+  g_events.erase(event);
 }
 
 static std::mutex g_attr_mutex;

@@ -142,5 +142,9 @@ def test_host_code_never_dereferences_device_memory(cusim_lib, tmp_path):
     assert subprocess.run([exe], env=env, capture_output=True, text=True, timeout=60).returncode == 0
     r = subprocess.run([exe, "--touch"], env=env, capture_output=True, text=True, timeout=60)
     assert r.returncode != 0 and "touched device memory" in r.stderr
-    out = _run_gpu_suite(cusim_lib, {"CUSIM_HOSTCHECK": "1"}, ["tests/test_gpu_parity.py", "tests/test_gpu_ros.py", "tests/test_gpu_zz_unmeasured.py"])
+    # CUSIM_ASYNC=1: a cudaMemcpyAsync(DeviceToHost) result arrives when the host synchronises with the stream (or an
+    # event behind the copy), not before — reading it early yields 0xEE here, stale data on the GPU box
+    r = subprocess.run([exe, "--async"], env=dict(env, CUSIM_ASYNC="1"), capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0, r.stdout + r.stderr
+    out = _run_gpu_suite(cusim_lib, {"CUSIM_HOSTCHECK": "1", "CUSIM_ASYNC": "1"}, ["tests/test_gpu_parity.py", "tests/test_gpu_ros.py", "tests/test_gpu_zz_unmeasured.py"])
     assert " passed" in out and "failed" not in out
