@@ -115,7 +115,10 @@ size_t cldn_b200_max_compressed_size(const cldn_info_t* info, size_t points_coun
 
 /* ---- encoder -------------------------------------------------------------------------------------------------- */
 /* PointcloudEncoder::PointcloudEncoder(info) (cloudini.cpp:430-440). `device` = CUDA ordinal, -1 = current.
- * `stream` = cudaStream_t to bind (NULL = a private non-blocking stream owned by the handle). */
+ * `stream` = cudaStream_t to bind (NULL = a private non-blocking stream owned by the handle).
+ * Device-pointer calls (CLDN_MEM_DEVICE) are ordered on that stream only: buffers another stream is still writing —
+ * the legacy default stream included, a non-blocking stream does not wait for it — must be complete (or the
+ * producer's stream passed here) before the call. */
 int cldn_b200_encoder_create(const cldn_info_t* info, int device, void* stream, cldn_encoder_t** out);
 void cldn_b200_encoder_destroy(cldn_encoder_t* enc);
 /* getHeader() (cloudini.hpp:176-178) */

@@ -30,6 +30,9 @@ class _Dev:
             self.t = (torch.from_numpy(np.array(src, dtype=np.uint8, copy=True)).cuda() if src is not None
                       else torch.zeros(size, dtype=torch.uint8, device="cuda"))
             self.ptr = self.t.data_ptr()
+            # torch filled the tensor on ITS stream; the handles launch on their own non-blocking streams, which do not
+            # order themselves after it — make the contents final before a product kernel can touch them
+            torch.cuda.synchronize()
 
     def numpy(self):
         return self.t if _emulated() else self.t.cpu().numpy()
