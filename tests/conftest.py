@@ -13,6 +13,22 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box via gpurun)")
 
 
+def pytest_collection_modifyitems(config, items):
+    # On the GPU box a kernel that never finishes blocks the test process inside a CUDA call for good (and whatever was
+    # to run after the tests with it). Every GPU test gets a bound; method "thread" = a watchdog thread that ends the
+    # process, because a signal handler cannot interrupt a blocking C call. Not under the CPU emulation (CLDN_B200_LIB
+    # set), whose sanitizer builds are slow by design.
+    if os.environ.get("CLDN_B200_LIB"):
+        return
+    try:
+        import pytest_timeout  # noqa: F401
+    except ImportError:
+        return
+    for item in items:
+        if item.get_closest_marker("gpu") and not item.get_closest_marker("timeout"):
+            item.add_marker(pytest.mark.timeout(900, method="thread"))
+
+
 @pytest.fixture(scope="session")
 def lib_built():
     """The C-ABI library, built once per session (nvcc cross-compiles sm_100a without a GPU)."""
