@@ -217,6 +217,8 @@ static inline unsigned __funnelshift_l(unsigned lo, unsigned hi, unsigned sh) { 
 static inline unsigned __byte_perm(unsigned a, unsigned b, unsigned sel) {
   const uint64_t v = (static_cast<uint64_t>(b) << 32) | a;
   unsigned r = 0;
+  // prmt's sign-replication mode (bit 3 of a selector nibble) is not restated: refuse rather than guess
+  if (sel & 0x8888u) { fprintf(stderr, "cusim: __byte_perm selector 0x%x uses the sign-replication bit\n", sel); abort(); }
   for (int i = 0; i < 4; ++i) r |= static_cast<unsigned>((v >> (8 * ((sel >> (4 * i)) & 7u))) & 0xFFu) << (8 * i);
   return r;
 }
