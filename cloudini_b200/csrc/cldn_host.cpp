@@ -167,11 +167,21 @@ int info_from_yaml(const char* yaml, size_t len, cldn_info_t* info) {
       line = trim(line.substr(2));
     }
     size_t colon = line.find(':');
-    if (colon == std::string::npos) continue;
+    // Inside the "fields:" sequence only the exact shape EncodingInfoToYAML writes is accepted. A damaged line there
+    // ("  Q name: y", a duplicated or unknown key, text after "fields:") would otherwise be skipped and the keys that follow
+    // would land in the wrong field: the blob would decode, silently, with a layout nobody wrote.
+    if (colon == std::string::npos) {
+      if (in_fields) return fail("malformed line in the field list:", line);
+      continue;
+    }
     const std::string key = trim(line.substr(0, colon));
     const std::string val = unquote(trim(line.substr(colon + 1)));
     if (!in_fields) {
-      if (key == "fields") { in_fields = true; continue; }
+      if (key == "fields") {
+        if (!val.empty() || new_item) return fail("unexpected text after 'fields:'", val);
+        in_fields = true;
+        continue;
+      }
       if (key == "version") {
         // the reference reads this scalar into a uint8_t, i.e. as ONE CHARACTER (yaml_parser.hpp:99-108), and DecodeHeader
         // then overrides it with the two digits of the magic (cloudini.cpp:389-392): any non-empty text is accepted;
@@ -194,9 +204,18 @@ int info_from_yaml(const char* yaml, size_t len, cldn_info_t* info) {
       cur = static_cast<int>(info->n_fields++);
       memset(&info->fields[cur], 0, sizeof(cldn_field_t));
     }
-    if (cur < 0) continue;
+    if (cur < 0) return fail("field key before the first list item:", key);
     cldn_field_t& f = info->fields[cur];
-    if (key == "name") { snprintf(f.name, sizeof(f.name), "%s", val.c_str()); field_keys[cur] |= 1; }
+    const uint8_t bit = key == "name" ? 1 : key == "offset" ? 2 : key == "type" ? 4 : key == "resolution" ? 8 : 0;
+    if (bit == 0) return fail("unexpected key in the field list:", key);
+    if (field_keys[cur] & bit) return fail("duplicate key in a field:", key);
+    if (new_item != (bit == 1)) return fail("a field starts with '- name:' and nothing else does:", key);
+    if (bit != 1 && val.find(':') != std::string::npos) return fail("a second ':' in a field scalar:", val);  // YAML would see a nested mapping
+    if (key == "name") {
+      if (val.empty()) return fail("empty field name (Node is not a string)", val);
+      snprintf(f.name, sizeof(f.name), "%s", val.c_str());
+      field_keys[cur] |= 1;
+    }
     else if (key == "offset") { if (!parse_u32_prefix(val, &f.offset)) return fail("Failed to convert scalar:", val); field_keys[cur] |= 2; }
     else if (key == "type") { if (!type_from_string(val, &f.type)) return fail("Invalid FieldType string:", val); field_keys[cur] |= 4; }
     else if (key == "resolution") {

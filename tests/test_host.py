@@ -157,6 +157,21 @@ def test_no_cpu_fallback_without_gpu(lib_built):
         ros.VizPreprocessor()
 
 
+def test_damaged_field_list_is_refused_not_reinterpreted(lib_built):
+    # found by tests/fuzz/fuzz_header_text.py: a damaged line inside "fields:" used to be skipped, the keys behind it landed
+    # in the previous field and the blob decoded — silently — with a layout nobody wrote
+    info, _ = synth.cloud_c2(100, seed=1)
+    blob = cb.EncodeHeader(info)
+    assert cb.DecodeHeader(blob)[0].fields[1].name == "y"
+    for old, new in ((b"  - name: y", b"  Q name: y"), (b"  - name: y", b"E - name: y"), (b"fields:\n", b"fields:*\n"),
+                     (b"  - name: x", b"  - nam8: x"), (b"    offset: 4", b"    offset: 4\n    offset: 8"), (b"offset: 12", b"offset: 1:"),
+                     (b"  - name: z", b"  - name:  "), (b"    type: FLOAT32\n    resolution: 0.001\n  - name: y", b"    type FLOAT32\n    resolution: 0.001\n  - name: y")):
+        bad = blob.replace(old, new, 1)
+        assert bad != blob, old
+        with pytest.raises(RuntimeError):
+            cb.DecodeHeader(bad)
+
+
 def test_forged_headers_are_refused_not_executed(lib_built):
     # a field that does not fit inside the point would make the decoders write past the output buffer (the reference
     # does exactly that: field_decoder.cpp:74-78 has no bound). Planning refuses such an EncodingInfo on both sides.
