@@ -145,6 +145,7 @@ def lib():
     L.cldn_b200_decode_batch.argtypes = [vp, C.POINTER(_CInfo), sz, C.POINTER(vp), C.POINTER(sz), C.POINTER(vp),
                                          C.POINTER(sz), C.c_int, C.c_int]
     L.cldn_b200_decoder_sync.argtypes = [vp]
+    L.cldn_b200_decoder_last_stats.argtypes = [vp, C.POINTER(C.c_uint32)]
     L.cldn_b200_EncodePointcloudData.argtypes = [C.c_char_p, vp, C.c_uint32, vp, C.c_uint32]
     L.cldn_b200_EncodePointcloudData.restype = C.c_uint32
     L.cldn_b200_DecodeCompressedData.argtypes = [vp, C.c_uint32, vp, C.c_uint32]
@@ -392,3 +393,9 @@ class PointcloudDecoder:
 
     def sync(self):
         _check(lib().cldn_b200_decoder_sync(self._h))
+
+    def last_stats(self):
+        """(chunks taken by the chunk-sequential fast reader, chunks it handed to the careful reader) of the last batch."""
+        st = (C.c_uint32 * 2)()
+        _check(lib().cldn_b200_decoder_last_stats(self._h, st))
+        return int(st[0]), int(st[1])

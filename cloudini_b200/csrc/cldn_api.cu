@@ -660,9 +660,11 @@ struct cldn_decoder {
   DevBuf<uint32_t> d_chunk_tiles, d_chunk_tile_begin, d_stream_end, d_tsums, d_chunk_frame, d_tile_chunk;
   DevBuf<uint64_t> d_tstatus;
   DevBuf<uint64_t> d_trace;
-  DevBuf<uint32_t> d_counter;
+  DevBuf<uint32_t> d_counter, d_redo;
   DevBuf<uint64_t> d_chunk_desc;  // chunk-sequential kernel: self-validating chunk descriptors (see walk_frame_publish)
   uint32_t desc_tag = 0;
+  bool fast_launched = false;  // the last batch went through decode_floatn_fast_kernel (cldn_b200_decoder_last_stats)
+  uint32_t fast_chunks = 0;
   CopyPipeline pipe;
   uint32_t epoch = 0;
 };
@@ -755,7 +757,7 @@ static int decode_batch_device(cldn_decoder* d, const cldn_info_t& info, size_t 
   L.chunk_frame = nullptr; L.tile_chunk = nullptr;
   L.chunk_tiles = nullptr; L.chunk_tile_begin = nullptr; L.stream_end = nullptr; L.tstatus = nullptr; L.tsums = nullptr;
   L.tile_capacity = 0; L.tile_grid = 0; L.epoch = 0; L.trace = nullptr; L.chunk_counter = nullptr; L.sections_only = 0;
-  L.chunk_desc = nullptr; L.desc_tag = 0; L.uniform_chunks = 0;
+  L.chunk_desc = nullptr; L.desc_tag = 0; L.uniform_chunks = 0; L.redo_list = nullptr; L.redo_mode = 0;
   if (d->plan.n_sections > 0 && chunks > 0 && !(d->plan.all_varint || d->plan.n_ops == 0)) {
     // V5 with raw / XOR / Gorilla fields in the regular stream: the per-chunk parser records where the sections start
     if (int rc = d->d_stream_end.reserve(static_cast<size_t>(chunks) + 1)) return rc;
@@ -795,6 +797,8 @@ static int decode_batch_device(cldn_decoder* d, const cldn_info_t& info, size_t 
     L.epoch = d->epoch;
     if (int rc = d->d_counter.reserve(4, true)) return rc;
     L.chunk_counter = d->d_counter.p;
+    if (int rc = d->d_redo.reserve(static_cast<size_t>(chunks) + 1)) return rc;
+    L.redo_list = d->d_redo.p;
     {
       const size_t had = d->d_chunk_desc.cap;
       if (int rc = d->d_chunk_desc.reserve(2 * static_cast<size_t>(chunks) + 2)) return rc;
@@ -814,6 +818,8 @@ static int decode_batch_device(cldn_decoder* d, const cldn_info_t& info, size_t 
       L.trace = d->d_trace.p;
     }
   }
+  d->fast_launched = L.redo_list != nullptr && decode_tiles_sequential(L.n_chunks_total) && decode_fast_enabled();
+  d->fast_chunks = d->fast_launched ? L.n_chunks_total : 0u;
   if (launch_decode(d->plan, L, d->stream) < 0) { set_error("decode kernel launch failed"); return CLDN_ERR_CUDA; }
   CUDA_TRY(cudaGetLastError());
   return CLDN_OK;
@@ -850,7 +856,7 @@ void cldn_b200_decoder_destroy(cldn_decoder_t* d) {
   if (d->stream) cudaStreamSynchronize(d->stream);
   d->d_plan.release(); d->d_frames.release(); d->h_frames.release(); d->d_chunk_offsets.release(); d->d_chunk_sizes.release();
   d->d_err.release(); d->h_err.release(); d->d_in.release(); d->d_out.release();
-  d->d_chunk_tiles.release(); d->d_chunk_tile_begin.release(); d->d_stream_end.release(); d->d_tsums.release(); d->d_tstatus.release(); d->d_chunk_frame.release(); d->d_tile_chunk.release(); d->d_trace.release(); d->d_counter.release(); d->d_chunk_desc.release(); d->pipe.release();
+  d->d_chunk_tiles.release(); d->d_chunk_tile_begin.release(); d->d_stream_end.release(); d->d_tsums.release(); d->d_tstatus.release(); d->d_chunk_frame.release(); d->d_tile_chunk.release(); d->d_trace.release(); d->d_counter.release(); d->d_redo.release(); d->d_chunk_desc.release(); d->pipe.release();
   if (d->own_stream && d->stream) cudaStreamDestroy(d->stream);
   delete d;
 }
@@ -867,6 +873,19 @@ int cldn_b200_decoder_sync(cldn_decoder_t* d) {
     }
   }
   return check_device_error(d->stream, d->d_err.p, d->h_err.p);
+}
+
+int cldn_b200_decoder_last_stats(cldn_decoder_t* d, uint32_t stats[2]) {
+  if (!d || !stats) { set_error("null argument"); return CLDN_ERR_INVALID_ARGUMENT; }
+  stats[0] = stats[1] = 0;
+  CUDA_TRY(cudaSetDevice(d->device));
+  if (!d->d_counter.p || !d->fast_launched) return CLDN_OK;
+  uint32_t c[4] = {0, 0, 0, 0};
+  CUDA_TRY(cudaStreamSynchronize(d->stream));
+  CUDA_TRY(cudaMemcpy(c, d->d_counter.p, sizeof(c), cudaMemcpyDeviceToHost));
+  stats[0] = d->fast_chunks;
+  stats[1] = c[3];
+  return CLDN_OK;
 }
 
 int cldn_b200_decode_batch(cldn_decoder_t* d, const cldn_info_t* info, size_t n_frames, const void* const* payloads,

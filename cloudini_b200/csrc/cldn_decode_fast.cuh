@@ -1,0 +1,408 @@
+// DECODE of FloatN-only regular streams, large batches: the chunk-sequential FAST kernel.
+//
+// Same arithmetic as FieldDecoderFloatN_Lossy::decode (cloudini_lib/src/field_decoder.cpp:43-86) for the common case --
+// every value 1..4 bytes long, no NaN marker -- and nothing else: a chunk that holds anything the fast reader cannot
+// prove to be that case (a 0x00 NaN marker, a varint of 5+ bytes, a malformed marker, a truncated stream) is put on the
+// launch's redo list and decoded from scratch by the careful chunk-sequential kernel (cldn_decode_tiles.cu), which also
+// owns every error report. So this kernel never has to be exact about the rare cases, only about detecting them.
+//
+// Shape (what makes it ~2.4x cheaper in instructions than the kernel it fronts):
+//  * a tile is a fixed number of POINTS (128 threads x 8 points), not a fixed number of bytes: every thread decodes
+//    exactly 8 points = 8K values, fields are static, the decoded prefix values live in a static register array and no
+//    per-thread rotation / run length / division exists anywhere;
+//  * the bytes of a tile are staged once (coalesced 16-byte loads) in a window sized from the previous tile's length;
+//    terminator bits (MSB clear) are ranked with one CTA scan; every thread finds the byte behind terminator 8K*t - 1
+//    by a two-level search of the scan (warp totals, lane totals) and a select inside the owner's mask words;
+//  * one straight-line reader per value: 4-byte window at the running bit position, m ^ (m - 1) isolates the value,
+//    two add/mask steps un-spread the 7-bit groups, un-zigzag and the per-field running sum are one multiply-add;
+//  * per-field sums: warp shuffle scan + 4 warp totals (one barrier); floats are staged per warp in a 16-byte-slot
+//    array (XOR-swizzled, conflict-free both ways) and leave with 16-byte coalesced stores;
+//  * 128-thread CTAs, 7 per SM: a 32-frame batch (992 chunks) is resident at once -- no quarter-full last wave.
+// Included by cldn_decode_tiles.cu (shares its chunk walk and select table; the build has no relocatable device code).
+#pragma once
+
+namespace cldn {
+
+constexpr int kFT = 128;                     // threads per CTA
+constexpr int kFW = kFT / 32;                // warps
+constexpr int kFP = 8;                       // points per thread and tile
+constexpr int kFTilePts = kFT * kFP;         // 1024 points per tile
+constexpr int kFMaxUnits = 19;               // 8-byte units per thread (odd: conflict-free LDS.64 at any count)
+constexpr int kFLead = 16;                   // bytes in front of the window (never read as data; keeps indices > 0)
+constexpr int kFWinBytes = kFMaxUnits * kFT * 8;        // 19456
+constexpr int kFWinAlloc = kFLead + kFWinBytes + 32;    // reads run at most 7 bytes past a value's last byte
+constexpr int kFMaskWords = (kFMaxUnits * 8 + 31) / 32; // 5 words of terminator bits per thread
+static_assert(kFTilePts * 16 <= kFWinAlloc, "the float staging aliases the window");
+
+struct FastShared {
+  uint32_t wcnt[kFW];                 // terminators per warp
+  uint32_t lane_incl[kFT];            // warp-local inclusive terminator counts
+  uint32_t masks[kFMaskWords][kFT];   // terminator bits of every thread's slice (word-major: conflict-free)
+  int32_t wsum[kFW][4];               // per-warp field sums
+  uint32_t next_cursor;               // window byte index (incl. kFLead) one past the tile's last value
+  uint32_t chunk;                     // claimed chunk
+  unsigned long long desc[2];
+};
+
+// (a & m) | (b & ~m) in one LOP3; min of three in one VIMNMX3
+__device__ __forceinline__ uint32_t bitselect(uint32_t m, uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("lop3.b32 %0, %1, %2, %3, 0xCA;" : "=r"(d) : "r"(m), "r"(a), "r"(b));
+  return d;
+}
+__device__ __forceinline__ uint32_t min3_u32(uint32_t a, uint32_t b, uint32_t c) {
+#ifdef CLDN_CUSIM
+  return min(a, min(b, c));
+#else
+  return __vimin3_u32(a, b, c);
+#endif
+}
+
+__device__ __forceinline__ uint32_t nth_set_bit32(uint32_t m, uint32_t n, const uint32_t* __restrict__ table) {
+  uint32_t base = 0;
+#pragma unroll
+  for (int by = 0; by < 3; ++by) {
+    const uint32_t c = __popc(m & 0xFFu);
+    if (n >= c) { n -= c; m >>= 8; base += 8u; }
+  }
+  return base + ((__ldg(&table[m & 0xFFu]) >> (4u * n)) & 7u);
+}
+
+template <int K>
+__global__ void __launch_bounds__(kFT, 7) decode_floatn_fast_kernel(const DecLaunch L, float m0, float m1, float m2, float m3,
+                                                                    uint32_t o0, uint32_t o1, uint32_t o2, uint32_t o3) {
+  extern __shared__ __align__(16) uint8_t dyn_smem[];
+  __shared__ FastShared sh;
+  uint8_t* win = dyn_smem;                                    // kFLead + window bytes
+  uint4* ostage = reinterpret_cast<uint4*>(dyn_smem);         // aliases the window once every thread has parsed its run
+  constexpr int VPT = kFP * K;                                // values per thread
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t step = L.plan->point_step;
+  const float mul[4] = {m0, m1, m2, m3};
+  const uint32_t off[4] = {o0, o1, o2, o3};
+
+  // Whichever CTA draws ticket 0 -- by construction one that is running -- follows the u32 chunk prefixes of every
+  // frame (cloudini.cpp:645-664) and publishes them; everybody else starts decoding and only waits for its own chunk.
+  if (threadIdx.x == 0) sh.chunk = atomicAdd(L.chunk_counter + 2, 1u);
+  __syncthreads();
+  if (sh.chunk == 0u) {
+    for (uint32_t f = threadIdx.x; f < L.n_frames; f += kFT) walk_frame_publish(L, f);
+  }
+  __syncthreads();
+
+  while (true) {
+    if (threadIdx.x == 0) {
+      const uint32_t i = atomicAdd(L.chunk_counter, 1u);
+      uint32_t gc_ = i;
+      if (i < L.n_chunks_total) {
+        if (L.uniform_chunks) gc_ = (i % L.n_frames) * L.uniform_chunks + i / L.n_frames;
+        unsigned long long w0, w1;
+        do {
+          w0 = ld_relaxed_u64(L.chunk_desc + 2ull * gc_);
+          w1 = ld_relaxed_u64(L.chunk_desc + 2ull * gc_ + 1);
+        } while (static_cast<uint32_t>(w0 >> 40) != L.desc_tag || static_cast<uint32_t>(w1 >> 40) != L.desc_tag);
+        sh.desc[0] = w0 & 0xFFFFFFFFFFull;
+        sh.desc[1] = w1 & 0xFFFFFFFFull;
+      }
+      sh.chunk = gc_;
+    }
+    __syncthreads();
+    const uint32_t gc = sh.chunk;
+    if (gc >= L.n_chunks_total) return;
+    uint32_t fidx;
+    if (L.uniform_chunks) {
+      fidx = gc / L.uniform_chunks;
+    } else {
+      uint32_t lo = 0, hi = L.n_frames - 1;
+      while (lo < hi) {
+        const uint32_t mid = (lo + hi + 1) >> 1;
+        if (L.frames[mid].chunk_begin <= gc) lo = mid; else hi = mid - 1;
+      }
+      fidx = lo;
+    }
+    const DecFrame F = L.frames[fidx];
+    const uint32_t chunk = gc - F.chunk_begin;
+    const uint32_t n_points = min(kChunkPoints, F.n_points - chunk * kChunkPoints);
+    const uint8_t* body = F.payload + sh.desc[0];
+    const uint32_t size = static_cast<uint32_t>(sh.desc[1]);
+    const uint8_t* pay_end = F.payload + F.payload_bytes;
+    uint8_t* out = F.out + static_cast<size_t>(chunk) * kChunkPoints * step;
+    const bool aligned4 = (((reinterpret_cast<uintptr_t>(out) | step | o0 | o1 | o2 | (K == 4 ? o3 : 0u)) & 3u) == 0u) &&
+        o0 != CLDN_SKIP_STORE_OFFSET && o1 != CLDN_SKIP_STORE_OFFSET && o2 != CLDN_SKIP_STORE_OFFSET && (K < 4 || o3 != CLDN_SKIP_STORE_OFFSET);
+    const bool dense4 = K == 4 && aligned4 && step == 16u && o0 == 0u && o1 == 4u && o2 == 8u && o3 == 12u &&
+        (reinterpret_cast<uintptr_t>(out) & 15u) == 0u;
+    __syncthreads();  // everybody has read sh.chunk / sh.desc before thread 0 may claim the next chunk
+
+    int32_t carry[K];
+#pragma unroll
+    for (int f = 0; f < K; ++f) carry[f] = 0;
+    uint32_t cursor = 0;                      // stream byte offset of the next tile's first value
+    uint32_t est = 0;                         // bytes of the previous tile (0: none yet)
+    bool redo = (size == 0u);                 // an empty body cannot hold n_points > 0 points: the careful kernel reports it
+    for (uint32_t pt0 = 0; pt0 < n_points && !redo; pt0 += kFTilePts) {
+      const uint32_t tile_pts = min(static_cast<uint32_t>(kFTilePts), n_points - pt0);
+      const uint32_t n_vals = tile_pts * K;
+      const uint32_t remaining = size - cursor;                                // stream bytes from the cursor on
+      if (remaining < n_vals) { redo = true; break; }                          // not even one byte per value left
+      const uint8_t* first = body + cursor;
+      const uint32_t c0 = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(first) & 15u);
+      const uint8_t* abase = first - c0;                                       // window byte i <-> abase[i]
+      if (est == 0) est = static_cast<uint32_t>((static_cast<uint64_t>(size) * tile_pts) / n_points);
+      uint32_t want = c0 + est + (est >> 3) + 96u;
+      uint32_t nu = (want + 1023u) >> 10;
+      nu = nu < 3u ? 3u : (nu | 1u);
+      if (nu > kFMaxUnits) nu = kFMaxUnits;
+      uint32_t m[kFMaskWords];
+      uint32_t total, incl, cnt;
+      while (true) {
+        // ---- stage the window: coalesced 16-byte loads, vector v <-> bytes [16 v, 16 v + 16) ----
+        const uint32_t n_vec = nu * (kFT * 8 / 16);
+        for (uint32_t v = threadIdx.x; v < n_vec; v += kFT) {
+          const uint8_t* g = abase + 16u * v;
+          uint4 q;
+          if (g >= F.payload && g + 16 <= pay_end) {
+            q = __ldcs(reinterpret_cast<const uint4*>(g));
+          } else {
+            uint32_t w[4] = {0, 0, 0, 0};
+            for (int b = 0; b < 16; ++b) {
+              const uint8_t* gb = g + b;
+              const uint32_t byte = (gb >= F.payload && gb < pay_end) ? *gb : 0x80u;
+              w[b >> 2] |= byte << (8 * (b & 3));
+            }
+            q = make_uint4(w[0], w[1], w[2], w[3]);
+          }
+          *reinterpret_cast<uint4*>(win + kFLead + 16u * v) = q;
+        }
+        __syncthreads();
+        // ---- terminator bits of my slice: nu units of 8 bytes, bit i of the mask <-> slice byte i ----
+        const uint32_t slice0 = threadIdx.x * nu * 8u;                         // window byte of my first unit
+#pragma unroll
+        for (int r = 0; r < kFMaskWords; ++r) m[r] = 0;
+#pragma unroll
+        for (int u = 0; u < kFMaxUnits; ++u) {
+          if (u < static_cast<int>(nu)) {
+            const uint2 q = *reinterpret_cast<const uint2*>(win + kFLead + slice0 + 8u * u);
+            const uint32_t x0 = ~q.x & 0x80808080u, x1 = ~q.y & 0x80808080u;
+            // (x * 0x00204081) >> 28 collects bits 7, 15, 23, 31 into a nibble
+            const uint32_t b8 = ((x0 * 0x00204081u) >> 28) | (((x1 * 0x00204081u) >> 28) << 4);
+            m[u / 4] |= b8 << (8 * (u % 4));
+          }
+        }
+        // bytes in front of the cursor (thread 0, c0 < 16) and past the end of the chunk are not values
+        if (threadIdx.x == 0) m[0] &= ~((1u << c0) - 1u);
+        const uint32_t wend = c0 + remaining;                                  // window byte one past the chunk
+        if (wend < nu * (kFT * 8u)) {
+#pragma unroll
+          for (int r = 0; r < kFMaskWords; ++r) {
+            const uint32_t b0 = slice0 + 32u * r;
+            if (b0 >= wend) m[r] = 0;
+            else if (wend - b0 < 32u) m[r] &= (1u << (wend - b0)) - 1u;
+          }
+        }
+        cnt = 0;
+#pragma unroll
+        for (int r = 0; r < kFMaskWords; ++r) cnt += __popc(m[r]);
+        incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+          if (lane >= d) incl += t;
+        }
+        if (lane == 31) sh.wcnt[warp] = incl;
+        sh.lane_incl[threadIdx.x] = incl;
+#pragma unroll
+        for (int r = 0; r < kFMaskWords; ++r) sh.masks[r][threadIdx.x] = m[r];
+        __syncthreads();
+        total = 0;
+#pragma unroll
+        for (int w = 0; w < kFW; ++w) total += sh.wcnt[w];
+        if (total >= n_vals) break;
+        // too few values in the window: widen it if the chunk has more bytes, otherwise give the chunk to the careful kernel
+        if (nu >= kFMaxUnits || wend <= nu * (kFT * 8u)) { redo = true; break; }
+        nu = min(static_cast<uint32_t>(kFMaxUnits), nu + 4u);
+        __syncthreads();  // everybody has read wcnt before the next round overwrites it
+      }
+      if (redo) break;
+
+      // ---- first byte of my run: one past terminator (VPT * t - 1); thread 0 starts at the cursor ----
+      const uint32_t v0 = threadIdx.x * VPT;
+      uint32_t start = kFLead + c0;
+      if (threadIdx.x > 0 && v0 < n_vals) {
+        uint32_t e = v0 - 1u;                                                  // rank of the terminator in the tile
+        uint32_t w = 0;
+#pragma unroll
+        for (int k = 0; k < kFW - 1; ++k) {
+          const uint32_t c = sh.wcnt[k];
+          if (w == static_cast<uint32_t>(k) && e >= c) { e -= c; w = k + 1; }
+        }
+        // smallest lane of warp w whose inclusive count exceeds e
+        const uint32_t* li = sh.lane_incl + 32u * w;
+        uint32_t lo = 0;
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) {
+          if (li[lo + s - 1] <= e) lo += s;
+        }
+        const uint32_t owner = 32u * w + lo;
+        uint32_t n = e - (lo ? li[lo - 1] : 0u);                               // index among the owner's terminators
+        uint32_t word = sh.masks[0][owner], wbase = 0;
+#pragma unroll
+        for (int r = 1; r < kFMaskWords; ++r) {
+          const uint32_t c = __popc(word);
+          if (wbase == 32u * (r - 1) && n >= c) { n -= c; word = sh.masks[r][owner]; wbase = 32u * r; }
+        }
+        start = kFLead + owner * nu * 8u + wbase + nth_set_bit32(word, n, kNthBit) + 1u;
+      }
+
+      // ---- parse my 8 points; P[j][f] = sum of my deltas of field f up to and including point j ----
+      const uint32_t my_pts = v0 < n_vals ? min(static_cast<uint32_t>(kFP), (n_vals - v0) / K) : 0u;
+      if (my_pts == 0u) start = kFLead;   // nothing of mine: parse whatever is there (ignored) from a safe place
+      int32_t P[kFP][K];
+      uint32_t trk = 0xFFFFFFFFu, trs = 0xFFFFFFFFu;
+      uint32_t pb = start * 8u, pbs = 0;
+      {
+        int32_t acc[K];
+#pragma unroll
+        for (int f = 0; f < K; ++f) acc[f] = 0;
+        const uint32_t* win32 = reinterpret_cast<const uint32_t*>(win);
+#pragma unroll
+        for (int j = 0; j < kFP; ++j) {
+#pragma unroll
+          for (int f = 0; f < K; ++f) {
+            const uint32_t wi = pb >> 5;
+            const uint32_t w = __funnelshift_r(win32[wi], win32[wi + 1], pb);  // the 4 bytes at the bit position pb
+            const uint32_t t = ~w & 0x80808080u;                               // terminators among them
+            const uint32_t msk = t ^ (t - 1u);                                 // everything up to the first one (all if none)
+            uint32_t x = w & 0x7F7F7F7Fu & msk;                                // the value's payload bits
+            trk = min3_u32(trk, t, x);                                         // 0 <=> no terminator in 4 bytes, or a zero value
+            pb += __popc(msk);
+            x = x - ((x >> 1) & 0x3F803F80u);                                  // 7-bit groups -> 14-bit groups
+            const uint32_t z = bitselect(0x3FFFu, x, x >> 2);                  // -> uval = zigzag + 1 (28 bits)
+            // un-zigzag of z - 1: odd z -> +(z >> 1), even z -> -(z >> 1); bit 0 of z is bit 0 of the window
+            const int32_t sgn = static_cast<int32_t>(w & 1u) * 2 - 1;
+            acc[f] = static_cast<int32_t>(static_cast<uint32_t>(acc[f]) + (z >> 1) * static_cast<uint32_t>(sgn));
+            P[j][f] = acc[f];
+          }
+          if (static_cast<uint32_t>(j + 1) == my_pts) { trs = trk; pbs = pb; }  // my last real point
+        }
+      }
+      // a 0x00 marker / zero value or a value without a terminator inside 4 bytes among my real values
+      const bool bad = my_pts > 0u && trs == 0u;
+      int32_t tot[K];
+#pragma unroll
+      for (int f = 0; f < K; ++f) tot[f] = my_pts > 0u ? P[kFP - 1][f] : 0;
+      if (my_pts > 0u && my_pts < static_cast<uint32_t>(kFP)) {
+#pragma unroll
+        for (int j = 0; j < kFP - 1; ++j) {
+          if (static_cast<uint32_t>(j + 1) == my_pts) {
+#pragma unroll
+            for (int f = 0; f < K; ++f) tot[f] = P[j][f];
+          }
+        }
+      }
+      // the thread that owns the tile's last point knows where the next tile starts
+      if (my_pts > 0u && v0 + my_pts * K == n_vals) sh.next_cursor = pbs >> 3;
+      int32_t inc[K];
+#pragma unroll
+      for (int f = 0; f < K; ++f) inc[f] = tot[f];
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+#pragma unroll
+        for (int f = 0; f < K; ++f) {
+          const int32_t up = __shfl_up_sync(0xffffffffu, inc[f], d);
+          if (lane >= d) inc[f] = static_cast<int32_t>(static_cast<uint32_t>(inc[f]) + static_cast<uint32_t>(up));
+        }
+      }
+      if (lane == 31) {
+#pragma unroll
+        for (int f = 0; f < K; ++f) sh.wsum[warp][f] = inc[f];
+      }
+      const int any_bad = __syncthreads_or(bad ? 1 : 0);  // also: every thread is done with the window bytes
+      if (any_bad) { redo = true; break; }
+      int32_t base[K];
+#pragma unroll
+      for (int f = 0; f < K; ++f) {
+        uint32_t b = static_cast<uint32_t>(carry[f]), c = static_cast<uint32_t>(carry[f]);
+#pragma unroll
+        for (int w = 0; w < kFW; ++w) {
+          const uint32_t s = static_cast<uint32_t>(sh.wsum[w][f]);
+          if (w < warp) b += s;
+          c += s;
+        }
+        carry[f] = static_cast<int32_t>(c);
+        base[f] = static_cast<int32_t>(b + static_cast<uint32_t>(inc[f]) - static_cast<uint32_t>(tot[f]));
+      }
+      const uint32_t ncur = sh.next_cursor;
+      // ---- floats into my warp's staging slots (16 bytes per point; slot of point j of lane l: 8 l + (j ^ (l & 7))) ----
+      uint4* wst = ostage + warp * (32 * kFP);
+#pragma unroll
+      for (int j = 0; j < kFP; ++j) {
+        uint32_t fl[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int f = 0; f < K; ++f) {
+          const int32_t v = static_cast<int32_t>(static_cast<uint32_t>(base[f]) + static_cast<uint32_t>(P[j][f]));
+          fl[f] = __float_as_uint(__fmul_rn(__int2float_rn(v), mul[f]));
+        }
+        wst[8 * lane + (j ^ (lane & 7))] = make_uint4(fl[0], fl[1], fl[2], fl[3]);
+      }
+      __syncwarp();
+      // ---- copy-out: lane l of iteration i takes point 32 i + l of the warp's 256 ----
+      const uint32_t wp0 = pt0 + warp * (32 * kFP);
+      const uint32_t wn = wp0 < n_points ? min(static_cast<uint32_t>(32 * kFP), n_points - wp0) : 0u;
+#pragma unroll
+      for (int i = 0; i < kFP; ++i) {
+        const uint32_t q = 32u * i + lane;
+        if (q < wn) {
+          const uint32_t ol = q >> 3;
+          const uint4 v = wst[8 * ol + ((q & 7u) ^ (ol & 7u))];
+          uint8_t* dst = out + static_cast<size_t>(wp0 + q) * step;
+          if (dense4) {
+            __stcs(reinterpret_cast<uint4*>(dst), v);
+          } else if (aligned4) {
+            __stcs(reinterpret_cast<unsigned int*>(dst + o0), v.x);
+            __stcs(reinterpret_cast<unsigned int*>(dst + o1), v.y);
+            __stcs(reinterpret_cast<unsigned int*>(dst + o2), v.z);
+            if (K == 4) __stcs(reinterpret_cast<unsigned int*>(dst + o3), v.w);
+          } else {
+            const uint32_t vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int f = 0; f < K; ++f) {
+              if (off[f] != CLDN_SKIP_STORE_OFFSET) store_u32(dst + off[f], vv[f]);
+            }
+          }
+        }
+      }
+      const uint32_t used = ncur - (kFLead + c0);
+      est = used;
+      cursor += used;
+      __syncthreads();  // the staging slots alias the window the next tile is about to load
+    }
+    if (redo) {
+      if (threadIdx.x == 0) L.redo_list[atomicAdd(L.chunk_counter + 3, 1u)] = gc;
+    } else if (threadIdx.x == 0) {
+      L.stream_end[gc] = cursor;  // V5: the sections start here
+    }
+  }
+}
+
+size_t decode_fast_smem_bytes() { return static_cast<size_t>(kFWinAlloc); }
+
+template <int K>
+static int launch_fast(const RegOp& op, const DecLaunch& L, int sm_count, cudaStream_t stream) {
+  const size_t smem = decode_fast_smem_bytes();
+  const float m3 = K == 4 ? op.dec_mul_f[3] : 0.f;
+  const uint32_t o3 = K == 4 ? op.offset[3] : 0u;
+  auto k = decode_floatn_fast_kernel<K>;
+  if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess) return -1;
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kFT, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+  const uint32_t grid = min(L.n_chunks_total, static_cast<uint32_t>(per_sm * sm_count));
+  k<<<grid, kFT, smem, stream>>>(L, op.dec_mul_f[0], op.dec_mul_f[1], op.dec_mul_f[2], m3, op.offset[0], op.offset[1], op.offset[2], o3);
+  return 1;
+}
+
+int launch_decode_fast(const Plan& plan, const DecLaunch& L, int sm_count, cudaStream_t stream) {
+  const RegOp& op = plan.ops[0];
+  return op.lanes == 4 ? launch_fast<4>(op, L, sm_count, stream) : launch_fast<3>(op, L, sm_count, stream);
+}
+
+}  // namespace cldn

@@ -799,17 +799,25 @@ __global__ void __launch_bounds__(kDT, CLDN_SEQ_MINB * (256 / kDT)) decode_chunk
   // CTA 0 (always the first one resident) follows the u32 chunk prefixes of every frame (cloudini.cpp:645-664, the same
   // checks as walk_chunks_kernel) and publishes every chunk as soon as it is known; the other CTAs start decoding at
   // once and only wait for the descriptor of the chunk they claimed.
-  if (blockIdx.x == 0) {
+  // (redo mode: the fast kernel of the same launch has published every descriptor already)
+  if (blockIdx.x == 0 && !L.redo_mode) {
     for (uint32_t f = threadIdx.x; f < L.n_frames; f += kDT) walk_frame_publish(L, f);
   }
 
   while (true) {
     if (threadIdx.x == 0) {
-      const uint32_t i = atomicAdd(L.chunk_counter, 1u);
-      uint32_t gc_ = i;
+      uint32_t i, gc_;
+      if (L.redo_mode) {  // only the chunks the fast kernel could not prove to be "plain"
+        i = atomicAdd(L.chunk_counter + 1, 1u);
+        gc_ = i < L.chunk_counter[3] ? L.redo_list[i] : 0xFFFFFFFFu;
+        i = gc_;
+      } else {
+        i = atomicAdd(L.chunk_counter, 1u);
+        gc_ = i;
+      }
       if (i < L.n_chunks_total) {
         // equal frames: claim chunk-index-major (all chunk 0s first), so early claims never wait long for the walk
-        if (L.uniform_chunks) gc_ = (i % L.n_frames) * L.uniform_chunks + i / L.n_frames;
+        if (L.uniform_chunks && !L.redo_mode) gc_ = (i % L.n_frames) * L.uniform_chunks + i / L.n_frames;
         unsigned long long w0, w1;
         do {
           w0 = ld_relaxed_u64(L.chunk_desc + 2ull * gc_);
@@ -912,6 +920,10 @@ __global__ void __launch_bounds__(kDT, CLDN_SEQ_MINB * (256 / kDT)) decode_chunk
   }
 }
 
+}  // namespace cldn
+#include "cldn_decode_fast.cuh"
+namespace cldn {
+
 // ------------------------------------------------------------------------------------------------------------------
 size_t decode_tiles_smem_bytes() { return static_cast<size_t>(kOStageOffset) + kOStageBytes; }
 uint32_t decode_tile_bytes() { return kTB; }
@@ -927,7 +939,7 @@ static int launch_floatn_decode(const RegOp& op, const DecLaunch& L, bool sequen
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kDT, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
     const uint32_t grid = min(L.n_chunks_total, static_cast<uint32_t>(per_sm * sm_count));
-    cudaMemsetAsync(L.chunk_counter, 0, sizeof(uint32_t), stream);
+    if (!L.redo_mode) cudaMemsetAsync(L.chunk_counter, 0, 4 * sizeof(uint32_t), stream);
     k<<<grid, kDT, smem, stream>>>(L, op.dec_mul_f[0], op.dec_mul_f[1], op.dec_mul_f[2], m3, op.offset[0], op.offset[1], op.offset[2], o3);
   } else {
     auto k = decode_tiles_kernel<K>;
@@ -958,6 +970,12 @@ bool decode_tiles_sequential(uint32_t n_chunks_total) {
   return sequential;
 }
 
+// CLDN_B200_DECODE_FAST=0 keeps the careful chunk-sequential kernel alone (A/B measurements, bisecting).
+bool decode_fast_enabled() {
+  const char* e = getenv("CLDN_B200_DECODE_FAST");
+  return !(e && e[0] == '0');
+}
+
 int launch_decode_tiles(const Plan& plan, const DecLaunch& L, cudaStream_t stream) {
   const RegOp& op = plan.ops[0];
   const int sm_count = device_sm_count();
@@ -971,6 +989,17 @@ int launch_decode_tiles(const Plan& plan, const DecLaunch& L, cudaStream_t strea
   if (!sequential) {
     scan_tiles_kernel<<<1, kThreads, 0, stream>>>(L);
     ++launches;
+  }
+  if (sequential && decode_fast_enabled() && L.redo_list) {
+    // fast kernel first; whatever it could not prove plain (NaN markers, 5+ byte varints, damage) goes to the careful
+    // kernel, which is launched on a small grid and returns at once when the redo list is empty
+    cudaMemsetAsync(L.chunk_counter, 0, 4 * sizeof(uint32_t), stream);
+    if (launch_decode_fast(plan, L, sm_count, stream) < 0) return -1;
+    DecLaunch R = L;
+    R.redo_mode = 1;
+    const int n = op.lanes == 4 ? launch_floatn_decode<4>(op, R, true, sm_count, stream)
+                                : launch_floatn_decode<3>(op, R, true, sm_count, stream);
+    return n < 0 ? -1 : launches + 1 + n;
   }
   const int n = op.lanes == 4 ? launch_floatn_decode<4>(op, L, sequential, sm_count, stream)
                               : launch_floatn_decode<3>(op, L, sequential, sm_count, stream);

@@ -70,7 +70,9 @@ struct DecLaunch {
   uint64_t* tstatus;           // per tile: look-back 1 (value counts)
   uint32_t* tsums;             // per tile: 2 x 8 words, look-back 2 (aggregate record, inclusive record)
   uint64_t* trace;             // optional (CLDN_B200_TRACE): 8 globaltimer stamps per tile
-  uint32_t* chunk_counter;     // work counter of the chunk-sequential kernel
+  uint32_t* chunk_counter;     // 4 words, zeroed per launch: [0] chunk claims, [1] redo claims, [2] walk ticket, [3] redo count
+  uint32_t* redo_list;         // chunks the fast chunk-sequential kernel handed to the careful one (n_chunks_total entries)
+  uint32_t redo_mode;          // careful kernel: 1 = decode exactly the chunks of redo_list (descriptors are already published)
   uint64_t* chunk_desc;        // chunk-sequential kernel: 2 self-validating words per chunk, [tag:24][offset:40] and
                                // [tag:24][size:32], published by CTA 0 while it walks the chunk prefixes
   uint32_t desc_tag;           // tag of this launch (never 0)
@@ -91,6 +93,8 @@ bool unmeasured_kernels_enabled();
 
 int launch_decode(const Plan& host_plan, const DecLaunch& L, cudaStream_t stream);
 int launch_decode_tiles(const Plan& host_plan, const DecLaunch& L, cudaStream_t stream);
+int launch_decode_fast(const Plan& host_plan, const DecLaunch& L, int sm_count, cudaStream_t stream);
+bool decode_fast_enabled();  // CLDN_B200_DECODE_FAST=0 keeps the careful chunk-sequential kernel alone
 bool decode_tiles_sequential(uint32_t n_chunks_total);  // which of the two FloatN kernels launch_decode_tiles will pick
 uint32_t decode_tile_bytes();
 

@@ -162,6 +162,10 @@ int cldn_b200_decode_batch(cldn_decoder_t* dec, const cldn_info_t* info, size_t 
                            const void* const* payloads, const size_t* payload_bytes, void* const* outs,
                            const size_t* out_capacities, int mem, int sync);
 int cldn_b200_decoder_sync(cldn_decoder_t* dec);
+/* Diagnostics of the LAST FloatN batch decode of this handle (no reference counterpart; synchronises the stream):
+ * stats[0] = chunks claimed by the chunk-sequential reader, stats[1] = chunks it handed to the careful reader
+ * (NaN markers, varints of 5+ bytes, damaged streams). Both 0 when the batch took another kernel. */
+int cldn_b200_decoder_last_stats(cldn_decoder_t* dec, uint32_t stats[2]);
 
 /* ---- one-shot convenience, same shape as the reference's own C ABI ------------------------------------------- */
 /* cldn_EncodePointcloudData (wasm_functions.h:88-93 / wasm_functions.cpp:217-248): YAML config + raw points -> blob

@@ -32,6 +32,8 @@ PTX = {
     # bfind.u32: position of the most significant set bit, 0xffffffff for 0
     "bfind.u32": lambda outs, ins: f"{outs[0]} = (({ins[0]}) == 0u) ? 0xffffffffu : (31u - static_cast<unsigned>(__builtin_clz({ins[0]})));",
     # shr.b32: shift amounts above 31 are clamped to 32 (result 0), unlike C++
+    # lop3.b32 d, a, b, c, immLut: bit i of d = immLut[(a_i << 2) | (b_i << 1) | c_i]; the LUT is part of the template text
+    "lop3.b32": lambda outs, ins, tmpl="": f"{outs[0]} = ::cusim::lop3({ins[0]}, {ins[1]}, {ins[2]}, {tmpl.rstrip(';').split(',')[-1].strip()});",
     "shr.b32": lambda outs, ins: f"{outs[0]} = (({ins[1]}) > 31u) ? 0u : (static_cast<unsigned>({ins[0]}) >> ({ins[1]}));",
 }
 
@@ -126,7 +128,7 @@ def _rewrite_asm(text, fname):
             return [o[o.index("(") + 1:o.rindex(")")] for o in _split_top(sec) if "(" in o]
         outs = operands(sections[1]) if len(sections) > 1 else []
         ins = operands(sections[2]) if len(sections) > 2 else []
-        out += text[pos:m.start()] + PTX[key](outs, ins)
+        out += text[pos:m.start()] + (PTX[key](outs, ins, tmpl.group(1)) if key == "lop3.b32" else PTX[key](outs, ins))
         pos = end + 1
 
 

@@ -222,6 +222,13 @@ static inline unsigned __byte_perm(unsigned a, unsigned b, unsigned sel) {
   for (int i = 0; i < 4; ++i) r |= static_cast<unsigned>((v >> (8 * ((sel >> (4 * i)) & 7u))) & 0xFFu) << (8 * i);
   return r;
 }
+namespace cusim {
+static inline unsigned lop3(unsigned a, unsigned b, unsigned c, unsigned lut) {
+  unsigned r = 0;
+  for (int i = 0; i < 32; ++i) r |= ((lut >> ((((a >> i) & 1u) << 2) | (((b >> i) & 1u) << 1) | ((c >> i) & 1u))) & 1u) << i;
+  return r;
+}
+}  // namespace cusim
 static inline unsigned __umulhi(unsigned a, unsigned b) { return static_cast<unsigned>((static_cast<uint64_t>(a) * b) >> 32); }
 static inline unsigned long long __umul64hi(unsigned long long a, unsigned long long b) { return static_cast<unsigned long long>((static_cast<unsigned __int128>(a) * b) >> 64); }
 template <class T> static inline T __ldg(const T* p) { return *p; }

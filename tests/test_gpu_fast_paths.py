@@ -1,0 +1,109 @@
+"""The fast FloatN readers / writers must (a) really be the kernels that run on plain clouds and (b) hand everything
+they cannot prove plain to the careful kernels, with bytes identical to the oracle either way. All through the C ABI."""
+import numpy as np
+import pytest
+
+import cloudini_b200 as cb
+from cloudini_b200 import synth
+from test_gpu_parity import _Dev
+
+pytestmark = pytest.mark.gpu
+
+
+def _encode_all(info, clouds, oracle):
+    blobs = [oracle.encode(info, c) for c in clouds]
+    hdr = len(cb.PointcloudEncoder(info).getHeader())
+    return blobs, hdr
+
+
+def _decode_batch(info, blobs, hdr, n_bytes, fill=0):
+    dec = cb.PointcloudDecoder()
+    d_blobs = [_Dev(src=np.frombuffer(b, dtype=np.uint8)) for b in blobs]
+    d_outs = [_Dev(src=np.full(n_bytes, fill, dtype=np.uint8)) for _ in blobs]
+    batch = dec.make_device_batch([t.ptr + hdr for t in d_blobs], [len(b) - hdr for b in blobs], [t.ptr for t in d_outs], [n_bytes] * len(blobs))
+    dec.decode_batch_device(info, batch, sync=True)
+    return [d.numpy() for d in d_outs], dec.last_stats()
+
+
+def _want(oracle, blob, n_bytes, fill=0):
+    w = np.full(n_bytes, fill, dtype=np.uint8)
+    oracle.decode(blob, w)
+    return w
+
+
+@pytest.mark.parametrize("n", [1, 7, 8, 9, 1023, 1024, 1025, 32767, 32768, 32769, 40_001, 100_000])
+def test_fast_reader_takes_plain_clouds(oracle, monkeypatch, n):
+    monkeypatch.setenv("CLDN_B200_DECODE_MODE", "seq")
+    for make, step, fill in ((synth.cloud_c2, 16, 0), (synth.cloud_c1, 12, 0x5A)):
+        frames = 3
+        made = [make(n, seed=40 + k) for k in range(frames)]
+        info = made[0][0]
+        blobs, hdr = _encode_all(info, [m[1] for m in made], oracle)
+        outs, (fast, redo) = _decode_batch(info, blobs, hdr, n * step, fill)
+        chunks = frames * ((n + 32767) // 32768)
+        assert (fast, redo) == (chunks, 0), (fast, redo, chunks)
+        for b, o in zip(blobs, outs):
+            assert np.array_equal(o, _want(oracle, b, n * step, fill))
+
+
+def test_fast_reader_hands_over_what_it_cannot_prove_plain(oracle, monkeypatch):
+    monkeypatch.setenv("CLDN_B200_DECODE_MODE", "seq")
+    n = 70_000
+    info, plain = synth.cloud_c2(n, seed=5)
+    pts = plain.view(np.float32).reshape(n, 4).copy()
+    nan_cloud = pts.copy(); nan_cloud[40_000, 1] = np.nan                 # one NaN marker in chunk 1
+    wide_cloud = pts.copy(); wide_cloud[100, 0] = np.float32(3.0e6)        # a 5-byte varint (and the jump back) in chunk 0
+    tail_cloud = pts.copy(); tail_cloud[n - 1, 3] = np.nan                 # NaN in the very last value of the stream
+    clouds = [plain, nan_cloud.view(np.uint8).reshape(-1), wide_cloud.view(np.uint8).reshape(-1), tail_cloud.view(np.uint8).reshape(-1)]
+    blobs, hdr = _encode_all(info, clouds, oracle)
+    outs, (fast, redo) = _decode_batch(info, blobs, hdr, n * 16, 0x11)
+    assert fast == 4 * 3 and redo == 3, (fast, redo)
+    for b, o in zip(blobs, outs):
+        assert np.array_equal(o, _want(oracle, b, n * 16, 0x11))
+
+
+def test_fast_reader_on_damaged_streams_reports_like_the_careful_one(oracle, monkeypatch):
+    # truncated bodies / forged sizes: the fast reader must not decide anything itself; the error and its message come
+    # from the careful kernel, exactly as with CLDN_B200_DECODE_FAST=0
+    n = 50_000
+    info, cloud = synth.cloud_c2(n, seed=6)
+    blob = oracle.encode(info, cloud)
+    hdr = len(cb.PointcloudEncoder(info).getHeader())
+    rng = np.random.default_rng(7)
+    for trial in range(12):
+        bad = bytearray(blob)
+        kind = trial % 3
+        if kind == 0:      # cut the payload
+            bad = bad[:hdr + int(rng.integers(5, len(blob) - hdr))]
+        elif kind == 1:    # flip bytes inside a chunk
+            for _ in range(4):
+                bad[hdr + 8 + int(rng.integers(0, len(blob) - hdr - 8))] = int(rng.integers(0, 256))
+        else:              # zero byte (NaN marker) in the middle
+            bad[hdr + 4 + int(rng.integers(0, 100_000))] = 0
+        results = []
+        for fastflag in ("1", "0"):
+            monkeypatch.setenv("CLDN_B200_DECODE_MODE", "seq")
+            monkeypatch.setenv("CLDN_B200_DECODE_FAST", fastflag)
+            out = np.full(n * 16, 0x33, dtype=np.uint8)
+            try:
+                cb.PointcloudDecoder().decode(info, bytes(bad[hdr:]), out)
+                results.append(("ok", out.tobytes()))
+            except RuntimeError as e:
+                results.append(("err", str(e)))
+        assert results[0][0] == results[1][0], (trial, results[0][0], results[1][0])
+        if results[0][0] == "ok":
+            assert results[0][1] == results[1][1], trial
+        else:
+            assert results[0][1] == results[1][1], (trial, results[0][1], results[1][1])
+
+
+def test_fast_reader_layouts(oracle, monkeypatch):
+    # padded / unaligned outputs and skipped fields go through the generic store path of the same kernel
+    monkeypatch.setenv("CLDN_B200_DECODE_MODE", "seq")
+    for n in (5_000, 66_000):
+        info, cloud = synth.cloud_c3(n, seed=n, version=5)   # XYZ + V5 sections, step 32
+        blob = oracle.encode(info, cloud)
+        dinfo, hdr = cb.DecodeHeader(blob)
+        got = np.full(n * 32, 0x77, dtype=np.uint8)
+        cb.PointcloudDecoder().decode(dinfo, blob[hdr:], got)
+        assert np.array_equal(got, _want(oracle, blob, n * 32, 0x77))
