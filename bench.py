@@ -36,7 +36,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-extras", action="store_true", help="skip the secondary measurements (tools_extras_bench.py, child process)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary measurements (tools/extras_bench.py, child process)")
     ap.add_argument("--e2e-frames", type=int, default=8, help="frames per end-to-end step (pinned host buffers)")
     return ap.parse_args()
 
@@ -174,7 +174,7 @@ def run_extras(timeout_s=240):
     """Secondary measurements (N3 kernels, C3 / V5 sections, DDS converter step) in a CHILD process: whatever happens
     there — exception, CUDA error, crash, timeout — ends up as a string in `extras`, never in the headline numbers."""
     try:
-        r = subprocess.run([sys.executable, os.path.join(ROOT, "tools_extras_bench.py")], capture_output=True, text=True, timeout=timeout_s)
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "extras_bench.py")], capture_output=True, text=True, timeout=timeout_s)
         lines = [ln for ln in r.stdout.strip().splitlines() if ln.startswith("{")]
         if r.returncode != 0 or not lines:
             return {"error": f"exit {r.returncode}: {(r.stderr or r.stdout)[-300:]}"}

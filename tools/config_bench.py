@@ -1,7 +1,7 @@
 """Device-resident encode / decode timing of the BASELINE.json configs C1..C4 (stage 1 only), with an oracle parity
 check of frame 0. Prints one JSON line per config. Development / reporting aid (bench.py stays the contract)."""
 import json, os, sys
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import cloudini_b200 as cb
 from cloudini_b200 import synth

@@ -1,5 +1,5 @@
 #!/usr/bin/env bash
-# usage: tools_quick_bench.sh <label>   (env selects variants) — prints encode/decode ms per 32-frame step
+# usage: tools/quick_bench.sh <label>   (env selects variants) — prints encode/decode ms per 32-frame step
 timeout 150 python bench.py --steps 20 --warmup 3 --no-e2e --no-extras --cpu-seconds 0.2 > /tmp/vb.out 2>&1
 tail -1 /tmp/vb.out > /tmp/vb.json
 python - "$1" <<'PY'

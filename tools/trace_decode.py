@@ -1,7 +1,7 @@
 """Development aid: decodes 8 frames once with CLDN_B200_TRACE and prints per-phase tile latencies."""
 import os, sys
 os.environ["CLDN_B200_TRACE"] = "/tmp/cldn_trace.bin"
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import cloudini_b200 as cb
 from cloudini_b200 import synth
