@@ -338,6 +338,30 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* s
   return res;
 }
 
+// The same for a CTA of NT threads (NT a multiple of 32, <= 1024). `scratch` = NT/32 + 1 words.
+template <int NT>
+__device__ __forceinline__ uint32_t block_exclusive_scan_n(uint32_t v, uint32_t* scratch, uint32_t* total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t inc = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= d) inc += t;
+  }
+  if (lane == 31) scratch[warp] = inc;
+  __syncthreads();
+  uint32_t before = 0, all = 0;
+#pragma unroll
+  for (int w = 0; w < NT / 32; ++w) {
+    const uint32_t c = scratch[w];
+    if (w < warp) before += c;
+    all += c;
+  }
+  __syncthreads();  // scratch may be reused at once
+  *total = all;
+  return before + inc - v;
+}
+
 // ---- tile status word for the decoupled look-back ---------------------------------------------------------------
 // [63:62] flag (0 = invalid, 1 = tile aggregate, 2 = inclusive prefix)   [61:40] launch epoch   [39:0] byte count
 constexpr uint64_t kFlagAgg = 1ull, kFlagIncl = 2ull;

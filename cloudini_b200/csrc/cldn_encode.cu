@@ -607,8 +607,13 @@ int launch_gorilla_prepass(const Plan& plan, const EncLaunch& L, cudaStream_t st
 // Header + size for a batch that only holds empty frames (no tile exists to do it).
 __global__ void empty_frames_kernel(const EncLaunch L) { handle_empty_frames(L); }
 
+}  // namespace cldn
+#include "cldn_encode_fast.cuh"
+namespace cldn {
+
 // Points per tile for a plan: the largest I in {8,4,2,1} whose staging buffer fits comfortably.
 uint32_t choose_tile_points(const Plan& plan) {
+  if (encode_fast_applies(plan)) return encode_fast_tile_points();
   if (plan.floatn_only) return floatn_variant() == 2 ? kThreads * 4 : kThreads * 8;
   const size_t budget = 96 * 1024;
   for (int I = 8; I >= 1; I >>= 1) {
@@ -630,6 +635,9 @@ int launch_encode_regular(const Plan& plan, const EncLaunch& L, cudaStream_t str
       const float m = plan.ops[0].enc_mul_f[k];
       if (!(m > 0.0f) || m > 3.0e38f) muls_ok = false;
     }
+  }
+  if (!(force && force[0] == '1') && encode_fast_applies(plan) && L.tile_points == encode_fast_tile_points()) {
+    return launch_encode_fast(plan, L, stream);
   }
   if (plan.floatn_only && muls_ok && !(force && force[0] == '1')) {
     const RegOp& op = plan.ops[0];

@@ -1,0 +1,328 @@
+// ENCODE of packed XYZI float32x4 clouds (point_step 16, 16-byte aligned frames): the FAST FloatN kernel.
+// Included by cldn_encode.cu (shares finish_tile / find_frame; the build has no relocatable device code).
+//
+// Same bytes as FieldEncoderFloatN_Lossy::encode (cloudini_lib/src/field_encoder.cpp:42-91) + WriteStage1Chunk's framing
+// (chunk_writer.cpp:27-48). Shape:
+//  * thread-blocked points: a thread owns 8 consecutive points of a 1024-point tile, so the previous point is a
+//    register (no shuffle / select per value) and the thread's bytes are ONE contiguous run of the output;
+//  * the tile is loaded with coalesced 16-byte loads and transposed through shared memory inside each warp
+//    (16-byte slots, XOR-swizzled: conflict-free both ways);
+//  * pass 1 (per value: FMUL, F2I, |s| tracking with max.NaN, delta, zigzag + 1, 7-bit groups -> bytes with two
+//    add/mask steps, continuation flags from the top bit) keeps the finished LEB128 words in registers and sums their
+//    lengths; one warp scan + 4 warp totals give every thread its byte offset;
+//  * pass 2 streams the words through a 64-bit register window and flushes aligned 32-bit words straight to their final
+//    place in the staging buffer: a thread starts its window with the last bytes of its predecessor (every thread
+//    publishes the last 4 bytes of its run before the scan), so words shared by two threads are written once, whole;
+//  * a CTA walks a group of 4 consecutive tiles of one frame: one decoupled look-back per group, the other tiles know
+//    their prefix locally and publish it as inclusive at once.
+// Anything the 4-byte fast path cannot represent -- NaN / inf input, |v * mul| >= 2^25 (so that every delta fits 4
+// varint bytes and no product reaches the x86 "integer indefinite" range), a partial tile -- sends the TILE to the exact
+// byte-wise path below, which evaluates everything like the reference does.
+#pragma once
+
+namespace cldn {
+
+constexpr int kET = 128;                  // threads per CTA
+constexpr int kEW = kET / 32;
+constexpr int kEP = 8;                    // points per thread and tile
+constexpr int kETilePts = kET * kEP;      // 1024
+constexpr int kEGroup = 4;                // tiles per CTA (uniform batches)
+constexpr int kEStageBytes = kETilePts * 20 + 64;  // worst case of the careful path: 5 bytes per value
+
+struct EncFastShared {
+  uint32_t wtot[kEW];        // bytes per warp
+  uint32_t wtail[kEW];       // last 4 bytes of every warp's run (top byte = most recent)
+  unsigned long long excl;   // look-back result of the group's first tile
+  uint32_t scan[kET / 32 + 1];
+};
+
+__device__ __forceinline__ float max_nan(float a, float b) {  // NaN if either is NaN (fmaxf would drop it)
+  float d;
+  asm("max.NaN.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b));
+  return d;
+}
+__device__ __forceinline__ uint32_t top_bit(uint32_t x) {  // index of the most significant set bit; 0xFFFFFFFF for 0
+  uint32_t b;
+  asm("bfind.u32 %0, %1;" : "=r"(b) : "r"(x));
+  return b;
+}
+__device__ __forceinline__ uint32_t shl_clamp(uint32_t v, uint32_t n) {  // v << n, 0 for n >= 32 (PTX semantics, not C++'s)
+  uint32_t d;
+  asm("shl.b32 %0, %1, %2;" : "=r"(d) : "r"(v), "r"(n));
+  return d;
+}
+__device__ __forceinline__ uint32_t bitselect_e(uint32_t m, uint32_t a, uint32_t b) {  // (a & m) | (b & ~m), one LOP3
+  uint32_t d;
+  asm("lop3.b32 %0, %1, %2, %3, 0xCA;" : "=r"(d) : "r"(m), "r"(a), "r"(b));
+  return d;
+}
+
+// Exact byte-wise evaluation of one tile (thread t owns points 8 t .. 8 t + 7), like the reference (field_encoder.cpp:42-91).
+// Returns the tile's byte count; the bytes are in `stage`. All threads of the CTA call it.
+template <int N>
+__device__ __noinline__ uint32_t encode_tile_careful(const EncFrame& F, const FloatNParams& P, uint32_t tile_p0, uint8_t* stage,
+                                                     uint32_t* scan_scratch) {
+  const uint32_t step = P.point_step;
+  uint32_t len[kEP];
+  uint32_t mine = 0;
+#pragma unroll 1
+  for (int i = 0; i < kEP; ++i) {
+    const uint32_t p = tile_p0 + threadIdx.x * kEP + i;
+    uint32_t l = 0;
+    if (p < F.n_points) {
+      const uint8_t* pt = F.in + static_cast<size_t>(p) * step;
+      const uint8_t* prevp = (p % kChunkPoints) ? pt - step : nullptr;
+#pragma unroll
+      for (int k = 0; k < N; ++k) {
+        const float x = __uint_as_float(load_u32(pt + P.offset[k]));
+        if (isnan(x)) { l += 1; continue; }
+        const int32_t q = quant_i32_x86(x, P.mul[k]);
+        int32_t pq = 0;
+        if (prevp) {
+          const float px = __uint_as_float(load_u32(prevp + P.offset[k]));
+          if (!isnan(px)) pq = quant_i32_x86(px, P.mul[k]);
+        }
+        const int32_t d = static_cast<int32_t>(static_cast<uint32_t>(q) - static_cast<uint32_t>(pq));
+        l += varint_len(zigzag_plus1(static_cast<int64_t>(d)));
+      }
+    }
+    len[i] = l;
+    mine += l;
+  }
+  __syncthreads();  // the staging buffer may still hold the transposed input other warps are reading
+  uint32_t total;
+  uint32_t off = block_exclusive_scan_n<kET>(mine, scan_scratch, &total);
+#pragma unroll 1
+  for (int i = 0; i < kEP; ++i) {
+    const uint32_t p = tile_p0 + threadIdx.x * kEP + i;
+    if (p < F.n_points) {
+      const uint8_t* pt = F.in + static_cast<size_t>(p) * step;
+      const uint8_t* prevp = (p % kChunkPoints) ? pt - step : nullptr;
+      ByteSink bs{stage + off};
+#pragma unroll
+      for (int k = 0; k < N; ++k) {
+        const float x = __uint_as_float(load_u32(pt + P.offset[k]));
+        if (isnan(x)) { bs.put_byte(0); continue; }
+        const int32_t q = quant_i32_x86(x, P.mul[k]);
+        int32_t pq = 0;
+        if (prevp) {
+          const float px = __uint_as_float(load_u32(prevp + P.offset[k]));
+          if (!isnan(px)) pq = quant_i32_x86(px, P.mul[k]);
+        }
+        const int32_t d = static_cast<int32_t>(static_cast<uint32_t>(q) - static_cast<uint32_t>(pq));
+        bs.put_varint(zigzag_plus1(static_cast<int64_t>(d)));
+      }
+      off += len[i];
+    }
+  }
+  return total;
+}
+
+// group = number of consecutive tiles one CTA walks (kEGroup for uniform batches, 1 otherwise)
+__global__ void __launch_bounds__(kET, 7) encode_xyzi_fast_kernel(const EncLaunch L, const FloatNParams P, const uint32_t group) {
+  extern __shared__ __align__(16) uint8_t dyn_smem[];
+  __shared__ EncFastShared sh;
+  uint8_t* stage = dyn_smem;                                 // output bytes of the tile
+  uint32_t* stage32 = reinterpret_cast<uint32_t*>(dyn_smem);
+  uint4* slots = reinterpret_cast<uint4*>(dyn_smem);        // transposed input (aliases the staging buffer)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+  if (blockIdx.x == 0) handle_empty_frames(L);
+  uint32_t fi, t0;
+  if (L.uniform_tiles) {
+    fi = blockIdx.x % L.n_frames;
+    t0 = (blockIdx.x / L.n_frames) * group;
+  } else {
+    fi = find_frame(L.frames, L.n_frames, blockIdx.x);
+    t0 = blockIdx.x - L.frames[fi].tile_begin;
+  }
+  const EncFrame F = L.frames[fi];
+  const float4* in4 = reinterpret_cast<const float4*>(F.in);
+  const bool aligned16 = (L.flags & kEncInputsAligned16) != 0u;
+  uint64_t excl = 0;       // data bytes of all earlier tiles of the frame (known after the first tile's look-back)
+
+  for (uint32_t g = 0; g < group; ++g) {
+    const uint32_t t = t0 + g;
+    if (t >= F.n_tiles) break;
+    const uint32_t tile = F.tile_begin + t;
+    const uint32_t tile_p0 = t * kETilePts;
+    const bool full = tile_p0 + kETilePts <= F.n_points;
+    uint32_t total = 0;
+    bool fast = full;
+    uint32_t X[kEP][4];
+    uint32_t mine = 0, tail4 = 0;
+    if (full) {
+      // ---- load + transpose inside the warp: lane l of iteration i loads point 32 i + l of the warp's 256 ----
+      const uint32_t wp0 = tile_p0 + warp * (32 * kEP);
+      uint4* wsl = slots + warp * (32 * kEP);
+#pragma unroll
+      for (int i = 0; i < kEP; ++i) {
+        const uint32_t q = 32u * i + lane;
+        float4 v;
+        if (aligned16) {
+          v = __ldcs(in4 + wp0 + q);
+        } else {
+          const uint8_t* pt = F.in + static_cast<size_t>(wp0 + q) * 16u;
+          v = make_float4(__uint_as_float(load_u32(pt)), __uint_as_float(load_u32(pt + 4)), __uint_as_float(load_u32(pt + 8)), __uint_as_float(load_u32(pt + 12)));
+        }
+        const uint32_t ol = q >> 3;  // owner lane; slot of point j of lane l: 8 l + (j ^ (l & 7))
+        wsl[8 * ol + ((q & 7u) ^ (ol & 7u))] = make_uint4(__float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w));
+      }
+      // previous point of my first point: 0 at a chunk start, else quantised like any point
+      const uint32_t p_first = wp0 + lane * kEP;
+      float4 pv = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (lane == 0 && (p_first % kChunkPoints) != 0) {
+        const uint8_t* pt = F.in + static_cast<size_t>(p_first - 1) * 16u;
+        pv = make_float4(__uint_as_float(load_u32(pt)), __uint_as_float(load_u32(pt + 4)), __uint_as_float(load_u32(pt + 8)), __uint_as_float(load_u32(pt + 12)));
+      }
+      __syncwarp();
+      if (lane != 0) {
+        const uint32_t pl = lane - 1;
+        const uint4 u = wsl[8 * pl + (7u ^ (pl & 7u))];
+        pv = make_float4(__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z), __uint_as_float(u.w));
+      }
+      float trk = 0.0f;
+      int32_t prev[4];
+      {
+        const float pf[4] = {pv.x, pv.y, pv.z, pv.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float s = __fmul_rn(pf[k], P.mul[k]);
+          trk = max_nan(trk, fabsf(s));
+          prev[k] = __float2int_rn(s);
+        }
+      }
+      // ---- pass 1: LEB128 words of my 32 values + their total length ----
+      uint32_t nbl[3] = {0, 0, 0};  // bit lengths of my last three values (for the tail word)
+#pragma unroll
+      for (int j = 0; j < kEP; ++j) {
+        const uint4 u = wsl[8 * lane + (j ^ (lane & 7))];
+        const float pf[4] = {__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z), __uint_as_float(u.w)};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float s = __fmul_rn(pf[k], P.mul[k]);   // _mm_mul_ps: IEEE RN, never contracted
+          trk = max_nan(trk, fabsf(s));
+          const int32_t q = __float2int_rn(s);          // cvtps2dq under the default MXCSR: ties to even
+          const uint32_t d = static_cast<uint32_t>(q) - static_cast<uint32_t>(prev[k]);
+          prev[k] = q;
+          const uint32_t zz1 = ((d << 1) ^ static_cast<uint32_t>(static_cast<int32_t>(d) >> 31)) + 1u;  // < 2^28 on the fast path
+          // 7-bit groups -> bytes: 14-bit halves into 16-bit lanes, then the upper 7 bits of each lane one bit up
+          uint32_t x = (zz1 & 0xFFFFC000u) * 3u + zz1;           // lo14 + hi14 * 2^16 (one LOP3 + one IMAD)
+          x = x + (x & 0x3F803F80u);
+          const uint32_t b = top_bit(x);                           // inside the value's last byte (garbage tiles: x may be 0)
+          x |= (shl_clamp(1u, b) - 1u) & 0x00808080u;              // continuation flags on every byte below it
+          X[j][k] = x;
+          mine += b >> 3;
+          if (j == kEP - 1 && k >= 1) nbl[k - 1] = (b & 0x18u) + 8u;
+        }
+      }
+      mine += kEP * 4;
+      // last 4 bytes of my run (top byte = most recent): the successor starts its window with them
+      tail4 = __funnelshift_rc(tail4, X[kEP - 1][1], nbl[0]);
+      tail4 = __funnelshift_rc(tail4, X[kEP - 1][2], nbl[1]);
+      tail4 = __funnelshift_rc(tail4, X[kEP - 1][3], nbl[2]);
+      fast = trk < 33554432.0f;  // 2^25; false for NaN
+    }
+    // ---- offsets: warp scan + warp totals ----
+    uint32_t inc = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t up = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= d) inc += up;
+    }
+    uint32_t ptail = __shfl_up_sync(0xffffffffu, tail4, 1);
+    if (lane == 31) { sh.wtot[warp] = inc; sh.wtail[warp] = tail4; }
+    const int any_slow = __syncthreads_or(fast ? 0 : 1);  // also: every warp is done with its transposed input
+    LookbackPoll lb;
+    if (!any_slow) {
+      uint32_t wbase = 0;
+#pragma unroll
+      for (int w = 0; w < kEW; ++w) {
+        const uint32_t c = sh.wtot[w];
+        if (w < warp) wbase += c;
+        total += c;
+      }
+      // the tile's size is final: publish it before the bytes are packed, so that successors never wait for pass 2
+      if (g == 0 && warp == 0) {
+        lb.begin(L.status, F.tile_begin, tile, L.epoch, total);
+        lb.issue(L.status, F.tile_begin, L.epoch);
+      }
+      if (lane == 0) ptail = warp > 0 ? sh.wtail[warp - 1] : 0u;
+      const uint32_t off = wbase + inc - mine;
+      // ---- pass 2: 64-bit window, aligned word flushes ----
+      const uint32_t r = off & 3u;
+      uint32_t pos = 8u * r;
+      uint32_t lo = __funnelshift_rc(ptail, 0u, 32u - pos);   // the last r bytes of the predecessor (0 for r == 0)
+      uint32_t* wp = stage32 + (off >> 2);
+#pragma unroll
+      for (int j = 0; j < kEP; ++j) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint32_t x = X[j][k];
+          const uint32_t b = top_bit(x);
+          lo |= x << pos;
+          const uint32_t hi = __funnelshift_l(x, 0u, pos);   // x >> (32 - pos), 0 for pos == 0
+          pos += (b & 0x18u) + 8u;
+          if (pos >= 32u) { *wp++ = lo; lo = hi; pos -= 32u; }
+        }
+      }
+      if (threadIdx.x == kET - 1 && pos != 0u) *wp = lo;     // nobody follows the tile's last thread
+    } else {
+      total = encode_tile_careful<4>(F, P, tile_p0, stage, sh.scan);
+      if (g == 0 && warp == 0) lb.begin(L.status, F.tile_begin, tile, L.epoch, total);
+    }
+    // ---- the tile's place in the frame: look-back for the first tile of the group, local knowledge afterwards ----
+    if (g == 0) {
+      if (warp == 0) {
+        const uint64_t e = lb.finish(L.status, F.tile_begin, tile, L.epoch, total);
+        if (lane == 0) sh.excl = e;
+      }
+    } else if (threadIdx.x == 0) {
+      st_relaxed_u64(L.status + tile, pack_status(kFlagIncl, L.epoch, excl + total));
+    }
+    __syncthreads();  // staged bytes + sh.excl complete
+    if (g == 0) excl = sh.excl;
+    finish_tile<kETilePts>(L, F, fi, t, stage, total, excl);
+    excl += total;
+    __syncthreads();  // the next tile's transposed input overwrites the staging buffer
+  }
+}
+
+static bool encode_fast_enabled() {
+  const char* e = getenv("CLDN_B200_ENC_FAST");
+  return !(e && e[0] == '0');
+}
+// Plans / batches the fast kernel takes: exactly one FloatN op over packed float32x4 at offsets 0,4,8,12 of a 16-byte point.
+bool encode_fast_applies(const Plan& plan) {
+  if (!plan.floatn_only || !encode_fast_enabled()) return false;
+  const RegOp& op = plan.ops[0];
+  if (!(op.lanes == 4 && plan.point_step == 16 && op.offset[0] == 0 && op.offset[1] == 4 && op.offset[2] == 8 && op.offset[3] == 12)) return false;
+  for (int k = 0; k < 4; ++k) {
+    const float m = op.enc_mul_f[k];
+    if (!(m > 0.0f) || m > 3.0e38f) return false;  // the |s| < 2^25 test must imply a finite, non-NaN input
+  }
+  return true;
+}
+uint32_t encode_fast_tile_points() { return kETilePts; }
+
+static int launch_encode_fast(const Plan& plan, const EncLaunch& L, cudaStream_t stream) {
+  FloatNParams P;
+  for (int k = 0; k < 4; ++k) {
+    P.offset[k] = plan.ops[0].offset[k];
+    P.mul[k] = plan.ops[0].enc_mul_f[k];
+  }
+  P.point_step = plan.point_step;
+  const size_t smem = kEStageBytes;
+  auto k = encode_xyzi_fast_kernel;
+  if (set_smem(k, smem) != cudaSuccess) return -1;
+  uint32_t group = 1, grid = L.n_tiles_total;
+  if (L.uniform_tiles) {
+    group = kEGroup;
+    grid = L.n_frames * ((L.uniform_tiles + group - 1) / group);
+  }
+  k<<<grid, kET, smem, stream>>>(L, P, group);
+  count_launch();
+  return 1;
+}
+
+}  // namespace cldn

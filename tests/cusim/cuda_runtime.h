@@ -214,6 +214,8 @@ static inline int __popcll(unsigned long long v) { return __builtin_popcountll(v
 static inline unsigned __brev(unsigned v) { unsigned r = 0; for (int i = 0; i < 32; ++i) r |= ((v >> i) & 1u) << (31 - i); return r; }
 static inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned sh) { return static_cast<unsigned>(((static_cast<uint64_t>(hi) << 32) | lo) >> (sh & 31u)); }
 static inline unsigned __funnelshift_l(unsigned lo, unsigned hi, unsigned sh) { return static_cast<unsigned>((((static_cast<uint64_t>(hi) << 32) | lo) << (sh & 31u)) >> 32); }
+static inline unsigned __funnelshift_rc(unsigned lo, unsigned hi, unsigned sh) { if (sh > 32u) sh = 32u; return static_cast<unsigned>(((static_cast<uint64_t>(hi) << 32) | lo) >> sh); }
+static inline unsigned __funnelshift_lc(unsigned lo, unsigned hi, unsigned sh) { if (sh > 32u) sh = 32u; return static_cast<unsigned>(((((static_cast<uint64_t>(hi) << 32) | lo) << sh) >> 32) & 0xffffffffu); }
 static inline unsigned __byte_perm(unsigned a, unsigned b, unsigned sel) {
   const uint64_t v = (static_cast<uint64_t>(b) << 32) | a;
   unsigned r = 0;

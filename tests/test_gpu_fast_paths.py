@@ -107,3 +107,69 @@ def test_fast_reader_layouts(oracle, monkeypatch):
         got = np.full(n * 32, 0x77, dtype=np.uint8)
         cb.PointcloudDecoder().decode(dinfo, blob[hdr:], got)
         assert np.array_equal(got, _want(oracle, blob, n * 32, 0x77))
+
+
+# ---- encoder -------------------------------------------------------------------------------------------------------
+def _xyzi_adversarial(n, seed):
+    info, cloud = synth.cloud_c2(n, seed=seed)
+    rng = np.random.default_rng(seed)
+    pts = cloud.view(np.float32).reshape(n, 4).copy()
+    flat = pts.reshape(-1)
+    k = max(n // 200, 1)
+    idx = rng.choice(flat.size, size=min(5 * k, flat.size), replace=False)
+    q = max(len(idx) // 5, 1)
+    flat[idx[:q]] = np.nan
+    flat[idx[q:2 * q]] = rng.choice(np.array([np.inf, -np.inf, 3e9, -3e9, 2.2e6, -2.2e6, 33554.4, -33554.5], dtype=np.float32), size=len(idx[q:2 * q]))
+    flat[idx[2 * q:3 * q]] = (rng.integers(-5000, 5000, size=len(idx[2 * q:3 * q])).astype(np.float32) + 0.5) * np.float32(0.001)  # .5 ties
+    flat[idx[3 * q:4 * q]] = rng.normal(0, 1e-4, size=len(idx[3 * q:4 * q])).astype(np.float32)
+    flat[idx[4 * q:]] = np.float32(-0.0)
+    return info, np.ascontiguousarray(pts).view(np.uint8).reshape(-1)
+
+
+@pytest.mark.parametrize("n", [1, 8, 1023, 1024, 1025, 4096, 4097, 32768, 32769, 70_000])
+def test_fast_writer_sizes_and_edges(oracle, n):
+    # tiles of 1024 points, groups of 4 tiles per CTA, chunk boundaries every 32 tiles, the partial last tile
+    info, cloud = synth.cloud_c2(n, seed=n)
+    assert cb.PointcloudEncoder(info).encode(cloud) == oracle.encode(info, cloud)
+    info, cloud = _xyzi_adversarial(n, seed=n + 1)   # NaN / inf / huge / tie values: those tiles take the exact path
+    assert cb.PointcloudEncoder(info).encode(cloud) == oracle.encode(info, cloud)
+
+
+def test_fast_writer_near_the_range_limit(oracle):
+    # |v * mul| just below / at / above 2^25 (the fast path's bound) and deltas that need exactly 4 / 5 varint bytes
+    n = 3000
+    info, cloud = synth.cloud_c2(n, seed=9)
+    pts = cloud.view(np.float32).reshape(n, 4).copy()
+    lim = np.float32(33554.432)  # 2^25 mm
+    for i, v in enumerate([lim, -lim, np.nextafter(lim, np.float32(0)), np.nextafter(lim, np.float32(1e9)), np.float32(33554.0), np.float32(-33554.3)]):
+        pts[100 + 300 * i, i % 3] = v
+    pts[2000, 0] = np.float32(134217.7); pts[2001, 0] = np.float32(-134217.7)   # delta 2^28: a 5-byte varint
+    cloud = np.ascontiguousarray(pts).view(np.uint8).reshape(-1)
+    assert cb.PointcloudEncoder(info).encode(cloud) == oracle.encode(info, cloud)
+
+
+def test_fast_writer_batches(oracle):
+    # uniform batch (frame-interleaved groups) through the device API, with one frame full of NaNs, and a 4-byte
+    # misaligned input (the kernel then loads field by field)
+    F, n = 5, 40_000
+    info = synth.info_xyzi(n)
+    clouds = [synth.cloud_c2(n, seed=70 + k)[1] for k in range(F)]
+    clouds[2] = _xyzi_adversarial(n, seed=99)[1]
+    enc = cb.PointcloudEncoder(info)
+    cap = cb.MaxCompressedSize(info, n, True)
+    d_in = [_Dev(src=c) for c in clouds]
+    d_blob = [_Dev(size=cap) for _ in range(F)]
+    sizes = enc.encode_batch_device(enc.make_device_batch([t.ptr for t in d_in], [n * 16] * F, [t.ptr for t in d_blob], [cap] * F),
+                                    write_header=True, want_sizes=True)
+    for k in range(F):
+        assert bytes(d_blob[k].numpy()[:sizes[k]]) == oracle.encode(info, clouds[k]), k
+    shifted = _Dev(size=n * 16 + 16)
+    if hasattr(shifted.t, "cpu"):
+        import torch
+        shifted.t[4:4 + n * 16] = torch.from_numpy(clouds[0]).to(shifted.t.device)
+        torch.cuda.synchronize()
+    else:
+        shifted.t[4:4 + n * 16] = clouds[0]
+    out = _Dev(size=cap)
+    sizes = enc.encode_batch_device(enc.make_device_batch([shifted.ptr + 4], [n * 16], [out.ptr], [cap]), write_header=True, want_sizes=True)
+    assert bytes(out.numpy()[:sizes[0]]) == oracle.encode(info, clouds[0])
