@@ -46,9 +46,9 @@ __device__ __forceinline__ uint32_t top_bit(uint32_t x) {  // index of the most 
   asm("bfind.u32 %0, %1;" : "=r"(b) : "r"(x));
   return b;
 }
-__device__ __forceinline__ uint32_t shl_clamp(uint32_t v, uint32_t n) {  // v << n, 0 for n >= 32 (PTX semantics, not C++'s)
+__device__ __forceinline__ uint32_t low_mask(uint32_t n) {  // (1 << n) - 1, all ones for n >= 32: one BMSK
   uint32_t d;
-  asm("shl.b32 %0, %1, %2;" : "=r"(d) : "r"(v), "r"(n));
+  asm("bmsk.clamp.b32 %0, %1, %2;" : "=r"(d) : "r"(0), "r"(n));
   return d;
 }
 __device__ __forceinline__ uint32_t bitselect_e(uint32_t m, uint32_t a, uint32_t b) {  // (a & m) | (b & ~m), one LOP3
@@ -136,7 +136,13 @@ __global__ void __launch_bounds__(kET, 7) encode_xyzi_fast_kernel(const EncLaunc
     fi = find_frame(L.frames, L.n_frames, blockIdx.x);
     t0 = blockIdx.x - L.frames[fi].tile_begin;
   }
-  const EncFrame F = L.frames[fi];
+  // frame record and field table live in shared memory: the exact tile path (a real call) takes them by reference, and
+  // the fast path only keeps the two words it needs in registers
+  __shared__ EncFrame s_F;
+  __shared__ FloatNParams s_P;
+  if (threadIdx.x == 0) { s_F = L.frames[fi]; s_P = P; }
+  __syncthreads();
+  const EncFrame& F = s_F;
   const float4* in4 = reinterpret_cast<const float4*>(F.in);
   const bool aligned16 = (L.flags & kEncInputsAligned16) != 0u;
   uint64_t excl = 0;       // data bytes of all earlier tiles of the frame (known after the first tile's look-back)
@@ -196,6 +202,7 @@ __global__ void __launch_bounds__(kET, 7) encode_xyzi_fast_kernel(const EncLaunc
       uint32_t nbl[3] = {0, 0, 0};  // bit lengths of my last three values (for the tail word)
 #pragma unroll
       for (int j = 0; j < kEP; ++j) {
+        asm volatile("" ::: "memory");  // one point at a time: hoisting all 8 slot loads would cost 32 live registers
         const uint4 u = wsl[8 * lane + (j ^ (lane & 7))];
         const float pf[4] = {__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z), __uint_as_float(u.w)};
 #pragma unroll
@@ -210,7 +217,7 @@ __global__ void __launch_bounds__(kET, 7) encode_xyzi_fast_kernel(const EncLaunc
           uint32_t x = (zz1 & 0xFFFFC000u) * 3u + zz1;           // lo14 + hi14 * 2^16 (one LOP3 + one IMAD)
           x = x + (x & 0x3F803F80u);
           const uint32_t b = top_bit(x);                           // inside the value's last byte (garbage tiles: x may be 0)
-          x |= (shl_clamp(1u, b) - 1u) & 0x00808080u;              // continuation flags on every byte below it
+          x |= low_mask(b) & 0x00808080u;                          // continuation flags on every byte below it
           X[j][k] = x;
           mine += b >> 3;
           if (j == kEP - 1 && k >= 1) nbl[k - 1] = (b & 0x18u) + 8u;
@@ -250,25 +257,29 @@ __global__ void __launch_bounds__(kET, 7) encode_xyzi_fast_kernel(const EncLaunc
       if (lane == 0) ptail = warp > 0 ? sh.wtail[warp - 1] : 0u;
       const uint32_t off = wbase + inc - mine;
       // ---- pass 2: 64-bit window, aligned word flushes ----
-      const uint32_t r = off & 3u;
-      uint32_t pos = 8u * r;
-      uint32_t lo = __funnelshift_rc(ptail, 0u, 32u - pos);   // the last r bytes of the predecessor (0 for r == 0)
-      uint32_t* wp = stage32 + (off >> 2);
+      // `bit` = bit position of the next byte in the tile's stream; the window's low word is the aligned word holding it
+      uint32_t bit = 8u * off;
+      uint32_t lo = __funnelshift_rc(ptail, 0u, 32u - (bit & 31u));   // the last off % 4 bytes of the predecessor (0 if none)
+      uint32_t wa = (bit >> 3) & ~3u;                                 // byte address of that word in the staging buffer
 #pragma unroll
       for (int j = 0; j < kEP; ++j) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const uint32_t x = X[j][k];
           const uint32_t b = top_bit(x);
-          lo |= x << pos;
-          const uint32_t hi = __funnelshift_l(x, 0u, pos);   // x >> (32 - pos), 0 for pos == 0
-          pos += (b & 0x18u) + 8u;
-          if (pos >= 32u) { *wp++ = lo; lo = hi; pos -= 32u; }
+          lo |= __funnelshift_l(0u, x, bit);                 // x << (bit % 32)
+          const uint32_t hi = __funnelshift_l(x, 0u, bit);   // x >> (32 - bit % 32), 0 for bit % 32 == 0
+          bit += (b & 0x18u) + 8u;
+          const uint32_t wn = (bit >> 3) & ~3u;
+          if (wn != wa) { *reinterpret_cast<uint32_t*>(stage + wa) = lo; lo = hi; }
+          wa = wn;
         }
       }
+      const uint32_t pos = bit & 31u;
+      uint32_t* wp = reinterpret_cast<uint32_t*>(stage + wa);
       if (threadIdx.x == kET - 1 && pos != 0u) *wp = lo;     // nobody follows the tile's last thread
     } else {
-      total = encode_tile_careful<4>(F, P, tile_p0, stage, sh.scan);
+      total = encode_tile_careful<4>(s_F, s_P, tile_p0, stage, sh.scan);
       if (g == 0 && warp == 0) lb.begin(L.status, F.tile_begin, tile, L.epoch, total);
     }
     // ---- the tile's place in the frame: look-back for the first tile of the group, local knowledge afterwards ----

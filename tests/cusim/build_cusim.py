@@ -34,6 +34,8 @@ PTX = {
     # shr.b32: shift amounts above 31 are clamped to 32 (result 0), unlike C++
     # lop3.b32 d, a, b, c, immLut: bit i of d = immLut[(a_i << 2) | (b_i << 1) | c_i]; the LUT is part of the template text
     "lop3.b32": lambda outs, ins, tmpl="": f"{outs[0]} = ::cusim::lop3({ins[0]}, {ins[1]}, {ins[2]}, {tmpl.rstrip(';').split(',')[-1].strip()});",
+    # bmsk.clamp.b32 d, a, b: b bits set starting at bit a (both clamped to 32)
+    "bmsk.clamp.b32": lambda outs, ins: f"{outs[0]} = ::cusim::bmsk_clamp({ins[0]}, {ins[1]});",
     "shl.b32": lambda outs, ins: f"{outs[0]} = (({ins[1]}) > 31u) ? 0u : (static_cast<unsigned>({ins[0]}) << ({ins[1]}));",
     # max.NaN.f32: NaN if either operand is NaN
     "max.NaN.f32": lambda outs, ins: f"{outs[0]} = (std::isnan({ins[0]}) || std::isnan({ins[1]})) ? std::numeric_limits<float>::quiet_NaN() : fmaxf({ins[0]}, {ins[1]});",
@@ -122,6 +124,10 @@ def _rewrite_asm(text, fname):
             end += 1
         assert text[end] == ";", (fname, body)
         tmpl = re.match(r'\s*"([^"]*)"', body)
+        if tmpl.group(1).strip() == "":  # compiler barrier: keep it
+            out += text[pos:m.start()] + '__asm__ __volatile__("" ::: "memory");'
+            pos = end + 1
+            continue
         key = next((p for p in PTX if tmpl.group(1).startswith(p)), None)
         if key is None:
             raise RuntimeError(f"{fname}: no cusim restatement for inline PTX `{tmpl.group(1)}`")

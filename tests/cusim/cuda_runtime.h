@@ -225,6 +225,12 @@ static inline unsigned __byte_perm(unsigned a, unsigned b, unsigned sel) {
   return r;
 }
 namespace cusim {
+static inline unsigned bmsk_clamp(unsigned a, unsigned b) {
+  if (a > 32u) a = 32u;
+  if (b > 32u) b = 32u;
+  const uint64_t m = (b >= 32u ? 0xffffffffull : ((1ull << b) - 1ull)) << a;
+  return static_cast<unsigned>(m & 0xffffffffull);
+}
 static inline unsigned lop3(unsigned a, unsigned b, unsigned c, unsigned lut) {
   unsigned r = 0;
   for (int i = 0; i < 32; ++i) r |= ((lut >> ((((a >> i) & 1u) << 2) | (((b >> i) & 1u) << 1) | ((c >> i) & 1u))) & 1u) << i;
