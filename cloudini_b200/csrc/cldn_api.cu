@@ -8,6 +8,9 @@
 #include <string.h>
 
 #include <algorithm>
+#include <new>
+#include <stdexcept>
+#include <utility>
 #include <string>
 #include <vector>
 
@@ -48,7 +51,12 @@ struct DevBuf {
     size_t want = std::max<size_t>(n, 16);
     CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&p), want * sizeof(T)));
     cap = want;
-    if (zero) CUDA_TRY(cudaMemset(p, 0, want * sizeof(T)));
+    if (zero) {
+      // cudaMemset runs on the legacy stream and is asynchronous to the host; the handles' streams are non-blocking and
+      // would not order their kernels behind it, so the zeroes are made final here (growth is rare)
+      CUDA_TRY(cudaMemset(p, 0, want * sizeof(T)));
+      CUDA_TRY(cudaDeviceSynchronize());
+    }
     return CLDN_OK;
   }
   void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
@@ -249,6 +257,7 @@ const char* dev_error_text(uint32_t code) {
     case DEV_ERR_CHUNK_SIZE: return "Invalid chunk size found while decoding";
     case DEV_ERR_CHUNK_COUNT: return "Encoded data does not match the declared number of points (chunk count)";
     case DEV_ERR_OUTPUT_SMALL: return "Output buffer is too small to hold the decoded data";
+    case DEV_ERR_ENCODE_OUTPUT_SMALL: return "Output buffer too small for uncompressed chunk";  // chunk_writer.cpp:33-35
     default: return "unknown device error";
   }
 }
@@ -375,7 +384,7 @@ static int check_device_error(cudaStream_t stream, uint32_t* d_err, uint32_t* h_
     const uint32_t code = *h_err;
     cudaMemsetAsync(d_err, 0, sizeof(uint32_t), stream);
     set_error("%s", dev_error_text(code));
-    return CLDN_ERR_CORRUPT_DATA;
+    return code == DEV_ERR_ENCODE_OUTPUT_SMALL ? CLDN_ERR_BUFFER_TOO_SMALL : CLDN_ERR_CORRUPT_DATA;
   }
   return CLDN_OK;
 }
@@ -418,6 +427,7 @@ static int encode_batch_device(cldn_encoder* e, size_t n_frames, const void* con
     EncFrame& F = hf[f];
     F.in = static_cast<const uint8_t*>(clouds[f]);
     F.out = static_cast<uint8_t*>(outs[f]);
+    F.out_cap = out_capacities[f];
     F.n_points = static_cast<uint32_t>(n);
     F.tile_begin = static_cast<uint32_t>(tiles);
     F.n_tiles = static_cast<uint32_t>((n + T - 1) / T);
@@ -528,9 +538,25 @@ static int encode_batch_device(cldn_encoder* e, size_t n_frames, const void* con
   return CLDN_OK;
 }
 
-int cldn_b200_encode_batch(cldn_encoder_t* e, size_t n_frames, const void* const* clouds, const size_t* cloud_bytes,
-                           void* const* outs, const size_t* out_capacities, int write_header, size_t* written_host,
-                           int mem) {
+}  // extern "C"
+
+// No C++ exception may cross the C ABI (std::terminate under ctypes / C callers): allocation failures become a status.
+template <class Fn>
+static int guarded(Fn&& fn) {
+  try {
+    return fn();
+  } catch (const std::bad_alloc&) {
+    set_error("out of memory");
+    return CLDN_ERR_INTERNAL;
+  } catch (const std::exception& ex) {
+    set_error("internal error: %s", ex.what());
+    return CLDN_ERR_INTERNAL;
+  }
+}
+
+static int encode_batch_impl(cldn_encoder_t* e, size_t n_frames, const void* const* clouds, const size_t* cloud_bytes,
+                             void* const* outs, const size_t* out_capacities, int write_header, size_t* written_host,
+                             int mem) {
   if (!e || (n_frames && (!clouds || !cloud_bytes || !outs || !out_capacities))) {
     set_error("null argument");
     return CLDN_ERR_INVALID_ARGUMENT;
@@ -565,6 +591,7 @@ int cldn_b200_encode_batch(cldn_encoder_t* e, size_t n_frames, const void* const
       CUDA_TRY(cudaMemcpyAsync(e->h_sizes.p, e->d_sizes.p, sizeof(uint64_t), cudaMemcpyDeviceToHost, e->stream));
       if (int rc = check_device_error(e->stream, e->d_err.p, e->h_err.p)) return rc;
       const size_t s1 = static_cast<size_t>(e->h_sizes.p[0]);
+      if (s1 > cap1) { set_error("Output buffer too small for uncompressed chunk"); return CLDN_ERR_BUFFER_TOO_SMALL; }
       e->s2_tmp.resize(s1 + 16);
       if (s1) CUDA_TRY(cudaMemcpy(e->s2_tmp.data(), e->d_out.p, s1, cudaMemcpyDeviceToHost));
       uint8_t* out = static_cast<uint8_t*>(outs[f]);
@@ -600,8 +627,15 @@ int cldn_b200_encode_batch(cldn_encoder_t* e, size_t n_frames, const void* const
     in_off[f] = in_total;
     in_total += (cloud_bytes[f] + 255) & ~size_t(255);
     out_off[f] = out_total;
-    caps[f] = need;
-    out_total += (need + 255) & ~size_t(255);
+    // A committed V5 mode can exceed the reference's own worst-case formula (DeltaRle on a 64-bit field: 11 bytes per
+    // value against the 10 it budgets); the reference then succeeds iff the caller's buffer is large enough. Stage with
+    // room for the real worst case, never more than the caller gave: the kernels check every store against this bound.
+    size_t worst = need;
+    for (uint32_t s2 = 0; s2 < e->plan.n_sections; ++s2) {
+      if (e->plan.sections[s2].bpv == 8) worst += cloud_bytes[f] / e->info.point_step + 16 * ((cloud_bytes[f] / e->info.point_step) / kChunkPoints + 1);
+    }
+    caps[f] = std::min(out_capacities[f], worst);
+    out_total += (caps[f] + 255) & ~size_t(255);
   }
   if (int rc = e->d_in.reserve(in_total + 256)) return rc;
   if (int rc = e->d_out.reserve(out_total + 256)) return rc;
@@ -622,12 +656,24 @@ int cldn_b200_encode_batch(cldn_encoder_t* e, size_t n_frames, const void* const
   for (size_t f = 0; f < n_frames; ++f) {
     CUDA_TRY(cudaEventSynchronize(e->pipe.ev[2 * f + 1]));
     const size_t sz = static_cast<size_t>(e->h_sizes.p[f]);
-    if (sz > out_capacities[f]) { set_error("internal: encoded size exceeds capacity"); return CLDN_ERR_INTERNAL; }
+    if (sz > caps[f]) {  // the kernels refused the stores that did not fit and raised the error word
+      if (int rc = check_device_error(e->stream, e->d_err.p, e->h_err.p)) return rc;
+      set_error("Output buffer too small for uncompressed chunk");
+      return CLDN_ERR_BUFFER_TOO_SMALL;
+    }
     if (sz) CUDA_TRY(cudaMemcpyAsync(outs[f], e->d_out.p + out_off[f], sz, cudaMemcpyDeviceToHost, e->pipe.d2h));
     if (written_host) written_host[f] = sz;
   }
   CUDA_TRY(cudaStreamSynchronize(e->pipe.d2h));
   return check_device_error(e->stream, e->d_err.p, e->h_err.p);
+}
+
+extern "C" {
+
+int cldn_b200_encode_batch(cldn_encoder_t* e, size_t n_frames, const void* const* clouds, const size_t* cloud_bytes,
+                           void* const* outs, const size_t* out_capacities, int write_header, size_t* written_host,
+                           int mem) {
+  return guarded([&] { return encode_batch_impl(e, n_frames, clouds, cloud_bytes, outs, out_capacities, write_header, written_host, mem); });
 }
 
 int cldn_b200_encode(cldn_encoder_t* enc, const void* cloud, size_t cloud_bytes, void* out, size_t out_capacity,
@@ -701,15 +747,22 @@ static int decoder_update_plan(cldn_decoder* d, const cldn_info_t& info) {
   d->info = info;
   d->have_plan = true;
   // do the declared fields cover every byte of a point? (otherwise host outputs must round-trip their padding)
-  std::vector<uint8_t> cover(info.point_step, 0);
-  for (uint32_t i = 0; i < info.n_fields; ++i) {
-    const int sz = size_of_type(info.fields[i].type);
-    for (int b = 0; b < sz; ++b) {
-      const uint64_t o = static_cast<uint64_t>(info.fields[i].offset) + b;
-      if (o < info.point_step) cover[o] = 1;
-    }
+  // union of the field intervals, clipped to the point: at most CLDN_MAX_FIELDS of them, no point_step-sized table
+  // (the header is untrusted: a forged point_step must not size an allocation)
+  std::pair<uint64_t, uint64_t> iv[CLDN_MAX_FIELDS];
+  uint32_t n_iv = 0;
+  for (uint32_t i = 0; i < info.n_fields && n_iv < CLDN_MAX_FIELDS; ++i) {
+    const uint64_t lo = info.fields[i].offset, hi = std::min<uint64_t>(lo + static_cast<uint64_t>(size_of_type(info.fields[i].type)), info.point_step);
+    if (lo < hi) iv[n_iv++] = {lo, hi};
   }
-  d->has_padding = std::find(cover.begin(), cover.end(), 0) != cover.end();
+  std::sort(iv, iv + n_iv);
+  uint64_t covered_to = 0;
+  bool gap = false;
+  for (uint32_t i = 0; i < n_iv; ++i) {
+    if (iv[i].first > covered_to) gap = true;
+    covered_to = std::max(covered_to, iv[i].second);
+  }
+  d->has_padding = gap || covered_to < info.point_step;
   return CLDN_OK;
 }
 
@@ -758,7 +811,7 @@ static int decode_batch_device(cldn_decoder* d, const cldn_info_t& info, size_t 
   L.chunk_tiles = nullptr; L.chunk_tile_begin = nullptr; L.stream_end = nullptr; L.tstatus = nullptr; L.tsums = nullptr;
   L.tile_capacity = 0; L.tile_grid = 0; L.epoch = 0; L.trace = nullptr; L.chunk_counter = nullptr; L.sections_only = 0;
   L.chunk_desc = nullptr; L.desc_tag = 0; L.uniform_chunks = 0; L.redo_list = nullptr; L.redo_mode = 0;
-  if (d->plan.n_sections > 0 && chunks > 0 && !(d->plan.all_varint || d->plan.n_ops == 0)) {
+  if (d->plan.n_sections > 0 && chunks > 0 && (d->plan.regular_overlap || !(d->plan.all_varint || d->plan.n_ops == 0))) {
     // V5 with raw / XOR / Gorilla fields in the regular stream: the per-chunk parser records where the sections start
     if (int rc = d->d_stream_end.reserve(static_cast<size_t>(chunks) + 1)) return rc;
     L.stream_end = d->d_stream_end.p;
@@ -818,7 +871,7 @@ static int decode_batch_device(cldn_decoder* d, const cldn_info_t& info, size_t 
       L.trace = d->d_trace.p;
     }
   }
-  d->fast_launched = L.redo_list != nullptr && decode_tiles_sequential(L.n_chunks_total) && decode_fast_enabled();
+  d->fast_launched = L.redo_list != nullptr && decode_tiles_sequential(L.n_chunks_total) && decode_fast_enabled() && !d->plan.regular_overlap;
   d->fast_chunks = d->fast_launched ? L.n_chunks_total : 0u;
   if (launch_decode(d->plan, L, d->stream) < 0) { set_error("decode kernel launch failed"); return CLDN_ERR_CUDA; }
   CUDA_TRY(cudaGetLastError());
@@ -888,8 +941,10 @@ int cldn_b200_decoder_last_stats(cldn_decoder_t* d, uint32_t stats[2]) {
   return CLDN_OK;
 }
 
-int cldn_b200_decode_batch(cldn_decoder_t* d, const cldn_info_t* info, size_t n_frames, const void* const* payloads,
-                           const size_t* payload_bytes, void* const* outs, const size_t* out_capacities, int mem, int sync) {
+}  // extern "C"
+
+static int decode_batch_impl(cldn_decoder_t* d, const cldn_info_t* info, size_t n_frames, const void* const* payloads,
+                             const size_t* payload_bytes, void* const* outs, const size_t* out_capacities, int mem, int sync) {
   if (!d || !info || (n_frames && (!payloads || !payload_bytes || !outs || !out_capacities))) {
     set_error("null argument");
     return CLDN_ERR_INVALID_ARGUMENT;
@@ -917,6 +972,12 @@ int cldn_b200_decode_batch(cldn_decoder_t* d, const cldn_info_t* info, size_t n_
     plain.compression_opt = CLDN_COMP_NONE;
     bool ok;
     const size_t pts = static_cast<size_t>(info->width) * info->height;
+    for (size_t f = 0; f < n_frames; ++f) {  // before any scratch is sized from the (untrusted) header
+      if (out_capacities[f] / std::max<uint32_t>(info->point_step, 1u) < pts) {
+        set_error("Output buffer is too small to hold the decoded data");
+        return CLDN_ERR_BUFFER_TOO_SMALL;
+      }
+    }
     size_t max_body = max_compressed_size(plain, std::min<size_t>(pts, kChunkPoints), false, &ok);
     if (!ok) return CLDN_ERR_INVALID_ARGUMENT;
     max_body = std::max<size_t>(max_body, pts * info->point_step) + 64;  // DecompressChunk's bound is w*h*step (cloudini.cpp:672-675)
@@ -924,7 +985,7 @@ int cldn_b200_decode_batch(cldn_decoder_t* d, const cldn_info_t* info, size_t n_
       if (int rc = stage2_decompress_payload(info->compression_opt, static_cast<const uint8_t*>(payloads[f]), payload_bytes[f], d->s2_tmp, max_body)) return rc;
       const void* p1 = d->s2_tmp.data();
       const size_t b1 = d->s2_tmp.size();
-      if (int rc = cldn_b200_decode_batch(d, &plain, 1, &p1, &b1, &outs[f], &out_capacities[f], CLDN_MEM_HOST, 1)) return rc;
+      if (int rc = decode_batch_impl(d, &plain, 1, &p1, &b1, &outs[f], &out_capacities[f], CLDN_MEM_HOST, 1)) return rc;
     }
     return CLDN_OK;
   }
@@ -958,6 +1019,13 @@ int cldn_b200_decode_batch(cldn_decoder_t* d, const cldn_info_t* info, size_t n_
   CUDA_TRY(cudaStreamSynchronize(d->pipe.d2h));
   // a failed decode must not hand back garbage silently: the error word is checked after everything has drained
   return check_device_error(d->stream, d->d_err.p, d->h_err.p);
+}
+
+extern "C" {
+
+int cldn_b200_decode_batch(cldn_decoder_t* d, const cldn_info_t* info, size_t n_frames, const void* const* payloads,
+                           const size_t* payload_bytes, void* const* outs, const size_t* out_capacities, int mem, int sync) {
+  return guarded([&] { return decode_batch_impl(d, info, n_frames, payloads, payload_bytes, outs, out_capacities, mem, sync); });
 }
 
 int cldn_b200_decode(cldn_decoder_t* dec, const cldn_info_t* info, const void* payload, size_t payload_bytes, void* out,

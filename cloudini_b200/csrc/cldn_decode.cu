@@ -1669,12 +1669,27 @@ int launch_decode(const Plan& plan, const DecLaunch& L, cudaStream_t stream) {
   int launches = 0;
   if (L.n_chunks_total == 0 && L.n_frames == 0) return 0;
   // the chunk-sequential FloatN kernel walks the chunk prefixes itself (CTA 0) while the other CTAs already decode
-  const bool fused_walk = L.n_chunks_total > 0 && L.tile_grid > 0 && L.chunk_desc != nullptr && decode_tiles_sequential(L.n_chunks_total);
+  const bool fused_walk = L.n_chunks_total > 0 && L.tile_grid > 0 && L.chunk_desc != nullptr && decode_tiles_sequential(L.n_chunks_total) &&
+                          !plan.regular_overlap;
   if (!fused_walk) {
     walk_chunks_kernel<<<(L.n_frames + 127) / 128, 128, 0, stream>>>(L);
     ++launches;
   }
-  if (L.n_chunks_total > 0 && L.tile_grid > 0) {
+  if (L.n_chunks_total > 0 && plan.regular_overlap) {
+    // overlapping stored fields: the reference's store order (per point, field order, last writer wins) is only kept by
+    // the one-thread-per-chunk parser; sections follow in field order like everywhere else
+    decode_sequential_kernel<<<(L.n_chunks_total + 31) / 32, 32, 0, stream>>>(L);
+    ++launches;
+    if (plan.n_sections > 0) {
+      DecLaunch S = L;
+      S.sections_only = 1;
+      const size_t smem = dec_smem_bytes(false);
+      auto k = decode_chunks_kernel<0>;
+      if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess) return -1;
+      k<<<L.n_chunks_total, kThreads, smem, stream>>>(S);
+      ++launches;
+    }
+  } else if (L.n_chunks_total > 0 && L.tile_grid > 0) {
     // FloatN-only regular stream: tile-parallel kernel; V5 sections (if any) by the per-chunk kernel afterwards
     const int n = launch_decode_tiles(plan, L, stream);
     if (n < 0) return -1;

@@ -796,12 +796,17 @@ __global__ void __launch_bounds__(kDT, CLDN_SEQ_MINB * (256 / kDT)) decode_chunk
   const uint32_t off[4] = {o0, o1, o2, o3};
   const uint32_t step = L.plan->point_step;
 
-  // CTA 0 (always the first one resident) follows the u32 chunk prefixes of every frame (cloudini.cpp:645-664, the same
-  // checks as walk_chunks_kernel) and publishes every chunk as soon as it is known; the other CTAs start decoding at
-  // once and only wait for the descriptor of the chunk they claimed.
-  // (redo mode: the fast kernel of the same launch has published every descriptor already)
-  if (blockIdx.x == 0 && !L.redo_mode) {
-    for (uint32_t f = threadIdx.x; f < L.n_frames; f += kDT) walk_frame_publish(L, f);
+  // Whichever CTA draws ticket 0 -- by construction one that is running, whatever the block scheduler does -- follows
+  // the u32 chunk prefixes of every frame (cloudini.cpp:645-664, the same checks as walk_chunks_kernel) and publishes
+  // every chunk as soon as it is known; the other CTAs start decoding at once and only wait for the descriptor of the
+  // chunk they claimed. (redo mode: the fast kernel of the same launch has published every descriptor already)
+  if (!L.redo_mode) {
+    if (threadIdx.x == 0) s_chunk = atomicAdd(L.chunk_counter + 2, 1u);
+    __syncthreads();
+    if (s_chunk == 0u) {
+      for (uint32_t f = threadIdx.x; f < L.n_frames; f += kDT) walk_frame_publish(L, f);
+    }
+    __syncthreads();
   }
 
   while (true) {

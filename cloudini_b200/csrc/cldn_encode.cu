@@ -119,8 +119,11 @@ __device__ __forceinline__ void finish_tile(const EncLaunch& L, const EncFrame& 
   const uint64_t sec_before = F.sec_excl ? F.sec_excl[chunk] : 0;
   uint8_t* payload = F.out + L.header_bytes;
   // data position: one u32 prefix per chunk up to and including mine, all earlier data, all earlier chunks' sections
-  copy_stage_to_global(stage, total, payload + 4ull * (chunk + 1) + excl + sec_before);
-  if (t == 0) {
+  const uint64_t at = 4ull * (chunk + 1) + excl + sec_before;
+  const bool fits = L.header_bytes + at + total <= F.out_cap;  // "Output buffer too small for uncompressed chunk"
+  if (fits) copy_stage_to_global(stage, total, payload + at);
+  else if (threadIdx.x == 0) report_error(L.err, DEV_ERR_ENCODE_OUTPUT_SMALL);
+  if (t == 0 && L.header_bytes <= F.out_cap) {
     for (uint32_t i = threadIdx.x; i < L.header_bytes; i += blockDim.x) F.out[i] = L.header[i];
   }
   const bool last_of_frame = (t + 1 == F.n_tiles);
@@ -130,7 +133,9 @@ __device__ __forceinline__ void finish_tile(const EncLaunch& L, const EncFrame& 
     const uint64_t data_before_chunk = (first == 0) ? 0 : wait_inclusive(L.status, F.tile_begin + first - 1, L.epoch);
     const uint64_t sec_mine = F.sec_excl ? (F.sec_excl[chunk + 1] - F.sec_excl[chunk]) : 0;
     const uint64_t body = (excl + total) - data_before_chunk + sec_mine;
-    store_u32(payload + 4ull * chunk + data_before_chunk + sec_before, static_cast<uint32_t>(body));  // chunk_writer.cpp:33-40
+    if (L.header_bytes + 4ull * (chunk + 1) + data_before_chunk + sec_before <= F.out_cap) {
+      store_u32(payload + 4ull * chunk + data_before_chunk + sec_before, static_cast<uint32_t>(body));  // chunk_writer.cpp:33-40
+    }
     if (last_of_frame) {
       L.sizes[frame_idx] = L.header_bytes + 4ull * F.n_chunks + excl + total + (F.sec_excl ? F.sec_excl[F.n_chunks] : 0);
     }
@@ -560,7 +565,7 @@ __global__ void __launch_bounds__(kGorillaThreads) gorilla_prepass_kernel(const 
   }
 }
 
-// Gorilla pre-pass, hardware-verified version (the default until the warp-parallel one above has run on a GPU): one thread per (chunk, Gorilla op) walks its 32768 points in order (the window of the previous
+// Gorilla pre-pass, one-thread-per-chunk version (CLDN_B200_UNMEASURED=0 only): one thread per (chunk, Gorilla op) walks its 32768 points in order (the window of the previous
 // "new window" record is inherently sequential) and leaves a 12-byte record per point: bytes 0..9 the encoded value,
 // byte 11 its length. The generic kernel then copies the record like any other field. Side layout: [op][point][12].
 __global__ void gorilla_prepass_seq_kernel(const EncLaunch L) {
@@ -591,9 +596,12 @@ __global__ void gorilla_prepass_seq_kernel(const EncLaunch L) {
   }
 }
 
+// The parallel boundary-search decoders, the warp-parallel Gorilla pre-pass and the parallel run-table reader are the
+// defaults (hardware-green since the start of round 2: GPU suite with and without them, gpurun_out/r2_start).
+// CLDN_B200_UNMEASURED=0 selects the older one-thread-per-chunk versions again (bisecting aid).
 bool unmeasured_kernels_enabled() {
   const char* e = getenv("CLDN_B200_UNMEASURED");
-  return e && e[0] == '1';
+  return !(e && e[0] == '0');
 }
 
 int launch_gorilla_prepass(const Plan& plan, const EncLaunch& L, cudaStream_t stream) {

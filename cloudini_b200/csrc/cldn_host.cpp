@@ -443,6 +443,24 @@ static void finish_plan(Plan* p) {
   }
   p->floatn_only = (p->n_ops == 1 && p->ops[0].kind == OP_FLOATN) ? 1 : 0;
   if (p->n_ops == 0) { p->all_varint = 0; }
+  // stored byte ranges of the regular stream's fields: do any two intersect? (forged offsets, or e.g. `rgb` and `rgba`
+  // declared at the same offset)
+  p->regular_overlap = 0;
+  uint64_t lo[kMaxOps * 4], hi[kMaxOps * 4];
+  uint32_t n = 0;
+  for (uint32_t i = 0; i < p->n_ops; ++i) {
+    const RegOp& op = p->ops[i];
+    const uint32_t width = (op.kind == OP_FLOATN) ? 4u : op.size;
+    for (int l = 0; l < (op.kind == OP_FLOATN ? op.lanes : 1); ++l) {
+      if (op.offset[l] == CLDN_SKIP_STORE_OFFSET) continue;
+      lo[n] = op.offset[l]; hi[n] = static_cast<uint64_t>(op.offset[l]) + width; ++n;
+    }
+  }
+  for (uint32_t a = 0; a < n; ++a) {
+    for (uint32_t b = a + 1; b < n; ++b) {
+      if (lo[a] < hi[b] && lo[b] < hi[a]) p->regular_overlap = 1;
+    }
+  }
 }
 
 static int build_plan(const cldn_info_t& info, bool decoder, Plan* p) {

@@ -11,6 +11,8 @@ namespace cldn {
 struct EncFrame {
   const uint8_t* in;     // n_points * point_step bytes
   uint8_t* out;          // start of the blob (header goes here when write_header)
+  uint64_t out_cap;      // bytes available at `out`: every store is checked against it (a committed V5 mode can exceed
+                         // the reference's worst-case formula; the reference then throws, chunk_writer.cpp:33-35)
   uint32_t n_points;
   uint32_t tile_begin;   // global index of this frame's first tile (exclusive scan of n_tiles over the batch)
   uint32_t n_tiles;
@@ -85,10 +87,8 @@ struct DecLaunch {
   uint32_t par_runs;           // V5 Rle / DeltaRle readers: 1 = parallel run-table parse (see unmeasured_kernels_enabled)
 };
 
-// Kernels written after the round-1 GPU budget was spent (parallel boundary-search decoders, warp-parallel Gorilla
-// pre-pass, parallel run-table parse): bit-exact, memcheck- and racecheck-clean under tests/cusim, but not yet run on
-// hardware. Until they are, the hardware-verified kernels stay the default and CLDN_B200_UNMEASURED=1 selects these
-// (tests/test_gpu_zz_unmeasured.py runs the parity suite that way, last).
+// The parallel boundary-search decoders, the warp-parallel Gorilla pre-pass and the parallel run-table parse: defaults
+// since round 2 (hardware-green); CLDN_B200_UNMEASURED=0 selects the older one-thread-per-chunk versions (bisecting aid).
 bool unmeasured_kernels_enabled();
 
 int launch_decode(const Plan& host_plan, const DecLaunch& L, cudaStream_t stream);

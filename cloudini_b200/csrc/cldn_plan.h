@@ -64,7 +64,10 @@ struct Plan {
   uint8_t all_fixed;    // every regular op is fixed size (COPY)
   uint8_t supported;    // 0 if the plan contains ops this build cannot run at all
   uint8_t n_gorilla;    // number of OP_GORILLA64 ops (they need the sequential per-chunk pre-pass / decoder)
-  uint8_t pad_[2];
+  uint8_t regular_overlap;  // decoder: two stored fields of the regular stream cover the same byte of a point. The reference
+                            // stores per point in field order (last writer wins, v4_codec.cpp:85-117); only the per-chunk
+                            // sequential decoder reproduces that order, so such plans are routed to it
+  uint8_t pad_[1];
 };
 
 // Builds the ENCODER plan. Returns CLDN_OK or a negative status (message via set_error()).

@@ -512,6 +512,10 @@ __global__ void __launch_bounds__(kThreads) place_sections_kernel(const SecLaunc
   const uint32_t size = L.sec_sizes[blockIdx.x];
   const uint8_t* src = L.scratch + static_cast<size_t>(blockIdx.x) * L.sec_stride;
   uint8_t* dst = F.out + pos;
+  if (pos + size > F.out_cap) {  // the reference: "Output buffer too small for uncompressed chunk" (chunk_writer.cpp:33-35)
+    if (threadIdx.x == 0) report_error(L.err, DEV_ERR_ENCODE_OUTPUT_SMALL);
+    return;
+  }
   for (uint32_t i = threadIdx.x; i < size; i += blockDim.x) dst[i] = src[i];
 }
 

@@ -99,7 +99,12 @@ inline void check(int rc) {
   if (rc != CLDN_OK) throw std::runtime_error(cldn_b200_last_error());
 }
 inline cldn_info_t to_c(const EncodingInfo& in) {
-  if (in.fields.size() > CLDN_MAX_FIELDS) throw std::runtime_error("too many fields");
+  // limits of the C ABI's fixed-size record: refuse instead of silently producing a different header
+  if (in.fields.size() > CLDN_MAX_FIELDS) throw std::runtime_error("cloudini_b200: more than " + std::to_string(CLDN_MAX_FIELDS) + " fields are not supported");
+  if (in.encoding_config.size() >= sizeof(cldn_info_t{}.encoding_config)) throw std::runtime_error("cloudini_b200: encoding_config is too long for the C ABI record");
+  for (const auto& f : in.fields) {
+    if (f.name.size() >= CLDN_MAX_NAME) throw std::runtime_error("cloudini_b200: field name '" + f.name + "' is longer than " + std::to_string(CLDN_MAX_NAME - 1) + " characters");
+  }
   cldn_info_t c;
   cldn_b200_info_init(&c);
   c.width = in.width; c.height = in.height; c.point_step = in.point_step;

@@ -128,10 +128,10 @@ class RefOracle:
     def max_compressed_size(self, info: cb.EncodingInfo, points: int, include_header: bool = True) -> int:
         return int(self.L.ref_max_compressed_size(_yaml(info), info.version, points, int(include_header)))
 
-    def encode(self, info: cb.EncodingInfo, cloud, write_header: bool = True) -> bytes:
+    def encode(self, info: cb.EncodingInfo, cloud, write_header: bool = True, cap: int = None) -> bytes:
         data = _u8(cloud)
         n = data.nbytes // info.point_step if info.point_step else 0
-        cap = self.max_compressed_size(info, n, True) + 64
+        cap = self.max_compressed_size(info, n, True) + 64 if cap is None else cap
         out = np.empty(cap, dtype=np.uint8)
         w = self.L.ref_encode(_yaml(info), info.version, 0, data.ctypes.data, data.nbytes, out.ctypes.data, cap, int(write_header))
         if w < 0:
@@ -240,11 +240,11 @@ class PortOracle:
         c = cb._to_c(info)
         return int(self.L.orc_max_compressed_size(C.byref(c), points, int(include_header)))
 
-    def encode(self, info, cloud, write_header: bool = True) -> bytes:
+    def encode(self, info, cloud, write_header: bool = True, cap: int = None) -> bytes:
         data = _u8(cloud)
         c = cb._to_c(info)
         n = data.nbytes // info.point_step if info.point_step else 0
-        cap = self.max_compressed_size(info, n, True) + 64
+        cap = self.max_compressed_size(info, n, True) + 64 if cap is None else cap
         out = np.empty(cap, dtype=np.uint8)
         w = self.L.orc_encode(C.byref(c), data.ctypes.data, data.nbytes, out.ctypes.data, cap, int(write_header))
         if w < 0:

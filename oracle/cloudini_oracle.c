@@ -681,10 +681,14 @@ long long orc_encode(const cldn_info_t* in, const uint8_t* cloud, size_t cloud_b
     vals[s].v = (int64_t*)malloc(ORC_CHUNK * sizeof(int64_t));
     vals[s].raw = (uint64_t*)malloc(ORC_CHUNK * sizeof(uint64_t));
   }
+  /* the reference serialises a chunk into its own stage-1 buffer and only then copies it behind the u32 prefix,
+   * failing if it does not fit (chunk_writer.cpp:27-40): a committed section mode may exceed MaxCompressedSize's budget
+   * (DeltaRle on a 64-bit field: 11 bytes per value against the 10 budgeted) */
+  uint8_t* chunk_buf = (uint8_t*)malloc((size_t)ORC_CHUNK * ((size_t)in->point_step * 2 + 16 + (size_t)pl.n_secs * 12) + 4096);
   size_t done = 0;
   while (done < points) {
     const size_t n = (points - done) < ORC_CHUNK ? (points - done) : ORC_CHUNK;
-    uint8_t* body = out + pos + 4;
+    uint8_t* body = chunk_buf;
     size_t b = 0;
     reset_ops(&pl); /* v4_codec.cpp:69 / v5_codec.cpp:910-912 */
     for (size_t i = 0; i < n; ++i) {
@@ -710,11 +714,18 @@ long long orc_encode(const cldn_info_t* in, const uint8_t* cloud, size_t cloud_b
       }
     }
     const uint32_t sz = (uint32_t)b; /* chunk_writer.cpp:33-40 */
+    if (cap - pos < 4 || cap - pos - 4 < b) {
+      for (int s = 0; s < pl.n_secs; ++s) { free(vals[s].v); free(vals[s].raw); }
+      free(chunk_buf);
+      return fail("Output buffer too small for uncompressed chunk");
+    }
     memcpy(out + pos, &sz, 4);
+    memcpy(out + pos + 4, chunk_buf, b);
     pos += 4 + b;
     done += n;
   }
   for (int s = 0; s < pl.n_secs; ++s) { free(vals[s].v); free(vals[s].raw); }
+  free(chunk_buf);
   return (long long)pos;
 }
 

@@ -36,7 +36,7 @@ def _run_gpu_suite(cusim_lib, extra_env, selection):
 
 
 def test_parity_suite_under_emulation(cusim_lib):
-    out = _run_gpu_suite(cusim_lib, {"CLDN_B200_FUZZ": "1", "CLDN_B200_FUZZ_SEEDS": "60"}, ["tests/test_gpu_parity.py", "tests/test_gpu_ros.py", "tests/test_gpu_zz_unmeasured.py", "tests/test_cpp_shim.py"])
+    out = _run_gpu_suite(cusim_lib, {"CLDN_B200_FUZZ": "1", "CLDN_B200_FUZZ_SEEDS": "60"}, ["tests/test_gpu_parity.py", "tests/test_gpu_ros.py", "tests/test_gpu_zz_legacy_kernels.py", "tests/test_cpp_shim.py"])
     assert " passed" in out and "failed" not in out
 
 
@@ -45,7 +45,7 @@ def test_thread_order_and_cta_concurrency_do_not_matter(cusim_lib, order, worker
     # (the "rand" run also delays every CTA start at random: CUSIM_JITTER)
     # reverse / shuffled resume order inside a CTA, 1..8 OS threads running CTAs: same bytes (look-backs, persistent
     # chunk claims and the in-kernel chunk walk are the protocols this exercises)
-    sel = ["tests/test_gpu_parity.py", "tests/test_gpu_ros.py", "tests/test_gpu_zz_unmeasured.py", "-k",
+    sel = ["tests/test_gpu_parity.py", "tests/test_gpu_ros.py", "tests/test_gpu_zz_legacy_kernels.py", "-k",
            "float_clouds_sizes or adversarial or int_min or decode_modes or batch or c3_padded or v5_ or lossless or padded_and_unaligned or viz_ or raw_fields or gorilla_field or long_run"]
     env = {"CUSIM_ORDER": order, "CUSIM_WORKERS": workers}
     if order == "rand":
@@ -77,7 +77,7 @@ def test_no_out_of_bounds_access_under_asan(lib_built):
     env = dict(os.environ, CLDN_B200_LIB=lib, CLDN_B200_ALLOW_EMULATION="tests-only", LD_PRELOAD=f"{libasan} {libstdcxx}", ASAN_OPTIONS="detect_leaks=0", CLDN_B200_FUZZ="1",
                CLDN_B200_FUZZ_SEEDS="40")
     cmd = [sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", "-p", "no:cacheprovider", "-k", "not c2_full_size",
-           "tests/test_gpu_parity.py", "tests/test_gpu_ros.py", "tests/test_gpu_zz_unmeasured.py"]
+           "tests/test_gpu_parity.py", "tests/test_gpu_ros.py", "tests/test_gpu_zz_legacy_kernels.py"]
     r = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=3000)
     assert r.returncode == 0 and "AddressSanitizer" not in (r.stdout + r.stderr), r.stdout[-3000:] + r.stderr[-3000:]
 
@@ -146,5 +146,5 @@ def test_host_code_never_dereferences_device_memory(cusim_lib, tmp_path):
     # event behind the copy), not before — reading it early yields 0xEE here, stale data on the GPU box
     r = subprocess.run([exe, "--async"], env=dict(env, CUSIM_ASYNC="1"), capture_output=True, text=True, timeout=60)
     assert r.returncode == 0, r.stdout + r.stderr
-    out = _run_gpu_suite(cusim_lib, {"CUSIM_HOSTCHECK": "1", "CUSIM_ASYNC": "1"}, ["tests/test_gpu_parity.py", "tests/test_gpu_ros.py", "tests/test_gpu_zz_unmeasured.py"])
+    out = _run_gpu_suite(cusim_lib, {"CUSIM_HOSTCHECK": "1", "CUSIM_ASYNC": "1"}, ["tests/test_gpu_parity.py", "tests/test_gpu_ros.py", "tests/test_gpu_zz_legacy_kernels.py"])
     assert " passed" in out and "failed" not in out

@@ -313,6 +313,40 @@ def test_v5_palette_overflow_and_mode_commit(oracle):
     _roundtrip_check(*_int_cloud([("c", F.UINT64, w)], n), oracle)
 
 
+def test_v5_committed_mode_can_exceed_max_compressed_size(oracle):
+    # The V5 mode of a field is committed on the first 4096 values and applied blindly afterwards: a uint64 field that is
+    # constant at first (DeltaRle) and random later costs 11 bytes per value, more than MaxCompressedSize budgets. The
+    # reference then throws "Output buffer too small for uncompressed chunk" (chunk_writer.cpp:33-35) unless the caller's
+    # buffer happens to be larger; the kernels must do exactly that and never store past the capacity they were given.
+    F = cb.FieldType
+    n = 100_000
+    rng = np.random.default_rng(1)
+    v = rng.integers(0, 2**63, n, dtype=np.int64).astype(np.uint64) * np.uint64(2) + np.uint64(1)
+    v[:4096] = np.uint64(7)
+    info, cloud = _int_cloud([("u64", F.UINT64, v)], n, with_xyz=False)
+    need = cb.MaxCompressedSize(info, n, True)
+    enc = cb.PointcloudEncoder(info)
+    for extra in (0, 64):
+        with pytest.raises(RuntimeError, match="too small"):
+            oracle.encode(info, cloud, cap=need + extra)
+        guard = np.full(need + extra + 4096, 0xA5, dtype=np.uint8)
+        with pytest.raises(RuntimeError, match="too small"):
+            enc.encode_into(cloud, guard[:need + extra])
+        assert np.all(guard[need + extra:] == 0xA5)          # host path: nothing behind the caller's capacity was touched
+        d_in, d_out = _Dev(src=cloud), _Dev(src=guard)
+        with pytest.raises(RuntimeError, match="too small"):
+            enc.encode_batch_device(enc.make_device_batch([d_in.ptr], [cloud.nbytes], [d_out.ptr], [need + extra]), want_sizes=True)
+        assert np.all(d_out.numpy()[need + extra:] == 0xA5)  # device path: no store past the capacity
+    big = need + 2 * n
+    expect = oracle.encode(info, cloud, cap=big)
+    assert len(expect) > need
+    out = np.zeros(big, dtype=np.uint8)
+    w = enc.encode_into(cloud, out)
+    assert bytes(out[:w]) == expect
+    # the next call on the same handle is unaffected by the earlier failures
+    _roundtrip_check(*_int_cloud([("u16", F.UINT16, (np.arange(5000) % 7).astype(np.uint16))], 5000), oracle)
+
+
 def test_v5_section_decode_errors():
     info, cloud = synth.cloud_c3(40_000, seed=1)
     enc = cb.PointcloudEncoder(info)
@@ -486,7 +520,7 @@ def test_c4_velodyne_mixed_layout(oracle):
         assert bytes(o[:s]) == oracle.encode(info, c)
 
 
-@pytest.mark.parametrize("mode", ["seq"])  # "par" / "chase": tests/test_gpu_zz_unmeasured.py (kernels without a hardware run yet)
+@pytest.mark.parametrize("mode", ["par", "chase", "seq"])
 @pytest.mark.parametrize("version", [5, 4])
 def test_raw_fields_in_the_stream(oracle, monkeypatch, mode, version):
     # uint8 fields are raw Copy bytes between the varints: point boundaries by pointer jumping (decode_mixed_kernel, "par";
@@ -500,7 +534,7 @@ def test_raw_fields_in_the_stream(oracle, monkeypatch, mode, version):
     _roundtrip_check(info, cloud, oracle, fill=0)
 
 
-@pytest.mark.parametrize("mode", ["seq"])  # "par": tests/test_gpu_zz_unmeasured.py
+@pytest.mark.parametrize("mode", ["par", "seq"])
 def test_gorilla_field_positions(oracle, monkeypatch, mode):
     # a Gorilla record (FLOAT64 without a resolution) in the middle of the point, next to scalar lossy floats and a raw
     # uint8; two Gorilla fields in one point (the parallel decoder handles one: the per-chunk parser takes over);
@@ -576,6 +610,27 @@ def test_headline_batch_every_frame(oracle):
         oracle.decode(expect, want)
         assert bytes(d_blob[k].numpy()[:sizes[k]]) == expect, k
         assert np.array_equal(d_out[k].numpy(), want), k
+
+
+@pytest.mark.parametrize("mode", ["seq", "tile"])
+def test_overlapping_fields_are_stored_in_field_order(oracle, monkeypatch, mode):
+    # Two fields covering the same bytes of a point (a forged offset, or rgb / rgba declared at one offset): the
+    # reference stores per point in field order, the last writer wins (v4_codec.cpp:85-117). Parallel decoders promise
+    # no order between fields, so such plans go to the per-chunk sequential parser.
+    monkeypatch.setenv("CLDN_B200_DECODE_MODE", mode)
+    cases = [synth.cloud_c2(40_000, seed=3), synth.cloud_c3(36_000, seed=8), synth.cloud_livox(9000, seed=5, version=4)]
+    for info, cloud in cases:
+        blob = oracle.encode(info, cloud)
+        _, hdr = cb.DecodeHeader(blob)
+        for (a, b, shift) in ((1, 0, 0), (2, 1, 2), (0, 2, 0)):   # field a moved onto / across field b
+            mod, _ = cb.DecodeHeader(blob)
+            mod.fields[a].offset = mod.fields[b].offset + shift
+            n = info.width * info.point_step
+            want = np.full(n, 0x4D, dtype=np.uint8)
+            oracle.decode_payload(mod, blob[hdr:], want)
+            got = np.full(n, 0x4D, dtype=np.uint8)
+            cb.PointcloudDecoder().decode(mod, blob[hdr:], got)
+            assert np.array_equal(got, want), (a, b, shift, [f.name for f in info.fields])
 
 
 @pytest.mark.parametrize("mode", ["seq", "tile"])
