@@ -27,11 +27,12 @@ constexpr int kFT = 128;                     // threads per CTA
 constexpr int kFW = kFT / 32;                // warps
 constexpr int kFP = 8;                       // points per thread and tile
 constexpr int kFTilePts = kFT * kFP;         // 1024 points per tile
-constexpr int kFMaxUnits = 19;               // 8-byte units per thread (odd: conflict-free LDS.64 at any count)
+constexpr int kFUnit = 16;                   // bytes per unit: a thread's slice of the window is `nu` units (nu odd: the
+constexpr int kFMaxUnits = 11;               //   16-byte reads of a warp are then conflict-free at any count)
 constexpr int kFLead = 16;                   // bytes in front of the window (never read as data; keeps indices > 0)
-constexpr int kFWinBytes = kFMaxUnits * kFT * 8;        // 19456
+constexpr int kFWinBytes = kFMaxUnits * kFT * kFUnit;   // 22528
 constexpr int kFWinAlloc = kFLead + kFWinBytes + 32;    // reads run at most 7 bytes past a value's last byte
-constexpr int kFMaskWords = (kFMaxUnits * 8 + 31) / 32; // 5 words of terminator bits per thread
+constexpr int kFMaskWords = (kFMaxUnits * kFUnit + 31) / 32; // 6 words of terminator bits per thread
 static_assert(kFTilePts * 16 <= kFWinAlloc, "the float staging aliases the window");
 
 struct FastShared {
@@ -42,6 +43,13 @@ struct FastShared {
   uint32_t next_cursor;               // window byte index (incl. kFLead) one past the tile's last value
   uint32_t chunk;                     // claimed chunk
   unsigned long long desc[2];
+  // the claimed chunk, re-read from here in every tile instead of living in registers across the tile loop
+  const uint8_t* body;                // first byte of the chunk body
+  const uint8_t* pay_lo;              // the frame's payload [pay_lo, pay_hi): nothing outside may be read
+  const uint8_t* pay_hi;
+  uint8_t* out;                       // output of the chunk's first point
+  uint32_t size;                      // body bytes
+  uint32_t n_points;
 };
 
 // (a & m) | (b & ~m) in one LOP3; min of three in one VIMNMX3
@@ -49,6 +57,20 @@ __device__ __forceinline__ uint32_t bitselect(uint32_t m, uint32_t a, uint32_t b
   uint32_t d;
   asm("lop3.b32 %0, %1, %2, %3, 0xCA;" : "=r"(d) : "r"(m), "r"(a), "r"(b));
   return d;
+}
+// 16 bytes at g, byte by byte, reading only inside [lo, hi); bytes outside read as 0x80 (never terminate anything).
+__device__ __noinline__ uint4 load_vector_bounded(const uint8_t* g, const uint8_t* lo, const uint8_t* hi) {
+  uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+#pragma unroll 1
+  for (int b = 0; b < 16; ++b) {
+    const uint8_t* gb = g + b;
+    const uint32_t v = ((gb >= lo && gb < hi) ? static_cast<uint32_t>(*gb) : 0x80u) << (8 * (b & 3));
+    if (b < 4) w0 |= v; else if (b < 8) w1 |= v; else if (b < 12) w2 |= v; else w3 |= v;
+  }
+  return make_uint4(w0, w1, w2, w3);
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
 __device__ __forceinline__ uint32_t min3_u32(uint32_t a, uint32_t b, uint32_t c) {
 #ifdef CLDN_CUSIM
@@ -120,13 +142,23 @@ __global__ void __launch_bounds__(kFT, 7) decode_floatn_fast_kernel(const DecLau
       }
       fidx = lo;
     }
-    const DecFrame F = L.frames[fidx];
-    const uint32_t chunk = gc - F.chunk_begin;
-    const uint32_t n_points = min(kChunkPoints, F.n_points - chunk * kChunkPoints);
-    const uint8_t* body = F.payload + sh.desc[0];
-    const uint32_t size = static_cast<uint32_t>(sh.desc[1]);
-    const uint8_t* pay_end = F.payload + F.payload_bytes;
-    uint8_t* out = F.out + static_cast<size_t>(chunk) * kChunkPoints * step;
+    const uint32_t n_points = [&] {
+      const DecFrame F = L.frames[fidx];
+      const uint32_t chunk = gc - F.chunk_begin;
+      const uint32_t n = min(kChunkPoints, F.n_points - chunk * kChunkPoints);
+      if (threadIdx.x == 0) {
+        sh.body = F.payload + sh.desc[0];
+        sh.size = static_cast<uint32_t>(sh.desc[1]);
+        sh.pay_lo = F.payload;
+        sh.pay_hi = F.payload + F.payload_bytes;
+        sh.out = F.out + static_cast<size_t>(chunk) * kChunkPoints * step;
+        sh.n_points = n;
+      }
+      return n;
+    }();
+    __syncthreads();
+    uint8_t* const out = sh.out;
+    const uint32_t size = sh.size;
     const bool aligned4 = (((reinterpret_cast<uintptr_t>(out) | step | o0 | o1 | o2 | (K == 4 ? o3 : 0u)) & 3u) == 0u) &&
         o0 != CLDN_SKIP_STORE_OFFSET && o1 != CLDN_SKIP_STORE_OFFSET && o2 != CLDN_SKIP_STORE_OFFSET && (K < 4 || o3 != CLDN_SKIP_STORE_OFFSET);
     const bool dense4 = K == 4 && aligned4 && step == 16u && o0 == 0u && o1 == 4u && o2 == 8u && o3 == 12u &&
@@ -144,54 +176,64 @@ __global__ void __launch_bounds__(kFT, 7) decode_floatn_fast_kernel(const DecLau
       const uint32_t n_vals = tile_pts * K;
       const uint32_t remaining = size - cursor;                                // stream bytes from the cursor on
       if (remaining < n_vals) { redo = true; break; }                          // not even one byte per value left
+      const uint8_t* const body = sh.body;
       const uint8_t* first = body + cursor;
       const uint32_t c0 = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(first) & 15u);
       const uint8_t* abase = first - c0;                                       // window byte i <-> abase[i]
       if (est == 0) est = static_cast<uint32_t>((static_cast<uint64_t>(size) * tile_pts) / n_points);
       uint32_t want = c0 + est + (est >> 3) + 96u;
-      uint32_t nu = (want + 1023u) >> 10;
+      uint32_t nu = (want + (kFT * kFUnit - 1)) / (kFT * kFUnit);
       nu = nu < 3u ? 3u : (nu | 1u);
       if (nu > kFMaxUnits) nu = kFMaxUnits;
       uint32_t m[kFMaskWords];
       uint32_t total, incl, cnt;
       while (true) {
         // ---- stage the window: coalesced 16-byte loads, vector v <-> bytes [16 v, 16 v + 16) ----
-        const uint32_t n_vec = nu * (kFT * 8 / 16);
-        for (uint32_t v = threadIdx.x; v < n_vec; v += kFT) {
-          const uint8_t* g = abase + 16u * v;
-          uint4 q;
-          if (g >= F.payload && g + 16 <= pay_end) {
-            q = __ldcs(reinterpret_cast<const uint4*>(g));
-          } else {
-            uint32_t w[4] = {0, 0, 0, 0};
-            for (int b = 0; b < 16; ++b) {
-              const uint8_t* gb = g + b;
-              const uint32_t byte = (gb >= F.payload && gb < pay_end) ? *gb : 0x80u;
-              w[b >> 2] |= byte << (8 * (b & 3));
-            }
-            q = make_uint4(w[0], w[1], w[2], w[3]);
+        // vectors [v_lo, v_hi) lie completely inside the payload (only the very first / last ones of a frame can stick out)
+        const uint32_t n_vec = nu * kFT;
+        const uint8_t* const pay_lo = sh.pay_lo;
+        const uint8_t* const pay_end = sh.pay_hi;
+        const uint32_t v_lo = abase < pay_lo ? 1u : 0u;
+        const uint64_t room = static_cast<uint64_t>(pay_end - abase) >> 4;
+        const uint32_t v_hi = room < n_vec ? static_cast<uint32_t>(room) : n_vec;
+        const uint4* gv = reinterpret_cast<const uint4*>(abase) + threadIdx.x;
+        uint4* sv = reinterpret_cast<uint4*>(win + kFLead) + threadIdx.x;
+#pragma unroll
+        for (int r0 = 0; r0 < kFMaxUnits; r0 += 6) {       // up to 6 loads in flight per thread
+          uint4 q[6];
+#pragma unroll
+          for (int r = 0; r < 6; ++r) {
+            const uint32_t v = static_cast<uint32_t>(r0 + r) * kFT + threadIdx.x;
+            if (r0 + r < static_cast<int>(nu) && v >= v_lo && v < v_hi) q[r] = __ldcs(gv + (r0 + r) * kFT);
           }
-          *reinterpret_cast<uint4*>(win + kFLead + 16u * v) = q;
+#pragma unroll
+          for (int r = 0; r < 6; ++r) {
+            const uint32_t v = static_cast<uint32_t>(r0 + r) * kFT + threadIdx.x;
+            if (r0 + r < static_cast<int>(nu)) {
+              if (!(v >= v_lo && v < v_hi)) q[r] = load_vector_bounded(abase + 16u * v, pay_lo, pay_end);
+              sv[(r0 + r) * kFT] = q[r];
+            }
+          }
         }
         __syncthreads();
-        // ---- terminator bits of my slice: nu units of 8 bytes, bit i of the mask <-> slice byte i ----
-        const uint32_t slice0 = threadIdx.x * nu * 8u;                         // window byte of my first unit
+        // ---- terminator bits of my slice: nu units of 16 bytes, bit i of the mask <-> slice byte i ----
+        const uint32_t slice0 = threadIdx.x * nu * kFUnit;                     // window byte of my first unit
 #pragma unroll
         for (int r = 0; r < kFMaskWords; ++r) m[r] = 0;
 #pragma unroll
         for (int u = 0; u < kFMaxUnits; ++u) {
           if (u < static_cast<int>(nu)) {
-            const uint2 q = *reinterpret_cast<const uint2*>(win + kFLead + slice0 + 8u * u);
-            const uint32_t x0 = ~q.x & 0x80808080u, x1 = ~q.y & 0x80808080u;
+            const uint4 q = *reinterpret_cast<const uint4*>(win + kFLead + slice0 + kFUnit * u);
             // (x * 0x00204081) >> 28 collects bits 7, 15, 23, 31 into a nibble
-            const uint32_t b8 = ((x0 * 0x00204081u) >> 28) | (((x1 * 0x00204081u) >> 28) << 4);
-            m[u / 4] |= b8 << (8 * (u % 4));
+            const uint32_t b16 = (((~q.x & 0x80808080u) * 0x00204081u) >> 28) | ((((~q.y & 0x80808080u) * 0x00204081u) >> 28) << 4) |
+                                 ((((~q.z & 0x80808080u) * 0x00204081u) >> 28) << 8) | ((((~q.w & 0x80808080u) * 0x00204081u) >> 28) << 12);
+            m[u / 2] |= b16 << (16 * (u % 2));
           }
         }
         // bytes in front of the cursor (thread 0, c0 < 16) and past the end of the chunk are not values
         if (threadIdx.x == 0) m[0] &= ~((1u << c0) - 1u);
         const uint32_t wend = c0 + remaining;                                  // window byte one past the chunk
-        if (wend < nu * (kFT * 8u)) {
+        if (wend < nu * (kFT * kFUnit)) {
 #pragma unroll
           for (int r = 0; r < kFMaskWords; ++r) {
             const uint32_t b0 = slice0 + 32u * r;
@@ -218,8 +260,8 @@ __global__ void __launch_bounds__(kFT, 7) decode_floatn_fast_kernel(const DecLau
         for (int w = 0; w < kFW; ++w) total += sh.wcnt[w];
         if (total >= n_vals) break;
         // too few values in the window: widen it if the chunk has more bytes, otherwise give the chunk to the careful kernel
-        if (nu >= kFMaxUnits || wend <= nu * (kFT * 8u)) { redo = true; break; }
-        nu = min(static_cast<uint32_t>(kFMaxUnits), nu + 4u);
+        if (nu >= kFMaxUnits || wend <= nu * (kFT * kFUnit)) { redo = true; break; }
+        nu = min(static_cast<uint32_t>(kFMaxUnits), nu + 2u);
         __syncthreads();  // everybody has read wcnt before the next round overwrites it
       }
       if (redo) break;
@@ -250,7 +292,7 @@ __global__ void __launch_bounds__(kFT, 7) decode_floatn_fast_kernel(const DecLau
           const uint32_t c = __popc(word);
           if (wbase == 32u * (r - 1) && n >= c) { n -= c; word = sh.masks[r][owner]; wbase = 32u * r; }
         }
-        start = kFLead + owner * nu * 8u + wbase + nth_set_bit32(word, n, kNthBit) + 1u;
+        start = kFLead + owner * nu * kFUnit + wbase + nth_set_bit32(word, n, kNthBit) + 1u;
       }
 
       // ---- parse my 8 points; P[j][f] = sum of my deltas of field f up to and including point j ----
@@ -332,6 +374,12 @@ __global__ void __launch_bounds__(kFT, 7) decode_floatn_fast_kernel(const DecLau
         base[f] = static_cast<int32_t>(b + static_cast<uint32_t>(inc[f]) - static_cast<uint32_t>(tot[f]));
       }
       const uint32_t ncur = sh.next_cursor;
+      const uint32_t used = ncur - (kFLead + c0);
+      // the next tile's bytes are asked into L2 now (its loads are issued behind this tile's conversion and copy-out)
+      if (pt0 + kFTilePts < n_points) {
+        const uint32_t ahead = cursor + used + threadIdx.x * 128u;
+        if (ahead < size && threadIdx.x * 128u < used + (used >> 2) + 256u) prefetch_l2(body + ahead);
+      }
       // ---- floats into my warp's staging slots (16 bytes per point; slot of point j of lane l: 8 l + (j ^ (l & 7))) ----
       uint4* wst = ostage + warp * (32 * kFP);
 #pragma unroll
@@ -346,32 +394,43 @@ __global__ void __launch_bounds__(kFT, 7) decode_floatn_fast_kernel(const DecLau
       }
       __syncwarp();
       // ---- copy-out: lane l of iteration i takes point 32 i + l of the warp's 256 ----
+      // its slot: owner lane 4 i + (l >> 3), point l & 7 -> 8 (4 i + (l >> 3)) + ((l & 7) ^ ((4 i + (l >> 3)) & 7))
       const uint32_t wp0 = pt0 + warp * (32 * kFP);
       const uint32_t wn = wp0 < n_points ? min(static_cast<uint32_t>(32 * kFP), n_points - wp0) : 0u;
+      const uint32_t lh = lane >> 3, ll = lane & 7;
+      const uint4* rd_even = wst + 8 * lh + (ll ^ lh);          // i even: (4 i + lh) & 7 == lh
+      const uint4* rd_odd = wst + 8 * lh + (ll ^ (lh + 4));     // i odd:  (4 i + lh) & 7 == lh + 4
+      uint8_t* dst0 = sh.out + static_cast<size_t>(wp0 + lane) * step;
+      if (dense4 && wn == static_cast<uint32_t>(32 * kFP)) {
 #pragma unroll
-      for (int i = 0; i < kFP; ++i) {
-        const uint32_t q = 32u * i + lane;
-        if (q < wn) {
-          const uint32_t ol = q >> 3;
-          const uint4 v = wst[8 * ol + ((q & 7u) ^ (ol & 7u))];
-          uint8_t* dst = out + static_cast<size_t>(wp0 + q) * step;
-          if (dense4) {
-            __stcs(reinterpret_cast<uint4*>(dst), v);
-          } else if (aligned4) {
-            __stcs(reinterpret_cast<unsigned int*>(dst + o0), v.x);
-            __stcs(reinterpret_cast<unsigned int*>(dst + o1), v.y);
-            __stcs(reinterpret_cast<unsigned int*>(dst + o2), v.z);
-            if (K == 4) __stcs(reinterpret_cast<unsigned int*>(dst + o3), v.w);
-          } else {
-            const uint32_t vv[4] = {v.x, v.y, v.z, v.w};
+        for (int i = 0; i < kFP; ++i) {
+          const uint4 v = ((i & 1) ? rd_odd : rd_even)[32 * i];
+          __stcs(reinterpret_cast<uint4*>(dst0 + 512 * i), v);
+        }
+      } else {
 #pragma unroll
-            for (int f = 0; f < K; ++f) {
-              if (off[f] != CLDN_SKIP_STORE_OFFSET) store_u32(dst + off[f], vv[f]);
+        for (int i = 0; i < kFP; ++i) {
+          const uint32_t q = 32u * i + lane;
+          if (q < wn) {
+            const uint4 v = ((i & 1) ? rd_odd : rd_even)[32 * i];
+            uint8_t* dst = dst0 + static_cast<size_t>(32 * i) * step;
+            if (dense4) {
+              __stcs(reinterpret_cast<uint4*>(dst), v);
+            } else if (aligned4) {
+              __stcs(reinterpret_cast<unsigned int*>(dst + o0), v.x);
+              __stcs(reinterpret_cast<unsigned int*>(dst + o1), v.y);
+              __stcs(reinterpret_cast<unsigned int*>(dst + o2), v.z);
+              if (K == 4) __stcs(reinterpret_cast<unsigned int*>(dst + o3), v.w);
+            } else {
+              const uint32_t vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+              for (int f = 0; f < K; ++f) {
+                if (off[f] != CLDN_SKIP_STORE_OFFSET) store_u32(dst + off[f], vv[f]);
+              }
             }
           }
         }
       }
-      const uint32_t used = ncur - (kFLead + c0);
       est = used;
       cursor += used;
       __syncthreads();  // the staging slots alias the window the next tile is about to load

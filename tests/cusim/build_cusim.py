@@ -36,6 +36,7 @@ PTX = {
     "lop3.b32": lambda outs, ins, tmpl="": f"{outs[0]} = ::cusim::lop3({ins[0]}, {ins[1]}, {ins[2]}, {tmpl.rstrip(';').split(',')[-1].strip()});",
     # bmsk.clamp.b32 d, a, b: b bits set starting at bit a (both clamped to 32)
     "bmsk.clamp.b32": lambda outs, ins: f"{outs[0]} = ::cusim::bmsk_clamp({ins[0]}, {ins[1]});",
+    "prefetch.global.L2": lambda outs, ins: "((void)0);",
     "shl.b32": lambda outs, ins: f"{outs[0]} = (({ins[1]}) > 31u) ? 0u : (static_cast<unsigned>({ins[0]}) << ({ins[1]}));",
     # max.NaN.f32: NaN if either operand is NaN
     "max.NaN.f32": lambda outs, ins: f"{outs[0]} = (std::isnan({ins[0]}) || std::isnan({ins[1]})) ? std::numeric_limits<float>::quiet_NaN() : fmaxf({ins[0]}, {ins[1]});",
