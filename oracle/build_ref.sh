@@ -13,7 +13,8 @@ if [ ! -d "$REF/src" ]; then
   exit 3
 fi
 mkdir -p "$OUT"
-g++ -std=c++20 -O2 -msse4.1 -fPIC -shared \
+# -O3 -DNDEBUG: the reference's own default build type is Release (cloudini_lib/CMakeLists.txt:5-8)
+g++ -std=c++20 -O3 -DNDEBUG -msse4.1 -fPIC -shared \
     -I"$REF/include" -I"$REF/src" -I"$HERE/shim" \
     "$REF"/src/{chunk_writer,cloudini,codec_common,field_encoder,field_decoder,v4_codec,v5_codec,ros_msg_utils}.cpp \
     "$HERE/ref_wrapper.cpp" \

@@ -200,6 +200,80 @@ double ref_time_decode(const uint8_t* blob, size_t blob_bytes, int reps, int thr
   }
 }
 
+// ---- bench.py --impl reference: the whole reference arm without any product code in the process -------------------------
+// The EncodingInfo of BASELINE configs[1] (x y z intensity FLOAT32 at 1 mm, LOSSY, stage 1 only) is built HERE, so the
+// reference process never needs the product library to render a YAML header. `threads` workers, each with a PRIVATE copy
+// of one of the `n_clouds` distinct input clouds (worker t takes cloud t % n_clouds), its own encoder / decoder instance
+// and its own output buffers, run `passes` encode passes, then `passes` decode passes of the blob they produced.
+// Timed regions as in mcap_codec_benchmark.cpp:454-457 / 509-512 (encode / decode call only, buffers pre-sized).
+// Returns 0 and fills enc_s / dec_s (wall clock over all workers), -1 on exception.
+int ref_bench_xyzi(const uint8_t* clouds, size_t cloud_bytes, int n_clouds, float resolution, int threads, int passes,
+                   double* enc_s, double* dec_s, size_t* blob_bytes_out) {
+  try {
+    Cloudini::EncodingInfo info;
+    const char* names[4] = {"x", "y", "z", "intensity"};
+    for (int k = 0; k < 4; ++k) {
+      Cloudini::PointField f;
+      f.name = names[k];
+      f.offset = 4u * k;
+      f.type = Cloudini::FieldType::FLOAT32;
+      f.resolution = resolution;
+      info.fields.push_back(f);
+    }
+    info.point_step = 16;
+    info.width = static_cast<uint32_t>(cloud_bytes / 16);
+    info.height = 1;
+    info.encoding_opt = Cloudini::EncodingOptions::LOSSY;
+    info.compression_opt = Cloudini::CompressionOption::NONE;
+    info.use_threads = false;
+    const size_t cap = Cloudini::MaxCompressedSize(info, info.width, true);
+    std::vector<std::vector<uint8_t>> ins(threads), blobs(threads), outs(threads);
+    std::vector<size_t> sizes(threads, 0);
+    for (int t = 0; t < threads; ++t) {
+      const uint8_t* src = clouds + static_cast<size_t>(t % n_clouds) * cloud_bytes;
+      ins[t].assign(src, src + cloud_bytes);
+      blobs[t].resize(cap);
+      outs[t].resize(cloud_bytes);
+    }
+    auto run = [&](auto&& work) {
+      const auto t0 = std::chrono::steady_clock::now();
+      std::vector<std::thread> pool;
+      for (int t = 1; t < threads; ++t) pool.emplace_back(work, t);
+      work(0);
+      for (auto& th : pool) th.join();
+      return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    };
+    std::string first_error;
+    *enc_s = run([&](int t) {
+      try {
+        Cloudini::PointcloudEncoder enc(info);
+        for (int r = 0; r < passes; ++r) {
+          Cloudini::BufferView view(blobs[t].data(), blobs[t].size());
+          sizes[t] = enc.encode(Cloudini::ConstBufferView(ins[t].data(), ins[t].size()), view, true);
+        }
+      } catch (const std::exception& e) { if (t == 0) first_error = e.what(); }
+    });
+    *dec_s = run([&](int t) {
+      try {
+        Cloudini::ConstBufferView probe(blobs[t].data(), sizes[t]);
+        Cloudini::EncodingInfo hinfo = Cloudini::DecodeHeader(probe);
+        const size_t header_bytes = sizes[t] - probe.size();
+        Cloudini::PointcloudDecoder dec;
+        for (int r = 0; r < passes; ++r) {
+          dec.decode(hinfo, Cloudini::ConstBufferView(blobs[t].data() + header_bytes, sizes[t] - header_bytes),
+                     Cloudini::BufferView(outs[t].data(), outs[t].size()));
+        }
+      } catch (const std::exception& e) { if (t == 0) first_error = e.what(); }
+    });
+    if (!first_error.empty()) { g_err = first_error; return -1; }
+    if (blob_bytes_out) *blob_bytes_out = sizes[0];
+    return 0;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return -1;
+  }
+}
+
 // ---- N3: applyVizLossyPreprocessing on a raw cloud described by the YAML header text ------------------------------------
 // Returns the number of surviving points (-1 on exception); the rewritten cloud goes to `out`, the updated EncodingInfo
 // (width, height, FLOAT64 resolutions) to yaml_out.
