@@ -120,6 +120,7 @@ def lib():
                            "(tests/test_cusim_kernels.py sets CLDN_B200_ALLOW_EMULATION=tests-only for its sub-runs)")
     L.cldn_b200_last_error.restype = C.c_char_p
     L.cldn_b200_kernel_launch_count.restype = C.c_uint64
+    L.cldn_b200_bind_host_thread_to_device.argtypes = [C.c_int]
     L.cldn_b200_info_init.argtypes = [C.POINTER(_CInfo)]
     L.cldn_b200_info_to_yaml.argtypes = [C.POINTER(_CInfo), C.c_char_p, sz, C.POINTER(sz)]
     L.cldn_b200_info_from_yaml.argtypes = [C.c_char_p, sz, C.POINTER(_CInfo)]
@@ -165,6 +166,12 @@ def _check(rc: int):
 
 def kernel_launch_count() -> int:
     return int(lib().cldn_b200_kernel_launch_count())
+
+
+def bind_host_thread_to_device(device: int = -1) -> int:
+    """Pins the calling thread (and threads it starts later) to the CPUs next to `device` (NVML's CPU affinity), so that
+    pinned buffers allocated afterwards are NUMA-local to the GPU. Returns the number of CPUs in the set (0: unchanged)."""
+    return int(lib().cldn_b200_bind_host_thread_to_device(device))
 
 
 def _to_c(info: EncodingInfo) -> _CInfo:

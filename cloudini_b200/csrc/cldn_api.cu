@@ -3,6 +3,7 @@
 // fails with CLDN_ERR_CUDA.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <sched.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -304,6 +305,39 @@ struct cldn_encoder {
 extern "C" {
 
 uint64_t cldn_b200_kernel_launch_count(void) { return kernel_launch_count(); }
+
+int cldn_b200_bind_host_thread_to_device(int device) {
+  if (int rc = select_device(device)) return rc;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  char bus_id[64] = {0};
+  if (cudaDeviceGetPCIBusId(bus_id, sizeof(bus_id), dev) != cudaSuccess) return 0;
+  // NVML through dlopen: the library has no link-time dependency on it
+  static void* nvml = dlopen("libnvidia-ml.so.1", RTLD_NOW);
+  if (!nvml) return 0;
+  using InitFn = int (*)();
+  using HandleFn = int (*)(const char*, void**);
+  using AffFn = int (*)(void*, unsigned int, unsigned long*);
+  InitFn init = reinterpret_cast<InitFn>(dlsym(nvml, "nvmlInit_v2"));
+  HandleFn by_bus = reinterpret_cast<HandleFn>(dlsym(nvml, "nvmlDeviceGetHandleByPciBusId_v2"));
+  AffFn affinity = reinterpret_cast<AffFn>(dlsym(nvml, "nvmlDeviceGetCpuAffinity"));
+  if (!init || !by_bus || !affinity || init() != 0) return 0;
+  void* handle = nullptr;
+  if (by_bus(bus_id, &handle) != 0) return 0;
+  constexpr unsigned kWords = 16;  // 1024 CPUs
+  unsigned long words[kWords] = {0};
+  if (affinity(handle, kWords, words) != 0) return 0;
+  cpu_set_t set;
+  CPU_ZERO(&set);
+  int count = 0;
+  for (unsigned w = 0; w < kWords; ++w) {
+    for (unsigned b = 0; b < 8 * sizeof(unsigned long); ++b) {
+      if ((words[w] >> b) & 1ul) { CPU_SET(w * 8 * sizeof(unsigned long) + b, &set); ++count; }
+    }
+  }
+  if (count == 0 || sched_setaffinity(0, sizeof(set), &set) != 0) return 0;
+  return count;
+}
 
 int cldn_b200_encoder_create(const cldn_info_t* info, int device, void* stream, cldn_encoder_t** out) {
   if (!info || !out) { set_error("null argument"); return CLDN_ERR_INVALID_ARGUMENT; }

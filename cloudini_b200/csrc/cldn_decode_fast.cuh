@@ -198,21 +198,28 @@ __global__ void __launch_bounds__(kFT, 7) decode_floatn_fast_kernel(const DecLau
         const uint32_t v_hi = room < n_vec ? static_cast<uint32_t>(room) : n_vec;
         const uint4* gv = reinterpret_cast<const uint4*>(abase) + threadIdx.x;
         uint4* sv = reinterpret_cast<uint4*>(win + kFLead) + threadIdx.x;
+        if (v_lo == 0u && v_hi == n_vec) {
+          // the whole window lies inside the payload (every tile but the first / last few of a frame): plain loads, all of
+          // a thread's requests in flight before the first store
 #pragma unroll
-        for (int r0 = 0; r0 < kFMaxUnits; r0 += 6) {       // up to 6 loads in flight per thread
-          uint4 q[6];
+          for (int r0 = 0; r0 < kFMaxUnits; r0 += 4) {   // 4 requests in flight per thread and round (16 registers)
+            if (r0 < static_cast<int>(nu)) {
+              uint4 q[4];
 #pragma unroll
-          for (int r = 0; r < 6; ++r) {
-            const uint32_t v = static_cast<uint32_t>(r0 + r) * kFT + threadIdx.x;
-            if (r0 + r < static_cast<int>(nu) && v >= v_lo && v < v_hi) q[r] = __ldcs(gv + (r0 + r) * kFT);
-          }
+              for (int r = 0; r < 4; ++r) {
+                if (r0 + r < static_cast<int>(nu)) q[r] = __ldcs(gv + (r0 + r) * kFT);
+              }
 #pragma unroll
-          for (int r = 0; r < 6; ++r) {
-            const uint32_t v = static_cast<uint32_t>(r0 + r) * kFT + threadIdx.x;
-            if (r0 + r < static_cast<int>(nu)) {
-              if (!(v >= v_lo && v < v_hi)) q[r] = load_vector_bounded(abase + 16u * v, pay_lo, pay_end);
-              sv[(r0 + r) * kFT] = q[r];
+              for (int r = 0; r < 4; ++r) {
+                if (r0 + r < static_cast<int>(nu)) sv[(r0 + r) * kFT] = q[r];
+              }
             }
+          }
+        } else {
+#pragma unroll 1
+          for (uint32_t r = 0; r < nu; ++r) {
+            const uint32_t v = r * kFT + threadIdx.x;
+            sv[r * kFT] = (v >= v_lo && v < v_hi) ? __ldcs(gv + r * kFT) : load_vector_bounded(abase + 16u * v, pay_lo, pay_end);
           }
         }
         __syncthreads();
@@ -382,6 +389,8 @@ __global__ void __launch_bounds__(kFT, 7) decode_floatn_fast_kernel(const DecLau
       }
       // ---- floats into my warp's staging slots (16 bytes per point; slot of point j of lane l: 8 l + (j ^ (l & 7))) ----
       uint4* wst = ostage + warp * (32 * kFP);
+      uint4* const my_slots = wst + 8 * lane;
+      const uint32_t lx = lane & 7;
 #pragma unroll
       for (int j = 0; j < kFP; ++j) {
         uint32_t fl[4] = {0, 0, 0, 0};
@@ -390,7 +399,7 @@ __global__ void __launch_bounds__(kFT, 7) decode_floatn_fast_kernel(const DecLau
           const int32_t v = static_cast<int32_t>(static_cast<uint32_t>(base[f]) + static_cast<uint32_t>(P[j][f]));
           fl[f] = __float_as_uint(__fmul_rn(__int2float_rn(v), mul[f]));
         }
-        wst[8 * lane + (j ^ (lane & 7))] = make_uint4(fl[0], fl[1], fl[2], fl[3]);
+        my_slots[j ^ lx] = make_uint4(fl[0], fl[1], fl[2], fl[3]);
       }
       __syncwarp();
       // ---- copy-out: lane l of iteration i takes point 32 i + l of the warp's 256 ----

@@ -26,10 +26,9 @@ constexpr int kET = 128;                  // threads per CTA
 constexpr int kEW = kET / 32;
 constexpr int kEP = 8;                    // points per thread and tile
 constexpr int kETilePts = kET * kEP;      // 1024
-constexpr int kEGroup = 1;                // tiles per CTA. More than one serialises a frame: the next group's look-back waits
-                                          // for this CTA's LAST tile, which it reaches only after packing the earlier ones
-                                          // (measured: 4 tiles per CTA = 3.6 ms instead of 0.35 ms for 32 x 1M points)
-constexpr int kEStageBytes = kETilePts * 20 + 64;  // worst case of the careful path: 5 bytes per value
+constexpr int kEBufBytes = kETilePts * 16;          // one input buffer = one tile of transposed points (later: its staged bytes)
+constexpr int kECarefulBytes = kETilePts * 20 + 64; // worst case of the exact path: 5 bytes per value
+constexpr int kESmemBytes = (2 * kEBufBytes > kECarefulBytes ? 2 * kEBufBytes : kECarefulBytes) + 64;
 
 struct EncFastShared {
   uint32_t wtot[kEW];        // bytes per warp
@@ -38,6 +37,30 @@ struct EncFastShared {
   uint32_t scan[kET / 32 + 1];
 };
 
+// cp.async (LDGSTS): 16 bytes global -> shared without a register round trip; groups complete in commit order
+__device__ __forceinline__ void async_copy16(void* smem_dst, const void* gmem_src) {
+#ifdef CLDN_CUSIM
+  *reinterpret_cast<uint4*>(smem_dst) = *reinterpret_cast<const uint4*>(gmem_src);
+#else
+  const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+#endif
+}
+__device__ __forceinline__ void async_commit() {
+#ifndef CLDN_CUSIM
+  asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void async_wait_all_but_last() {
+#ifndef CLDN_CUSIM
+  asm volatile("cp.async.wait_group 1;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void async_wait_all() {
+#ifndef CLDN_CUSIM
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+#endif
+}
 __device__ __forceinline__ float max_nan(float a, float b) {  // NaN if either is NaN (fmaxf would drop it)
   float d;
   asm("max.NaN.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b));
@@ -120,38 +143,83 @@ __device__ __noinline__ uint32_t encode_tile_careful(const EncFrame& F, const Fl
   return total;
 }
 
-// group = number of consecutive tiles one CTA walks (kEGroup for uniform batches, 1 otherwise)
-__global__ void __launch_bounds__(kET, 7) encode_xyzi_fast_kernel(const EncLaunch L, const FloatNParams P, const uint32_t group) {
+// Persistent CTAs: CTA b takes the tiles b, b + G, b + 2 G, ... of the launch's global tile order (frame-interleaved for
+// uniform batches, so the tiles a look-back depends on are being processed by other CTAs at the same time). While tile i
+// is quantised and packed, tile i + G is already on its way into the other input buffer (cp.async, 16 bytes per lane,
+// straight into the transposed slots): the load latency that a one-tile-per-CTA kernel exposes at every CTA start
+// (measured: a third of all stall samples) is hidden behind the previous tile's arithmetic.
+// All G CTAs must be co-resident (the grid is sized by the occupancy query): a CTA spins on aggregates of tiles with a
+// smaller global index, which belong to CTAs that are running.
+__device__ __forceinline__ void tile_coords(const EncLaunch& L, uint32_t i, uint32_t* fi, uint32_t* t) {
+  if (L.uniform_tiles) {
+    *fi = i % L.n_frames;
+    *t = i / L.n_frames;
+  } else {
+    *fi = find_frame(L.frames, L.n_frames, i);
+    *t = i - L.frames[*fi].tile_begin;
+  }
+}
+
+__global__ void __launch_bounds__(kET, 6) encode_xyzi_fast_kernel(const EncLaunch L, const FloatNParams P) {
   extern __shared__ __align__(16) uint8_t dyn_smem[];
   __shared__ EncFastShared sh;
-  uint8_t* stage = dyn_smem;                                 // output bytes of the tile
-  uint32_t* stage32 = reinterpret_cast<uint32_t*>(dyn_smem);
-  uint4* slots = reinterpret_cast<uint4*>(dyn_smem);        // transposed input (aliases the staging buffer)
+  __shared__ EncFrame s_F[2];
+  __shared__ FloatNParams s_P;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool aligned16 = (L.flags & kEncInputsAligned16) != 0u;
+  const uint32_t G = gridDim.x;
 
   if (blockIdx.x == 0) handle_empty_frames(L);
-  uint32_t fi, t0;
-  if (L.uniform_tiles) {
-    fi = blockIdx.x % L.n_frames;
-    t0 = (blockIdx.x / L.n_frames) * group;
-  } else {
-    fi = find_frame(L.frames, L.n_frames, blockIdx.x);
-    t0 = blockIdx.x - L.frames[fi].tile_begin;
-  }
-  // frame record and field table live in shared memory: the exact tile path (a real call) takes them by reference, and
-  // the fast path only keeps the two words it needs in registers
-  __shared__ EncFrame s_F;
-  __shared__ FloatNParams s_P;
-  if (threadIdx.x == 0) { s_F = L.frames[fi]; s_P = P; }
+  uint32_t i = blockIdx.x;
+  if (i >= L.n_tiles_total) return;
+  uint32_t fi, t;
+  tile_coords(L, i, &fi, &t);
+  if (threadIdx.x == 0) { s_F[0] = L.frames[fi]; s_P = P; }
   __syncthreads();
-  const EncFrame& F = s_F;
-  const float4* in4 = reinterpret_cast<const float4*>(F.in);
-  const bool aligned16 = (L.flags & kEncInputsAligned16) != 0u;
-  uint64_t excl = 0;       // data bytes of all earlier tiles of the frame (known after the first tile's look-back)
 
-  for (uint32_t g = 0; g < group; ++g) {
-    const uint32_t t = t0 + g;
-    if (t >= F.n_tiles) break;
+  // asks for the 1024 points of tile t of frame F into `buf` (transposed slots); false if the tile is not eligible
+  auto prefetch = [&](const EncFrame& F, uint32_t tt, uint8_t* buf) -> bool {
+    const uint32_t p0 = tt * kETilePts;
+    if (!aligned16 || p0 + kETilePts > F.n_points) return false;
+    const uint4* src = reinterpret_cast<const uint4*>(F.in) + p0 + warp * (32 * kEP) + lane;
+    uint4* wsl = reinterpret_cast<uint4*>(buf) + warp * (32 * kEP);
+#pragma unroll
+    for (int k = 0; k < kEP; ++k) {
+      const uint32_t q = 32u * k + lane, ol = q >> 3;
+      async_copy16(wsl + 8 * ol + ((q & 7u) ^ (ol & 7u)), src + 32 * k);
+    }
+    return true;
+  };
+  bool have_cur = prefetch(s_F[0], t, dyn_smem);
+  async_commit();
+
+  for (uint32_t cur = 0; i < L.n_tiles_total; i += G, cur ^= 1u) {
+    const EncFrame& F = s_F[cur];
+    uint8_t* buf = dyn_smem + cur * kEBufBytes;            // this tile's transposed input, then its staged output
+    uint8_t* stage = buf;
+    // ---- the next tile of this CTA goes into the other buffer now ----
+    const uint32_t nxt = i + G;
+    bool have_next = false;
+    uint32_t nfi = 0, nt = 0;
+    if (nxt < L.n_tiles_total) {
+      tile_coords(L, nxt, &nfi, &nt);
+      if (threadIdx.x == 0) s_F[cur ^ 1u] = L.frames[nfi];
+      // (every thread needs the frame's input pointer and size for its own copies: read them from the table directly)
+      const EncFrame* NF = L.frames + nfi;
+      const uint32_t p0 = nt * kETilePts;
+      if (aligned16 && p0 + kETilePts <= NF->n_points) {
+        const uint4* src = reinterpret_cast<const uint4*>(NF->in) + p0 + warp * (32 * kEP) + lane;
+        uint4* wsl = reinterpret_cast<uint4*>(dyn_smem + (cur ^ 1u) * kEBufBytes) + warp * (32 * kEP);
+#pragma unroll
+        for (int k = 0; k < kEP; ++k) {
+          const uint32_t q = 32u * k + lane, ol = q >> 3;
+          async_copy16(wsl + 8 * ol + ((q & 7u) ^ (ol & 7u)), src + 32 * k);
+        }
+        have_next = true;
+      }
+    }
+    async_commit();
+
     const uint32_t tile = F.tile_begin + t;
     const uint32_t tile_p0 = t * kETilePts;
     const bool full = tile_p0 + kETilePts <= F.n_points;
@@ -160,39 +228,42 @@ __global__ void __launch_bounds__(kET, 7) encode_xyzi_fast_kernel(const EncLaunc
     uint32_t X[kEP][4];
     uint32_t mine = 0, tail4 = 0;
     if (full) {
-      // ---- load + transpose inside the warp: lane l of iteration i loads point 32 i + l of the warp's 256 ----
       const uint32_t wp0 = tile_p0 + warp * (32 * kEP);
-      uint4* wsl = slots + warp * (32 * kEP);
+      uint4* wsl = reinterpret_cast<uint4*>(buf) + warp * (32 * kEP);
+      if (have_cur) {
+        async_wait_all_but_last();   // this tile's copies have landed (the next tile's may still be in flight)
+      } else {
+        // ---- load + transpose inside the warp: lane l of iteration k loads point 32 k + l of the warp's 256 ----
 #pragma unroll
-      for (int i = 0; i < kEP; ++i) {
-        const uint32_t q = 32u * i + lane;
-        float4 v;
-        if (aligned16) {
-          v = __ldcs(in4 + wp0 + q);
-        } else {
-          const uint8_t* pt = F.in + static_cast<size_t>(wp0 + q) * 16u;
-          v = make_float4(__uint_as_float(load_u32(pt)), __uint_as_float(load_u32(pt + 4)), __uint_as_float(load_u32(pt + 8)), __uint_as_float(load_u32(pt + 12)));
+        for (int k = 0; k < kEP; ++k) {
+          const uint32_t q = 32u * k + lane;
+          uint4 v;
+          if (aligned16) {
+            v = __ldcs(reinterpret_cast<const uint4*>(F.in) + wp0 + q);
+          } else {
+            const uint8_t* pt = F.in + static_cast<size_t>(wp0 + q) * 16u;
+            v = make_uint4(load_u32(pt), load_u32(pt + 4), load_u32(pt + 8), load_u32(pt + 12));
+          }
+          const uint32_t ol = q >> 3;  // owner lane; slot of point j of lane l: 8 l + (j ^ (l & 7))
+          wsl[8 * ol + ((q & 7u) ^ (ol & 7u))] = v;
         }
-        const uint32_t ol = q >> 3;  // owner lane; slot of point j of lane l: 8 l + (j ^ (l & 7))
-        wsl[8 * ol + ((q & 7u) ^ (ol & 7u))] = make_uint4(__float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w));
       }
       // previous point of my first point: 0 at a chunk start, else quantised like any point
       const uint32_t p_first = wp0 + lane * kEP;
-      float4 pv = make_float4(0.f, 0.f, 0.f, 0.f);
+      uint4 pvu = make_uint4(0, 0, 0, 0);
       if (lane == 0 && (p_first % kChunkPoints) != 0) {
         const uint8_t* pt = F.in + static_cast<size_t>(p_first - 1) * 16u;
-        pv = make_float4(__uint_as_float(load_u32(pt)), __uint_as_float(load_u32(pt + 4)), __uint_as_float(load_u32(pt + 8)), __uint_as_float(load_u32(pt + 12)));
+        pvu = make_uint4(load_u32(pt), load_u32(pt + 4), load_u32(pt + 8), load_u32(pt + 12));
       }
       __syncwarp();
       if (lane != 0) {
         const uint32_t pl = lane - 1;
-        const uint4 u = wsl[8 * pl + (7u ^ (pl & 7u))];
-        pv = make_float4(__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z), __uint_as_float(u.w));
+        pvu = wsl[8 * pl + (7u ^ (pl & 7u))];
       }
       float trk = 0.0f;
       int32_t prev[4];
       {
-        const float pf[4] = {pv.x, pv.y, pv.z, pv.w};
+        const float pf[4] = {__uint_as_float(pvu.x), __uint_as_float(pvu.y), __uint_as_float(pvu.z), __uint_as_float(pvu.w)};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const float s = __fmul_rn(pf[k], P.mul[k]);
@@ -204,7 +275,6 @@ __global__ void __launch_bounds__(kET, 7) encode_xyzi_fast_kernel(const EncLaunc
       uint32_t nbl[3] = {0, 0, 0};  // bit lengths of my last three values (for the tail word)
 #pragma unroll
       for (int j = 0; j < kEP; ++j) {
-        asm volatile("" ::: "memory");  // one point at a time: hoisting all 8 slot loads would cost 32 live registers
         const uint4 u = wsl[8 * lane + (j ^ (lane & 7))];
         const float pf[4] = {__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z), __uint_as_float(u.w)};
 #pragma unroll
@@ -252,7 +322,7 @@ __global__ void __launch_bounds__(kET, 7) encode_xyzi_fast_kernel(const EncLaunc
         total += c;
       }
       // the tile's size is final: publish it before the bytes are packed, so that successors never wait for pass 2
-      if (g == 0 && warp == 0) {
+      if (warp == 0) {
         lb.begin(L.status, F.tile_begin, tile, L.epoch, total);
         lb.issue(L.status, F.tile_begin, L.epoch);
       }
@@ -277,28 +347,30 @@ __global__ void __launch_bounds__(kET, 7) encode_xyzi_fast_kernel(const EncLaunc
           wa = wn;
         }
       }
-      const uint32_t pos = bit & 31u;
-      uint32_t* wp = reinterpret_cast<uint32_t*>(stage + wa);
-      if (threadIdx.x == kET - 1 && pos != 0u) *wp = lo;     // nobody follows the tile's last thread
+      if (threadIdx.x == kET - 1 && (bit & 31u) != 0u) *reinterpret_cast<uint32_t*>(stage + wa) = lo;  // nobody follows the tile's last thread
     } else {
-      total = encode_tile_careful<4>(s_F, s_P, tile_p0, stage, sh.scan);
-      if (g == 0 && warp == 0) lb.begin(L.status, F.tile_begin, tile, L.epoch, total);
+      // exact path: up to 20 bytes per point, staged from the start of the dynamic shared memory across BOTH input buffers --
+      // the next tile's copies are drained first and the tile is loaded again, synchronously, when its turn comes
+      async_wait_all();
+      __syncthreads();
+      have_next = false;
+      stage = dyn_smem;
+      total = encode_tile_careful<4>(F, s_P, tile_p0, stage, sh.scan);
+      if (warp == 0) lb.begin(L.status, F.tile_begin, tile, L.epoch, total);
     }
-    // ---- the tile's place in the frame: look-back for the first tile of the group, local knowledge afterwards ----
-    if (g == 0) {
-      if (warp == 0) {
-        const uint64_t e = lb.finish(L.status, F.tile_begin, tile, L.epoch, total);
-        if (lane == 0) sh.excl = e;
-      }
-    } else if (threadIdx.x == 0) {
-      st_relaxed_u64(L.status + tile, pack_status(kFlagIncl, L.epoch, excl + total));
+    // ---- the tile's place in the frame ----
+    if (warp == 0) {
+      const uint64_t e = lb.finish(L.status, F.tile_begin, tile, L.epoch, total);
+      if (lane == 0) sh.excl = e;
     }
-    __syncthreads();  // staged bytes + sh.excl complete
-    if (g == 0) excl = sh.excl;
-    finish_tile<kETilePts>(L, F, fi, t, stage, total, excl);
-    excl += total;
-    __syncthreads();  // the next tile's transposed input overwrites the staging buffer
+    __syncthreads();  // staged bytes + sh.excl complete (and s_F[cur ^ 1] written)
+    finish_tile<kETilePts>(L, F, fi, t, stage, total, sh.excl);
+    __syncthreads();  // this buffer receives the tile after next
+    have_cur = have_next;
+    fi = nfi;
+    t = nt;
   }
+  async_wait_all();
 }
 
 static bool encode_fast_enabled() {
@@ -325,15 +397,20 @@ static int launch_encode_fast(const Plan& plan, const EncLaunch& L, cudaStream_t
     P.mul[k] = plan.ops[0].enc_mul_f[k];
   }
   P.point_step = plan.point_step;
-  const size_t smem = kEStageBytes;
+  const size_t smem = kESmemBytes;
   auto k = encode_xyzi_fast_kernel;
   if (set_smem(k, smem) != cudaSuccess) return -1;
-  uint32_t group = 1, grid = L.n_tiles_total;
-  if (L.uniform_tiles) {
-    group = kEGroup;
-    grid = L.n_frames * ((L.uniform_tiles + group - 1) / group);
+  // persistent grid: every CTA must be resident (they wait for each other's tile sizes)
+  static int resident = 0;
+  if (resident == 0) {
+    int dev = 0, sms = 0, per_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kET, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    resident = std::max(1, sms) * per_sm;
   }
-  k<<<grid, kET, smem, stream>>>(L, P, group);
+  const uint32_t grid = std::min<uint32_t>(L.n_tiles_total, static_cast<uint32_t>(resident));
+  k<<<grid, kET, smem, stream>>>(L, P);
   count_launch();
   return 1;
 }

@@ -92,6 +92,13 @@ const char* cldn_b200_version(void);
 const char* cldn_b200_last_error(void);
 /* Number of kernels this library has launched in this process (bench.py reports it as gpu_launches). */
 uint64_t cldn_b200_kernel_launch_count(void);
+/* Host-side placement for the host-pointer API (no reference counterpart: the reference never leaves the CPU).
+ * Binds the CALLING thread (and the threads it creates afterwards) to the CPUs of the NUMA node that `device` (-1: the
+ * current one) hangs off, as NVML reports them, so that buffers the thread allocates and pins from now on are local to
+ * the GPU's PCIe root: on a two-socket host a remote node halves the achievable host<->device bandwidth when several
+ * GPUs stream at once. Returns the number of CPUs in the set, 0 if NVML / the affinity call is unavailable (nothing
+ * changed), or a negative status. */
+int cldn_b200_bind_host_thread_to_device(int device);
 
 /* ---- configuration <-> text (host only) ---------------------------------------------------------------------- */
 void cldn_b200_info_init(cldn_info_t* info); /* EncodingInfo defaults, cloudini.hpp:65-90 */

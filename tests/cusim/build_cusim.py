@@ -37,6 +37,10 @@ PTX = {
     # bmsk.clamp.b32 d, a, b: b bits set starting at bit a (both clamped to 32)
     "bmsk.clamp.b32": lambda outs, ins: f"{outs[0]} = ::cusim::bmsk_clamp({ins[0]}, {ins[1]});",
     "prefetch.global.L2": lambda outs, ins: "((void)0);",
+    # cp.async: the kernels compile these only without CLDN_CUSIM (the emulation copies synchronously); still rewritten
+    "cp.async.cg.shared.global": lambda outs, ins: "((void)0);",
+    "cp.async.commit_group": lambda outs, ins: "((void)0);",
+    "cp.async.wait_group": lambda outs, ins: "((void)0);",
     "shl.b32": lambda outs, ins: f"{outs[0]} = (({ins[1]}) > 31u) ? 0u : (static_cast<unsigned>({ins[0]}) << ({ins[1]}));",
     # max.NaN.f32: NaN if either operand is NaN
     "max.NaN.f32": lambda outs, ins: f"{outs[0]} = (std::isnan({ins[0]}) || std::isnan({ins[1]})) ? std::numeric_limits<float>::quiet_NaN() : fmaxf({ins[0]}, {ins[1]});",
