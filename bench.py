@@ -136,9 +136,12 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def measured_traffic(kernel="encode_floatn_kernel"):
+NCU_SUMMARY = "profiles/r2_final_ncu_full_summary.json"
+
+
+def measured_traffic(kernel):
     """DRAM bytes per launch of `kernel` from the committed `ncu --set full` capture (profiles/), and the batch it was taken on."""
-    p = os.path.join(ROOT, "profiles", "r1_final_ncu_full_summary.json")
+    p = os.path.join(ROOT, NCU_SUMMARY)
     try:
         for k in json.load(open(p)):
             if kernel in k["kernel"]:
@@ -274,6 +277,9 @@ def main():
         raise SystemExit("bench.py: no CUDA device — cloudini_b200 has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # host side of the end-to-end leg: this rank's threads and the pinned buffers they allocate live on the NUMA node of
+    # its GPU (with 8 ranks streaming at once, remote-node staging halves the achievable PCIe rate)
+    numa_cpus = cb.bind_host_thread_to_device(local_rank)
     distributed = world > 1
     if distributed:
         dist.init_process_group("nccl", device_id=dev)
@@ -297,21 +303,25 @@ def main():
     dbatch = dec.make_device_batch([t.data_ptr() + hdr for t in d_blob], [s - hdr for s in sizes], [t.data_ptr() for t in d_out], [POINTS * 16] * F)
     dec.decode_batch_device(info, dbatch, sync=True)
 
-    # ---- parity spot check inside the bench (checker only): frame 0 against the oracle ----
+    # ---- parity check inside the bench (checker only): EVERY frame of rank 0's pool against the oracle ----
     parity = "unchecked"
     if rank == 0:
         try:
             from oracle.client import best_oracle
             oracle = best_oracle()
-            expect = oracle.encode(info, host_clouds[0])
-            got = bytes(d_blob[0][:sizes[0]].cpu().numpy())
-            want = np.zeros(POINTS * 16, dtype=np.uint8)
-            oracle.decode(expect, want)
-            parity = "bit-exact" if (got == expect and np.array_equal(d_out[0].cpu().numpy(), want)) else "MISMATCH"
+            ok = True
+            for k in range(F):
+                expect = oracle.encode(info, host_clouds[k])
+                got = bytes(d_blob[k][:sizes[k]].cpu().numpy())
+                want = np.zeros(POINTS * 16, dtype=np.uint8)
+                oracle.decode(expect, want)
+                ok = ok and got == expect and np.array_equal(d_out[k].cpu().numpy(), want)
+            parity = f"bit-exact (all {F} frames)" if ok else "MISMATCH"
         except Exception as e:  # the oracle is a checker; its absence must not turn into a fake number
             parity = f"oracle unavailable: {e}"
         if parity == "MISMATCH":
             raise SystemExit("bench.py: GPU output differs from the oracle — refusing to report a number")
+    fast_chunks, redo_chunks = dec.last_stats()
 
     def barrier():
         torch.cuda.synchronize()
@@ -419,11 +429,32 @@ def main():
             ws = henc.encode_batch_host(h_in, h_blob, write_header=True)
             hdec.decode_batch_host(info, [b[hdr:n] for b, n in zip(h_blob, ws)], h_out)
         serial_s = (time.perf_counter() - t0) / 3
-        if rank == 0 and parity == "bit-exact":
+        if rank == 0 and parity.startswith("bit-exact"):
             assert np.array_equal(h_out[0].numpy(), d_out[0].cpu().numpy()), "host path differs from device path"
+        # the same call with PAGEABLE caller buffers (what a ROS plugin hands over: std::vector), and the latency of one
+        # 1M-point message through the host-pointer API (encode call, then decode call)
+        p_in = [np.array(host_clouds[k], copy=True) for k in range(Fe)]
+        p_blob = [np.empty(cap, dtype=np.uint8) for _ in range(Fe)]
+        p_out = [np.zeros(POINTS * 16, dtype=np.uint8) for _ in range(Fe)]
+        henc.encode_batch_host(p_in, p_blob, write_header=True)
+        t0 = time.perf_counter()
+        for _ in range(2):
+            ws = henc.encode_batch_host(p_in, p_blob, write_header=True)
+            hdec.decode_batch_host(info, [b[hdr:n] for b, n in zip(p_blob, ws)], p_out)
+        pageable_s = (time.perf_counter() - t0) / 2
+        lat_e, lat_d = [], []
+        for _ in range(7):
+            t0 = time.perf_counter()
+            w1 = henc.encode_batch_host(h_in[:1], h_blob[:1], write_header=True)
+            t1 = time.perf_counter()
+            hdec.decode_batch_host(info, [h_blob[0][hdr:w1[0]]], h_out[:1])
+            t2 = time.perf_counter()
+            lat_e.append(t1 - t0)
+            lat_d.append(t2 - t1)
         blob_bytes = int(sum(w))
         e2e = {"seconds": e2e_s, "steps": e2e_steps, "frames": Fe, "h2d": Fe * POINTS * 16 + blob_bytes - Fe * hdr, "d2h": blob_bytes + Fe * POINTS * 16,
-               "serial_mpts": Fe * POINTS / serial_s / 1e6}
+               "serial_mpts": Fe * POINTS / serial_s / 1e6, "pageable_mpts": Fe * POINTS / pageable_s / 1e6,
+               "lat_enc_ms": float(np.median(lat_e)) * 1e3, "lat_dec_ms": float(np.median(lat_d)) * 1e3}
 
     # ---- reduce over ranks: time = max, points = sum (no data-path collective: frames are independent) ----
     from cloudini_b200 import dist as cdist
@@ -436,9 +467,9 @@ def main():
         stage1_bytes = float(np.mean(sizes)) - hdr                      # S: stage-1 bytes incl. the u32 chunk prefixes
         algo_bytes = F * (POINTS * 16 + stage1_bytes)                    # encode: read N*point_step once + write S once
         achieved = algo_bytes / (enc_ms * 1e-3) / 1e9
-        tb, tf = measured_traffic()
+        tb, tf = measured_traffic("encode_xyzi_fast_kernel")
         traffic = tb * F / tf if tb else None
-        tbd, tfd = measured_traffic("decode_chunks_seq_kernel")
+        tbd, tfd = measured_traffic("decode_floatn_fast_kernel")
         dec_traffic = tbd * F / tfd if tbd else None
         dec_achieved = algo_bytes / (dec_ms * 1e-3) / 1e9
         line = {
@@ -448,16 +479,18 @@ def main():
             "config": {"workload": WORKLOAD, "frames_per_gpu_per_step": F, "points_per_frame": POINTS, "point_step": 16,
                        "stage1_bytes_per_point": stage1_bytes / POINTS, "cache": "inputs larger than L2 (pool of %d x 16 MB per GPU)" % F,
                        "parallelism": f"frame-sharded x{world}, no data-path collective", "parity": parity,
+                       "host_numa_cpus": numa_cpus,
                        "encode_mpts": world * F * POINTS / (enc_ms_max * 1e-3) / 1e6, "decode_mpts": world * F * POINTS / (dec_ms_max * 1e-3) / 1e6,
                        "encode_ms_per_step": enc_ms, "decode_ms_per_step": dec_ms},
             # dominant kernel of the step = the one with the larger share of the timed region (the FloatN decode);
             # the encode kernel (the one SURVEY 8(d)'s 60 % target is stated on) is reported next to it
-            "roofline": {"bound": "hbm", "kernel": "decode_chunks_seq_kernel<4> (varint scan + un-zigzag + per-field prefix sums + dequantise)",
+            "roofline": {"bound": "hbm", "kernel": "decode_floatn_fast_kernel<4> (terminator ranking + varint reader + un-zigzag + per-field prefix sums + dequantise)",
                          "achieved": dec_achieved, "peak": peak, "unit": "GB/s", "frac": dec_achieved / peak,
                          "traffic": dec_traffic, "share_of_step": dec_ms / (enc_ms + dec_ms),
-                         "traffic_source": "profiles/r1_final_ncu_full_summary.json (ncu --set full, dram__bytes_read+write, one 32-frame launch, scaled by frames)",
+                         "traffic_source": NCU_SUMMARY + " (ncu --set full, dram__bytes_read+write, one 32-frame launch, scaled by frames)",
+                         "chunks_fast_reader": fast_chunks, "chunks_careful_reader": redo_chunks,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": algo_bytes, "launch_ms": dec_ms,
-                         "encode": {"kernel": "encode_floatn_kernel<4,8,vec4> (quantise + delta + zigzag varint + pack)", "achieved": achieved,
+                         "encode": {"kernel": "encode_xyzi_fast_kernel (quantise + delta + zigzag varint + pack, persistent CTAs)", "achieved": achieved,
                                     "frac": achieved / peak, "traffic": traffic, "launch_ms": enc_ms, "share_of_step": enc_ms / (enc_ms + dec_ms),
                                     "algorithmic_bytes_per_launch": algo_bytes}},
             "gpu_launches": int(launches),
@@ -469,7 +502,10 @@ def main():
                            "d2h_bytes_per_step": int(e2e["d2h"]), "frames_per_step": e2e["frames"],
                            "api": "cldn_b200_encode_batch + cldn_b200_decode_batch, CLDN_MEM_HOST, pinned host buffers; encoder and "
                                   "decoder handles driven by two host threads (batch i decodes while batch i+1 encodes)",
-                           "serial_roundtrip_mpoints_s": world * e2e["serial_mpts"]}
+                           "serial_roundtrip_mpoints_s": world * e2e["serial_mpts"],
+                           "pageable_buffers_mpoints_s": world * e2e["pageable_mpts"],
+                           "one_message_latency_ms": {"encode": e2e["lat_enc_ms"], "decode": e2e["lat_dec_ms"],
+                                                      "note": "one 1M-point frame, pinned host buffers, host-pointer API, median of 7"}}
         # ---- CPU baseline on this box's host cores (rank 0, N=1 only): bounded sample ----
         if world == 1:
             try:

@@ -283,6 +283,7 @@ static inline cudaError_t cudaPeekAtLastError() { return cudaSuccess; }
 static inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
 static inline cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
 static inline cudaError_t cudaSetDevice(int d) { return d == 0 ? cudaSuccess : cudaErrorInvalidValue; }
+static inline cudaError_t cudaDeviceGetPCIBusId(char*, int, int) { return cudaErrorInvalidValue; }  // no PCI device behind the emulation
 static inline cudaError_t cudaDeviceSynchronize() { ::cusim::flush_d2h(nullptr, true); return cudaSuccess; }
 static inline cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr a, int) { *v = (a == cudaDevAttrMultiProcessorCount) ? cusim::sm_count() : 0; return cudaSuccess; }
 // fresh device memory holds whatever the previous owner left there: fill it with a pattern, so that code that relies on

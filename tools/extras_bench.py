@@ -20,6 +20,14 @@ import cloudini_b200 as cb  # noqa: E402
 from cloudini_b200 import ros, synth  # noqa: E402
 
 
+def hbm_peak():
+    """Measured copy bandwidth of this pool's B200s (MEASURED_PEAKS.json), else the profiling guide's fallback."""
+    try:
+        return float(json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        return 6650.0
+
+
 def numpy_first_voxel_mask(cloud, step, res):
     """finite && first occurrence of (lround(x/res), lround(y/res), lround(z/res)) truncated to 21 bits per axis."""
     n = cloud.size // step
@@ -54,7 +62,8 @@ def bench_viz(out):
         pp.run_device(info, d_in.data_ptr(), cloud.size, d_out.data_ptr(), cloud.size)  # synchronous (4-byte count read-back)
     ms = (time.perf_counter() - t0) / reps * 1e3
     out["viz_preprocess"] = {"points": n, "kept": int(kept), "ms_per_call": ms, "mpoints_s": n / ms / 1e3, "matches_numpy_restatement": ok,
-                             "algorithmic_bytes": int(n * 16 + kept * 16), "gbs": (n * 16 + kept * 16) / ms / 1e6}
+                             "algorithmic_bytes": int(n * 16 + kept * 16), "gbs": (n * 16 + kept * 16) / ms / 1e6,
+                             "frac_of_hbm": (n * 16 + kept * 16) / ms / 1e6 / hbm_peak()}
     # preprocessing straight into the encoder, everything device resident
     enc = cb.PointcloudEncoder(new_info)
     cap = cb.MaxCompressedSize(new_info, kept, True)
@@ -112,7 +121,8 @@ def bench_c3(out):
     algo = F * (n * step + S)
     out["c3_v5_sections"] = {"frames": F, "points": n, "point_step": step, "stage1_B_per_pt": S / n, "encode_ms": te, "decode_ms": td,
                              "encode_mpts": F * n / te / 1e3, "decode_mpts": F * n / td / 1e3, "encode_gbs": algo / te / 1e6,
-                             "decode_gbs": algo / td / 1e6, "ints_roundtrip_exact": ints_ok, "max_float_error": f_err}
+                             "decode_gbs": algo / td / 1e6, "encode_frac_of_hbm": algo / te / 1e6 / hbm_peak(),
+                             "decode_frac_of_hbm": algo / td / 1e6 / hbm_peak(), "ints_roundtrip_exact": ints_ok, "max_float_error": f_err}
 
 
 def bench_c4_mixed(out):
@@ -153,7 +163,10 @@ def bench_c4_mixed(out):
     te, td = te / reps, td / reps
     S = float(np.mean(sizes)) - hdr
     out["c4_velodyne_xyzirt"] = {"frames": F, "points": n, "point_step": step, "stage1_B_per_pt": S / n, "encode_ms": te, "decode_ms": td,
-                                 "encode_mpts": F * n / te / 1e3, "decode_mpts": F * n / td / 1e3, "ring_roundtrip_exact": ring_ok}
+                                 "encode_mpts": F * n / te / 1e3, "decode_mpts": F * n / td / 1e3, "ring_roundtrip_exact": ring_ok,
+                                 "encode_gbs": F * (n * step + S) / te / 1e6, "decode_gbs": F * (n * step + S) / td / 1e6,
+                                 "encode_frac_of_hbm": F * (n * step + S) / te / 1e6 / hbm_peak(),
+                                 "decode_frac_of_hbm": F * (n * step + S) / td / 1e6 / hbm_peak()}
 
 
 def bench_msg(out):
