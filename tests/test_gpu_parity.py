@@ -183,10 +183,11 @@ def test_lossless_truncated_stream_is_rejected():
         cb.PointcloudDecoder().decode(dinfo, blob[hdr:-7], out)
 
 
-@pytest.mark.skipif(not os.environ.get("CLDN_B200_FUZZ"), reason="opt-in sweep (CLDN_B200_FUZZ=1): random layouts through the generic kernels")
+# 30 seeds by default; CLDN_B200_FUZZ=1 (+ CLDN_B200_FUZZ_SEEDS) widens the sweep
 def test_random_layouts_sweep(oracle):
     # same seeds as tests/test_oracle.py::test_port_vs_reference_random_layouts; layouts the reference rejects are skipped
-    for seed in range(int(os.environ.get("CLDN_B200_FUZZ_SEEDS", "120"))):
+    n_seeds = int(os.environ.get("CLDN_B200_FUZZ_SEEDS", "120")) if os.environ.get("CLDN_B200_FUZZ") else 30
+    for seed in range(n_seeds):
         info, cloud = synth.random_layout_case(seed)
         try:
             expected = oracle.encode(info, cloud)
@@ -693,17 +694,21 @@ def test_skip_store_in_v5_sections_is_honoured_here():
 
 
 def _reference_samples():
-    """The reference's own sample data (cloudini_lib/samples). Only where the reference tree exists (the build container:
-    under tests/cusim); the files never travel to the GPU box — there the committed excerpts in tests/golden stand in."""
+    """The reference's own sample data (cloudini_lib/samples): read from the reference tree where it exists, otherwise
+    from the full-length copies in tests/golden/samples_v1.npz (tests/golden/make_samples.py) -- the GPU box has no
+    /root/reference."""
     base = os.path.join(os.environ.get("CLOUDINI_REFERENCE", "/root/reference"), "cloudini_lib", "samples")
-    if not os.path.exists(os.path.join(base, "lidar.pcd")):
-        pytest.skip("reference sample files not present here")
-    raw = open(os.path.join(base, "lidar.pcd"), "rb").read()
-    n = int(raw[raw.index(b"POINTS ") + 7:raw.index(b"\n", raw.index(b"POINTS "))])
-    body = raw[raw.index(b"DATA binary\n") + 12:]
-    yield "lidar.pcd", synth.info_xyzi(n), np.frombuffer(body[:n * 16], dtype=np.uint8), {5: ("d8b95f6208899099", "dcd32492c331c988", 567_028)}
+    if os.path.exists(os.path.join(base, "lidar.pcd")):
+        raw = open(os.path.join(base, "lidar.pcd"), "rb").read()
+        n = int(raw[raw.index(b"POINTS ") + 7:raw.index(b"\n", raw.index(b"POINTS "))])
+        body = np.frombuffer(raw[raw.index(b"DATA binary\n") + 12:], dtype=np.uint8)
+        dds = open(os.path.join(base, "dds_message.bin"), "rb").read()
+    else:
+        z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "samples_v1.npz"))
+        n, body, dds = int(z["lidar_pcd_n"][0]), z["lidar_pcd_points"], bytes(z["dds_message_bin"])
+    yield "lidar.pcd", synth.info_xyzi(n), np.array(body[:n * 16]), {5: ("d8b95f6208899099", "dcd32492c331c988", 567_028)}
     from cloudini_b200 import ros
-    pc = ros.getDeserializedPointCloudMessage(open(os.path.join(base, "dds_message.bin"), "rb").read())
+    pc = ros.getDeserializedPointCloudMessage(dds)
     info = ros.toEncodingInfo(pc)
     info.compression_opt, info.use_threads = cb.CompressionOption.NONE, False
     for f in info.fields:
