@@ -411,6 +411,23 @@ int cldn_b200_encoder_info(const cldn_encoder_t* enc, cldn_info_t* info) {
 
 const uint64_t* cldn_b200_encoder_sizes_device(const cldn_encoder_t* enc) { return enc ? enc->d_sizes.p : nullptr; }
 
+int cldn_b200_encoder_set_dims(cldn_encoder_t* e, uint32_t width, uint32_t height) {
+  if (!e) { set_error("null encoder"); return CLDN_ERR_INVALID_ARGUMENT; }
+  if (e->info.width == width && e->info.height == height) return CLDN_OK;
+  CUDA_TRY(cudaSetDevice(e->device));
+  e->info.width = width;
+  e->info.height = height;
+  cldn_info_t full = e->info;
+  full.compression_opt = static_cast<uint8_t>(e->stage2);
+  const std::vector<uint8_t> h = make_header(full);
+  // the device copy of the previous header may still be read by kernels in flight on the handle's stream
+  CUDA_TRY(cudaStreamSynchronize(e->stream));
+  if (int rc = e->d_header.reserve(h.size())) return rc;
+  CUDA_TRY(cudaMemcpy(e->d_header.p, h.data(), h.size(), cudaMemcpyHostToDevice));
+  e->header = h;
+  return CLDN_OK;
+}
+
 static int check_device_error(cudaStream_t stream, uint32_t* d_err, uint32_t* h_err) {
   CUDA_TRY(cudaMemcpyAsync(h_err, d_err, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
   CUDA_TRY(cudaStreamSynchronize(stream));

@@ -4,6 +4,7 @@
 // CDR rules restated from the reference's vendored nanocdr (include/cloudini_lib/contrib/nanocdr.hpp:252-293 decoder
 // header checks, :346-368 / :391-414 primitives aligned to their size relative to the byte after the 4-byte
 // encapsulation header, :313-333 / :417-424 strings = u32 length including the NUL + bytes).
+#include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
@@ -272,6 +273,193 @@ int cldn_b200_ros_decompress_msg(cldn_decoder_t* dec, const cldn_ros_msg_t* msg,
   return CLDN_OK;
 }
 
+}  // extern "C"
+
+// ---- per-thread handle pool: the converter step and the one-shots below reuse handles instead of creating streams, device
+// buffers and pinned memory for every message (handles are single-threaded, so the pool is too; it is never torn down:
+// at process exit the driver may already be gone) ---------------------------------------------------------------------------
+namespace {
+struct LayoutKey {
+  cldn_info_t info;  // width / height zeroed
+  bool same(const cldn_info_t& o) const {
+    if (info.point_step != o.point_step || info.encoding_opt != o.encoding_opt || info.compression_opt != o.compression_opt ||
+        info.version != o.version || info.n_fields != o.n_fields) return false;
+    for (uint32_t i = 0; i < o.n_fields; ++i) {
+      const cldn_field_t &a = info.fields[i], &b = o.fields[i];
+      if (strncmp(a.name, b.name, CLDN_MAX_NAME) != 0 || a.offset != b.offset || a.type != b.type || a.has_resolution != b.has_resolution ||
+          (a.has_resolution && memcmp(&a.resolution, &b.resolution, 4) != 0)) return false;
+    }
+    return true;
+  }
+};
+struct HandlePool {
+  cudaStream_t stream = nullptr;
+  std::vector<std::pair<LayoutKey, cldn_encoder_t*>> encoders;  // most recently used first
+  cldn_decoder_t* decoder = nullptr;
+  cldn_preproc_t* preproc = nullptr;
+  uint8_t *d_in = nullptr, *d_mid = nullptr, *d_blob = nullptr;
+  size_t cap_in = 0, cap_mid = 0, cap_blob = 0;
+  bool ready() {
+    if (stream) return true;
+    return cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking) == cudaSuccess;
+  }
+  static bool grow(uint8_t** p, size_t* cap, size_t need) {
+    if (need <= *cap) return true;
+    if (*p) cudaFree(*p);
+    *p = nullptr; *cap = 0;
+    const size_t want = need + need / 4 + 4096;
+    if (cudaMalloc(reinterpret_cast<void**>(p), want) != cudaSuccess) return false;
+    *cap = want;
+    return true;
+  }
+  cldn_encoder_t* encoder_for(const cldn_info_t& info) {
+    for (size_t i = 0; i < encoders.size(); ++i) {
+      if (encoders[i].first.same(info)) {
+        auto hit = encoders[i];
+        encoders.erase(encoders.begin() + i);
+        encoders.insert(encoders.begin(), hit);
+        if (cldn_b200_encoder_set_dims(hit.second, info.width, info.height) != CLDN_OK) return nullptr;
+        return hit.second;
+      }
+    }
+    if (!ready()) { set_error("cudaStreamCreate failed"); return nullptr; }
+    cldn_encoder_t* enc = nullptr;
+    if (cldn_b200_encoder_create(&info, -1, stream, &enc) != CLDN_OK) return nullptr;
+    LayoutKey k;
+    k.info = info;
+    encoders.insert(encoders.begin(), {k, enc});
+    if (encoders.size() > 8) {  // bounded: a process talks to a handful of sensor layouts
+      cldn_b200_encoder_destroy(encoders.back().second);
+      encoders.pop_back();
+    }
+    return enc;
+  }
+  cldn_decoder_t* the_decoder() {
+    if (!decoder && ready() && cldn_b200_decoder_create(-1, stream, &decoder) != CLDN_OK) decoder = nullptr;
+    return decoder;
+  }
+  cldn_preproc_t* the_preproc() {
+    if (!preproc && ready() && cldn_b200_preproc_create(-1, stream, &preproc) != CLDN_OK) preproc = nullptr;
+    return preproc;
+  }
+};
+HandlePool& pool() {
+  static thread_local HandlePool* p = new HandlePool();  // deliberately leaked (see above)
+  return *p;
+}
+}  // namespace
+
+extern "C" int cldn_b200_pool_encoder(const cldn_info_t* info, cldn_encoder_t** out) {
+  if (!info || !out) { set_error("null argument"); return CLDN_ERR_INVALID_ARGUMENT; }
+  *out = pool().encoder_for(*info);
+  return *out ? CLDN_OK : CLDN_ERR_INVALID_ARGUMENT;
+}
+extern "C" int cldn_b200_pool_decoder(cldn_decoder_t** out) {
+  if (!out) { set_error("null argument"); return CLDN_ERR_INVALID_ARGUMENT; }
+  *out = pool().the_decoder();
+  return *out ? CLDN_OK : CLDN_ERR_CUDA;
+}
+extern "C" int cldn_b200_pool_preproc(cldn_preproc_t** out) {
+  if (!out) { set_error("null argument"); return CLDN_ERR_INVALID_ARGUMENT; }
+  *out = pool().the_preproc();
+  return *out ? CLDN_OK : CLDN_ERR_CUDA;
+}
+
+extern "C" int cldn_b200_ros_convert_msg(const void* dds_msg, size_t msg_bytes, const char* const* names, const float* resolutions,
+                                         size_t n_profile, const float* default_resolution, int viz, int encoding_opt,
+                                         int compression_opt, int version, void* out, size_t out_capacity, size_t* written) {
+  cldn_ros_msg_t m;
+  if (int rc = cldn_b200_ros_parse(dds_msg, msg_bytes, &m)) return rc;
+  if (int rc = cldn_b200_ros_apply_resolution_profile(m.fields, &m.n_fields, names, resolutions, n_profile, default_resolution)) return rc;
+  cldn_info_t info;
+  if (int rc = cldn_b200_ros_to_encoding_info(&m, &info)) return rc;
+  info.encoding_opt = static_cast<uint8_t>(encoding_opt);
+  info.compression_opt = static_cast<uint8_t>(compression_opt);
+  info.version = static_cast<uint8_t>(version);
+  info.use_threads = 0;
+  HandlePool& P = pool();
+  if (!P.ready()) { set_error("cudaStreamCreate failed"); return CLDN_ERR_CUDA; }
+  const size_t step = m.point_step;
+  const size_t points_in = step ? m.data_bytes / step : 0;
+  // worst-case size of the output message (before preprocessing: it only ever shrinks the cloud)
+  {
+    cldn_encoder_t* probe = P.encoder_for(info);
+    if (!probe) return CLDN_ERR_INVALID_ARGUMENT;
+    size_t worst = 0;
+    if (int rc = cldn_b200_ros_compress_msg(probe, &m, nullptr, 0, &worst)) return rc;
+    if (!out) { if (written) *written = worst; return CLDN_OK; }
+    if (out_capacity < worst) { set_error("output buffer smaller than the worst-case message (%zu bytes)", worst); return CLDN_ERR_BUFFER_TOO_SMALL; }
+  }
+  if (compression_opt != CLDN_COMP_NONE || m.data_bytes == 0 || step == 0 || m.data_bytes % step != 0) {
+    // stage 2 runs in the host libraries (and degenerate messages take the plain path): preprocessing through the host API
+    std::vector<uint8_t> kept_data;
+    if (viz && m.data_bytes) {
+      cldn_preproc_t* pp = P.the_preproc();
+      if (!pp) return CLDN_ERR_CUDA;
+      kept_data.resize(m.data_bytes);
+      size_t kept = 0;
+      int applied = 0;
+      if (int rc = cldn_b200_viz_lossy_preprocess(pp, &info, m.data, m.data_bytes, kept_data.data(), kept_data.size(), &kept, &applied, CLDN_MEM_HOST)) return rc;
+      if (applied) {
+        m.data = kept_data.data(); m.data_bytes = kept * step; m.width = info.width; m.height = 1; m.row_step = m.point_step * m.width;
+        for (uint32_t i = 0; i < info.n_fields; ++i) m.fields[i] = info.fields[i];
+      }
+    }
+    cldn_encoder_t* enc = P.encoder_for(info);
+    if (!enc) return CLDN_ERR_INVALID_ARGUMENT;
+    return cldn_b200_ros_compress_msg(enc, &m, out, out_capacity, written);
+  }
+  // ---- device-resident: one upload, kernels, one download ----
+  if (!HandlePool::grow(&P.d_in, &P.cap_in, m.data_bytes)) { set_error("cudaMalloc failed"); return CLDN_ERR_CUDA; }
+  if (cudaMemcpyAsync(P.d_in, m.data, m.data_bytes, cudaMemcpyHostToDevice, P.stream) != cudaSuccess) { set_error("upload failed"); return CLDN_ERR_CUDA; }
+  const uint8_t* d_cloud = P.d_in;
+  size_t n_points = points_in;
+  if (viz) {
+    cldn_preproc_t* pp = P.the_preproc();
+    if (!pp) return CLDN_ERR_CUDA;
+    if (!HandlePool::grow(&P.d_mid, &P.cap_mid, m.data_bytes)) { set_error("cudaMalloc failed"); return CLDN_ERR_CUDA; }
+    size_t kept = 0;
+    int applied = 0;
+    if (int rc = cldn_b200_viz_lossy_preprocess(pp, &info, P.d_in, m.data_bytes, P.d_mid, P.cap_mid, &kept, &applied, CLDN_MEM_DEVICE)) return rc;
+    if (applied) {
+      d_cloud = P.d_mid; n_points = kept;
+      m.width = info.width; m.height = 1; m.row_step = m.point_step * m.width;
+      for (uint32_t i = 0; i < info.n_fields; ++i) m.fields[i] = info.fields[i];
+    }
+  }
+  cldn_encoder_t* enc = P.encoder_for(info);
+  if (!enc) return CLDN_ERR_INVALID_ARGUMENT;
+  const size_t blob_cap = cldn_b200_max_compressed_size(&info, n_points, 1);
+  if (blob_cap == 0) return CLDN_ERR_INVALID_ARGUMENT;
+  if (!HandlePool::grow(&P.d_blob, &P.cap_blob, blob_cap)) { set_error("cudaMalloc failed"); return CLDN_ERR_CUDA; }
+  size_t blob = 0;
+  if (int rc = cldn_b200_encode(enc, d_cloud, n_points * step, P.d_blob, blob_cap, 1, &blob, CLDN_MEM_DEVICE)) return rc;
+  // message: header, u32 blob size, blob, is_dense, "cloudini" (convertPointCloud2ToCompressedCloud, :167-213)
+  CdrWriter w;
+  write_pc_header(w, m);
+  w.u32(0);
+  const size_t size_at = w.buf.size() - 4, prev = w.buf.size();
+  uint8_t* o = static_cast<uint8_t*>(out);
+  memcpy(o, w.buf.data(), prev);
+  if (cudaMemcpyAsync(o + prev, P.d_blob, blob, cudaMemcpyDeviceToHost, P.stream) != cudaSuccess || cudaStreamSynchronize(P.stream) != cudaSuccess) {
+    set_error("download failed");
+    return CLDN_ERR_CUDA;
+  }
+  const uint32_t sz = static_cast<uint32_t>(blob);
+  memcpy(o + size_at, &sz, 4);
+  size_t pos = prev + blob;
+  o[pos++] = m.is_dense;
+  while ((pos - 4) % 4) o[pos++] = 0;
+  uint32_t len = 9;
+  if (w.big) len = __builtin_bswap32(len);
+  memcpy(o + pos, &len, 4);
+  memcpy(o + pos + 4, "cloudini", 9);
+  if (written) *written = pos + 13;
+  return CLDN_OK;
+}
+
+extern "C" {
+
 // ---- the DDS-message half of the reference's own C ABI (src/wasm_functions.cpp:24-226) ------------------------------------
 uint32_t cldn_b200_GetHeaderAsYAML(const void* encoded_data, uint32_t encoded_data_size, char* output_yaml, uint32_t capacity) {
   if (!encoded_data || !output_yaml) { set_error("null argument"); return 0; }
@@ -312,13 +500,12 @@ static bool message_encoding_info(const void* msg, uint32_t size, float resoluti
 }
 
 static uint32_t encode_message_payload(const cldn_ros_msg_t& m, const cldn_info_t& info, std::vector<uint8_t>* blob) {
-  cldn_encoder_t* enc = nullptr;
-  if (cldn_b200_encoder_create(&info, -1, nullptr, &enc) != CLDN_OK) return 0;
+  cldn_encoder_t* enc = pool().encoder_for(info);  // reused across messages of the same layout
+  if (!enc) return 0;
   const size_t cap = info.point_step ? cldn_b200_max_compressed_size(&info, m.data_bytes / info.point_step, 1) : 0;
   blob->resize(cap);
   size_t written = 0;
   const int rc = cap ? cldn_b200_encode(enc, m.data, m.data_bytes, blob->data(), blob->size(), 1, &written, CLDN_MEM_HOST) : CLDN_ERR_INVALID_ARGUMENT;
-  cldn_b200_encoder_destroy(enc);
   return rc == CLDN_OK ? static_cast<uint32_t>(written) : 0;
 }
 
@@ -352,11 +539,10 @@ uint32_t cldn_b200_ConvertCompressedMsgToPointCloud2Msg(const void* compressed_m
   if (!output_msg) { set_error("null argument"); return 0; }
   cldn_ros_msg_t m;
   if (cldn_b200_ros_parse(compressed_msg, msg_size, &m) != CLDN_OK) return 0;
-  cldn_decoder_t* dec = nullptr;
-  if (cldn_b200_decoder_create(-1, nullptr, &dec) != CLDN_OK) return 0;
+  cldn_decoder_t* dec = pool().the_decoder();
+  if (!dec) return 0;
   size_t written = 0;
   const int rc = cldn_b200_ros_decompress_msg(dec, &m, output_msg, capacity, &written);
-  cldn_b200_decoder_destroy(dec);
   return rc == CLDN_OK ? static_cast<uint32_t>(written) : 0;
 }
 

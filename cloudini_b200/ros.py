@@ -49,6 +49,9 @@ def _L():
         L.cldn_b200_ros_compress_msg.argtypes = [vp, C.POINTER(_CRosMsg), vp, sz, C.POINTER(sz)]
         L.cldn_b200_ros_decompress_msg.argtypes = [vp, C.POINTER(_CRosMsg), vp, sz, C.POINTER(sz)]
         L.cldn_b200_encoder_info.argtypes = [vp, C.POINTER(_CInfo)]
+        L.cldn_b200_encoder_set_dims.argtypes = [vp, C.c_uint32, C.c_uint32]
+        L.cldn_b200_ros_convert_msg.argtypes = [vp, sz, C.POINTER(C.c_char_p), C.POINTER(C.c_float), sz, C.POINTER(C.c_float), C.c_int, C.c_int,
+                                                C.c_int, C.c_int, vp, sz, C.POINTER(sz)]
         _bound = True
     return L
 
@@ -141,9 +144,29 @@ def toEncodingInfo(pc: RosPointCloud2) -> EncodingInfo:  # ros_msg_utils.cpp:122
     return _from_c(c)
 
 
+_ENCODERS: Dict[tuple, PointcloudEncoder] = {}   # per layout: the reference builds an encoder per message (:198); here that
+_DECODERS: Dict[int, PointcloudDecoder] = {}      # would mean streams, device buffers and pinned memory per message
+
+
+def _layout_key(info: EncodingInfo, device: int) -> tuple:
+    return (device, info.point_step, int(info.encoding_opt), int(info.compression_opt), info.version,
+            tuple((f.name, f.offset, int(f.type), f.resolution) for f in info.fields))
+
+
+def _pooled_encoder(info: EncodingInfo, device: int) -> PointcloudEncoder:
+    key = _layout_key(info, device)
+    enc = _ENCODERS.get(key)
+    if enc is None:
+        if len(_ENCODERS) >= 8:
+            _ENCODERS.pop(next(iter(_ENCODERS)))
+        enc = _ENCODERS[key] = PointcloudEncoder(info, device=device)
+    _check(_L().cldn_b200_encoder_set_dims(enc._h, info.width, info.height))
+    return enc
+
+
 def convertPointCloud2ToCompressedCloud(pc: RosPointCloud2, encoding_info: EncodingInfo, device: int = -1) -> bytes:
     """ros_msg_utils.cpp:167-213. Returns the serialised CompressedPointCloud2 message."""
-    enc = PointcloudEncoder(encoding_info, device=device)  # a fresh encoder per message, like the reference (:198)
+    enc = _pooled_encoder(encoding_info, device)
     m, _keep = pc._c_view()
     need = C.c_size_t(0)
     _check(_L().cldn_b200_ros_compress_msg(enc._h, C.byref(m), None, 0, C.byref(need)))
@@ -155,13 +178,39 @@ def convertPointCloud2ToCompressedCloud(pc: RosPointCloud2, encoding_info: Encod
 
 def convertCompressedCloudToPointCloud2(pc: RosPointCloud2, device: int = -1) -> bytes:
     """ros_msg_utils.cpp:134-165. Returns the serialised PointCloud2 message."""
-    dec = PointcloudDecoder(device=device)
+    dec = _DECODERS.get(device)
+    if dec is None:
+        dec = _DECODERS[device] = PointcloudDecoder(device=device)
     m, _keep = pc._c_view()
     need = C.c_size_t(0)
     _check(_L().cldn_b200_ros_decompress_msg(dec._h, C.byref(m), None, 0, C.byref(need)))
     out = np.zeros(need.value, dtype=np.uint8)
     w = C.c_size_t(0)
     _check(_L().cldn_b200_ros_decompress_msg(dec._h, C.byref(m), out.ctypes.data, out.size, C.byref(w)))
+    return bytes(out[:w.value])
+
+
+def convert_message(msg: bytes, profile: Optional[Dict[str, float]] = None, default_resolution: Optional[float] = None, viz: bool = False,
+                    encoding_opt=None, compression_opt=None, version: int = 5) -> bytes:
+    """The converter's per-message step (tools/src/mcap_converter.cpp:184-204) as ONE library call: parse, resolution
+    profile, optional viz preprocessing, encode, write the CompressedPointCloud2 message. The payload is uploaded once and
+    stays on the GPU in between; handles come from the library's per-thread pool."""
+    from . import CompressionOption, EncodingOptions
+    profile = profile or {}
+    raw = bytes(msg)
+    buf = np.frombuffer(raw, dtype=np.uint8)
+    names = (C.c_char_p * max(1, len(profile)))(*[k.encode("utf-8", "surrogateescape") for k in profile])
+    res = (C.c_float * max(1, len(profile)))(*[float(v) for v in profile.values()])
+    dflt = C.byref(C.c_float(default_resolution)) if default_resolution is not None else None
+    eo = int(EncodingOptions.LOSSY if encoding_opt is None else encoding_opt)
+    co = int(CompressionOption.ZSTD if compression_opt is None else compression_opt)
+    L = _L()
+    need = C.c_size_t(0)
+    args = (buf.ctypes.data if len(raw) else None, len(raw), names, res, len(profile), dflt, 1 if viz else 0, eo, co, int(version))
+    _check(L.cldn_b200_ros_convert_msg(*args, None, 0, C.byref(need)))
+    out = np.empty(need.value, dtype=np.uint8)
+    w = C.c_size_t(0)
+    _check(L.cldn_b200_ros_convert_msg(*args, out.ctypes.data, out.size, C.byref(w)))
     return bytes(out[:w.value])
 
 

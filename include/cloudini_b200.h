@@ -151,6 +151,10 @@ int cldn_b200_encode_batch(cldn_encoder_t* enc, size_t n_frames, const void* con
                            int mem);
 /* Device array (uint64 per frame of the last batch) with the encoded sizes; valid after the stream is synchronised. */
 const uint64_t* cldn_b200_encoder_sizes_device(const cldn_encoder_t* enc);
+/* Re-uses an encoder for messages of the same layout but another width / height (no reference counterpart: the
+ * reference constructs a PointcloudEncoder per message, ros_msg_utils.cpp:198, which here would mean streams, device
+ * buffers and pinned memory per message). Only the header text changes. Synchronises the handle's stream. */
+int cldn_b200_encoder_set_dims(cldn_encoder_t* enc, uint32_t width, uint32_t height);
 /* Waits for everything enqueued on the handle's stream; reports device-side errors of the last call. */
 int cldn_b200_encoder_sync(cldn_encoder_t* enc);
 

@@ -164,8 +164,8 @@ inline Cloudini::EncodingInfo toEncodingInfo(const RosPointCloud2& pc_info) {
 inline void convertPointCloud2ToCompressedCloud(const RosPointCloud2& pc_info, const Cloudini::EncodingInfo& encoding_info,
                                                 std::vector<uint8_t>& compressed_dds_msg) {
   const cldn_info_t c = Cloudini::detail::to_c(encoding_info);
-  cldn_encoder_t* enc = nullptr;
-  Cloudini::detail::check(cldn_b200_encoder_create(&c, -1, nullptr, &enc));  // a fresh encoder per message (:198)
+  cldn_encoder_t* enc = nullptr;  // from the library's per-thread pool (the reference builds one per message, :198)
+  Cloudini::detail::check(cldn_b200_pool_encoder(&c, &enc));
   const cldn_ros_msg_t m = detail::to_c(pc_info);
   size_t need = 0, written = 0;
   int rc = cldn_b200_ros_compress_msg(enc, &m, nullptr, 0, &need);
@@ -173,7 +173,6 @@ inline void convertPointCloud2ToCompressedCloud(const RosPointCloud2& pc_info, c
     compressed_dds_msg.resize(need);
     rc = cldn_b200_ros_compress_msg(enc, &m, compressed_dds_msg.data(), compressed_dds_msg.size(), &written);
   }
-  cldn_b200_encoder_destroy(enc);
   Cloudini::detail::check(rc);
   compressed_dds_msg.resize(written);
 }
@@ -181,7 +180,7 @@ inline void convertPointCloud2ToCompressedCloud(const RosPointCloud2& pc_info, c
 // ros_msg_utils.cpp:134-165 — the blob is decoded on the GPU straight into the output message
 inline void convertCompressedCloudToPointCloud2(const RosPointCloud2& pc_info, std::vector<uint8_t>& pc2_dds_msg) {
   cldn_decoder_t* dec = nullptr;
-  Cloudini::detail::check(cldn_b200_decoder_create(-1, nullptr, &dec));
+  Cloudini::detail::check(cldn_b200_pool_decoder(&dec));
   const cldn_ros_msg_t m = detail::to_c(pc_info);
   size_t need = 0, written = 0;
   int rc = cldn_b200_ros_decompress_msg(dec, &m, nullptr, 0, &need);
@@ -189,7 +188,6 @@ inline void convertCompressedCloudToPointCloud2(const RosPointCloud2& pc_info, s
     pc2_dds_msg.resize(need);
     rc = cldn_b200_ros_decompress_msg(dec, &m, pc2_dds_msg.data(), pc2_dds_msg.size(), &written);
   }
-  cldn_b200_decoder_destroy(dec);
   Cloudini::detail::check(rc);
   pc2_dds_msg.resize(written);
 }
@@ -199,13 +197,12 @@ inline void applyVizLossyPreprocessing(RosPointCloud2& pc_info) {
   Cloudini::EncodingInfo info = toEncodingInfo(pc_info);
   cldn_info_t c = Cloudini::detail::to_c(info);
   cldn_preproc_t* pp = nullptr;
-  Cloudini::detail::check(cldn_b200_preproc_create(-1, nullptr, &pp));
+  Cloudini::detail::check(cldn_b200_pool_preproc(&pp));
   std::vector<uint8_t> out(pc_info.data.size());
   size_t kept = 0;
   int applied = 0;
   const int rc = cldn_b200_viz_lossy_preprocess(pp, &c, pc_info.data.data(), pc_info.data.size(), out.data(), out.size(), &kept,
                                                 &applied, CLDN_MEM_HOST);
-  cldn_b200_preproc_destroy(pp);
   Cloudini::detail::check(rc);
   if (!applied) return;  // the reference's early returns leave pc_info untouched
   out.resize(kept * pc_info.point_step);

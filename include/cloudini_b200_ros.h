@@ -84,6 +84,25 @@ int cldn_b200_ros_compress_msg(cldn_encoder_t* enc, const cldn_ros_msg_t* msg, v
 int cldn_b200_ros_decompress_msg(cldn_decoder_t* dec, const cldn_ros_msg_t* msg, void* out, size_t out_capacity,
                                  size_t* written);
 
+/* The converter's per-message step (tools/src/mcap_converter.cpp:184-204: getDeserializedPointCloudMessage ->
+ * applyResolutionProfile -> [applyVizLossyPreprocessing] -> toEncodingInfo + options -> convertPointCloud2ToCompressedCloud)
+ * as ONE call, host message in, host message out. Same bytes as the five calls; what differs is where the payload lives:
+ * it is uploaded once, stays in HBM between the preprocessing and the encode kernels (only the 4-byte survivor count and
+ * the 8-byte blob size come back), and encoder / preprocessor / staging buffers come from a per-thread pool keyed by the
+ * layout instead of being created per message. compression_opt != NONE: stage 1 as above, then the host libraries.
+ * out == NULL queries a worst-case size. */
+int cldn_b200_ros_convert_msg(const void* dds_msg, size_t msg_bytes, const char* const* names, const float* resolutions,
+                              size_t n_profile, const float* default_resolution, int viz, int encoding_opt,
+                              int compression_opt, int version, void* out, size_t out_capacity, size_t* written);
+
+/* Handles of the calling thread's pool (created on first use, owned by the library, never to be destroyed by the caller;
+ * valid for this thread only). The reference constructs encoder / decoder objects per message, which costs it nothing;
+ * a GPU handle owns streams, device buffers and pinned memory, so the per-message callers (the shims of
+ * convertPointCloud2ToCompressedCloud & co.) take theirs from here. The encoder is re-dimensioned to info->width / height. */
+int cldn_b200_pool_encoder(const cldn_info_t* info, cldn_encoder_t** out);
+int cldn_b200_pool_decoder(cldn_decoder_t** out);
+int cldn_b200_pool_preproc(cldn_preproc_t** out);
+
 /* ---- the rest of the reference's own C ABI (include/cloudini_lib/wasm_functions.h:30-93, src/wasm_functions.cpp), the
  * functions that take DDS messages. Same shape and "return 0 on any failure" convention; every output pointer is
  * followed by its capacity (the WASM module trusts the caller's allocation instead). Host memory. ------------------- */

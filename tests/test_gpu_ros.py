@@ -89,6 +89,8 @@ def test_stage2_messages_interoperate(ref, comp):
     # default toEncodingInfo compression is ZSTD: compressed bytes differ between library versions, the round trip must not
     name, msg, profile, res = next(_cases())
     ours = _convert(msg, profile, res, False, comp)
+    fused = ros.convert_message(msg, profile, res, True, cb.EncodingOptions.LOSSY, comp, 5)   # stage 2 after the fused stage 1
+    assert ref.ros_decompress(fused, len(msg) + 4096) == ref.ros_decompress(ref.ros_compress(msg, profile, res, True, 1, int(comp), 5), len(msg) + 4096)
     theirs = ref.ros_compress(msg, profile, res, False, 1, int(comp), 5)
     want = ref.ros_decompress(theirs, len(msg) + 4096)
     assert ref.ros_decompress(ours, len(msg) + 4096) == want
@@ -100,6 +102,12 @@ def test_golden_messages(golden_ros):
     for name, g in golden_ros.items():
         got = _convert(g["msg"], g["profile"], g["default_resolution"], g["viz"], cb.CompressionOption.NONE)
         assert got == g["compressed"], name
+        # the same step as ONE library call (payload device resident between preprocessing and encode, pooled handles):
+        # twice, so that the second call runs on reused handles with another width than the first left behind
+        for _ in range(2):
+            fused = ros.convert_message(g["msg"], g["profile"], g["default_resolution"], g["viz"], cb.EncodingOptions.LOSSY,
+                                        cb.CompressionOption.NONE, 5)
+            assert fused == g["compressed"], name
         back = ros.convertCompressedCloudToPointCloud2(ros.getDeserializedPointCloudMessage(g["compressed"]))
         assert back == g["restored"], name
 

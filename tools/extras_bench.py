@@ -194,7 +194,15 @@ def bench_msg(out):
             step(viz)
         res["viz" if viz else "plain"] = {"ms_per_message": (time.perf_counter() - t0) / 5 * 1e3, "compressed_bytes": len(comp),
                                           "restored_bytes": len(back)}
-    out["dds_converter_step"] = dict(res, points=n, note="host buffers, Python mirror (fresh encoder per message like the reference)")
+    for viz in (False, True):   # the same step as one library call: payload device resident between viz and encode, pooled handles
+        want = step(viz)
+        got = ros.convert_message(msg, {}, 0.001, viz, cb.EncodingOptions.LOSSY, cb.CompressionOption.NONE, 5)
+        t0 = time.perf_counter()
+        for _ in range(10):
+            ros.convert_message(msg, {}, 0.001, viz, cb.EncodingOptions.LOSSY, cb.CompressionOption.NONE, 5)
+        res["fused_viz" if viz else "fused_plain"] = {"ms_per_message": (time.perf_counter() - t0) / 10 * 1e3, "same_bytes_as_the_five_calls": got == want}
+    out["dds_converter_step"] = dict(res, points=n, note="pageable host message in, host message out; plain / viz: the five mirror calls "
+                                     "(pooled handles); fused_*: cldn_b200_ros_convert_msg")
 
 
 if __name__ == "__main__":
