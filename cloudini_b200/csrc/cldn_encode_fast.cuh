@@ -1,20 +1,22 @@
-// ENCODE of packed XYZI float32x4 clouds (point_step 16, 16-byte aligned frames): the FAST FloatN kernel.
-// Included by cldn_encode.cu (shares finish_tile / find_frame; the build has no relocatable device code).
+// ENCODE of packed XYZI float32x4 clouds (point_step 16): the FAST FloatN kernel.
+// Included by cldn_encode.cu (shares find_frame / status words; the build has no relocatable device code).
 //
 // Same bytes as FieldEncoderFloatN_Lossy::encode (cloudini_lib/src/field_encoder.cpp:42-91) + WriteStage1Chunk's framing
 // (chunk_writer.cpp:27-48). Shape:
-//  * thread-blocked points: a thread owns 8 consecutive points of a 1024-point tile, so the previous point is a
-//    register (no shuffle / select per value) and the thread's bytes are ONE contiguous run of the output;
-//  * the tile is loaded with coalesced 16-byte loads and transposed through shared memory inside each warp
-//    (16-byte slots, XOR-swizzled: conflict-free both ways);
+//  * the unit of work is a WARP tile of 256 points; warps are independent persistent workers (worker w takes the tiles
+//    w, w + W, ... of the launch's global tile order) and never meet at a CTA barrier: everything a tile needs from
+//    other tiles arrives through the decoupled look-back over the frame's tile status words;
+//  * thread-blocked points: a lane owns 8 consecutive points, so the previous point is a register (no shuffle / select
+//    per value) and the lane's bytes are ONE contiguous run of the output;
+//  * the tile after next is already on its way while a tile is processed: cp.async (16 bytes per lane, straight into the
+//    XOR-swizzled 16-byte slots that make the transposed reads conflict-free), together with its frame record;
 //  * pass 1 (per value: FMUL, F2I, |s| tracking with max.NaN, delta, zigzag + 1, 7-bit groups -> bytes with two
 //    add/mask steps, continuation flags from the top bit) keeps the finished LEB128 words in registers and sums their
-//    lengths; one warp scan + 4 warp totals give every thread its byte offset;
+//    lengths; one warp scan gives every lane its byte offset and the tile its size, which is published at once;
 //  * pass 2 streams the words through a 64-bit register window and flushes aligned 32-bit words straight to their final
-//    place in the staging buffer: a thread starts its window with the last bytes of its predecessor (every thread
-//    publishes the last 4 bytes of its run before the scan), so words shared by two threads are written once, whole;
-//  * a CTA walks a group of 4 consecutive tiles of one frame: one decoupled look-back per group, the other tiles know
-//    their prefix locally and publish it as inclusive at once.
+//    place in the staging buffer: a lane starts its window with the last bytes of its predecessor, so words shared by
+//    two lanes are written once, whole;
+//  * copy-out with 16-byte stores, chunk prefix back-patch by the chunk's last tile.
 // Anything the 4-byte fast path cannot represent -- NaN / inf input, |v * mul| >= 2^25 (so that every delta fits 4
 // varint bytes and no product reaches the x86 "integer indefinite" range), a partial tile -- sends the TILE to the exact
 // byte-wise path below, which evaluates everything like the reference does.
@@ -22,20 +24,14 @@
 
 namespace cldn {
 
-constexpr int kET = 128;                  // threads per CTA
+constexpr int kET = 128;                  // threads per CTA (a container of 4 independent warps)
 constexpr int kEW = kET / 32;
-constexpr int kEP = 8;                    // points per thread and tile
-constexpr int kETilePts = kET * kEP;      // 1024
+constexpr int kEP = 8;                    // points per lane and tile
+constexpr int kETilePts = 32 * kEP;       // 256
 constexpr int kEBufBytes = kETilePts * 16;          // one input buffer = one tile of transposed points (later: its staged bytes)
-constexpr int kECarefulBytes = kETilePts * 20 + 64; // worst case of the exact path: 5 bytes per value
-constexpr int kESmemBytes = (2 * kEBufBytes > kECarefulBytes ? 2 * kEBufBytes : kECarefulBytes) + 64;
-
-struct EncFastShared {
-  uint32_t wtot[kEW];        // bytes per warp
-  uint32_t wtail[kEW];       // last 4 bytes of every warp's run (top byte = most recent)
-  unsigned long long excl;   // look-back result of the group's first tile
-  uint32_t scan[kET / 32 + 1];
-};
+constexpr int kEWarpBytes = 2 * kEBufBytes + 128;   // two buffers (the exact path stages up to 20 bytes per point across both) + slack
+constexpr int kESmemBytes = kEW * kEWarpBytes;
+constexpr int kEFrameCache = 32;          // frame records kept in shared memory per CTA
 
 // cp.async (LDGSTS): 16 bytes global -> shared without a register round trip; groups complete in commit order
 __device__ __forceinline__ void async_copy16(void* smem_dst, const void* gmem_src) {
@@ -44,6 +40,14 @@ __device__ __forceinline__ void async_copy16(void* smem_dst, const void* gmem_sr
 #else
   const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+#endif
+}
+__device__ __forceinline__ void async_copy8(void* smem_dst, const void* gmem_src) {
+#ifdef CLDN_CUSIM
+  *reinterpret_cast<uint2*>(smem_dst) = *reinterpret_cast<const uint2*>(gmem_src);
+#else
+  const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gmem_src) : "memory");
 #endif
 }
 __device__ __forceinline__ void async_commit() {
@@ -82,23 +86,22 @@ __device__ __forceinline__ uint32_t bitselect_e(uint32_t m, uint32_t a, uint32_t
   return d;
 }
 
-// Exact byte-wise evaluation of one tile (thread t owns points 8 t .. 8 t + 7), like the reference (field_encoder.cpp:42-91).
-// Returns the tile's byte count; the bytes are in `stage`. All threads of the CTA call it.
-template <int N>
-__device__ __noinline__ uint32_t encode_tile_careful(const EncFrame& F, const FloatNParams& P, uint32_t tile_p0, uint8_t* stage,
-                                                     uint32_t* scan_scratch) {
+// Exact byte-wise evaluation of one warp tile (lane l owns points 8 l .. 8 l + 7), like the reference
+// (field_encoder.cpp:42-91). Returns the tile's byte count; the bytes are in `stage`. One full warp calls it.
+__device__ __noinline__ uint32_t encode_warp_tile_careful(const EncFrame& F, const FloatNParams& P, uint32_t tile_p0, uint8_t* stage) {
+  const uint32_t lane = threadIdx.x & 31u;
   const uint32_t step = P.point_step;
   uint32_t len[kEP];
   uint32_t mine = 0;
 #pragma unroll 1
   for (int i = 0; i < kEP; ++i) {
-    const uint32_t p = tile_p0 + threadIdx.x * kEP + i;
+    const uint32_t p = tile_p0 + lane * kEP + i;
     uint32_t l = 0;
     if (p < F.n_points) {
       const uint8_t* pt = F.in + static_cast<size_t>(p) * step;
       const uint8_t* prevp = (p % kChunkPoints) ? pt - step : nullptr;
 #pragma unroll
-      for (int k = 0; k < N; ++k) {
+      for (int k = 0; k < 4; ++k) {
         const float x = __uint_as_float(load_u32(pt + P.offset[k]));
         if (isnan(x)) { l += 1; continue; }
         const int32_t q = quant_i32_x86(x, P.mul[k]);
@@ -114,18 +117,23 @@ __device__ __noinline__ uint32_t encode_tile_careful(const EncFrame& F, const Fl
     len[i] = l;
     mine += l;
   }
-  __syncthreads();  // the staging buffer may still hold the transposed input other warps are reading
-  uint32_t total;
-  uint32_t off = block_exclusive_scan_n<kET>(mine, scan_scratch, &total);
+  uint32_t inc = mine;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t up = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= static_cast<uint32_t>(d)) inc += up;
+  }
+  const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
+  uint32_t off = inc - mine;
 #pragma unroll 1
   for (int i = 0; i < kEP; ++i) {
-    const uint32_t p = tile_p0 + threadIdx.x * kEP + i;
+    const uint32_t p = tile_p0 + lane * kEP + i;
     if (p < F.n_points) {
       const uint8_t* pt = F.in + static_cast<size_t>(p) * step;
       const uint8_t* prevp = (p % kChunkPoints) ? pt - step : nullptr;
       ByteSink bs{stage + off};
 #pragma unroll
-      for (int k = 0; k < N; ++k) {
+      for (int k = 0; k < 4; ++k) {
         const float x = __uint_as_float(load_u32(pt + P.offset[k]));
         if (isnan(x)) { bs.put_byte(0); continue; }
         const int32_t q = quant_i32_x86(x, P.mul[k]);
@@ -140,16 +148,31 @@ __device__ __noinline__ uint32_t encode_tile_careful(const EncFrame& F, const Fl
       off += len[i];
     }
   }
+  __syncwarp();
   return total;
 }
 
-// Persistent CTAs: CTA b takes the tiles b, b + G, b + 2 G, ... of the launch's global tile order (frame-interleaved for
-// uniform batches, so the tiles a look-back depends on are being processed by other CTAs at the same time). While tile i
-// is quantised and packed, tile i + G is already on its way into the other input buffer (cp.async, 16 bytes per lane,
-// straight into the transposed slots): the load latency that a one-tile-per-CTA kernel exposes at every CTA start
-// (measured: a third of all stall samples) is hidden behind the previous tile's arithmetic.
-// All G CTAs must be co-resident (the grid is sized by the occupancy query): a CTA spins on aggregates of tiles with a
-// smaller global index, which belong to CTAs that are running.
+// Warp version of copy_stage_to_global: `n` staged bytes (16-byte aligned shared memory, readable up to n + 16) to an
+// arbitrarily aligned global address: 16-byte stores for the aligned body, byte stores for the <= 15-byte head and tail.
+__device__ __forceinline__ void warp_copy_stage_to_global(const uint8_t* stage, uint32_t n, uint8_t* g) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t a = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(g) & 15u);
+  uint32_t head = (16u - a) & 15u;
+  if (head > n) head = n;
+  const uint32_t nvec = (n - head) >> 4;
+  const uint32_t tail_begin = head + (nvec << 4);
+  if (lane < head) g[lane] = stage[lane];
+  if (lane >= 16u && lane - 16u < n - tail_begin) g[tail_begin + lane - 16u] = stage[tail_begin + lane - 16u];
+  const uint32_t sh = (head & 3u) * 8u;
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(stage + (head & ~3u));
+  uint4* gv = reinterpret_cast<uint4*>(g + head);
+  for (uint32_t j = lane; j < nvec; j += 32u) {
+    const uint32_t* q = w + 4 * j;
+    const uint32_t w0 = q[0], w1 = q[1], w2 = q[2], w3 = q[3], w4 = q[4];
+    gv[j] = make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh));
+  }
+}
+
 __device__ __forceinline__ void tile_coords(const EncLaunch& L, uint32_t i, uint32_t* fi, uint32_t* t) {
   if (L.uniform_tiles) {
     *fi = i % L.n_frames;
@@ -160,29 +183,41 @@ __device__ __forceinline__ void tile_coords(const EncLaunch& L, uint32_t i, uint
   }
 }
 
+// All workers must be co-resident (the grid is sized by the occupancy query): a worker spins on the sizes of tiles with a
+// smaller global index, which belong to workers that are running.
 __global__ void __launch_bounds__(kET, 6) encode_xyzi_fast_kernel(const EncLaunch L, const FloatNParams P) {
   extern __shared__ __align__(16) uint8_t dyn_smem[];
-  __shared__ EncFastShared sh;
-  __shared__ EncFrame s_F[2];
+  __shared__ EncFrame s_F[kEW][2];       // per worker: records of frames beyond the cache (double buffered)
+  __shared__ EncFrame s_cache[kEFrameCache];  // the batch's first frames (all of them for the usual batch sizes)
   __shared__ FloatNParams s_P;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   const bool aligned16 = (L.flags & kEncInputsAligned16) != 0u;
-  const uint32_t G = gridDim.x;
+  const uint32_t W = gridDim.x * kEW;
+  uint8_t* const wsm = dyn_smem + warp * kEWarpBytes;
 
   if (blockIdx.x == 0) handle_empty_frames(L);
-  uint32_t i = blockIdx.x;
+  if (threadIdx.x == 0) s_P = P;
+  {
+    const uint32_t n_cached = min(L.n_frames, static_cast<uint32_t>(kEFrameCache));
+    const unsigned long long* src = reinterpret_cast<const unsigned long long*>(L.frames);
+    unsigned long long* dst = reinterpret_cast<unsigned long long*>(s_cache);
+    for (uint32_t k = threadIdx.x; k < n_cached * (sizeof(EncFrame) / 8); k += kET) dst[k] = src[k];
+  }
+  __syncthreads();  // the only CTA barrier: frame records and the field table are in shared memory
+
+  uint32_t i = blockIdx.x * kEW + warp;
   if (i >= L.n_tiles_total) return;
   uint32_t fi, t;
   tile_coords(L, i, &fi, &t);
-  if (threadIdx.x == 0) { s_F[0] = L.frames[fi]; s_P = P; }
-  __syncthreads();
+  if (lane == 0 && fi >= kEFrameCache) s_F[warp][0] = L.frames[fi];
+  __syncwarp();
 
-  // asks for the 1024 points of tile t of frame F into `buf` (transposed slots); false if the tile is not eligible
+  // asks for the 256 points of tile tt of frame F into `buf` (transposed slots); false if the tile is not eligible
   auto prefetch = [&](const EncFrame& F, uint32_t tt, uint8_t* buf) -> bool {
     const uint32_t p0 = tt * kETilePts;
     if (!aligned16 || p0 + kETilePts > F.n_points) return false;
-    const uint4* src = reinterpret_cast<const uint4*>(F.in) + p0 + warp * (32 * kEP) + lane;
-    uint4* wsl = reinterpret_cast<uint4*>(buf) + warp * (32 * kEP);
+    const uint4* src = reinterpret_cast<const uint4*>(F.in) + p0 + lane;
+    uint4* wsl = reinterpret_cast<uint4*>(buf);
 #pragma unroll
     for (int k = 0; k < kEP; ++k) {
       const uint32_t q = 32u * k + lane, ol = q >> 3;
@@ -190,26 +225,33 @@ __global__ void __launch_bounds__(kET, 6) encode_xyzi_fast_kernel(const EncLaunc
     }
     return true;
   };
-  bool have_cur = prefetch(s_F[0], t, dyn_smem);
+  bool have_cur = prefetch(fi < kEFrameCache ? s_cache[fi] : s_F[warp][0], t, wsm);
   async_commit();
 
-  for (uint32_t cur = 0; i < L.n_tiles_total; i += G, cur ^= 1u) {
-    const EncFrame& F = s_F[cur];
-    uint8_t* buf = dyn_smem + cur * kEBufBytes;            // this tile's transposed input, then its staged output
+  for (uint32_t cur = 0; i < L.n_tiles_total; i += W, cur ^= 1u) {
+    uint8_t* buf = wsm + cur * kEBufBytes;                 // this tile's transposed input, then its staged output
     uint8_t* stage = buf;
-    // ---- the next tile of this CTA goes into the other buffer now ----
-    const uint32_t nxt = i + G;
+    // ---- the next tile of this worker (and its frame record) goes into the other buffer now ----
+    const uint32_t nxt = i + W;
     bool have_next = false;
     uint32_t nfi = 0, nt = 0;
     if (nxt < L.n_tiles_total) {
       tile_coords(L, nxt, &nfi, &nt);
-      if (threadIdx.x == 0) s_F[cur ^ 1u] = L.frames[nfi];
-      // (every thread needs the frame's input pointer and size for its own copies: read them from the table directly)
-      const EncFrame* NF = L.frames + nfi;
+      uint32_t np;
+      const uint8_t* nin;
+      if (nfi < kEFrameCache) {
+        np = s_cache[nfi].n_points;
+        nin = s_cache[nfi].in;
+      } else {  // large batches: the record travels with the tile's points, its two words needed now come straight from L2
+        const EncFrame* NF = L.frames + nfi;
+        if (lane < sizeof(EncFrame) / 8) async_copy8(reinterpret_cast<uint8_t*>(&s_F[warp][cur ^ 1u]) + 8 * lane, reinterpret_cast<const uint8_t*>(NF) + 8 * lane);
+        np = __ldg(&NF->n_points);
+        nin = reinterpret_cast<const uint8_t*>(__ldg(reinterpret_cast<const unsigned long long*>(&NF->in)));
+      }
       const uint32_t p0 = nt * kETilePts;
-      if (aligned16 && p0 + kETilePts <= NF->n_points) {
-        const uint4* src = reinterpret_cast<const uint4*>(NF->in) + p0 + warp * (32 * kEP) + lane;
-        uint4* wsl = reinterpret_cast<uint4*>(dyn_smem + (cur ^ 1u) * kEBufBytes) + warp * (32 * kEP);
+      if (aligned16 && p0 + kETilePts <= np) {
+        const uint4* src = reinterpret_cast<const uint4*>(nin) + p0 + lane;
+        uint4* wsl = reinterpret_cast<uint4*>(wsm + (cur ^ 1u) * kEBufBytes);
 #pragma unroll
         for (int k = 0; k < kEP; ++k) {
           const uint32_t q = 32u * k + lane, ol = q >> 3;
@@ -219,6 +261,9 @@ __global__ void __launch_bounds__(kET, 6) encode_xyzi_fast_kernel(const EncLaunc
       }
     }
     async_commit();
+    async_wait_all_but_last();   // this tile's copies (points, frame record) have landed; the next tile's may be in flight
+    __syncwarp();
+    const EncFrame& F = fi < kEFrameCache ? s_cache[fi] : s_F[warp][cur];
 
     const uint32_t tile = F.tile_begin + t;
     const uint32_t tile_p0 = t * kETilePts;
@@ -228,20 +273,17 @@ __global__ void __launch_bounds__(kET, 6) encode_xyzi_fast_kernel(const EncLaunc
     uint32_t X[kEP][4];
     uint32_t mine = 0, tail4 = 0;
     if (full) {
-      const uint32_t wp0 = tile_p0 + warp * (32 * kEP);
-      uint4* wsl = reinterpret_cast<uint4*>(buf) + warp * (32 * kEP);
-      if (have_cur) {
-        async_wait_all_but_last();   // this tile's copies have landed (the next tile's may still be in flight)
-      } else {
-        // ---- load + transpose inside the warp: lane l of iteration k loads point 32 k + l of the warp's 256 ----
+      uint4* wsl = reinterpret_cast<uint4*>(buf);
+      if (!have_cur) {
+        // ---- load + transpose: lane l of iteration k loads point 32 k + l of the tile ----
 #pragma unroll
         for (int k = 0; k < kEP; ++k) {
           const uint32_t q = 32u * k + lane;
           uint4 v;
           if (aligned16) {
-            v = __ldcs(reinterpret_cast<const uint4*>(F.in) + wp0 + q);
+            v = __ldcs(reinterpret_cast<const uint4*>(F.in) + tile_p0 + q);
           } else {
-            const uint8_t* pt = F.in + static_cast<size_t>(wp0 + q) * 16u;
+            const uint8_t* pt = F.in + static_cast<size_t>(tile_p0 + q) * 16u;
             v = make_uint4(load_u32(pt), load_u32(pt + 4), load_u32(pt + 8), load_u32(pt + 12));
           }
           const uint32_t ol = q >> 3;  // owner lane; slot of point j of lane l: 8 l + (j ^ (l & 7))
@@ -249,10 +291,9 @@ __global__ void __launch_bounds__(kET, 6) encode_xyzi_fast_kernel(const EncLaunc
         }
       }
       // previous point of my first point: 0 at a chunk start, else quantised like any point
-      const uint32_t p_first = wp0 + lane * kEP;
       uint4 pvu = make_uint4(0, 0, 0, 0);
-      if (lane == 0 && (p_first % kChunkPoints) != 0) {
-        const uint8_t* pt = F.in + static_cast<size_t>(p_first - 1) * 16u;
+      if (lane == 0 && (tile_p0 % kChunkPoints) != 0) {
+        const uint8_t* pt = F.in + static_cast<size_t>(tile_p0 - 1) * 16u;
         pvu = make_uint4(load_u32(pt), load_u32(pt + 4), load_u32(pt + 8), load_u32(pt + 12));
       }
       __syncwarp();
@@ -273,9 +314,11 @@ __global__ void __launch_bounds__(kET, 6) encode_xyzi_fast_kernel(const EncLaunc
       }
       // ---- pass 1: LEB128 words of my 32 values + their total length ----
       uint32_t nbl[3] = {0, 0, 0};  // bit lengths of my last three values (for the tail word)
+      const uint4* my_slots = wsl + 8 * lane;
+      const uint32_t lx = lane & 7u;
 #pragma unroll
       for (int j = 0; j < kEP; ++j) {
-        const uint4 u = wsl[8 * lane + (j ^ (lane & 7))];
+        const uint4 u = my_slots[j ^ lx];
         const float pf[4] = {__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z), __uint_as_float(u.w)};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -302,32 +345,23 @@ __global__ void __launch_bounds__(kET, 6) encode_xyzi_fast_kernel(const EncLaunc
       tail4 = __funnelshift_rc(tail4, X[kEP - 1][3], nbl[2]);
       fast = trk < 33554432.0f;  // 2^25; false for NaN
     }
-    // ---- offsets: warp scan + warp totals ----
-    uint32_t inc = mine;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const uint32_t up = __shfl_up_sync(0xffffffffu, inc, d);
-      if (lane >= d) inc += up;
-    }
-    uint32_t ptail = __shfl_up_sync(0xffffffffu, tail4, 1);
-    if (lane == 31) { sh.wtot[warp] = inc; sh.wtail[warp] = tail4; }
-    const int any_slow = __syncthreads_or(fast ? 0 : 1);  // also: every warp is done with its transposed input
     LookbackPoll lb;
-    if (!any_slow) {
-      uint32_t wbase = 0;
+    if (__all_sync(0xffffffffu, fast)) {
+      // ---- offsets: one warp scan ----
+      uint32_t inc = mine;
 #pragma unroll
-      for (int w = 0; w < kEW; ++w) {
-        const uint32_t c = sh.wtot[w];
-        if (w < warp) wbase += c;
-        total += c;
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t up = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= static_cast<uint32_t>(d)) inc += up;
       }
+      total = __shfl_sync(0xffffffffu, inc, 31);
+      uint32_t ptail = __shfl_up_sync(0xffffffffu, tail4, 1);
+      if (lane == 0) ptail = 0u;
       // the tile's size is final: publish it before the bytes are packed, so that successors never wait for pass 2
-      if (warp == 0) {
-        lb.begin(L.status, F.tile_begin, tile, L.epoch, total);
-        lb.issue(L.status, F.tile_begin, L.epoch);
-      }
-      if (lane == 0) ptail = warp > 0 ? sh.wtail[warp - 1] : 0u;
-      const uint32_t off = wbase + inc - mine;
+      lb.begin(L.status, F.tile_begin, tile, L.epoch, total);
+      lb.issue(L.status, F.tile_begin, L.epoch);
+      const uint32_t off = inc - mine;
+      __syncwarp();  // every lane is done with the transposed input the staged bytes are about to overwrite
       // ---- pass 2: 64-bit window, aligned word flushes ----
       // `bit` = bit position of the next byte in the tile's stream; the window's low word is the aligned word holding it
       uint32_t bit = 8u * off;
@@ -347,25 +381,43 @@ __global__ void __launch_bounds__(kET, 6) encode_xyzi_fast_kernel(const EncLaunc
           wa = wn;
         }
       }
-      if (threadIdx.x == kET - 1 && (bit & 31u) != 0u) *reinterpret_cast<uint32_t*>(stage + wa) = lo;  // nobody follows the tile's last thread
+      if (lane == 31u && (bit & 31u) != 0u) *reinterpret_cast<uint32_t*>(stage + wa) = lo;  // nobody follows the tile's last lane
     } else {
-      // exact path: up to 20 bytes per point, staged from the start of the dynamic shared memory across BOTH input buffers --
-      // the next tile's copies are drained first and the tile is loaded again, synchronously, when its turn comes
+      // exact path: up to 20 bytes per point, staged across BOTH buffers -- the next tile's copies are drained first and
+      // that tile is loaded again, synchronously, when its turn comes (its frame record has landed with them)
       async_wait_all();
-      __syncthreads();
+      __syncwarp();
       have_next = false;
-      stage = dyn_smem;
-      total = encode_tile_careful<4>(F, s_P, tile_p0, stage, sh.scan);
-      if (warp == 0) lb.begin(L.status, F.tile_begin, tile, L.epoch, total);
+      stage = wsm;
+      total = encode_warp_tile_careful(F, s_P, tile_p0, stage);
+      lb.begin(L.status, F.tile_begin, tile, L.epoch, total);
     }
-    // ---- the tile's place in the frame ----
-    if (warp == 0) {
-      const uint64_t e = lb.finish(L.status, F.tile_begin, tile, L.epoch, total);
-      if (lane == 0) sh.excl = e;
+    const uint64_t excl = lb.finish(L.status, F.tile_begin, tile, L.epoch, total);
+    __syncwarp();  // staged bytes complete
+    // ---- the tile's place in the frame: copy-out, chunk prefix back-patch, frame size (finish_tile for a warp) ----
+    {
+      constexpr uint32_t tiles_per_chunk = kChunkPoints / kETilePts;
+      const uint32_t chunk = t / tiles_per_chunk;
+      uint8_t* payload = F.out + L.header_bytes;
+      const uint64_t at = 4ull * (chunk + 1) + excl;
+      if (L.header_bytes + at + total <= F.out_cap) warp_copy_stage_to_global(stage, total, payload + at);
+      else if (lane == 0) report_error(L.err, DEV_ERR_ENCODE_OUTPUT_SMALL);
+      if (t == 0 && L.header_bytes <= F.out_cap) {
+        for (uint32_t k = lane; k < L.header_bytes; k += 32u) F.out[k] = L.header[k];
+      }
+      const bool last_of_frame = (t + 1 == F.n_tiles);
+      const bool last_of_chunk = last_of_frame || ((t + 1) % tiles_per_chunk == 0);
+      if (last_of_chunk && lane == 0) {
+        const uint32_t first = chunk * tiles_per_chunk;
+        const uint64_t data_before_chunk = (first == 0) ? 0 : wait_inclusive(L.status, F.tile_begin + first - 1, L.epoch);
+        const uint64_t body = (excl + total) - data_before_chunk;
+        if (L.header_bytes + 4ull * (chunk + 1) + data_before_chunk <= F.out_cap) {
+          store_u32(payload + 4ull * chunk + data_before_chunk, static_cast<uint32_t>(body));  // chunk_writer.cpp:33-40
+        }
+        if (last_of_frame) L.sizes[fi] = L.header_bytes + 4ull * F.n_chunks + excl + total;
+      }
     }
-    __syncthreads();  // staged bytes + sh.excl complete (and s_F[cur ^ 1] written)
-    finish_tile<kETilePts>(L, F, fi, t, stage, total, sh.excl);
-    __syncthreads();  // this buffer receives the tile after next
+    __syncwarp();  // this buffer receives the tile after next
     have_cur = have_next;
     fi = nfi;
     t = nt;
@@ -401,7 +453,7 @@ static int launch_encode_fast(const Plan& plan, const EncLaunch& L, cudaStream_t
   auto k = encode_xyzi_fast_kernel;
   if (set_smem(k, smem) != cudaSuccess) return -1;
   // persistent grid: every CTA must be resident (they wait for each other's tile sizes)
-  static int resident = 0;
+  static int resident = 0;  // CTAs (of 4 independent warp workers each)
   if (resident == 0) {
     int dev = 0, sms = 0, per_sm = 0;
     cudaGetDevice(&dev);
@@ -409,7 +461,7 @@ static int launch_encode_fast(const Plan& plan, const EncLaunch& L, cudaStream_t
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kET, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
     resident = std::max(1, sms) * per_sm;
   }
-  const uint32_t grid = std::min<uint32_t>(L.n_tiles_total, static_cast<uint32_t>(resident));
+  const uint32_t grid = std::min<uint32_t>((L.n_tiles_total + kEW - 1) / kEW, static_cast<uint32_t>(resident));
   k<<<grid, kET, smem, stream>>>(L, P);
   count_launch();
   return 1;

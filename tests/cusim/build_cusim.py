@@ -39,6 +39,7 @@ PTX = {
     "prefetch.global.L2": lambda outs, ins: "((void)0);",
     # cp.async: the kernels compile these only without CLDN_CUSIM (the emulation copies synchronously); still rewritten
     "cp.async.cg.shared.global": lambda outs, ins: "((void)0);",
+    "cp.async.ca.shared.global": lambda outs, ins: "((void)0);",
     "cp.async.commit_group": lambda outs, ins: "((void)0);",
     "cp.async.wait_group": lambda outs, ins: "((void)0);",
     "shl.b32": lambda outs, ins: f"{outs[0]} = (({ins[1]}) > 31u) ? 0u : (static_cast<unsigned>({ins[0]}) << ({ins[1]}));",

@@ -173,3 +173,23 @@ def test_fast_writer_batches(oracle):
     out = _Dev(size=cap)
     sizes = enc.encode_batch_device(enc.make_device_batch([shifted.ptr + 4], [n * 16], [out.ptr], [cap]), write_header=True, want_sizes=True)
     assert bytes(out.numpy()[:sizes[0]]) == oracle.encode(info, clouds[0])
+
+
+def test_fast_writer_large_and_ragged_batches(oracle):
+    # more frames than the kernel caches records for (32), frames of different sizes (no uniform tile order), empty frames
+    rng = np.random.default_rng(3)
+    sizes_pts = [int(x) for x in rng.integers(1, 5000, 44)] + [0, 256, 257, 32768, 33000, 0]
+    F = len(sizes_pts)
+    info = synth.info_xyzi(1)
+    clouds = [synth.cloud_c2(max(n, 1), seed=500 + k)[1][:n * 16] for k, n in enumerate(sizes_pts)]
+    clouds[5] = _xyzi_adversarial(sizes_pts[5] or 1, seed=77)[1][:sizes_pts[5] * 16]
+    enc = cb.PointcloudEncoder(info)
+    caps = [cb.MaxCompressedSize(synth.info_xyzi(max(n, 1)), n, True) + 64 for n in sizes_pts]
+    d_in = [_Dev(src=c) if c.size else _Dev(size=16) for c in clouds]
+    d_blob = [_Dev(size=c) for c in caps]
+    sizes = enc.encode_batch_device(enc.make_device_batch([t.ptr for t in d_in], [n * 16 for n in sizes_pts], [t.ptr for t in d_blob], caps),
+                                    write_header=False, want_sizes=True)
+    for k, n in enumerate(sizes_pts):
+        one = synth.info_xyzi(n)
+        want = oracle.encode(one, clouds[k], write_header=False) if n else b""
+        assert bytes(d_blob[k].numpy()[:sizes[k]]) == want, (k, n)
