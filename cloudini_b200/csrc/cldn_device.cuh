@@ -417,13 +417,14 @@ struct LookbackPoll {
   uint64_t s;          // this lane's status word in flight
   bool done;
 
-  __device__ __forceinline__ void begin(uint64_t* status, uint32_t first, uint32_t me, uint32_t epoch, uint64_t aggregate) {
+  // `publish` = false: another warp of the CTA publishes this tile's words; this warp only resolves the prefix for itself
+  __device__ __forceinline__ void begin(uint64_t* status, uint32_t first, uint32_t me, uint32_t epoch, uint64_t aggregate, bool publish = true) {
     const int lane = threadIdx.x & 31;
     exclusive = 0;
     idx = static_cast<int64_t>(me) - 1;
     done = (me == first);
     s = 0;
-    if (lane == 0) st_relaxed_u64(status + me, pack_status(done ? kFlagIncl : kFlagAgg, epoch, aggregate));
+    if (publish && lane == 0) st_relaxed_u64(status + me, pack_status(done ? kFlagIncl : kFlagAgg, epoch, aggregate));
   }
   __device__ __forceinline__ void issue(const uint64_t* status, uint32_t first, uint32_t epoch) {
     if (done) return;
@@ -444,13 +445,13 @@ struct LookbackPoll {
     exclusive += v;
     if (incl_mask) done = true; else idx -= 32;
   }
-  __device__ __forceinline__ uint64_t finish(uint64_t* status, uint32_t first, uint32_t me, uint32_t epoch, uint64_t aggregate) {
+  __device__ __forceinline__ uint64_t finish(uint64_t* status, uint32_t first, uint32_t me, uint32_t epoch, uint64_t aggregate, bool publish = true) {
     const bool was_first = (me == first);
     while (!done) {
       issue(status, first, epoch);
       eval(epoch);
     }
-    if (!was_first && (threadIdx.x & 31) == 0) st_relaxed_u64(status + me, pack_status(kFlagIncl, epoch, exclusive + aggregate));
+    if (publish && !was_first && (threadIdx.x & 31) == 0) st_relaxed_u64(status + me, pack_status(kFlagIncl, epoch, exclusive + aggregate));
     return exclusive;
   }
 };

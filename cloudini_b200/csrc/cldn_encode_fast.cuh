@@ -3,9 +3,12 @@
 //
 // Same bytes as FieldEncoderFloatN_Lossy::encode (cloudini_lib/src/field_encoder.cpp:42-91) + WriteStage1Chunk's framing
 // (chunk_writer.cpp:27-48). Shape:
-//  * the unit of work is a WARP tile of 256 points; warps are independent persistent workers (worker w takes the tiles
-//    w, w + W, ... of the launch's global tile order) and never meet at a CTA barrier: everything a tile needs from
-//    other tiles arrives through the decoupled look-back over the frame's tile status words;
+//  * persistent CTAs: CTA b takes the tiles (1024 points) b, b + G, ... of the launch's global tile order; a tile is four
+//    warp quarters of 256 points with warp-private buffers, so the warps meet at ONE barrier per tile (the tile's size
+//    and the quarters' offsets); every warp then resolves the decoupled look-back over the frame's tile status words for
+//    itself and copies its own bytes out -- no barrier for the prefix, none for buffer reuse. (Measured alternatives:
+//    one tile per CTA exposes the load latency at every CTA start; 256-point warp tiles without any barrier make the
+//    look-back four times deeper and lose to it.)
 //  * thread-blocked points: a lane owns 8 consecutive points, so the previous point is a register (no shuffle / select
 //    per value) and the lane's bytes are ONE contiguous run of the output;
 //  * the tile after next is already on its way while a tile is processed: cp.async (16 bytes per lane, straight into the
@@ -27,8 +30,10 @@ namespace cldn {
 constexpr int kET = 128;                  // threads per CTA (a container of 4 independent warps)
 constexpr int kEW = kET / 32;
 constexpr int kEP = 8;                    // points per lane and tile
-constexpr int kETilePts = 32 * kEP;       // 256
-constexpr int kEBufBytes = kETilePts * 16;          // one input buffer = one tile of transposed points (later: its staged bytes)
+constexpr int kEQuarterPts = 32 * kEP;    // 256 points per warp
+constexpr int kETilePts = kEW * kEQuarterPts;       // 1024
+constexpr int kEBufBytes = kEQuarterPts * 16 + 16;  // one input buffer = a warp's transposed points + the point in front of them
+                                                    // (later: the warp's staged bytes)
 constexpr int kEWarpBytes = 2 * kEBufBytes + 128;   // two buffers (the exact path stages up to 20 bytes per point across both) + slack
 constexpr int kESmemBytes = kEW * kEWarpBytes;
 constexpr int kEFrameCache = 32;          // frame records kept in shared memory per CTA
@@ -183,56 +188,69 @@ __device__ __forceinline__ void tile_coords(const EncLaunch& L, uint32_t i, uint
   }
 }
 
-// All workers must be co-resident (the grid is sized by the occupancy query): a worker spins on the sizes of tiles with a
-// smaller global index, which belong to workers that are running.
+// All CTAs must be co-resident (the grid is sized by the occupancy query): a CTA spins on the sizes of tiles with a smaller
+// global index, which belong to CTAs that are running.
+struct EncFastShared {
+  uint32_t wtot[2][kEW];   // bytes per warp quarter, by tile parity (no barrier separates consecutive tiles)
+  uint32_t slow[2];        // exact path: second exchange
+};
+
 __global__ void __launch_bounds__(kET, 6) encode_xyzi_fast_kernel(const EncLaunch L, const FloatNParams P) {
   extern __shared__ __align__(16) uint8_t dyn_smem[];
-  __shared__ EncFrame s_F[kEW][2];       // per worker: records of frames beyond the cache (double buffered)
-  __shared__ EncFrame s_cache[kEFrameCache];  // the batch's first frames (all of them for the usual batch sizes)
+  __shared__ EncFastShared sh;
+  __shared__ EncFrame s_F[kEW][2];             // per warp: records of frames beyond the cache (double buffered by tile parity)
+  __shared__ EncFrame s_cache[kEFrameCache];   // the batch's first frames (all of them for the usual batch sizes)
   __shared__ FloatNParams s_P;
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   const bool aligned16 = (L.flags & kEncInputsAligned16) != 0u;
-  const uint32_t W = gridDim.x * kEW;
+  const uint32_t G = gridDim.x;
   uint8_t* const wsm = dyn_smem + warp * kEWarpBytes;
 
   if (blockIdx.x == 0) handle_empty_frames(L);
-  if (threadIdx.x == 0) s_P = P;
+  uint32_t i = blockIdx.x;
+  uint32_t fi = 0, t = 0;
+  if (i < L.n_tiles_total) tile_coords(L, i, &fi, &t);
+  if (threadIdx.x == 0) {
+    s_P = P;
+  }
+  if (lane == 0 && i < L.n_tiles_total && fi >= kEFrameCache) s_F[warp][0] = L.frames[fi];
   {
     const uint32_t n_cached = min(L.n_frames, static_cast<uint32_t>(kEFrameCache));
     const unsigned long long* src = reinterpret_cast<const unsigned long long*>(L.frames);
     unsigned long long* dst = reinterpret_cast<unsigned long long*>(s_cache);
     for (uint32_t k = threadIdx.x; k < n_cached * (sizeof(EncFrame) / 8); k += kET) dst[k] = src[k];
   }
-  __syncthreads();  // the only CTA barrier: frame records and the field table are in shared memory
-
-  uint32_t i = blockIdx.x * kEW + warp;
+  __syncthreads();  // frame records and the field table are in shared memory
   if (i >= L.n_tiles_total) return;
-  uint32_t fi, t;
-  tile_coords(L, i, &fi, &t);
-  if (lane == 0 && fi >= kEFrameCache) s_F[warp][0] = L.frames[fi];
-  __syncwarp();
 
-  // asks for the 256 points of tile tt of frame F into `buf` (transposed slots); false if the tile is not eligible
-  auto prefetch = [&](const EncFrame& F, uint32_t tt, uint8_t* buf) -> bool {
+  // asks for this warp's 256 points of tile tt (frame input `in`, `np` points) into `buf` (transposed slots, + the point
+  // in front of them in slot 256); false if the tile is not eligible
+  auto prefetch = [&](const uint8_t* in, uint32_t np, uint32_t tt, uint8_t* buf) -> bool {
     const uint32_t p0 = tt * kETilePts;
-    if (!aligned16 || p0 + kETilePts > F.n_points) return false;
-    const uint4* src = reinterpret_cast<const uint4*>(F.in) + p0 + lane;
+    if (!aligned16 || p0 + kETilePts > np) return false;
+    const uint32_t q0 = p0 + warp * kEQuarterPts;
+    const uint4* src = reinterpret_cast<const uint4*>(in) + q0 + lane;
     uint4* wsl = reinterpret_cast<uint4*>(buf);
 #pragma unroll
     for (int k = 0; k < kEP; ++k) {
       const uint32_t q = 32u * k + lane, ol = q >> 3;
       async_copy16(wsl + 8 * ol + ((q & 7u) ^ (ol & 7u)), src + 32 * k);
     }
+    if (lane == 0 && (q0 % kChunkPoints) != 0) async_copy16(wsl + kEQuarterPts, reinterpret_cast<const uint4*>(in) + q0 - 1);
     return true;
   };
-  bool have_cur = prefetch(fi < kEFrameCache ? s_cache[fi] : s_F[warp][0], t, wsm);
+  bool have_cur;
+  {
+    const EncFrame& F0 = fi < kEFrameCache ? s_cache[fi] : s_F[warp][0];
+    have_cur = prefetch(F0.in, F0.n_points, t, wsm);
+  }
   async_commit();
 
-  for (uint32_t cur = 0; i < L.n_tiles_total; i += W, cur ^= 1u) {
-    uint8_t* buf = wsm + cur * kEBufBytes;                 // this tile's transposed input, then its staged output
+  for (uint32_t cur = 0; i < L.n_tiles_total; i += G, cur ^= 1u) {
+    uint8_t* buf = wsm + cur * kEBufBytes;                 // this quarter's transposed input, then its staged output
     uint8_t* stage = buf;
-    // ---- the next tile of this worker (and its frame record) goes into the other buffer now ----
-    const uint32_t nxt = i + W;
+    // ---- the next tile of this CTA (and, for large batches, its frame record) goes into the other buffer now ----
+    const uint32_t nxt = i + G;
     bool have_next = false;
     uint32_t nfi = 0, nt = 0;
     if (nxt < L.n_tiles_total) {
@@ -248,58 +266,50 @@ __global__ void __launch_bounds__(kET, 6) encode_xyzi_fast_kernel(const EncLaunc
         np = __ldg(&NF->n_points);
         nin = reinterpret_cast<const uint8_t*>(__ldg(reinterpret_cast<const unsigned long long*>(&NF->in)));
       }
-      const uint32_t p0 = nt * kETilePts;
-      if (aligned16 && p0 + kETilePts <= np) {
-        const uint4* src = reinterpret_cast<const uint4*>(nin) + p0 + lane;
-        uint4* wsl = reinterpret_cast<uint4*>(wsm + (cur ^ 1u) * kEBufBytes);
-#pragma unroll
-        for (int k = 0; k < kEP; ++k) {
-          const uint32_t q = 32u * k + lane, ol = q >> 3;
-          async_copy16(wsl + 8 * ol + ((q & 7u) ^ (ol & 7u)), src + 32 * k);
-        }
-        have_next = true;
-      }
+      have_next = prefetch(nin, np, nt, wsm + (cur ^ 1u) * kEBufBytes);
     }
     async_commit();
-    async_wait_all_but_last();   // this tile's copies (points, frame record) have landed; the next tile's may be in flight
+    async_wait_all_but_last();   // this tile's copies have landed; the next tile's may be in flight
     __syncwarp();
     const EncFrame& F = fi < kEFrameCache ? s_cache[fi] : s_F[warp][cur];
 
     const uint32_t tile = F.tile_begin + t;
     const uint32_t tile_p0 = t * kETilePts;
+    const uint32_t q0 = tile_p0 + warp * kEQuarterPts;     // my warp's first point
     const bool full = tile_p0 + kETilePts <= F.n_points;
-    uint32_t total = 0;
     bool fast = full;
     uint32_t X[kEP][4];
-    uint32_t mine = 0, tail4 = 0;
+    uint32_t mine = 0;
     if (full) {
       uint4* wsl = reinterpret_cast<uint4*>(buf);
       if (!have_cur) {
-        // ---- load + transpose: lane l of iteration k loads point 32 k + l of the tile ----
+        // ---- load + transpose: lane l of iteration k loads point 32 k + l of the quarter ----
 #pragma unroll
         for (int k = 0; k < kEP; ++k) {
           const uint32_t q = 32u * k + lane;
           uint4 v;
           if (aligned16) {
-            v = __ldcs(reinterpret_cast<const uint4*>(F.in) + tile_p0 + q);
+            v = __ldcs(reinterpret_cast<const uint4*>(F.in) + q0 + q);
           } else {
-            const uint8_t* pt = F.in + static_cast<size_t>(tile_p0 + q) * 16u;
+            const uint8_t* pt = F.in + static_cast<size_t>(q0 + q) * 16u;
             v = make_uint4(load_u32(pt), load_u32(pt + 4), load_u32(pt + 8), load_u32(pt + 12));
           }
           const uint32_t ol = q >> 3;  // owner lane; slot of point j of lane l: 8 l + (j ^ (l & 7))
           wsl[8 * ol + ((q & 7u) ^ (ol & 7u))] = v;
         }
+        if (lane == 0 && (q0 % kChunkPoints) != 0) {
+          const uint8_t* pt = F.in + static_cast<size_t>(q0 - 1) * 16u;
+          wsl[kEQuarterPts] = make_uint4(load_u32(pt), load_u32(pt + 4), load_u32(pt + 8), load_u32(pt + 12));
+        }
+        __syncwarp();
       }
       // previous point of my first point: 0 at a chunk start, else quantised like any point
       uint4 pvu = make_uint4(0, 0, 0, 0);
-      if (lane == 0 && (tile_p0 % kChunkPoints) != 0) {
-        const uint8_t* pt = F.in + static_cast<size_t>(tile_p0 - 1) * 16u;
-        pvu = make_uint4(load_u32(pt), load_u32(pt + 4), load_u32(pt + 8), load_u32(pt + 12));
-      }
-      __syncwarp();
       if (lane != 0) {
         const uint32_t pl = lane - 1;
         pvu = wsl[8 * pl + (7u ^ (pl & 7u))];
+      } else if ((q0 % kChunkPoints) != 0) {
+        pvu = wsl[kEQuarterPts];
       }
       float trk = 0.0f;
       int32_t prev[4];
@@ -313,7 +323,6 @@ __global__ void __launch_bounds__(kET, 6) encode_xyzi_fast_kernel(const EncLaunc
         }
       }
       // ---- pass 1: LEB128 words of my 32 values + their total length ----
-      uint32_t nbl[3] = {0, 0, 0};  // bit lengths of my last three values (for the tail word)
       const uint4* my_slots = wsl + 8 * lane;
       const uint32_t lx = lane & 7u;
 #pragma unroll
@@ -335,37 +344,61 @@ __global__ void __launch_bounds__(kET, 6) encode_xyzi_fast_kernel(const EncLaunc
           x |= low_mask(b) & 0x00808080u;                          // continuation flags on every byte below it
           X[j][k] = x;
           mine += b >> 3;
-          if (j == kEP - 1 && k >= 1) nbl[k - 1] = (b & 0x18u) + 8u;
         }
       }
       mine += kEP * 4;
-      // last 4 bytes of my run (top byte = most recent): the successor starts its window with them
-      tail4 = __funnelshift_rc(tail4, X[kEP - 1][1], nbl[0]);
-      tail4 = __funnelshift_rc(tail4, X[kEP - 1][2], nbl[1]);
-      tail4 = __funnelshift_rc(tail4, X[kEP - 1][3], nbl[2]);
       fast = trk < 33554432.0f;  // 2^25; false for NaN
     }
-    LookbackPoll lb;
-    if (__all_sync(0xffffffffu, fast)) {
-      // ---- offsets: one warp scan ----
-      uint32_t inc = mine;
+    // ---- offsets inside the quarter (warp scan); the quarters' sizes meet at the tile's one barrier ----
+    uint32_t inc = mine;
 #pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t up = __shfl_up_sync(0xffffffffu, inc, d);
-        if (lane >= static_cast<uint32_t>(d)) inc += up;
-      }
-      total = __shfl_sync(0xffffffffu, inc, 31);
-      uint32_t ptail = __shfl_up_sync(0xffffffffu, tail4, 1);
-      if (lane == 0) ptail = 0u;
-      // the tile's size is final: publish it before the bytes are packed, so that successors never wait for pass 2
-      lb.begin(L.status, F.tile_begin, tile, L.epoch, total);
-      lb.issue(L.status, F.tile_begin, L.epoch);
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t up = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= static_cast<uint32_t>(d)) inc += up;
+    }
+    uint32_t wtot = __shfl_sync(0xffffffffu, inc, 31);
+    if (lane == 0) sh.wtot[cur][warp] = wtot;
+    const int any_slow = __syncthreads_or(fast ? 0 : 1);
+    if (any_slow) {
+      // exact path: up to 20 bytes per point, staged across BOTH of the warp's buffers -- the next tile's copies are drained
+      // first and that tile is loaded again, synchronously, when its turn comes
+      async_wait_all();
+      __syncwarp();
+      have_next = false;
+      stage = wsm;
+      wtot = encode_warp_tile_careful(F, s_P, q0, stage);
+      if (lane == 0) sh.wtot[cur][warp] = wtot;   // every warp has read the fast sizes? they are not used on this path
+      __syncthreads();
+    }
+    uint32_t wbase = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < kEW; ++w) {
+      const uint32_t c = sh.wtot[cur][w];
+      if (static_cast<uint32_t>(w) < warp) wbase += c;
+      total += c;
+    }
+    // the tile's size is final: warp 0 publishes it before the bytes are packed; every warp follows the look-back itself
+    LookbackPoll lb;
+    lb.begin(L.status, F.tile_begin, tile, L.epoch, total, warp == 0);
+    lb.issue(L.status, F.tile_begin, L.epoch);
+    if (!any_slow) {
       const uint32_t off = inc - mine;
       __syncwarp();  // every lane is done with the transposed input the staged bytes are about to overwrite
-      // ---- pass 2: 64-bit window, aligned word flushes ----
-      // `bit` = bit position of the next byte in the tile's stream; the window's low word is the aligned word holding it
+      // ---- pass 2: 64-bit window, aligned word flushes. The quarter's bytes start at staging offset 0. ----
+      // `bit` = bit position of the next byte in the quarter's stream; the window's low word is the aligned word holding it
       uint32_t bit = 8u * off;
-      uint32_t lo = __funnelshift_rc(ptail, 0u, 32u - (bit & 31u));   // the last off % 4 bytes of the predecessor (0 if none)
+      // a lane starts its window with the last off % 4 bytes of its predecessor: the last 4 bytes of every lane's run
+      // (top byte = most recent) travel one lane up
+      uint32_t lo;
+      {
+        uint32_t t4 = 0;
+        t4 = __funnelshift_rc(t4, X[kEP - 1][1], (top_bit(X[kEP - 1][1]) & 0x18u) + 8u);
+        t4 = __funnelshift_rc(t4, X[kEP - 1][2], (top_bit(X[kEP - 1][2]) & 0x18u) + 8u);
+        t4 = __funnelshift_rc(t4, X[kEP - 1][3], (top_bit(X[kEP - 1][3]) & 0x18u) + 8u);
+        uint32_t ptail = __shfl_up_sync(0xffffffffu, t4, 1);
+        if (lane == 0) ptail = 0u;
+        lo = __funnelshift_rc(ptail, 0u, 32u - (bit & 31u));
+      }
       uint32_t wa = (bit >> 3) & ~3u;                                 // byte address of that word in the staging buffer
 #pragma unroll
       for (int j = 0; j < kEP; ++j) {
@@ -381,33 +414,24 @@ __global__ void __launch_bounds__(kET, 6) encode_xyzi_fast_kernel(const EncLaunc
           wa = wn;
         }
       }
-      if (lane == 31u && (bit & 31u) != 0u) *reinterpret_cast<uint32_t*>(stage + wa) = lo;  // nobody follows the tile's last lane
-    } else {
-      // exact path: up to 20 bytes per point, staged across BOTH buffers -- the next tile's copies are drained first and
-      // that tile is loaded again, synchronously, when its turn comes (its frame record has landed with them)
-      async_wait_all();
-      __syncwarp();
-      have_next = false;
-      stage = wsm;
-      total = encode_warp_tile_careful(F, s_P, tile_p0, stage);
-      lb.begin(L.status, F.tile_begin, tile, L.epoch, total);
+      if (lane == 31u && (bit & 31u) != 0u) *reinterpret_cast<uint32_t*>(stage + wa) = lo;  // nobody follows the quarter's last lane
     }
-    const uint64_t excl = lb.finish(L.status, F.tile_begin, tile, L.epoch, total);
+    const uint64_t excl = lb.finish(L.status, F.tile_begin, tile, L.epoch, total, warp == 0);
     __syncwarp();  // staged bytes complete
-    // ---- the tile's place in the frame: copy-out, chunk prefix back-patch, frame size (finish_tile for a warp) ----
+    // ---- the quarter's place in the frame: copy-out; the tile's last warp back-patches the chunk prefix / frame size ----
     {
       constexpr uint32_t tiles_per_chunk = kChunkPoints / kETilePts;
       const uint32_t chunk = t / tiles_per_chunk;
       uint8_t* payload = F.out + L.header_bytes;
-      const uint64_t at = 4ull * (chunk + 1) + excl;
-      if (L.header_bytes + at + total <= F.out_cap) warp_copy_stage_to_global(stage, total, payload + at);
+      const uint64_t at = 4ull * (chunk + 1) + excl + wbase;
+      if (L.header_bytes + at + wtot <= F.out_cap) warp_copy_stage_to_global(stage, wtot, payload + at);
       else if (lane == 0) report_error(L.err, DEV_ERR_ENCODE_OUTPUT_SMALL);
-      if (t == 0 && L.header_bytes <= F.out_cap) {
+      if (t == 0 && warp == 0 && L.header_bytes <= F.out_cap) {
         for (uint32_t k = lane; k < L.header_bytes; k += 32u) F.out[k] = L.header[k];
       }
       const bool last_of_frame = (t + 1 == F.n_tiles);
       const bool last_of_chunk = last_of_frame || ((t + 1) % tiles_per_chunk == 0);
-      if (last_of_chunk && lane == 0) {
+      if (last_of_chunk && warp == kEW - 1 && lane == 0) {
         const uint32_t first = chunk * tiles_per_chunk;
         const uint64_t data_before_chunk = (first == 0) ? 0 : wait_inclusive(L.status, F.tile_begin + first - 1, L.epoch);
         const uint64_t body = (excl + total) - data_before_chunk;
@@ -453,7 +477,7 @@ static int launch_encode_fast(const Plan& plan, const EncLaunch& L, cudaStream_t
   auto k = encode_xyzi_fast_kernel;
   if (set_smem(k, smem) != cudaSuccess) return -1;
   // persistent grid: every CTA must be resident (they wait for each other's tile sizes)
-  static int resident = 0;  // CTAs (of 4 independent warp workers each)
+  static int resident = 0;
   if (resident == 0) {
     int dev = 0, sms = 0, per_sm = 0;
     cudaGetDevice(&dev);
@@ -461,7 +485,7 @@ static int launch_encode_fast(const Plan& plan, const EncLaunch& L, cudaStream_t
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kET, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
     resident = std::max(1, sms) * per_sm;
   }
-  const uint32_t grid = std::min<uint32_t>((L.n_tiles_total + kEW - 1) / kEW, static_cast<uint32_t>(resident));
+  const uint32_t grid = std::min<uint32_t>(L.n_tiles_total, static_cast<uint32_t>(resident));
   k<<<grid, kET, smem, stream>>>(L, P);
   count_launch();
   return 1;
