@@ -70,6 +70,9 @@ __device__ __forceinline__ void async_wait_all() {
   asm volatile("cp.async.wait_group 0;" ::: "memory");
 #endif
 }
+__device__ __forceinline__ void prefetch_l2_enc(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
 __device__ __forceinline__ float max_nan(float a, float b) {  // NaN if either is NaN (fmaxf would drop it)
   float d;
   asm("max.NaN.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b));
@@ -191,14 +194,46 @@ __device__ __forceinline__ void tile_coords(const EncLaunch& L, uint32_t i, uint
 // All CTAs must be co-resident (the grid is sized by the occupancy query): a CTA spins on the sizes of tiles with a smaller
 // global index, which belong to CTAs that are running.
 struct EncFastShared {
-  uint32_t wtot[2][kEW];   // bytes per warp quarter, by tile parity (no barrier separates consecutive tiles)
-  uint32_t slow[2];        // exact path: second exchange
+  uint32_t wtot[2][kEW];        // bytes per warp quarter, by tile parity (no barrier separates consecutive tiles)
+  unsigned long long excl[2];   // look-back result of the pending tile (by ITS parity), written by warp 0
 };
+
+// What a warp remembers of the tile whose bytes are staged but not yet copied out: the copy happens one tile later, behind
+// the next tile's barrier, so that the look-back (warp 0) has a whole pass 1 to resolve instead of being waited for.
+struct PendingQuarter {
+  const uint8_t* stage;
+  uint32_t wtot, wbase, total, fi, t, par;
+  bool valid;
+};
+
+__device__ __forceinline__ void place_quarter(const EncLaunch& L, const EncFrame& F, const PendingQuarter& Q, uint64_t excl) {
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  constexpr uint32_t tiles_per_chunk = kChunkPoints / kETilePts;
+  const uint32_t chunk = Q.t / tiles_per_chunk;
+  uint8_t* payload = F.out + L.header_bytes;
+  const uint64_t at = 4ull * (chunk + 1) + excl + Q.wbase;
+  if (L.header_bytes + at + Q.wtot <= F.out_cap) warp_copy_stage_to_global(Q.stage, Q.wtot, payload + at);
+  else if (lane == 0) report_error(L.err, DEV_ERR_ENCODE_OUTPUT_SMALL);
+  if (Q.t == 0 && warp == 0 && L.header_bytes <= F.out_cap) {
+    for (uint32_t k = lane; k < L.header_bytes; k += 32u) F.out[k] = L.header[k];
+  }
+  const bool last_of_frame = (Q.t + 1 == F.n_tiles);
+  const bool last_of_chunk = last_of_frame || ((Q.t + 1) % tiles_per_chunk == 0);
+  if (last_of_chunk && warp == kEW - 1 && lane == 0) {
+    const uint32_t first = chunk * tiles_per_chunk;
+    const uint64_t data_before_chunk = (first == 0) ? 0 : wait_inclusive(L.status, F.tile_begin + first - 1, L.epoch);
+    const uint64_t body = (excl + Q.total) - data_before_chunk;
+    if (L.header_bytes + 4ull * (chunk + 1) + data_before_chunk <= F.out_cap) {
+      store_u32(payload + 4ull * chunk + data_before_chunk, static_cast<uint32_t>(body));  // chunk_writer.cpp:33-40
+    }
+    if (last_of_frame) L.sizes[Q.fi] = L.header_bytes + 4ull * F.n_chunks + excl + Q.total;
+  }
+}
 
 __global__ void __launch_bounds__(kET, 6) encode_xyzi_fast_kernel(const EncLaunch L, const FloatNParams P) {
   extern __shared__ __align__(16) uint8_t dyn_smem[];
   __shared__ EncFastShared sh;
-  __shared__ EncFrame s_F[kEW][2];             // per warp: records of frames beyond the cache (double buffered by tile parity)
+  __shared__ EncFrame s_F[kEW][3];             // per warp: records of frames beyond the cache (ring of 3: next, current, pending)
   __shared__ EncFrame s_cache[kEFrameCache];   // the batch's first frames (all of them for the usual batch sizes)
   __shared__ FloatNParams s_P;
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -210,9 +245,7 @@ __global__ void __launch_bounds__(kET, 6) encode_xyzi_fast_kernel(const EncLaunc
   uint32_t i = blockIdx.x;
   uint32_t fi = 0, t = 0;
   if (i < L.n_tiles_total) tile_coords(L, i, &fi, &t);
-  if (threadIdx.x == 0) {
-    s_P = P;
-  }
+  if (threadIdx.x == 0) s_P = P;
   if (lane == 0 && i < L.n_tiles_total && fi >= kEFrameCache) s_F[warp][0] = L.frames[fi];
   {
     const uint32_t n_cached = min(L.n_frames, static_cast<uint32_t>(kEFrameCache));
@@ -246,32 +279,39 @@ __global__ void __launch_bounds__(kET, 6) encode_xyzi_fast_kernel(const EncLaunc
   }
   async_commit();
 
-  for (uint32_t cur = 0; i < L.n_tiles_total; i += G, cur ^= 1u) {
+  PendingQuarter pend;
+  pend.valid = false;
+  pend.stage = nullptr; pend.wtot = pend.wbase = pend.total = pend.fi = pend.t = pend.par = 0;
+  LookbackPoll lb;   // warp 0: the look-back of the pending tile
+  lb.done = true; lb.idx = 0; lb.exclusive = 0; lb.s = 0;
+  uint32_t pend_tile = 0, pend_first = 0;  // warp 0: status indices of the pending tile
+
+  uint32_t it = 0;
+  for (; i < L.n_tiles_total; i += G, ++it) {
+    const uint32_t cur = it & 1u, ring = it % 3u;
     uint8_t* buf = wsm + cur * kEBufBytes;                 // this quarter's transposed input, then its staged output
     uint8_t* stage = buf;
-    // ---- the next tile of this CTA (and, for large batches, its frame record) goes into the other buffer now ----
+    // ---- which tile comes next (its points are asked into L2 now, into shared memory once the other buffer is free) ----
     const uint32_t nxt = i + G;
-    bool have_next = false;
-    uint32_t nfi = 0, nt = 0;
+    uint32_t nfi = 0, nt = 0, np = 0;
+    const uint8_t* nin = nullptr;
     if (nxt < L.n_tiles_total) {
       tile_coords(L, nxt, &nfi, &nt);
-      uint32_t np;
-      const uint8_t* nin;
       if (nfi < kEFrameCache) {
         np = s_cache[nfi].n_points;
         nin = s_cache[nfi].in;
       } else {  // large batches: the record travels with the tile's points, its two words needed now come straight from L2
         const EncFrame* NF = L.frames + nfi;
-        if (lane < sizeof(EncFrame) / 8) async_copy8(reinterpret_cast<uint8_t*>(&s_F[warp][cur ^ 1u]) + 8 * lane, reinterpret_cast<const uint8_t*>(NF) + 8 * lane);
         np = __ldg(&NF->n_points);
         nin = reinterpret_cast<const uint8_t*>(__ldg(reinterpret_cast<const unsigned long long*>(&NF->in)));
       }
-      have_next = prefetch(nin, np, nt, wsm + (cur ^ 1u) * kEBufBytes);
+      if (static_cast<uint64_t>(nt) * kETilePts + kETilePts <= np) {
+        prefetch_l2_enc(nin + (static_cast<size_t>(nt) * kETilePts + warp * kEQuarterPts) * 16u + lane * 128u);
+      }
     }
-    async_commit();
-    async_wait_all_but_last();   // this tile's copies have landed; the next tile's may be in flight
+    async_wait_all();            // this tile's copies have landed
     __syncwarp();
-    const EncFrame& F = fi < kEFrameCache ? s_cache[fi] : s_F[warp][cur];
+    const EncFrame& F = fi < kEFrameCache ? s_cache[fi] : s_F[warp][ring];
 
     const uint32_t tile = F.tile_begin + t;
     const uint32_t tile_p0 = t * kETilePts;
@@ -358,18 +398,34 @@ __global__ void __launch_bounds__(kET, 6) encode_xyzi_fast_kernel(const EncLaunc
     }
     uint32_t wtot = __shfl_sync(0xffffffffu, inc, 31);
     if (lane == 0) sh.wtot[cur][warp] = wtot;
+    // warp 0: the pending tile's look-back has had this whole pass to resolve; its result travels through the barrier
+    if (warp == 0 && pend.valid) {
+      const uint64_t e = lb.finish(L.status, pend_first, pend_tile, L.epoch, pend.total);
+      if (lane == 0) sh.excl[pend.par] = e;
+    }
     const int any_slow = __syncthreads_or(fast ? 0 : 1);
-    if (any_slow) {
-      // exact path: up to 20 bytes per point, staged across BOTH of the warp's buffers -- the next tile's copies are drained
-      // first and that tile is loaded again, synchronously, when its turn comes
-      async_wait_all();
+    // ---- the pending tile's quarter leaves now: its buffer is the one the next tile's points go into ----
+    if (pend.valid) {
+      const EncFrame& PF = pend.fi < kEFrameCache ? s_cache[pend.fi] : s_F[warp][(it + 2u) % 3u];
+      place_quarter(L, PF, pend, sh.excl[pend.par]);
+      pend.valid = false;
       __syncwarp();
-      have_next = false;
+    }
+    bool have_next = false;
+    if (nxt < L.n_tiles_total && nfi >= kEFrameCache && lane < sizeof(EncFrame) / 8) {  // the next tile's frame record
+      async_copy8(reinterpret_cast<uint8_t*>(&s_F[warp][(it + 1u) % 3u]) + 8 * lane, reinterpret_cast<const uint8_t*>(L.frames + nfi) + 8 * lane);
+    }
+    if (any_slow) {
+      // exact path: up to 20 bytes per point, staged across BOTH of the warp's buffers; the next tile is loaded
+      // synchronously when its turn comes
       stage = wsm;
       wtot = encode_warp_tile_careful(F, s_P, q0, stage);
-      if (lane == 0) sh.wtot[cur][warp] = wtot;   // every warp has read the fast sizes? they are not used on this path
+      if (lane == 0) sh.wtot[cur][warp] = wtot;   // (the fast sizes are not read on this path)
       __syncthreads();
+    } else if (nxt < L.n_tiles_total) {
+      have_next = prefetch(nin, np, nt, wsm + (cur ^ 1u) * kEBufBytes);
     }
+    async_commit();
     uint32_t wbase = 0, total = 0;
 #pragma unroll
     for (int w = 0; w < kEW; ++w) {
@@ -377,10 +433,13 @@ __global__ void __launch_bounds__(kET, 6) encode_xyzi_fast_kernel(const EncLaunc
       if (static_cast<uint32_t>(w) < warp) wbase += c;
       total += c;
     }
-    // the tile's size is final: warp 0 publishes it before the bytes are packed; every warp follows the look-back itself
-    LookbackPoll lb;
-    lb.begin(L.status, F.tile_begin, tile, L.epoch, total, warp == 0);
-    lb.issue(L.status, F.tile_begin, L.epoch);
+    // the tile's size is final: warp 0 publishes it before the bytes are packed and starts the look-back
+    if (warp == 0) {
+      lb.begin(L.status, F.tile_begin, tile, L.epoch, total);
+      lb.issue(L.status, F.tile_begin, L.epoch);
+      pend_tile = tile;
+      pend_first = F.tile_begin;
+    }
     if (!any_slow) {
       const uint32_t off = inc - mine;
       __syncwarp();  // every lane is done with the transposed input the staged bytes are about to overwrite
@@ -416,37 +475,35 @@ __global__ void __launch_bounds__(kET, 6) encode_xyzi_fast_kernel(const EncLaunc
       }
       if (lane == 31u && (bit & 31u) != 0u) *reinterpret_cast<uint32_t*>(stage + wa) = lo;  // nobody follows the quarter's last lane
     }
-    const uint64_t excl = lb.finish(L.status, F.tile_begin, tile, L.epoch, total, warp == 0);
     __syncwarp();  // staged bytes complete
-    // ---- the quarter's place in the frame: copy-out; the tile's last warp back-patches the chunk prefix / frame size ----
-    {
-      constexpr uint32_t tiles_per_chunk = kChunkPoints / kETilePts;
-      const uint32_t chunk = t / tiles_per_chunk;
-      uint8_t* payload = F.out + L.header_bytes;
-      const uint64_t at = 4ull * (chunk + 1) + excl + wbase;
-      if (L.header_bytes + at + wtot <= F.out_cap) warp_copy_stage_to_global(stage, wtot, payload + at);
-      else if (lane == 0) report_error(L.err, DEV_ERR_ENCODE_OUTPUT_SMALL);
-      if (t == 0 && warp == 0 && L.header_bytes <= F.out_cap) {
-        for (uint32_t k = lane; k < L.header_bytes; k += 32u) F.out[k] = L.header[k];
+    pend.valid = true;
+    pend.stage = stage; pend.wtot = wtot; pend.wbase = wbase; pend.total = total; pend.fi = fi; pend.t = t; pend.par = cur;
+    if (any_slow) {
+      // the exact path's bytes lie across both buffers: they leave at once (the next tile needs one of them)
+      if (warp == 0) {
+        const uint64_t e = lb.finish(L.status, pend_first, pend_tile, L.epoch, total);
+        if (lane == 0) sh.excl[cur] = e;
       }
-      const bool last_of_frame = (t + 1 == F.n_tiles);
-      const bool last_of_chunk = last_of_frame || ((t + 1) % tiles_per_chunk == 0);
-      if (last_of_chunk && warp == kEW - 1 && lane == 0) {
-        const uint32_t first = chunk * tiles_per_chunk;
-        const uint64_t data_before_chunk = (first == 0) ? 0 : wait_inclusive(L.status, F.tile_begin + first - 1, L.epoch);
-        const uint64_t body = (excl + total) - data_before_chunk;
-        if (L.header_bytes + 4ull * (chunk + 1) + data_before_chunk <= F.out_cap) {
-          store_u32(payload + 4ull * chunk + data_before_chunk, static_cast<uint32_t>(body));  // chunk_writer.cpp:33-40
-        }
-        if (last_of_frame) L.sizes[fi] = L.header_bytes + 4ull * F.n_chunks + excl + total;
-      }
+      __syncthreads();
+      place_quarter(L, F, pend, sh.excl[cur]);
+      pend.valid = false;
+      __syncwarp();
     }
-    __syncwarp();  // this buffer receives the tile after next
     have_cur = have_next;
     fi = nfi;
     t = nt;
   }
+  // ---- the last tile of this CTA is still pending ----
   async_wait_all();
+  if (warp == 0 && pend.valid) {
+    const uint64_t e = lb.finish(L.status, pend_first, pend_tile, L.epoch, pend.total);
+    if (lane == 0) sh.excl[pend.par] = e;
+  }
+  __syncthreads();
+  if (pend.valid) {
+    const EncFrame& PF = pend.fi < kEFrameCache ? s_cache[pend.fi] : s_F[warp][(it + 2u) % 3u];
+    place_quarter(L, PF, pend, sh.excl[pend.par]);
+  }
 }
 
 static bool encode_fast_enabled() {
