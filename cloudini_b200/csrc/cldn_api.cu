@@ -259,6 +259,7 @@ const char* dev_error_text(uint32_t code) {
     case DEV_ERR_CHUNK_COUNT: return "Encoded data does not match the declared number of points (chunk count)";
     case DEV_ERR_OUTPUT_SMALL: return "Output buffer is too small to hold the decoded data";
     case DEV_ERR_ENCODE_OUTPUT_SMALL: return "Output buffer too small for uncompressed chunk";  // chunk_writer.cpp:33-35
+    case DEV_ERR_LZ4: return "LZ4 decompression failed";  // codec_common.cpp:279-281
     default: return "unknown device error";
   }
 }
@@ -300,7 +301,16 @@ struct cldn_encoder {
   DevBuf<uint64_t> d_hash;
   DevBuf<uint8_t> d_gorilla;  // Gorilla pre-pass records: [frame][op][point][12]
   size_t last_frames = 0;
+  // stage 2 on the device (LZ4): stage-1 arena, per-chunk slots, chunk tables
+  DevBuf<uint8_t> d_s1, d_lz_scratch;
+  DevBuf<uint32_t> d_lz_chunk_frame, d_lz_chunk_sizes;
+  DevBuf<Lz4Frame> d_lz_frames;
+  PinRing<Lz4Frame> h_lz_frames;
+  PinRing<uint32_t> h_lz_chunk_frame;
 };
+
+// LZ4_COMPRESSBOUND (lz4.h): worst case of a block for n input bytes
+static size_t lz4_bound(size_t n) { return n + n / 255 + 16; }
 
 extern "C" {
 
@@ -349,7 +359,8 @@ int cldn_b200_encoder_create(const cldn_info_t* info, int device, void* stream, 
     return CLDN_ERR_UNSUPPORTED;
   }
   if (info->compression_opt > CLDN_COMP_ZSTD) { set_error("Unsupported compression option"); return CLDN_ERR_INVALID_ARGUMENT; }
-  if (info->compression_opt != CLDN_COMP_NONE && !g_stage2.load(info->compression_opt)) return CLDN_ERR_UNSUPPORTED;
+  // ZSTD exists only as the host library; LZ4 also runs on the device, so a missing liblz4 only matters to the host-pointer API
+  if (info->compression_opt == CLDN_COMP_ZSTD && !g_stage2.load(info->compression_opt)) return CLDN_ERR_UNSUPPORTED;
   if (int rc = select_device(device)) return rc;
   cldn_encoder* e = new cldn_encoder();
   e->info = *info;
@@ -391,6 +402,8 @@ void cldn_b200_encoder_destroy(cldn_encoder_t* e) {
   e->d_sizes.release(); e->h_sizes.release(); e->d_err.release(); e->h_err.release(); e->d_in.release(); e->d_out.release();
   e->d_modes.release(); e->d_sec_scratch.release(); e->d_sec_sizes.release(); e->d_sec_excl.release();
   e->d_chunk_frame.release(); e->h_chunk_frame.release(); e->d_hash.release(); e->d_gorilla.release(); e->pipe.release();
+  e->d_s1.release(); e->d_lz_scratch.release(); e->d_lz_chunk_frame.release(); e->d_lz_chunk_sizes.release(); e->d_lz_frames.release();
+  e->h_lz_frames.release(); e->h_lz_chunk_frame.release();
   if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
   delete e;
 }
@@ -605,6 +618,80 @@ static int guarded(Fn&& fn) {
   }
 }
 
+// Device pointers in, device pointers out, compression LZ4: stage 1 into an internal arena, one LZ4 block per chunk on the
+// device (cldn_lz4.cu), blobs packed behind their headers. Nothing crosses PCIe except the 8-byte sizes, if asked for.
+static int encode_batch_device_lz4(cldn_encoder* e, size_t n_frames, const void* const* clouds, const size_t* cloud_bytes,
+                                   void* const* outs, const size_t* out_capacities, int write_header) {
+  const cldn_info_t& info = e->info;  // compression NONE: what the stage-1 kernels produce
+  if (info.point_step == 0) { set_error("point_step cannot be 0"); return CLDN_ERR_INVALID_ARGUMENT; }
+  cldn_info_t full = info;
+  full.compression_opt = CLDN_COMP_LZ4;
+  const size_t hdr = write_header ? e->header.size() : 0;
+  std::vector<size_t> s1_off(n_frames), s1_cap(n_frames);
+  size_t arena = 0, chunks = 0, max_chunk = 0;
+  for (size_t f = 0; f < n_frames; ++f) {
+    if (cloud_bytes[f] % info.point_step != 0) { set_error("Input cloud_data size is not a multiple of point_step"); return CLDN_ERR_INVALID_ARGUMENT; }
+    const size_t n = cloud_bytes[f] / info.point_step;
+    bool ok;
+    const size_t need = max_compressed_size(full, n, false, &ok) + hdr;  // cloudini.cpp:530-534
+    if (!ok) return CLDN_ERR_INVALID_ARGUMENT;
+    if (out_capacities[f] < need) { set_error("Output buffer too small for worst-case compressed size"); return CLDN_ERR_BUFFER_TOO_SMALL; }
+    s1_cap[f] = max_compressed_size(info, n, false, &ok) + 64 * ((n + kChunkPoints - 1) / kChunkPoints + 1);
+    s1_off[f] = arena;
+    arena += (s1_cap[f] + 255) & ~size_t(255);
+    chunks += (n + kChunkPoints - 1) / kChunkPoints;
+    max_chunk = std::max(max_chunk, max_compressed_size(info, std::min<size_t>(n, kChunkPoints), false, &ok) + 64);
+  }
+  if (chunks > 0x7FFFFFFFull) { set_error("batch too large"); return CLDN_ERR_UNSUPPORTED; }
+  if (int rc = e->d_s1.reserve(arena + 256)) return rc;
+  std::vector<const void*> s1_ptr_c(n_frames);
+  std::vector<void*> s1_ptr(n_frames);
+  for (size_t f = 0; f < n_frames; ++f) s1_ptr[f] = e->d_s1.p + s1_off[f];
+  if (int rc = encode_batch_device(e, n_frames, clouds, cloud_bytes, s1_ptr.data(), s1_cap.data(), 0)) return rc;
+  // chunk tables + per-chunk slots
+  const size_t slot = (lz4_bound(max_chunk) + 15) & ~size_t(15);
+  if (slot > 0xFFFFFFF0ull) { set_error("chunk too large for LZ4"); return CLDN_ERR_UNSUPPORTED; }
+  if (int rc = e->d_lz_scratch.reserve(std::max<size_t>(chunks, 1) * slot)) return rc;
+  if (int rc = e->d_lz_chunk_sizes.reserve(chunks + 1)) return rc;
+  if (int rc = e->d_lz_chunk_frame.reserve(chunks + 1)) return rc;
+  if (int rc = e->d_lz_frames.reserve(n_frames)) return rc;
+  Lz4Frame* hf = nullptr; int hf_slot = 0;
+  uint32_t* hcf = nullptr; int hcf_slot = 0;
+  if (int rc = e->h_lz_frames.acquire(n_frames, &hf, &hf_slot)) return rc;
+  if (int rc = e->h_lz_chunk_frame.acquire(chunks + 1, &hcf, &hcf_slot)) return rc;
+  uint32_t cb = 0;
+  for (size_t f = 0; f < n_frames; ++f) {
+    const size_t n = cloud_bytes[f] / info.point_step;
+    Lz4Frame& F = hf[f];
+    memset(&F, 0, sizeof(F));
+    F.plain = e->d_s1.p + s1_off[f];
+    F.plain_bytes = e->d_sizes.p + f;
+    F.blob_out = static_cast<uint8_t*>(outs[f]);
+    F.blob_cap = out_capacities[f];
+    F.n_chunks = static_cast<uint32_t>((n + kChunkPoints - 1) / kChunkPoints);
+    F.chunk_begin = cb;
+    for (uint32_t c = 0; c < F.n_chunks; ++c) hcf[cb + c] = static_cast<uint32_t>(f);
+    cb += F.n_chunks;
+  }
+  CUDA_TRY(cudaMemcpyAsync(e->d_lz_frames.p, hf, n_frames * sizeof(Lz4Frame), cudaMemcpyHostToDevice, e->stream));
+  if (int rc = e->h_lz_frames.commit(hf_slot, e->stream)) return rc;
+  if (chunks) CUDA_TRY(cudaMemcpyAsync(e->d_lz_chunk_frame.p, hcf, chunks * sizeof(uint32_t), cudaMemcpyHostToDevice, e->stream));
+  if (int rc = e->h_lz_chunk_frame.commit(hcf_slot, e->stream)) return rc;
+  Lz4Launch Z;
+  Z.frames = e->d_lz_frames.p;
+  Z.n_frames = static_cast<uint32_t>(n_frames);
+  Z.n_chunks_total = static_cast<uint32_t>(chunks);
+  Z.chunk_frame = e->d_lz_chunk_frame.p;
+  Z.scratch = e->d_lz_scratch.p;
+  Z.slot_stride = static_cast<uint32_t>(slot);
+  Z.chunk_sizes = e->d_lz_chunk_sizes.p;
+  Z.sizes = e->d_sizes.p;   // the pack kernel overwrites the stage-1 sizes with the blob sizes (it runs after every reader)
+  Z.err = e->d_err.p;
+  if (launch_lz4_compress(Z, e->d_header.p, static_cast<uint32_t>(hdr), e->stream) < 0) { set_error("LZ4 kernel launch failed"); return CLDN_ERR_CUDA; }
+  CUDA_TRY(cudaGetLastError());
+  return CLDN_OK;
+}
+
 static int encode_batch_impl(cldn_encoder_t* e, size_t n_frames, const void* const* clouds, const size_t* cloud_bytes,
                              void* const* outs, const size_t* out_capacities, int write_header, size_t* written_host,
                              int mem) {
@@ -614,11 +701,22 @@ static int encode_batch_impl(cldn_encoder_t* e, size_t n_frames, const void* con
   }
   if (n_frames == 0) return CLDN_OK;
   CUDA_TRY(cudaSetDevice(e->device));
+  if (mem == CLDN_MEM_DEVICE && e->stage2 == CLDN_COMP_LZ4) {
+    if (int rc = encode_batch_device_lz4(e, n_frames, clouds, cloud_bytes, outs, out_capacities, write_header)) return rc;
+    if (written_host) {
+      if (int rc = e->h_sizes.reserve(n_frames)) return rc;
+      CUDA_TRY(cudaMemcpyAsync(e->h_sizes.p, e->d_sizes.p, n_frames * sizeof(uint64_t), cudaMemcpyDeviceToHost, e->stream));
+      if (int rc = check_device_error(e->stream, e->d_err.p, e->h_err.p)) return rc;
+      for (size_t f = 0; f < n_frames; ++f) written_host[f] = static_cast<size_t>(e->h_sizes.p[f]);
+    }
+    return CLDN_OK;
+  }
   if (mem == CLDN_MEM_DEVICE && e->stage2 != CLDN_COMP_NONE) {
-    set_error("compression_opt %d needs the host-pointer API: stage 2 (LZ4/ZSTD) is delegated to the host libraries", e->stage2);
+    set_error("compression_opt %d needs the host-pointer API: ZSTD is delegated to the host library (LZ4 runs on the device)", e->stage2);
     return CLDN_ERR_UNSUPPORTED;
   }
   if (mem == CLDN_MEM_HOST && e->stage2 != CLDN_COMP_NONE) {
+    if (!g_stage2.load(e->stage2)) return CLDN_ERR_UNSUPPORTED;
     // stage 1 on the GPU, then every chunk through the system compressor (not pipelined: this is not the product path)
     cldn_info_t full = e->info;
     full.compression_opt = static_cast<uint8_t>(e->stage2);
@@ -760,6 +858,14 @@ struct cldn_decoder {
   DevBuf<uint32_t> d_counter, d_redo;
   DevBuf<uint64_t> d_chunk_desc;  // chunk-sequential kernel: self-validating chunk descriptors (see walk_frame_publish)
   uint32_t desc_tag = 0;
+  // stage 2 on the device (LZ4)
+  DevBuf<uint8_t> d_s1, d_lz_scratch;
+  DevBuf<uint32_t> d_lz_chunk_frame, d_lz_chunk_sizes;
+  DevBuf<Lz4Frame> d_lz_frames;
+  DevBuf<uint64_t> d_lz_sizes;
+  PinBuf<uint64_t> h_lz_sizes;
+  PinRing<Lz4Frame> h_lz_frames;
+  PinRing<uint32_t> h_lz_chunk_frame;
   bool fast_launched = false;  // the last batch went through decode_floatn_fast_kernel (cldn_b200_decoder_last_stats)
   uint32_t fast_chunks = 0;
   CopyPipeline pipe;
@@ -787,7 +893,7 @@ static int decoder_update_plan(cldn_decoder* d, const cldn_info_t& info) {
     return CLDN_ERR_UNSUPPORTED;
   }
   if (info.compression_opt != CLDN_COMP_NONE) {
-    set_error("compression_opt %d: stage 2 (LZ4/ZSTD) is delegated; decompress the chunks first", static_cast<int>(info.compression_opt));
+    set_error("compression_opt %d: stage 2 is undone before the stage-1 decode (LZ4 on the device, ZSTD by the host library)", static_cast<int>(info.compression_opt));
     return CLDN_ERR_UNSUPPORTED;
   }
   if (info.version < 3) { set_error("wire version %d (single unframed chunk) is not supported", info.version); return CLDN_ERR_UNSUPPORTED; }
@@ -961,6 +1067,8 @@ void cldn_b200_decoder_destroy(cldn_decoder_t* d) {
   d->d_plan.release(); d->d_frames.release(); d->h_frames.release(); d->d_chunk_offsets.release(); d->d_chunk_sizes.release();
   d->d_err.release(); d->h_err.release(); d->d_in.release(); d->d_out.release();
   d->d_chunk_tiles.release(); d->d_chunk_tile_begin.release(); d->d_stream_end.release(); d->d_tsums.release(); d->d_tstatus.release(); d->d_chunk_frame.release(); d->d_tile_chunk.release(); d->d_trace.release(); d->d_counter.release(); d->d_redo.release(); d->d_chunk_desc.release(); d->pipe.release();
+  d->d_s1.release(); d->d_lz_scratch.release(); d->d_lz_chunk_frame.release(); d->d_lz_chunk_sizes.release(); d->d_lz_frames.release();
+  d->d_lz_sizes.release(); d->h_lz_sizes.release(); d->h_lz_frames.release(); d->h_lz_chunk_frame.release();
   if (d->own_stream && d->stream) cudaStreamDestroy(d->stream);
   delete d;
 }
@@ -994,6 +1102,74 @@ int cldn_b200_decoder_last_stats(cldn_decoder_t* d, uint32_t stats[2]) {
 
 }  // extern "C"
 
+static int decode_batch_device(cldn_decoder* d, const cldn_info_t& info, size_t n_frames, const void* const* payloads,
+                               const size_t* payload_bytes, void* const* outs, const size_t* out_capacities);
+
+// Device pointers, compression LZ4: every chunk's block is decompressed on the device into a slot, the slots are re-framed
+// into a stage-1 payload per frame (internal arena) and the ordinary stage-1 decode runs on that. One read-back of the
+// frames' stage-1 sizes (8 bytes each) sits between the two.
+static int decode_batch_device_lz4(cldn_decoder* d, const cldn_info_t& info, size_t n_frames, const void* const* payloads,
+                                   const size_t* payload_bytes, void* const* outs, const size_t* out_capacities) {
+  cldn_info_t plain = info;
+  plain.compression_opt = CLDN_COMP_NONE;
+  const uint64_t n_points = static_cast<uint64_t>(info.width) * info.height;
+  if (n_points > 0xFFFFFFFFull) { set_error("too many points"); return CLDN_ERR_UNSUPPORTED; }
+  for (size_t f = 0; f < n_frames; ++f) {
+    if (out_capacities[f] < n_points * info.point_step) { set_error("Output buffer is too small to hold the decoded data"); return CLDN_ERR_BUFFER_TOO_SMALL; }
+  }
+  bool ok;
+  const size_t chunks_per_frame = static_cast<size_t>((n_points + kChunkPoints - 1) / kChunkPoints);
+  const size_t max_chunk = max_compressed_size(plain, std::min<size_t>(n_points, kChunkPoints), false, &ok) + 64;
+  if (!ok) return CLDN_ERR_INVALID_ARGUMENT;
+  const size_t slot = (max_chunk + 15) & ~size_t(15);
+  const size_t s1_cap = ((chunks_per_frame * (slot + 4) + 255) & ~size_t(255));
+  const size_t chunks = chunks_per_frame * n_frames;
+  if (chunks > 0x7FFFFFFFull || slot > 0xFFFFFFF0ull) { set_error("batch too large"); return CLDN_ERR_UNSUPPORTED; }
+  if (int rc = d->d_s1.reserve(std::max<size_t>(s1_cap * n_frames, 256))) return rc;
+  if (int rc = d->d_lz_scratch.reserve(std::max<size_t>(chunks, 1) * slot)) return rc;
+  if (int rc = d->d_lz_chunk_sizes.reserve(chunks + 1)) return rc;
+  if (int rc = d->d_lz_chunk_frame.reserve(chunks + 1)) return rc;
+  if (int rc = d->d_lz_frames.reserve(n_frames)) return rc;
+  if (int rc = d->d_lz_sizes.reserve(n_frames)) return rc;
+  if (int rc = d->h_lz_sizes.reserve(n_frames)) return rc;
+  Lz4Frame* hf = nullptr; int hf_slot = 0;
+  uint32_t* hcf = nullptr; int hcf_slot = 0;
+  if (int rc = d->h_lz_frames.acquire(n_frames, &hf, &hf_slot)) return rc;
+  if (int rc = d->h_lz_chunk_frame.acquire(chunks + 1, &hcf, &hcf_slot)) return rc;
+  for (size_t f = 0; f < n_frames; ++f) {
+    Lz4Frame& F = hf[f];
+    memset(&F, 0, sizeof(F));
+    F.packed_in = static_cast<const uint8_t*>(payloads[f]);
+    F.packed_in_bytes = payload_bytes[f];
+    F.plain_out = d->d_s1.p + f * s1_cap;
+    F.plain_cap = s1_cap;
+    F.n_chunks = static_cast<uint32_t>(chunks_per_frame);
+    F.chunk_begin = static_cast<uint32_t>(f * chunks_per_frame);
+    for (size_t c = 0; c < chunks_per_frame; ++c) hcf[f * chunks_per_frame + c] = static_cast<uint32_t>(f);
+  }
+  CUDA_TRY(cudaMemcpyAsync(d->d_lz_frames.p, hf, n_frames * sizeof(Lz4Frame), cudaMemcpyHostToDevice, d->stream));
+  if (int rc = d->h_lz_frames.commit(hf_slot, d->stream)) return rc;
+  if (chunks) CUDA_TRY(cudaMemcpyAsync(d->d_lz_chunk_frame.p, hcf, chunks * sizeof(uint32_t), cudaMemcpyHostToDevice, d->stream));
+  if (int rc = d->h_lz_chunk_frame.commit(hcf_slot, d->stream)) return rc;
+  Lz4Launch Z;
+  Z.frames = d->d_lz_frames.p;
+  Z.n_frames = static_cast<uint32_t>(n_frames);
+  Z.n_chunks_total = static_cast<uint32_t>(chunks);
+  Z.chunk_frame = d->d_lz_chunk_frame.p;
+  Z.scratch = d->d_lz_scratch.p;
+  Z.slot_stride = static_cast<uint32_t>(slot);
+  Z.chunk_sizes = d->d_lz_chunk_sizes.p;
+  Z.sizes = d->d_lz_sizes.p;
+  Z.err = d->d_err.p;
+  if (launch_lz4_decompress(Z, d->stream) < 0) { set_error("LZ4 kernel launch failed"); return CLDN_ERR_CUDA; }
+  CUDA_TRY(cudaMemcpyAsync(d->h_lz_sizes.p, d->d_lz_sizes.p, n_frames * sizeof(uint64_t), cudaMemcpyDeviceToHost, d->stream));
+  if (int rc = check_device_error(d->stream, d->d_err.p, d->h_err.p)) return rc;  // synchronises; damaged blocks stop here
+  std::vector<const void*> p1(n_frames);
+  std::vector<size_t> b1(n_frames);
+  for (size_t f = 0; f < n_frames; ++f) { p1[f] = d->d_s1.p + f * s1_cap; b1[f] = static_cast<size_t>(d->h_lz_sizes.p[f]); }
+  return decode_batch_device(d, plain, n_frames, p1.data(), b1.data(), outs, out_capacities);
+}
+
 static int decode_batch_impl(cldn_decoder_t* d, const cldn_info_t* info, size_t n_frames, const void* const* payloads,
                              const size_t* payload_bytes, void* const* outs, const size_t* out_capacities, int mem, int sync) {
   if (!d || !info || (n_frames && (!payloads || !payload_bytes || !outs || !out_capacities))) {
@@ -1003,7 +1179,11 @@ static int decode_batch_impl(cldn_decoder_t* d, const cldn_info_t* info, size_t 
   if (n_frames == 0) return CLDN_OK;
   CUDA_TRY(cudaSetDevice(d->device));
   if (mem == CLDN_MEM_DEVICE) {
-    if (int rc = decode_batch_device(d, *info, n_frames, payloads, payload_bytes, outs, out_capacities)) return rc;
+    if (info->compression_opt == CLDN_COMP_LZ4) {
+      if (int rc = decode_batch_device_lz4(d, *info, n_frames, payloads, payload_bytes, outs, out_capacities)) return rc;
+    } else if (int rc = decode_batch_device(d, *info, n_frames, payloads, payload_bytes, outs, out_capacities)) {
+      return rc;
+    }
     if (sync) return check_device_error(d->stream, d->d_err.p, d->h_err.p);
     return CLDN_OK;
   }

@@ -23,6 +23,7 @@ enum DevError : uint32_t {
   DEV_ERR_CHUNK_SIZE = 8,      // "Invalid chunk size found while decoding" cloudini.cpp:653-655
   DEV_ERR_CHUNK_COUNT = 9,     // cloudini.cpp:648-650,662-664
   DEV_ERR_OUTPUT_SMALL = 10,
+  DEV_ERR_LZ4 = 12,                  // "LZ4 decompression failed" codec_common.cpp:279-281
   DEV_ERR_ENCODE_OUTPUT_SMALL = 11,  // "Output buffer too small for uncompressed chunk" chunk_writer.cpp:33-35
 };
 

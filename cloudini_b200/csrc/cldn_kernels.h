@@ -120,6 +120,36 @@ size_t palette_overflow_scratch_bytes();
 int launch_place_sections(const Plan& host_plan, const SecLaunch& L, const uint64_t* status, uint32_t epoch,
                           uint32_t tile_points, cudaStream_t stream);
 
+// ---- stage 2 on the device (LZ4 blocks per chunk; cldn_lz4.cu) ----------------------------------------------------------
+struct Lz4Frame {
+  // compress: stage-1 payload of the frame ([u32 size][bytes])*, its byte count (device word written by the stage-1
+  // kernels), and where the finished blob goes
+  const uint8_t* plain;
+  const uint64_t* plain_bytes;
+  uint8_t* blob_out;
+  uint64_t blob_cap;
+  // decompress: the blob's payload ([u32 csize][LZ4 block])* and where the re-framed stage-1 payload goes
+  const uint8_t* packed_in;
+  uint64_t packed_in_bytes;
+  uint8_t* plain_out;
+  uint64_t plain_cap;
+  uint32_t n_chunks;
+  uint32_t chunk_begin;  // global index of the frame's first chunk
+};
+struct Lz4Launch {
+  const Lz4Frame* frames;      // device
+  uint32_t n_frames;
+  uint32_t n_chunks_total;
+  const uint32_t* chunk_frame; // per global chunk: frame index
+  uint8_t* scratch;            // n_chunks_total slots of slot_stride bytes
+  uint32_t slot_stride;
+  uint32_t* chunk_sizes;       // per global chunk: bytes in its slot
+  uint64_t* sizes;             // per frame: bytes written by the pack kernel (0: did not fit)
+  uint32_t* err;
+};
+int launch_lz4_compress(const Lz4Launch& L, const uint8_t* header, uint32_t header_bytes, cudaStream_t stream);
+int launch_lz4_decompress(const Lz4Launch& L, cudaStream_t stream);
+
 uint64_t kernel_launch_count();
 void count_launch(int n = 1);
 

@@ -1,0 +1,264 @@
+// Stage 2 on the device, LZ4 only (SURVEY §8(f) N1 / BASELINE configs[3]): every chunk's stage-1 bytes are compressed
+// into an LZ4 *block* (the format LZ4_compress_default / LZ4_decompress_safe speak, which is what the reference calls per
+// chunk: cloudini_lib/src/codec_common.cpp:220-299, chunk_writer.cpp:42-47) without leaving HBM.
+//
+// north_star delegates stage 2 to nvCOMP; this image has no nvCOMP (probed on the GPU box: gpurun_out/r2_start/probe.txt),
+// so the block coder is written here. It is not byte-identical to liblz4's output -- no two LZ4 compressors are -- but
+// every block it writes is a valid LZ4 block: the stock reference decodes the blobs (tests/test_gpu_stage2_device.py),
+// and the decompressor below accepts whatever liblz4 wrote.
+//
+//  compress    one warp per chunk. 32 consecutive positions per step: every lane hashes the 4 bytes at its position, reads
+//              the candidate the table holds and verifies it by content; the first verified lane (ballot) becomes the match,
+//              which the warp extends 32 bytes per ballot; literals and the sequence header leave cooperatively. Greedy,
+//              4096-entry table of 16-bit positions in shared memory (candidates are rebuilt modulo 64 KB and always
+//              checked by content, so stale or uninitialised entries are harmless).
+//  decompress  one warp per chunk: the (cheap, serial) sequence headers are parsed by all lanes in lock step, literal and
+//              match bytes move cooperatively (overlapping matches with offset < 32 by the closed form k mod offset).
+//  pack        one CTA per frame: exclusive scan of the chunk sizes, then [u32 size][bytes] back to back behind the header.
+#include <stdio.h>
+
+#include "cldn_device.cuh"
+#include "cldn_kernels.h"
+
+namespace cldn {
+
+constexpr int kLzThreads = 128;          // 4 warps = 4 chunks per CTA
+constexpr int kLzWarps = kLzThreads / 32;
+constexpr uint32_t kLzHashBits = 12;
+
+__device__ __forceinline__ uint32_t lz_load32(const uint8_t* p) {  // any alignment
+  const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~uintptr_t(3));
+  const uint32_t sh = static_cast<uint32_t>(a & 3u) * 8u;
+  if (sh == 0) return w[0];
+  return __funnelshift_r(w[0], w[1], sh);
+}
+__device__ __forceinline__ uint32_t lz_hash(uint32_t v) { return (v * 2654435761u) >> (32u - kLzHashBits); }
+
+// Length field of a sequence: nibble value 15 is followed by bytes of 255 and a last byte < 255 (uniform over the warp).
+__device__ __forceinline__ uint32_t lz_ext_bytes(uint32_t len) { return len >= 15u ? (len - 15u) / 255u + 1u : 0u; }
+__device__ __forceinline__ void lz_write_ext(uint8_t* dst, uint32_t len, uint32_t lane) {  // len >= 15
+  const uint32_t rest = len - 15u, full = rest / 255u;
+  for (uint32_t k = lane; k < full; k += 32u) dst[k] = 255u;
+  if (lane == 0) dst[full] = static_cast<uint8_t>(rest - full * 255u);
+}
+
+// One full warp. Returns the compressed size, 0 if `cap` is too small.
+__device__ uint32_t lz4_compress_warp(const uint8_t* __restrict__ src, uint32_t n, uint8_t* __restrict__ dst, uint32_t cap,
+                                      uint16_t* table) {
+  const uint32_t lane = threadIdx.x & 31u;
+  uint32_t ip = 0, anchor = 0, op = 0;
+  // LZ4 block rules: the last match starts at least 12 bytes before the end, the last 5 bytes are literals
+  const uint32_t mflimit = n > 12u ? n - 12u : 0u;
+  const uint32_t matchlimit = n > 5u ? n - 5u : 0u;
+  // the aligned word pairs lz_load32 reads must stay inside [src & ~3, src + n + 3]: positions < mflimit read <= n - 9
+  while (ip < mflimit) {
+    const uint32_t p = ip + lane;
+    const bool ok = p < mflimit;
+    const uint32_t v = ok ? lz_load32(src + p) : 0u;
+    const uint32_t h = lz_hash(v);
+    const uint32_t stored = table[h];
+    __syncwarp();
+    if (ok) table[h] = static_cast<uint16_t>(p);
+    __syncwarp();
+    const uint32_t d = (p - stored) & 0xFFFFu;
+    const uint32_t cand = p - d;
+    const bool valid = ok && d != 0u && d <= p && lz_load32(src + cand) == v;
+    const uint32_t mask = __ballot_sync(0xffffffffu, valid);
+    if (mask == 0u) { ip += 32u; continue; }
+    const int first = __ffs(static_cast<int>(mask)) - 1;
+    const uint32_t mp = ip + static_cast<uint32_t>(first);
+    const uint32_t ref = __shfl_sync(0xffffffffu, cand, first);
+    uint32_t len = 4u;
+    while (true) {  // 32 more bytes per round
+      const uint32_t q = mp + len + lane;
+      const bool eq = q < matchlimit && src[q] == src[ref + len + lane];
+      const uint32_t ne = __ballot_sync(0xffffffffu, !eq);
+      if (ne) { len += static_cast<uint32_t>(__ffs(static_cast<int>(ne)) - 1); break; }
+      len += 32u;
+    }
+    const uint32_t lit = mp - anchor, ml = len - 4u;
+    const uint32_t need = 1u + lz_ext_bytes(lit) + lit + 2u + lz_ext_bytes(ml);
+    if (op + need + 16u > cap) return 0u;  // (+ room for the final literals' header)
+    if (lane == 0) dst[op] = static_cast<uint8_t>((lit >= 15u ? 15u : lit) << 4 | (ml >= 15u ? 15u : ml));
+    op += 1u;
+    if (lit >= 15u) { lz_write_ext(dst + op, lit, lane); op += lz_ext_bytes(lit); }
+    for (uint32_t k = lane; k < lit; k += 32u) dst[op + k] = src[anchor + k];
+    op += lit;
+    if (lane == 0) { dst[op] = static_cast<uint8_t>(mp - ref); dst[op + 1] = static_cast<uint8_t>((mp - ref) >> 8); }
+    op += 2u;
+    if (ml >= 15u) { lz_write_ext(dst + op, ml, lane); op += lz_ext_bytes(ml); }
+    ip = mp + len;
+    anchor = ip;
+  }
+  const uint32_t lit = n - anchor;
+  if (op + 1u + lz_ext_bytes(lit) + lit > cap) return 0u;
+  if (lane == 0) dst[op] = static_cast<uint8_t>((lit >= 15u ? 15u : lit) << 4);
+  op += 1u;
+  if (lit >= 15u) { lz_write_ext(dst + op, lit, lane); op += lz_ext_bytes(lit); }
+  for (uint32_t k = lane; k < lit; k += 32u) dst[op + k] = src[anchor + k];
+  op += lit;
+  __syncwarp();
+  return op;
+}
+
+// One full warp. Returns the decompressed size, 0xFFFFFFFF for a malformed block / a block that does not fit `cap`.
+__device__ uint32_t lz4_decompress_warp(const uint8_t* __restrict__ src, uint32_t n, uint8_t* dst, uint32_t cap) {
+  const uint32_t lane = threadIdx.x & 31u;
+  uint32_t ip = 0, op = 0;
+  if (n == 0) return 0xFFFFFFFFu;
+  while (true) {
+    if (ip >= n) return 0xFFFFFFFFu;
+    const uint32_t token = src[ip++];
+    uint32_t lit = token >> 4;
+    if (lit == 15u) {
+      uint32_t b;
+      do {
+        if (ip >= n) return 0xFFFFFFFFu;
+        b = src[ip++];
+        lit += b;
+      } while (b == 255u);
+    }
+    if (lit > n - ip || lit > cap - op) return 0xFFFFFFFFu;
+    for (uint32_t k = lane; k < lit; k += 32u) dst[op + k] = src[ip + k];
+    ip += lit;
+    op += lit;
+    if (ip >= n) break;  // a block ends with literals
+    if (n - ip < 2u) return 0xFFFFFFFFu;
+    const uint32_t offset = static_cast<uint32_t>(src[ip]) | (static_cast<uint32_t>(src[ip + 1]) << 8);
+    ip += 2u;
+    if (offset == 0u || offset > op) return 0xFFFFFFFFu;
+    uint32_t ml = token & 15u;
+    if (ml == 15u) {
+      uint32_t b;
+      do {
+        if (ip >= n) return 0xFFFFFFFFu;
+        b = src[ip++];
+        ml += b;
+      } while (b == 255u);
+    }
+    ml += 4u;
+    if (ml > cap - op) return 0xFFFFFFFFu;
+    __syncwarp();  // the literals just written may be the match's source
+    if (offset >= 32u) {
+      for (uint32_t base = 0; base < ml; base += 32u) {
+        const uint32_t k = base + lane;
+        if (k < ml) dst[op + k] = dst[op + k - offset];
+        __syncwarp();  // a later round may read what this one wrote
+      }
+    } else {
+      const uint8_t* pat = dst + op - offset;  // the match repeats these `offset` bytes
+      for (uint32_t k = lane; k < ml; k += 32u) dst[op + k] = pat[k % offset];
+      __syncwarp();
+    }
+    op += ml;
+  }
+  __syncwarp();
+  return op;
+}
+
+// Position of chunk `c` inside a framed payload ([u32 size][bytes])*: *body = offset of its bytes, returns its size;
+// 0xFFFFFFFF if the chain leaves the payload. (<= a few dozen hops: every frame has ceil(points / 32768) chunks.)
+__device__ __forceinline__ uint32_t lz_find_chunk(const uint8_t* payload, uint64_t bytes, uint32_t c, uint64_t* body) {
+  uint64_t pos = 0;
+  for (uint32_t k = 0;; ++k) {
+    if (bytes - pos < 4u || pos > bytes) return 0xFFFFFFFFu;
+    const uint32_t sz = load_u32(payload + pos);
+    if (sz > bytes - pos - 4u) return 0xFFFFFFFFu;
+    if (k == c) { *body = pos + 4u; return sz; }
+    pos += 4ull + sz;
+  }
+}
+
+// grid: ceil(n_chunks_total / 4) CTAs of 4 warps; warp -> (frame, chunk) through chunk_frame[]
+__global__ void __launch_bounds__(kLzThreads) lz4_compress_chunks_kernel(const Lz4Launch L) {
+  __shared__ uint16_t s_table[kLzWarps][1u << kLzHashBits];
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+  const uint32_t gc = blockIdx.x * kLzWarps + warp;
+  if (gc >= L.n_chunks_total) return;
+  const uint32_t f = L.chunk_frame[gc];
+  const Lz4Frame F = L.frames[f];
+  const uint32_t c = gc - F.chunk_begin;
+  uint64_t body = 0;
+  const uint32_t n = lz_find_chunk(F.plain, *F.plain_bytes, c, &body);
+  uint32_t csize = 0;
+  if (n != 0xFFFFFFFFu) csize = lz4_compress_warp(F.plain + body, n, L.scratch + static_cast<size_t>(gc) * L.slot_stride, L.slot_stride, s_table[warp]);
+  if (lane == 0) {
+    L.chunk_sizes[gc] = csize;
+    if (csize == 0u) report_error(L.err, DEV_ERR_LZ4);  // cannot happen with slots of LZ4_COMPRESSBOUND size
+  }
+}
+
+__global__ void __launch_bounds__(kLzThreads) lz4_decompress_chunks_kernel(const Lz4Launch L) {
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+  const uint32_t gc = blockIdx.x * kLzWarps + warp;
+  if (gc >= L.n_chunks_total) return;
+  const uint32_t f = L.chunk_frame[gc];
+  const Lz4Frame F = L.frames[f];
+  const uint32_t c = gc - F.chunk_begin;
+  uint64_t body = 0;
+  const uint32_t n = lz_find_chunk(F.packed_in, F.packed_in_bytes, c, &body);
+  uint32_t dsize = 0xFFFFFFFFu;
+  if (n != 0xFFFFFFFFu) dsize = lz4_decompress_warp(F.packed_in + body, n, L.scratch + static_cast<size_t>(gc) * L.slot_stride, L.slot_stride);
+  if (lane == 0) {
+    L.chunk_sizes[gc] = dsize == 0xFFFFFFFFu ? 0u : dsize;
+    if (n == 0xFFFFFFFFu) report_error(L.err, DEV_ERR_CHUNK_SIZE);  // "Invalid chunk size found while decoding"
+    else if (dsize == 0xFFFFFFFFu) report_error(L.err, DEV_ERR_LZ4);  // "LZ4 decompression failed"
+  }
+}
+
+// One CTA per frame: ([u32 size][bytes])* of the frame's chunks, back to back at `dst` (behind `header_bytes` bytes of
+// header, which are copied too); the frame's total goes to sizes[f]. Stores are checked against dst_cap.
+__global__ void __launch_bounds__(256) lz4_pack_frames_kernel(const Lz4Launch L, const uint8_t* header, uint32_t header_bytes, int to_blob) {
+  const uint32_t f = blockIdx.x;
+  const Lz4Frame F = L.frames[f];
+  uint8_t* dst = to_blob ? F.blob_out : F.plain_out;
+  const uint64_t cap = to_blob ? F.blob_cap : F.plain_cap;
+  __shared__ unsigned long long s_pos;
+  uint64_t pos = header_bytes;
+  if (header_bytes <= cap) {
+    for (uint32_t k = threadIdx.x; k < header_bytes; k += blockDim.x) dst[k] = header[k];
+  }
+  bool fits = header_bytes <= cap;
+  for (uint32_t c = 0; c < F.n_chunks; ++c) {
+    const uint32_t gc = F.chunk_begin + c;
+    const uint32_t sz = L.chunk_sizes[gc];
+    const uint8_t* src = L.scratch + static_cast<size_t>(gc) * L.slot_stride;
+    if (pos + 4ull + sz > cap) { fits = false; break; }
+    if (threadIdx.x == 0) store_u32(dst + pos, sz);
+    for (uint32_t k = threadIdx.x; k < sz; k += blockDim.x) dst[pos + 4u + k] = src[k];
+    pos += 4ull + sz;
+  }
+  if (threadIdx.x == 0) {
+    s_pos = pos;
+    L.sizes[f] = fits ? pos : 0ull;
+    if (!fits) report_error(L.err, to_blob ? DEV_ERR_ENCODE_OUTPUT_SMALL : DEV_ERR_LZ4);
+  }
+  (void)s_pos;
+}
+
+int launch_lz4_compress(const Lz4Launch& L, const uint8_t* header, uint32_t header_bytes, cudaStream_t stream) {
+  if (L.n_frames == 0) return 0;
+  int n = 0;
+  if (L.n_chunks_total) {
+    lz4_compress_chunks_kernel<<<(L.n_chunks_total + kLzWarps - 1) / kLzWarps, kLzThreads, 0, stream>>>(L);
+    ++n;
+  }
+  lz4_pack_frames_kernel<<<L.n_frames, 256, 0, stream>>>(L, header, header_bytes, 1);
+  count_launch(n + 1);
+  return n + 1;
+}
+
+int launch_lz4_decompress(const Lz4Launch& L, cudaStream_t stream) {
+  if (L.n_frames == 0) return 0;
+  int n = 0;
+  if (L.n_chunks_total) {
+    lz4_decompress_chunks_kernel<<<(L.n_chunks_total + kLzWarps - 1) / kLzWarps, kLzThreads, 0, stream>>>(L);
+    ++n;
+  }
+  lz4_pack_frames_kernel<<<L.n_frames, 256, 0, stream>>>(L, nullptr, 0, 0);
+  count_launch(n + 1);
+  return n + 1;
+}
+
+}  // namespace cldn
