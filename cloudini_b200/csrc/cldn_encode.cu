@@ -617,11 +617,16 @@ __global__ void empty_frames_kernel(const EncLaunch L) { handle_empty_frames(L);
 
 }  // namespace cldn
 #include "cldn_encode_fast.cuh"
+#include "cldn_encode_points.cuh"
 namespace cldn {
 
 // Points per tile for a plan: the largest I in {8,4,2,1} whose staging buffer fits comfortably.
 uint32_t choose_tile_points(const Plan& plan) {
   if (encode_fast_applies(plan)) return encode_fast_tile_points();
+  {
+    PointsParams pp;
+    if (encode_points_applies(plan, &pp)) return encode_points_tile(plan);
+  }
   if (plan.floatn_only) return floatn_variant() == 2 ? kThreads * 4 : kThreads * 8;
   const size_t budget = 96 * 1024;
   for (int I = 8; I >= 1; I >>= 1) {
@@ -646,6 +651,12 @@ int launch_encode_regular(const Plan& plan, const EncLaunch& L, cudaStream_t str
   }
   if (!(force && force[0] == '1') && encode_fast_applies(plan) && L.tile_points == encode_fast_tile_points()) {
     return launch_encode_fast(plan, L, stream);
+  }
+  {
+    PointsParams pp;
+    if (!(force && force[0] == '1') && !encode_fast_applies(plan) && encode_points_applies(plan, &pp) && L.tile_points == encode_points_tile(plan)) {
+      return launch_encode_points(plan, L, pp, stream);
+    }
   }
   if (plan.floatn_only && muls_ok && !(force && force[0] == '1')) {
     const RegOp& op = plan.ops[0];
