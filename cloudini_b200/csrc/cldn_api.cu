@@ -974,6 +974,29 @@ static int decode_batch_device(cldn_decoder* d, const cldn_info_t& info, size_t 
     L.stream_end = d->d_stream_end.p;
   }
   const char* force_chunk = getenv("CLDN_B200_FORCE_CHUNK_DECODE");
+  const bool fast_general = !d->plan.floatn_only && chunks > 0 && decode_fast_general_plan(d->plan) &&
+                            decode_tiles_sequential(static_cast<uint32_t>(chunks)) && decode_fast_enabled() && !(force_chunk && force_chunk[0] == '1');
+  if (fast_general) {
+    // float-varint streams with scalar lossy fields (Velodyne XYZIRT ...): fast chunk-sequential reader + redo list
+    if (int rc = d->d_stream_end.reserve(static_cast<size_t>(chunks) + 1)) return rc;
+    if (int rc = d->d_counter.reserve(4, true)) return rc;
+    if (int rc = d->d_redo.reserve(static_cast<size_t>(chunks) + 1)) return rc;
+    const size_t had = d->d_chunk_desc.cap;
+    if (int rc = d->d_chunk_desc.reserve(2 * static_cast<size_t>(chunks) + 2)) return rc;
+    d->desc_tag = (d->desc_tag + 1) & 0xFFFFFFu;
+    if (d->d_chunk_desc.cap != had || d->desc_tag == 0) {
+      CUDA_TRY(cudaMemsetAsync(d->d_chunk_desc.p, 0, d->d_chunk_desc.cap * sizeof(uint64_t), d->stream));
+      if (d->desc_tag == 0) d->desc_tag = 1;
+    }
+    L.stream_end = d->d_stream_end.p;
+    L.chunk_counter = d->d_counter.p;
+    L.redo_list = d->d_redo.p;
+    L.chunk_desc = d->d_chunk_desc.p;
+    L.desc_tag = d->desc_tag;
+    bool uniform = n_frames > 0 && hf[0].n_chunks > 0;
+    for (size_t f = 1; f < n_frames; ++f) uniform = uniform && hf[f].n_chunks == hf[0].n_chunks;
+    L.uniform_chunks = uniform ? hf[0].n_chunks : 0u;
+  }
   if (d->plan.floatn_only && chunks > 0 && !(force_chunk && force_chunk[0] == '1')) {
     // tile-parallel path: host upper bound on the tile count (every chunk adds at most 2 tiles of rounding/misalignment)
     uint64_t tiles = 0;
@@ -1029,6 +1052,7 @@ static int decode_batch_device(cldn_decoder* d, const cldn_info_t& info, size_t 
     }
   }
   d->fast_launched = L.redo_list != nullptr && decode_tiles_sequential(L.n_chunks_total) && decode_fast_enabled() && !d->plan.regular_overlap;
+  (void)fast_general;
   d->fast_chunks = d->fast_launched ? L.n_chunks_total : 0u;
   if (launch_decode(d->plan, L, d->stream) < 0) { set_error("decode kernel launch failed"); return CLDN_ERR_CUDA; }
   CUDA_TRY(cudaGetLastError());

@@ -771,7 +771,11 @@ __global__ void __launch_bounds__(kThreads) decode_chunks_kernel(const DecLaunch
   uint32_t* nanbits = reinterpret_cast<uint32_t*>(vals_raw + kValBytes);
   RunBatch& rb = *reinterpret_cast<RunBatch*>(reinterpret_cast<uint8_t*>(nanbits) + kDecTileBytes / 8);
 
-  const uint32_t gc = blockIdx.x;
+  uint32_t gc = blockIdx.x;
+  if (L.redo_mode) {  // only the chunks the fast reader handed over (NaN markers, 5+ byte varints, wide scalars, damage)
+    if (gc >= L.chunk_counter[3]) return;
+    gc = L.redo_list[gc];
+  }
   if (threadIdx.x == 0) {
     uint32_t lo = 0, hi = L.n_frames - 1;
     while (lo < hi) {
@@ -1669,8 +1673,12 @@ int launch_decode(const Plan& plan, const DecLaunch& L, cudaStream_t stream) {
   int launches = 0;
   if (L.n_chunks_total == 0 && L.n_frames == 0) return 0;
   // the chunk-sequential FloatN kernel walks the chunk prefixes itself (CTA 0) while the other CTAs already decode
-  const bool fused_walk = L.n_chunks_total > 0 && L.tile_grid > 0 && L.chunk_desc != nullptr && decode_tiles_sequential(L.n_chunks_total) &&
-                          !plan.regular_overlap;
+  // float-varint streams beyond the FloatN-only ones (a FloatN group + scalar lossy floats: Velodyne XYZIRT ...): the fast
+  // chunk-sequential reader for large batches, the generic per-chunk kernel for whatever it hands over
+  const bool fast_general = L.n_chunks_total > 0 && !plan.floatn_only && L.redo_list != nullptr && L.chunk_desc != nullptr &&
+                            decode_fast_general_plan(plan) && decode_tiles_sequential(L.n_chunks_total) && decode_fast_enabled();
+  const bool fused_walk = fast_general || (L.n_chunks_total > 0 && L.tile_grid > 0 && L.chunk_desc != nullptr &&
+                                           decode_tiles_sequential(L.n_chunks_total) && !plan.regular_overlap);
   if (!fused_walk) {
     walk_chunks_kernel<<<(L.n_frames + 127) / 128, 128, 0, stream>>>(L);
     ++launches;
@@ -1680,6 +1688,31 @@ int launch_decode(const Plan& plan, const DecLaunch& L, cudaStream_t stream) {
     // the one-thread-per-chunk parser; sections follow in field order like everywhere else
     decode_sequential_kernel<<<(L.n_chunks_total + 31) / 32, 32, 0, stream>>>(L);
     ++launches;
+    if (plan.n_sections > 0) {
+      DecLaunch S = L;
+      S.sections_only = 1;
+      const size_t smem = dec_smem_bytes(false);
+      auto k = decode_chunks_kernel<0>;
+      if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess) return -1;
+      k<<<L.n_chunks_total, kThreads, smem, stream>>>(S);
+      ++launches;
+    }
+  } else if (fast_general) {
+    int sms = 0, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaMemsetAsync(L.chunk_counter, 0, 4 * sizeof(uint32_t), stream);
+    if (launch_decode_fast(plan, L, sms > 0 ? sms : 148, stream) < 0) return -1;
+    ++launches;
+    {
+      DecLaunch R = L;
+      R.redo_mode = 1;
+      const size_t smem = dec_smem_bytes(false);
+      auto k = decode_chunks_kernel<0>;
+      if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess) return -1;
+      k<<<L.n_chunks_total, kThreads, smem, stream>>>(R);  // CTAs beyond the redo list return at once
+      ++launches;
+    }
     if (plan.n_sections > 0) {
       DecLaunch S = L;
       S.sections_only = 1;

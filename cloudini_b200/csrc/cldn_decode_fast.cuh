@@ -25,21 +25,30 @@ namespace cldn {
 
 constexpr int kFT = 128;                     // threads per CTA
 constexpr int kFW = kFT / 32;                // warps
-constexpr int kFP = 8;                       // points per thread and tile
-constexpr int kFTilePts = kFT * kFP;         // 1024 points per tile
+// points per thread and tile: FP = 8 for <= 4 values per point (1024-point tiles), 4 for 5 or 6 (512-point tiles): the
+// decoded prefix values of a thread stay in registers, a point's floats in one 16-byte (two for 5 / 6 values) staging slot
+// Values 0 .. n_floatn-1 of a point are the FloatN group (int32 arithmetic, wrapping like the reference's Vector4i); the
+// rest are scalar lossy FLOAT32 fields, which the reference accumulates in int64 (field_decoder.hpp:331-353): the fast
+// reader keeps 64-bit bases for them and hands the chunk to the careful kernel if a value leaves the int32 range.
+struct FastDecParams {
+  float mul[6];
+  uint32_t off[6];
+  uint32_t n_floatn;
+};
 constexpr int kFUnit = 16;                   // bytes per unit: a thread's slice of the window is `nu` units (nu odd: the
 constexpr int kFMaxUnits = 11;               //   16-byte reads of a warp are then conflict-free at any count)
 constexpr int kFLead = 16;                   // bytes in front of the window (never read as data; keeps indices > 0)
 constexpr int kFWinBytes = kFMaxUnits * kFT * kFUnit;   // 22528
 constexpr int kFWinAlloc = kFLead + kFWinBytes + 32;    // reads run at most 7 bytes past a value's last byte
 constexpr int kFMaskWords = (kFMaxUnits * kFUnit + 31) / 32; // 6 words of terminator bits per thread
-static_assert(kFTilePts * 16 <= kFWinAlloc, "the float staging aliases the window");
+static_assert(kFT * 8 * 16 <= kFWinAlloc, "the float staging aliases the window");
 
 struct FastShared {
   uint32_t wcnt[kFW];                 // terminators per warp
   uint32_t lane_incl[kFT];            // warp-local inclusive terminator counts
   uint32_t masks[kFMaskWords][kFT];   // terminator bits of every thread's slice (word-major: conflict-free)
-  int32_t wsum[kFW][4];               // per-warp field sums
+  int32_t wsum[kFW][6];               // per-warp field sums (int32, wrapping: FloatN fields)
+  long long wsum64[kFW][6];           // scalar lossy fields: the reference keeps them in int64
   uint32_t next_cursor;               // window byte index (incl. kFLead) one past the tile's last value
   uint32_t chunk;                     // claimed chunk
   unsigned long long desc[2];
@@ -90,9 +99,11 @@ __device__ __forceinline__ uint32_t nth_set_bit32(uint32_t m, uint32_t n, const 
   return base + ((__ldg(&table[m & 0xFFu]) >> (4u * n)) & 7u);
 }
 
-template <int K>
-__global__ void __launch_bounds__(kFT, 7) decode_floatn_fast_kernel(const DecLaunch L, float m0, float m1, float m2, float m3,
-                                                                    uint32_t o0, uint32_t o1, uint32_t o2, uint32_t o3) {
+template <int K, int FP, bool MIXED>
+__global__ void __launch_bounds__(kFT, 7) decode_floatn_fast_kernel(const DecLaunch L, const FastDecParams Q) {
+  constexpr int kFP = FP;
+  constexpr int kFTilePts = kFT * FP;
+  constexpr int kSlots = K <= 4 ? 1 : 2;                     // 16-byte staging slots per point
   extern __shared__ __align__(16) uint8_t dyn_smem[];
   __shared__ FastShared sh;
   uint8_t* win = dyn_smem;                                    // kFLead + window bytes
@@ -100,8 +111,11 @@ __global__ void __launch_bounds__(kFT, 7) decode_floatn_fast_kernel(const DecLau
   constexpr int VPT = kFP * K;                                // values per thread
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t step = L.plan->point_step;
-  const float mul[4] = {m0, m1, m2, m3};
-  const uint32_t off[4] = {o0, o1, o2, o3};
+  float mul[K];
+  uint32_t off[K];
+#pragma unroll
+  for (int f = 0; f < K; ++f) { mul[f] = Q.mul[f]; off[f] = Q.off[f]; }
+  const uint32_t n_floatn = MIXED ? Q.n_floatn : static_cast<uint32_t>(K);
 
   // Whichever CTA draws ticket 0 -- by construction one that is running -- follows the u32 chunk prefixes of every
   // frame (cloudini.cpp:645-664) and publishes them; everybody else starts decoding and only waits for its own chunk.
@@ -159,15 +173,18 @@ __global__ void __launch_bounds__(kFT, 7) decode_floatn_fast_kernel(const DecLau
     __syncthreads();
     uint8_t* const out = sh.out;
     const uint32_t size = sh.size;
-    const bool aligned4 = (((reinterpret_cast<uintptr_t>(out) | step | o0 | o1 | o2 | (K == 4 ? o3 : 0u)) & 3u) == 0u) &&
-        o0 != CLDN_SKIP_STORE_OFFSET && o1 != CLDN_SKIP_STORE_OFFSET && o2 != CLDN_SKIP_STORE_OFFSET && (K < 4 || o3 != CLDN_SKIP_STORE_OFFSET);
-    const bool dense4 = K == 4 && aligned4 && step == 16u && o0 == 0u && o1 == 4u && o2 == 8u && o3 == 12u &&
-        (reinterpret_cast<uintptr_t>(out) & 15u) == 0u;
+    bool aligned4 = ((reinterpret_cast<uintptr_t>(out) | step) & 3u) == 0u;
+#pragma unroll
+    for (int f = 0; f < K; ++f) aligned4 = aligned4 && (off[f] & 3u) == 0u && off[f] != CLDN_SKIP_STORE_OFFSET;
+    bool dense4 = K == 4 && aligned4 && step == 16u && (reinterpret_cast<uintptr_t>(out) & 15u) == 0u;
+#pragma unroll
+    for (int f = 0; f < K; ++f) dense4 = dense4 && off[f] == 4u * f;
     __syncthreads();  // everybody has read sh.chunk / sh.desc before thread 0 may claim the next chunk
 
     int32_t carry[K];
+    long long carry64[MIXED ? K : 1];
 #pragma unroll
-    for (int f = 0; f < K; ++f) carry[f] = 0;
+    for (int f = 0; f < K; ++f) { carry[f] = 0; if (MIXED) carry64[f] = 0; }
     uint32_t cursor = 0;                      // stream byte offset of the next tile's first value
     uint32_t est = 0;                         // bytes of the previous tile (0: none yet)
     bool redo = (size == 0u);                 // an empty body cannot hold n_points > 0 points: the careful kernel reports it
@@ -361,13 +378,32 @@ __global__ void __launch_bounds__(kFT, 7) decode_floatn_fast_kernel(const DecLau
           if (lane >= d) inc[f] = static_cast<int32_t>(static_cast<uint32_t>(inc[f]) + static_cast<uint32_t>(up));
         }
       }
+      long long inc64[MIXED ? K : 1];
+      if (MIXED) {  // scalar fields: the same scan in 64 bits (a warp's sum of 4-byte deltas does not fit 32)
+#pragma unroll
+        for (int f = 0; f < K; ++f) inc64[f] = tot[f];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+#pragma unroll
+          for (int f = 0; f < K; ++f) {
+            if (static_cast<uint32_t>(f) >= n_floatn) {
+              const long long up = __shfl_up_sync(0xffffffffu, inc64[f], d);
+              if (lane >= d) inc64[f] += up;
+            }
+          }
+        }
+      }
       if (lane == 31) {
 #pragma unroll
-        for (int f = 0; f < K; ++f) sh.wsum[warp][f] = inc[f];
+        for (int f = 0; f < K; ++f) {
+          sh.wsum[warp][f] = inc[f];
+          if (MIXED) sh.wsum64[warp][f] = inc64[f];
+        }
       }
       const int any_bad = __syncthreads_or(bad ? 1 : 0);  // also: every thread is done with the window bytes
       if (any_bad) { redo = true; break; }
       int32_t base[K];
+      long long base64[MIXED ? K : 1];
 #pragma unroll
       for (int f = 0; f < K; ++f) {
         uint32_t b = static_cast<uint32_t>(carry[f]), c = static_cast<uint32_t>(carry[f]);
@@ -379,6 +415,17 @@ __global__ void __launch_bounds__(kFT, 7) decode_floatn_fast_kernel(const DecLau
         }
         carry[f] = static_cast<int32_t>(c);
         base[f] = static_cast<int32_t>(b + static_cast<uint32_t>(inc[f]) - static_cast<uint32_t>(tot[f]));
+        if (MIXED && static_cast<uint32_t>(f) >= n_floatn) {
+          long long b64 = carry64[f], c64 = carry64[f];
+#pragma unroll
+          for (int w = 0; w < kFW; ++w) {
+            const long long s64 = sh.wsum64[w][f];
+            if (w < warp) b64 += s64;
+            c64 += s64;
+          }
+          carry64[f] = c64;
+          base64[f] = b64 + inc64[f] - tot[f];
+        }
       }
       const uint32_t ncur = sh.next_cursor;
       const uint32_t used = ncur - (kFLead + c0);
@@ -387,51 +434,88 @@ __global__ void __launch_bounds__(kFT, 7) decode_floatn_fast_kernel(const DecLau
         const uint32_t ahead = cursor + used + threadIdx.x * 128u;
         if (ahead < size && threadIdx.x * 128u < used + (used >> 2) + 256u) prefetch_l2(body + ahead);
       }
-      // ---- floats into my warp's staging slots (16 bytes per point; slot of point j of lane l: 8 l + (j ^ (l & 7))) ----
-      uint4* wst = ostage + warp * (32 * kFP);
+      // ---- floats into my warp's staging slots (16 bytes per point, two for 5 / 6 values; a lane's 8 slots are XOR-swizzled
+      //      with its index so that both the lane-blocked writes and the point-strided reads are conflict-free) ----
+      uint4* wst = ostage + warp * (32 * 8);
       uint4* const my_slots = wst + 8 * lane;
       const uint32_t lx = lane & 7;
+      bool wide = false;   // a scalar lossy value left the int32 range: the careful kernel (int64 like the reference) decides
 #pragma unroll
       for (int j = 0; j < kFP; ++j) {
-        uint32_t fl[4] = {0, 0, 0, 0};
+        uint32_t fl[kSlots * 4];
+#pragma unroll
+        for (int f = 0; f < kSlots * 4; ++f) fl[f] = 0;
 #pragma unroll
         for (int f = 0; f < K; ++f) {
-          const int32_t v = static_cast<int32_t>(static_cast<uint32_t>(base[f]) + static_cast<uint32_t>(P[j][f]));
+          int32_t v = static_cast<int32_t>(static_cast<uint32_t>(base[f]) + static_cast<uint32_t>(P[j][f]));
+          if (MIXED && static_cast<uint32_t>(f) >= n_floatn) {
+            const long long v64 = base64[f] + P[j][f];
+            v = static_cast<int32_t>(v64);
+            wide = wide || (v64 != static_cast<long long>(v));
+          }
           fl[f] = __float_as_uint(__fmul_rn(__int2float_rn(v), mul[f]));
         }
-        my_slots[j ^ lx] = make_uint4(fl[0], fl[1], fl[2], fl[3]);
+        if (kSlots == 1) {
+          my_slots[j ^ lx] = make_uint4(fl[0], fl[1], fl[2], fl[3]);
+        } else {
+          my_slots[(2 * j) ^ lx] = make_uint4(fl[0], fl[1], fl[2], fl[3]);
+          my_slots[(2 * j + 1) ^ lx] = make_uint4(fl[4], fl[5], fl[6], fl[7]);
+        }
       }
       __syncwarp();
-      // ---- copy-out: lane l of iteration i takes point 32 i + l of the warp's 256 ----
-      // its slot: owner lane 4 i + (l >> 3), point l & 7 -> 8 (4 i + (l >> 3)) + ((l & 7) ^ ((4 i + (l >> 3)) & 7))
+      // ---- copy-out: lane l of iteration i takes point 32 i + l of the warp's 32 * FP ----
       const uint32_t wp0 = pt0 + warp * (32 * kFP);
       const uint32_t wn = wp0 < n_points ? min(static_cast<uint32_t>(32 * kFP), n_points - wp0) : 0u;
-      const uint32_t lh = lane >> 3, ll = lane & 7;
-      const uint4* rd_even = wst + 8 * lh + (ll ^ lh);          // i even: (4 i + lh) & 7 == lh
-      const uint4* rd_odd = wst + 8 * lh + (ll ^ (lh + 4));     // i odd:  (4 i + lh) & 7 == lh + 4
       uint8_t* dst0 = sh.out + static_cast<size_t>(wp0 + lane) * step;
-      if (dense4 && wn == static_cast<uint32_t>(32 * kFP)) {
+      if (kSlots == 1) {
+        // slot of point 32 i + l: owner lane 4 i + (l >> 3), its point l & 7 -> 8 (4 i + (l >> 3)) + ((l & 7) ^ ((4 i + (l >> 3)) & 7))
+        const uint32_t lh = lane >> 3, ll = lane & 7;
+        const uint4* rd_even = wst + 8 * lh + (ll ^ lh);          // i even: (4 i + lh) & 7 == lh
+        const uint4* rd_odd = wst + 8 * lh + (ll ^ (lh + 4));     // i odd:  (4 i + lh) & 7 == lh + 4
+        if (dense4 && wn == static_cast<uint32_t>(32 * kFP)) {
 #pragma unroll
-        for (int i = 0; i < kFP; ++i) {
-          const uint4 v = ((i & 1) ? rd_odd : rd_even)[32 * i];
-          __stcs(reinterpret_cast<uint4*>(dst0 + 512 * i), v);
+          for (int i = 0; i < kFP; ++i) {
+            const uint4 v = ((i & 1) ? rd_odd : rd_even)[32 * i];
+            __stcs(reinterpret_cast<uint4*>(dst0 + 512 * i), v);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < kFP; ++i) {
+            const uint32_t q = 32u * i + lane;
+            if (q < wn) {
+              const uint4 v = ((i & 1) ? rd_odd : rd_even)[32 * i];
+              uint8_t* dst = dst0 + static_cast<size_t>(32 * i) * step;
+              const uint32_t vv[4] = {v.x, v.y, v.z, v.w};
+              if (dense4) {
+                __stcs(reinterpret_cast<uint4*>(dst), v);
+              } else if (aligned4) {
+#pragma unroll
+                for (int f = 0; f < K; ++f) __stcs(reinterpret_cast<unsigned int*>(dst + off[f]), vv[f]);
+              } else {
+#pragma unroll
+                for (int f = 0; f < K; ++f) {
+                  if (off[f] != CLDN_SKIP_STORE_OFFSET) store_u32(dst + off[f], vv[f]);
+                }
+              }
+            }
+          }
         }
       } else {
+        // two slots per point, 4 points per lane: point 32 i + l belongs to lane 8 i + (l >> 2), its point l & 3
+        const uint32_t lo4 = lane >> 2, lj = lane & 3;
+        const uint4* rd0 = wst + 8 * lo4 + ((2 * lj) ^ lo4);
+        const uint4* rd1 = wst + 8 * lo4 + ((2 * lj + 1) ^ lo4);
 #pragma unroll
         for (int i = 0; i < kFP; ++i) {
           const uint32_t q = 32u * i + lane;
           if (q < wn) {
-            const uint4 v = ((i & 1) ? rd_odd : rd_even)[32 * i];
+            const uint4 a = rd0[64 * i], b = rd1[64 * i];
             uint8_t* dst = dst0 + static_cast<size_t>(32 * i) * step;
-            if (dense4) {
-              __stcs(reinterpret_cast<uint4*>(dst), v);
-            } else if (aligned4) {
-              __stcs(reinterpret_cast<unsigned int*>(dst + o0), v.x);
-              __stcs(reinterpret_cast<unsigned int*>(dst + o1), v.y);
-              __stcs(reinterpret_cast<unsigned int*>(dst + o2), v.z);
-              if (K == 4) __stcs(reinterpret_cast<unsigned int*>(dst + o3), v.w);
+            const uint32_t vv[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+            if (aligned4) {
+#pragma unroll
+              for (int f = 0; f < K; ++f) __stcs(reinterpret_cast<unsigned int*>(dst + off[f]), vv[f]);
             } else {
-              const uint32_t vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
               for (int f = 0; f < K; ++f) {
                 if (off[f] != CLDN_SKIP_STORE_OFFSET) store_u32(dst + off[f], vv[f]);
@@ -442,10 +526,18 @@ __global__ void __launch_bounds__(kFT, 7) decode_floatn_fast_kernel(const DecLau
       }
       est = used;
       cursor += used;
-      __syncthreads();  // the staging slots alias the window the next tile is about to load
+      // the staging slots alias the window the next tile is about to load
+      if (MIXED) {
+        if (__syncthreads_or(wide ? 1 : 0)) { redo = true; break; }
+      } else {
+        __syncthreads();
+      }
     }
     if (redo) {
-      if (threadIdx.x == 0) L.redo_list[atomicAdd(L.chunk_counter + 3, 1u)] = gc;
+      if (threadIdx.x == 0) {
+        L.redo_list[atomicAdd(L.chunk_counter + 3, 1u)] = gc;
+        L.stream_end[gc] = 0xFFFFFFFFu;  // the careful kernel owns this chunk now (its sections too)
+      }
     } else if (threadIdx.x == 0) {
       L.stream_end[gc] = cursor;  // V5: the sections start here
     }
@@ -454,23 +546,59 @@ __global__ void __launch_bounds__(kFT, 7) decode_floatn_fast_kernel(const DecLau
 
 size_t decode_fast_smem_bytes() { return static_cast<size_t>(kFWinAlloc); }
 
-template <int K>
-static int launch_fast(const RegOp& op, const DecLaunch& L, int sm_count, cudaStream_t stream) {
+template <int K, int FP, bool MIXED>
+static int launch_fast(const FastDecParams& Q, const DecLaunch& L, int sm_count, cudaStream_t stream) {
   const size_t smem = decode_fast_smem_bytes();
-  const float m3 = K == 4 ? op.dec_mul_f[3] : 0.f;
-  const uint32_t o3 = K == 4 ? op.offset[3] : 0u;
-  auto k = decode_floatn_fast_kernel<K>;
+  auto k = decode_floatn_fast_kernel<K, FP, MIXED>;
   if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess) return -1;
   int per_sm = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kFT, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
   const uint32_t grid = min(L.n_chunks_total, static_cast<uint32_t>(per_sm * sm_count));
-  k<<<grid, kFT, smem, stream>>>(L, op.dec_mul_f[0], op.dec_mul_f[1], op.dec_mul_f[2], m3, op.offset[0], op.offset[1], op.offset[2], o3);
+  k<<<grid, kFT, smem, stream>>>(L, Q);
   return 1;
 }
 
+// Plans the fast reader takes: every value of the regular stream is a 32-bit float varint -- one leading FloatN group and /
+// or scalar lossy FLOAT32 fields --, 3 .. 6 values per point.
+bool decode_fast_plan(const Plan& plan, FastDecParams* Q) {
+  if (!plan.all_varint || plan.n_ops == 0 || plan.n_gorilla || plan.regular_overlap) return false;
+  uint32_t nv = 0;
+  Q->n_floatn = 0;
+  for (uint32_t i = 0; i < plan.n_ops; ++i) {
+    const RegOp& op = plan.ops[i];
+    if (op.kind == OP_FLOATN && i == 0) {
+      for (int l = 0; l < op.lanes; ++l) { Q->mul[nv] = op.dec_mul_f[l]; Q->off[nv] = op.offset[l]; ++nv; }
+      Q->n_floatn = op.lanes;
+    } else if (op.kind == OP_F32_LOSSY) {
+      if (nv >= 6) return false;
+      Q->mul[nv] = op.dec_mul_f[0]; Q->off[nv] = op.offset[0]; ++nv;
+    } else {
+      return false;
+    }
+  }
+  if (nv < 3 || nv > 6) return false;
+  for (uint32_t k = nv; k < 6; ++k) { Q->mul[k] = 0.f; Q->off[k] = 0; }
+  return true;
+}
+
+bool decode_fast_general_plan(const Plan& plan) {
+  FastDecParams Q;
+  return decode_fast_plan(plan, &Q);
+}
+
 int launch_decode_fast(const Plan& plan, const DecLaunch& L, int sm_count, cudaStream_t stream) {
-  const RegOp& op = plan.ops[0];
-  return op.lanes == 4 ? launch_fast<4>(op, L, sm_count, stream) : launch_fast<3>(op, L, sm_count, stream);
+  FastDecParams Q;
+  if (!decode_fast_plan(plan, &Q)) return -1;
+  const uint32_t nv = plan.values_per_point;
+  if (Q.n_floatn == nv) {
+    return nv == 4 ? launch_fast<4, 8, false>(Q, L, sm_count, stream) : launch_fast<3, 8, false>(Q, L, sm_count, stream);
+  }
+  switch (nv) {
+    case 3: return launch_fast<3, 8, true>(Q, L, sm_count, stream);
+    case 4: return launch_fast<4, 8, true>(Q, L, sm_count, stream);
+    case 5: return launch_fast<5, 4, true>(Q, L, sm_count, stream);
+    default: return launch_fast<6, 4, true>(Q, L, sm_count, stream);
+  }
 }
 
 }  // namespace cldn

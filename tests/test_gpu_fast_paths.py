@@ -193,3 +193,59 @@ def test_fast_writer_large_and_ragged_batches(oracle):
         one = synth.info_xyzi(n)
         want = oracle.encode(one, clouds[k], write_header=False) if n else b""
         assert bytes(d_blob[k].numpy()[:sizes[k]]) == want, (k, n)
+
+
+# ---- sensor layouts with scalar lossy floats behind the FloatN group (Velodyne XYZIRT ...) -----------------------------
+def _xyzirt(n, seed, time_scale=1.0):
+    info, cloud = synth.cloud_c4_mixed_frame(seed)
+    n0 = info.width
+    reps = (n + n0 - 1) // n0
+    buf = np.tile(cloud.reshape(n0, 22), (reps, 1))[:n].copy()
+    t = (np.arange(n, dtype=np.float64) * 1e-4 * time_scale).astype(np.float32)
+    buf[:, 18:22] = t.view(np.uint8).reshape(n, 4)
+    info.width = n
+    return info, np.ascontiguousarray(buf).reshape(-1)
+
+
+def test_mixed_float_layouts_take_the_fast_paths(oracle, monkeypatch):
+    monkeypatch.setenv("CLDN_B200_DECODE_MODE", "seq")
+    F = cb.FieldType
+    for n in (1, 511, 512, 513, 40_000, 70_001):
+        cases = [_xyzirt(n, 3)]
+        # three scalar lossy floats and no FloatN group at all (an int field first breaks the leading group), step 20
+        rng = np.random.default_rng(n)
+        raw = np.zeros((n, 20), dtype=np.uint8)
+        raw[:, 0:4] = (np.arange(n) % 5).astype(np.uint32).view(np.uint8).reshape(n, 4)
+        for k in range(3):
+            raw[:, 4 + 4 * k:8 + 4 * k] = np.cumsum(rng.normal(0, 0.05, n)).astype(np.float32).view(np.uint8).reshape(n, 4)
+        info = cb.EncodingInfo(fields=[cb.PointField("id", 0, F.UINT32, None), cb.PointField("a", 4, F.FLOAT32, 0.001), cb.PointField("b", 8, F.FLOAT32, 0.002),
+                                       cb.PointField("c", 12, F.FLOAT32, 0.0005)],
+                               width=n, height=1, point_step=20, compression_opt=cb.CompressionOption.NONE, use_threads=False, version=5)
+        cases.append((info, raw.reshape(-1)))
+        for info, cloud in cases:
+            blob = oracle.encode(info, cloud)
+            assert cb.PointcloudEncoder(info).encode(cloud) == blob
+            hdr = len(cb.PointcloudEncoder(info).getHeader())
+            outs, (fast, redo) = _decode_batch(info, [blob, blob], hdr, cloud.size, 0x19)
+            chunks = 2 * ((n + 32767) // 32768)
+            assert (fast, redo) == (chunks, 0), (n, fast, redo)
+            for o in outs:
+                assert np.array_equal(o, _want(oracle, blob, cloud.size, 0x19))
+
+
+def test_mixed_float_layouts_hand_over_what_is_not_plain(oracle, monkeypatch):
+    monkeypatch.setenv("CLDN_B200_DECODE_MODE", "seq")
+    n = 70_000
+    info, plain = _xyzirt(n, 5)
+    pts = plain.reshape(n, 22).copy()
+    nan_c = pts.copy(); nan_c[40_000, 18:22] = np.frombuffer(np.float32(np.nan).tobytes(), dtype=np.uint8)   # NaN in the scalar field
+    wide_c = pts.copy(); wide_c[100, 0:4] = np.frombuffer(np.float32(3.0e6).tobytes(), dtype=np.uint8)        # 5-byte varint
+    _, big_t = _xyzirt(n, 5, time_scale=5000.0)        # time * 1e5 leaves the int32 range half way through the cloud
+    clouds = [plain, nan_c.reshape(-1), wide_c.reshape(-1), big_t]
+    blobs, hdr = _encode_all(info, clouds, oracle)
+    for c, b in zip(clouds, blobs):
+        assert cb.PointcloudEncoder(info).encode(c) == b
+    outs, (fast, redo) = _decode_batch(info, blobs, hdr, n * 22, 0x44)
+    assert fast == 4 * 3 and redo >= 3, (fast, redo)
+    for b, o in zip(blobs, outs):
+        assert np.array_equal(o, _want(oracle, b, n * 22, 0x44))
