@@ -413,6 +413,9 @@ static int launch_encode_fast(const Plan& plan, const EncLaunch& L, cudaStream_t
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kET, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
     resident = std::max(1, sms) * per_sm;
+#ifdef CLDN_CUSIM
+    resident = static_cast<int>(::cusim::coresident_ctas());  // the emulation runs this many CTAs at a time, not 148 SMs' worth
+#endif
   }
   const uint32_t grid = std::min<uint32_t>(L.n_tiles_total, static_cast<uint32_t>(resident));
   k<<<grid, kET, smem, stream>>>(L, P);

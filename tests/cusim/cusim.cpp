@@ -311,6 +311,16 @@ void run_cta(Cta* c, dim3 grid, dim3 block, uint3 bid) {
 
 }  // namespace
 
+// CTAs the emulation really runs at the same time (one per OS thread): a persistent kernel whose CTAs wait for each other
+// must not launch more than this many (on the GPU the occupancy query gives the corresponding bound)
+unsigned coresident_ctas() {
+  unsigned workers = std::thread::hardware_concurrency();
+  if (const char* e = getenv("CUSIM_WORKERS")) workers = static_cast<unsigned>(atoi(e));
+  if (workers < 1) workers = 1;
+  if (workers > 16) workers = 16;
+  return workers;
+}
+
 int sm_count() {
   const char* e = getenv("CUSIM_SMS");
   const int v = e ? atoi(e) : 0;
