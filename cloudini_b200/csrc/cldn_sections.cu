@@ -255,7 +255,9 @@ __device__ bool palette_insert_all(const PaletteTable& T, const SecItem& it, uin
         h = (h + 1) & (T.slots - 1);
       }
     }
-    atomicMin(&T.firsts[h], i);
+    // indexes arrive in roughly rising order, so after its first few appearances a value's entry is already below i:
+    // the plain read keeps 32768 atomics off a handful of addresses (8 colours -> 4096 serialised updates each)
+    if (reinterpret_cast<volatile uint32_t*>(T.firsts)[h] > i) atomicMin(&T.firsts[h], i);
   }
   __syncthreads();
   const bool ok = *s_count <= T.slots / 2;

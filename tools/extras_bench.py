@@ -127,7 +127,7 @@ def bench_c3(out):
 
 def bench_c4_mixed(out):
     """BASELINE configs[3] with the sensor's own layout (XYZI + ring u16 + time f32, step 22, generic kernels + V5 section)."""
-    F = 64
+    F = 256   # 1024 chunks: the chunk-sequential readers want at least one chunk per resident CTA (1036 on 148 SMs)
     info, _ = synth.cloud_c4_mixed_frame(0)
     clouds = [synth.cloud_c4_mixed_frame(k)[1] for k in range(F)]
     n, step = info.width, info.point_step
