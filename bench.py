@@ -32,7 +32,9 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--frames", type=int, default=32, help="distinct 1M-point clouds per GPU per step")
+    ap.add_argument("--frames", type=int, default=128,
+                    help="distinct 1M-point clouds per GPU per step (C5 is a batch of 10k clouds; 128 = 2 GB of input per launch. "
+                         "Round 1 used 32: profiles/r2_batch_sweep.json has 32 / 64 / 100 / 128 side by side)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-e2e", action="store_true")

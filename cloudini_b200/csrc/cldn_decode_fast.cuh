@@ -34,6 +34,7 @@ struct FastDecParams {
   float mul[6];
   uint32_t off[6];
   uint32_t n_floatn;
+  uint32_t rows;   // the regular fields and the V5 section fields together cover every byte of a point: whole rows may be written
 };
 constexpr int kFUnit = 16;                   // bytes per unit: a thread's slice of the window is `nu` units (nu odd: the
 constexpr int kFMaxUnits = 11;               //   16-byte reads of a warp are then conflict-free at any count)
@@ -179,6 +180,14 @@ __global__ void __launch_bounds__(kFT, 7) decode_floatn_fast_kernel(const DecLau
     bool dense4 = K == 4 && aligned4 && step == 16u && (reinterpret_cast<uintptr_t>(out) & 15u) == 0u;
 #pragma unroll
     for (int f = 0; f < K; ++f) dense4 = dense4 && off[f] == 4u * f;
+    // Whole-row copy-out: when every byte of a point belongs to a decoded field (regular or V5 section -- the section
+    // reader runs behind this kernel and overwrites its bytes), the warp builds its 32 * FP points as contiguous rows in
+    // shared memory and writes them with 16-byte stores. Per-field 4-byte stores of 32 lanes touch one 32-byte sector
+    // per lane and field (XYZIRT, step 22: 16 sectors per store instruction measured, 5x the row bytes through L2).
+    const bool rows = !dense4 && Q.rows != 0u && step * (32u * kFP) <= 4096u && (reinterpret_cast<uintptr_t>(out) & 15u) == 0u;
+    uint32_t row_align = step;
+#pragma unroll
+    for (int f = 0; f < K; ++f) row_align |= off[f];
     __syncthreads();  // everybody has read sh.chunk / sh.desc before thread 0 may claim the next chunk
 
     int32_t carry[K];
@@ -455,7 +464,22 @@ __global__ void __launch_bounds__(kFT, 7) decode_floatn_fast_kernel(const DecLau
           }
           fl[f] = __float_as_uint(__fmul_rn(__int2float_rn(v), mul[f]));
         }
-        if (kSlots == 1) {
+        if (rows) {
+          uint8_t* row = reinterpret_cast<uint8_t*>(wst) + static_cast<uint32_t>(kFP * lane + j) * step;
+#pragma unroll
+          for (int f = 0; f < K; ++f) {
+            uint8_t* d = row + off[f];
+            if ((row_align & 3u) == 0u) {
+              *reinterpret_cast<uint32_t*>(d) = fl[f];
+            } else if ((row_align & 1u) == 0u) {
+              *reinterpret_cast<uint16_t*>(d) = static_cast<uint16_t>(fl[f]);
+              *reinterpret_cast<uint16_t*>(d + 2) = static_cast<uint16_t>(fl[f] >> 16);
+            } else {
+              d[0] = static_cast<uint8_t>(fl[f]); d[1] = static_cast<uint8_t>(fl[f] >> 8);
+              d[2] = static_cast<uint8_t>(fl[f] >> 16); d[3] = static_cast<uint8_t>(fl[f] >> 24);
+            }
+          }
+        } else if (kSlots == 1) {
           my_slots[j ^ lx] = make_uint4(fl[0], fl[1], fl[2], fl[3]);
         } else {
           my_slots[(2 * j) ^ lx] = make_uint4(fl[0], fl[1], fl[2], fl[3]);
@@ -467,7 +491,16 @@ __global__ void __launch_bounds__(kFT, 7) decode_floatn_fast_kernel(const DecLau
       const uint32_t wp0 = pt0 + warp * (32 * kFP);
       const uint32_t wn = wp0 < n_points ? min(static_cast<uint32_t>(32 * kFP), n_points - wp0) : 0u;
       uint8_t* dst0 = sh.out + static_cast<size_t>(wp0 + lane) * step;
-      if (kSlots == 1) {
+      if (rows) {
+        const uint32_t total = wn * step;                      // bytes of this warp's rows; its first byte is 16-byte aligned
+        uint8_t* dst = sh.out + static_cast<size_t>(wp0) * step;
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(wst);
+        for (uint32_t o = 16u * lane; o + 16u <= total; o += 512u) {
+          __stcs(reinterpret_cast<uint4*>(dst + o), *reinterpret_cast<const uint4*>(src + o));
+        }
+        const uint32_t tail0 = total & ~15u;
+        if (tail0 + lane < total) dst[tail0 + lane] = src[tail0 + lane];
+      } else if (kSlots == 1) {
         // slot of point 32 i + l: owner lane 4 i + (l >> 3), its point l & 7 -> 8 (4 i + (l >> 3)) + ((l & 7) ^ ((4 i + (l >> 3)) & 7))
         const uint32_t lh = lane >> 3, ll = lane & 7;
         const uint4* rd_even = wst + 8 * lh + (ll ^ lh);          // i even: (4 i + lh) & 7 == lh
@@ -578,6 +611,23 @@ bool decode_fast_plan(const Plan& plan, FastDecParams* Q) {
   }
   if (nv < 3 || nv > 6) return false;
   for (uint32_t k = nv; k < 6; ++k) { Q->mul[k] = 0.f; Q->off[k] = 0; }
+  // rows: every byte of [0, point_step) is written by a regular field (4 bytes each here) or by a V5 section field
+  Q->rows = 0;
+  if (plan.point_step <= 64) {
+    uint64_t covered = 0;
+    bool ok = true;
+    for (uint32_t k = 0; k < nv; ++k) {
+      if (Q->off[k] == CLDN_SKIP_STORE_OFFSET || Q->off[k] + 4u > plan.point_step) { ok = false; break; }
+      covered |= 0xFull << Q->off[k];
+    }
+    for (uint32_t s2 = 0; ok && s2 < plan.n_sections; ++s2) {
+      const SectionField& sf = plan.sections[s2];
+      if (sf.offset == CLDN_SKIP_STORE_OFFSET || sf.offset + sf.bpv > plan.point_step) { ok = false; break; }
+      covered |= ((1ull << sf.bpv) - 1ull) << sf.offset;
+    }
+    const uint64_t all = plan.point_step == 64 ? ~0ull : ((1ull << plan.point_step) - 1ull);
+    if (ok && covered == all) Q->rows = 1;
+  }
   return true;
 }
 

@@ -249,3 +249,29 @@ def test_mixed_float_layouts_hand_over_what_is_not_plain(oracle, monkeypatch):
     assert fast == 4 * 3 and redo >= 3, (fast, redo)
     for b, o in zip(blobs, outs):
         assert np.array_equal(o, _want(oracle, b, n * 22, 0x44))
+
+
+@pytest.mark.parametrize("shift", [0, 2, 16])
+def test_whole_row_copy_out_at_any_output_address(oracle, monkeypatch, shift):
+    """Layouts whose fields cover every byte of a point leave the fast reader as whole rows (16-byte stores) when the output
+    is 16-byte aligned, and field by field otherwise: same bytes, nothing outside [out, out + n * step) is touched."""
+    monkeypatch.setenv("CLDN_B200_DECODE_MODE", "seq")
+    for n in (129, 40_003):
+        made = [_xyzirt(n, 5), synth.cloud_c1(n, seed=9)]
+        for info, cloud in made:
+            blob = oracle.encode(info, cloud)
+            hdr = len(cb.PointcloudEncoder(info).getHeader())
+            dec = cb.PointcloudDecoder()
+            d_blob = _Dev(src=np.frombuffer(blob, dtype=np.uint8))
+            guard = 64
+            d_out = _Dev(src=np.full(cloud.size + 2 * guard + 32, 0xA7, dtype=np.uint8))
+            base = d_out.ptr + guard
+            base += (-base) % 16 + shift                      # 16-byte aligned + shift
+            batch = dec.make_device_batch([d_blob.ptr + hdr], [len(blob) - hdr], [base], [cloud.size])
+            dec.decode_batch_device(info, batch, sync=True)
+            fast, redo = dec.last_stats()
+            assert (fast, redo) == ((n + 32767) // 32768, 0)
+            got = d_out.numpy()
+            o0 = base - d_out.ptr
+            assert np.array_equal(got[o0:o0 + cloud.size], _want(oracle, blob, cloud.size, 0xA7))
+            assert np.all(got[:o0] == 0xA7) and np.all(got[o0 + cloud.size:] == 0xA7)
