@@ -572,7 +572,7 @@ static int encode_batch_device(cldn_encoder* e, size_t n_frames, const void* con
     if (int rc = e->h_chunk_frame.commit(hcf_slot, e->stream)) return rc;
     CUDA_TRY(cudaMemcpyAsync(e->d_frames.p, hf, n_frames * sizeof(EncFrame), cudaMemcpyHostToDevice, e->stream));
     if (int rc = e->h_frames.commit(hf_slot, e->stream)) return rc;
-    SecLaunch S;
+    SecLaunch S{};
     S.frames = e->d_frames.p;
     S.n_frames = static_cast<uint32_t>(n_frames);
     S.n_chunks_total = static_cast<uint32_t>(chunks);

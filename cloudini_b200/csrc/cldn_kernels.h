@@ -115,6 +115,7 @@ struct SecLaunch {
   uint64_t* hash_scratch;        // palette hash tables
   uint32_t* err;
   uint32_t header_bytes;
+  uint32_t staged;               // set by launch_encode_sections: fields of <= 4 bytes are taken by encode_sections_staged_kernel
 };
 int launch_encode_sections(const Plan& host_plan, const SecLaunch& L, cudaStream_t stream);
 size_t palette_overflow_scratch_bytes();

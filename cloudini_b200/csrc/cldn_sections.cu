@@ -12,6 +12,7 @@
 //                          output positions)
 //   place_sections_kernel  after the regular stream kernel: copies every section behind its chunk's stream
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "cldn_device.cuh"
 #include "cldn_kernels.h"
@@ -432,6 +433,7 @@ __global__ void __launch_bounds__(kSecThreads, 1) encode_sections_kernel(const S
   const Plan& plan = *L.plan;
   const uint32_t ns = plan.n_sections;
   const uint32_t gc = blockIdx.x / ns, s = blockIdx.x % ns;
+  if (L.staged && plan.sections[s].bpv <= 4) return;  // encode_sections_staged_kernel
   const uint32_t f = L.chunk_frame[gc];
   const EncFrame F = L.frames[f];
   const uint32_t chunk = gc - L.chunk_first[f];
@@ -447,6 +449,255 @@ __global__ void __launch_bounds__(kSecThreads, 1) encode_sections_kernel(const S
       PaletteTable T{sh.keys, sh.firsts, sh.ranks, kSmemPaletteSlots};
       size = write_palette_section(T, it, out, sh.idx16, &sh.count, sh.scan);
     } break;
+  }
+  if (threadIdx.x == 0) L.sec_sizes[blockIdx.x] = size;  // 0xFFFFFFFF = palette overflow, finished by the next kernel
+}
+
+// ---- staged writers: fields of at most 4 bytes ------------------------------------------------------------------------
+// The writers above fetch a value from the strided cloud every time they look at it: 3-4 sector loads per value, most of
+// them from L2 (a chunk's field spans 32768 sectors = 1 MB, four times the L1), and the kernel waits on them (ncu:
+// long-scoreboard 24 per issue, issue slots 19 % busy). Here the chunk's values are loaded ONCE, 32 independent loads in
+// flight per thread, into 128 KB of shared memory; every pass of the four modes then runs from there.
+//   layout   value i lives in word i ^ ((i >> 5) & 31): conflict-free both for the point-strided passes (lane = i & 31) and
+//            for the thread-blocked passes (thread t owns values 32 t .. 32 t + 31, the order the output needs)
+//   runs     one flag bit per value (mask word t = values of thread t, built with one ballot per warp and 32 values) and a
+//            32-word summary of the non-empty mask words: the run that starts at a head ends at the next set bit, found
+//            with two count-trailing-zeros -- no compacted head list
+//   palette  same table as above; ranks in first-appearance order from the "first occurrence" flag bits; then every value
+//            is replaced in place by its rank and 8 values are packed into exactly `bits` bytes by one thread
+struct StagedShared {
+  uint32_t scan[kSecThreads / 32 + 1];
+  uint32_t count;
+  uint32_t summary[32];
+  uint32_t mask[kChunkPoints / 32];
+  unsigned long long keys[kSmemPaletteSlots + 1];
+  uint32_t firsts[kSmemPaletteSlots + 1];
+  uint16_t ranks[kSmemPaletteSlots + 2];
+  uint32_t vals[kChunkPoints];
+};
+
+__device__ __forceinline__ uint32_t sidx(uint32_t i) { return i ^ ((i >> 5) & 31u); }
+__device__ __forceinline__ int64_t ext_value(uint32_t raw, uint8_t type) {  // ToInt64<T> for the <= 4-byte types
+  switch (type) {
+    case CLDN_INT8: return static_cast<int8_t>(raw);
+    case CLDN_INT16: return static_cast<int16_t>(raw);
+    case CLDN_INT32: return static_cast<int32_t>(raw);
+    default: return static_cast<int64_t>(raw);
+  }
+}
+
+struct StagedItem {
+  const uint32_t* vals;
+  uint32_t n;
+  uint8_t type, bpv;
+  __device__ __forceinline__ uint32_t raw(uint32_t i) const { return vals[sidx(i)]; }
+  __device__ __forceinline__ int64_t value(uint32_t i) const { return ext_value(vals[sidx(i)], type); }
+  __device__ __forceinline__ int64_t delta(uint32_t i) const { return value(i) - (i ? value(i - 1) : 0ll); }
+};
+
+// next set bit of the flag mask behind position i (exclusive), n if there is none
+__device__ __forceinline__ uint32_t next_flag(const StagedShared& sh, uint32_t i, uint32_t n) {
+  const uint32_t w = i >> 5, k = i & 31u;
+  const uint32_t m = k == 31u ? 0u : (sh.mask[w] >> (k + 1u));
+  if (m) return i + static_cast<uint32_t>(__ffs(static_cast<int>(m)));
+  uint32_t s = w >> 5;
+  const uint32_t kw = w & 31u;
+  uint32_t sm = kw == 31u ? 0u : ((sh.summary[s] >> (kw + 1u)) << (kw + 1u));
+  while (sm == 0u) {
+    if (++s >= 32u) return n;
+    sm = sh.summary[s];
+  }
+  const uint32_t w2 = 32u * s + static_cast<uint32_t>(__ffs(static_cast<int>(sm)) - 1);
+  return 32u * w2 + static_cast<uint32_t>(__ffs(static_cast<int>(sh.mask[w2])) - 1);
+}
+
+// flag bits from a predicate over the values, evaluated point-strided (one ballot per warp and 32 values) + the summary
+template <typename Pred>
+__device__ __forceinline__ void build_flags(StagedShared& sh, uint32_t n, Pred pred) {
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+#pragma unroll 4
+  for (uint32_t it = 0; it < kChunkPoints / kSecThreads; ++it) {
+    const uint32_t i = it * kSecThreads + threadIdx.x;
+    const bool f = i < n && pred(i);
+    const uint32_t b = __ballot_sync(0xffffffffu, f);
+    if (lane == 0) sh.mask[it * (kSecThreads / 32) + warp] = b;
+  }
+  __syncthreads();
+  {
+    const uint32_t b = __ballot_sync(0xffffffffu, sh.mask[32u * warp + lane] != 0u);
+    if (lane == 0) sh.summary[warp] = b;
+  }
+  __syncthreads();
+}
+
+__device__ uint32_t staged_delta_section(StagedShared& sh, const StagedItem& it, uint8_t* out) {
+  if (threadIdx.x == 0) out[0] = 0;
+  const uint32_t i0 = 32u * threadIdx.x;
+  const uint32_t cnt = i0 < it.n ? min(32u, it.n - i0) : 0u;
+  uint32_t mine = 0;
+  {
+    int64_t prev = i0 && cnt ? it.value(i0 - 1) : 0ll;
+    for (uint32_t k = 0; k < cnt; ++k) {
+      const int64_t v = it.value(i0 + k);
+      mine += varint_len(zigzag_plus1(v - prev));
+      prev = v;
+    }
+  }
+  uint32_t total;
+  const uint32_t off = 1u + sec_exclusive_scan(mine, sh.scan, &total);
+  {
+    ByteSink bs{out + off};
+    int64_t prev = i0 && cnt ? it.value(i0 - 1) : 0ll;
+    for (uint32_t k = 0; k < cnt; ++k) {
+      const int64_t v = it.value(i0 + k);
+      bs.put_varint(zigzag_plus1(v - prev));
+      prev = v;
+    }
+  }
+  __syncthreads();
+  return 1u + total;
+}
+
+template <bool DELTA>
+__device__ uint32_t staged_run_section(StagedShared& sh, const StagedItem& it, uint8_t* out) {
+  if (DELTA) build_flags(sh, it.n, [&](uint32_t i) { return i == 0u || it.delta(i) != it.delta(i - 1); });
+  else build_flags(sh, it.n, [&](uint32_t i) { return i == 0u || it.raw(i) != it.raw(i - 1); });
+  const uint32_t i0 = 32u * threadIdx.x;
+  const uint32_t m = sh.mask[threadIdx.x];
+  uint32_t mine = 0;
+  for (uint32_t r = m; r; r &= r - 1u) {
+    const uint32_t h = i0 + static_cast<uint32_t>(__ffs(static_cast<int>(r)) - 1);
+    const uint32_t len = next_flag(sh, h, it.n) - h;
+    mine += (DELTA ? static_cast<uint32_t>(varint_len(zigzag_plus1(it.delta(h)))) : static_cast<uint32_t>(it.bpv)) + uvarint_len(len);
+  }
+  uint32_t total, runs;
+  const uint32_t off = 5u + sec_exclusive_scan(mine, sh.scan, &total);
+  __syncthreads();
+  sec_exclusive_scan(__popc(m), sh.scan, &runs);
+  if (threadIdx.x == 0) {
+    out[0] = DELTA ? 3 : 2;
+    store_u32(out + 1, runs);
+  }
+  ByteSink bs{out + off};
+  for (uint32_t r = m; r; r &= r - 1u) {
+    const uint32_t h = i0 + static_cast<uint32_t>(__ffs(static_cast<int>(r)) - 1);
+    uint32_t l = next_flag(sh, h, it.n) - h;
+    if (DELTA) {
+      bs.put_varint(zigzag_plus1(it.delta(h)));
+    } else {
+      const uint32_t raw = it.raw(h);
+      for (int b = 0; b < it.bpv; ++b) bs.put_byte(static_cast<uint8_t>(raw >> (8 * b)));
+    }
+    while (l > 0x7Fu) { bs.put_byte(static_cast<uint8_t>((l & 0x7Fu) | 0x80u)); l >>= 7; }  // appendUVarint
+    bs.put_byte(static_cast<uint8_t>(l));
+  }
+  __syncthreads();
+  return 5u + total;
+}
+
+__device__ uint32_t staged_palette_section(StagedShared& sh, const StagedItem& it, uint8_t* out) {
+  PaletteTable T{sh.keys, sh.firsts, sh.ranks, kSmemPaletteSlots};
+  for (uint32_t i = threadIdx.x; i <= T.slots; i += blockDim.x) {
+    T.keys[i] = kEmptyKey;
+    T.firsts[i] = 0xFFFFFFFFu;
+  }
+  if (threadIdx.x == 0) sh.count = 0;
+  __syncthreads();
+  for (uint32_t i = threadIdx.x; i < it.n; i += blockDim.x) {
+    if (*reinterpret_cast<volatile uint32_t*>(&sh.count) > T.slots / 2) break;
+    const uint64_t raw = it.raw(i);  // <= 32 bits: never the empty marker
+    uint32_t h = static_cast<uint32_t>(mix64(raw)) & (T.slots - 1);
+    while (true) {
+      const unsigned long long k = T.keys[h];
+      if (k == raw) break;
+      if (k == kEmptyKey) {
+        const unsigned long long old = atomicCAS(&T.keys[h], kEmptyKey, static_cast<unsigned long long>(raw));
+        if (old == kEmptyKey) { atomicAdd(&sh.count, 1u); break; }
+        if (old == raw) break;
+      }
+      h = (h + 1) & (T.slots - 1);
+    }
+    if (reinterpret_cast<volatile uint32_t*>(T.firsts)[h] > i) atomicMin(&T.firsts[h], i);
+  }
+  __syncthreads();
+  if (sh.count > T.slots / 2) return 0xFFFFFFFFu;  // more distinct values than the table holds: palette_overflow_kernel
+  build_flags(sh, it.n, [&](uint32_t i) { return T.firsts[palette_find(T, it.raw(i))] == i; });
+  const uint32_t i0 = 32u * threadIdx.x;
+  const uint32_t m = sh.mask[threadIdx.x];
+  uint32_t unique;
+  uint32_t rank = sec_exclusive_scan(__popc(m), sh.scan, &unique);
+  for (uint32_t r = m; r; r &= r - 1u) {
+    const uint32_t i = i0 + static_cast<uint32_t>(__ffs(static_cast<int>(r)) - 1);
+    const uint32_t raw = it.raw(i);
+    T.ranks[palette_find(T, raw)] = static_cast<uint16_t>(rank);
+    uint8_t* dst = out + 3 + static_cast<size_t>(rank) * it.bpv;
+    for (int b = 0; b < it.bpv; ++b) dst[b] = static_cast<uint8_t>(raw >> (8 * b));
+    ++rank;
+  }
+  if (threadIdx.x == 0) {
+    out[0] = 1;
+    store_u16(out + 1, unique & 0xFFFFu);  // static_cast<uint16_t>(palette.size())
+  }
+  __syncthreads();
+  uint32_t* vals = const_cast<uint32_t*>(it.vals);
+  for (uint32_t i = threadIdx.x; i < it.n; i += blockDim.x) vals[sidx(i)] = T.ranks[palette_find(T, vals[sidx(i)])];
+  __syncthreads();
+  const uint32_t bits = bits_for_index(unique);
+  const uint32_t idx_bytes = static_cast<uint32_t>((static_cast<uint64_t>(bits) * it.n + 7u) / 8u);
+  uint8_t* ib = out + 3 + static_cast<size_t>(unique) * it.bpv;
+  if (bits) {
+    // 8 indexes are exactly `bits` bytes: unit u = values 8 u .. 8 u + 7 -> bytes [u * bits, (u + 1) * bits), LSB first
+    const uint32_t units = (it.n + 7u) / 8u;
+    for (uint32_t u = threadIdx.x; u < units; u += blockDim.x) {
+      unsigned long long lo = 0, hi = 0;
+#pragma unroll
+      for (uint32_t k = 0; k < 8; ++k) {
+        const uint32_t i = 8u * u + k;
+        const unsigned long long v = i < it.n ? vals[sidx(i)] : 0u;
+        const uint32_t sh_ = k * bits;
+        if (sh_ < 64u) {
+          lo |= v << sh_;
+          if (sh_ + bits > 64u) hi |= v >> (64u - sh_);
+        } else {
+          hi |= v << (sh_ - 64u);
+        }
+      }
+      const uint32_t b0 = u * bits;
+      const uint32_t nb = min(bits, idx_bytes - b0);
+      for (uint32_t b = 0; b < nb; ++b) ib[b0 + b] = static_cast<uint8_t>(b < 8u ? (lo >> (8u * b)) : (hi >> (8u * (b - 8u))));
+    }
+  }
+  __syncthreads();
+  return 3u + unique * it.bpv + idx_bytes;
+}
+
+__global__ void __launch_bounds__(kSecThreads, 1) encode_sections_staged_kernel(const SecLaunch L) {
+  extern __shared__ __align__(16) uint8_t dyn_smem[];
+  StagedShared& sh = *reinterpret_cast<StagedShared*>(dyn_smem);
+  const Plan& plan = *L.plan;
+  const uint32_t ns = plan.n_sections;
+  const uint32_t gc = blockIdx.x / ns, s = blockIdx.x % ns;
+  if (plan.sections[s].bpv > 4) return;  // 64-bit fields: encode_sections_kernel
+  const uint32_t f = L.chunk_frame[gc];
+  const EncFrame F = L.frames[f];
+  const uint32_t chunk = gc - L.chunk_first[f];
+  const SecItem src = make_item(F, plan, chunk, s);
+  // the one pass over the cloud: 32 independent strided loads per thread
+#pragma unroll 8
+  for (uint32_t k = 0; k < kChunkPoints / kSecThreads; ++k) {
+    const uint32_t i = k * kSecThreads + threadIdx.x;
+    if (i < src.n) sh.vals[sidx(i)] = static_cast<uint32_t>(item_raw(src, i));
+  }
+  __syncthreads();
+  const StagedItem it{sh.vals, src.n, src.type, src.bpv};
+  uint8_t* out = L.scratch + static_cast<size_t>(blockIdx.x) * L.sec_stride;
+  const uint8_t mode = L.modes[f * ns + s];
+  uint32_t size;
+  switch (mode) {
+    case 0: size = staged_delta_section(sh, it, out); break;
+    case 2: size = staged_run_section<false>(sh, it, out); break;
+    case 3: size = staged_run_section<true>(sh, it, out); break;
+    default: size = staged_palette_section(sh, it, out); break;
   }
   if (threadIdx.x == 0) L.sec_sizes[blockIdx.x] = size;  // 0xFFFFFFFF = palette overflow, finished by the next kernel
 }
@@ -533,12 +784,29 @@ int launch_encode_sections(const Plan& plan, const SecLaunch& L, cudaStream_t st
   if (cudaFuncSetAttribute(probe_modes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess) return -1;
   if (cudaFuncSetAttribute(encode_sections_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess) return -1;
   if (cudaFuncSetAttribute(palette_overflow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess) return -1;
-  probe_modes_kernel<<<L.n_frames * plan.n_sections, kSecThreads, smem, stream>>>(L);
-  encode_sections_kernel<<<L.n_chunks_total * plan.n_sections, kSecThreads, smem, stream>>>(L);
-  palette_overflow_kernel<<<kOverflowTables, kSecThreads, smem, stream>>>(L);
-  scan_sections_kernel<<<(L.n_frames + 127) / 128, 128, 0, stream>>>(L);
-  count_launch(4);
-  return 4;
+  // fields of <= 4 bytes: the staged writers (values loaded once into shared memory); 64-bit fields: the writers that
+  // read the cloud in place. CLDN_B200_SECTIONS_STAGED=0 sends everything to the latter (bisecting aid).
+  static const bool staged_on = [] { const char* e = getenv("CLDN_B200_SECTIONS_STAGED"); return !(e && e[0] == '0'); }();
+  bool any_small = false, any_wide = false;
+  for (uint32_t s = 0; s < plan.n_sections; ++s) (plan.sections[s].bpv <= 4 ? any_small : any_wide) = true;
+  SecLaunch L2 = L;
+  L2.staged = staged_on ? 1u : 0u;
+  int launched = 3;
+  probe_modes_kernel<<<L.n_frames * plan.n_sections, kSecThreads, smem, stream>>>(L2);
+  if (staged_on && any_small) {
+    const size_t smem2 = sizeof(StagedShared) + 16;
+    if (cudaFuncSetAttribute(encode_sections_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem2)) != cudaSuccess) return -1;
+    encode_sections_staged_kernel<<<L.n_chunks_total * plan.n_sections, kSecThreads, smem2, stream>>>(L2);
+    ++launched;
+  }
+  if (!staged_on || any_wide) {
+    encode_sections_kernel<<<L.n_chunks_total * plan.n_sections, kSecThreads, smem, stream>>>(L2);
+    ++launched;
+  }
+  palette_overflow_kernel<<<kOverflowTables, kSecThreads, smem, stream>>>(L2);
+  scan_sections_kernel<<<(L.n_frames + 127) / 128, 128, 0, stream>>>(L2);
+  count_launch(launched);
+  return launched;
 }
 
 int launch_place_sections(const Plan& plan, const SecLaunch& L, const uint64_t* status, uint32_t epoch, uint32_t tile_points,
