@@ -477,21 +477,18 @@ struct StagedShared {
 };
 
 __device__ __forceinline__ uint32_t sidx(uint32_t i) { return i ^ ((i >> 5) & 31u); }
-__device__ __forceinline__ int64_t ext_value(uint32_t raw, uint8_t type) {  // ToInt64<T> for the <= 4-byte types
-  switch (type) {
-    case CLDN_INT8: return static_cast<int8_t>(raw);
-    case CLDN_INT16: return static_cast<int16_t>(raw);
-    case CLDN_INT32: return static_cast<int32_t>(raw);
-    default: return static_cast<int64_t>(raw);
-  }
-}
-
+// Signed fields are stored sign-extended to 32 bits (equal raw values stay equal, the low bpv bytes are the raw value), so
+// ToInt64<T> is one widening conversion chosen by a CTA-uniform flag instead of a switch over the field type per value.
 struct StagedItem {
   const uint32_t* vals;
   uint32_t n;
-  uint8_t type, bpv;
+  bool is_signed;
+  uint8_t bpv;
   __device__ __forceinline__ uint32_t raw(uint32_t i) const { return vals[sidx(i)]; }
-  __device__ __forceinline__ int64_t value(uint32_t i) const { return ext_value(vals[sidx(i)], type); }
+  __device__ __forceinline__ int64_t value(uint32_t i) const {
+    const uint32_t v = vals[sidx(i)];
+    return is_signed ? static_cast<int64_t>(static_cast<int32_t>(v)) : static_cast<int64_t>(v);
+  }
   __device__ __forceinline__ int64_t delta(uint32_t i) const { return value(i) - (i ? value(i - 1) : 0ll); }
 };
 
@@ -682,14 +679,19 @@ __global__ void __launch_bounds__(kSecThreads, 1) encode_sections_staged_kernel(
   const EncFrame F = L.frames[f];
   const uint32_t chunk = gc - L.chunk_first[f];
   const SecItem src = make_item(F, plan, chunk, s);
+  const bool is_signed = src.type == CLDN_INT8 || src.type == CLDN_INT16 || src.type == CLDN_INT32;
+  const uint32_t ext_shift = 32u - 8u * src.bpv;
   // the one pass over the cloud: 32 independent strided loads per thread
 #pragma unroll 8
   for (uint32_t k = 0; k < kChunkPoints / kSecThreads; ++k) {
     const uint32_t i = k * kSecThreads + threadIdx.x;
-    if (i < src.n) sh.vals[sidx(i)] = static_cast<uint32_t>(item_raw(src, i));
+    if (i < src.n) {
+      const uint32_t raw = static_cast<uint32_t>(item_raw(src, i));
+      sh.vals[sidx(i)] = is_signed ? static_cast<uint32_t>(static_cast<int32_t>(raw << ext_shift) >> ext_shift) : raw;
+    }
   }
   __syncthreads();
-  const StagedItem it{sh.vals, src.n, src.type, src.bpv};
+  const StagedItem it{sh.vals, src.n, is_signed, src.bpv};
   uint8_t* out = L.scratch + static_cast<size_t>(blockIdx.x) * L.sec_stride;
   const uint8_t mode = L.modes[f * ns + s];
   uint32_t size;
