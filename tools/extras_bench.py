@@ -3,7 +3,7 @@ runs this file in a child process with a timeout and records whatever JSON line 
 
   viz   applyVizLossyPreprocessing kernels on a device-resident 1M-point XYZI cloud: ms per call,
         survivors checked against a numpy restatement of "finite && first point of its voxel" (no oracle involved)
-  c3    BASELINE configs[2]: 1M-point XYZ + rgba u32 + ring u16 (V5 adaptive sections), 8 frames, encode / decode ms
+  c3    BASELINE configs[2]: 1M-point XYZ + rgba u32 + ring u16 (V5 adaptive sections), 32 frames, encode / decode ms
   c4    BASELINE configs[3] with the Velodyne XYZIRT layout (step 22), 64 frames of 130 048 points, encode / decode ms
   msg   the DDS converter step (parse -> profile -> viz -> compress message) on one 1M-point PointCloud2, host buffers
 """
@@ -79,7 +79,7 @@ def bench_viz(out):
 
 
 def bench_c3(out):
-    F, n = 8, 1_000_000
+    F, n = 32, 1_000_000   # 992 chunks: one per resident CTA of the chunk-sequential reader, like the headline batch
     info, _ = synth.cloud_c3(n)
     clouds = [synth.cloud_c3(n, seed=3 + k)[1] for k in range(F)]
     s = torch.cuda.Stream()

@@ -118,7 +118,7 @@ def main():
         res["workloads"].append(leg.timed()); leg.profiled(); del leg
     if want("c3"):
         info, _ = synth.cloud_c3(1_000_000)
-        leg = Leg("c3 8x1M xyz+rgba+ring step32 (V5 sections)", info, [synth.cloud_c3(1_000_000, seed=3 + k)[1] for k in range(8)])
+        leg = Leg("c3 32x1M xyz+rgba+ring step32 (V5 sections)", info, [synth.cloud_c3(1_000_000, seed=3 + k)[1] for k in range(32)])
         res["workloads"].append(leg.timed()); leg.profiled(); del leg
     if want("c4"):
         info, _ = synth.cloud_c4_mixed_frame(0)
