@@ -30,6 +30,9 @@ constexpr int kFW = kFT / 32;                // warps
 // Values 0 .. n_floatn-1 of a point are the FloatN group (int32 arithmetic, wrapping like the reference's Vector4i); the
 // rest are scalar lossy FLOAT32 fields, which the reference accumulates in int64 (field_decoder.hpp:331-353): the fast
 // reader keeps 64-bit bases for them and hands the chunk to the careful kernel if a value leaves the int32 range.
+#ifndef CLDN_FAST_DEC_MINB
+#define CLDN_FAST_DEC_MINB 7   // resident CTAs per SM the register allocation aims at (8 spills; 6 loses more than it gains: profiles/r2_variants.txt)
+#endif
 struct FastDecParams {
   float mul[6];
   uint32_t off[6];
@@ -101,7 +104,7 @@ __device__ __forceinline__ uint32_t nth_set_bit32(uint32_t m, uint32_t n, const 
 }
 
 template <int K, int FP, bool MIXED>
-__global__ void __launch_bounds__(kFT, 7) decode_floatn_fast_kernel(const DecLaunch L, const FastDecParams Q) {
+__global__ void __launch_bounds__(kFT, CLDN_FAST_DEC_MINB) decode_floatn_fast_kernel(const DecLaunch L, const FastDecParams Q) {
   constexpr int kFP = FP;
   constexpr int kFTilePts = kFT * FP;
   constexpr int kSlots = K <= 4 ? 1 : 2;                     // 16-byte staging slots per point

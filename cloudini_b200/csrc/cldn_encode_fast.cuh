@@ -21,6 +21,9 @@
 #pragma once
 
 namespace cldn {
+#ifndef CLDN_FAST_ENC_MINB
+#define CLDN_FAST_ENC_MINB 6
+#endif
 
 constexpr int kET = 128;                  // threads per CTA
 constexpr int kEW = kET / 32;
@@ -165,7 +168,7 @@ __device__ __forceinline__ void tile_coords(const EncLaunch& L, uint32_t i, uint
   }
 }
 
-__global__ void __launch_bounds__(kET, 6) encode_xyzi_fast_kernel(const EncLaunch L, const FloatNParams P) {
+__global__ void __launch_bounds__(kET, CLDN_FAST_ENC_MINB) encode_xyzi_fast_kernel(const EncLaunch L, const FloatNParams P) {
   extern __shared__ __align__(16) uint8_t dyn_smem[];
   __shared__ EncFastShared sh;
   __shared__ EncFrame s_F[2];

@@ -1,6 +1,6 @@
 #!/usr/bin/env bash
-# usage: tools/quick_bench.sh <label>   (env selects variants) — prints encode/decode ms per 32-frame step
-timeout 150 python bench.py --steps 20 --warmup 3 --no-e2e --no-extras --cpu-seconds 0.2 > /tmp/vb.out 2>&1
+# usage: tools/quick_bench.sh <label>   (env selects variants) — prints encode/decode ms per step of FRAMES (default 128) frames
+timeout 300 python bench.py --frames ${FRAMES:-128} --steps 20 --warmup 3 --no-e2e --no-extras --cpu-seconds 0.2 > /tmp/vb.out 2>&1
 tail -1 /tmp/vb.out > /tmp/vb.json
 python - "$1" <<'PY'
 import json, sys
