@@ -103,7 +103,7 @@ __device__ __forceinline__ uint32_t nth_set_bit32(uint32_t m, uint32_t n, const 
   return base + ((__ldg(&table[m & 0xFFu]) >> (4u * n)) & 7u);
 }
 
-template <int K, int FP, bool MIXED>
+template <int K, int FP, bool MIXED, bool ROWS>
 __global__ void __launch_bounds__(kFT, CLDN_FAST_DEC_MINB) decode_floatn_fast_kernel(const DecLaunch L, const FastDecParams Q) {
   constexpr int kFP = FP;
   constexpr int kFTilePts = kFT * FP;
@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(kFT, CLDN_FAST_DEC_MINB) decode_floatn_fast_ke
     // reader runs behind this kernel and overwrites its bytes), the warp builds its 32 * FP points as contiguous rows in
     // shared memory and writes them with 16-byte stores. Per-field 4-byte stores of 32 lanes touch one 32-byte sector
     // per lane and field (XYZIRT, step 22: 16 sectors per store instruction measured, 5x the row bytes through L2).
-    const bool rows = !dense4 && Q.rows != 0u && step * (32u * kFP) <= 4096u && (reinterpret_cast<uintptr_t>(out) & 15u) == 0u;
+    const bool rows = ROWS && !dense4 && Q.rows != 0u && step * (32u * kFP) <= 4096u && (reinterpret_cast<uintptr_t>(out) & 15u) == 0u;
     uint32_t row_align = step;
 #pragma unroll
     for (int f = 0; f < K; ++f) row_align |= off[f];
@@ -582,10 +582,10 @@ __global__ void __launch_bounds__(kFT, CLDN_FAST_DEC_MINB) decode_floatn_fast_ke
 
 size_t decode_fast_smem_bytes() { return static_cast<size_t>(kFWinAlloc); }
 
-template <int K, int FP, bool MIXED>
+template <int K, int FP, bool MIXED, bool ROWS>
 static int launch_fast(const FastDecParams& Q, const DecLaunch& L, int sm_count, cudaStream_t stream) {
   const size_t smem = decode_fast_smem_bytes();
-  auto k = decode_floatn_fast_kernel<K, FP, MIXED>;
+  auto k = decode_floatn_fast_kernel<K, FP, MIXED, ROWS>;
   if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess) return -1;
   int per_sm = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kFT, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
@@ -643,14 +643,20 @@ int launch_decode_fast(const Plan& plan, const DecLaunch& L, int sm_count, cudaS
   FastDecParams Q;
   if (!decode_fast_plan(plan, &Q)) return -1;
   const uint32_t nv = plan.values_per_point;
+  // whole-row copy-out is a separate instantiation: its extra live state costs the dense XYZI reader (which never needs it:
+  // one 16-byte store per point already) 4 % when it is merely a run-time branch
+  bool dense_xyzi = nv == 4 && plan.point_step == 16;
+  for (uint32_t k = 0; k < 4; ++k) dense_xyzi = dense_xyzi && Q.off[k] == 4 * k;
+  const bool rows = Q.rows != 0 && !dense_xyzi;
   if (Q.n_floatn == nv) {
-    return nv == 4 ? launch_fast<4, 8, false>(Q, L, sm_count, stream) : launch_fast<3, 8, false>(Q, L, sm_count, stream);
+    if (nv == 4) return rows ? launch_fast<4, 8, false, true>(Q, L, sm_count, stream) : launch_fast<4, 8, false, false>(Q, L, sm_count, stream);
+    return rows ? launch_fast<3, 8, false, true>(Q, L, sm_count, stream) : launch_fast<3, 8, false, false>(Q, L, sm_count, stream);
   }
   switch (nv) {
-    case 3: return launch_fast<3, 8, true>(Q, L, sm_count, stream);
-    case 4: return launch_fast<4, 8, true>(Q, L, sm_count, stream);
-    case 5: return launch_fast<5, 4, true>(Q, L, sm_count, stream);
-    default: return launch_fast<6, 4, true>(Q, L, sm_count, stream);
+    case 3: return rows ? launch_fast<3, 8, true, true>(Q, L, sm_count, stream) : launch_fast<3, 8, true, false>(Q, L, sm_count, stream);
+    case 4: return rows ? launch_fast<4, 8, true, true>(Q, L, sm_count, stream) : launch_fast<4, 8, true, false>(Q, L, sm_count, stream);
+    case 5: return rows ? launch_fast<5, 4, true, true>(Q, L, sm_count, stream) : launch_fast<5, 4, true, false>(Q, L, sm_count, stream);
+    default: return rows ? launch_fast<6, 4, true, true>(Q, L, sm_count, stream) : launch_fast<6, 4, true, false>(Q, L, sm_count, stream);
   }
 }
 
