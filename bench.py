@@ -138,16 +138,19 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-NCU_SUMMARY = "profiles/r2_final_ncu_full_summary.json"
+NCU_SUMMARY = "profiles/r2_kernels.json"
 
 
 def measured_traffic(kernel):
-    """DRAM bytes per launch of `kernel` from the committed `ncu --set full` capture (profiles/), and the batch it was taken on."""
+    """DRAM bytes per launch of `kernel` from the committed `ncu --set full` capture (profiles/r2_kernels.json, workload
+    `xyzi`: tools/kernel_tour.py, one 32-frame launch), and the batch it was taken on."""
     p = os.path.join(ROOT, NCU_SUMMARY)
     try:
-        for k in json.load(open(p)):
+        w = json.load(open(p))["workloads"]["xyzi"]
+        frames = int(w["event_timed_legs"][0]["frames"]) if w.get("event_timed_legs") else 32
+        for k in w["kernels"]:
             if kernel in k["kernel"]:
-                return float(k["dram_traffic_bytes"]), 32
+                return float(k["dram_traffic_bytes"]), frames
     except Exception:
         pass
     return None, None
@@ -489,7 +492,7 @@ def main():
             "roofline": {"bound": "hbm", "kernel": "decode_floatn_fast_kernel<4> (terminator ranking + varint reader + un-zigzag + per-field prefix sums + dequantise)",
                          "achieved": dec_achieved, "peak": peak, "unit": "GB/s", "frac": dec_achieved / peak,
                          "traffic": dec_traffic, "share_of_step": dec_ms / (enc_ms + dec_ms),
-                         "traffic_source": NCU_SUMMARY + " (ncu --set full, dram__bytes_read+write, one 32-frame launch, scaled by frames)",
+                         "traffic_source": NCU_SUMMARY + " (ncu --set full, dram__bytes_read+write of one 32-frame launch, scaled to this batch)",
                          "chunks_fast_reader": fast_chunks, "chunks_careful_reader": redo_chunks,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": algo_bytes, "launch_ms": dec_ms,
                          "encode": {"kernel": "encode_xyzi_fast_kernel (quantise + delta + zigzag varint + pack, persistent CTAs)", "achieved": achieved,

@@ -10,6 +10,10 @@ timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -8 > $OUT/pytest.txt
 cat $OUT/pytest.txt
 timeout 900 python bench.py ${BENCH_ARGS:-} > $OUT/bench.json 2> $OUT/bench.err
 tail -c 1500 $OUT/bench.json
+timeout 600 python bench.py --frames 32 --steps 100 --warmup 5 --no-e2e --no-extras > $OUT/bench_f32.json 2> $OUT/bench_f32.err
+tail -c 600 $OUT/bench_f32.json
+timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/bench_reference.json 2> $OUT/bench_reference.err
+tail -c 800 $OUT/bench_reference.json
 timeout 900 python tools/config4_bench.py --frames ${C4_FRAMES:-1000} > $OUT/config4.json 2> $OUT/config4.err
 cat $OUT/config4.json; tail -3 $OUT/config4.err
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches_bench.csv \
