@@ -732,7 +732,7 @@ static int encode_batch_impl(cldn_encoder_t* e, size_t n_frames, const void* con
       size_t cap1 = max_compressed_size(e->info, n, false, &ok);
       if (int rc = e->d_in.reserve(cloud_bytes[f] + 256)) return rc;
       if (int rc = e->d_out.reserve(cap1 + 256)) return rc;
-      if (copy_h2d(e->d_in.p, clouds[f], cloud_bytes[f], e->stream)) { set_error("upload failed"); return CLDN_ERR_CUDA; }
+      if (cloud_bytes[f]) CUDA_TRY(cudaMemcpyAsync(e->d_in.p, clouds[f], cloud_bytes[f], cudaMemcpyHostToDevice, e->stream));
       const void* din = e->d_in.p;
       void* dout = e->d_out.p;
       if (int rc = encode_batch_device(e, 1, &din, &cloud_bytes[f], &dout, &cap1, 0)) return rc;
@@ -742,8 +742,7 @@ static int encode_batch_impl(cldn_encoder_t* e, size_t n_frames, const void* con
       const size_t s1 = static_cast<size_t>(e->h_sizes.p[0]);
       if (s1 > cap1) { set_error("Output buffer too small for uncompressed chunk"); return CLDN_ERR_BUFFER_TOO_SMALL; }
       e->s2_tmp.resize(s1 + 16);
-      if (copy_d2h(e->s2_tmp.data(), e->d_out.p, s1, e->stream)) { set_error("download failed"); return CLDN_ERR_CUDA; }
-      CUDA_TRY(cudaStreamSynchronize(e->stream));
+      if (s1) CUDA_TRY(cudaMemcpy(e->s2_tmp.data(), e->d_out.p, s1, cudaMemcpyDeviceToHost));
       uint8_t* out = static_cast<uint8_t*>(outs[f]);
       if (hdr) memcpy(out, e->header.data(), hdr);
       size_t w = 0;
@@ -795,7 +794,7 @@ static int encode_batch_impl(cldn_encoder_t* e, size_t n_frames, const void* con
   for (size_t f = 0; f < n_frames; ++f) {
     const void* din = e->d_in.p + in_off[f];
     void* dout = e->d_out.p + out_off[f];
-    if (copy_h2d(e->d_in.p + in_off[f], clouds[f], cloud_bytes[f], e->pipe.h2d)) { set_error("upload failed"); return CLDN_ERR_CUDA; }
+    if (cloud_bytes[f]) CUDA_TRY(cudaMemcpyAsync(e->d_in.p + in_off[f], clouds[f], cloud_bytes[f], cudaMemcpyHostToDevice, e->pipe.h2d));
     CUDA_TRY(cudaEventRecord(e->pipe.ev[2 * f], e->pipe.h2d));
     CUDA_TRY(cudaStreamWaitEvent(e->stream, e->pipe.ev[2 * f], 0));
     if (int rc = encode_batch_device(e, 1, &din, &cloud_bytes[f], &dout, &caps[f], write_header)) return rc;
@@ -811,7 +810,7 @@ static int encode_batch_impl(cldn_encoder_t* e, size_t n_frames, const void* con
       set_error("Output buffer too small for uncompressed chunk");
       return CLDN_ERR_BUFFER_TOO_SMALL;
     }
-    if (copy_d2h(outs[f], e->d_out.p + out_off[f], sz, e->pipe.d2h)) { set_error("download failed"); return CLDN_ERR_CUDA; }
+    if (sz) CUDA_TRY(cudaMemcpyAsync(outs[f], e->d_out.p + out_off[f], sz, cudaMemcpyDeviceToHost, e->pipe.d2h));
     if (written_host) written_host[f] = sz;
   }
   CUDA_TRY(cudaStreamSynchronize(e->pipe.d2h));
@@ -1262,19 +1261,15 @@ static int decode_batch_impl(cldn_decoder_t* d, const cldn_info_t* info, size_t 
   for (size_t f = 0; f < n_frames; ++f) {
     const void* din = d->d_in.p + in_off[f];
     void* dout = d->d_out.p + out_stride * f;
-    if (copy_h2d(d->d_in.p + in_off[f], payloads[f], payload_bytes[f], d->pipe.h2d)) { set_error("upload failed"); return CLDN_ERR_CUDA; }
+    if (payload_bytes[f]) CUDA_TRY(cudaMemcpyAsync(d->d_in.p + in_off[f], payloads[f], payload_bytes[f], cudaMemcpyHostToDevice, d->pipe.h2d));
     // only declared field bytes are written by the decoder: keep the caller's padding bytes intact
-    if (d->has_padding && copy_h2d(dout, outs[f], out_need, d->pipe.h2d)) { set_error("upload failed"); return CLDN_ERR_CUDA; }
+    if (d->has_padding && out_need) CUDA_TRY(cudaMemcpyAsync(dout, outs[f], out_need, cudaMemcpyHostToDevice, d->pipe.h2d));
     CUDA_TRY(cudaEventRecord(d->pipe.ev[2 * f], d->pipe.h2d));
     CUDA_TRY(cudaStreamWaitEvent(d->stream, d->pipe.ev[2 * f], 0));
     if (int rc = decode_batch_device(d, *info, 1, &din, &payload_bytes[f], &dout, &out_need)) return rc;
     CUDA_TRY(cudaEventRecord(d->pipe.ev[2 * f + 1], d->stream));
     CUDA_TRY(cudaStreamWaitEvent(d->pipe.d2h, d->pipe.ev[2 * f + 1], 0));
-  }
-  // downloads in a second loop: into pageable memory they are staged by this thread (cldn_stage.cpp) and would otherwise
-  // hold back the uploads of the following frames; into pinned memory they are plain asynchronous copies either way
-  for (size_t f = 0; f < n_frames; ++f) {
-    if (copy_d2h(outs[f], d->d_out.p + out_stride * f, out_need, d->pipe.d2h)) { set_error("download failed"); return CLDN_ERR_CUDA; }
+    if (out_need) CUDA_TRY(cudaMemcpyAsync(outs[f], dout, out_need, cudaMemcpyDeviceToHost, d->pipe.d2h));
   }
   CUDA_TRY(cudaStreamSynchronize(d->pipe.d2h));
   // a failed decode must not hand back garbage silently: the error word is checked after everything has drained

@@ -122,13 +122,6 @@ size_t palette_overflow_scratch_bytes();
 int launch_place_sections(const Plan& host_plan, const SecLaunch& L, const uint64_t* status, uint32_t epoch,
                           uint32_t tile_points, cudaStream_t stream);
 
-// ---- host <-> device copies of caller buffers (cldn_stage.cpp): pageable memory is staged through a pinned ring by a few
-//      copy threads, pinned memory goes straight to cudaMemcpyAsync. Return 0 or -1 (CUDA error).
-int copy_h2d(void* dst_dev, const void* src_host, size_t bytes, cudaStream_t s);  // returns once the source is consumed
-int copy_d2h(void* dst_host, const void* src_dev, size_t bytes, cudaStream_t s);  // pageable: destination complete on return;
-                                                                                 // pinned: asynchronous on `s` like cudaMemcpyAsync
-bool host_is_pageable(const void* p);
-
 // ---- stage 2 on the device (LZ4 blocks per chunk; cldn_lz4.cu) ----------------------------------------------------------
 struct Lz4Frame {
   // compress: stage-1 payload of the frame ([u32 size][bytes])*, its byte count (device word written by the stage-1

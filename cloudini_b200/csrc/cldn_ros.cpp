@@ -13,7 +13,6 @@
 #include <vector>
 
 #include "../../include/cloudini_b200_ros.h"
-#include "cldn_kernels.h"
 #include "cldn_plan.h"
 
 using cldn::set_error;
@@ -412,7 +411,7 @@ extern "C" int cldn_b200_ros_convert_msg(const void* dds_msg, size_t msg_bytes, 
   }
   // ---- device-resident: one upload, kernels, one download ----
   if (!HandlePool::grow(&P.d_in, &P.cap_in, m.data_bytes)) { set_error("cudaMalloc failed"); return CLDN_ERR_CUDA; }
-  if (cldn::copy_h2d(P.d_in, m.data, m.data_bytes, P.stream)) { set_error("upload failed"); return CLDN_ERR_CUDA; }
+  if (cudaMemcpyAsync(P.d_in, m.data, m.data_bytes, cudaMemcpyHostToDevice, P.stream) != cudaSuccess) { set_error("upload failed"); return CLDN_ERR_CUDA; }
   const uint8_t* d_cloud = P.d_in;
   size_t n_points = points_in;
   if (viz) {
@@ -442,7 +441,7 @@ extern "C" int cldn_b200_ros_convert_msg(const void* dds_msg, size_t msg_bytes, 
   const size_t size_at = w.buf.size() - 4, prev = w.buf.size();
   uint8_t* o = static_cast<uint8_t*>(out);
   memcpy(o, w.buf.data(), prev);
-  if (cldn::copy_d2h(o + prev, P.d_blob, blob, P.stream) || cudaStreamSynchronize(P.stream) != cudaSuccess) {
+  if (cudaMemcpyAsync(o + prev, P.d_blob, blob, cudaMemcpyDeviceToHost, P.stream) != cudaSuccess || cudaStreamSynchronize(P.stream) != cudaSuccess) {
     set_error("download failed");
     return CLDN_ERR_CUDA;
   }

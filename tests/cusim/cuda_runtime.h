@@ -300,13 +300,6 @@ static inline cudaError_t cudaMallocHost(void** p, size_t n) {
   return cudaSuccess;
 }
 template <class T> static inline cudaError_t cudaMallocHost(T** p, size_t n) { return cudaMallocHost(reinterpret_cast<void**>(p), n); }
-// what kind of memory a pointer is: the emulation has no registered host memory, every host pointer is "pageable"
-enum cudaMemoryType { cudaMemoryTypeUnregistered = 0, cudaMemoryTypeHost = 1, cudaMemoryTypeDevice = 2, cudaMemoryTypeManaged = 3 };
-struct cudaPointerAttributes { cudaMemoryType type; int device; void* devicePointer; void* hostPointer; };
-static inline cudaError_t cudaPointerGetAttributes(cudaPointerAttributes* a, const void*) {
-  a->type = cudaMemoryTypeUnregistered; a->device = 0; a->devicePointer = nullptr; a->hostPointer = nullptr;
-  return cudaSuccess;
-}
 static inline cudaError_t cudaFreeHost(void* p) { ::cusim::flush_d2h(nullptr, true); free(p); return cudaSuccess; }
 static inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { ::cusim::DeviceAccess da; if (n) memmove(d, s, n); return cudaSuccess; }
 static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind kind, cudaStream_t stream = nullptr) {
