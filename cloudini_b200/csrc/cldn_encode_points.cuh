@@ -253,7 +253,10 @@ static uint32_t encode_points_values(const Plan& plan) {
   for (uint32_t i = 0; i < plan.n_ops; ++i) nv += plan.ops[i].kind == OP_FLOATN ? plan.ops[i].lanes : 1u;
   return nv;
 }
-static uint32_t encode_points_tile(const Plan& plan) { return encode_points_values(plan) <= 4 ? kPT * 8 : kPT * 4; }
+#ifndef CLDN_POINTS_EP_WIDE
+#define CLDN_POINTS_EP_WIDE 4   // points per thread for 5 / 6 values per point (8: 40-48 values in registers)
+#endif
+static uint32_t encode_points_tile(const Plan& plan) { return encode_points_values(plan) <= 4 ? kPT * 8 : kPT * CLDN_POINTS_EP_WIDE; }
 
 template <int NV, int EP>
 static int launch_points_nv(const Plan& plan, const EncLaunch& L, const PointsParams& P, cudaStream_t stream) {
@@ -283,8 +286,8 @@ static int launch_encode_points(const Plan& plan, const EncLaunch& L, const Poin
   switch (encode_points_values(plan)) {
     case 3: return launch_points_nv<3, 8>(plan, L, P, stream);
     case 4: return launch_points_nv<4, 8>(plan, L, P, stream);
-    case 5: return launch_points_nv<5, 4>(plan, L, P, stream);
-    default: return launch_points_nv<6, 4>(plan, L, P, stream);
+    case 5: return launch_points_nv<5, CLDN_POINTS_EP_WIDE>(plan, L, P, stream);
+    default: return launch_points_nv<6, CLDN_POINTS_EP_WIDE>(plan, L, P, stream);
   }
 }
 

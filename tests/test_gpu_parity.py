@@ -728,3 +728,14 @@ def test_reference_sample_files(oracle):
             out = np.zeros(cloud.size, dtype=np.uint8)
             cb.PointcloudDecoder().decode(cb.DecodeHeader(blob)[0], blob[cb.DecodeHeader(blob)[1]:], out)
             assert (len(blob), "%016x" % synth.fnv1a64(blob), "%016x" % synth.fnv1a64(out)) == (size, blob_hash, decoded_hash), (name, version)
+
+
+def test_large_pageable_host_buffers(oracle):
+    """Large pageable caller buffers through the host-pointer API: clouds, blobs and padded outputs (which are uploaded
+    too, to keep the caller's padding bytes) arrive intact."""
+    n = 1_200_003
+    info, cloud = synth.cloud_c2(n, seed=77)                       # 19.2 MB in, ~9 MB blob
+    _roundtrip_check(info, cloud, oracle)
+    n3 = 450_001
+    info3, cloud3 = synth.cloud_c3(n3, seed=78)                    # 14.4 MB, padded layout: the output is uploaded first
+    _roundtrip_check(info3, cloud3, oracle, fill=0x3C)
