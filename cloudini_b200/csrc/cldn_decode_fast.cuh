@@ -30,6 +30,12 @@ constexpr int kFW = kFT / 32;                // warps
 // Values 0 .. n_floatn-1 of a point are the FloatN group (int32 arithmetic, wrapping like the reference's Vector4i); the
 // rest are scalar lossy FLOAT32 fields, which the reference accumulates in int64 (field_decoder.hpp:331-353): the fast
 // reader keeps 64-bit bases for them and hands the chunk to the careful kernel if a value leaves the int32 range.
+#ifndef CLDN_FAST_DEC_CPASYNC
+#define CLDN_FAST_DEC_CPASYNC 0
+#endif
+#ifndef CLDN_FAST_DEC_ROLLING
+#define CLDN_FAST_DEC_ROLLING 1
+#endif
 #ifndef CLDN_FAST_DEC_MINB
 #define CLDN_FAST_DEC_MINB 7   // resident CTAs per SM the register allocation aims at (8 spills; 6 loses more than it gains: profiles/r2_variants.txt)
 #endif
@@ -228,6 +234,16 @@ __global__ void __launch_bounds__(kFT, CLDN_FAST_DEC_MINB) decode_floatn_fast_ke
         const uint4* gv = reinterpret_cast<const uint4*>(abase) + threadIdx.x;
         uint4* sv = reinterpret_cast<uint4*>(win + kFLead) + threadIdx.x;
         if (v_lo == 0u && v_hi == n_vec) {
+#if CLDN_FAST_DEC_CPASYNC
+          // the whole window lies inside the payload (every tile but the first / last few of a frame): cp.async, global ->
+          // shared without the register round trip, every request of the thread in flight at once
+#pragma unroll
+          for (int r = 0; r < kFMaxUnits; ++r) {
+            if (r < static_cast<int>(nu)) async_copy16(sv + r * kFT, gv + r * kFT);
+          }
+          async_commit();
+          async_wait_all();
+#else
           // the whole window lies inside the payload (every tile but the first / last few of a frame): plain loads, all of
           // a thread's requests in flight before the first store
 #pragma unroll
@@ -244,6 +260,7 @@ __global__ void __launch_bounds__(kFT, CLDN_FAST_DEC_MINB) decode_floatn_fast_ke
               }
             }
           }
+#endif
         } else {
 #pragma unroll 1
           for (uint32_t r = 0; r < nu; ++r) {
@@ -342,17 +359,36 @@ __global__ void __launch_bounds__(kFT, CLDN_FAST_DEC_MINB) decode_floatn_fast_ke
 #pragma unroll
         for (int f = 0; f < K; ++f) acc[f] = 0;
         const uint32_t* win32 = reinterpret_cast<const uint32_t*>(win);
+#if CLDN_FAST_DEC_ROLLING
+        // rolling 64-bit window: the shared-memory loads follow the WORD index, which only ever steps by one, so the next
+        // word is in a register before it is needed and no load sits on the value-to-value dependency chain
+        constexpr uint32_t kLastWord = (kFWinAlloc >> 2) - 1;
+        uint32_t wi = pb >> 5;
+        uint32_t lo = win32[wi], hi = win32[wi + 1], nx = win32[min(wi + 2u, kLastWord)];
+#endif
 #pragma unroll
         for (int j = 0; j < kFP; ++j) {
 #pragma unroll
           for (int f = 0; f < K; ++f) {
+#if CLDN_FAST_DEC_ROLLING
+            const uint32_t w = __funnelshift_r(lo, hi, pb);                    // the 4 bytes at the bit position pb
+#else
             const uint32_t wi = pb >> 5;
             const uint32_t w = __funnelshift_r(win32[wi], win32[wi + 1], pb);  // the 4 bytes at the bit position pb
+#endif
             const uint32_t t = ~w & 0x80808080u;                               // terminators among them
             const uint32_t msk = t ^ (t - 1u);                                 // everything up to the first one (all if none)
             uint32_t x = w & 0x7F7F7F7Fu & msk;                                // the value's payload bits
             trk = min3_u32(trk, t, x);                                         // 0 <=> no terminator in 4 bytes, or a zero value
             pb += __popc(msk);
+#if CLDN_FAST_DEC_ROLLING
+            if ((pb >> 5) != wi) {                                             // a value is at most 32 bits: one word step at most
+              ++wi;
+              lo = hi;
+              hi = nx;
+              nx = win32[min(wi + 2u, kLastWord)];
+            }
+#endif
             x = x - ((x >> 1) & 0x3F803F80u);                                  // 7-bit groups -> 14-bit groups
             const uint32_t z = bitselect(0x3FFFu, x, x >> 2);                  // -> uval = zigzag + 1 (28 bits)
             // un-zigzag of z - 1: odd z -> +(z >> 1), even z -> -(z >> 1); bit 0 of z is bit 0 of the window

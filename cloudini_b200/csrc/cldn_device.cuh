@@ -364,6 +364,30 @@ __device__ __forceinline__ uint32_t block_exclusive_scan_n(uint32_t v, uint32_t*
   return before + inc - v;
 }
 
+// cp.async (LDGSTS): 16 bytes global -> shared without a register round trip; groups complete in commit order
+__device__ __forceinline__ void async_copy16(void* smem_dst, const void* gmem_src) {
+#ifdef CLDN_CUSIM
+  *reinterpret_cast<uint4*>(smem_dst) = *reinterpret_cast<const uint4*>(gmem_src);
+#else
+  const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+#endif
+}
+__device__ __forceinline__ void async_commit() {
+#ifndef CLDN_CUSIM
+  asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void async_wait_all_but_last() {
+#ifndef CLDN_CUSIM
+  asm volatile("cp.async.wait_group 1;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void async_wait_all() {
+#ifndef CLDN_CUSIM
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+#endif
+}
 // ---- tile status word for the decoupled look-back ---------------------------------------------------------------
 // [63:62] flag (0 = invalid, 1 = tile aggregate, 2 = inclusive prefix)   [61:40] launch epoch   [39:0] byte count
 constexpr uint64_t kFlagAgg = 1ull, kFlagIncl = 2ull;

@@ -40,30 +40,6 @@ struct EncFastShared {
   uint32_t scan[kET / 32 + 1];
 };
 
-// cp.async (LDGSTS): 16 bytes global -> shared without a register round trip; groups complete in commit order
-__device__ __forceinline__ void async_copy16(void* smem_dst, const void* gmem_src) {
-#ifdef CLDN_CUSIM
-  *reinterpret_cast<uint4*>(smem_dst) = *reinterpret_cast<const uint4*>(gmem_src);
-#else
-  const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
-#endif
-}
-__device__ __forceinline__ void async_commit() {
-#ifndef CLDN_CUSIM
-  asm volatile("cp.async.commit_group;" ::: "memory");
-#endif
-}
-__device__ __forceinline__ void async_wait_all_but_last() {
-#ifndef CLDN_CUSIM
-  asm volatile("cp.async.wait_group 1;" ::: "memory");
-#endif
-}
-__device__ __forceinline__ void async_wait_all() {
-#ifndef CLDN_CUSIM
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
-#endif
-}
 __device__ __forceinline__ float max_nan(float a, float b) {  // NaN if either is NaN (fmaxf would drop it)
   float d;
   asm("max.NaN.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b));
