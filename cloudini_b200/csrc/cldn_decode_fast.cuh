@@ -30,6 +30,9 @@ constexpr int kFW = kFT / 32;                // warps
 // Values 0 .. n_floatn-1 of a point are the FloatN group (int32 arithmetic, wrapping like the reference's Vector4i); the
 // rest are scalar lossy FLOAT32 fields, which the reference accumulates in int64 (field_decoder.hpp:331-353): the fast
 // reader keeps 64-bit bases for them and hands the chunk to the careful kernel if a value leaves the int32 range.
+#ifndef CLDN_FAST_DEC_DIRECT
+#define CLDN_FAST_DEC_DIRECT 1   // dense XYZI: floats leave from registers, the next tile's window is requested early
+#endif
 #ifndef CLDN_FAST_DEC_CPASYNC
 #define CLDN_FAST_DEC_CPASYNC 1   // window staging by cp.async: 1.101 -> 1.049 ms per 128 frames (plain loads + stores: 0)
 #endif
@@ -205,6 +208,13 @@ __global__ void __launch_bounds__(kFT, CLDN_FAST_DEC_MINB) decode_floatn_fast_ke
     for (int f = 0; f < K; ++f) { carry[f] = 0; if (MIXED) carry64[f] = 0; }
     uint32_t cursor = 0;                      // stream byte offset of the next tile's first value
     uint32_t est = 0;                         // bytes of the previous tile (0: none yet)
+    // Dense XYZI (one 16-byte store per point): a thread's 8 consecutive points leave straight from its registers, 16
+    // bytes each. Nothing aliases the window then, so once every thread has parsed (the any_bad barrier) the NEXT tile's
+    // window is requested with cp.async and lands while this tile is summed, converted and stored; the barrier that
+    // separated the staged copy-out from the next staging is gone.
+    const bool direct = CLDN_FAST_DEC_DIRECT && CLDN_FAST_DEC_CPASYNC && K == 4 && !MIXED && !ROWS && dense4;
+    bool pre = false;                         // the next tile's window has been requested ...
+    uint32_t pre_nu = 0;                      // ... with this many units per thread
     bool redo = (size == 0u);                 // an empty body cannot hold n_points > 0 points: the careful kernel reports it
     for (uint32_t pt0 = 0; pt0 < n_points && !redo; pt0 += kFTilePts) {
       const uint32_t tile_pts = min(static_cast<uint32_t>(kFTilePts), n_points - pt0);
@@ -220,6 +230,7 @@ __global__ void __launch_bounds__(kFT, CLDN_FAST_DEC_MINB) decode_floatn_fast_ke
       uint32_t nu = (want + (kFT * kFUnit - 1)) / (kFT * kFUnit);
       nu = nu < 3u ? 3u : (nu | 1u);
       if (nu > kFMaxUnits) nu = kFMaxUnits;
+      if (pre) nu = pre_nu;
       uint32_t m[kFMaskWords];
       uint32_t total, incl, cnt;
       while (true) {
@@ -233,7 +244,10 @@ __global__ void __launch_bounds__(kFT, CLDN_FAST_DEC_MINB) decode_floatn_fast_ke
         const uint32_t v_hi = room < n_vec ? static_cast<uint32_t>(room) : n_vec;
         const uint4* gv = reinterpret_cast<const uint4*>(abase) + threadIdx.x;
         uint4* sv = reinterpret_cast<uint4*>(win + kFLead) + threadIdx.x;
-        if (v_lo == 0u && v_hi == n_vec) {
+        if (pre) {
+          async_wait_all();   // requested behind the previous tile's parse
+          pre = false;
+        } else if (v_lo == 0u && v_hi == n_vec) {
 #if CLDN_FAST_DEC_CPASYNC
           // the whole window lies inside the payload (every tile but the first / last few of a frame): cp.async, global ->
           // shared without the register round trip, every request of the thread in flight at once
@@ -477,6 +491,47 @@ __global__ void __launch_bounds__(kFT, CLDN_FAST_DEC_MINB) decode_floatn_fast_ke
       }
       const uint32_t ncur = sh.next_cursor;
       const uint32_t used = ncur - (kFLead + c0);
+      if (direct) {
+        // ---- request the next tile's window (same sizing rule as the loop head, est = used) ----
+        if (pt0 + kFTilePts < n_points) {
+          const uint32_t ncursor = cursor + used;
+          const uint8_t* nfirst = body + ncursor;
+          const uint32_t nc0 = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(nfirst) & 15u);
+          const uint8_t* nab = nfirst - nc0;
+          uint32_t nnu = (nc0 + used + (used >> 3) + 96u + (kFT * kFUnit - 1)) / (kFT * kFUnit);
+          nnu = nnu < 3u ? 3u : (nnu | 1u);
+          if (nnu > kFMaxUnits) nnu = kFMaxUnits;
+          if (ncursor < size && nab >= sh.pay_lo && (static_cast<uint64_t>(sh.pay_hi - nab) >> 4) >= nnu * kFT) {
+            const uint4* gv = reinterpret_cast<const uint4*>(nab) + threadIdx.x;
+            uint4* sv = reinterpret_cast<uint4*>(win + kFLead) + threadIdx.x;
+#pragma unroll
+            for (int r = 0; r < kFMaxUnits; ++r) {
+              if (r < static_cast<int>(nnu)) async_copy16(sv + r * kFT, gv + r * kFT);
+            }
+            async_commit();
+            pre = true;
+            pre_nu = nnu;
+          }
+          // ... and the tile after it into L2
+          const uint32_t ahead = ncursor + used + threadIdx.x * 128u;
+          if (ahead < size && threadIdx.x * 128u < used + (used >> 2) + 256u) prefetch_l2(body + ahead);
+        }
+        // ---- my points, 16 bytes each, straight from the registers ----
+        uint8_t* dst = out + static_cast<size_t>(pt0 + threadIdx.x * kFP) * 16u;
+#pragma unroll
+        for (int j = 0; j < kFP; ++j) {
+          uint32_t fl[4];
+#pragma unroll
+          for (int f = 0; f < 4; ++f) {
+            const int32_t v = static_cast<int32_t>(static_cast<uint32_t>(base[f < K ? f : 0]) + static_cast<uint32_t>(P[j][f < K ? f : 0]));
+            fl[f] = __float_as_uint(__fmul_rn(__int2float_rn(v), mul[f < K ? f : 0]));
+          }
+          if (static_cast<uint32_t>(j) < my_pts) __stcs(reinterpret_cast<uint4*>(dst + 16 * j), make_uint4(fl[0], fl[1], fl[2], fl[3]));
+        }
+        est = used;
+        cursor += used;
+        continue;   // no barrier: the next staging waits for its own copies, and nothing of this tile lives in shared memory
+      }
       // the next tile's bytes are asked into L2 now (its loads are issued behind this tile's conversion and copy-out)
       if (pt0 + kFTilePts < n_points) {
         const uint32_t ahead = cursor + used + threadIdx.x * 128u;
@@ -605,6 +660,7 @@ __global__ void __launch_bounds__(kFT, CLDN_FAST_DEC_MINB) decode_floatn_fast_ke
         __syncthreads();
       }
     }
+    if (pre) { async_wait_all(); pre = false; }   // (a tile loop left early with a window still in flight)
     if (redo) {
       if (threadIdx.x == 0) {
         L.redo_list[atomicAdd(L.chunk_counter + 3, 1u)] = gc;
