@@ -33,6 +33,9 @@ constexpr int kFW = kFT / 32;                // warps
 #ifndef CLDN_FAST_DEC_DIRECT
 #define CLDN_FAST_DEC_DIRECT 0   // 1 = dense XYZI stores its floats straight from registers and requests the next window early: measured 1.29 vs 1.05 ms per 128 frames (32 lanes x 16 B at a 128-byte stride per store instruction)
 #endif
+#ifndef CLDN_FAST_DEC_SPLIT
+#define CLDN_FAST_DEC_SPLIT 1   // <= 4 values per point: float staging in its own 8 KB (two half passes), next window requested early
+#endif
 #ifndef CLDN_FAST_DEC_CPASYNC
 #define CLDN_FAST_DEC_CPASYNC 1   // window staging by cp.async: 1.101 -> 1.049 ms per 128 frames (plain loads + stores: 0)
 #endif
@@ -49,12 +52,14 @@ struct FastDecParams {
   uint32_t rows;   // the regular fields and the V5 section fields together cover every byte of a point: whole rows may be written
 };
 constexpr int kFUnit = 16;                   // bytes per unit: a thread's slice of the window is `nu` units (nu odd: the
-constexpr int kFMaxUnits = 11;               //   16-byte reads of a warp are then conflict-free at any count)
+constexpr int kFMaxUnits = 9;                //   16-byte reads of a warp are then conflict-free at any count); 18 KB = 18 B per point
 constexpr int kFLead = 16;                   // bytes in front of the window (never read as data; keeps indices > 0)
-constexpr int kFWinBytes = kFMaxUnits * kFT * kFUnit;   // 22528
+constexpr int kFWinBytes = kFMaxUnits * kFT * kFUnit;   // 18432
 constexpr int kFWinAlloc = kFLead + kFWinBytes + 32;    // reads run at most 7 bytes past a value's last byte
-constexpr int kFMaskWords = (kFMaxUnits * kFUnit + 31) / 32; // 6 words of terminator bits per thread
+constexpr int kFMaskWords = (kFMaxUnits * kFUnit + 31) / 32; // 5 words of terminator bits per thread
 static_assert(kFT * 8 * 16 <= kFWinAlloc, "the float staging aliases the window");
+constexpr int kFOut2Off = (kFWinAlloc + 15) & ~15;      // split staging (SPLIT): 4 slots per lane, private to each warp, behind the window
+constexpr int kFOut2Bytes = kFT * 4 * 16;               // 8 KB
 
 struct FastShared {
   uint32_t wcnt[kFW];                 // terminators per warp
@@ -117,6 +122,7 @@ __global__ void __launch_bounds__(kFT, CLDN_FAST_DEC_MINB) decode_floatn_fast_ke
   constexpr int kFP = FP;
   constexpr int kFTilePts = kFT * FP;
   constexpr int kSlots = K <= 4 ? 1 : 2;                     // 16-byte staging slots per point
+  constexpr bool kSplit = CLDN_FAST_DEC_SPLIT && CLDN_FAST_DEC_CPASYNC && K <= 4 && FP == 8 && !ROWS;
   extern __shared__ __align__(16) uint8_t dyn_smem[];
   __shared__ FastShared sh;
   uint8_t* win = dyn_smem;                                    // kFLead + window bytes
@@ -491,8 +497,9 @@ __global__ void __launch_bounds__(kFT, CLDN_FAST_DEC_MINB) decode_floatn_fast_ke
       }
       const uint32_t ncur = sh.next_cursor;
       const uint32_t used = ncur - (kFLead + c0);
-      if (direct) {
-        // ---- request the next tile's window (same sizing rule as the loop head, est = used) ----
+      if (direct || kSplit) {
+        // ---- request the next tile's window (same sizing rule as the loop head, est = used): every thread has parsed, and
+        //      neither variant stages its floats inside the window ----
         if (pt0 + kFTilePts < n_points) {
           const uint32_t ncursor = cursor + used;
           const uint8_t* nfirst = body + ncursor;
@@ -516,6 +523,8 @@ __global__ void __launch_bounds__(kFT, CLDN_FAST_DEC_MINB) decode_floatn_fast_ke
           const uint32_t ahead = ncursor + used + threadIdx.x * 128u;
           if (ahead < size && threadIdx.x * 128u < used + (used >> 2) + 256u) prefetch_l2(body + ahead);
         }
+      }
+      if (direct) {
         // ---- my points, 16 bytes each, straight from the registers ----
         uint8_t* dst = out + static_cast<size_t>(pt0 + threadIdx.x * kFP) * 16u;
 #pragma unroll
@@ -531,6 +540,65 @@ __global__ void __launch_bounds__(kFT, CLDN_FAST_DEC_MINB) decode_floatn_fast_ke
         est = used;
         cursor += used;
         continue;   // no barrier: the next staging waits for its own copies, and nothing of this tile lives in shared memory
+      }
+      if (kSplit) {
+        // ---- two half passes through 4 private slots per lane: lane l stages its points 4 h .. 4 h + 3, then lanes 4 m .. 4 m + 3
+        //      store the four consecutive points of owner lane 8 i + m (64 contiguous bytes for XYZI: full sectors) ----
+        uint4* wst2 = reinterpret_cast<uint4*>(dyn_smem + kFOut2Off) + warp * (32 * 4);
+        const uint32_t wp0 = pt0 + warp * (32 * kFP);
+        const uint32_t wn = wp0 < n_points ? min(static_cast<uint32_t>(32 * kFP), n_points - wp0) : 0u;
+        const uint32_t sw = (static_cast<uint32_t>(lane) >> 1) & 3u;
+        bool wide = false;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            const int j = 4 * h + jj;
+            uint32_t fl[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+            for (int f = 0; f < K; ++f) {
+              int32_t v = static_cast<int32_t>(static_cast<uint32_t>(base[f]) + static_cast<uint32_t>(P[j][f]));
+              if (MIXED && static_cast<uint32_t>(f) >= n_floatn) {
+                const long long v64 = base64[f] + P[j][f];
+                v = static_cast<int32_t>(v64);
+                wide = wide || (v64 != static_cast<long long>(v));
+              }
+              fl[f] = __float_as_uint(__fmul_rn(__int2float_rn(v), mul[f]));
+            }
+            wst2[4 * lane + (static_cast<uint32_t>(jj) ^ sw)] = make_uint4(fl[0], fl[1], fl[2], fl[3]);
+          }
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const uint32_t o = 8u * i + (static_cast<uint32_t>(lane) >> 2), jj = static_cast<uint32_t>(lane) & 3u;
+            const uint32_t q = 8u * o + 4u * h + jj;                     // point of the warp's 256
+            if (q < wn) {
+              const uint4 v = wst2[4 * o + (jj ^ ((o >> 1) & 3u))];
+              uint8_t* dst = out + static_cast<size_t>(wp0 + q) * step;
+              if (dense4) {
+                __stcs(reinterpret_cast<uint4*>(dst), v);
+              } else {
+                const uint32_t vv[4] = {v.x, v.y, v.z, v.w};
+                if (aligned4) {
+#pragma unroll
+                  for (int f = 0; f < K; ++f) __stcs(reinterpret_cast<unsigned int*>(dst + off[f]), vv[f]);
+                } else {
+#pragma unroll
+                  for (int f = 0; f < K; ++f) {
+                    if (off[f] != CLDN_SKIP_STORE_OFFSET) store_u32(dst + off[f], vv[f]);
+                  }
+                }
+              }
+            }
+          }
+          __syncwarp();
+        }
+        est = used;
+        cursor += used;
+        if (MIXED) {
+          if (__syncthreads_or(wide ? 1 : 0)) { redo = true; break; }
+        }
+        continue;   // (plain float plans: no CTA barrier here -- the staging is private to the warp, the window is not touched)
       }
       // the next tile's bytes are asked into L2 now (its loads are issued behind this tile's conversion and copy-out)
       if (pt0 + kFTilePts < n_points) {
@@ -672,7 +740,7 @@ __global__ void __launch_bounds__(kFT, CLDN_FAST_DEC_MINB) decode_floatn_fast_ke
   }
 }
 
-size_t decode_fast_smem_bytes() { return static_cast<size_t>(kFWinAlloc); }
+size_t decode_fast_smem_bytes() { return static_cast<size_t>(kFOut2Off + kFOut2Bytes); }
 
 template <int K, int FP, bool MIXED, bool ROWS>
 static int launch_fast(const FastDecParams& Q, const DecLaunch& L, int sm_count, cudaStream_t stream) {
