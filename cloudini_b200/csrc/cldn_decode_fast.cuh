@@ -34,7 +34,8 @@ constexpr int kFW = kFT / 32;                // warps
 #define CLDN_FAST_DEC_DIRECT 0   // 1 = dense XYZI stores its floats straight from registers and requests the next window early: measured 1.29 vs 1.05 ms per 128 frames (32 lanes x 16 B at a 128-byte stride per store instruction)
 #endif
 #ifndef CLDN_FAST_DEC_SPLIT
-#define CLDN_FAST_DEC_SPLIT 1   // <= 4 values per point: float staging in its own 8 KB (two half passes), next window requested early
+#define CLDN_FAST_DEC_SPLIT 0   // 1 = <= 4 values per point stage their floats in their own 8 KB (two half passes of 64-byte pieces), request the next
+                                //     window behind the parse barrier and drop the end-of-tile barrier: measured 1.17 vs 1.05 ms per 128 frames
 #endif
 #ifndef CLDN_FAST_DEC_CPASYNC
 #define CLDN_FAST_DEC_CPASYNC 1   // window staging by cp.async: 1.101 -> 1.049 ms per 128 frames (plain loads + stores: 0)
@@ -52,11 +53,11 @@ struct FastDecParams {
   uint32_t rows;   // the regular fields and the V5 section fields together cover every byte of a point: whole rows may be written
 };
 constexpr int kFUnit = 16;                   // bytes per unit: a thread's slice of the window is `nu` units (nu odd: the
-constexpr int kFMaxUnits = 9;                //   16-byte reads of a warp are then conflict-free at any count); 18 KB = 18 B per point
+constexpr int kFMaxUnits = CLDN_FAST_DEC_SPLIT ? 9 : 11;   //   16-byte reads of a warp are then conflict-free at any count)
 constexpr int kFLead = 16;                   // bytes in front of the window (never read as data; keeps indices > 0)
-constexpr int kFWinBytes = kFMaxUnits * kFT * kFUnit;   // 18432
+constexpr int kFWinBytes = kFMaxUnits * kFT * kFUnit;   // 22528
 constexpr int kFWinAlloc = kFLead + kFWinBytes + 32;    // reads run at most 7 bytes past a value's last byte
-constexpr int kFMaskWords = (kFMaxUnits * kFUnit + 31) / 32; // 5 words of terminator bits per thread
+constexpr int kFMaskWords = (kFMaxUnits * kFUnit + 31) / 32; // 6 words of terminator bits per thread
 static_assert(kFT * 8 * 16 <= kFWinAlloc, "the float staging aliases the window");
 constexpr int kFOut2Off = (kFWinAlloc + 15) & ~15;      // split staging (SPLIT): 4 slots per lane, private to each warp, behind the window
 constexpr int kFOut2Bytes = kFT * 4 * 16;               // 8 KB
@@ -740,7 +741,7 @@ __global__ void __launch_bounds__(kFT, CLDN_FAST_DEC_MINB) decode_floatn_fast_ke
   }
 }
 
-size_t decode_fast_smem_bytes() { return static_cast<size_t>(kFOut2Off + kFOut2Bytes); }
+size_t decode_fast_smem_bytes() { return static_cast<size_t>(CLDN_FAST_DEC_SPLIT ? kFOut2Off + kFOut2Bytes : kFWinAlloc); }
 
 template <int K, int FP, bool MIXED, bool ROWS>
 static int launch_fast(const FastDecParams& Q, const DecLaunch& L, int sm_count, cudaStream_t stream) {
