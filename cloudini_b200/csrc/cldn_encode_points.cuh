@@ -72,10 +72,11 @@ __global__ void __launch_bounds__(kPT) encode_points_fast_kernel(const EncLaunch
     const uint32_t nvec = (bytes - head) >> 4;
     const uint4* gv = reinterpret_cast<const uint4*>(g + head);
     uint4* sv = reinterpret_cast<uint4*>(s + head);
-#pragma unroll 4
-    for (uint32_t i = threadIdx.x; i < nvec; i += kPT) sv[i] = __ldcs(gv + i);
+    for (uint32_t i = threadIdx.x; i < nvec; i += kPT) async_copy16(sv + i, gv + i);   // cp.async: no register round trip
+    async_commit();
     const uint32_t done = head + 16u * nvec;
     if (threadIdx.x < bytes - done) s[done + threadIdx.x] = g[done + threadIdx.x];
+    async_wait_all();
   }
   __syncthreads();
 
