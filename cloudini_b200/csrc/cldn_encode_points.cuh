@@ -26,6 +26,10 @@ struct PointsParams {
   uint32_t point_step;
 };
 
+#ifndef CLDN_POINTS_CPASYNC
+#define CLDN_POINTS_CPASYNC 1   // tile bytes by cp.async (0: ld.global.cs + st.shared)
+#endif
+
 template <bool ALIGNED4>
 __device__ __forceinline__ uint32_t smem_load_u32(const uint8_t* base, uint32_t byte_off) {
   if (ALIGNED4) return *reinterpret_cast<const uint32_t*>(base + byte_off);
@@ -72,8 +76,13 @@ __global__ void __launch_bounds__(kPT) encode_points_fast_kernel(const EncLaunch
     const uint32_t nvec = (bytes - head) >> 4;
     const uint4* gv = reinterpret_cast<const uint4*>(g + head);
     uint4* sv = reinterpret_cast<uint4*>(s + head);
+#if CLDN_POINTS_CPASYNC
     for (uint32_t i = threadIdx.x; i < nvec; i += kPT) async_copy16(sv + i, gv + i);   // cp.async: no register round trip
     async_commit();
+#else
+#pragma unroll 4
+    for (uint32_t i = threadIdx.x; i < nvec; i += kPT) sv[i] = __ldcs(gv + i);
+#endif
     const uint32_t done = head + 16u * nvec;
     if (threadIdx.x < bytes - done) s[done + threadIdx.x] = g[done + threadIdx.x];
     async_wait_all();
