@@ -30,15 +30,37 @@ struct PointsParams {
 #define CLDN_POINTS_CPASYNC 1   // tile bytes by cp.async (0: ld.global.cs + st.shared)
 #endif
 
+// Field reads from the staged tile. On the device the address is a 32-bit shared-window address and the loads are
+// ld.shared: through a generic `const uint8_t*` every read cost 64-bit pointer arithmetic and a generic load (17
+// instructions per value measured; the kernel is instruction-bound).
+#ifdef CLDN_CUSIM
+typedef const uint8_t* SmemAddr;
+__device__ __forceinline__ SmemAddr smem_addr(const uint8_t* p) { return p; }
 template <bool ALIGNED4>
-__device__ __forceinline__ uint32_t smem_load_u32(const uint8_t* base, uint32_t byte_off) {
+__device__ __forceinline__ uint32_t smem_load_u32(SmemAddr base, uint32_t byte_off) {
   if (ALIGNED4) return *reinterpret_cast<const uint32_t*>(base + byte_off);
   const uintptr_t a = reinterpret_cast<uintptr_t>(base + byte_off);
   const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~uintptr_t(3));
   return __funnelshift_r(w[0], w[1], 8u * static_cast<uint32_t>(a & 3u));
 }
+#else
+typedef uint32_t SmemAddr;
+__device__ __forceinline__ SmemAddr smem_addr(const uint8_t* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+template <bool ALIGNED4>
+__device__ __forceinline__ uint32_t smem_load_u32(SmemAddr base, uint32_t byte_off) {
+  const uint32_t a = base + byte_off;
+  if (ALIGNED4) return lds_u32(a);
+  const uint32_t w = a & ~3u;
+  return __funnelshift_r(lds_u32(w), lds_u32(w + 4u), 8u * a);   // the funnel shift takes the low 5 bits: 8 * (a & 3)
+}
+#endif
 
-template <int NV, int EP, bool ALIGNED4>
+template <int NV, int EP, bool ALIGNED4, int NF>   // NF: lanes of the leading FloatN group (ties to even); the others round half away
 __global__ void __launch_bounds__(kPT) encode_points_fast_kernel(const EncLaunch L, const PointsParams P) {
   constexpr uint32_t T = kPT * EP;
   extern __shared__ __align__(16) uint8_t dyn_smem[];
@@ -100,19 +122,19 @@ __global__ void __launch_bounds__(kPT) encode_points_fast_kernel(const EncLaunch
 #pragma unroll
       for (int k = 0; k < NV; ++k) prev[k] = 0;
     } else {
-      const uint8_t* pp = pts + (static_cast<int32_t>(p_local) - 1) * static_cast<int32_t>(step);
+      const SmemAddr pp = smem_addr(pts) + (static_cast<int32_t>(p_local) - 1) * static_cast<int32_t>(step);
 #pragma unroll
       for (int k = 0; k < NV; ++k) {
         const float v = __uint_as_float(smem_load_u32<ALIGNED4>(pp, P.offset[k]));
         const float s = __fmul_rn(v, P.mul[k]);
         trk = max_nan(trk, fabsf(s));
-        prev[k] = (static_cast<uint32_t>(k) < P.n_floatn) ? __float2int_rn(s) : __float2int_rn(roundf(s));
+        prev[k] = k < NF ? __float2int_rn(s) : __float2int_rn(roundf(s));
       }
     }
     uint32_t nbl[3] = {0, 0, 0};
 #pragma unroll
     for (int j = 0; j < EP; ++j) {
-      const uint8_t* pt = pts + (p_local + j) * step;
+      const SmemAddr pt = smem_addr(pts) + (p_local + j) * step;
 #pragma unroll
       for (int k = 0; k < NV; ++k) {
         const float v = __uint_as_float(smem_load_u32<ALIGNED4>(pt, P.offset[k]));
@@ -120,7 +142,7 @@ __global__ void __launch_bounds__(kPT) encode_points_fast_kernel(const EncLaunch
         trk = max_nan(trk, fabsf(s));
         // FloatN: cvtps2dq, ties to even. Scalar: static_cast<int64_t>(std::round(s)), half away from zero; identical to
         // the 64-bit value while |s| < 2^25 (checked below)
-        const int32_t q = (static_cast<uint32_t>(k) < P.n_floatn) ? __float2int_rn(s) : __float2int_rn(roundf(s));
+        const int32_t q = k < NF ? __float2int_rn(s) : __float2int_rn(roundf(s));
         const uint32_t d = static_cast<uint32_t>(q) - static_cast<uint32_t>(prev[k]);
         prev[k] = q;
         const uint32_t zz1 = ((d << 1) ^ static_cast<uint32_t>(static_cast<int32_t>(d) >> 31)) + 1u;
@@ -268,28 +290,40 @@ static uint32_t encode_points_values(const Plan& plan) {
 #endif
 static uint32_t encode_points_tile(const Plan& plan) { return encode_points_values(plan) <= 4 ? kPT * 8 : kPT * CLDN_POINTS_EP_WIDE; }
 
-template <int NV, int EP>
-static int launch_points_nv(const Plan& plan, const EncLaunch& L, const PointsParams& P, cudaStream_t stream) {
+template <int NV, int EP, int NF>
+static int launch_points_nf(const Plan& plan, const EncLaunch& L, const PointsParams& P, cudaStream_t stream) {
   constexpr uint32_t T = kPT * EP;
   const size_t raw = ((plan.point_step + 15u) & ~15u) + 32 + static_cast<size_t>(T) * plan.point_step + 32;
   const size_t stg = static_cast<size_t>(T) * plan.max_point_bytes + 64;
   const size_t smem = std::max(raw, stg);
   bool aligned4 = (plan.point_step & 3u) == 0u;
   for (int k = 0; k < NV; ++k) aligned4 = aligned4 && (P.offset[k] & 3u) == 0u;
-  // (the shared copy keeps the global misalignment of the tile's first byte only modulo 4 when the copy is word-wise; with
-  //  a 4-byte aligned layout and 4-byte aligned frames every field read is one aligned word)
+  // (the shared copy keeps the global misalignment of the tile's first byte modulo 16; with a 4-byte aligned layout and
+  //  16-byte aligned frames every field read is one aligned word)
   aligned4 = aligned4 && (L.flags & kEncInputsAligned16);
   if (aligned4) {
-    auto k = encode_points_fast_kernel<NV, EP, true>;
+    auto k = encode_points_fast_kernel<NV, EP, true, NF>;
     if (set_smem(k, smem) != cudaSuccess) return -1;
     k<<<L.n_tiles_total, kPT, smem, stream>>>(L, P);
   } else {
-    auto k = encode_points_fast_kernel<NV, EP, false>;
+    auto k = encode_points_fast_kernel<NV, EP, false, NF>;
     if (set_smem(k, smem) != cudaSuccess) return -1;
     k<<<L.n_tiles_total, kPT, smem, stream>>>(L, P);
   }
   count_launch();
   return 1;
+}
+
+// the FloatN group has 0 (no leading group), 3 or 4 lanes and is followed by at least one scalar field
+template <int NV, int EP>
+static int launch_points_nv(const Plan& plan, const EncLaunch& L, const PointsParams& P, cudaStream_t stream) {
+  if (P.n_floatn == 0) return launch_points_nf<NV, EP, 0>(plan, L, P, stream);
+  if (P.n_floatn == 3) {
+    if (NV >= 4) return launch_points_nf<NV, EP, NV >= 4 ? 3 : 0>(plan, L, P, stream);
+  } else if (P.n_floatn == 4) {
+    if (NV >= 5) return launch_points_nf<NV, EP, NV >= 5 ? 4 : 0>(plan, L, P, stream);
+  }
+  return -1;
 }
 
 static int launch_encode_points(const Plan& plan, const EncLaunch& L, const PointsParams& P, cudaStream_t stream) {

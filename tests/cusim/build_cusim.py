@@ -41,6 +41,9 @@ PTX = {
     "cp.async.cg.shared.global": lambda outs, ins: "((void)0);",
     "cp.async.ca.shared.global": lambda outs, ins: "((void)0);",
     "cp.async.commit_group": lambda outs, ins: "((void)0);",
+    # ld.shared.u32 with a 32-bit shared-window address: device builds only (the sources take the pointer path under CLDN_CUSIM);
+    # restated as a trap so that a use that slips through is loud
+    "ld.shared.u32": lambda outs, ins: f"{outs[0]} = 0; abort();",
     "cp.async.wait_group": lambda outs, ins: "((void)0);",
     "shl.b32": lambda outs, ins: f"{outs[0]} = (({ins[1]}) > 31u) ? 0u : (static_cast<unsigned>({ins[0]}) << ({ins[1]}));",
     # max.NaN.f32: NaN if either operand is NaN

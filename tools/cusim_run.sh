@@ -4,4 +4,5 @@
 set -eu
 cd "$(dirname "$0")/.."
 LIB=$(python -c "import sys; sys.path.insert(0,'tests/cusim'); import build_cusim; print(build_cusim.build())" | tail -1)
+[ -f "$LIB" ] || { echo "cusim build failed"; exit 1; }
 CLDN_B200_LIB=$LIB CLDN_B200_ALLOW_EMULATION=tests-only python -m pytest -x -q -m gpu -p no:cacheprovider "$@"
