@@ -612,43 +612,53 @@ __global__ void __launch_bounds__(kFT, CLDN_FAST_DEC_MINB) decode_floatn_fast_ke
       uint4* const my_slots = wst + 8 * lane;
       const uint32_t lx = lane & 7;
       bool wide = false;   // a scalar lossy value left the int32 range: the careful kernel (int64 like the reference) decides
+      // MODE: 0 = 16-byte slots, 4 / 2 / 1 = whole rows assembled with 4- / 2- / 1-byte stores. One instantiation of the
+      // loop per mode behind a CTA-uniform branch: as one loop the three row variants were if-converted and every tile
+      // issued all of them (25 predicated-off instructions per point on XYZIRT).
+      auto emit = [&](auto mode_tag) {
+        constexpr int MODE = decltype(mode_tag)::value;
 #pragma unroll
-      for (int j = 0; j < kFP; ++j) {
-        uint32_t fl[kSlots * 4];
+        for (int j = 0; j < kFP; ++j) {
+          uint32_t fl[kSlots * 4];
 #pragma unroll
-        for (int f = 0; f < kSlots * 4; ++f) fl[f] = 0;
-#pragma unroll
-        for (int f = 0; f < K; ++f) {
-          int32_t v = static_cast<int32_t>(static_cast<uint32_t>(base[f]) + static_cast<uint32_t>(P[j][f]));
-          if (MIXED && static_cast<uint32_t>(f) >= n_floatn) {
-            const long long v64 = base64[f] + P[j][f];
-            v = static_cast<int32_t>(v64);
-            wide = wide || (v64 != static_cast<long long>(v));
-          }
-          fl[f] = __float_as_uint(__fmul_rn(__int2float_rn(v), mul[f]));
-        }
-        if (rows) {
-          uint8_t* row = reinterpret_cast<uint8_t*>(wst) + static_cast<uint32_t>(kFP * lane + j) * step;
+          for (int f = 0; f < kSlots * 4; ++f) fl[f] = 0;
 #pragma unroll
           for (int f = 0; f < K; ++f) {
-            uint8_t* d = row + off[f];
-            if ((row_align & 3u) == 0u) {
-              *reinterpret_cast<uint32_t*>(d) = fl[f];
-            } else if ((row_align & 1u) == 0u) {
-              *reinterpret_cast<uint16_t*>(d) = static_cast<uint16_t>(fl[f]);
-              *reinterpret_cast<uint16_t*>(d + 2) = static_cast<uint16_t>(fl[f] >> 16);
-            } else {
-              d[0] = static_cast<uint8_t>(fl[f]); d[1] = static_cast<uint8_t>(fl[f] >> 8);
-              d[2] = static_cast<uint8_t>(fl[f] >> 16); d[3] = static_cast<uint8_t>(fl[f] >> 24);
+            int32_t v = static_cast<int32_t>(static_cast<uint32_t>(base[f]) + static_cast<uint32_t>(P[j][f]));
+            if (MIXED && static_cast<uint32_t>(f) >= n_floatn) {
+              const long long v64 = base64[f] + P[j][f];
+              v = static_cast<int32_t>(v64);
+              wide = wide || (v64 != static_cast<long long>(v));
             }
+            fl[f] = __float_as_uint(__fmul_rn(__int2float_rn(v), mul[f]));
           }
-        } else if (kSlots == 1) {
-          my_slots[j ^ lx] = make_uint4(fl[0], fl[1], fl[2], fl[3]);
-        } else {
-          my_slots[(2 * j) ^ lx] = make_uint4(fl[0], fl[1], fl[2], fl[3]);
-          my_slots[(2 * j + 1) ^ lx] = make_uint4(fl[4], fl[5], fl[6], fl[7]);
+          if (MODE != 0) {
+            uint8_t* row = reinterpret_cast<uint8_t*>(wst) + static_cast<uint32_t>(kFP * lane + j) * step;
+#pragma unroll
+            for (int f = 0; f < K; ++f) {
+              uint8_t* d = row + off[f];
+              if (MODE == 4) {
+                *reinterpret_cast<uint32_t*>(d) = fl[f];
+              } else if (MODE == 2) {
+                *reinterpret_cast<uint16_t*>(d) = static_cast<uint16_t>(fl[f]);
+                *reinterpret_cast<uint16_t*>(d + 2) = static_cast<uint16_t>(fl[f] >> 16);
+              } else {
+                d[0] = static_cast<uint8_t>(fl[f]); d[1] = static_cast<uint8_t>(fl[f] >> 8);
+                d[2] = static_cast<uint8_t>(fl[f] >> 16); d[3] = static_cast<uint8_t>(fl[f] >> 24);
+              }
+            }
+          } else if (kSlots == 1) {
+            my_slots[j ^ lx] = make_uint4(fl[0], fl[1], fl[2], fl[3]);
+          } else {
+            my_slots[(2 * j) ^ lx] = make_uint4(fl[0], fl[1], fl[2], fl[3]);
+            my_slots[(2 * j + 1) ^ lx] = make_uint4(fl[4], fl[5], fl[6], fl[7]);
+          }
         }
-      }
+      };
+      if (!ROWS || !rows) emit(std::integral_constant<int, 0>{});
+      else if ((row_align & 3u) == 0u) emit(std::integral_constant<int, 4>{});
+      else if ((row_align & 1u) == 0u) emit(std::integral_constant<int, 2>{});
+      else emit(std::integral_constant<int, 1>{});
       __syncwarp();
       // ---- copy-out: lane l of iteration i takes point 32 i + l of the warp's 32 * FP ----
       const uint32_t wp0 = pt0 + warp * (32 * kFP);

@@ -13,6 +13,8 @@
 //                             of a chunk: (1) number of values before the tile, (2) per-field sum since the last reset.
 #include <stdio.h>
 
+#include <type_traits>
+
 #include "cldn_device.cuh"
 #include "cldn_kernels.h"
 
