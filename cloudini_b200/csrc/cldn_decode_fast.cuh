@@ -118,7 +118,7 @@ __device__ __forceinline__ uint32_t nth_set_bit32(uint32_t m, uint32_t n, const 
   return base + ((__ldg(&table[m & 0xFFu]) >> (4u * n)) & 7u);
 }
 
-template <int K, int FP, bool MIXED, bool ROWS>
+template <int K, int FP, bool MIXED, bool ROWS, int NF>   // NF: lanes of the leading FloatN group (K when !MIXED)
 __global__ void __launch_bounds__(kFT, CLDN_FAST_DEC_MINB) decode_floatn_fast_kernel(const DecLaunch L, const FastDecParams Q) {
   constexpr int kFP = FP;
   constexpr int kFTilePts = kFT * FP;
@@ -135,7 +135,8 @@ __global__ void __launch_bounds__(kFT, CLDN_FAST_DEC_MINB) decode_floatn_fast_ke
   uint32_t off[K];
 #pragma unroll
   for (int f = 0; f < K; ++f) { mul[f] = Q.mul[f]; off[f] = Q.off[f]; }
-  const uint32_t n_floatn = MIXED ? Q.n_floatn : static_cast<uint32_t>(K);
+  constexpr uint32_t n_floatn = MIXED ? static_cast<uint32_t>(NF) : static_cast<uint32_t>(K);   // compile time: the int64 side of a
+                                                                                               // mixed plan exists only for its scalar fields
 
   // Whichever CTA draws ticket 0 -- by construction one that is running -- follows the u32 chunk prefixes of every
   // frame (cloudini.cpp:645-664) and publishes them; everybody else starts decoding and only waits for its own chunk.
@@ -753,10 +754,10 @@ __global__ void __launch_bounds__(kFT, CLDN_FAST_DEC_MINB) decode_floatn_fast_ke
 
 size_t decode_fast_smem_bytes() { return static_cast<size_t>(CLDN_FAST_DEC_SPLIT ? kFOut2Off + kFOut2Bytes : kFWinAlloc); }
 
-template <int K, int FP, bool MIXED, bool ROWS>
+template <int K, int FP, bool MIXED, bool ROWS, int NF>
 static int launch_fast(const FastDecParams& Q, const DecLaunch& L, int sm_count, cudaStream_t stream) {
   const size_t smem = decode_fast_smem_bytes();
-  auto k = decode_floatn_fast_kernel<K, FP, MIXED, ROWS>;
+  auto k = decode_floatn_fast_kernel<K, FP, MIXED, ROWS, NF>;
   if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess) return -1;
   int per_sm = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kFT, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
@@ -820,15 +821,17 @@ int launch_decode_fast(const Plan& plan, const DecLaunch& L, int sm_count, cudaS
   for (uint32_t k = 0; k < 4; ++k) dense_xyzi = dense_xyzi && Q.off[k] == 4 * k;
   const bool rows = Q.rows != 0 && !dense_xyzi;
   if (Q.n_floatn == nv) {
-    if (nv == 4) return rows ? launch_fast<4, 8, false, true>(Q, L, sm_count, stream) : launch_fast<4, 8, false, false>(Q, L, sm_count, stream);
-    return rows ? launch_fast<3, 8, false, true>(Q, L, sm_count, stream) : launch_fast<3, 8, false, false>(Q, L, sm_count, stream);
+    if (nv == 4) return rows ? launch_fast<4, 8, false, true, 4>(Q, L, sm_count, stream) : launch_fast<4, 8, false, false, 4>(Q, L, sm_count, stream);
+    return rows ? launch_fast<3, 8, false, true, 3>(Q, L, sm_count, stream) : launch_fast<3, 8, false, false, 3>(Q, L, sm_count, stream);
   }
-  switch (nv) {
-    case 3: return rows ? launch_fast<3, 8, true, true>(Q, L, sm_count, stream) : launch_fast<3, 8, true, false>(Q, L, sm_count, stream);
-    case 4: return rows ? launch_fast<4, 8, true, true>(Q, L, sm_count, stream) : launch_fast<4, 8, true, false>(Q, L, sm_count, stream);
-    case 5: return rows ? launch_fast<5, 4, true, true>(Q, L, sm_count, stream) : launch_fast<5, 4, true, false>(Q, L, sm_count, stream);
-    default: return rows ? launch_fast<6, 4, true, true>(Q, L, sm_count, stream) : launch_fast<6, 4, true, false>(Q, L, sm_count, stream);
-  }
+  // mixed plans: (values per point, FloatN lanes) -- the group has 0, 3 or 4 lanes and at least one scalar field follows it
+#define CLDN_FAST_MIXED(KK, FPP, NFF) \
+  if (nv == KK && Q.n_floatn == NFF) return rows ? launch_fast<KK, FPP, true, true, NFF>(Q, L, sm_count, stream) : launch_fast<KK, FPP, true, false, NFF>(Q, L, sm_count, stream);
+  CLDN_FAST_MIXED(3, 8, 0) CLDN_FAST_MIXED(4, 8, 0) CLDN_FAST_MIXED(4, 8, 3)
+  CLDN_FAST_MIXED(5, 4, 0) CLDN_FAST_MIXED(5, 4, 3) CLDN_FAST_MIXED(5, 4, 4)
+  CLDN_FAST_MIXED(6, 4, 0) CLDN_FAST_MIXED(6, 4, 3) CLDN_FAST_MIXED(6, 4, 4)
+#undef CLDN_FAST_MIXED
+  return -1;
 }
 
 }  // namespace cldn
