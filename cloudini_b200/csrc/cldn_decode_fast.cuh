@@ -56,7 +56,8 @@ constexpr int kFUnit = 16;                   // bytes per unit: a thread's slice
 constexpr int kFMaxUnits = CLDN_FAST_DEC_SPLIT ? 9 : 11;   //   16-byte reads of a warp are then conflict-free at any count)
 constexpr int kFLead = 16;                   // bytes in front of the window (never read as data; keeps indices > 0)
 constexpr int kFWinBytes = kFMaxUnits * kFT * kFUnit;   // 22528
-constexpr int kFWinAlloc = kFLead + kFWinBytes + 32;    // reads run at most 7 bytes past a value's last byte
+constexpr int kFWinAlloc = kFLead + kFWinBytes + 160;   // a thread's reader may run 32 values x 4 bytes (garbage behind its last real
+                                                        // point) + two prefetched words past the window
 constexpr int kFMaskWords = (kFMaxUnits * kFUnit + 31) / 32; // 6 words of terminator bits per thread
 static_assert(kFT * 8 * 16 <= kFWinAlloc, "the float staging aliases the window");
 constexpr int kFOut2Off = (kFWinAlloc + 15) & ~15;      // split staging (SPLIT): 4 slots per lane, private to each warp, behind the window
@@ -384,9 +385,8 @@ __global__ void __launch_bounds__(kFT, CLDN_FAST_DEC_MINB) decode_floatn_fast_ke
 #if CLDN_FAST_DEC_ROLLING
         // rolling 64-bit window: the shared-memory loads follow the WORD index, which only ever steps by one, so the next
         // word is in a register before it is needed and no load sits on the value-to-value dependency chain
-        constexpr uint32_t kLastWord = (kFWinAlloc >> 2) - 1;
         uint32_t wi = pb >> 5;
-        uint32_t lo = win32[wi], hi = win32[wi + 1], nx = win32[min(wi + 2u, kLastWord)];
+        uint32_t lo = win32[wi], hi = win32[wi + 1], nx = win32[wi + 2u];   // (kFWinAlloc leaves room behind the window)
 #endif
 #pragma unroll
         for (int j = 0; j < kFP; ++j) {
@@ -408,7 +408,7 @@ __global__ void __launch_bounds__(kFT, CLDN_FAST_DEC_MINB) decode_floatn_fast_ke
               ++wi;
               lo = hi;
               hi = nx;
-              nx = win32[min(wi + 2u, kLastWord)];
+              nx = win32[wi + 2u];
             }
 #endif
             x = x - ((x >> 1) & 0x3F803F80u);                                  // 7-bit groups -> 14-bit groups
