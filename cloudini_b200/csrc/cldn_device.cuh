@@ -441,6 +441,7 @@ struct LookbackPoll {
   uint64_t exclusive;  // sum of the tiles in (idx, me)
   uint64_t s;          // this lane's status word in flight
   bool done;
+  bool published = false;   // poll_once() already wrote the inclusive prefix
 
   // `publish` = false: another warp of the CTA publishes this tile's words; this warp only resolves the prefix for itself
   __device__ __forceinline__ void begin(uint64_t* status, uint32_t first, uint32_t me, uint32_t epoch, uint64_t aggregate, bool publish = true) {
@@ -448,6 +449,7 @@ struct LookbackPoll {
     exclusive = 0;
     idx = static_cast<int64_t>(me) - 1;
     done = (me == first);
+    published = false;
     s = 0;
     if (publish && lane == 0) st_relaxed_u64(status + me, pack_status(done ? kFlagIncl : kFlagAgg, epoch, aggregate));
   }
@@ -470,13 +472,25 @@ struct LookbackPoll {
     exclusive += v;
     if (incl_mask) done = true; else idx -= 32;
   }
+  // One non-blocking step for a warp that has other work between polls: evaluates the words asked for by the last issue(),
+  // publishes this tile's inclusive prefix the moment it is known (successors stop walking here), else asks again.
+  __device__ __forceinline__ void poll_once(uint64_t* status, uint32_t first, uint32_t me, uint32_t epoch, uint64_t aggregate) {
+    if (done) return;
+    eval(epoch);
+    if (done) {
+      if (me != first && (threadIdx.x & 31) == 0) st_relaxed_u64(status + me, pack_status(kFlagIncl, epoch, exclusive + aggregate));
+      published = true;
+    } else {
+      issue(status, first, epoch);
+    }
+  }
   __device__ __forceinline__ uint64_t finish(uint64_t* status, uint32_t first, uint32_t me, uint32_t epoch, uint64_t aggregate, bool publish = true) {
     const bool was_first = (me == first);
     while (!done) {
       issue(status, first, epoch);
       eval(epoch);
     }
-    if (publish && !was_first && (threadIdx.x & 31) == 0) st_relaxed_u64(status + me, pack_status(kFlagIncl, epoch, exclusive + aggregate));
+    if (publish && !published && !was_first && (threadIdx.x & 31) == 0) st_relaxed_u64(status + me, pack_status(kFlagIncl, epoch, exclusive + aggregate));
     return exclusive;
   }
 };

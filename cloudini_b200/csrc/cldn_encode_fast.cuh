@@ -21,6 +21,9 @@
 #pragma once
 
 namespace cldn {
+#ifndef CLDN_FAST_ENC_POLL_IN_PASS2
+#define CLDN_FAST_ENC_POLL_IN_PASS2 1
+#endif
 #ifndef CLDN_FAST_ENC_MINB
 #define CLDN_FAST_ENC_MINB 6
 #endif
@@ -330,6 +333,11 @@ __global__ void __launch_bounds__(kET, CLDN_FAST_ENC_MINB) encode_xyzi_fast_kern
           if (wn != wa) { *reinterpret_cast<uint32_t*>(stage + wa) = lo; lo = hi; }
           wa = wn;
         }
+#if CLDN_FAST_ENC_POLL_IN_PASS2
+        // warp 0 looks at its look-back window between points: the tile's inclusive prefix is published as soon as the
+        // predecessors allow, not only after this warp's share of the packing
+        if (warp == 0 && (j & 1) == 1) lb.poll_once(L.status, F.tile_begin, tile, L.epoch, total);
+#endif
       }
       if (threadIdx.x == kET - 1 && (bit & 31u) != 0u) *reinterpret_cast<uint32_t*>(stage + wa) = lo;  // nobody follows the tile's last thread
     } else {
