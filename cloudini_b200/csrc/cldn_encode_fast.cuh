@@ -22,7 +22,7 @@
 
 namespace cldn {
 #ifndef CLDN_FAST_ENC_POLL_IN_PASS2
-#define CLDN_FAST_ENC_POLL_IN_PASS2 1
+#define CLDN_FAST_ENC_POLL_IN_PASS2 0   // 1 = warp 0 polls its look-back window between points of pass 2: 0.997 vs 0.989 ms per 128 frames
 #endif
 #ifndef CLDN_FAST_ENC_MINB
 #define CLDN_FAST_ENC_MINB 6
