@@ -550,7 +550,7 @@ static int encode_batch_device(cldn_encoder* e, size_t n_frames, const void* con
       const uint32_t bpv = e->plan.sections[s].bpv;
       per_value = std::max<uint32_t>(per_value, (bpv == 2 ? 3u : bpv == 4 ? 5u : 10u) + 1u);
     }
-    const uint32_t stride = 16 + kChunkPoints * per_value;
+    const uint32_t stride = 32 + kChunkPoints * per_value;   // 5 header bytes + 16 bytes the vector copy of place_sections_kernel may read past the end
     if (int rc = e->d_modes.reserve(n_frames * ns)) return rc;
     if (int rc = e->d_sec_scratch.reserve(static_cast<size_t>(chunks) * ns * stride)) return rc;
     if (int rc = e->d_sec_sizes.reserve(static_cast<size_t>(chunks) * ns + 1)) return rc;
