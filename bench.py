@@ -457,7 +457,44 @@ def main():
             lat_e.append(t1 - t0)
             lat_d.append(t2 - t1)
         blob_bytes = int(sum(w))
-        e2e = {"seconds": e2e_s, "steps": e2e_steps, "frames": Fe, "h2d": Fe * POINTS * 16 + blob_bytes - Fe * hdr, "d2h": blob_bytes + Fe * POINTS * 16,
+        # ---- the PCIe ceiling of this box for exactly this traffic: plain pinned copies of one step's bytes (no kernels),
+        #      each direction alone and both at once on two streams. The e2e figure is read against `both`. ----
+        pcie = None
+        try:
+            s_up, s_dn = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+            up_dev = [torch.empty_like(t, device=dev) for t in h_in] + [torch.empty(int(n), dtype=torch.uint8, device=dev) for n in w]
+            up_src = list(h_in) + [b[:int(n)] for b, n in zip(h_blob, w)]
+            dn_dev = [torch.empty(int(n), dtype=torch.uint8, device=dev) for n in w] + [torch.empty(POINTS * 16, dtype=torch.uint8, device=dev) for _ in range(Fe)]
+            dn_dst = [b[:int(n)] for b, n in zip(h_blob2[1], w)] + list(h_out)
+
+            def copy_round(up, dn, reps=4):
+                torch.cuda.synchronize()
+                t0_ = time.perf_counter()
+                for _ in range(reps):
+                    if up:
+                        with torch.cuda.stream(s_up):
+                            for d_, s_ in zip(up_dev, up_src):
+                                d_.copy_(s_, non_blocking=True)
+                    if dn:
+                        with torch.cuda.stream(s_dn):
+                            for d_, s_ in zip(dn_dst, dn_dev):
+                                d_.copy_(s_, non_blocking=True)
+                torch.cuda.synchronize()
+                return (time.perf_counter() - t0_) / reps
+
+            copy_round(True, True, 1)
+            up_b = sum(t.numel() for t in up_src)
+            dn_b = sum(t.numel() for t in dn_dst)
+            t_up, t_dn, t_both = copy_round(True, False), copy_round(False, True), copy_round(True, True)
+            pcie = {"h2d_alone_gbs": up_b / t_up / 1e9, "d2h_alone_gbs": dn_b / t_dn / 1e9,
+                    "both_gbs_each_way": 0.5 * (up_b + dn_b) / t_both / 1e9,
+                    "ceiling_mpoints_s": Fe * POINTS / t_both / 1e6,
+                    "note": "pinned cudaMemcpyAsync of one e2e step's bytes (clouds + blobs up, blobs + clouds down), no kernels, "
+                            "two streams; ceiling = the points of one step / the time both directions need together"}
+            del up_dev, dn_dev
+        except Exception as ex:  # noqa: BLE001 - the probe is context for the e2e figure, never a reason to lose the line
+            pcie = {"error": str(ex)}
+        e2e = {"seconds": e2e_s, "pcie": pcie, "steps": e2e_steps, "frames": Fe, "h2d": Fe * POINTS * 16 + blob_bytes - Fe * hdr, "d2h": blob_bytes + Fe * POINTS * 16,
                "serial_mpts": Fe * POINTS / serial_s / 1e6, "pageable_mpts": Fe * POINTS / pageable_s / 1e6,
                "lat_enc_ms": float(np.median(lat_e)) * 1e3, "lat_dec_ms": float(np.median(lat_d)) * 1e3}
 
@@ -509,6 +546,9 @@ def main():
                                   "decoder handles driven by two host threads (batch i decodes while batch i+1 encodes)",
                            "serial_roundtrip_mpoints_s": world * e2e["serial_mpts"],
                            "pageable_buffers_mpoints_s": world * e2e["pageable_mpts"],
+                           "pcie_ceiling": e2e["pcie"],
+                           "frac_of_pcie_ceiling": (e2e_pts / e2e_s_max / 1e6 / (world * e2e["pcie"]["ceiling_mpoints_s"])
+                                                    if e2e["pcie"] and "ceiling_mpoints_s" in e2e["pcie"] else None),
                            "one_message_latency_ms": {"encode": e2e["lat_enc_ms"], "decode": e2e["lat_dec_ms"],
                                                       "note": "one 1M-point frame, pinned host buffers, host-pointer API, median of 7"}}
         # ---- CPU baseline on this box's host cores (rank 0, N=1 only): bounded sample ----

@@ -147,6 +147,7 @@ def lib():
                                          C.POINTER(sz), C.c_int, C.c_int]
     L.cldn_b200_decoder_sync.argtypes = [vp]
     L.cldn_b200_decoder_last_stats.argtypes = [vp, C.POINTER(C.c_uint32)]
+    L.cldn_b200_decoder_last_sections_ahead.argtypes = [vp]
     L.cldn_b200_EncodePointcloudData.argtypes = [C.c_char_p, vp, C.c_uint32, vp, C.c_uint32]
     L.cldn_b200_EncodePointcloudData.restype = C.c_uint32
     L.cldn_b200_DecodeCompressedData.argtypes = [vp, C.c_uint32, vp, C.c_uint32]
@@ -406,3 +407,9 @@ class PointcloudDecoder:
         st = (C.c_uint32 * 2)()
         _check(lib().cldn_b200_decoder_last_stats(self._h, st))
         return int(st[0]), int(st[1])
+
+    def last_sections_ahead(self) -> bool:
+        """True if the last batch decoded its V5 sections ahead of the regular stream (merged row writes)."""
+        r = lib().cldn_b200_decoder_last_sections_ahead(self._h)
+        _check(r if r < 0 else 0)
+        return r == 1

@@ -856,6 +856,7 @@ struct cldn_decoder {
   DevBuf<uint64_t> d_tstatus;
   DevBuf<uint64_t> d_trace;
   DevBuf<uint32_t> d_counter, d_redo;
+  DevBuf<uint8_t> d_side;         // side mode: section values decoded ahead of the regular stream (DecLaunch::side)
   DevBuf<uint64_t> d_chunk_desc;  // chunk-sequential kernel: self-validating chunk descriptors (see walk_frame_publish)
   uint32_t desc_tag = 0;
   // stage 2 on the device (LZ4)
@@ -868,6 +869,7 @@ struct cldn_decoder {
   PinRing<uint32_t> h_lz_chunk_frame;
   bool fast_launched = false;  // the last batch went through decode_floatn_fast_kernel (cldn_b200_decoder_last_stats)
   uint32_t fast_chunks = 0;
+  bool sections_ahead = false;    // the last batch ran in side mode (cldn_b200_decoder_last_sections_ahead)
   CopyPipeline pipe;
   uint32_t epoch = 0;
 };
@@ -925,6 +927,7 @@ static int decoder_update_plan(cldn_decoder* d, const cldn_info_t& info) {
 
 static int decode_batch_device(cldn_decoder* d, const cldn_info_t& info, size_t n_frames, const void* const* payloads,
                                const size_t* payload_bytes, void* const* outs, const size_t* out_capacities) {
+  d->sections_ahead = false;
   if (int rc = decoder_update_plan(d, info)) return rc;
   const uint64_t n_points = static_cast<uint64_t>(info.width) * info.height;
   if (n_points > 0xFFFFFFFFull) { set_error("too many points"); return CLDN_ERR_UNSUPPORTED; }
@@ -968,6 +971,8 @@ static int decode_batch_device(cldn_decoder* d, const cldn_info_t& info, size_t 
   L.chunk_tiles = nullptr; L.chunk_tile_begin = nullptr; L.stream_end = nullptr; L.tstatus = nullptr; L.tsums = nullptr;
   L.tile_capacity = 0; L.tile_grid = 0; L.epoch = 0; L.trace = nullptr; L.chunk_counter = nullptr; L.sections_only = 0;
   L.chunk_desc = nullptr; L.desc_tag = 0; L.uniform_chunks = 0; L.redo_list = nullptr; L.redo_mode = 0;
+  L.side = nullptr; L.side_mode = 0;
+  for (int s = 0; s < kMaxSideFields; ++s) L.side_off[s] = 0;
   if (d->plan.n_sections > 0 && chunks > 0 && (d->plan.regular_overlap || !(d->plan.all_varint || d->plan.n_ops == 0))) {
     // V5 with raw / XOR / Gorilla fields in the regular stream: the per-chunk parser records where the sections start
     if (int rc = d->d_stream_end.reserve(static_cast<size_t>(chunks) + 1)) return rc;
@@ -1052,6 +1057,14 @@ static int decode_batch_device(cldn_decoder* d, const cldn_info_t& info, size_t 
     }
   }
   d->fast_launched = L.redo_list != nullptr && decode_tiles_sequential(L.n_chunks_total) && decode_fast_enabled() && !d->plan.regular_overlap;
+  if (d->fast_launched && L.chunk_desc && L.stream_end && L.chunk_counter && decode_side_plan(d->plan) && decode_fast_general_plan(d->plan) &&
+      !(force_chunk && force_chunk[0] == '1')) {
+    // V5 sections ahead of the regular stream: compact per-chunk arrays the fast reader merges into the rows (DecLaunch::side)
+    const size_t side_bytes = decode_side_bytes(d->plan, chunks, L.side_off);
+    if (int rc = d->d_side.reserve(side_bytes + 256)) return rc;
+    L.side = d->d_side.p;
+  }
+  d->sections_ahead = decode_side_active(d->plan, L);
   (void)fast_general;
   d->fast_chunks = d->fast_launched ? L.n_chunks_total : 0u;
   if (launch_decode(d->plan, L, d->stream) < 0) { set_error("decode kernel launch failed"); return CLDN_ERR_CUDA; }
@@ -1090,7 +1103,7 @@ void cldn_b200_decoder_destroy(cldn_decoder_t* d) {
   if (d->stream) cudaStreamSynchronize(d->stream);
   d->d_plan.release(); d->d_frames.release(); d->h_frames.release(); d->d_chunk_offsets.release(); d->d_chunk_sizes.release();
   d->d_err.release(); d->h_err.release(); d->d_in.release(); d->d_out.release();
-  d->d_chunk_tiles.release(); d->d_chunk_tile_begin.release(); d->d_stream_end.release(); d->d_tsums.release(); d->d_tstatus.release(); d->d_chunk_frame.release(); d->d_tile_chunk.release(); d->d_trace.release(); d->d_counter.release(); d->d_redo.release(); d->d_chunk_desc.release(); d->pipe.release();
+  d->d_chunk_tiles.release(); d->d_chunk_tile_begin.release(); d->d_stream_end.release(); d->d_tsums.release(); d->d_tstatus.release(); d->d_chunk_frame.release(); d->d_tile_chunk.release(); d->d_trace.release(); d->d_counter.release(); d->d_redo.release(); d->d_side.release(); d->d_chunk_desc.release(); d->pipe.release();
   d->d_s1.release(); d->d_lz_scratch.release(); d->d_lz_chunk_frame.release(); d->d_lz_chunk_sizes.release(); d->d_lz_frames.release();
   d->d_lz_sizes.release(); d->h_lz_sizes.release(); d->h_lz_frames.release(); d->h_lz_chunk_frame.release();
   if (d->own_stream && d->stream) cudaStreamDestroy(d->stream);
@@ -1122,6 +1135,11 @@ int cldn_b200_decoder_last_stats(cldn_decoder_t* d, uint32_t stats[2]) {
   stats[0] = d->fast_chunks;
   stats[1] = c[3];
   return CLDN_OK;
+}
+
+int cldn_b200_decoder_last_sections_ahead(cldn_decoder_t* d) {
+  if (!d) { set_error("null argument"); return CLDN_ERR_INVALID_ARGUMENT; }
+  return d->sections_ahead ? 1 : 0;
 }
 
 }  // extern "C"

@@ -852,6 +852,7 @@ __global__ void __launch_bounds__(kThreads) decode_chunks_kernel(const DecLaunch
   __shared__ DecShared sh;
   __shared__ DecSlot s_slots[kMaxOps + 1];
   __shared__ uint32_t s_frame;
+  __shared__ uint32_t s_side_err;   // side mode: the error word of this chunk's sections
   // dynamic smem: tile bytes | values | nan bits | run batch
   uint8_t* tile_bytes = dyn_smem;
   uint8_t* vals_raw = tile_bytes + kLookBehind + kDecTileBytes + 16;
@@ -871,6 +872,7 @@ __global__ void __launch_bounds__(kThreads) decode_chunks_kernel(const DecLaunch
       if (L.frames[mid].chunk_begin <= gc) lo = mid; else hi = mid - 1;
     }
     s_frame = lo;
+    s_side_err = 0u;
   }
   const Plan& plan = *L.plan;
   // expand the regular ops into slots
@@ -896,11 +898,17 @@ __global__ void __launch_bounds__(kThreads) decode_chunks_kernel(const DecLaunch
   const uint32_t body_bytes = L.chunk_sizes[gc];
   uint8_t* out = F.out + static_cast<size_t>(c) * kChunkPoints * plan.point_step;
 
+  // Side mode: the sections are decoded AHEAD of the regular stream (stream_end_kernel said where they start) into compact
+  // per-chunk arrays that the fast reader merges into the rows it writes. Nothing is reported from here then: whatever
+  // is wrong with a section marks the chunk, and the careful kernels decode it again in the reference's order (regular
+  // stream first), so the first error a caller sees is the one the reference would raise.
+  const bool side = L.sections_only != 0u && L.side_mode != 0u;
+  uint32_t* const err = side ? &s_side_err : L.err;
   uint32_t pos = 0;
   if (L.sections_only) {
     // the regular stream was decoded by another kernel; sections start where it ended
     pos = L.stream_end[gc];
-    if (pos > body_bytes) return;  // regular stream failed (error already reported)
+    if (pos > body_bytes) return;  // regular stream failed (error already reported / chunk already marked)
   } else if (plan.values_per_point > 0) {
     const uint32_t used = decode_varint_stream<KT>(body, body_bytes, n_points, static_cast<int>(plan.values_per_point), s_slots,
                                                    out, plan.point_step, sh, tile_bytes, vals_raw, nanbits, L.err);
@@ -908,14 +916,29 @@ __global__ void __launch_bounds__(kThreads) decode_chunks_kernel(const DecLaunch
     pos = used;
   }
   for (uint32_t s = 0; s < plan.n_sections; ++s) {
-    const uint32_t used = decode_section<KT>(body + pos, body_bytes - pos, n_points, plan.sections[s], out, plan.point_step,
-                                             sh, tile_bytes, vals_raw, nanbits, rb, &s_slots[kMaxOps], L.err, L.par_runs != 0);
-    if (used == 0xFFFFFFFFu) return;
+    SectionField sf = plan.sections[s];
+    uint8_t* dst = out;
+    uint32_t dstep = plan.point_step;
+    if (side) {
+      dst = L.side + L.side_off[s] + static_cast<size_t>(gc) * kChunkPoints * sf.bpv;
+      dstep = sf.bpv;
+      if (sf.offset != CLDN_SKIP_STORE_OFFSET) sf.offset = 0;
+    }
+    const uint32_t used = decode_section<KT>(body + pos, body_bytes - pos, n_points, sf, dst, dstep,
+                                             sh, tile_bytes, vals_raw, nanbits, rb, &s_slots[kMaxOps], err, L.par_runs != 0);
+    if (used == 0xFFFFFFFFu) {
+      if (side && threadIdx.x == 0) L.stream_end[gc] = 0xFFFFFFFFu;
+      return;
+    }
     pos += used;
     __syncthreads();
   }
   // DecodeV5Stage1Chunk rejects trailing bytes (v5_codec.cpp:1008-1010); DecodeV4Stage1Chunk does not check.
-  if (plan.uses_v5 && pos != body_bytes && threadIdx.x == 0) report_error(L.err, DEV_ERR_TRAILING);
+  if (plan.uses_v5 && pos != body_bytes && threadIdx.x == 0) report_error(err, DEV_ERR_TRAILING);
+  if (side) {
+    __syncthreads();
+    if (threadIdx.x == 0 && s_side_err != 0u) L.stream_end[gc] = 0xFFFFFFFFu;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -1757,6 +1780,48 @@ static size_t dec_smem_bytes(bool k32) {
          sizeof(RunBatch) + 16;
 }
 
+// The V5 sections of every chunk (or, redo = true, of the chunks on the redo list), starting at stream_end[]; side = true
+// stores into the side arrays (see DecLaunch::side) instead of the rows.
+static int launch_sections_only(const DecLaunch& L, cudaStream_t stream, bool side, bool redo) {
+  DecLaunch S = L;
+  S.sections_only = 1;
+  S.side_mode = side ? 1u : 0u;
+  S.redo_mode = redo ? 1u : 0u;
+  const size_t smem = dec_smem_bytes(false);
+  auto k = decode_chunks_kernel<0>;
+  if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess) return -1;
+  k<<<L.n_chunks_total, kThreads, smem, stream>>>(S);  // redo: CTAs beyond the redo list return at once
+  return 1;
+}
+
+bool decode_side_plan(const Plan& plan) {
+  const char* e = getenv("CLDN_B200_DECODE_SIDE");
+  if (e && e[0] == '0') return false;
+  if (plan.n_sections == 0 || plan.n_sections > static_cast<uint32_t>(kMaxSideFields) || plan.regular_overlap) return false;
+  uint32_t sum = 0;
+  for (uint32_t s = 0; s < plan.n_sections; ++s) {
+    const uint32_t b = plan.sections[s].bpv;
+    if (!(b == 1 || b == 2 || b == 4 || b == 8)) return false;
+    sum += b;
+  }
+  // the fast reader keeps one tile of section values in 8 KB of shared memory (tiles: 1024 points for <= 4 values per point, else 512)
+  const uint32_t tile_points = plan.values_per_point <= 4 ? 1024u : 512u;
+  return sum * tile_points <= 8192u;
+}
+size_t decode_side_bytes(const Plan& plan, uint64_t n_chunks_total, uint64_t side_off[kMaxSideFields]) {
+  uint64_t at = 0;
+  for (uint32_t s = 0; s < static_cast<uint32_t>(kMaxSideFields); ++s) {
+    side_off[s] = at;
+    if (s < plan.n_sections) at += ((n_chunks_total * kChunkPoints * plan.sections[s].bpv) + 255u) & ~255ull;
+  }
+  return static_cast<size_t>(at);
+}
+bool decode_side_active(const Plan& plan, const DecLaunch& L) {
+  return L.side != nullptr && L.n_chunks_total > 0 && L.redo_list != nullptr && L.chunk_desc != nullptr && L.stream_end != nullptr &&
+         L.chunk_counter != nullptr && decode_side_plan(plan) && decode_fast_general_plan(plan) &&
+         decode_tiles_sequential(L.n_chunks_total) && decode_fast_enabled();
+}
+
 int launch_decode(const Plan& plan, const DecLaunch& L, cudaStream_t stream) {
   int launches = 0;
   if (L.n_chunks_total == 0 && L.n_frames == 0) return 0;
@@ -1790,6 +1855,12 @@ int launch_decode(const Plan& plan, const DecLaunch& L, cudaStream_t stream) {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaMemsetAsync(L.chunk_counter, 0, 4 * sizeof(uint32_t), stream);
+    const bool side = decode_side_active(plan, L);
+    if (side) {
+      // sections first, into the side arrays; the fast reader writes every row once, section fields included
+      if (launch_stream_end(plan, L, stream) < 0 || launch_sections_only(L, stream, true, false) < 0) return -1;
+      launches += 2;
+    }
     if (launch_decode_fast(plan, L, sms > 0 ? sms : 148, stream) < 0) return -1;
     ++launches;
     {
@@ -1798,30 +1869,28 @@ int launch_decode(const Plan& plan, const DecLaunch& L, cudaStream_t stream) {
       const size_t smem = dec_smem_bytes(false);
       auto k = decode_chunks_kernel<0>;
       if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess) return -1;
-      k<<<L.n_chunks_total, kThreads, smem, stream>>>(R);  // CTAs beyond the redo list return at once
+      k<<<L.n_chunks_total, kThreads, smem, stream>>>(R);  // CTAs beyond the redo list return at once; regular stream + sections
       ++launches;
     }
-    if (plan.n_sections > 0) {
-      DecLaunch S = L;
-      S.sections_only = 1;
-      const size_t smem = dec_smem_bytes(false);
-      auto k = decode_chunks_kernel<0>;
-      if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess) return -1;
-      k<<<L.n_chunks_total, kThreads, smem, stream>>>(S);
+    if (plan.n_sections > 0 && !side) {
+      if (launch_sections_only(L, stream, false, false) < 0) return -1;
       ++launches;
     }
   } else if (L.n_chunks_total > 0 && L.tile_grid > 0) {
-    // FloatN-only regular stream: tile-parallel kernel; V5 sections (if any) by the per-chunk kernel afterwards
+    // FloatN-only regular stream: tile-parallel kernel; V5 sections (if any) by the per-chunk kernel afterwards -- or, large
+    // batches in side mode, ahead of it (launch_decode_tiles then runs the merging fast reader and the sections of the
+    // chunks it handed to the careful kernel follow)
+    const bool side = decode_side_active(plan, L);
+    if (side) {
+      cudaMemsetAsync(L.chunk_counter, 0, 4 * sizeof(uint32_t), stream);
+      if (launch_stream_end(plan, L, stream) < 0 || launch_sections_only(L, stream, true, false) < 0) return -1;
+      launches += 2;
+    }
     const int n = launch_decode_tiles(plan, L, stream);
     if (n < 0) return -1;
     launches += n;
     if (plan.n_sections > 0) {
-      const size_t smem = dec_smem_bytes(false);
-      auto k = decode_chunks_kernel<0>;
-      if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess) return -1;
-      DecLaunch S = L;
-      S.sections_only = 1;
-      k<<<L.n_chunks_total, kThreads, smem, stream>>>(S);
+      if (launch_sections_only(L, stream, false, side) < 0) return -1;
       ++launches;
     }
   } else if (L.n_chunks_total > 0) {

@@ -51,6 +51,10 @@ struct FastDecParams {
   uint32_t off[6];
   uint32_t n_floatn;
   uint32_t rows;   // the regular fields and the V5 section fields together cover every byte of a point: whole rows may be written
+  // side mode (SIDE instantiations): the V5 section fields whose values wait in DecLaunch::side
+  uint32_t n_side;
+  uint32_t side_offset[kMaxSideFields];   // byte offset inside a point (CLDN_SKIP_STORE_OFFSET: decoded, not stored)
+  uint32_t side_bpv[kMaxSideFields];
 };
 constexpr int kFUnit = 16;                   // bytes per unit: a thread's slice of the window is `nu` units (nu odd: the
 constexpr int kFMaxUnits = CLDN_FAST_DEC_SPLIT ? 9 : 11;   //   16-byte reads of a warp are then conflict-free at any count)
@@ -60,6 +64,8 @@ constexpr int kFWinAlloc = kFLead + kFWinBytes + 160;   // a thread's reader may
                                                         // point) + two prefetched words past the window
 constexpr int kFMaskWords = (kFMaxUnits * kFUnit + 31) / 32; // 6 words of terminator bits per thread
 static_assert(kFT * 8 * 16 <= kFWinAlloc, "the float staging aliases the window");
+constexpr int kFSideOff = (kFWinAlloc + 15) & ~15;      // SIDE: the tile's section values (cp.async at the tile start) behind the window
+constexpr int kFSideBytes = 8192;                        //   sum over the section fields of tile points * bpv fits here (decode_side_plan)
 constexpr int kFOut2Off = (kFWinAlloc + 15) & ~15;      // split staging (SPLIT): 4 slots per lane, private to each warp, behind the window
 constexpr int kFOut2Bytes = kFT * 4 * 16;               // 8 KB
 
@@ -119,12 +125,22 @@ __device__ __forceinline__ uint32_t nth_set_bit32(uint32_t m, uint32_t n, const 
   return base + ((__ldg(&table[m & 0xFFu]) >> (4u * n)) & 7u);
 }
 
-template <int K, int FP, bool MIXED, bool ROWS, int NF>   // NF: lanes of the leading FloatN group (K when !MIXED)
+// One value of a side array (naturally aligned: the arrays start at 256-byte boundaries, values are bpv = 1 / 2 / 4 / 8 bytes)
+__device__ __forceinline__ uint64_t load_side_value(const uint8_t* p, uint32_t bpv) {
+  if (bpv == 2) return *reinterpret_cast<const uint16_t*>(p);
+  if (bpv == 4) return *reinterpret_cast<const uint32_t*>(p);
+  if (bpv == 8) return *reinterpret_cast<const uint64_t*>(p);
+  return p[0];
+}
+
+// SIDE: the chunk's V5 sections were decoded ahead of this kernel into DecLaunch::side (stream_end_kernel found where
+// they start); their values are merged into the rows as they are written, so every output sector is written by ONE pass.
+template <int K, int FP, bool MIXED, bool ROWS, int NF, bool SIDE>   // NF: lanes of the leading FloatN group (K when !MIXED)
 __global__ void __launch_bounds__(kFT, CLDN_FAST_DEC_MINB) decode_floatn_fast_kernel(const DecLaunch L, const FastDecParams Q) {
   constexpr int kFP = FP;
   constexpr int kFTilePts = kFT * FP;
   constexpr int kSlots = K <= 4 ? 1 : 2;                     // 16-byte staging slots per point
-  constexpr bool kSplit = CLDN_FAST_DEC_SPLIT && CLDN_FAST_DEC_CPASYNC && K <= 4 && FP == 8 && !ROWS;
+  constexpr bool kSplit = CLDN_FAST_DEC_SPLIT && CLDN_FAST_DEC_CPASYNC && K <= 4 && FP == 8 && !ROWS && !SIDE;
   extern __shared__ __align__(16) uint8_t dyn_smem[];
   __shared__ FastShared sh;
   uint8_t* win = dyn_smem;                                    // kFLead + window bytes
@@ -221,10 +237,11 @@ __global__ void __launch_bounds__(kFT, CLDN_FAST_DEC_MINB) decode_floatn_fast_ke
     // bytes each. Nothing aliases the window then, so once every thread has parsed (the any_bad barrier) the NEXT tile's
     // window is requested with cp.async and lands while this tile is summed, converted and stored; the barrier that
     // separated the staged copy-out from the next staging is gone.
-    const bool direct = CLDN_FAST_DEC_DIRECT && CLDN_FAST_DEC_CPASYNC && K == 4 && !MIXED && !ROWS && dense4;
+    const bool direct = CLDN_FAST_DEC_DIRECT && CLDN_FAST_DEC_CPASYNC && K == 4 && !MIXED && !ROWS && !SIDE && dense4;
     bool pre = false;                         // the next tile's window has been requested ...
     uint32_t pre_nu = 0;                      // ... with this many units per thread
     bool redo = (size == 0u);                 // an empty body cannot hold n_points > 0 points: the careful kernel reports it
+    if (SIDE) redo = redo || L.stream_end[gc] == 0xFFFFFFFFu;   // no stream end / a damaged section: nothing to merge, the careful kernels decide
     for (uint32_t pt0 = 0; pt0 < n_points && !redo; pt0 += kFTilePts) {
       const uint32_t tile_pts = min(static_cast<uint32_t>(kFTilePts), n_points - pt0);
       const uint32_t n_vals = tile_pts * K;
@@ -240,6 +257,21 @@ __global__ void __launch_bounds__(kFT, CLDN_FAST_DEC_MINB) decode_floatn_fast_ke
       nu = nu < 3u ? 3u : (nu | 1u);
       if (nu > kFMaxUnits) nu = kFMaxUnits;
       if (pre) nu = pre_nu;
+      if (SIDE) {
+        // the tile's section values (whole tile: a chunk's slot holds kChunkPoints values whatever its point count) are
+        // requested now and land while the window is staged and parsed
+        uint32_t soff = 0;
+        for (uint32_t s = 0; s < Q.n_side; ++s) {
+          const uint32_t bpv = Q.side_bpv[s];
+          const uint8_t* src = L.side + L.side_off[s] + (static_cast<size_t>(gc) * kChunkPoints + pt0) * bpv;
+          const uint32_t bytes = kFTilePts * bpv;
+          for (uint32_t u = 16u * threadIdx.x; u < bytes; u += 16u * kFT) {
+            async_copy16(reinterpret_cast<uint4*>(dyn_smem + kFSideOff + soff + u), reinterpret_cast<const uint4*>(src + u));
+          }
+          soff += bytes;
+        }
+        async_commit();
+      }
       uint32_t m[kFMaskWords];
       uint32_t total, incl, cnt;
       while (true) {
@@ -291,6 +323,7 @@ __global__ void __launch_bounds__(kFT, CLDN_FAST_DEC_MINB) decode_floatn_fast_ke
             sv[r * kFT] = (v >= v_lo && v < v_hi) ? __ldcs(gv + r * kFT) : load_vector_bounded(abase + 16u * v, pay_lo, pay_end);
           }
         }
+        if (SIDE) async_wait_all();   // (the section values too; a no-op in the widening rounds)
         __syncthreads();
         // ---- terminator bits of my slice: nu units of 16 bytes, bit i of the mask <-> slice byte i ----
         const uint32_t slice0 = threadIdx.x * nu * kFUnit;                     // window byte of my first unit
@@ -660,6 +693,20 @@ __global__ void __launch_bounds__(kFT, CLDN_FAST_DEC_MINB) decode_floatn_fast_ke
       else if ((row_align & 3u) == 0u) emit(std::integral_constant<int, 4>{});
       else if ((row_align & 1u) == 0u) emit(std::integral_constant<int, 2>{});
       else emit(std::integral_constant<int, 1>{});
+      if (SIDE && ROWS && rows) {
+        // the section values of my kFP consecutive points go into my rows (bytes: a row may sit at any alignment)
+        uint32_t soff = 0;
+        for (uint32_t s = 0; s < Q.n_side; ++s) {
+          const uint32_t bpv = Q.side_bpv[s], so = Q.side_offset[s];
+          const uint8_t* sv = dyn_smem + kFSideOff + soff + threadIdx.x * kFP * bpv;
+          soff += kFTilePts * bpv;
+          if (so == CLDN_SKIP_STORE_OFFSET) continue;
+          uint8_t* d = reinterpret_cast<uint8_t*>(wst) + static_cast<uint32_t>(kFP * lane) * step + so;
+          for (uint32_t j = 0; j < static_cast<uint32_t>(kFP); ++j) {
+            for (uint32_t b = 0; b < bpv; ++b) d[j * step + b] = sv[j * bpv + b];
+          }
+        }
+      }
       __syncwarp();
       // ---- copy-out: lane l of iteration i takes point 32 i + l of the warp's 32 * FP ----
       const uint32_t wp0 = pt0 + warp * (32 * kFP);
@@ -731,6 +778,38 @@ __global__ void __launch_bounds__(kFT, CLDN_FAST_DEC_MINB) decode_floatn_fast_ke
           }
         }
       }
+      if (SIDE && !rows) {
+        // per-point copy-out of the section fields: lane l of iteration i takes point 32 i + l like the floats above, so a
+        // point's section bytes follow its floats into the same sectors while they are still in L2
+        uint32_t soff = 0;
+        for (uint32_t s = 0; s < Q.n_side; ++s) {
+          const uint32_t bpv = Q.side_bpv[s], so = Q.side_offset[s];
+          const uint8_t* sv = dyn_smem + kFSideOff + soff + (static_cast<uint32_t>(warp) * (32 * kFP) + lane) * bpv;
+          soff += kFTilePts * bpv;
+          if (so == CLDN_SKIP_STORE_OFFSET) continue;
+          uint8_t* d = dst0 + so;
+          const bool al = ((static_cast<uint32_t>(reinterpret_cast<uintptr_t>(d)) | step) & (bpv - 1u)) == 0u;
+          if (bpv == 4u && al) {
+#pragma unroll
+            for (int i = 0; i < kFP; ++i) {
+              if (32u * i + lane < wn) __stcs(reinterpret_cast<unsigned int*>(d + static_cast<size_t>(32 * i) * step), *reinterpret_cast<const uint32_t*>(sv + 128 * i));
+            }
+          } else if (bpv == 2u && al) {
+#pragma unroll
+            for (int i = 0; i < kFP; ++i) {
+              if (32u * i + lane < wn) *reinterpret_cast<uint16_t*>(d + static_cast<size_t>(32 * i) * step) = *reinterpret_cast<const uint16_t*>(sv + 64 * i);
+            }
+          } else {
+#pragma unroll 1
+            for (int i = 0; i < kFP; ++i) {
+              if (32u * i + lane < wn) {
+                uint8_t* dp = d + static_cast<size_t>(32 * i) * step;
+                for (uint32_t b = 0; b < bpv; ++b) dp[b] = sv[32u * i * bpv + b];
+              }
+            }
+          }
+        }
+      }
       est = used;
       cursor += used;
       // the staging slots alias the window the next tile is about to load
@@ -746,24 +825,40 @@ __global__ void __launch_bounds__(kFT, CLDN_FAST_DEC_MINB) decode_floatn_fast_ke
         L.redo_list[atomicAdd(L.chunk_counter + 3, 1u)] = gc;
         L.stream_end[gc] = 0xFFFFFFFFu;  // the careful kernel owns this chunk now (its sections too)
       }
+    } else if (SIDE && cursor != L.stream_end[gc]) {
+      // (cannot happen for a stream the tile loop accepted: it ends behind its n_points * K-th terminator, which is what
+      // the pre-pass looked for. Kept as a cross-check: the merged section values belong to that position.)
+      if (threadIdx.x == 0) {
+        L.redo_list[atomicAdd(L.chunk_counter + 3, 1u)] = gc;
+        L.stream_end[gc] = 0xFFFFFFFFu;
+      }
     } else if (threadIdx.x == 0) {
       L.stream_end[gc] = cursor;  // V5: the sections start here
     }
+    if (SIDE) __syncthreads();  // everybody has compared the pre-pass's stream end before thread 0 may have replaced it
   }
 }
 
-size_t decode_fast_smem_bytes() { return static_cast<size_t>(CLDN_FAST_DEC_SPLIT ? kFOut2Off + kFOut2Bytes : kFWinAlloc); }
+size_t decode_fast_smem_bytes(bool side) {
+  if (side) return static_cast<size_t>(kFSideOff + kFSideBytes);
+  return static_cast<size_t>(CLDN_FAST_DEC_SPLIT ? kFOut2Off + kFOut2Bytes : kFWinAlloc);
+}
 
-template <int K, int FP, bool MIXED, bool ROWS, int NF>
-static int launch_fast(const FastDecParams& Q, const DecLaunch& L, int sm_count, cudaStream_t stream) {
-  const size_t smem = decode_fast_smem_bytes();
-  auto k = decode_floatn_fast_kernel<K, FP, MIXED, ROWS, NF>;
+template <int K, int FP, bool MIXED, bool ROWS, int NF, bool SIDE>
+static int launch_fast_one(const FastDecParams& Q, const DecLaunch& L, int sm_count, cudaStream_t stream) {
+  const size_t smem = decode_fast_smem_bytes(SIDE);
+  auto k = decode_floatn_fast_kernel<K, FP, MIXED, ROWS, NF, SIDE>;
   if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess) return -1;
   int per_sm = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kFT, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
   const uint32_t grid = min(L.n_chunks_total, static_cast<uint32_t>(per_sm * sm_count));
   k<<<grid, kFT, smem, stream>>>(L, Q);
   return 1;
+}
+template <int K, int FP, bool MIXED, bool ROWS, int NF>
+static int launch_fast(const FastDecParams& Q, const DecLaunch& L, int sm_count, cudaStream_t stream) {
+  return Q.n_side ? launch_fast_one<K, FP, MIXED, ROWS, NF, true>(Q, L, sm_count, stream)
+                  : launch_fast_one<K, FP, MIXED, ROWS, NF, false>(Q, L, sm_count, stream);
 }
 
 // Plans the fast reader takes: every value of the regular stream is a 32-bit float varint -- one leading FloatN group and /
@@ -786,6 +881,8 @@ bool decode_fast_plan(const Plan& plan, FastDecParams* Q) {
   }
   if (nv < 3 || nv > 6) return false;
   for (uint32_t k = nv; k < 6; ++k) { Q->mul[k] = 0.f; Q->off[k] = 0; }
+  Q->n_side = 0;   // launch_decode_fast fills the side fields in when the launch runs in side mode
+  for (int k = 0; k < kMaxSideFields; ++k) { Q->side_offset[k] = CLDN_SKIP_STORE_OFFSET; Q->side_bpv[k] = 1; }
   // rows: every byte of [0, point_step) is written by a regular field (4 bytes each here) or by a V5 section field
   Q->rows = 0;
   if (plan.point_step <= 64) {
@@ -811,9 +908,174 @@ bool decode_fast_general_plan(const Plan& plan) {
   return decode_fast_plan(plan, &Q);
 }
 
+// ---- side mode pre-pass: where does the regular stream of every chunk end? ----------------------------------------------
+// The V5 sections of a chunk start behind its regular stream, whose length is only known once it has been decoded -- or
+// counted: every value is one varint (or a 0x00 NaN marker), i.e. exactly one byte with a clear top bit, so the stream ends
+// right behind the chunk's (n_points * K)-th such byte. One CTA per chunk counts them 512 bytes per warp and step, finds
+// the 512-byte block holding that terminator from the block counts and the byte inside it with one warp. It also does
+// the launch's chunk walk (ticket 0, like the fast reader, which then finds the descriptors published). A chunk without
+// that many terminators inside the longest possible stream gets 0xFFFFFFFF: the careful kernels report what is wrong.
+constexpr int kSeT = 256;
+constexpr uint32_t kSeBlock = 512;                                 // bytes per warp step
+constexpr uint32_t kSeMaxBlocks = (kChunkPoints * 6u * 10u) / kSeBlock + 2u;  // 6 values of at most 10 bytes per point
+
+__device__ __forceinline__ uint32_t terminator_bits16(const uint4& q) {
+  return (((~q.x & 0x80808080u) * 0x00204081u) >> 28) | ((((~q.y & 0x80808080u) * 0x00204081u) >> 28) << 4) |
+         ((((~q.z & 0x80808080u) * 0x00204081u) >> 28) << 8) | ((((~q.w & 0x80808080u) * 0x00204081u) >> 28) << 12);
+}
+
+__global__ void __launch_bounds__(kSeT) stream_end_kernel(const DecLaunch L, const uint32_t K) {
+  __shared__ uint16_t s_cnt[kSeMaxBlocks];
+  __shared__ uint32_t s_scan[kSeT / 32 + 1];
+  __shared__ unsigned long long s_desc[2];
+  __shared__ uint32_t s_ticket, s_found, s_rank;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) { s_ticket = atomicAdd(L.chunk_counter + 2, 1u); s_found = 0xFFFFFFFFu; s_rank = 0; }
+  __syncthreads();
+  if (s_ticket == 0u) {
+    for (uint32_t f = threadIdx.x; f < L.n_frames; f += kSeT) walk_frame_publish(L, f);
+  }
+  const uint32_t gc = blockIdx.x;
+  if (gc >= L.n_chunks_total) return;
+  if (threadIdx.x == 0) {
+    unsigned long long w0, w1;
+    do {
+      w0 = ld_relaxed_u64(L.chunk_desc + 2ull * gc);
+      w1 = ld_relaxed_u64(L.chunk_desc + 2ull * gc + 1);
+    } while (static_cast<uint32_t>(w0 >> 40) != L.desc_tag || static_cast<uint32_t>(w1 >> 40) != L.desc_tag);
+    s_desc[0] = w0 & 0xFFFFFFFFFFull;
+    s_desc[1] = w1 & 0xFFFFFFFFull;
+  }
+  __syncthreads();
+  uint32_t fidx;
+  if (L.uniform_chunks) {
+    fidx = gc / L.uniform_chunks;
+  } else {
+    uint32_t lo = 0, hi = L.n_frames - 1;
+    while (lo < hi) {
+      const uint32_t mid = (lo + hi + 1) >> 1;
+      if (L.frames[mid].chunk_begin <= gc) lo = mid; else hi = mid - 1;
+    }
+    fidx = lo;
+  }
+  const DecFrame F = L.frames[fidx];
+  const uint32_t n_points = min(kChunkPoints, F.n_points - (gc - F.chunk_begin) * kChunkPoints);
+  const uint32_t size = static_cast<uint32_t>(s_desc[1]);
+  const uint32_t N = n_points * K;                                   // <= 32768 * 6
+  if (N == 0u || size < N) {                                         // (an empty chunk has no stream: its sections start at 0)
+    if (threadIdx.x == 0) L.stream_end[gc] = N == 0u ? 0u : 0xFFFFFFFFu;
+    return;
+  }
+  const uint8_t* body = F.payload + s_desc[0];
+  const uint8_t* pay_lo = F.payload;
+  const uint8_t* pay_hi = F.payload + F.payload_bytes;
+  const uint32_t limit = size < N * 10u ? size : N * 10u;            // (N * 10 <= 1 966 080)
+  const uint32_t c0 = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(body) & 15u);
+  const uint8_t* abase = body - c0;                                  // window byte i <-> abase[i]; the stream is [c0, c0 + limit)
+  const uint32_t wend = c0 + limit;
+  const uint32_t nblk = (wend + kSeBlock - 1u) / kSeBlock;           // <= kSeMaxBlocks
+  // terminator bits of the 16 bytes at window offset o, bytes outside the stream masked off
+  auto unit_bits = [&](uint32_t o) -> uint32_t {
+    if (o >= wend) return 0u;
+    const uint8_t* g = abase + o;
+    const uint4 q = (g >= pay_lo && g + 16 <= pay_hi) ? __ldg(reinterpret_cast<const uint4*>(g)) : load_vector_bounded(g, pay_lo, pay_hi);
+    uint32_t m = terminator_bits16(q);
+    if (o < c0) m &= ~((1u << (c0 - o)) - 1u);                        // (only the first unit: c0 < 16)
+    if (wend - o < 16u) m &= (1u << (wend - o)) - 1u;
+    return m;
+  };
+  // blocks [b_lo, b_hi) lie completely inside the stream and the payload: four of a warp's loads in flight, no masking
+  const uint32_t b_lo = 1u;
+  uint32_t b_hi = nblk > 0u ? nblk - 1u : 0u;
+  if (abase + static_cast<size_t>(b_hi) * kSeBlock > pay_hi) b_hi = 0u;   // (cannot happen: the stream lies inside the payload)
+  constexpr uint32_t kWarps = kSeT / 32;
+  uint32_t b = b_lo + warp;
+  for (; b + 3u * kWarps < b_hi; b += 4u * kWarps) {
+    uint4 q[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) q[r] = __ldg(reinterpret_cast<const uint4*>(abase + static_cast<size_t>(b + r * kWarps) * kSeBlock) + lane);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      uint32_t c = __popc(terminator_bits16(q[r]));
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+      if (lane == 0) s_cnt[b + r * kWarps] = static_cast<uint16_t>(c);
+    }
+  }
+  for (; b < b_hi; b += kWarps) {
+    uint32_t c = __popc(terminator_bits16(__ldg(reinterpret_cast<const uint4*>(abase + static_cast<size_t>(b) * kSeBlock) + lane)));
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+    if (lane == 0) s_cnt[b] = static_cast<uint16_t>(c);
+  }
+  // the first and the last block: bytes outside the stream / the payload masked off
+  if (warp < 2) {
+    const uint32_t be = warp == 0 ? 0u : nblk - 1u;
+    if (warp == 0 || nblk > 1u) {
+      uint32_t c = __popc(unit_bits(be * kSeBlock + 16u * lane));
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+      if (lane == 0) s_cnt[be] = static_cast<uint16_t>(c);
+    }
+  }
+  __syncthreads();
+  // the block holding terminator N (1-based): thread t scans blocks [t * per, (t + 1) * per)
+  const uint32_t per = (nblk + kSeT - 1u) / kSeT;
+  uint32_t mine = 0;
+  for (uint32_t i = 0; i < per; ++i) {
+    const uint32_t b = threadIdx.x * per + i;
+    if (b < nblk) mine += s_cnt[b];
+  }
+  uint32_t total;
+  uint32_t before = block_exclusive_scan_n<kSeT>(mine, s_scan, &total);
+  if (before < N && before + mine >= N) {
+    for (uint32_t i = 0; i < per; ++i) {
+      const uint32_t b = threadIdx.x * per + i;
+      const uint32_t c = b < nblk ? s_cnt[b] : 0u;
+      if (before + c >= N) { s_found = b; s_rank = N - before; break; }
+      before += c;
+    }
+  }
+  __syncthreads();
+  const uint32_t fb = s_found;
+  if (fb == 0xFFFFFFFFu) {
+    if (threadIdx.x == 0) L.stream_end[gc] = 0xFFFFFFFFu;
+    return;
+  }
+  if (warp == 0) {
+    const uint32_t o = fb * kSeBlock + 16u * lane;
+    uint32_t m = unit_bits(o);
+    const uint32_t c = __popc(m);
+    uint32_t inc = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= d) inc += t;
+    }
+    const uint32_t r = s_rank;                                        // 1-based inside the block
+    if (inc - c < r && r <= inc) {
+      for (uint32_t i = inc - c + 1u; i < r; ++i) m &= m - 1u;        // drop the terminators in front of it
+      L.stream_end[gc] = o + static_cast<uint32_t>(__ffs(static_cast<int>(m))) - c0;   // one past it, relative to the body
+    }
+  }
+}
+
+int launch_stream_end(const Plan& plan, const DecLaunch& L, cudaStream_t stream) {
+  if (plan.values_per_point == 0 || plan.values_per_point > 6) return -1;
+  stream_end_kernel<<<L.n_chunks_total, kSeT, 0, stream>>>(L, plan.values_per_point);
+  return 1;
+}
+
 int launch_decode_fast(const Plan& plan, const DecLaunch& L, int sm_count, cudaStream_t stream) {
   FastDecParams Q;
   if (!decode_fast_plan(plan, &Q)) return -1;
+  if (decode_side_active(plan, L)) {
+    Q.n_side = plan.n_sections;
+    for (uint32_t s2 = 0; s2 < plan.n_sections; ++s2) {
+      Q.side_offset[s2] = plan.sections[s2].offset;
+      Q.side_bpv[s2] = plan.sections[s2].bpv;
+    }
+  }
   const uint32_t nv = plan.values_per_point;
   // whole-row copy-out is a separate instantiation: its extra live state costs the dense XYZI reader (which never needs it:
   // one 16-byte store per point already) 4 % when it is merely a run-time branch

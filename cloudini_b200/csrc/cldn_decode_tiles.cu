@@ -1000,7 +1000,7 @@ int launch_decode_tiles(const Plan& plan, const DecLaunch& L, cudaStream_t strea
   if (sequential && decode_fast_enabled() && L.redo_list) {
     // fast kernel first; whatever it could not prove plain (NaN markers, 5+ byte varints, damage) goes to the careful
     // kernel, which is launched on a small grid and returns at once when the redo list is empty
-    cudaMemsetAsync(L.chunk_counter, 0, 4 * sizeof(uint32_t), stream);
+    if (!decode_side_active(plan, L)) cudaMemsetAsync(L.chunk_counter, 0, 4 * sizeof(uint32_t), stream);  // (side mode: zeroed before its pre-pass)
     if (launch_decode_fast(plan, L, sm_count, stream) < 0) return -1;
     DecLaunch R = L;
     R.redo_mode = 1;

@@ -45,6 +45,7 @@ uint32_t choose_tile_points(const Plan& plan);
 int launch_encode_regular(const Plan& host_plan, const EncLaunch& L, cudaStream_t stream);
 int launch_gorilla_prepass(const Plan& host_plan, const EncLaunch& L, cudaStream_t stream);
 
+constexpr int kMaxSideFields = 4;   // V5 section fields the side mode carries (more: the sections are decoded behind the stream)
 struct DecFrame {
   const uint8_t* payload;  // header-less payload
   uint64_t payload_bytes;
@@ -85,6 +86,14 @@ struct DecLaunch {
   uint32_t epoch;
   uint32_t mix_chase;          // decode_mixed_kernel: 1 = one thread follows next() through the tile instead of pointer doubling
   uint32_t par_runs;           // V5 Rle / DeltaRle readers: 1 = parallel run-table parse (see unmeasured_kernels_enabled)
+  // Side mode (V5 sections decoded AHEAD of the regular stream, large batches): stream_end_kernel finds where every chunk's
+  // regular stream ends, the section reader writes its values into compact arrays -- section s of global chunk gc at
+  // side + side_off[s] + gc * kChunkPoints * bpv -- and the fast reader merges them into the rows it writes, so that
+  // every output sector is written once instead of once per pass.
+  uint8_t* side;               // nullptr: off
+  uint64_t side_off[kMaxSideFields];
+  uint32_t side_mode;          // decode_chunks_kernel, sections_only: 1 = store into the side arrays; any anomaly marks the
+                               // chunk (stream_end = 0xFFFFFFFF) for the careful kernels instead of raising the error word
 };
 
 // The parallel boundary-search decoders, the warp-parallel Gorilla pre-pass and the parallel run-table parse: defaults
@@ -98,6 +107,11 @@ bool decode_fast_general_plan(const Plan& host_plan);  // a FloatN group and / o
 bool decode_fast_enabled();  // CLDN_B200_DECODE_FAST=0 keeps the careful chunk-sequential kernel alone
 bool decode_tiles_sequential(uint32_t n_chunks_total);  // which of the two FloatN kernels launch_decode_tiles will pick
 uint32_t decode_tile_bytes();
+// Side mode applies to this plan (1..kMaxSideFields section fields, CLDN_B200_DECODE_SIDE != 0) / to this launch
+bool decode_side_plan(const Plan& host_plan);
+bool decode_side_active(const Plan& host_plan, const DecLaunch& L);
+size_t decode_side_bytes(const Plan& host_plan, uint64_t n_chunks_total, uint64_t side_off[kMaxSideFields]);
+int launch_stream_end(const Plan& host_plan, const DecLaunch& L, cudaStream_t stream);
 
 // V5 adaptive integer sections (encode side).
 struct SecLaunch {

@@ -177,6 +177,10 @@ int cldn_b200_decoder_sync(cldn_decoder_t* dec);
  * stats[0] = chunks claimed by the chunk-sequential reader, stats[1] = chunks it handed to the careful reader
  * (NaN markers, varints of 5+ bytes, damaged streams). Both 0 when the batch took another kernel. */
 int cldn_b200_decoder_last_stats(cldn_decoder_t* dec, uint32_t stats[2]);
+/* 1 if the LAST batch decode of this handle decoded its V5 sections ahead of the regular stream and merged them into the
+ * rows the chunk-sequential reader writes (large batches of FloatN / lossy-float layouts with 1..4 adaptive integer
+ * fields; CLDN_B200_DECODE_SIDE=0 turns it off), else 0. No reference counterpart; negative status on a null handle. */
+int cldn_b200_decoder_last_sections_ahead(cldn_decoder_t* dec);
 
 /* ---- one-shot convenience, same shape as the reference's own C ABI ------------------------------------------- */
 /* cldn_EncodePointcloudData (wasm_functions.h:88-93 / wasm_functions.cpp:217-248): YAML config + raw points -> blob

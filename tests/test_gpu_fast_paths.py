@@ -275,3 +275,159 @@ def test_whole_row_copy_out_at_any_output_address(oracle, monkeypatch, shift):
             o0 = base - d_out.ptr
             assert np.array_equal(got[o0:o0 + cloud.size], _want(oracle, blob, cloud.size, 0xA7))
             assert np.all(got[:o0] == 0xA7) and np.all(got[o0 + cloud.size:] == 0xA7)
+
+
+# ---- V5 sections ahead of the regular stream (side mode) -------------------------------------------------------------
+def _decode_batch_side(info, blobs, hdr, n_bytes, fill, shift=0):
+    dec = cb.PointcloudDecoder()
+    d_blobs = [_Dev(src=np.frombuffer(b, dtype=np.uint8)) for b in blobs]
+    d_outs = [_Dev(src=np.full(n_bytes + 64, fill, dtype=np.uint8)) for _ in blobs]
+    bases = [t.ptr + (-t.ptr) % 16 + shift for t in d_outs]
+    batch = dec.make_device_batch([t.ptr + hdr for t in d_blobs], [len(b) - hdr for b in blobs], bases, [n_bytes] * len(blobs))
+    dec.decode_batch_device(info, batch, sync=True)
+    outs = []
+    for d, b in zip(d_outs, bases):
+        a = d.numpy()
+        o0 = b - d.ptr
+        assert np.all(a[:o0] == fill) and np.all(a[o0 + n_bytes:] == fill)
+        outs.append(a[o0:o0 + n_bytes])
+    return outs, dec.last_stats(), dec.last_sections_ahead()
+
+
+def _int_sections_layout(n, seed, with_u64=False, only_u64=False):
+    """XYZ (FloatN) + int16 / uint32 / (uint64) / uint16 adaptive fields, padded step 40: every V5 mode shows up. The side
+    mode carries at most 8 bytes of section values per point (1024-point tiles): with_u64 = 16 bytes, sections behind."""
+    F = cb.FieldType
+    rng = np.random.default_rng(seed)
+    raw = np.full((n, 40), 0xEE, dtype=np.uint8)
+    xyz = np.cumsum(rng.normal(0, 0.01, (n, 3)), axis=0).astype(np.float32)
+    raw[:, 0:12] = xyz.view(np.uint8).reshape(n, 12)
+    a = (rng.integers(-300, 300, n)).astype(np.int16)                                   # DeltaVarint
+    b = rng.choice(np.array([7, 1 << 20, 0xFFFFFFF0, 12345], dtype=np.uint32), n)       # Palette
+    c = (np.arange(n, dtype=np.uint64) // 900) * np.uint64(1 << 33)                     # Rle (64-bit)
+    d = (np.arange(n) % 128).astype(np.uint16)                                          # DeltaRle
+    raw[:, 12:14] = a.view(np.uint8).reshape(n, 2)
+    raw[:, 16:20] = b.view(np.uint8).reshape(n, 4)
+    raw[:, 24:32] = c.view(np.uint8).reshape(n, 8)
+    raw[:, 32:34] = d.view(np.uint8).reshape(n, 2)
+    fields = [cb.PointField("x", 0, F.FLOAT32, 0.001), cb.PointField("y", 4, F.FLOAT32, 0.001), cb.PointField("z", 8, F.FLOAT32, 0.001)]
+    if only_u64:
+        fields.append(cb.PointField("c", 24, F.UINT64, None))
+    else:
+        fields += [cb.PointField("a", 12, F.INT16, None), cb.PointField("b", 16, F.UINT32, None)]
+        if with_u64:
+            fields.append(cb.PointField("c", 24, F.UINT64, None))
+        fields.append(cb.PointField("d", 32, F.UINT16, None))
+    info = cb.EncodingInfo(fields=fields, width=n, height=1, point_step=40, compression_opt=cb.CompressionOption.NONE, use_threads=False, version=5)
+    return info, raw.reshape(-1)
+
+
+@pytest.mark.parametrize("n", [1, 9, 1024, 4097, 32768, 32769, 70_001])
+def test_sections_ahead_same_bytes_as_sections_behind(oracle, monkeypatch, n):
+    monkeypatch.setenv("CLDN_B200_DECODE_MODE", "seq")
+    cases = [synth.cloud_c3(n, seed=n, version=5), _xyzirt(n, 3), _int_sections_layout(n, n), _int_sections_layout(n, n + 1, only_u64=True)]
+    for info, cloud in cases:
+        step = info.point_step
+        clouds = [cloud, np.ascontiguousarray(cloud.reshape(n, step)[::-1]).reshape(-1)]
+        blobs, hdr = _encode_all(info, clouds, oracle)
+        for shift in (0, 2):
+            seen = {}
+            for flag in ("1", "0"):
+                monkeypatch.setenv("CLDN_B200_DECODE_SIDE", flag)
+                outs, (fast, redo), ahead = _decode_batch_side(info, blobs, hdr, n * step, 0x5C, shift)
+                assert ahead == (flag == "1"), (n, flag)
+                assert (fast, redo) == (2 * ((n + 32767) // 32768), 0), (n, flag, fast, redo)
+                seen[flag] = outs
+            for b, o1, o0 in zip(blobs, seen["1"], seen["0"]):
+                want = _want(oracle, b, n * step, 0x5C)
+                assert np.array_equal(o1, want), (n, shift)
+                assert np.array_equal(o0, want), (n, shift)
+
+
+def test_sections_ahead_with_chunks_for_the_careful_kernels(oracle, monkeypatch):
+    """NaN markers / wide values in the regular stream: the chunk's sections were decoded ahead, its rows were not merged; the
+    careful kernels decode stream and sections again. Batches mix plain and redone chunks."""
+    monkeypatch.setenv("CLDN_B200_DECODE_MODE", "seq")
+    n = 70_000
+    for make in (lambda: synth.cloud_c3(n, seed=11, version=5), lambda: _xyzirt(n, 5), lambda: _int_sections_layout(n, 12)):
+        info, plain = make()
+        step = info.point_step
+        pts = plain.reshape(n, step).copy()
+        nan_c = pts.copy(); nan_c[40_000, 4:8] = np.frombuffer(np.float32(np.nan).tobytes(), dtype=np.uint8)
+        wide_c = pts.copy(); wide_c[100, 0:4] = np.frombuffer(np.float32(3.0e6).tobytes(), dtype=np.uint8)
+        last_c = pts.copy(); last_c[n - 1, 8:12] = np.frombuffer(np.float32(np.nan).tobytes(), dtype=np.uint8)
+        clouds = [plain, nan_c.reshape(-1), wide_c.reshape(-1), last_c.reshape(-1)]
+        blobs, hdr = _encode_all(info, clouds, oracle)
+        outs, (fast, redo), ahead = _decode_batch_side(info, blobs, hdr, n * step, 0x21)
+        assert ahead and fast == 12 and redo == 3, (fast, redo, ahead)
+        for b, o in zip(blobs, outs):
+            assert np.array_equal(o, _want(oracle, b, n * step, 0x21))
+
+
+def test_sections_ahead_on_damaged_blobs_reports_like_sections_behind(oracle, monkeypatch):
+    """Damage anywhere in a V5 blob (stream, section modes, palettes, run tables, trailing bytes): same outcome, same message
+    and -- when the blob still decodes -- same bytes with the sections ahead of or behind the regular stream."""
+    n = 40_000
+    rng = np.random.default_rng(99)
+    for info, cloud in (synth.cloud_c3(n, seed=21, version=5), _int_sections_layout(n, 22)):
+        step = info.point_step
+        blob = oracle.encode(info, cloud)
+        hdr = len(cb.PointcloudEncoder(info).getHeader())
+        # where chunk 0's sections start: its stream ends there
+        size0 = int(np.frombuffer(blob[hdr:hdr + 4], dtype=np.uint32)[0])
+        for trial in range(24):
+            bad = bytearray(blob)
+            kind = trial % 6
+            if kind == 0:      # cut the payload
+                bad = bad[:hdr + int(rng.integers(5, len(blob) - hdr))]
+            elif kind == 1:    # flip bytes anywhere
+                for _ in range(3):
+                    bad[hdr + 4 + int(rng.integers(0, len(blob) - hdr - 4))] = int(rng.integers(0, 256))
+            elif kind == 2:    # flip bytes near the end of chunk 0 (its sections)
+                for _ in range(3):
+                    bad[hdr + 4 + size0 - 1 - int(rng.integers(0, min(size0 - 1, 3000)))] = int(rng.integers(0, 256))
+            elif kind == 3:    # one terminator more / less in the stream: the sections start elsewhere
+                at = hdr + 4 + int(rng.integers(10, size0 // 2))
+                bad[at] ^= 0x80
+            elif kind == 4:    # chunk 0 claims one byte less than it has (trailing byte for chunk 0, shifted chunk 1)
+                bad[hdr:hdr + 4] = np.uint32(size0 - 1).tobytes()
+            else:              # zero byte (NaN marker) in the stream
+                bad[hdr + 4 + int(rng.integers(0, size0 // 2))] = 0
+            results = []
+            for flag in ("1", "0"):
+                monkeypatch.setenv("CLDN_B200_DECODE_MODE", "seq")
+                monkeypatch.setenv("CLDN_B200_DECODE_SIDE", flag)
+                out = np.full(n * step, 0x33, dtype=np.uint8)
+                try:
+                    cb.PointcloudDecoder().decode(info, bytes(bad[hdr:]), out)
+                    results.append(("ok", out.tobytes()))
+                except RuntimeError as e:
+                    results.append(("err", str(e)))
+            assert results[0] == results[1], (trial, kind, results[0][0], results[1][0], results[0][1][:80] if results[0][0] == "err" else "", results[1][1][:80] if results[1][0] == "err" else "")
+
+
+def test_sections_ahead_limits(oracle, monkeypatch):
+    """More adaptive fields than the side arrays carry: sections behind the stream, same bytes. Empty clouds: nothing runs."""
+    monkeypatch.setenv("CLDN_B200_DECODE_MODE", "seq")
+    F = cb.FieldType
+    n = 5_000
+    rng = np.random.default_rng(4)
+    raw = np.zeros((n, 32), dtype=np.uint8)
+    raw[:, 0:12] = np.cumsum(rng.normal(0, 0.01, (n, 3)), axis=0).astype(np.float32).view(np.uint8).reshape(n, 12)
+    fields = [cb.PointField("x", 0, F.FLOAT32, 0.001), cb.PointField("y", 4, F.FLOAT32, 0.001), cb.PointField("z", 8, F.FLOAT32, 0.001)]
+    for k in range(5):
+        raw[:, 12 + 4 * k:16 + 4 * k] = rng.integers(0, 50, n).astype(np.uint32).view(np.uint8).reshape(n, 4)
+        fields.append(cb.PointField(f"i{k}", 12 + 4 * k, F.UINT32, None))
+    info = cb.EncodingInfo(fields=fields, width=n, height=1, point_step=32, compression_opt=cb.CompressionOption.NONE, use_threads=False, version=5)
+    blob = oracle.encode(info, raw.reshape(-1))
+    hdr = len(cb.PointcloudEncoder(info).getHeader())
+    outs, (fast, redo), ahead = _decode_batch_side(info, [blob], hdr, n * 32, 0x42)
+    assert not ahead and (fast, redo) == (1, 0)
+    assert np.array_equal(outs[0], _want(oracle, blob, n * 32, 0x42))
+    # 16 bytes of section values per point: more than a tile's shared-memory budget
+    info, cloud = _int_sections_layout(n, 8, with_u64=True)
+    blob = oracle.encode(info, cloud)
+    hdr = len(cb.PointcloudEncoder(info).getHeader())
+    outs, (fast, redo), ahead = _decode_batch_side(info, [blob], hdr, n * 40, 0x42)
+    assert not ahead and (fast, redo) == (1, 0)
+    assert np.array_equal(outs[0], _want(oracle, blob, n * 40, 0x42))
