@@ -40,6 +40,9 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary measurements (tools/extras_bench.py, child process)")
     ap.add_argument("--e2e-frames", type=int, default=8, help="frames per end-to-end step (pinned host buffers)")
+    ap.add_argument("--e2e-pipelines", type=int, default=2,
+                    help="independent encoder/decoder handle pairs streaming side by side in the end-to-end leg (each pair = two host "
+                         "threads; a second pair fills the copy-engine bubbles between the batches of the first)")
     return ap.parse_args()
 
 
@@ -374,8 +377,10 @@ def main():
         h_in = [torch.from_numpy(host_clouds[k]).pin_memory() for k in range(Fe)]
         h_blob = [torch.empty(cap, dtype=torch.uint8).pin_memory() for _ in range(Fe)]
         h_out = [torch.zeros(POINTS * 16, dtype=torch.uint8).pin_memory() for _ in range(Fe)]
-        henc = cb.PointcloudEncoder(info, device=local_rank)
-        hdec = cb.PointcloudDecoder(device=local_rank)
+        P = max(1, args.e2e_pipelines)
+        hencs = [cb.PointcloudEncoder(info, device=local_rank) for _ in range(P)]
+        hdecs = [cb.PointcloudDecoder(device=local_rank) for _ in range(P)]
+        henc, hdec = hencs[0], hdecs[0]
 
         # Two host threads, as a streaming user of the C ABI would run it: one drives the encoder handle, the other the
         # decoder handle (each handle is single-threaded, the two are independent), so frame batch i is decoded while
@@ -383,36 +388,52 @@ def main():
         # downloaded, uploaded again as a blob, decoded and downloaded inside the timed region.
         import queue, threading
         h_blob2 = [h_blob, [torch.empty(cap, dtype=torch.uint8).pin_memory() for _ in range(Fe)]]
+        # pipeline 0 uses the buffers above; every further pipeline has its own blob ring and output buffers
+        pipe_blobs = [h_blob2] + [[[torch.empty(cap, dtype=torch.uint8).pin_memory() for _ in range(Fe)] for _ in range(2)] for _ in range(P - 1)]
+        pipe_outs = [h_out] + [[torch.zeros(POINTS * 16, dtype=torch.uint8).pin_memory() for _ in range(Fe)] for _ in range(P - 1)]
         last_w = [None]
 
         def run_pipeline(n_steps):
-            free, ready, errs = threading.Semaphore(2), queue.Queue(), []
+            """n_steps batches of Fe frames in total, dealt round-robin to the P handle pairs."""
+            errs, ts = [], []
 
-            def enc_loop():
-                try:
-                    for s_ in range(n_steps):
-                        free.acquire()
-                        w_ = henc.encode_batch_host(h_in, h_blob2[s_ & 1], write_header=True)
-                        ready.put((s_ & 1, w_))
-                except Exception as ex:  # noqa: BLE001 - surfaced below
-                    errs.append(ex)
-                    ready.put(None)
+            def make(pi, steps_here):
+                free, ready = threading.Semaphore(2), queue.Queue()
+                enc_h, dec_h, blobs, outs = hencs[pi], hdecs[pi], pipe_blobs[pi], pipe_outs[pi]
 
-            def dec_loop():
-                try:
-                    for _ in range(n_steps):
-                        item = ready.get()
-                        if item is None:
-                            return
-                        b_, w_ = item
-                        hdec.decode_batch_host(info, [x[hdr:n] for x, n in zip(h_blob2[b_], w_)], h_out)
-                        last_w[0] = w_
+                def enc_loop():
+                    try:
+                        cb.bind_host_thread_to_device(local_rank)
+                        for s_ in range(steps_here):
+                            free.acquire()
+                            w_ = enc_h.encode_batch_host(h_in, blobs[s_ & 1], write_header=True)
+                            ready.put((s_ & 1, w_))
+                    except Exception as ex:  # noqa: BLE001 - surfaced below
+                        errs.append(ex)
+                        ready.put(None)
+
+                def dec_loop():
+                    try:
+                        cb.bind_host_thread_to_device(local_rank)
+                        for _ in range(steps_here):
+                            item = ready.get()
+                            if item is None:
+                                return
+                            b_, w_ = item
+                            dec_h.decode_batch_host(info, [x[hdr:n] for x, n in zip(blobs[b_], w_)], outs)
+                            if pi == 0:
+                                last_w[0] = w_
+                            free.release()
+                    except Exception as ex:  # noqa: BLE001
+                        errs.append(ex)
                         free.release()
-                except Exception as ex:  # noqa: BLE001
-                    errs.append(ex)
-                    free.release()
 
-            ts = [threading.Thread(target=enc_loop), threading.Thread(target=dec_loop)]
+                return [threading.Thread(target=enc_loop), threading.Thread(target=dec_loop)]
+
+            for pi in range(P):
+                steps_here = n_steps // P + (1 if pi < n_steps % P else 0)
+                if steps_here:
+                    ts += make(pi, steps_here)
             for t_ in ts:
                 t_.start()
             for t_ in ts:
@@ -420,9 +441,9 @@ def main():
             if errs:
                 raise errs[0]
 
-        run_pipeline(max(args.warmup, 3))
+        run_pipeline(max(args.warmup, 3) * P)
         barrier()
-        e2e_steps = max(4, min(args.steps, 12))
+        e2e_steps = max(4, min(args.steps, 12)) * P
         t0 = time.perf_counter()
         run_pipeline(e2e_steps)
         torch.cuda.synchronize()
@@ -494,7 +515,7 @@ def main():
             del up_dev, dn_dev
         except Exception as ex:  # noqa: BLE001 - the probe is context for the e2e figure, never a reason to lose the line
             pcie = {"error": str(ex)}
-        e2e = {"seconds": e2e_s, "pcie": pcie, "steps": e2e_steps, "frames": Fe, "h2d": Fe * POINTS * 16 + blob_bytes - Fe * hdr, "d2h": blob_bytes + Fe * POINTS * 16,
+        e2e = {"seconds": e2e_s, "pcie": pcie, "pipelines": P, "steps": e2e_steps, "frames": Fe, "h2d": Fe * POINTS * 16 + blob_bytes - Fe * hdr, "d2h": blob_bytes + Fe * POINTS * 16,
                "serial_mpts": Fe * POINTS / serial_s / 1e6, "pageable_mpts": Fe * POINTS / pageable_s / 1e6,
                "lat_enc_ms": float(np.median(lat_e)) * 1e3, "lat_dec_ms": float(np.median(lat_d)) * 1e3}
 
@@ -542,8 +563,10 @@ def main():
             e2e_pts = world * e2e["frames"] * POINTS * e2e["steps"]
             line["e2e"] = {"value": e2e_pts / e2e_s_max / 1e6, "unit": "Mpoints/s", "h2d_bytes_per_step": int(e2e["h2d"]),
                            "d2h_bytes_per_step": int(e2e["d2h"]), "frames_per_step": e2e["frames"],
-                           "api": "cldn_b200_encode_batch + cldn_b200_decode_batch, CLDN_MEM_HOST, pinned host buffers; encoder and "
-                                  "decoder handles driven by two host threads (batch i decodes while batch i+1 encodes)",
+                           "api": "cldn_b200_encode_batch + cldn_b200_decode_batch, CLDN_MEM_HOST, pinned host buffers; %d independent "
+                                  "encoder/decoder handle pair(s), each driven by two host threads (batch i decodes while batch i+1 "
+                                  "encodes); every point is uploaded, encoded, downloaded, uploaded as a blob, decoded and downloaded" % e2e["pipelines"],
+                           "pipelines": e2e["pipelines"],
                            "serial_roundtrip_mpoints_s": world * e2e["serial_mpts"],
                            "pageable_buffers_mpoints_s": world * e2e["pageable_mpts"],
                            "pcie_ceiling": e2e["pcie"],

@@ -1798,6 +1798,10 @@ bool decode_side_plan(const Plan& plan) {
   const char* e = getenv("CLDN_B200_DECODE_SIDE");
   if (e && e[0] == '0') return false;
   if (plan.n_sections == 0 || plan.n_sections > static_cast<uint32_t>(kMaxSideFields) || plan.regular_overlap) return false;
+  // Measured (Velodyne XYZIRT, 256 frames): a layout without padding and with ONE section field gains nothing -- the section
+  // reader's direct stores cost 262 us, pre-pass + side arrays + merge 59 + 174 + 51 us. Padded layouts (every store of
+  // every pass a sector read-modify-write) and several section fields are where writing each row once pays
+  if (e == nullptr && plan.n_sections == 1 && decode_fast_whole_rows(plan)) return false;
   uint32_t sum = 0;
   for (uint32_t s = 0; s < plan.n_sections; ++s) {
     const uint32_t b = plan.sections[s].bpv;

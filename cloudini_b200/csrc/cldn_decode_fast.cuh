@@ -50,7 +50,8 @@ struct FastDecParams {
   float mul[6];
   uint32_t off[6];
   uint32_t n_floatn;
-  uint32_t rows;   // the regular fields and the V5 section fields together cover every byte of a point: whole rows may be written
+  uint32_t rows;   // 1: the regular fields and the V5 section fields together cover every byte of a point, whole rows may be written;
+                   // 2: every field lies inside the point but some bytes belong to none (whole rows over a copy of the old ones); 0: neither
   // side mode (SIDE instantiations): the V5 section fields whose values wait in DecLaunch::side
   uint32_t n_side;
   uint32_t side_offset[kMaxSideFields];   // byte offset inside a point (CLDN_SKIP_STORE_OFFSET: decoded, not stored)
@@ -64,8 +65,14 @@ constexpr int kFWinAlloc = kFLead + kFWinBytes + 160;   // a thread's reader may
                                                         // point) + two prefetched words past the window
 constexpr int kFMaskWords = (kFMaxUnits * kFUnit + 31) / 32; // 6 words of terminator bits per thread
 static_assert(kFT * 8 * 16 <= kFWinAlloc, "the float staging aliases the window");
-constexpr int kFSideOff = (kFWinAlloc + 15) & ~15;      // SIDE: the tile's section values (cp.async at the tile start) behind the window
-constexpr int kFSideBytes = 8192;                        //   sum over the section fields of tile points * bpv fits here (decode_side_plan)
+// SIDE: the tile's section values (cp.async at the tile start) live behind a window of at most 9 units per thread -- enough
+// for every tile the fast reader accepts (<= 4 bytes per value, <= 16 bytes per point and thread slot) -- so that window +
+// values + the static shared memory still fit 7 CTAs per SM (a 32-frame batch is one chunk per resident CTA: with 6 per SM
+// a seventh of the chunks waits for a second round and the launch takes twice as long -- measured)
+constexpr int kFSideMaxUnits = 9;
+constexpr int kFSideOff = (kFLead + kFSideMaxUnits * kFT * kFUnit + 160 + 15) & ~15;   // 18608
+constexpr int kFSideBytes = 8192;                        // sum over the section fields of tile points * bpv fits here (decode_side_plan)
+static_assert(kFT * 8 * 16 <= kFSideOff, "the float staging aliases the window, not the section values");
 constexpr int kFOut2Off = (kFWinAlloc + 15) & ~15;      // split staging (SPLIT): 4 slots per lane, private to each warp, behind the window
 constexpr int kFOut2Bytes = kFT * 4 * 16;               // 8 KB
 
@@ -141,6 +148,7 @@ __global__ void __launch_bounds__(kFT, CLDN_FAST_DEC_MINB) decode_floatn_fast_ke
   constexpr int kFTilePts = kFT * FP;
   constexpr int kSlots = K <= 4 ? 1 : 2;                     // 16-byte staging slots per point
   constexpr bool kSplit = CLDN_FAST_DEC_SPLIT && CLDN_FAST_DEC_CPASYNC && K <= 4 && FP == 8 && !ROWS && !SIDE;
+  constexpr int kMaxU = SIDE ? (kFSideMaxUnits < kFMaxUnits ? kFSideMaxUnits : kFMaxUnits) : kFMaxUnits;   // window units per thread
   extern __shared__ __align__(16) uint8_t dyn_smem[];
   __shared__ FastShared sh;
   uint8_t* win = dyn_smem;                                    // kFLead + window bytes
@@ -221,7 +229,15 @@ __global__ void __launch_bounds__(kFT, CLDN_FAST_DEC_MINB) decode_floatn_fast_ke
     // reader runs behind this kernel and overwrites its bytes), the warp builds its 32 * FP points as contiguous rows in
     // shared memory and writes them with 16-byte stores. Per-field 4-byte stores of 32 lanes touch one 32-byte sector
     // per lane and field (XYZIRT, step 22: 16 sectors per store instruction measured, 5x the row bytes through L2).
-    const bool rows = ROWS && !dense4 && Q.rows != 0u && step * (32u * kFP) <= 4096u && (reinterpret_cast<uintptr_t>(out) & 15u) == 0u;
+    // A warp's staging holds 4 KB: layouts whose 32 * FP rows need more go out in 2, 4 or 8 passes of contiguous rows (the
+    // owner lanes of a pass fill it, everybody copies it out). Q.rows == 2: some bytes of a point belong to no field
+    // (padding); they must keep what the caller's buffer holds, so a pass starts from the OLD rows (cp.async, coalesced) --
+    // one full-sector read + one full-sector write per 32 bytes of output where per-field stores are one partial-sector
+    // write per field and point (measured on C3, step 32: the kernel is bound by L2 sector writes, 5 per point).
+    uint32_t rows_shift = 0;
+    while (((step * (32u * kFP)) >> rows_shift) > 4096u && rows_shift < 3u) ++rows_shift;
+    const bool rows = ROWS && !dense4 && Q.rows != 0u && ((step * (32u * kFP)) >> rows_shift) <= 4096u && (reinterpret_cast<uintptr_t>(out) & 15u) == 0u;
+    const bool rows_holes = Q.rows == 2u;
     uint32_t row_align = step;
 #pragma unroll
     for (int f = 0; f < K; ++f) row_align |= off[f];
@@ -255,7 +271,7 @@ __global__ void __launch_bounds__(kFT, CLDN_FAST_DEC_MINB) decode_floatn_fast_ke
       uint32_t want = c0 + est + (est >> 3) + 96u;
       uint32_t nu = (want + (kFT * kFUnit - 1)) / (kFT * kFUnit);
       nu = nu < 3u ? 3u : (nu | 1u);
-      if (nu > kFMaxUnits) nu = kFMaxUnits;
+      if (nu > kMaxU) nu = kMaxU;
       if (pre) nu = pre_nu;
       if (SIDE) {
         // the tile's section values (whole tile: a chunk's slot holds kChunkPoints values whatever its point count) are
@@ -271,6 +287,12 @@ __global__ void __launch_bounds__(kFT, CLDN_FAST_DEC_MINB) decode_floatn_fast_ke
           soff += bytes;
         }
         async_commit();
+      }
+      if (ROWS && rows && rows_holes) {
+        // the tile's old rows are needed behind the parse: ask them into L2 now
+        const uint8_t* orow = out + static_cast<size_t>(pt0) * step;
+        const uint32_t obytes = tile_pts * step;
+        for (uint32_t o = 128u * threadIdx.x; o < obytes; o += 128u * kFT) prefetch_l2(orow + o);
       }
       uint32_t m[kFMaskWords];
       uint32_t total, incl, cnt;
@@ -293,7 +315,7 @@ __global__ void __launch_bounds__(kFT, CLDN_FAST_DEC_MINB) decode_floatn_fast_ke
           // the whole window lies inside the payload (every tile but the first / last few of a frame): cp.async, global ->
           // shared without the register round trip, every request of the thread in flight at once
 #pragma unroll
-          for (int r = 0; r < kFMaxUnits; ++r) {
+          for (int r = 0; r < kMaxU; ++r) {
             if (r < static_cast<int>(nu)) async_copy16(sv + r * kFT, gv + r * kFT);
           }
           async_commit();
@@ -302,7 +324,7 @@ __global__ void __launch_bounds__(kFT, CLDN_FAST_DEC_MINB) decode_floatn_fast_ke
           // the whole window lies inside the payload (every tile but the first / last few of a frame): plain loads, all of
           // a thread's requests in flight before the first store
 #pragma unroll
-          for (int r0 = 0; r0 < kFMaxUnits; r0 += 4) {   // 4 requests in flight per thread and round (16 registers)
+          for (int r0 = 0; r0 < kMaxU; r0 += 4) {   // 4 requests in flight per thread and round (16 registers)
             if (r0 < static_cast<int>(nu)) {
               uint4 q[4];
 #pragma unroll
@@ -330,7 +352,7 @@ __global__ void __launch_bounds__(kFT, CLDN_FAST_DEC_MINB) decode_floatn_fast_ke
 #pragma unroll
         for (int r = 0; r < kFMaskWords; ++r) m[r] = 0;
 #pragma unroll
-        for (int u = 0; u < kFMaxUnits; ++u) {
+        for (int u = 0; u < kMaxU; ++u) {
           if (u < static_cast<int>(nu)) {
             const uint4 q = *reinterpret_cast<const uint4*>(win + kFLead + slice0 + kFUnit * u);
             // (x * 0x00204081) >> 28 collects bits 7, 15, 23, 31 into a nibble
@@ -369,8 +391,8 @@ __global__ void __launch_bounds__(kFT, CLDN_FAST_DEC_MINB) decode_floatn_fast_ke
         for (int w = 0; w < kFW; ++w) total += sh.wcnt[w];
         if (total >= n_vals) break;
         // too few values in the window: widen it if the chunk has more bytes, otherwise give the chunk to the careful kernel
-        if (nu >= kFMaxUnits || wend <= nu * (kFT * kFUnit)) { redo = true; break; }
-        nu = min(static_cast<uint32_t>(kFMaxUnits), nu + 2u);
+        if (nu >= kMaxU || wend <= nu * (kFT * kFUnit)) { redo = true; break; }
+        nu = min(static_cast<uint32_t>(kMaxU), nu + 2u);
         __syncthreads();  // everybody has read wcnt before the next round overwrites it
       }
       if (redo) break;
@@ -542,12 +564,12 @@ __global__ void __launch_bounds__(kFT, CLDN_FAST_DEC_MINB) decode_floatn_fast_ke
           const uint8_t* nab = nfirst - nc0;
           uint32_t nnu = (nc0 + used + (used >> 3) + 96u + (kFT * kFUnit - 1)) / (kFT * kFUnit);
           nnu = nnu < 3u ? 3u : (nnu | 1u);
-          if (nnu > kFMaxUnits) nnu = kFMaxUnits;
+          if (nnu > kMaxU) nnu = kMaxU;
           if (ncursor < size && nab >= sh.pay_lo && (static_cast<uint64_t>(sh.pay_hi - nab) >> 4) >= nnu * kFT) {
             const uint4* gv = reinterpret_cast<const uint4*>(nab) + threadIdx.x;
             uint4* sv = reinterpret_cast<uint4*>(win + kFLead) + threadIdx.x;
 #pragma unroll
-            for (int r = 0; r < kFMaxUnits; ++r) {
+            for (int r = 0; r < kMaxU; ++r) {
               if (r < static_cast<int>(nnu)) async_copy16(sv + r * kFT, gv + r * kFT);
             }
             async_commit();
@@ -649,6 +671,7 @@ __global__ void __launch_bounds__(kFT, CLDN_FAST_DEC_MINB) decode_floatn_fast_ke
       // MODE: 0 = 16-byte slots, 4 / 2 / 1 = whole rows assembled with 4- / 2- / 1-byte stores. One instantiation of the
       // loop per mode behind a CTA-uniform branch: as one loop the three row variants were if-converted and every tile
       // issued all of them (25 predicated-off instructions per point on XYZIRT).
+      uint8_t* row0 = reinterpret_cast<uint8_t*>(wst) + static_cast<uint32_t>(kFP * lane) * step;   // my first row in the staging (row modes)
       auto emit = [&](auto mode_tag) {
         constexpr int MODE = decltype(mode_tag)::value;
 #pragma unroll
@@ -667,7 +690,7 @@ __global__ void __launch_bounds__(kFT, CLDN_FAST_DEC_MINB) decode_floatn_fast_ke
             fl[f] = __float_as_uint(__fmul_rn(__int2float_rn(v), mul[f]));
           }
           if (MODE != 0) {
-            uint8_t* row = reinterpret_cast<uint8_t*>(wst) + static_cast<uint32_t>(kFP * lane + j) * step;
+            uint8_t* row = row0 + static_cast<uint32_t>(j) * step;
 #pragma unroll
             for (int f = 0; f < K; ++f) {
               uint8_t* d = row + off[f];
@@ -689,38 +712,59 @@ __global__ void __launch_bounds__(kFT, CLDN_FAST_DEC_MINB) decode_floatn_fast_ke
           }
         }
       };
-      if (!ROWS || !rows) emit(std::integral_constant<int, 0>{});
-      else if ((row_align & 3u) == 0u) emit(std::integral_constant<int, 4>{});
-      else if ((row_align & 1u) == 0u) emit(std::integral_constant<int, 2>{});
-      else emit(std::integral_constant<int, 1>{});
-      if (SIDE && ROWS && rows) {
-        // the section values of my kFP consecutive points go into my rows (bytes: a row may sit at any alignment)
-        uint32_t soff = 0;
-        for (uint32_t s = 0; s < Q.n_side; ++s) {
-          const uint32_t bpv = Q.side_bpv[s], so = Q.side_offset[s];
-          const uint8_t* sv = dyn_smem + kFSideOff + soff + threadIdx.x * kFP * bpv;
-          soff += kFTilePts * bpv;
-          if (so == CLDN_SKIP_STORE_OFFSET) continue;
-          uint8_t* d = reinterpret_cast<uint8_t*>(wst) + static_cast<uint32_t>(kFP * lane) * step + so;
-          for (uint32_t j = 0; j < static_cast<uint32_t>(kFP); ++j) {
-            for (uint32_t b = 0; b < bpv; ++b) d[j * step + b] = sv[j * bpv + b];
-          }
-        }
-      }
-      __syncwarp();
       // ---- copy-out: lane l of iteration i takes point 32 i + l of the warp's 32 * FP ----
       const uint32_t wp0 = pt0 + warp * (32 * kFP);
       const uint32_t wn = wp0 < n_points ? min(static_cast<uint32_t>(32 * kFP), n_points - wp0) : 0u;
       uint8_t* dst0 = sh.out + static_cast<size_t>(wp0 + lane) * step;
-      if (rows) {
-        const uint32_t total = wn * step;                      // bytes of this warp's rows; its first byte is 16-byte aligned
-        uint8_t* dst = sh.out + static_cast<size_t>(wp0) * step;
-        const uint8_t* src = reinterpret_cast<const uint8_t*>(wst);
-        for (uint32_t o = 16u * lane; o + 16u <= total; o += 512u) {
-          __stcs(reinterpret_cast<uint4*>(dst + o), *reinterpret_cast<const uint4*>(src + o));
+      if (!ROWS || !rows) {
+        emit(std::integral_constant<int, 0>{});
+        __syncwarp();
+      }
+      if (ROWS && rows) {
+        // ---- whole rows, 1 << rows_shift passes of contiguous rows through the warp's 4 KB ----
+        const uint32_t lpp = 32u >> rows_shift;            // owner lanes per pass
+        const uint32_t rpp = lpp * kFP;                    // rows per pass
+        uint8_t* const wsb = reinterpret_cast<uint8_t*>(wst);
+        row0 = wsb + static_cast<uint32_t>(kFP * (lane & (lpp - 1u))) * step;
+        for (uint32_t h = 0; h < (1u << rows_shift); ++h) {
+          const uint32_t p_lo = h * rpp;
+          const uint32_t cnt_rows = wn > p_lo ? min(rpp, wn - p_lo) : 0u;
+          const uint32_t total = cnt_rows * step;          // bytes of this pass; its first byte is 16-byte aligned
+          uint8_t* dst = sh.out + static_cast<size_t>(wp0 + p_lo) * step;
+          const uint32_t tail0 = total & ~15u;
+          if (rows_holes) {
+            for (uint32_t o = 16u * lane; o + 16u <= total; o += 512u) async_copy16(wsb + o, dst + o);
+            async_commit();
+            if (tail0 + lane < total) wsb[tail0 + lane] = dst[tail0 + lane];
+            async_wait_all();
+            __syncwarp();
+          }
+          if ((static_cast<uint32_t>(lane) >> (5u - rows_shift)) == h) {
+            if ((row_align & 3u) == 0u) emit(std::integral_constant<int, 4>{});
+            else if ((row_align & 1u) == 0u) emit(std::integral_constant<int, 2>{});
+            else emit(std::integral_constant<int, 1>{});
+            if (SIDE) {
+              // the section values of my kFP consecutive points go into my rows (bytes: a row may sit at any alignment)
+              uint32_t soff = 0;
+              for (uint32_t s = 0; s < Q.n_side; ++s) {
+                const uint32_t bpv = Q.side_bpv[s], so = Q.side_offset[s];
+                const uint8_t* sv = dyn_smem + kFSideOff + soff + threadIdx.x * kFP * bpv;
+                soff += kFTilePts * bpv;
+                if (so == CLDN_SKIP_STORE_OFFSET) continue;
+                uint8_t* d = row0 + so;
+                for (uint32_t j = 0; j < static_cast<uint32_t>(kFP); ++j) {
+                  for (uint32_t b = 0; b < bpv; ++b) d[j * step + b] = sv[j * bpv + b];
+                }
+              }
+            }
+          }
+          __syncwarp();
+          for (uint32_t o = 16u * lane; o + 16u <= total; o += 512u) {
+            __stcs(reinterpret_cast<uint4*>(dst + o), *reinterpret_cast<const uint4*>(wsb + o));
+          }
+          if (tail0 + lane < total) dst[tail0 + lane] = wsb[tail0 + lane];
+          __syncwarp();   // the next pass refills the staging
         }
-        const uint32_t tail0 = total & ~15u;
-        if (tail0 + lane < total) dst[tail0 + lane] = src[tail0 + lane];
       } else if (kSlots == 1) {
         // slot of point 32 i + l: owner lane 4 i + (l >> 3), its point l & 7 -> 8 (4 i + (l >> 3)) + ((l & 7) ^ ((4 i + (l >> 3)) & 7))
         const uint32_t lh = lane >> 3, ll = lane & 7;
@@ -898,7 +942,7 @@ bool decode_fast_plan(const Plan& plan, FastDecParams* Q) {
       covered |= ((1ull << sf.bpv) - 1ull) << sf.offset;
     }
     const uint64_t all = plan.point_step == 64 ? ~0ull : ((1ull << plan.point_step) - 1ull);
-    if (ok && covered == all) Q->rows = 1;
+    if (ok) Q->rows = covered == all ? 1 : 2;   // 2: padding bytes -- whole rows are written over a copy of the old ones
   }
   return true;
 }
@@ -906,6 +950,10 @@ bool decode_fast_plan(const Plan& plan, FastDecParams* Q) {
 bool decode_fast_general_plan(const Plan& plan) {
   FastDecParams Q;
   return decode_fast_plan(plan, &Q);
+}
+bool decode_fast_whole_rows(const Plan& plan) {
+  FastDecParams Q;
+  return decode_fast_plan(plan, &Q) && Q.rows == 1;
 }
 
 // ---- side mode pre-pass: where does the regular stream of every chunk end? ----------------------------------------------

@@ -104,6 +104,7 @@ int launch_decode(const Plan& host_plan, const DecLaunch& L, cudaStream_t stream
 int launch_decode_tiles(const Plan& host_plan, const DecLaunch& L, cudaStream_t stream);
 int launch_decode_fast(const Plan& host_plan, const DecLaunch& L, int sm_count, cudaStream_t stream);
 bool decode_fast_general_plan(const Plan& host_plan);  // a FloatN group and / or scalar lossy floats, 3..6 values per point
+bool decode_fast_whole_rows(const Plan& host_plan);    // ... whose regular + section fields cover every byte of a point
 bool decode_fast_enabled();  // CLDN_B200_DECODE_FAST=0 keeps the careful chunk-sequential kernel alone
 bool decode_tiles_sequential(uint32_t n_chunks_total);  // which of the two FloatN kernels launch_decode_tiles will pick
 uint32_t decode_tile_bytes();

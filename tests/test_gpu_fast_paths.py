@@ -348,6 +348,7 @@ def test_sections_ahead_with_chunks_for_the_careful_kernels(oracle, monkeypatch)
     """NaN markers / wide values in the regular stream: the chunk's sections were decoded ahead, its rows were not merged; the
     careful kernels decode stream and sections again. Batches mix plain and redone chunks."""
     monkeypatch.setenv("CLDN_B200_DECODE_MODE", "seq")
+    monkeypatch.setenv("CLDN_B200_DECODE_SIDE", "1")   # (unpadded one-section layouts like XYZIRT only take it when asked)
     n = 70_000
     for make in (lambda: synth.cloud_c3(n, seed=11, version=5), lambda: _xyzirt(n, 5), lambda: _int_sections_layout(n, 12)):
         info, plain = make()
@@ -407,8 +408,16 @@ def test_sections_ahead_on_damaged_blobs_reports_like_sections_behind(oracle, mo
 
 
 def test_sections_ahead_limits(oracle, monkeypatch):
-    """More adaptive fields than the side arrays carry: sections behind the stream, same bytes. Empty clouds: nothing runs."""
+    """More adaptive fields than the side arrays carry: sections behind the stream, same bytes. Defaults: padded layouts take
+    the side mode, an unpadded layout with one section field (XYZIRT) does not."""
     monkeypatch.setenv("CLDN_B200_DECODE_MODE", "seq")
+    monkeypatch.delenv("CLDN_B200_DECODE_SIDE", raising=False)
+    for (info, cloud), expect in ((synth.cloud_c3(3000, seed=1, version=5), True), (_xyzirt(3000, 3), False)):
+        blob = oracle.encode(info, cloud)
+        hdr = len(cb.PointcloudEncoder(info).getHeader())
+        outs, _, ahead = _decode_batch_side(info, [blob], hdr, cloud.size, 0x42)
+        assert ahead == expect
+        assert np.array_equal(outs[0], _want(oracle, blob, cloud.size, 0x42))
     F = cb.FieldType
     n = 5_000
     rng = np.random.default_rng(4)
