@@ -322,9 +322,12 @@ def _int_sections_layout(n, seed, with_u64=False, only_u64=False):
     return info, raw.reshape(-1)
 
 
+@pytest.mark.parametrize("holes", ["0", "1"])
 @pytest.mark.parametrize("n", [1, 9, 1024, 4097, 32768, 32769, 70_001])
-def test_sections_ahead_same_bytes_as_sections_behind(oracle, monkeypatch, n):
+def test_sections_ahead_same_bytes_as_sections_behind(oracle, monkeypatch, n, holes):
+    """holes = 1: padded layouts leave the fast reader as whole rows over a copy of the old rows (opt-in: measured slower)."""
     monkeypatch.setenv("CLDN_B200_DECODE_MODE", "seq")
+    monkeypatch.setenv("CLDN_B200_DECODE_ROWS_HOLES", holes)
     cases = [synth.cloud_c3(n, seed=n, version=5), _xyzirt(n, 3), _int_sections_layout(n, n), _int_sections_layout(n, n + 1, only_u64=True)]
     for info, cloud in cases:
         step = info.point_step
