@@ -27,9 +27,6 @@ namespace cldn {
 #ifndef CLDN_FAST_ENC_MINB
 #define CLDN_FAST_ENC_MINB 6
 #endif
-#ifndef CLDN_FAST_ENC_PIPE
-#define CLDN_FAST_ENC_PIPE 0   // 1 = pass 1 of tile i + 1 runs between pass 2 of tile i and its look-back result (build variant, below)
-#endif
 
 constexpr int kET = 128;                  // threads per CTA
 constexpr int kEW = kET / 32;
@@ -138,6 +135,9 @@ __device__ __noinline__ uint32_t encode_tile_careful(const EncFrame& F, const Fl
 // is quantised and packed, tile i + G is already on its way into the other input buffer (cp.async, 16 bytes per lane,
 // straight into the transposed slots): the load latency that a one-tile-per-CTA kernel exposes at every CTA start
 // (measured: a third of all stall samples) is hidden behind the previous tile's arithmetic.
+// Also measured (commit 5f46c71 has the code: CLDN_FAST_ENC_PIPE=1/2, removed again): pass 1 of tile i + 1 between pass 2 of tile i and its
+// look-back result, with and without the barrier behind the copy-out: 1.047 / 1.089 vs 0.986 ms per 128 frames -- the
+// later inclusive prefix makes every successor's look-back longer than the wait it hides.
 // All G CTAs must be co-resident (the grid is sized by the occupancy query): a CTA spins on aggregates of tiles with a
 // smaller global index, which belong to CTAs that are running.
 __device__ __forceinline__ void tile_coords(const EncLaunch& L, uint32_t i, uint32_t* fi, uint32_t* t) {
@@ -150,7 +150,6 @@ __device__ __forceinline__ void tile_coords(const EncLaunch& L, uint32_t i, uint
   }
 }
 
-#if !CLDN_FAST_ENC_PIPE
 __global__ void __launch_bounds__(kET, CLDN_FAST_ENC_MINB) encode_xyzi_fast_kernel(const EncLaunch L, const FloatNParams P) {
   extern __shared__ __align__(16) uint8_t dyn_smem[];
   __shared__ EncFastShared sh;
@@ -368,272 +367,6 @@ __global__ void __launch_bounds__(kET, CLDN_FAST_ENC_MINB) encode_xyzi_fast_kern
   }
   async_wait_all();
 }
-#else
-// Software-pipelined variant. The tile loop above waits twice on other CTAs' progress: warp 0 for the look-back words and
-// then everybody for warp 0 (barrier stall 2.8 per issue in ncu). Here the words of tile i + 1 are computed (pass 1, from the
-// other input buffer) between pass 2 of tile i and the moment tile i's look-back result is needed, so the round trip to the
-// status words has a whole pass 1 to come back. Per iteration: [sizes of tile i: scan + barrier] [pass 2 of tile i]
-// [look-back words requested] [pass 1 of tile i + 1] [look-back evaluated] [barrier, copy-out of tile i, barrier]
-// [tile i + 2 requested into tile i's buffer]. X[][] is free once pass 2 has consumed it, so the register budget is the same.
-// Variant 2: the barrier behind the copy-out is gone -- the next tile is requested right behind the NEXT iteration's size barrier
-// (which every warp reaches after its share of the copy-out) and has pass 2 to arrive.
-__global__ void __launch_bounds__(kET, CLDN_FAST_ENC_MINB) encode_xyzi_fast_kernel(const EncLaunch L, const FloatNParams P) {
-  extern __shared__ __align__(16) uint8_t dyn_smem[];
-  __shared__ EncFastShared sh;
-  __shared__ EncFrame s_F[2];
-  __shared__ FloatNParams s_P;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const bool aligned16 = (L.flags & kEncInputsAligned16) != 0u;
-  const uint32_t G = gridDim.x;
-
-  if (blockIdx.x == 0) handle_empty_frames(L);
-  if (blockIdx.x >= L.n_tiles_total) return;
-
-  // asks for the 1024 points of tile `idx` into buffer b (transposed slots) and puts its frame record next to it;
-  // false: no such tile, or not a full tile of 16-byte aligned points (pass 1 then loads it itself / leaves it to the exact path)
-  auto request = [&](uint32_t idx, uint32_t b) -> bool {
-    if (idx >= L.n_tiles_total) return false;
-    uint32_t f_, t_;
-    tile_coords(L, idx, &f_, &t_);
-    if (threadIdx.x == 0) s_F[b] = L.frames[f_];
-    const EncFrame* NF = L.frames + f_;   // (every thread needs the input pointer and size for its own copies)
-    const uint32_t p0 = t_ * kETilePts;
-    if (!aligned16 || p0 + kETilePts > NF->n_points) return false;
-    const uint4* src = reinterpret_cast<const uint4*>(NF->in) + p0 + warp * (32 * kEP) + lane;
-    uint4* wsl = reinterpret_cast<uint4*>(dyn_smem + b * kEBufBytes) + warp * (32 * kEP);
-#pragma unroll
-    for (int k = 0; k < kEP; ++k) {
-      const uint32_t q = 32u * k + lane, ol = q >> 3;
-      async_copy16(wsl + 8 * ol + ((q & 7u) ^ (ol & 7u)), src + 32 * k);
-    }
-    return true;
-  };
-
-  uint32_t i = blockIdx.x;              // the tile pass 1 runs on next
-  bool have_n = request(i, 0);          // ... and whether its points were requested with cp.async
-  async_commit();
-#if CLDN_FAST_ENC_PIPE == 1
-  bool have_nn = request(i + G, 1);     // the tile after it
-  async_commit();
-#endif
-  if (threadIdx.x == 0) s_P = P;
-  __syncthreads();
-
-  bool pending = false;                 // a tile's words sit in X[][] (pass 1 done), its buffer is `cur`
-  uint32_t cur = 0;                     // pending: that tile's buffer; else the buffer of tile i
-  uint32_t pfi = 0, pt = 0;             // the pending tile's frame and tile-in-frame
-  uint32_t X[kEP][4];
-  uint32_t mine = 0, tail4 = 0;
-  bool fast = false;
-
-  while (true) {
-    uint32_t total = 0;
-    bool staged = false;                // the pending tile went through pass 2: look-back + copy-out follow behind pass 1
-    LookbackPoll lb;
-    if (pending) {
-      const EncFrame& F = s_F[cur];
-      const uint32_t tile = F.tile_begin + pt;
-      // ---- offsets: warp scan + warp totals ----
-      uint32_t inc = mine;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t up = __shfl_up_sync(0xffffffffu, inc, d);
-        if (lane >= d) inc += up;
-      }
-      uint32_t ptail = __shfl_up_sync(0xffffffffu, tail4, 1);
-      if (lane == 31) { sh.wtot[warp] = inc; sh.wtail[warp] = tail4; }
-      const int any_slow = __syncthreads_or(fast ? 0 : 1);  // also: every warp is done with the tile's transposed input
-      if (!any_slow) {
-        uint8_t* stage = dyn_smem + cur * kEBufBytes;
-#if CLDN_FAST_ENC_PIPE == 2
-        // the other buffer is free (its tile was copied out before this barrier): the next tile's points land behind pass 2
-        have_n = request(i, cur ^ 1u);
-        async_commit();
-#endif
-        uint32_t wbase = 0;
-#pragma unroll
-        for (int w = 0; w < kEW; ++w) {
-          const uint32_t c = sh.wtot[w];
-          if (w < warp) wbase += c;
-          total += c;
-        }
-        // the tile's size is final: publish it before the bytes are packed, so that successors never wait for pass 2
-        if (warp == 0) lb.begin(L.status, F.tile_begin, tile, L.epoch, total);
-        if (lane == 0) ptail = warp > 0 ? sh.wtail[warp - 1] : 0u;
-        const uint32_t off = wbase + inc - mine;
-        // ---- pass 2: 64-bit window, aligned word flushes ----
-        uint32_t bit = 8u * off;
-        uint32_t lo = __funnelshift_rc(ptail, 0u, 32u - (bit & 31u));   // the last off % 4 bytes of the predecessor (0 if none)
-        uint32_t wa = (bit >> 3) & ~3u;                                 // byte address of that word in the staging buffer
-#pragma unroll
-        for (int j = 0; j < kEP; ++j) {
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint32_t x = X[j][k];
-            const uint32_t b = top_bit(x);
-            lo |= __funnelshift_l(0u, x, bit);                 // x << (bit % 32)
-            const uint32_t hi = __funnelshift_l(x, 0u, bit);   // x >> (32 - bit % 32), 0 for bit % 32 == 0
-            bit += (b & 0x18u) + 8u;
-            const uint32_t wn = (bit >> 3) & ~3u;
-            if (wn != wa) { *reinterpret_cast<uint32_t*>(stage + wa) = lo; lo = hi; }
-            wa = wn;
-          }
-        }
-        if (threadIdx.x == kET - 1 && (bit & 31u) != 0u) *reinterpret_cast<uint32_t*>(stage + wa) = lo;  // nobody follows the tile's last thread
-        if (warp == 0) lb.issue(L.status, F.tile_begin, L.epoch);   // evaluated behind the next tile's pass 1
-        staged = true;
-      } else {
-        // exact path: up to 20 bytes per point, staged across BOTH buffers -- the next tile's copies are drained first; the
-        // pipeline starts again behind this tile (tile i into buffer 0, tile i + G into buffer 1)
-        async_wait_all();
-        __syncthreads();
-        total = encode_tile_careful<4>(F, s_P, pt * kETilePts, dyn_smem, sh.scan);
-        if (warp == 0) {
-          lb.begin(L.status, F.tile_begin, tile, L.epoch, total);
-          const uint64_t e = lb.finish(L.status, F.tile_begin, tile, L.epoch, total);
-          if (lane == 0) sh.excl = e;
-        }
-        __syncthreads();
-        finish_tile<kETilePts>(L, F, pfi, pt, dyn_smem, total, sh.excl);
-        __syncthreads();
-        pending = false;
-        cur = 0;
-        have_n = request(i, 0);
-        async_commit();
-#if CLDN_FAST_ENC_PIPE == 1
-        have_nn = request(i + G, 1);
-        async_commit();
-#endif
-        __syncthreads();   // the frame records
-      }
-    }
-
-    // ---- pass 1 of tile i (if there is one) from buffer nb ----
-    const uint32_t nb = pending ? cur ^ 1u : cur;
-    const bool n_exists = i < L.n_tiles_total;
-    uint32_t nfi = 0, nt = 0;
-    if (n_exists) {
-      tile_coords(L, i, &nfi, &nt);
-      const EncFrame* NF = L.frames + nfi;   // (not s_F[nb]: variant 2 writes that record without a barrier before this point)
-      const uint8_t* const f_in = NF->in;
-      const uint32_t tile_p0 = nt * kETilePts;
-      const bool full = tile_p0 + kETilePts <= NF->n_points;
-      mine = 0;
-      tail4 = 0;
-      fast = full;
-      if (full) {
-        const uint32_t wp0 = tile_p0 + warp * (32 * kEP);
-        uint4* wsl = reinterpret_cast<uint4*>(dyn_smem + nb * kEBufBytes) + warp * (32 * kEP);
-        if (have_n) {
-          // outstanding groups: this tile's, and behind a fresh start also the next tile's
-#if CLDN_FAST_ENC_PIPE == 1
-          if (pending) async_wait_all(); else async_wait_all_but_last();
-#else
-          async_wait_all();
-#endif
-        } else {
-          // ---- load + transpose inside the warp: lane l of iteration k loads point 32 k + l of the warp's 256 ----
-#pragma unroll
-          for (int k = 0; k < kEP; ++k) {
-            const uint32_t q = 32u * k + lane;
-            uint4 v;
-            if (aligned16) {
-              v = __ldcs(reinterpret_cast<const uint4*>(f_in) + wp0 + q);
-            } else {
-              const uint8_t* ptr = f_in + static_cast<size_t>(wp0 + q) * 16u;
-              v = make_uint4(load_u32(ptr), load_u32(ptr + 4), load_u32(ptr + 8), load_u32(ptr + 12));
-            }
-            const uint32_t ol = q >> 3;  // owner lane; slot of point j of lane l: 8 l + (j ^ (l & 7))
-            wsl[8 * ol + ((q & 7u) ^ (ol & 7u))] = v;
-          }
-        }
-        // previous point of my first point: 0 at a chunk start, else quantised like any point
-        const uint32_t p_first = wp0 + lane * kEP;
-        uint4 pvu = make_uint4(0, 0, 0, 0);
-        if (lane == 0 && (p_first % kChunkPoints) != 0) {
-          const uint8_t* ptr = f_in + static_cast<size_t>(p_first - 1) * 16u;
-          pvu = make_uint4(load_u32(ptr), load_u32(ptr + 4), load_u32(ptr + 8), load_u32(ptr + 12));
-        }
-        __syncwarp();
-        if (lane != 0) {
-          const uint32_t pl = lane - 1;
-          pvu = wsl[8 * pl + (7u ^ (pl & 7u))];
-        }
-        float trk = 0.0f;
-        int32_t prev[4];
-        {
-          const float pf[4] = {__uint_as_float(pvu.x), __uint_as_float(pvu.y), __uint_as_float(pvu.z), __uint_as_float(pvu.w)};
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const float sc = __fmul_rn(pf[k], P.mul[k]);
-            trk = max_nan(trk, fabsf(sc));
-            prev[k] = __float2int_rn(sc);
-          }
-        }
-        // ---- pass 1: LEB128 words of my 32 values + their total length ----
-        uint32_t nbl[3] = {0, 0, 0};  // bit lengths of my last three values (for the tail word)
-#pragma unroll
-        for (int j = 0; j < kEP; ++j) {
-          const uint4 u = wsl[8 * lane + (j ^ (lane & 7))];
-          const float pf[4] = {__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z), __uint_as_float(u.w)};
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const float sc = __fmul_rn(pf[k], P.mul[k]);   // _mm_mul_ps: IEEE RN, never contracted
-            trk = max_nan(trk, fabsf(sc));
-            const int32_t q = __float2int_rn(sc);          // cvtps2dq under the default MXCSR: ties to even
-            const uint32_t d = static_cast<uint32_t>(q) - static_cast<uint32_t>(prev[k]);
-            prev[k] = q;
-            const uint32_t zz1 = ((d << 1) ^ static_cast<uint32_t>(static_cast<int32_t>(d) >> 31)) + 1u;  // < 2^28 on the fast path
-            uint32_t x = (zz1 & 0xFFFFC000u) * 3u + zz1;           // lo14 + hi14 * 2^16 (one LOP3 + one IMAD)
-            x = x + (x & 0x3F803F80u);
-            const uint32_t b = top_bit(x);                           // inside the value's last byte (garbage tiles: x may be 0)
-            x |= low_mask(b) & 0x00808080u;                          // continuation flags on every byte below it
-            X[j][k] = x;
-            mine += b >> 3;
-            if (j == kEP - 1 && k >= 1) nbl[k - 1] = (b & 0x18u) + 8u;
-          }
-        }
-        mine += kEP * 4;
-        tail4 = __funnelshift_rc(tail4, X[kEP - 1][1], nbl[0]);
-        tail4 = __funnelshift_rc(tail4, X[kEP - 1][2], nbl[1]);
-        tail4 = __funnelshift_rc(tail4, X[kEP - 1][3], nbl[2]);
-        fast = trk < 33554432.0f;  // 2^25; false for NaN
-      }
-    }
-
-    // ---- the pending tile's place in the frame, copy-out, its buffer to the tile after next ----
-#if CLDN_FAST_ENC_PIPE == 1
-    bool have_next_n = have_nn;
-#endif
-    if (staged) {
-      const EncFrame& F = s_F[cur];
-      const uint32_t tile = F.tile_begin + pt;
-      if (warp == 0) {
-        lb.eval(L.epoch);
-        const uint64_t e = lb.finish(L.status, F.tile_begin, tile, L.epoch, total);
-        if (lane == 0) sh.excl = e;
-      }
-      __syncthreads();  // staged bytes + sh.excl complete
-      finish_tile<kETilePts>(L, F, pfi, pt, dyn_smem + cur * kEBufBytes, total, sh.excl);
-#if CLDN_FAST_ENC_PIPE == 1
-      __syncthreads();  // the buffer receives the tile after next
-      have_next_n = request(i + G, cur);
-      async_commit();
-#endif
-    }
-    if (!n_exists) break;   // (nothing pending any more either: a pending tile was finished above)
-    pending = true;
-    cur = nb;
-    pfi = nfi;
-    pt = nt;
-#if CLDN_FAST_ENC_PIPE == 1
-    have_n = have_next_n;
-#endif
-    i += G;
-  }
-  async_wait_all();
-}
-#endif
 
 static bool encode_fast_enabled() {
   const char* e = getenv("CLDN_B200_ENC_FAST");
