@@ -51,7 +51,8 @@ struct FastDecParams {
   uint32_t off[6];
   uint32_t n_floatn;
   uint32_t rows;   // 1: the regular fields and the V5 section fields together cover every byte of a point, whole rows may be written;
-                   // 2: every field lies inside the point but some bytes belong to none (whole rows over a copy of the old ones); 0: neither
+                   // 2: every field lies inside the point but some bytes belong to none (rows leave word by word, padding masked); 0: neither
+  uint64_t cover;  // rows == 2: bit b set <=> byte b of a point belongs to a field
   // side mode (SIDE instantiations): the V5 section fields whose values wait in DecLaunch::side
   uint32_t n_side;
   uint32_t side_offset[kMaxSideFields];   // byte offset inside a point (CLDN_SKIP_STORE_OFFSET: decoded, not stored)
@@ -231,9 +232,11 @@ __global__ void __launch_bounds__(kFT, CLDN_FAST_DEC_MINB) decode_floatn_fast_ke
     // per lane and field (XYZIRT, step 22: 16 sectors per store instruction measured, 5x the row bytes through L2).
     // A warp's staging holds 4 KB: layouts whose 32 * FP rows need more go out in 2, 4 or 8 passes of contiguous rows (the
     // owner lanes of a pass fill it, everybody copies it out). Q.rows == 2: some bytes of a point belong to no field
-    // (padding); they must keep what the caller's buffer holds, so a pass starts from the OLD rows (cp.async, coalesced) --
-    // one full-sector read + one full-sector write per 32 bytes of output where per-field stores are one partial-sector
-    // write per field and point (measured on C3, step 32: the kernel is bound by L2 sector writes, 5 per point).
+    // (padding) and must keep what the caller's buffer holds: the rows leave word by word, 32 consecutive words per store
+    // instruction, with the padding words switched off -- every sector is written once, where per-field stores write it
+    // once per field (measured on C3, step 32: the per-field reader is bound by L2 sector writes, 5 per point). Fetching
+    // the old rows to write whole ones was measured too: 1.90 vs 1.16 ms on C3 (a second 32 B per point from DRAM, and every
+    // pass of a warp waits for them).
     uint32_t rows_shift = 0;
     while (((step * (32u * kFP)) >> rows_shift) > 4096u && rows_shift < 3u) ++rows_shift;
     const bool rows = ROWS && !dense4 && Q.rows != 0u && ((step * (32u * kFP)) >> rows_shift) <= 4096u && (reinterpret_cast<uintptr_t>(out) & 15u) == 0u;
@@ -287,12 +290,6 @@ __global__ void __launch_bounds__(kFT, CLDN_FAST_DEC_MINB) decode_floatn_fast_ke
           soff += bytes;
         }
         async_commit();
-      }
-      if (ROWS && rows && rows_holes) {
-        // the tile's old rows are needed behind the parse: ask them into L2 now
-        const uint8_t* orow = out + static_cast<size_t>(pt0) * step;
-        const uint32_t obytes = tile_pts * step;
-        for (uint32_t o = 128u * threadIdx.x; o < obytes; o += 128u * kFT) prefetch_l2(orow + o);
       }
       uint32_t m[kFMaskWords];
       uint32_t total, incl, cnt;
@@ -732,13 +729,6 @@ __global__ void __launch_bounds__(kFT, CLDN_FAST_DEC_MINB) decode_floatn_fast_ke
           const uint32_t total = cnt_rows * step;          // bytes of this pass; its first byte is 16-byte aligned
           uint8_t* dst = sh.out + static_cast<size_t>(wp0 + p_lo) * step;
           const uint32_t tail0 = total & ~15u;
-          if (rows_holes) {
-            for (uint32_t o = 16u * lane; o + 16u <= total; o += 512u) async_copy16(wsb + o, dst + o);
-            async_commit();
-            if (tail0 + lane < total) wsb[tail0 + lane] = dst[tail0 + lane];
-            async_wait_all();
-            __syncwarp();
-          }
           if ((static_cast<uint32_t>(lane) >> (5u - rows_shift)) == h) {
             if ((row_align & 3u) == 0u) emit(std::integral_constant<int, 4>{});
             else if ((row_align & 1u) == 0u) emit(std::integral_constant<int, 2>{});
@@ -759,10 +749,31 @@ __global__ void __launch_bounds__(kFT, CLDN_FAST_DEC_MINB) decode_floatn_fast_ke
             }
           }
           __syncwarp();
-          for (uint32_t o = 16u * lane; o + 16u <= total; o += 512u) {
-            __stcs(reinterpret_cast<uint4*>(dst + o), *reinterpret_cast<const uint4*>(wsb + o));
+          if (rows_holes) {
+            // padded layout (step % 4 == 0): word by word, 32 consecutive words per store instruction, a word that holds padding
+            // is skipped or stored byte-wise -- the same full or partial sectors as per-field stores, once per sector
+            uint32_t r = (4u * lane) % step;             // byte offset of my word inside its row
+            const uint32_t adv = 128u % step;
+            for (uint32_t o = 4u * lane; o < total; o += 128u) {
+              const uint32_t nib = static_cast<uint32_t>(Q.cover >> r) & 0xFu;
+              const uint32_t wv = *reinterpret_cast<const uint32_t*>(wsb + o);
+              if (nib == 0xFu) {
+                __stcs(reinterpret_cast<unsigned int*>(dst + o), wv);
+              } else if (nib != 0u) {
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                  if ((nib >> b) & 1u) dst[o + b] = static_cast<uint8_t>(wv >> (8 * b));
+                }
+              }
+              r += adv;
+              if (r >= step) r -= step;
+            }
+          } else {
+            for (uint32_t o = 16u * lane; o + 16u <= total; o += 512u) {
+              __stcs(reinterpret_cast<uint4*>(dst + o), *reinterpret_cast<const uint4*>(wsb + o));
+            }
+            if (tail0 + lane < total) dst[tail0 + lane] = wsb[tail0 + lane];
           }
-          if (tail0 + lane < total) dst[tail0 + lane] = wsb[tail0 + lane];
           __syncwarp();   // the next pass refills the staging
         }
       } else if (kSlots == 1) {
@@ -929,6 +940,7 @@ bool decode_fast_plan(const Plan& plan, FastDecParams* Q) {
   for (int k = 0; k < kMaxSideFields; ++k) { Q->side_offset[k] = CLDN_SKIP_STORE_OFFSET; Q->side_bpv[k] = 1; }
   // rows: every byte of [0, point_step) is written by a regular field (4 bytes each here) or by a V5 section field
   Q->rows = 0;
+  Q->cover = 0;
   if (plan.point_step <= 64) {
     uint64_t covered = 0;
     bool ok = true;
@@ -942,11 +954,11 @@ bool decode_fast_plan(const Plan& plan, FastDecParams* Q) {
       covered |= ((1ull << sf.bpv) - 1ull) << sf.offset;
     }
     const uint64_t all = plan.point_step == 64 ? ~0ull : ((1ull << plan.point_step) - 1ull);
-    // 2 (padding bytes: whole rows written over a copy of the old ones) only on request: measured on C3 (32 x 1M points, step 32
-    // with 8 padding bytes) the decode went from 1.16 to 1.90 ms -- the old rows are a second 32 B per point from DRAM and
-    // every pass of a warp waits for them, which costs more than the partial-sector stores it replaces
+    // 2 (padding bytes): rows assembled in shared memory, stored word by word with the padding masked. CLDN_B200_DECODE_ROWS_HOLES=0
+    // keeps per-field stores for such layouts
     const char* he = getenv("CLDN_B200_DECODE_ROWS_HOLES");
-    const bool holes = he && he[0] == '1';
+    const bool holes = !(he && he[0] == '0') && (plan.point_step & 3u) == 0u;
+    Q->cover = covered;
     if (ok) Q->rows = covered == all ? 1 : (holes ? 2 : 0);
   }
   return true;

@@ -7,11 +7,14 @@
 // every block it writes is a valid LZ4 block: the stock reference decodes the blobs (tests/test_gpu_stage2_device.py),
 // and the decompressor below accepts whatever liblz4 wrote.
 //
-//  compress    one warp per chunk. 32 consecutive positions per step: every lane hashes the 4 bytes at its position, reads
-//              the candidate the table holds and verifies it by content; the first verified lane (ballot) becomes the match,
-//              which the warp extends 32 bytes per ballot; literals and the sequence header leave cooperatively. Greedy,
-//              4096-entry table of 16-bit positions in shared memory (candidates are rebuilt modulo 64 KB and always
-//              checked by content, so stale or uninitialised entries are harmless).
+//  compress    one warp per chunk. 128 consecutive positions per step (4 per lane, all of a step's loads in flight together):
+//              every lane hashes the 4 bytes at its positions, reads the candidates the table holds and verifies them by
+//              content over EIGHT bytes; the first verified position (ballots) becomes the match, which the warp extends 32
+//              bytes per ballot; literals leave as aligned 16-byte stores. Greedy, 4096-entry table of 16-bit positions in
+//              shared memory (candidates are rebuilt modulo 64 KB and always checked by content, so stale or uninitialised
+//              entries are harmless). Why 8 bytes: on varint streams 4-byte repeats are everywhere and each saves about
+//              one byte, while a sequence costs the warp a chain of dependent global round trips -- the round-1 coder
+//              (4-byte matches, 32 positions per step) spent 9.8 ms per 64 frames to gain 2.5 %.
 //  decompress  one warp per chunk: the (cheap, serial) sequence headers are parsed by all lanes in lock step, literal and
 //              match bytes move cooperatively (overlapping matches with offset < 32 by the closed form k mod offset).
 //  pack        one CTA per frame: exclusive scan of the chunk sizes, then [u32 size][bytes] back to back behind the header.
@@ -25,6 +28,11 @@ namespace cldn {
 constexpr int kLzThreads = 128;          // 4 warps = 4 chunks per CTA
 constexpr int kLzWarps = kLzThreads / 32;
 constexpr uint32_t kLzHashBits = 12;
+constexpr int kLzR = 4;                  // positions per lane and step of the compressor
+#ifndef CLDN_LZ4_MIN_MATCH
+#define CLDN_LZ4_MIN_MATCH 8
+#endif
+constexpr int kLzMinMatch = CLDN_LZ4_MIN_MATCH;   // 4 (the format's minimum) .. 8: shortest match the compressor takes
 
 __device__ __forceinline__ uint32_t lz_load32(const uint8_t* p) {  // any alignment
   const uintptr_t a = reinterpret_cast<uintptr_t>(p);
@@ -32,6 +40,41 @@ __device__ __forceinline__ uint32_t lz_load32(const uint8_t* p) {  // any alignm
   const uint32_t sh = static_cast<uint32_t>(a & 3u) * 8u;
   if (sh == 0) return w[0];
   return __funnelshift_r(w[0], w[1], sh);
+}
+__device__ __forceinline__ uint2 lz_load64(const uint8_t* p) {  // any alignment; reads the aligned words covering [p, p + 8)
+  const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~uintptr_t(3));
+  const uint32_t sh = static_cast<uint32_t>(a & 3u) * 8u;
+  const uint32_t w0 = w[0], w1 = w[1];
+  if (sh == 0) return make_uint2(w0, w1);
+  const uint32_t w2 = w[2];
+  return make_uint2(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh));
+}
+// n bytes from src to dst by `nt` threads (this one is `tid`): 16-byte stores for the aligned body of dst, the (unaligned)
+// source through aligned words + funnel shifts. Reads the aligned words covering [src, src + n) only.
+__device__ __forceinline__ void lz_copy(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, uint32_t n, uint32_t tid, uint32_t nt) {
+  uint32_t head = (16u - static_cast<uint32_t>(reinterpret_cast<uintptr_t>(dst) & 15u)) & 15u;
+  if (head > n) head = n;
+  for (uint32_t k = tid; k < head; k += nt) dst[k] = src[k];
+  const uint32_t nv = (n - head) >> 4;
+  const uint8_t* s0 = src + head;
+  const uint32_t a = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(s0) & 3u);
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(s0 - a);
+  uint4* dv = reinterpret_cast<uint4*>(dst + head);
+  if (a == 0u) {
+    for (uint32_t v = tid; v < nv; v += nt) {
+      const uint32_t* q = w + 4u * v;
+      dv[v] = make_uint4(q[0], q[1], q[2], q[3]);
+    }
+  } else {
+    const uint32_t sh = a * 8u;
+    for (uint32_t v = tid; v < nv; v += nt) {
+      const uint32_t* q = w + 4u * v;
+      const uint32_t w0 = q[0], w1 = q[1], w2 = q[2], w3 = q[3], w4 = q[4];
+      dv[v] = make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh));
+    }
+  }
+  for (uint32_t k = head + (nv << 4) + tid; k < n; k += nt) dst[k] = src[k];
 }
 __device__ __forceinline__ uint32_t lz_hash(uint32_t v) { return (v * 2654435761u) >> (32u - kLzHashBits); }
 
@@ -53,24 +96,53 @@ __device__ uint32_t lz4_compress_warp(const uint8_t* __restrict__ src, uint32_t 
   const uint32_t matchlimit = n > 5u ? n - 5u : 0u;
   // the aligned word pairs lz_load32 reads must stay inside [src & ~3, src + n + 3]: positions < mflimit read <= n - 9
   while (ip < mflimit) {
-    const uint32_t p = ip + lane;
-    const bool ok = p < mflimit;
-    const uint32_t v = ok ? lz_load32(src + p) : 0u;
-    const uint32_t h = lz_hash(v);
-    const uint32_t stored = table[h];
+    // ---- kLzR * 32 positions: position ip + 32 r + lane is lane's r-th; every load of the step is issued before the first use ----
+    uint2 v[kLzR];
+    uint32_t stored[kLzR];
+    bool ok[kLzR];
+#pragma unroll
+    for (int r = 0; r < kLzR; ++r) {
+      const uint32_t p = ip + 32u * r + lane;
+      ok[r] = p < mflimit;
+      v[r] = ok[r] ? lz_load64(src + p) : make_uint2(0u, 0u);
+    }
+#pragma unroll
+    for (int r = 0; r < kLzR; ++r) stored[r] = table[lz_hash(v[r].x)];
     __syncwarp();
-    if (ok) table[h] = static_cast<uint16_t>(p);
+#pragma unroll
+    for (int r = 0; r < kLzR; ++r) {
+      if (ok[r]) table[lz_hash(v[r].x)] = static_cast<uint16_t>(ip + 32u * r + lane);
+    }
     __syncwarp();
-    const uint32_t d = (p - stored) & 0xFFFFu;
-    const uint32_t cand = p - d;
-    const bool valid = ok && d != 0u && d <= p && lz_load32(src + cand) == v;
-    const uint32_t mask = __ballot_sync(0xffffffffu, valid);
-    if (mask == 0u) { ip += 32u; continue; }
-    const int first = __ffs(static_cast<int>(mask)) - 1;
-    const uint32_t mp = ip + static_cast<uint32_t>(first);
-    const uint32_t ref = __shfl_sync(0xffffffffu, cand, first);
-    uint32_t len = 4u;
-    while (true) {  // 32 more bytes per round
+    uint32_t cand[kLzR];
+    uint2 cv[kLzR];
+    bool maybe[kLzR];
+#pragma unroll
+    for (int r = 0; r < kLzR; ++r) {
+      const uint32_t p = ip + 32u * r + lane;
+      const uint32_t d = (p - stored[r]) & 0xFFFFu;
+      cand[r] = p - d;
+      maybe[r] = ok[r] && d != 0u && d <= p;
+      cv[r] = maybe[r] ? lz_load64(src + cand[r]) : make_uint2(0u, 0u);
+    }
+    uint32_t mp = 0xFFFFFFFFu, ref = 0, len = 0;
+#pragma unroll
+    for (int r = 0; r < kLzR; ++r) {
+      // equal leading bytes among the eight in registers (8 = all of them: the match may go on)
+      const uint32_t dx = cv[r].x ^ v[r].x, dy = cv[r].y ^ v[r].y;
+      const uint32_t common = dx ? static_cast<uint32_t>(__ffs(static_cast<int>(dx)) - 1) >> 3 : 4u + (dy ? static_cast<uint32_t>(__ffs(static_cast<int>(dy)) - 1) >> 3 : 4u);
+      const bool valid = maybe[r] && common >= static_cast<uint32_t>(kLzMinMatch);
+      const uint32_t mask = __ballot_sync(0xffffffffu, valid);
+      if (mp == 0xFFFFFFFFu && mask != 0u) {
+        const int first = __ffs(static_cast<int>(mask)) - 1;
+        mp = ip + 32u * r + static_cast<uint32_t>(first);
+        ref = __shfl_sync(0xffffffffu, cand[r], first);
+        len = __shfl_sync(0xffffffffu, common, first);
+      }
+    }
+    if (mp == 0xFFFFFFFFu) { ip += 32u * kLzR; continue; }
+    // (mp < mflimit = n - 12: the eight compared bytes end in front of the last five, which must stay literals)
+    while (len >= 8u) {  // the match may go on: 32 more bytes per round
       const uint32_t q = mp + len + lane;
       const bool eq = q < matchlimit && src[q] == src[ref + len + lane];
       const uint32_t ne = __ballot_sync(0xffffffffu, !eq);
@@ -83,7 +155,7 @@ __device__ uint32_t lz4_compress_warp(const uint8_t* __restrict__ src, uint32_t 
     if (lane == 0) dst[op] = static_cast<uint8_t>((lit >= 15u ? 15u : lit) << 4 | (ml >= 15u ? 15u : ml));
     op += 1u;
     if (lit >= 15u) { lz_write_ext(dst + op, lit, lane); op += lz_ext_bytes(lit); }
-    for (uint32_t k = lane; k < lit; k += 32u) dst[op + k] = src[anchor + k];
+    lz_copy(dst + op, src + anchor, lit, lane, 32u);
     op += lit;
     if (lane == 0) { dst[op] = static_cast<uint8_t>(mp - ref); dst[op + 1] = static_cast<uint8_t>((mp - ref) >> 8); }
     op += 2u;
@@ -96,7 +168,7 @@ __device__ uint32_t lz4_compress_warp(const uint8_t* __restrict__ src, uint32_t 
   if (lane == 0) dst[op] = static_cast<uint8_t>((lit >= 15u ? 15u : lit) << 4);
   op += 1u;
   if (lit >= 15u) { lz_write_ext(dst + op, lit, lane); op += lz_ext_bytes(lit); }
-  for (uint32_t k = lane; k < lit; k += 32u) dst[op + k] = src[anchor + k];
+  lz_copy(dst + op, src + anchor, lit, lane, 32u);
   op += lit;
   __syncwarp();
   return op;
@@ -120,7 +192,7 @@ __device__ uint32_t lz4_decompress_warp(const uint8_t* __restrict__ src, uint32_
       } while (b == 255u);
     }
     if (lit > n - ip || lit > cap - op) return 0xFFFFFFFFu;
-    for (uint32_t k = lane; k < lit; k += 32u) dst[op + k] = src[ip + k];
+    lz_copy(dst + op, src + ip, lit, lane, 32u);
     ip += lit;
     op += lit;
     if (ip >= n) break;  // a block ends with literals
@@ -226,7 +298,7 @@ __global__ void __launch_bounds__(256) lz4_pack_frames_kernel(const Lz4Launch L,
     const uint8_t* src = L.scratch + static_cast<size_t>(gc) * L.slot_stride;
     if (pos + 4ull + sz > cap) { fits = false; break; }
     if (threadIdx.x == 0) store_u32(dst + pos, sz);
-    for (uint32_t k = threadIdx.x; k < sz; k += blockDim.x) dst[pos + 4u + k] = src[k];
+    lz_copy(dst + pos + 4u, src, sz, threadIdx.x, blockDim.x);
     pos += 4ull + sz;
   }
   if (threadIdx.x == 0) {
