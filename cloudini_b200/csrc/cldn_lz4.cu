@@ -10,9 +10,10 @@
 //  compress    one warp per chunk. 128 consecutive positions per step (4 per lane, all of a step's loads in flight together):
 //              every lane hashes the 4 bytes at its positions, reads the candidates the table holds and verifies them by
 //              content over EIGHT bytes; the first verified position (ballots) becomes the match, which the warp extends 32
-//              bytes per ballot; literals leave as aligned 16-byte stores. Greedy, 4096-entry table of 16-bit positions in
-//              shared memory (candidates are rebuilt modulo 64 KB and always checked by content, so stale or uninitialised
-//              entries are harmless). Why 8 bytes: on varint streams 4-byte repeats are everywhere and each saves about
+//              bytes per ballot; literals leave as aligned 16-byte stores. Greedy, 2048-entry table in shared memory: 16-bit
+//              position (candidates are rebuilt modulo 64 KB) + 16-bit tag of the hashed value, so that only candidates that
+//              very likely hold the same four bytes are fetched; always checked by content (stale or uninitialised entries
+//              are harmless). Why 8 bytes: on varint streams 4-byte repeats are everywhere and each saves about
 //              one byte, while a sequence costs the warp a chain of dependent global round trips -- the round-1 coder
 //              (4-byte matches, 32 positions per step) spent 9.8 ms per 64 frames to gain 2.5 %.
 //  decompress  one warp per chunk: the (cheap, serial) sequence headers are parsed by all lanes in lock step, literal and
@@ -27,7 +28,7 @@ namespace cldn {
 
 constexpr int kLzThreads = 128;          // 4 warps = 4 chunks per CTA
 constexpr int kLzWarps = kLzThreads / 32;
-constexpr uint32_t kLzHashBits = 12;
+constexpr uint32_t kLzHashBits = 11;    // 2048 entries of (16-bit tag << 16 | 16-bit position) per warp = 8 KB
 constexpr int kLzR = 4;                  // positions per lane and step of the compressor
 #ifndef CLDN_LZ4_MIN_MATCH
 #define CLDN_LZ4_MIN_MATCH 8
@@ -76,7 +77,9 @@ __device__ __forceinline__ void lz_copy(uint8_t* __restrict__ dst, const uint8_t
   }
   for (uint32_t k = head + (nv << 4) + tid; k < n; k += nt) dst[k] = src[k];
 }
-__device__ __forceinline__ uint32_t lz_hash(uint32_t v) { return (v * 2654435761u) >> (32u - kLzHashBits); }
+__device__ __forceinline__ uint32_t lz_mix(uint32_t v) { return v * 2654435761u; }
+__device__ __forceinline__ uint32_t lz_slot(uint32_t m) { return m >> (32u - kLzHashBits); }           // top bits: the table slot
+__device__ __forceinline__ uint32_t lz_tag(uint32_t m) { return (m << kLzHashBits) & 0xFFFF0000u; }   // the 16 bits below them, moved to the entry's top half
 
 // Length field of a sequence: nibble value 15 is followed by bytes of 255 and a last byte < 255 (uniform over the warp).
 __device__ __forceinline__ uint32_t lz_ext_bytes(uint32_t len) { return len >= 15u ? (len - 15u) / 255u + 1u : 0u; }
@@ -88,7 +91,7 @@ __device__ __forceinline__ void lz_write_ext(uint8_t* dst, uint32_t len, uint32_
 
 // One full warp. Returns the compressed size, 0 if `cap` is too small.
 __device__ uint32_t lz4_compress_warp(const uint8_t* __restrict__ src, uint32_t n, uint8_t* __restrict__ dst, uint32_t cap,
-                                      uint16_t* table) {
+                                      uint32_t* table) {
   const uint32_t lane = threadIdx.x & 31u;
   uint32_t ip = 0, anchor = 0, op = 0;
   // LZ4 block rules: the last match starts at least 12 bytes before the end, the last 5 bytes are literals
@@ -106,12 +109,16 @@ __device__ uint32_t lz4_compress_warp(const uint8_t* __restrict__ src, uint32_t 
       ok[r] = p < mflimit;
       v[r] = ok[r] ? lz_load64(src + p) : make_uint2(0u, 0u);
     }
+    uint32_t mix[kLzR];
 #pragma unroll
-    for (int r = 0; r < kLzR; ++r) stored[r] = table[lz_hash(v[r].x)];
+    for (int r = 0; r < kLzR; ++r) {
+      mix[r] = lz_mix(v[r].x);
+      stored[r] = table[lz_slot(mix[r])];
+    }
     __syncwarp();
 #pragma unroll
     for (int r = 0; r < kLzR; ++r) {
-      if (ok[r]) table[lz_hash(v[r].x)] = static_cast<uint16_t>(ip + 32u * r + lane);
+      if (ok[r]) table[lz_slot(mix[r])] = lz_tag(mix[r]) | ((ip + 32u * r + lane) & 0xFFFFu);
     }
     __syncwarp();
     uint32_t cand[kLzR];
@@ -122,7 +129,9 @@ __device__ uint32_t lz4_compress_warp(const uint8_t* __restrict__ src, uint32_t 
       const uint32_t p = ip + 32u * r + lane;
       const uint32_t d = (p - stored[r]) & 0xFFFFu;
       cand[r] = p - d;
-      maybe[r] = ok[r] && d != 0u && d <= p;
+      // the entry's tag: 16 more bits of the hash. Without it nearly every position verified a stale candidate -- 128 scattered
+      // sectors from L2 per 128 bytes of input, which is what the round-1 coder's time went into
+      maybe[r] = ok[r] && d != 0u && d <= p && (stored[r] & 0xFFFF0000u) == lz_tag(mix[r]);
       cv[r] = maybe[r] ? lz_load64(src + cand[r]) : make_uint2(0u, 0u);
     }
     uint32_t mp = 0xFFFFFFFFu, ref = 0, len = 0;
@@ -244,7 +253,7 @@ __device__ __forceinline__ uint32_t lz_find_chunk(const uint8_t* payload, uint64
 
 // grid: ceil(n_chunks_total / 4) CTAs of 4 warps; warp -> (frame, chunk) through chunk_frame[]
 __global__ void __launch_bounds__(kLzThreads) lz4_compress_chunks_kernel(const Lz4Launch L) {
-  __shared__ uint16_t s_table[kLzWarps][1u << kLzHashBits];
+  __shared__ uint32_t s_table[kLzWarps][1u << kLzHashBits];
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
   const uint32_t gc = blockIdx.x * kLzWarps + warp;
   if (gc >= L.n_chunks_total) return;
