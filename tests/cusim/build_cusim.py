@@ -37,6 +37,7 @@ PTX = {
     # bmsk.clamp.b32 d, a, b: b bits set starting at bit a (both clamped to 32)
     "bmsk.clamp.b32": lambda outs, ins: f"{outs[0]} = ::cusim::bmsk_clamp({ins[0]}, {ins[1]});",
     "prefetch.global.L2": lambda outs, ins: "((void)0);",
+    "prefetch.global.L1": lambda outs, ins: "((void)0);",
     # cp.async: the kernels compile these only without CLDN_CUSIM (the emulation copies synchronously); still rewritten
     "cp.async.cg.shared.global": lambda outs, ins: "((void)0);",
     "cp.async.ca.shared.global": lambda outs, ins: "((void)0);",
