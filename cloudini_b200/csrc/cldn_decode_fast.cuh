@@ -462,6 +462,11 @@ __global__ void __launch_bounds__(kFT, CLDN_FAST_DEC_MINB) decode_floatn_fast_ke
               hi = nx;
               nx = win32[wi + 2u];
             }
+            // (nine instructions per value as compiled: compare, address, three moves, increment, predicated load, two copies.
+            // Two shorter forms were measured at the end of round 2 -- selects, which the compiler turns into compare + select +
+            // a predicated load of `hi` (5 instructions), and a mask from wi - wn with two LOP3 and an unconditional load (6):
+            // both 1.063 against 1.034 ms per 128 frames. Fewer instructions, slower: the kernel is not bound by issue slots
+            // alone at this point of the loop)
 #endif
             x = x - ((x >> 1) & 0x3F803F80u);                                  // 7-bit groups -> 14-bit groups
             const uint32_t z = bitselect(0x3FFFu, x, x >> 2);                  // -> uval = zigzag + 1 (28 bits)
