@@ -50,6 +50,15 @@ def _cases():
     info, cloud = synth.cloud_c4_mixed_frame(3)                                                      # Velodyne XYZIRT, step 22
     yield "xyzirt", info, [cloud, synth.cloud_c4_mixed_frame(4)[1]]
     yield "tiny", synth.info_xyzi(3), [synth.cloud_c2(3, seed=1)[1]]                                 # blocks below the 13-byte minimum
+    # a sweep that repeats every 977 points: the stage-1 bytes repeat at a distance of a few KB, so matches span many of the
+    # compressor's 128-position steps and run into the end of every chunk (last-match / last-literals rules of the block format);
+    # the second cloud stops 5 points into its third chunk (a block of a few bytes behind two full ones)
+    rng = np.random.default_rng(77)
+    base = np.cumsum(rng.normal(0, 0.02, (977, 4)), axis=0).astype(np.float32)
+    per = np.tile(base, (n // 977 + 1, 1))[:n]
+    yield "periodic", synth.info_xyzi(n), [np.ascontiguousarray(per).view(np.uint8).reshape(-1)]
+    m = 2 * 32768 + 5
+    yield "periodic-ragged", synth.info_xyzi(m), [np.ascontiguousarray(np.tile(base, (m // 977 + 1, 1))[:m]).view(np.uint8).reshape(-1)]
 
 
 @pytest.mark.parametrize("case", list(_cases()), ids=lambda c: c[0])
